@@ -1,0 +1,408 @@
+// Fused segmentation loss / metric kernels and the fused clip + Adam step.
+// Reference behaviour: deadtrees/loss/losses.py:124-141 (class2one_hot), :226-247 (DiceLoss),
+// :273-291 (FocalLoss); deadtrees/loss/gdl.py:10-27 (GeneralizedDiceLoss); smp Fscore as used at
+// deadtrees/network/segmodel.py:145-149,202-208; calculate_loss at segmodel.py:169-200; Adam at :420-425.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int KMAX = 4;
+constexpr float kEps = 1e-10f;
+
+template <int K>
+__device__ __forceinline__ void softmax_px(const float* __restrict__ z, int64_t plane, float (&p)[K]) {
+  float m = z[0];
+#pragma unroll
+  for (int k = 1; k < K; ++k) m = fmaxf(m, z[k * plane]);
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < K; ++k) { p[k] = expf(z[k * plane] - m); s += p[k]; }
+#pragma unroll
+  for (int k = 0; k < K; ++k) p[k] = p[k] / s;
+}
+
+// grid = (chunks, N).  sums[n][k][4], counts[k][3].
+template <int K>
+__global__ void loss_partials_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels, int64_t HW,
+                                     double* __restrict__ sums, unsigned long long* __restrict__ counts,
+                                     int* __restrict__ bad_label) {
+  const int n = blockIdx.y;
+  const float* zl = logits + static_cast<int64_t>(n) * K * HW;
+  const int64_t* ll = labels + static_cast<int64_t>(n) * HW;
+  float s_pt[K], s_p[K], s_t[K], s_f[K];
+  unsigned c_tp[K], c_pr[K], c_gt[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) { s_pt[k] = s_p[k] = s_t[k] = s_f[k] = 0.f; c_tp[k] = c_pr[k] = c_gt[k] = 0u; }
+  bool bad = false;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < HW;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float p[K];
+    softmax_px<K>(zl + i, HW, p);
+    const int64_t lab = ll[i];
+    if (lab < 0 || lab >= K) bad = true;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const bool t = (lab == k);
+      const bool pr = p[k] > 0.5f;
+      s_p[k] += p[k];
+      if (t) {
+        s_pt[k] += p[k];
+        s_t[k] += 1.f;
+        const float q = 1.f - p[k];
+        s_f[k] += q * q * logf(p[k] + kEps);
+      }
+      c_pr[k] += pr;
+      c_gt[k] += t;
+      c_tp[k] += (pr && t);
+    }
+  }
+  if (bad) atomicOr(bad_label, 1);
+  __shared__ double sh[kThreads / 32][K][4];
+  __shared__ unsigned shc[kThreads / 32][K][3];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const double a = warp_sum(static_cast<double>(s_pt[k])), b = warp_sum(static_cast<double>(s_p[k]));
+    const double c = warp_sum(static_cast<double>(s_t[k])), d = warp_sum(static_cast<double>(s_f[k]));
+    const unsigned e = warp_sum(c_tp[k]), f = warp_sum(c_pr[k]), g = warp_sum(c_gt[k]);
+    if (lane == 0) {
+      sh[warp][k][0] = a; sh[warp][k][1] = b; sh[warp][k][2] = c; sh[warp][k][3] = d;
+      shc[warp][k][0] = e; shc[warp][k][1] = f; shc[warp][k][2] = g;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < K * 4) {
+    const int k = threadIdx.x / 4, j = threadIdx.x % 4;
+    double t = 0;
+    for (int w = 0; w < kThreads / 32; ++w) t += sh[w][k][j];
+    atomicAdd(&sums[(static_cast<int64_t>(n) * K + k) * 4 + j], t);
+  } else if (threadIdx.x >= 32 && threadIdx.x < 32 + K * 3) {
+    const int k = (threadIdx.x - 32) / 3, j = (threadIdx.x - 32) % 3;
+    unsigned long long t = 0;
+    for (int w = 0; w < kThreads / 32; ++w) t += shc[w][k][j];
+    atomicAdd(&counts[k * 3 + j], t);
+  }
+}
+
+// single block; thread-per-(n,k) work is tiny
+__global__ void loss_finalize_kernel(const double* __restrict__ sums, const long long* __restrict__ counts, int N,
+                                     int K, int dice_mode, int use_focal, float* __restrict__ out,
+                                     float* __restrict__ coef, float* __restrict__ focal_scale) {
+  if (threadIdx.x != 0) return;
+  float dice = 0.f, focal = 0.f;
+  for (int i = 0; i < N * K * 2; ++i) coef[i] = 0.f;
+  if (dice_mode == 1) {
+    // DiceLoss over foreground classes: mean_{b,c}(1 - (2I + eps) / (U + eps))
+    const int cnt = N * (K - 1);
+    float acc = 0.f;
+    for (int n = 0; n < N; ++n)
+      for (int k = 1; k < K; ++k) {
+        const double* s = sums + (static_cast<int64_t>(n) * K + k) * 4;
+        const float I = static_cast<float>(s[0]), U = static_cast<float>(s[1]) + static_cast<float>(s[2]);
+        acc += 1.f - (2.f * I + kEps) / (U + kEps);
+        coef[(n * K + k) * 2 + 0] = -2.f / (U + kEps) / cnt;
+        coef[(n * K + k) * 2 + 1] = (2.f * I + kEps) / ((U + kEps) * (U + kEps)) / cnt;
+      }
+    dice = cnt > 0 ? acc / cnt : 0.f;
+  } else if (dice_mode == 2) {
+    // GeneralizedDiceLoss: batch-global class weights 1 / (count^2 + 1e-9)
+    float num = 0.f, den = 0.f, wk[KMAX];
+    for (int k = 0; k < K; ++k) {
+      double pt = 0, ps = 0, ts = 0;
+      for (int n = 0; n < N; ++n) {
+        const double* s = sums + (static_cast<int64_t>(n) * K + k) * 4;
+        pt += s[0]; ps += s[1]; ts += s[2];
+      }
+      const long long cnt = static_cast<long long>(ts + 0.5);
+      wk[k] = 1.0f / (static_cast<float>(cnt * cnt) + 1e-9f);
+      num += wk[k] * static_cast<float>(pt);
+      den += wk[k] * static_cast<float>(ts + ps);
+    }
+    dice = 1.f - 2.f * (num + 1e-9f) / (den + 1e-9f);
+    for (int n = 0; n < N; ++n)
+      for (int k = 0; k < K; ++k) {
+        coef[(n * K + k) * 2 + 0] = -2.f * wk[k] / (den + 1e-9f);
+        coef[(n * K + k) * 2 + 1] = 2.f * (num + 1e-9f) * wk[k] / ((den + 1e-9f) * (den + 1e-9f));
+      }
+  }
+  float fs = 0.f;
+  if (use_focal) {
+    double f = 0, t = 0;
+    for (int i = 0; i < N * K; ++i) { f += sums[i * 4 + 3]; t += sums[i * 4 + 2]; }
+    fs = 1.f / (static_cast<float>(t) + kEps);
+    focal = -static_cast<float>(f) * fs;
+  }
+  *focal_scale = fs;
+  // smp Fscore (beta 1, eps 1e-7, threshold 0.5), micro-averaged over the kept channels
+  float fscore[2];
+  for (int with_bg = 0; with_bg < 2; ++with_bg) {
+    long long tp = 0, pr = 0, gt = 0;
+    for (int k = with_bg ? 0 : 1; k < K; ++k) { tp += counts[k * 3]; pr += counts[k * 3 + 1]; gt += counts[k * 3 + 2]; }
+    const float ftp = static_cast<float>(tp), ffp = static_cast<float>(pr - tp), ffn = static_cast<float>(gt - tp);
+    fscore[with_bg] = (2.f * ftp + 1e-7f) / (2.f * ftp + ffn + ffp + 1e-7f);
+  }
+  out[0] = dice; out[1] = focal; out[2] = dice + focal; out[3] = fscore[0]; out[4] = fscore[1];
+  out[5] = out[6] = out[7] = 0.f;
+}
+
+template <int K>
+__global__ void loss_backward_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels, int64_t HW,
+                                     const float* __restrict__ coef, const float* __restrict__ focal_scale,
+                                     float upstream, float* __restrict__ grad) {
+  const int n = blockIdx.y;
+  const float* zl = logits + static_cast<int64_t>(n) * K * HW;
+  const int64_t* ll = labels + static_cast<int64_t>(n) * HW;
+  float* gl = grad + static_cast<int64_t>(n) * K * HW;
+  float a[K], b[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) { a[k] = coef[(n * K + k) * 2]; b[k] = coef[(n * K + k) * 2 + 1]; }
+  const float fs = *focal_scale;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < HW;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float p[K], g[K];
+    softmax_px<K>(zl + i, HW, p);
+    const int64_t lab = ll[i];
+    float dot = 0.f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      g[k] = b[k];
+      if (lab == k) {
+        const float q = 1.f - p[k], pe = p[k] + kEps;
+        g[k] += a[k] - fs * (-2.f * q * logf(pe) + q * q / pe);
+      }
+      dot += g[k] * p[k];
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) gl[k * HW + i] = upstream * p[k] * (g[k] - dot);
+  }
+}
+
+// ---- probability / one-hot API (the reference's loss callables take softmax output + one-hot) ----
+
+__global__ void one_hot_kernel(const int64_t* __restrict__ labels, int K, int64_t HW, int64_t total,
+                               int32_t* __restrict__ out, int* __restrict__ bad_label) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t n = i / HW, px = i % HW;
+    const int64_t lab = labels[i];
+    if (lab < 0 || lab >= K) atomicOr(bad_label, 1);
+    for (int k = 0; k < K; ++k) out[(n * K + k) * HW + px] = (lab == k) ? 1 : 0;
+  }
+}
+
+__global__ void softmax_nchw_kernel(const float* __restrict__ z, int K, int64_t HW, int64_t total,
+                                    float* __restrict__ p) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t n = i / HW, px = i % HW;
+    const float* zp = z + n * K * HW + px;
+    float* pp = p + n * K * HW + px;
+    float m = zp[0];
+    for (int k = 1; k < K; ++k) m = fmaxf(m, zp[k * HW]);
+    float s = 0.f;
+    for (int k = 0; k < K; ++k) s += expf(zp[k * HW] - m);
+    for (int k = 0; k < K; ++k) pp[k * HW] = expf(zp[k * HW] - m) / s;
+  }
+}
+
+// grid = (chunks, N*K): one (n, k) plane per blockIdx.y.  sums[n][k][4] as in loss_partials_kernel,
+// with the focal exponent gamma and a target that is either int32 one-hot or a float map.
+template <typename TT>
+__global__ void prob_partials_kernel(const float* __restrict__ probs, const TT* __restrict__ target, int64_t HW,
+                                     float gamma, double* __restrict__ sums) {
+  const int64_t plane = blockIdx.y;
+  const float* pp = probs + plane * HW;
+  const TT* tp = target + plane * HW;
+  float s_pt = 0.f, s_p = 0.f, s_t = 0.f, s_f = 0.f;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < HW;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float p = pp[i], t = static_cast<float>(tp[i]);
+    s_pt += p * t;
+    s_p += p;
+    s_t += t;
+    if (t != 0.f) {
+      const float q = 1.f - p;
+      const float w = gamma == 2.f ? q * q : powf(q, gamma);
+      s_f += w * t * logf(p + kEps);
+    }
+  }
+  __shared__ double sh[kThreads / 32][4];
+  const double a = warp_sum(static_cast<double>(s_pt)), b = warp_sum(static_cast<double>(s_p));
+  const double c = warp_sum(static_cast<double>(s_t)), d = warp_sum(static_cast<double>(s_f));
+  if ((threadIdx.x & 31) == 0) {
+    double* r = sh[threadIdx.x >> 5];
+    r[0] = a; r[1] = b; r[2] = c; r[3] = d;
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double t = 0;
+    for (int w = 0; w < kThreads / 32; ++w) t += sh[w][threadIdx.x];
+    atomicAdd(&sums[plane * 4 + threadIdx.x], t);
+  }
+}
+
+__global__ void sumsq_kernel(const float* __restrict__ g, int64_t n, double* __restrict__ out) {
+  float acc = 0.f;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    acc = fmaf(g[i], g[i], acc);
+  double d = warp_sum(static_cast<double>(acc));
+  __shared__ double sh[kThreads / 32];
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = d;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0;
+    for (int w = 0; w < kThreads / 32; ++w) t += sh[w];
+    atomicAdd(out, t);
+  }
+}
+
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps, float bc1,
+                            float bc2_sqrt, const double* __restrict__ sumsq, float max_norm) {
+  float clip = 1.f;
+  if (max_norm > 0.f) {
+    const float norm = static_cast<float>(sqrt(*sumsq));
+    clip = fminf(1.f, max_norm / (norm + 1e-6f));
+  }
+  const float step_size = lr / bc1;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float gi = g[i] * clip;
+    const float mi = m[i] + (1.f - b1) * (gi - m[i]);            // torch: exp_avg.lerp_(grad, 1 - beta1)
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;           // exp_avg_sq.mul_(b2).addcmul_(g, g, 1 - b2)
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] -= step_size * (mi / denom);
+  }
+}
+
+inline int grid_for(int64_t work) {
+  int64_t blocks = (work + kThreads - 1) / kThreads;
+  const int64_t cap = static_cast<int64_t>(dt_num_sms()) * 8;
+  return static_cast<int>(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
+}
+
+}  // namespace
+
+extern "C" {
+
+int dt_seg_loss_partials(const float* logits, const int64_t* labels, int N, int K, int H, int W, double* sums,
+                         int64_t* counts, int32_t* bad_label, dt_stream_t stream) {
+  DT_ARCH_GUARD();
+  DT_REQUIRE(N > 0 && N <= 65535 && H > 0 && W > 0, DT_ERR_BAD_SHAPE, "dt_seg_loss_partials: bad shape");
+  DT_REQUIRE(K >= 2 && K <= KMAX, DT_ERR_BAD_SHAPE, "dt_seg_loss_partials: K=%d (2..4)", K);
+  const int64_t HW = static_cast<int64_t>(H) * W;
+  int chunks = static_cast<int>((HW + kThreads * 8 - 1) / (kThreads * 8));
+  const int cap = (dt_num_sms() * 8 + N - 1) / N;
+  if (chunks > cap) chunks = cap;
+  if (chunks < 1) chunks = 1;
+  dim3 grid(chunks, N);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  unsigned long long* c = reinterpret_cast<unsigned long long*>(counts);
+  switch (K) {
+    case 2: loss_partials_kernel<2><<<grid, kThreads, 0, s>>>(logits, labels, HW, sums, c, bad_label); break;
+    case 3: loss_partials_kernel<3><<<grid, kThreads, 0, s>>>(logits, labels, HW, sums, c, bad_label); break;
+    default: loss_partials_kernel<4><<<grid, kThreads, 0, s>>>(logits, labels, HW, sums, c, bad_label); break;
+  }
+  DT_LAUNCH_CHECK();
+  return DT_OK;
+}
+
+int dt_seg_loss_finalize(const double* sums, const int64_t* counts, int N, int K, int dice_mode, int use_focal,
+                         float* out, float* coef, float* focal_scale, dt_stream_t stream) {
+  DT_ARCH_GUARD();
+  DT_REQUIRE(N > 0 && K >= 2 && K <= KMAX && dice_mode >= 0 && dice_mode <= 2, DT_ERR_BAD_SHAPE,
+             "dt_seg_loss_finalize: bad arguments");
+  loss_finalize_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      sums, reinterpret_cast<const long long*>(counts), N, K, dice_mode, use_focal, out, coef, focal_scale);
+  DT_LAUNCH_CHECK();
+  return DT_OK;
+}
+
+int dt_seg_loss_backward(const float* logits, const int64_t* labels, int N, int K, int H, int W, const float* coef,
+                         const float* focal_scale, float upstream, float* grad_logits, dt_stream_t stream) {
+  DT_ARCH_GUARD();
+  DT_REQUIRE(N > 0 && N <= 65535 && H > 0 && W > 0 && K >= 2 && K <= KMAX, DT_ERR_BAD_SHAPE,
+             "dt_seg_loss_backward: bad shape");
+  const int64_t HW = static_cast<int64_t>(H) * W;
+  int chunks = static_cast<int>((HW + kThreads * 4 - 1) / (kThreads * 4));
+  if (chunks < 1) chunks = 1;
+  dim3 grid(chunks, N);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (K) {
+    case 2: loss_backward_kernel<2><<<grid, kThreads, 0, s>>>(logits, labels, HW, coef, focal_scale, upstream, grad_logits); break;
+    case 3: loss_backward_kernel<3><<<grid, kThreads, 0, s>>>(logits, labels, HW, coef, focal_scale, upstream, grad_logits); break;
+    default: loss_backward_kernel<4><<<grid, kThreads, 0, s>>>(logits, labels, HW, coef, focal_scale, upstream, grad_logits); break;
+  }
+  DT_LAUNCH_CHECK();
+  return DT_OK;
+}
+
+int dt_class2one_hot(const int64_t* labels, int N, int K, int H, int W, int32_t* onehot, int32_t* bad_label,
+                     dt_stream_t stream) {
+  DT_ARCH_GUARD();
+  DT_REQUIRE(N > 0 && K > 0 && H > 0 && W > 0, DT_ERR_BAD_SHAPE, "dt_class2one_hot: bad shape");
+  const int64_t HW = static_cast<int64_t>(H) * W, total = HW * N;
+  one_hot_kernel<<<grid_for(total), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(labels, K, HW, total, onehot,
+                                                                                     bad_label);
+  DT_LAUNCH_CHECK();
+  return DT_OK;
+}
+
+int dt_softmax_nchw(const float* logits, int N, int K, int H, int W, float* probs, dt_stream_t stream) {
+  DT_ARCH_GUARD();
+  DT_REQUIRE(N > 0 && K > 0 && H > 0 && W > 0, DT_ERR_BAD_SHAPE, "dt_softmax_nchw: bad shape");
+  const int64_t HW = static_cast<int64_t>(H) * W, total = HW * N;
+  softmax_nchw_kernel<<<grid_for(total), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(logits, K, HW, total, probs);
+  DT_LAUNCH_CHECK();
+  return DT_OK;
+}
+
+int dt_prob_loss_partials(const float* probs, const void* target, int target_is_float, int N, int K, int H, int W,
+                          float gamma, double* sums, dt_stream_t stream) {
+  DT_ARCH_GUARD();
+  DT_REQUIRE(N > 0 && K > 0 && H > 0 && W > 0 && static_cast<int64_t>(N) * K <= 65535, DT_ERR_BAD_SHAPE,
+             "dt_prob_loss_partials: bad shape");
+  const int64_t HW = static_cast<int64_t>(H) * W;
+  int chunks = static_cast<int>((HW + kThreads * 8 - 1) / (kThreads * 8));
+  const int cap = (dt_num_sms() * 8 + N * K - 1) / (N * K);
+  if (chunks > cap) chunks = cap;
+  if (chunks < 1) chunks = 1;
+  dim3 grid(chunks, N * K);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (target_is_float)
+    prob_partials_kernel<float><<<grid, kThreads, 0, s>>>(probs, static_cast<const float*>(target), HW, gamma, sums);
+  else
+    prob_partials_kernel<int32_t><<<grid, kThreads, 0, s>>>(probs, static_cast<const int32_t*>(target), HW, gamma, sums);
+  DT_LAUNCH_CHECK();
+  return DT_OK;
+}
+
+int dt_sumsq(const float* g, int64_t n, double* sumsq, dt_stream_t stream) {
+  DT_ARCH_GUARD();
+  DT_REQUIRE(n >= 0, DT_ERR_BAD_SHAPE, "dt_sumsq: n < 0");
+  if (n == 0) return DT_OK;
+  sumsq_kernel<<<grid_for(n), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(g, n, sumsq);
+  DT_LAUNCH_CHECK();
+  return DT_OK;
+}
+
+int dt_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                 float eps, int step, const double* sumsq, float max_norm, dt_stream_t stream) {
+  DT_ARCH_GUARD();
+  DT_REQUIRE(n >= 0 && step >= 1, DT_ERR_BAD_SHAPE, "dt_adam_step: bad arguments");
+  DT_REQUIRE(max_norm <= 0.f || sumsq != nullptr, DT_ERR_BAD_SHAPE, "dt_adam_step: clipping needs sumsq");
+  if (n == 0) return DT_OK;
+  // bias corrections in double on the host, as torch.optim.Adam does in Python floats
+  const float bc1 = static_cast<float>(1.0 - pow(static_cast<double>(beta1), step));
+  const float bc2_sqrt = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(beta2), step)));
+  adam_kernel<<<grid_for(n), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps,
+                                                                               bc1, bc2_sqrt, sumsq, max_norm);
+  DT_LAUNCH_CHECK();
+  return DT_OK;
+}
+
+}  // extern "C"

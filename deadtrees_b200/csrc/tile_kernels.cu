@@ -1,0 +1,393 @@
+// HBM-bound tiler kernels: block split/merge, tile gather + normalise, mask stitch, blended stitch.
+// Reference behaviour: deadtrees/utils/data_handling.py:9-34, deadtrees/deployment/tiler.py:105-170,
+// deadtrees/data/deadtreedata.py:148-154 (see include/deadtrees_b200.h for the per-entry citations).
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+inline int grid_for(int64_t work, int threads = kThreads) {
+  int64_t blocks = (work + threads - 1) / threads;
+  const int64_t cap = static_cast<int64_t>(dt_num_sms()) * 32;  // grid-stride beyond 32 CTAs / SM
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks);
+}
+
+template <int U> struct Unit;
+template <> struct Unit<1> { using T = uint8_t; };
+template <> struct Unit<2> { using T = uint16_t; };
+template <> struct Unit<4> { using T = uint32_t; };
+template <> struct Unit<8> { using T = uint64_t; };
+template <> struct Unit<16> { using T = uint4; };
+
+// dst (nb, p, d, d) <- src (p, m, n); everything measured in units of U bytes along the row.
+template <int U>
+__global__ void make_blocks_kernel(const typename Unit<U>::T* __restrict__ src,
+                                   typename Unit<U>::T* __restrict__ dst, int p, int m, int n_u, int d, int d_u) {
+  const int nbx = n_u / d_u;
+  const int64_t total = static_cast<int64_t>(p) * m * n_u;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    int64_t r = i;
+    const int xu = static_cast<int>(r % d_u); r /= d_u;
+    const int y = static_cast<int>(r % d); r /= d;
+    const int c = static_cast<int>(r % p); r /= p;
+    const int b = static_cast<int>(r);
+    const int by = b / nbx, bx = b % nbx;
+    dst[i] = src[(static_cast<int64_t>(c) * m + (by * d + y)) * n_u + bx * d_u + xu];
+  }
+}
+
+// dst (m, n) <- src (nb, d, d)
+template <int U>
+__global__ void unmake_blocks_kernel(const typename Unit<U>::T* __restrict__ src,
+                                     typename Unit<U>::T* __restrict__ dst, int m, int n_u, int d, int d_u) {
+  const int nbx = n_u / d_u;
+  const int64_t total = static_cast<int64_t>(m) * n_u;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int xg = static_cast<int>(i % n_u);
+    const int yg = static_cast<int>(i / n_u);
+    const int b = (yg / d) * nbx + xg / d_u;
+    dst[i] = src[(static_cast<int64_t>(b) * d + (yg % d)) * d_u + (xg % d_u)];
+  }
+}
+
+int pick_unit(const void* a, const void* b, int64_t row_bytes_a, int64_t row_bytes_b, int elem) {
+  for (int u = 16; u > elem; u >>= 1) {
+    if (row_bytes_a % u == 0 && row_bytes_b % u == 0 && reinterpret_cast<uintptr_t>(a) % u == 0 &&
+        reinterpret_cast<uintptr_t>(b) % u == 0)
+      return u;
+  }
+  return elem;
+}
+
+struct NormParams {
+  float offset[4];
+  float scale[4];
+};
+
+// One thread = 4 consecutive pixels of one tile row.  Fast paths read 4 bytes per channel (planar)
+// or 12/16 contiguous bytes (interleaved RGB / RGBA); everything else falls back to guarded byte loads.
+template <bool OUT_BF16>
+__global__ void gather_normalize_kernel(const uint8_t* __restrict__ mosaic, int H, int W, int C, int64_t row_stride,
+                                        int64_t pix_stride, int64_t chan_stride, int T, int step, int gx, int tile0,
+                                        int ntiles, NormParams np, void* __restrict__ out) {
+  const int q = T >> 2;
+  const int64_t total = static_cast<int64_t>(ntiles) * T * q;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int x4 = static_cast<int>(i % q);
+    const int y = static_cast<int>((i / q) % T);
+    const int t = static_cast<int>(i / (static_cast<int64_t>(q) * T));
+    const int cell = tile0 + t;
+    const int gy0 = (cell / gx) * step + y;
+    const int gx0 = (cell % gx) * step + x4 * 4;
+    uint32_t px[4] = {0u, 0u, 0u, 0u};  // px[j] = bytes c0..c3 of pixel j
+    if (gy0 < H && gx0 < W) {
+      const uint8_t* base = mosaic + gy0 * row_stride + gx0 * pix_stride;
+      const bool full = gx0 + 3 < W;
+      if (full && pix_stride == 1 && ((reinterpret_cast<uintptr_t>(base) | chan_stride) & 3) == 0) {
+        // planar: one aligned 32-bit load per channel
+        for (int c = 0; c < C; ++c) {
+          const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(base + c * chan_stride));
+#pragma unroll
+          for (int j = 0; j < 4; ++j) px[j] |= ((v >> (8 * j)) & 0xffu) << (8 * c);
+        }
+      } else if (full && chan_stride == 1 && pix_stride == 4 && C == 4 &&
+                 (reinterpret_cast<uintptr_t>(base) & 15) == 0) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(base));
+        px[0] = v.x; px[1] = v.y; px[2] = v.z; px[3] = v.w;
+      } else if (full && chan_stride == 1 && pix_stride == 3 && C == 3 &&
+                 (reinterpret_cast<uintptr_t>(base) & 3) == 0) {
+        const uint32_t a = __ldg(reinterpret_cast<const uint32_t*>(base));
+        const uint32_t b = __ldg(reinterpret_cast<const uint32_t*>(base) + 1);
+        const uint32_t c = __ldg(reinterpret_cast<const uint32_t*>(base) + 2);
+        px[0] = a & 0xffffffu;
+        px[1] = (a >> 24) | ((b & 0xffffu) << 8);
+        px[2] = (b >> 16) | ((c & 0xffu) << 16);
+        px[3] = c >> 8;
+      } else {
+        for (int j = 0; j < 4; ++j) {
+          if (gx0 + j < W) {
+            for (int c = 0; c < C; ++c)
+              px[j] |= static_cast<uint32_t>(__ldg(base + j * pix_stride + c * chan_stride)) << (8 * c);
+          }
+        }
+      }
+    }
+    float v[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float u = static_cast<float>((px[j] >> (8 * c)) & 0xffu);
+        // subtract, then multiply by the reciprocal (albumentations Normalize); no FMA contraction
+        v[j][c] = (c < C) ? __fmul_rn(__fsub_rn(u, np.offset[c]), np.scale[c]) : 0.0f;
+      }
+    }
+    if (OUT_BF16) {
+      uint4* o = reinterpret_cast<uint4*>(out) + i * 2;
+      o[0] = make_uint4(pack_bf16x2(v[0][0], v[0][1]), pack_bf16x2(v[0][2], v[0][3]),
+                        pack_bf16x2(v[1][0], v[1][1]), pack_bf16x2(v[1][2], v[1][3]));
+      o[1] = make_uint4(pack_bf16x2(v[2][0], v[2][1]), pack_bf16x2(v[2][2], v[2][3]),
+                        pack_bf16x2(v[3][0], v[3][1]), pack_bf16x2(v[3][2], v[3][3]));
+    } else {
+      float4* o = reinterpret_cast<float4*>(out) + i * 4;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[j] = make_float4(v[j][0], v[j][1], v[j][2], v[j][3]);
+    }
+  }
+}
+
+// overlap-0 stitch: one thread = V consecutive pixels of one tile row.
+template <int V>
+__global__ void stitch_mask_kernel(const uint8_t* __restrict__ tiles, int T, int gx, int tile0, int ntiles,
+                                   uint8_t* __restrict__ mosaic, int H, int W, int64_t row_stride) {
+  const int q = T / V;
+  const int64_t total = static_cast<int64_t>(ntiles) * T * q;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int xv = static_cast<int>(i % q);
+    const int y = static_cast<int>((i / q) % T);
+    const int t = static_cast<int>(i / (static_cast<int64_t>(q) * T));
+    const int cell = tile0 + t;
+    const int my = (cell / gx) * T + y;
+    const int mx = (cell % gx) * T + xv * V;
+    if (my >= H || mx >= W) continue;
+    const uint8_t* s = tiles + (static_cast<int64_t>(t) * T + y) * T + xv * V;
+    uint8_t* d = mosaic + my * row_stride + mx;
+    if (V == 16 && mx + 16 <= W && (reinterpret_cast<uintptr_t>(d) & 15) == 0) {
+      st_na_v4(d, ld_nc_v4(s));
+    } else {
+      for (int j = 0; j < V && mx + j < W; ++j) d[j] = s[j];
+    }
+  }
+}
+
+template <typename LT> __device__ __forceinline__ float load_logit(const LT* p);
+template <> __device__ __forceinline__ float load_logit<float>(const float* p) { return __ldg(p); }
+template <> __device__ __forceinline__ float load_logit<__nv_bfloat16>(const __nv_bfloat16* p) {
+  return bf16_bits_to_float(__ldg(reinterpret_cast<const uint16_t*>(p)));
+}
+
+// gather-form blend: one thread = one mosaic pixel; visits the <= 4 covering tiles in (ty, tx) order.
+template <typename LT, int K>
+__global__ void stitch_blend_kernel(const LT* __restrict__ logits, int T, int step, int gy, int gx, int ty_base,
+                                    const float* __restrict__ win, uint8_t* __restrict__ mask,
+                                    float* __restrict__ blended, int H, int W, int row0, int nrows) {
+  const int64_t total = static_cast<int64_t>(nrows) * W;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int x = static_cast<int>(i % W);
+    const int y = row0 + static_cast<int>(i / W);
+    int ty0 = (y - T + step) / step;  // ceil((y - T + 1) / step) for y - T + 1 > 0
+    if (y - T + 1 <= 0) ty0 = 0;
+    int tx0 = (x - T + step) / step;
+    if (x - T + 1 <= 0) tx0 = 0;
+    const int ty1 = min(gy - 1, y / step), tx1 = min(gx - 1, x / step);
+    float acc[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) acc[k] = 0.0f;
+    float wsum = 0.0f;
+    for (int ty = ty0; ty <= ty1; ++ty) {
+      const int ly = y - ty * step;
+      const float wy = __ldg(win + ly);
+      for (int tx = tx0; tx <= tx1; ++tx) {
+        const int lx = x - tx * step;
+        const float w = __fmul_rn(wy, __ldg(win + lx));
+        const LT* p = logits + ((static_cast<int64_t>(ty - ty_base) * gx + tx) * T * T + static_cast<int64_t>(ly) * T + lx) * K;
+#pragma unroll
+        for (int k = 0; k < K; ++k) acc[k] = __fadd_rn(acc[k], __fmul_rn(load_logit<LT>(p + k), w));
+        wsum = __fadd_rn(wsum, w);
+      }
+    }
+    int best = 0;
+    float bv = __fdiv_rn(acc[0], wsum);
+    if (blended) blended[(static_cast<int64_t>(y) * W + x) * K] = bv;
+#pragma unroll
+    for (int k = 1; k < K; ++k) {
+      const float v = __fdiv_rn(acc[k], wsum);
+      if (blended) blended[(static_cast<int64_t>(y) * W + x) * K + k] = v;
+      if (v > bv) { bv = v; best = k; }
+    }
+    mask[static_cast<int64_t>(y) * W + x] = static_cast<uint8_t>(best);
+  }
+}
+
+// (N, C_src, H, W) fp32 planes -> (N, H, W, 4) NHWC, first C channels kept (RGB slice), rest zero.
+template <bool OUT_BF16>
+__global__ void pack_nchw_kernel(const float* __restrict__ x, int N, int C_src, int C, int64_t HW,
+                                 void* __restrict__ out) {
+  const int64_t total = static_cast<int64_t>(N) * HW;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t n = i / HW, px = i % HW;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int c = 0; c < C; ++c) v[c] = __ldg(x + (n * C_src + c) * HW + px);
+    if (OUT_BF16)
+      reinterpret_cast<uint2*>(out)[i] = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
+    else
+      reinterpret_cast<float4*>(out)[i] = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int dt_pack_input_nchw(const float* x, int N, int C_src, int C, int H, int W, int out_dtype, void* out,
+                       dt_stream_t stream) {
+  DT_ARCH_GUARD();
+  DT_REQUIRE(N > 0 && H > 0 && W > 0 && C >= 1 && C <= 4 && C_src >= C, DT_ERR_BAD_SHAPE,
+             "dt_pack_input_nchw: N=%d C_src=%d C=%d", N, C_src, C);
+  DT_REQUIRE(out_dtype == DT_BF16 || out_dtype == DT_F32, DT_ERR_BAD_SHAPE, "dt_pack_input_nchw: dtype %d", out_dtype);
+  DT_REQUIRE(reinterpret_cast<uintptr_t>(out) % 16 == 0, DT_ERR_BAD_ALIGN, "dt_pack_input_nchw: out alignment");
+  const int64_t HW = static_cast<int64_t>(H) * W;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (out_dtype == DT_BF16)
+    pack_nchw_kernel<true><<<grid_for(N * HW), kThreads, 0, s>>>(x, N, C_src, C, HW, out);
+  else
+    pack_nchw_kernel<false><<<grid_for(N * HW), kThreads, 0, s>>>(x, N, C_src, C, HW, out);
+  DT_LAUNCH_CHECK();
+  return DT_OK;
+}
+
+int dt_make_blocks(const void* src, int p, int m, int n, int d, int elem_size, void* dst, dt_stream_t stream) {
+  DT_ARCH_GUARD();
+  DT_REQUIRE(p > 0 && m > 0 && n > 0 && d > 0 && m % d == 0 && n % d == 0, DT_ERR_BAD_SHAPE,
+             "dt_make_blocks: (p,m,n)=(%d,%d,%d) not divisible by d=%d", p, m, n, d);
+  DT_REQUIRE(elem_size == 1 || elem_size == 2 || elem_size == 4 || elem_size == 8, DT_ERR_BAD_SHAPE,
+             "dt_make_blocks: elem_size %d", elem_size);
+  DT_REQUIRE(reinterpret_cast<uintptr_t>(src) % elem_size == 0 && reinterpret_cast<uintptr_t>(dst) % elem_size == 0,
+             DT_ERR_BAD_ALIGN, "dt_make_blocks: pointers not aligned to the element size");
+  const int u = pick_unit(src, dst, static_cast<int64_t>(n) * elem_size, static_cast<int64_t>(d) * elem_size, elem_size);
+  const int n_u = n * elem_size / u, d_u = d * elem_size / u;
+  const int64_t total = static_cast<int64_t>(p) * m * n_u;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+#define DT_MB(U)                                                                                      \
+  make_blocks_kernel<U><<<grid_for(total), kThreads, 0, s>>>(                                         \
+      static_cast<const Unit<U>::T*>(src), static_cast<Unit<U>::T*>(dst), p, m, n_u, d, d_u)
+  switch (u) {
+    case 16: DT_MB(16); break;
+    case 8: DT_MB(8); break;
+    case 4: DT_MB(4); break;
+    case 2: DT_MB(2); break;
+    default: DT_MB(1); break;
+  }
+#undef DT_MB
+  DT_LAUNCH_CHECK();
+  return DT_OK;
+}
+
+int dt_unmake_blocks(const void* src, int d, int m, int n, int elem_size, void* dst, dt_stream_t stream) {
+  DT_ARCH_GUARD();
+  DT_REQUIRE(m > 0 && n > 0 && d > 0 && m % d == 0 && n % d == 0, DT_ERR_BAD_SHAPE,
+             "dt_unmake_blocks: (m,n)=(%d,%d) not divisible by d=%d", m, n, d);
+  DT_REQUIRE(elem_size == 1 || elem_size == 2 || elem_size == 4 || elem_size == 8, DT_ERR_BAD_SHAPE,
+             "dt_unmake_blocks: elem_size %d", elem_size);
+  DT_REQUIRE(reinterpret_cast<uintptr_t>(src) % elem_size == 0 && reinterpret_cast<uintptr_t>(dst) % elem_size == 0,
+             DT_ERR_BAD_ALIGN, "dt_unmake_blocks: pointers not aligned to the element size");
+  const int u = pick_unit(src, dst, static_cast<int64_t>(n) * elem_size, static_cast<int64_t>(d) * elem_size, elem_size);
+  const int n_u = n * elem_size / u, d_u = d * elem_size / u;
+  const int64_t total = static_cast<int64_t>(m) * n_u;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+#define DT_UB(U)                                                                                      \
+  unmake_blocks_kernel<U><<<grid_for(total), kThreads, 0, s>>>(                                       \
+      static_cast<const Unit<U>::T*>(src), static_cast<Unit<U>::T*>(dst), m, n_u, d, d_u)
+  switch (u) {
+    case 16: DT_UB(16); break;
+    case 8: DT_UB(8); break;
+    case 4: DT_UB(4); break;
+    case 2: DT_UB(2); break;
+    default: DT_UB(1); break;
+  }
+#undef DT_UB
+  DT_LAUNCH_CHECK();
+  return DT_OK;
+}
+
+int dt_tile_gather_normalize(const uint8_t* mosaic, int H, int W, int C, int64_t row_stride, int64_t pix_stride,
+                             int64_t chan_stride, int tile, int step, int gx, int tile0, int ntiles,
+                             const float* offset, const float* scale, int c_out, int out_dtype, void* out,
+                             dt_stream_t stream) {
+  DT_ARCH_GUARD();
+  DT_REQUIRE(C >= 1 && C <= 4 && c_out == 4, DT_ERR_BAD_SHAPE, "dt_tile_gather_normalize: C=%d c_out=%d (need C<=4, c_out==4)", C, c_out);
+  DT_REQUIRE(tile > 0 && tile % 4 == 0 && step > 0 && step <= tile && gx > 0 && ntiles >= 0 && tile0 >= 0,
+             DT_ERR_BAD_SHAPE, "dt_tile_gather_normalize: tile=%d step=%d gx=%d", tile, step, gx);
+  DT_REQUIRE(out_dtype == DT_BF16 || out_dtype == DT_F32, DT_ERR_BAD_SHAPE, "dt_tile_gather_normalize: out_dtype %d", out_dtype);
+  DT_REQUIRE(reinterpret_cast<uintptr_t>(out) % 16 == 0, DT_ERR_BAD_ALIGN, "dt_tile_gather_normalize: out must be 16-byte aligned");
+  if (ntiles == 0) return DT_OK;
+  NormParams np;
+  for (int c = 0; c < 4; ++c) {
+    np.offset[c] = c < C ? offset[c] : 0.f;
+    np.scale[c] = c < C ? scale[c] : 0.f;
+  }
+  const int64_t total = static_cast<int64_t>(ntiles) * tile * (tile / 4);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (out_dtype == DT_BF16)
+    gather_normalize_kernel<true><<<grid_for(total), kThreads, 0, s>>>(mosaic, H, W, C, row_stride, pix_stride,
+                                                                      chan_stride, tile, step, gx, tile0, ntiles, np, out);
+  else
+    gather_normalize_kernel<false><<<grid_for(total), kThreads, 0, s>>>(mosaic, H, W, C, row_stride, pix_stride,
+                                                                       chan_stride, tile, step, gx, tile0, ntiles, np, out);
+  DT_LAUNCH_CHECK();
+  return DT_OK;
+}
+
+int dt_stitch_mask_u8(const uint8_t* tile_masks, int T, int gx, int tile0, int ntiles, uint8_t* mosaic_mask, int H,
+                      int W, int64_t row_stride, dt_stream_t stream) {
+  DT_ARCH_GUARD();
+  DT_REQUIRE(T > 0 && gx > 0 && ntiles >= 0 && tile0 >= 0 && H > 0 && W > 0 && row_stride >= W, DT_ERR_BAD_SHAPE,
+             "dt_stitch_mask_u8: T=%d gx=%d H=%d W=%d", T, gx, H, W);
+  if (ntiles == 0) return DT_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (T % 16 == 0 && reinterpret_cast<uintptr_t>(tile_masks) % 16 == 0) {
+    const int64_t total = static_cast<int64_t>(ntiles) * T * (T / 16);
+    stitch_mask_kernel<16><<<grid_for(total), kThreads, 0, s>>>(tile_masks, T, gx, tile0, ntiles, mosaic_mask, H, W, row_stride);
+  } else {
+    const int64_t total = static_cast<int64_t>(ntiles) * T * T;
+    stitch_mask_kernel<1><<<grid_for(total), kThreads, 0, s>>>(tile_masks, T, gx, tile0, ntiles, mosaic_mask, H, W, row_stride);
+  }
+  DT_LAUNCH_CHECK();
+  return DT_OK;
+}
+
+int dt_stitch_blend_argmax(const void* logits, int dtype, int K, int T, int overlap, int gy, int gx, int ty_base,
+                           const float* win, uint8_t* mosaic_mask, float* blended, int H, int W, int row0,
+                           int nrows, dt_stream_t stream) {
+  DT_ARCH_GUARD();
+  DT_REQUIRE(K >= 1 && K <= 4, DT_ERR_BAD_SHAPE, "dt_stitch_blend_argmax: K=%d (1..4)", K);
+  DT_REQUIRE(T > 0 && overlap >= 0 && overlap < T && gy > 0 && gx > 0, DT_ERR_BAD_SHAPE,
+             "dt_stitch_blend_argmax: T=%d overlap=%d grid=%dx%d", T, overlap, gy, gx);
+  DT_REQUIRE(ty_base >= 0 && (row0 - T + 1 <= 0 ? 0 : (row0 - overlap) / (T - overlap)) >= ty_base, DT_ERR_BAD_SHAPE,
+             "dt_stitch_blend_argmax: rows from %d need tile rows before ty_base=%d", row0, ty_base);
+  DT_REQUIRE(row0 >= 0 && nrows >= 0 && row0 + nrows <= H && H <= (gy - 1) * (T - overlap) + T &&
+                 W <= (gx - 1) * (T - overlap) + T,
+             DT_ERR_BAD_SHAPE, "dt_stitch_blend_argmax: rows [%d,%d) of %dx%d not covered by the grid", row0, row0 + nrows, H, W);
+  if (nrows == 0) return DT_OK;
+  const int step = T - overlap;
+  const int64_t total = static_cast<int64_t>(nrows) * W;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+#define DT_SB(LT, KK)                                                                                  \
+  stitch_blend_kernel<LT, KK><<<grid_for(total), kThreads, 0, s>>>(static_cast<const LT*>(logits), T, step, gy, gx, \
+                                                                  ty_base, win, mosaic_mask, blended, H, W, row0, nrows)
+#define DT_SBK(LT)                     \
+  switch (K) {                         \
+    case 1: DT_SB(LT, 1); break;       \
+    case 2: DT_SB(LT, 2); break;       \
+    case 3: DT_SB(LT, 3); break;       \
+    default: DT_SB(LT, 4); break;      \
+  }
+  if (dtype == DT_BF16) { DT_SBK(__nv_bfloat16) } else if (dtype == DT_F32) { DT_SBK(float) } else {
+    DT_REQUIRE(false, DT_ERR_BAD_SHAPE, "dt_stitch_blend_argmax: dtype %d", dtype);
+  }
+#undef DT_SBK
+#undef DT_SB
+  DT_LAUNCH_CHECK();
+  return DT_OK;
+}
+
+}  // extern "C"

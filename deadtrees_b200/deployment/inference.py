@@ -1,0 +1,193 @@
+"""Inference back-ends — drop-in for ``deadtrees.deployment.inference`` plus the whole-mosaic pipeline.
+
+Mirrors ``deadtrees/deployment/inference.py``: ``Inference`` (:14-27), ``PyTorchInference`` (:30-62),
+``PyTorchEnsembleInference`` (:65-116).  ``MosaicInference`` is the B200 form of the hot loop in
+``scripts/inference.py:85-111`` (tile -> normalise -> forward -> argmax -> stitch) with every stage on the
+device: uint8 mosaic in, uint8 class-id mosaic out.
+"""
+from __future__ import annotations
+
+import math
+from abc import ABC, abstractmethod
+from pathlib import Path
+from typing import Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+
+from .. import ops
+from .._lib import require_device
+from ..data.deadtreedata import normalize_constants
+from ..engine import UnetEngine
+from ..network.segmodel import SemSegment
+
+
+class Inference(ABC):
+    def __init__(self, model_file: Union[str, Path]) -> None:
+        self._model_file = model_file if isinstance(model_file, Path) else Path(model_file)
+        super().__init__()
+
+    @property
+    def model_file(self) -> str:
+        return self._model_file.name
+
+    @abstractmethod
+    def run(self, input_tensor: torch.Tensor):
+        pass
+
+
+class PyTorchInference(Inference):
+    def __init__(self, model_file) -> None:
+        super().__init__(model_file)
+        if self._model_file.suffix != ".ckpt":
+            raise ValueError(f"ckpt file expected, but {self._model_file.suffix} received")
+        model = SemSegment.load_from_checkpoint(self._model_file)
+        model.eval()
+        self._channels = list(model.parameters())[0].shape[1]
+        self._model = model.model
+
+    def run(self, input_tensor, device: str = "cuda"):
+        """(N, C, H, W) or (C, H, W) float tensor -> int64 class ids, squeezed (inference.py:47-62).
+
+        The reference defaults ``device="cpu"``; this build has no CPU path, so a CPU device raises."""
+        if not isinstance(input_tensor, torch.Tensor):
+            raise TypeError("no pytorch tensor provided")
+        require_device()
+        if torch.device(device).type != "cuda":
+            raise RuntimeError("deadtrees_b200 runs on CUDA (B200) devices only: pass device='cuda'")
+        self._model.to(device)
+        if input_tensor.dim() == 3:
+            input_tensor.unsqueeze_(0)
+        with torch.no_grad():
+            # rgb model but rgbn data: the input packer keeps the first `_channels` channels
+            out = self._model(input_tensor.to(device))
+        return ops.argmax_nchw(out).long().squeeze()
+
+
+class PyTorchEnsembleInference:
+    def __init__(self, *model_files: Path):
+        self._models = []
+        self._channels = None
+        if len(model_files) % 2 == 0:
+            raise ValueError("PyTorchEnsembleInference requires an uneven number of models")
+        for model_file in model_files:
+            model_file = Path(model_file)
+            if model_file.suffix != ".ckpt":
+                raise ValueError(f"Ckpt file expected, but {model_file.suffix} received")
+            model = SemSegment.load_from_checkpoint(model_file)
+            model.eval()
+            channels = list(model.parameters())[0].shape[1]
+            if not self._channels:
+                self._channels = channels
+            if channels != self._channels:
+                raise ValueError("Models are not compatible since they were trained for different channel configs")
+            self._models.append(model.model)
+
+    def run(self, input_tensor, device: str = "cuda"):
+        if not isinstance(input_tensor, torch.Tensor):
+            raise TypeError("No PyTorch tensor provided")
+        require_device()
+        if input_tensor.dim() == 3:
+            input_tensor.unsqueeze_(0)
+        outs = []
+        for model in self._models:
+            model.to(device)
+            with torch.no_grad():
+                outs.append(ops.argmax_nchw(model(input_tensor.to(device))).long().squeeze())
+        return torch.mode(torch.stack(outs, dim=1), axis=1)[0]
+
+
+# --------------------------------------------------------------------------------------------------
+
+def overlap_grid(H: int, W: int, T: int, overlap: int) -> Tuple[int, int]:
+    """number of tiles (gy, gx) at stride T - overlap covering H x W (zero padding beyond the edge)."""
+    if not 0 <= overlap < T:
+        raise ValueError("overlap must be in [0, T)")
+    s = T - overlap
+    return max(0, math.ceil((H - T) / s)) + 1, max(0, math.ceil((W - T) / s)) + 1
+
+
+def blend_window(T: int, overlap: int, device) -> torch.Tensor:
+    """1-D blending weights: linear ramp across the overlap, 1 inside (all ones when overlap == 0)."""
+    i = np.arange(T, dtype=np.float32)
+    w = np.minimum(np.minimum(i + 1, T - i), np.float32(overlap + 1)) / np.float32(overlap + 1)
+    return torch.from_numpy(w.astype(np.float32)).to(device)
+
+
+class MosaicInference:
+    """Sliding-window segmentation of a whole uint8 mosaic on one GPU (or one tile-row shard of it)."""
+
+    def __init__(self, model, tile: int = 256, overlap: int = 0, batch_tiles: int = 128,
+                 precision: Optional[str] = None, mean=None, std=None):
+        require_device()
+        if isinstance(model, SemSegment):
+            model = model.model
+        if isinstance(model, UnetEngine):
+            self.engine = model
+        else:
+            if precision is not None:
+                model.set_precision(precision)
+            self.engine = model.eval().engine()
+        if tile % 32:
+            raise ValueError("tile must be a multiple of 32 (five stride-2 stages)")
+        self.tile, self.overlap, self.batch_tiles = tile, overlap, batch_tiles
+        self.offset, self.scale = normalize_constants(self.engine.in_channels, mean, std)
+        self.win = blend_window(tile, overlap, self.engine.device)
+        self._bufs = {}
+
+    def _buf(self, key, shape, dtype):
+        t = self._bufs.get(key)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+            t = torch.empty(shape, dtype=dtype, device=self.engine.device)
+            self._bufs[key] = t
+        return t
+
+    def run(self, mosaic: torch.Tensor, layout: str = "hwc", tile_rows: Optional[Tuple[int, int]] = None,
+            out: Optional[torch.Tensor] = None, halo_hook=None) -> torch.Tensor:
+        """mosaic: CUDA uint8 (H, W, C) ["hwc"] or (C, H, W) ["chw"] -> uint8 class ids (H, W).
+
+        ``tile_rows=(r0, r1)`` restricts the work to that range of tile rows (multi-GPU sharding); the
+        returned mask is then only valid on the mosaic rows this shard owns, ``owned_rows(...)``."""
+        H, W = (mosaic.shape[0], mosaic.shape[1]) if layout == "hwc" else (mosaic.shape[1], mosaic.shape[2])
+        T, ov, eng = self.tile, self.overlap, self.engine
+        gy, gx = overlap_grid(H, W, T, ov)
+        r0, r1 = (0, gy) if tile_rows is None else tile_rows
+        mask = out if out is not None else self._buf("mask", (H, W), torch.uint8)
+        ntiles = (r1 - r0) * gx
+        bt = min(self.batch_tiles, max(ntiles, 1))
+        x = self._buf("x", (bt, T, T, 4), eng.act_dtype)
+        if ov == 0:
+            tmask = self._buf("tmask", (bt, T, T), torch.uint8)
+        else:
+            halo = 1 if r0 > 0 else 0  # room for the neighbour's last tile row (only its bottom rows are read)
+            logits = self._buf("logits", ((r1 - r0 + halo) * gx, T, T, eng.classes), eng.act_dtype)
+        for t0 in range(r0 * gx, r1 * gx, bt):
+            n = min(bt, r1 * gx - t0)
+            xb = x[:n]
+            ops.tile_gather_normalize(mosaic, layout, eng.in_channels, T, ov, (gy, gx), t0, n, self.offset,
+                                      self.scale, out=xb)
+            if ov == 0:
+                eng.forward(xb, mask_out=tmask[:n])
+                ops.stitch_mask(tmask[:n], gx, t0, mask)
+            else:
+                lo = t0 - (r0 - halo) * gx
+                eng.forward(xb, logits_nhwc_out=logits[lo: lo + n])
+        if ov > 0:
+            if halo_hook is not None:
+                halo_hook(logits, gx, halo)  # multi-GPU: exchange boundary logits rows with the neighbours
+            y0, y1 = self.owned_rows(H, T, ov, gy, r0, r1)
+            ops.stitch_blend_argmax(logits, ov, (gy, gx), self.win, mask, row0=y0, nrows=y1 - y0, ty_base=r0 - halo)
+        return mask
+
+    @staticmethod
+    def owned_rows(H: int, T: int, overlap: int, gy: int, r0: int, r1: int) -> Tuple[int, int]:
+        """mosaic rows whose output a shard with tile rows [r0, r1) writes."""
+        s = T - overlap
+        return min(H, r0 * s), (H if r1 >= gy else min(H, r1 * s))
+
+    def run_host(self, mosaic: np.ndarray, layout: str = "hwc") -> np.ndarray:
+        """host ndarray in, host ndarray out (pinned staging; the end-to-end path of ``scripts/inference.py``)."""
+        src = torch.from_numpy(np.ascontiguousarray(mosaic))
+        dev = self._buf("mosaic_dev", tuple(src.shape), torch.uint8)
+        dev.copy_(src.pin_memory() if not src.is_pinned() else src, non_blocking=True)
+        return self.run(dev, layout).cpu().numpy()

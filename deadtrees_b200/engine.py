@@ -1,0 +1,227 @@
+"""Inference engine for Unet(resnet34): folds BN, repacks weights for the CUDA kernels and sequences
+the fused convolutions of one forward pass.
+
+Follows what ``smp.Unet.forward`` computes in the reference (call sites
+``deadtrees/network/segmodel.py:214`` and ``deadtrees/deployment/inference.py:60``; layer list in
+SURVEY.md Appendix A); state-dict key layout = smp's.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional
+
+import torch
+
+from . import ops
+from ._lib import require_device
+
+BN_EPS = 1e-5
+RESNET34_LAYERS = (3, 4, 6, 3)
+RESNET34_PLANES = (64, 128, 256, 512)
+BK = 64
+
+
+@dataclass
+class FusedConv:
+    """conv (+ folded eval BatchNorm) (+ residual) (+ ReLU) in the kernels' weight layout."""
+    name: str
+    C_in: int
+    C_x: int
+    C_out: int
+    R: int
+    S: int
+    stride: int
+    pad: int
+    relu: bool
+    upsample: bool
+    w: torch.Tensor
+    scale: torch.Tensor
+    shift: torch.Tensor
+    flops_per_px_out: int = field(default=0)
+
+
+def fold_bn(sd: Dict[str, torch.Tensor], prefix: str, C_out: int, device):
+    """eval BatchNorm -> per-channel (scale, shift): y = x*g/sqrt(v+eps) + (b - m*g/sqrt(v+eps))."""
+    if prefix + ".weight" not in sd:
+        return torch.ones(C_out, device=device), torch.zeros(C_out, device=device)
+    g, b = sd[prefix + ".weight"].float(), sd[prefix + ".bias"].float()
+    m, v = sd[prefix + ".running_mean"].float(), sd[prefix + ".running_var"].float()
+    scale = g / torch.sqrt(v + BN_EPS)
+    return scale.to(device).contiguous(), (b - m * scale).to(device).contiguous()
+
+
+def pack_weight(w: torch.Tensor, precision: str, stem: bool, device) -> torch.Tensor:
+    """OIHW fp32 -> kernel layout (see include/deadtrees_b200.h, dt_conv2d_fwd)."""
+    C_out, C_in, R, S = w.shape
+    w = w.float()
+    if stem and C_in < 4:
+        w = torch.cat([w, w.new_zeros(C_out, 4 - C_in, R, S)], dim=1)
+        C_in = 4
+    if precision == "fp32":
+        return w.permute(2, 3, 1, 0).reshape(R * S, C_in, C_out).contiguous().to(device)
+    if stem:
+        wp = w.new_zeros(C_out, R, 8, 4)
+        wp[:, :, :S, :] = w.permute(0, 2, 3, 1)
+        flat = wp.reshape(C_out, R * 32)
+        kpad = 256
+    else:
+        flat = w.permute(0, 2, 3, 1).reshape(C_out, R * S * C_in)
+        kpad = (flat.shape[1] + BK - 1) // BK * BK
+    out = w.new_zeros(C_out, kpad)
+    out[:, : flat.shape[1]] = flat
+    return out.to(torch.bfloat16).contiguous().to(device)
+
+
+class UnetEngine:
+    """B200 forward pass of the reference's ``smp.Unet(resnet34, depth 5, decoder (256,128,64,32,16))``."""
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor], in_channels: int, classes: int,
+                 precision: str = "bf16", device: Optional[torch.device] = None, conv_flags: int = 0):
+        if precision not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16' or 'fp32'")
+        require_device()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.precision = precision
+        self.act_dtype = torch.bfloat16 if precision == "bf16" else torch.float32
+        self.in_channels, self.classes = in_channels, classes
+        self.conv_flags = conv_flags
+        if not 1 <= in_channels <= 4:
+            raise ValueError("in_channels must be 1..4")
+        if not 1 <= classes <= 4:
+            raise ValueError("classes must be 1..4")
+        sd = {k: v.detach() for k, v in state_dict.items()}
+        self.layers: Dict[str, FusedConv] = {}
+        self._build(sd)
+        self._ws: Dict[tuple, Dict[str, torch.Tensor]] = {}
+
+    # ------------------------------------------------------------------------------------------
+    def _conv(self, sd, name, conv_key, bn_key, stride, pad, relu, C_x=None, upsample=False, stem=False):
+        w = sd[conv_key + ".weight"]
+        C_out, C_in, R, S = w.shape
+        scale, shift = fold_bn(sd, bn_key, C_out, self.device)
+        if stem:
+            C_in = 4
+        self.layers[name] = FusedConv(name, C_in, C_in if C_x is None else C_x, C_out, R, S, stride, pad, relu,
+                                      upsample, pack_weight(w, self.precision, stem, self.device), scale, shift,
+                                      2 * C_in * R * S * C_out)
+
+    def _build(self, sd):
+        self._conv(sd, "stem", "encoder.conv1", "encoder.bn1", 2, 3, True, stem=True)
+        for li, nblk in enumerate(RESNET34_LAYERS, start=1):
+            for b in range(nblk):
+                p = f"encoder.layer{li}.{b}"
+                stride = 2 if (b == 0 and li > 1) else 1
+                self._conv(sd, p + ".conv1", p + ".conv1", p + ".bn1", stride, 1, True)
+                self._conv(sd, p + ".conv2", p + ".conv2", p + ".bn2", 1, 1, True)  # ReLU after the residual add
+                if p + ".downsample.0.weight" in sd:
+                    self._conv(sd, p + ".downsample", p + ".downsample.0", p + ".downsample.1", stride, 0, False)
+        self.decoder_blocks = 0
+        while f"decoder.blocks.{self.decoder_blocks}.conv1.0.weight" in sd:
+            self.decoder_blocks += 1
+        if self.decoder_blocks != 5:
+            raise NotImplementedError("only encoder_depth=5 / five decoder blocks are supported")
+        x_ch = 512
+        for i in range(5):
+            p = f"decoder.blocks.{i}"
+            self._conv(sd, p + ".conv1", p + ".conv1.0", p + ".conv1.1", 1, 1, True, C_x=x_ch, upsample=True)
+            self._conv(sd, p + ".conv2", p + ".conv2.0", p + ".conv2.1", 1, 1, True)
+            x_ch = self.layers[p + ".conv1"].C_out
+        hw = sd["segmentation_head.0.weight"].float()
+        if hw.shape[0] != self.classes:
+            raise ValueError("segmentation head does not match `classes`")
+        self.head_w = hw.permute(2, 3, 1, 0).reshape(9, hw.shape[1], hw.shape[0]).contiguous().to(self.device)
+        self.head_b = sd["segmentation_head.0.bias"].float().contiguous().to(self.device)
+
+    # ------------------------------------------------------------------------------------------
+    def _run(self, name, x, N, H, W, skip=None, residual=None, out=None):
+        L = self.layers[name]
+        return ops.conv2d(x, L.w, L.scale, L.shift, N=N, H=H, W=W, C_in=L.C_in, C_x=L.C_x, C_out=L.C_out, R=L.R,
+                          S=L.S, stride=L.stride, pad=L.pad, relu=L.relu, skip=skip, upsample=L.upsample,
+                          residual=residual, out=out, flags=self.conv_flags)
+
+    def _buf(self, ws, key, shape):
+        t = ws.get(key)
+        if t is None or tuple(t.shape) != tuple(shape):
+            t = torch.empty(shape, dtype=self.act_dtype, device=self.device)
+            ws[key] = t
+        return t
+
+    def forward_features(self, x: torch.Tensor, keep: Optional[Dict[str, torch.Tensor]] = None) -> torch.Tensor:
+        """x: (N, T, T, 4) NHWC in the engine's activation dtype -> decoder output (N, T, T, 16)."""
+        N, T, T2, C4 = x.shape
+        if C4 != 4 or T != T2 or T % 32:
+            raise ValueError(f"input must be (N, T, T, 4) with T % 32 == 0, got {tuple(x.shape)}")
+        ws = self._ws.setdefault((N, T), {})
+        buf = lambda key, h, c: self._buf(ws, key, (N, h, h, c))
+        f = {}
+        f[1] = self._run("stem", x, N, T, T, out=buf("f1", T // 2, 64))
+        cur = ops.maxpool3x3s2(f[1], out=buf("pool", T // 4, 64))
+        H = T // 4
+        for li, (planes, nblk) in enumerate(zip(RESNET34_PLANES, RESNET34_LAYERS), start=1):
+            for b in range(nblk):
+                p = f"encoder.layer{li}.{b}"
+                strided = b == 0 and li > 1
+                Ho = H // 2 if strided else H
+                identity = cur
+                if strided:
+                    identity = self._run(p + ".downsample", cur, N, H, H, out=buf(f"ds{li}", Ho, planes))
+                t = self._run(p + ".conv1", cur, N, H, H, out=buf(f"t{li}", Ho, planes))
+                last = b == nblk - 1
+                key = f"f{li + 1}" if last else f"a{li}_{b % 2}"
+                cur = self._run(p + ".conv2", t, N, Ho, Ho, residual=identity, out=buf(key, Ho, planes))
+                H = Ho
+            f[li + 1] = cur
+        if keep is not None:
+            keep.update({f"f{i}": f[i] for i in f})
+        xcur, H = f[5], T // 32
+        skips = [f[4], f[3], f[2], f[1], None]
+        for i in range(5):
+            p = f"decoder.blocks.{i}"
+            H *= 2
+            c_out = self.layers[p + ".conv1"].C_out
+            t = self._run(p + ".conv1", xcur, N, H, H, skip=skips[i], out=buf(f"dt{i}", H, c_out))
+            xcur = self._run(p + ".conv2", t, N, H, H, out=buf(f"d{i}", H, c_out))
+            if keep is not None:
+                keep[f"d{i}"] = xcur
+        return xcur
+
+    def forward(self, x: torch.Tensor, *, want_logits_nchw: bool = False, want_logits_nhwc: bool = False,
+                want_mask: bool = False, mask_out: Optional[torch.Tensor] = None,
+                logits_nhwc_out: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+        d = self.forward_features(x)
+        N, T = x.shape[0], x.shape[1]
+        out: Dict[str, torch.Tensor] = {}
+        if want_logits_nchw:
+            out["logits_nchw"] = torch.empty((N, self.classes, T, T), dtype=torch.float32, device=self.device)
+        if want_logits_nhwc or logits_nhwc_out is not None:
+            out["logits_nhwc"] = logits_nhwc_out if logits_nhwc_out is not None else torch.empty(
+                (N, T, T, self.classes), dtype=self.act_dtype, device=self.device)
+        if want_mask or mask_out is not None:
+            out["mask"] = mask_out if mask_out is not None else torch.empty((N, T, T), dtype=torch.uint8,
+                                                                            device=self.device)
+        ops.head(d, self.head_w, self.head_b, logits_nchw=out.get("logits_nchw"), logits_nhwc=out.get("logits_nhwc"),
+                 mask=out.get("mask"))
+        return out
+
+
+
+def conv_flops_per_tile(T: int, in_channels: int = 3, classes: int = 3) -> float:
+    """Algorithmic conv FLOPs (2 * MACs) of one T x T tile through Unet-resnet34 incl. the head
+    (15.6657 GFLOP at T=256, RGB, 3 classes)."""
+    total = 2.0 * (T // 2) ** 2 * 64 * in_channels * 49
+    H, cin = T // 4, 64
+    for li, (planes, nblk) in enumerate(zip(RESNET34_PLANES, RESNET34_LAYERS), start=1):
+        for b in range(nblk):
+            if b == 0 and li > 1:
+                H //= 2
+                total += 2.0 * H * H * planes * cin            # 1x1 downsample
+            total += 2.0 * H * H * planes * cin * 9            # conv1
+            total += 2.0 * H * H * planes * planes * 9         # conv2
+            cin = planes
+    H, x_ch = T // 32, 512
+    for skip, out in zip((256, 128, 64, 64, 0), (256, 128, 64, 32, 16)):
+        H *= 2
+        total += 2.0 * H * H * out * (x_ch + skip) * 9
+        total += 2.0 * H * H * out * out * 9
+        x_ch = out
+    return total + 2.0 * T * T * classes * 16 * 9

@@ -1,0 +1,37 @@
+"""Fused logits-level loss/metric pass used by ``SemSegment`` (one read of the logits).
+
+``SemSegment.training_step`` in the reference does ``class2one_hot`` + ``softmax`` + Dice/GDL + Focal +
+two Fscore passes (``deadtrees/network/segmodel.py:214-225,169-208``).  ``dt_seg_loss_partials`` does all
+the per-pixel work in one kernel, ``dt_seg_loss_finalize`` turns the sums into the scalars, and
+``dt_seg_loss_backward`` produces d(loss)/d(logits).
+"""
+from __future__ import annotations
+
+import torch
+
+from .. import ops
+
+
+def softmax_nchw(logits: torch.Tensor) -> torch.Tensor:
+    return ops.softmax_nchw(logits)
+
+
+class SegLossTerms:
+    def __init__(self, logits: torch.Tensor, labels: torch.Tensor, dice_mode: int, use_focal: bool):
+        if labels.dtype != torch.int64:
+            labels = labels.long()
+        self.logits, self.labels = logits.contiguous(), labels.contiguous()
+        self.sums, self.counts, self.bad = ops.seg_loss_partials(self.logits, self.labels)
+        self.out, self.coef, self.focal_scale = ops.seg_loss_finalize(self.sums, self.counts, dice_mode, use_focal)
+
+    dice_loss = property(lambda self: self.out[0])
+    focal_loss = property(lambda self: self.out[1])
+    total_loss = property(lambda self: self.out[2])
+    fscore = property(lambda self: self.out[3])
+    fscore_with_bg = property(lambda self: self.out[4])
+
+    def check_labels(self) -> None:
+        assert int(self.bad.item()) == 0, "labels outside [0, K) (class2one_hot assert, losses.py:129)"
+
+    def grad_logits(self, upstream: float = 1.0) -> torch.Tensor:
+        return ops.seg_loss_backward(self.logits, self.labels, self.coef, self.focal_scale, upstream)

@@ -1,0 +1,32 @@
+"""Fused global-norm clip + Adam step (``configure_optimizers`` at ``deadtrees/network/segmodel.py:420-429``
+with ``gradient_clip_val: 0.5`` from ``configs/trainer/default.yaml:18``)."""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+
+
+class FusedAdam(torch.optim.Optimizer):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, max_grad_norm: float = 0.0):
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, max_grad_norm=max_grad_norm))
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        for group in self.param_groups:
+            params = [p for p in group["params"] if p.grad is not None]
+            acc = None
+            if group["max_grad_norm"] > 0:
+                acc = torch.zeros((1,), dtype=torch.float64, device=params[0].device)
+                for p in params:
+                    ops.sumsq(p.grad.contiguous(), acc)
+            for p in params:
+                st = self.state[p]
+                if not st:
+                    st["step"] = 0
+                    st["exp_avg"] = torch.zeros_like(p)
+                    st["exp_avg_sq"] = torch.zeros_like(p)
+                st["step"] += 1
+                ops.adam_step(p, p.grad.contiguous(), st["exp_avg"], st["exp_avg_sq"], lr=group["lr"],
+                              beta1=group["betas"][0], beta2=group["betas"][1], eps=group["eps"], step=st["step"],
+                              sumsq_acc=acc, max_norm=group["max_grad_norm"])

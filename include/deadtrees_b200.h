@@ -1,0 +1,188 @@
+/* deadtrees_b200 — C-ABI of the B200 (sm_100a) hot path of cwerner/deadtrees.
+ *
+ * The reference is pure Python and has NO native/FFI boundary for this path; the
+ * drop-in boundary is the set of Python signatures in `deadtrees_b200/` (mirroring `deadtrees/`).
+ * Those call this library through ctypes.  Every entry point below names the reference code it
+ * replaces (paths relative to the reference repo).
+ *
+ * Conventions
+ *  - all data pointers are DEVICE pointers owned by the caller (PyTorch); the library never
+ *    allocates or frees device memory; `stream` is a cudaStream_t; every call is asynchronous
+ *  - return value: DT_OK or a negative DT_ERR_*; `dt_last_error` returns the thread-local message
+ *  - there is no CPU fallback: on a device that is not compute capability 10.x every compute
+ *    entry point returns DT_ERR_UNSUPPORTED_ARCH
+ *  - activations are NHWC; "act dtype" 0 = bf16 (tensor-core path), 1 = fp32 (check mode)
+ */
+#ifndef DEADTREES_B200_H_
+#define DEADTREES_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DT_VERSION 100
+
+enum {
+  DT_OK = 0,
+  DT_ERR_BAD_SHAPE = -1,
+  DT_ERR_BAD_ALIGN = -2,
+  DT_ERR_UNSUPPORTED_ARCH = -3,
+  DT_ERR_CUDA = -4,
+  DT_ERR_UNSUPPORTED = -5
+};
+
+enum { DT_BF16 = 0, DT_F32 = 1 };
+
+typedef void* dt_stream_t; /* cudaStream_t */
+
+int dt_version(void);
+/* copies the calling thread's last error message into buf (NUL-terminated); returns its length */
+int dt_last_error(char* buf, size_t n);
+/* DT_OK iff the current CUDA device is sm_100-class */
+int dt_device_check(void);
+
+/* ---- T1/T2: block split / merge --------------------------------------------------------------
+ * deadtrees/utils/data_handling.py:9-19  make_blocks_vectorized(x, d):
+ *   src (p, m, n) -> dst (m/d * n/d, p, d, d), block = row_block * (n/d) + col_block.
+ * deadtrees/utils/data_handling.py:22-34 unmake_blocks_vectorized(x, d, m, n):
+ *   src (m/d * n/d, d, d) -> dst (m, n).
+ * Pure index permutations of `elem_size`-byte elements (1, 2, 4 or 8): bit-exact. */
+int dt_make_blocks(const void* src, int p, int m, int n, int d, int elem_size, void* dst, dt_stream_t stream);
+int dt_unmake_blocks(const void* src, int d, int m, int n, int elem_size, void* dst, dt_stream_t stream);
+
+/* ---- K1: tile gather + normalise ---------------------------------------------------------------
+ * Replaces Tiler.get_batches (deadtrees/deployment/tiler.py:142-145) followed by the per-tile
+ * val_transform loop (scripts/inference.py:94-96, deadtrees/data/deadtreedata.py:148-154) and the
+ * RGB slice (deadtrees/deployment/inference.py:57-59).
+ * Mosaic: uint8, element (y, x, c) at mosaic + y*row_stride + x*pix_stride + c*chan_stride (bytes),
+ * so both band-planar (rasterio) and interleaved layouts are accepted.  Tile t (0 <= t < ntiles)
+ * is grid cell (tile0 + t) of a gy x gx grid, origin (ty*step, tx*step); pixels outside H x W read
+ * as raw 0 (the reference zero-pads the uint8 array, tiler.py:106-111).
+ * out[t, y, x, c] = (u8 - offset[c]) * scale[c] for c < C, 0 for C <= c < c_out; fp32 arithmetic
+ * (subtract, then multiply), rounded to bf16 when out_dtype == DT_BF16.  offset/scale are HOST
+ * pointers to 4 floats. */
+int dt_tile_gather_normalize(const uint8_t* mosaic, int H, int W, int C, int64_t row_stride, int64_t pix_stride,
+                             int64_t chan_stride, int tile, int step, int gx, int tile0, int ntiles,
+                             const float* offset, const float* scale, int c_out, int out_dtype, void* out,
+                             dt_stream_t stream);
+
+/* NCHW fp32 batch (what callers hand to `PyTorchInference.run` / `self.model(img)`) -> NHWC with 4
+ * channels in `out_dtype`; keeps the first C of C_src channels (the RGB slice of
+ * deadtrees/deployment/inference.py:57-59), zero-fills the rest. */
+int dt_pack_input_nchw(const float* x, int N, int C_src, int C, int H, int W, int out_dtype, void* out,
+                       dt_stream_t stream);
+
+/* ---- K12: stitching ----------------------------------------------------------------------------
+ * dt_stitch_mask_u8: Tiler.put_batches at overlap 0 (deadtrees/deployment/tiler.py:147-170 ->
+ * unmake_blocks_vectorized): per-tile class ids (ntiles, T, T) uint8 -> mosaic rows, cropped to H x W.
+ * dt_stitch_blend_argmax (extension): overlapping tiles, logits (ntiles_total, T, T, K)
+ * in `dtype`; for every mosaic pixel of rows [row0, row0+nrows): blended = sum_t w*logit / sum_t w
+ * over covering tiles in (ty, tx) order, w = win[y]*win[x]; mask = first-max argmax; optional fp32
+ * blended output (H, W, K).  `win` is a device array of T floats.  `ty_base` is the tile row stored
+ * first in `logits` (0 for a whole mosaic; > 0 for a tile-row shard of a multi-GPU run). */
+int dt_stitch_mask_u8(const uint8_t* tile_masks, int T, int gx, int tile0, int ntiles, uint8_t* mosaic_mask, int H,
+                      int W, int64_t row_stride, dt_stream_t stream);
+int dt_stitch_blend_argmax(const void* logits, int dtype, int K, int T, int overlap, int gy, int gx, int ty_base,
+                           const float* win, uint8_t* mosaic_mask, float* blended, int H, int W, int row0,
+                           int nrows, dt_stream_t stream);
+
+/* ---- K2-K9: convolutions -----------------------------------------------------------------------
+ * One fused conv = smp `Conv2dReLU` / torchvision BasicBlock conv with eval-mode BatchNorm folded:
+ *   y = act( scale[co] * conv(x)[co] + shift[co] (+ residual) ).
+ * Input is the *virtual* tensor cat([up2(x) if upsample else x, skip], C) — the nearest-x2 upsample
+ * and the concat of the smp UnetDecoder block (deadtrees/network/extra/resunet/decoder.py:41-43 shows
+ * the convention) are never materialised.
+ * Layouts: x (N, H/(upsample?2:1), W/(..), C_x), skip (N, H, W, C_in - C_x), y (N, Ho, Wo, C_out) NHWC.
+ * Weights (packed by the host package):
+ *   dtype DT_F32  : float [R*S][C_in][C_out]
+ *   dtype DT_BF16 : bf16 [C_out][Kpad], k = (r*S + s)*C_in + ci, Kpad = roundup(R*S*C_in, 64);
+ *                   stem (C_in == 4, R == S == 7): k = r*32 + s*4 + ci, Kpad = 256. */
+typedef struct {
+  int32_t N, H, W;      /* batch, spatial size of the (virtual) conv input */
+  int32_t C_in;         /* channels of the virtual input */
+  int32_t C_x;          /* channels taken from x (== C_in when there is no skip) */
+  int32_t upsample;     /* 1: x is stored at half resolution and nearest-upsampled x2 */
+  int32_t C_out, R, S, stride, pad;
+  int32_t relu;         /* apply ReLU */
+  int32_t has_residual; /* add residual (N, Ho, Wo, C_out) before the ReLU */
+  int32_t dtype;        /* DT_BF16: tcgen05 implicit GEMM; DT_F32: CUDA-core check mode */
+  int32_t flags;        /* DT_CONV_* */
+} dt_conv_desc;
+
+enum {
+  DT_CONV_FORCE_GATHER = 1, /* A operand through the generic gather producer even if TMA-eligible */
+  DT_CONV_FORCE_DIRECT = 2  /* CUDA-core direct kernel for bf16 tensors (debug/validation) */
+};
+
+int dt_conv2d_fwd(const dt_conv_desc* desc, const void* x, const void* skip, const void* w, const float* scale,
+                  const float* shift, const void* residual, void* y, dt_stream_t stream);
+
+/* K3: maxpool 3x3 stride 2 pad 1 (torchvision resnet `maxpool`), NHWC, dtype as above. */
+int dt_maxpool3x3s2(const void* x, int N, int H, int W, int C, int dtype, void* y, dt_stream_t stream);
+
+/* ---- K9-K11: segmentation head -------------------------------------------------------------------
+ * smp SegmentationHead conv 3x3 (C -> K, bias) fused with the consumers of the logits:
+ *   logits_nchw (N, K, H, W) fp32   — what `self.model(img)` returns (segmodel.py:214)
+ *   logits_nhwc (N, H, W, K) in `x_dtype` — input of dt_stitch_blend_argmax
+ *   mask (N, H, W) uint8            — `out.argmax(dim=1)` (deployment/inference.py:62), first max wins
+ * any of the three outputs may be NULL.  w: float [9][C][K], bias: float [K]; K <= 4. */
+int dt_head_fwd(const void* x, int x_dtype, int N, int H, int W, int C, int K, const float* w, const float* bias,
+                float* logits_nchw, void* logits_nhwc, uint8_t* mask, dt_stream_t stream);
+
+/* argmax over the class dim of NCHW fp32 logits -> uint8 (first max wins) */
+int dt_argmax_nchw(const float* logits, int N, int K, int H, int W, uint8_t* mask, dt_stream_t stream);
+
+/* ---- K11: losses and metric ----------------------------------------------------------------------
+ * One pass over logits (N, K, H, W) fp32 + labels (N, H, W) int64 computing softmax in registers and
+ * the partial sums every reference loss needs (deadtrees/loss/losses.py:226-247 DiceLoss, :273-291
+ * FocalLoss, deadtrees/loss/gdl.py:10-27 GeneralizedDiceLoss, smp Fscore at segmodel.py:145-149).
+ * sums: double [N][K][4] = { sum p*t, sum p, sum t, sum (1-p)^2 * t * log(p + 1e-10) }
+ * counts: int64 [K][3]  = { tp, sum_pr, sum_gt } with pr = (p > 0.5)   (whole batch)
+ * bad_label: int32 flag set when a label is outside [0, K) (class2one_hot's assert, losses.py:129).
+ * Caller zeroes sums/counts/bad_label. */
+int dt_seg_loss_partials(const float* logits, const int64_t* labels, int N, int K, int H, int W, double* sums,
+                         int64_t* counts, int32_t* bad_label, dt_stream_t stream);
+/* Tiny single-block finalize: turns the partial sums into the reference's scalars and the
+ * coefficient tables the backward pass needs.
+ * dice_mode: 0 none, 1 DiceLoss(idc = 1..K-1) (losses.py:226-247), 2 GeneralizedDiceLoss (gdl.py:10-27);
+ * use_focal: FocalLoss(idc = 0..K-1, gamma = 2) (losses.py:273-291).
+ * out: float [8] = { dice_loss, focal_loss, total_loss, fscore_without_bg, fscore_with_bg, 0, 0, 0 }
+ *      (total = dice + focal as SemSegment.calculate_loss, segmodel.py:169-200; Fscore eps 1e-7)
+ * coef: float [N][K][2] (a, b) with d(dice)/dp[n,k,x] = a*t + b;  focal_scale: float [1] = 1/(sum t + 1e-10)
+ * (0 when focal is off). */
+int dt_seg_loss_finalize(const double* sums, const int64_t* counts, int N, int K, int dice_mode, int use_focal,
+                         float* out, float* coef, float* focal_scale, dt_stream_t stream);
+/* d(total_loss)/d(logits): grad_p = a*t + b - focal_scale * t * (-2(1-p)log(p+1e-10) + (1-p)^2/(p+1e-10)),
+ * then the softmax Jacobian dz_k = p_k (g_k - sum_j g_j p_j); scaled by `upstream`.  grad_logits (N,K,H,W) fp32. */
+int dt_seg_loss_backward(const float* logits, const int64_t* labels, int N, int K, int H, int W, const float* coef,
+                         const float* focal_scale, float upstream, float* grad_logits, dt_stream_t stream);
+
+/* The reference's loss callables take softmax probabilities and an int32 one-hot target
+ * (segmodel.py:215-216); these three entry points serve that API:
+ * dt_class2one_hot: losses.py:124-141 (int32 scatter; bad_label flag = its label-range assert)
+ * dt_softmax_nchw : logits.softmax(dim=1) (segmodel.py:216)
+ * dt_prob_loss_partials: per (n, k) plane { sum p*t, sum p, sum t, sum (1-p)^gamma * t * log(p+1e-10) }
+ *   into double sums [N][K][4] (caller zeroes); target is int32 one-hot or, with target_is_float,
+ *   a float map (the distance maps of SurfaceLoss, losses.py:250-270). */
+int dt_class2one_hot(const int64_t* labels, int N, int K, int H, int W, int32_t* onehot, int32_t* bad_label,
+                     dt_stream_t stream);
+int dt_softmax_nchw(const float* logits, int N, int K, int H, int W, float* probs, dt_stream_t stream);
+int dt_prob_loss_partials(const float* probs, const void* target, int target_is_float, int N, int K, int H, int W,
+                          float gamma, double* sums, dt_stream_t stream);
+
+/* ---- O1: optimizer ------------------------------------------------------------------------------
+ * torch.optim.Adam step (segmodel.py:420-425 defaults) with the Lightning global-norm clip
+ * (configs/trainer/default.yaml:18) folded in: g *= min(1, max_norm / (norm + 1e-6)).
+ * sumsq: device double[1] holding the sum of squares of all grads (dt_sumsq accumulates into it;
+ * the caller zeroes it); max_norm <= 0 disables clipping (sumsq may then be NULL). */
+int dt_sumsq(const float* g, int64_t n, double* sumsq, dt_stream_t stream);
+int dt_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                 float eps, int step, const double* sumsq, float max_norm, dt_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEADTREES_B200_H_ */

@@ -1,0 +1,78 @@
+"""Generate ``tests/golden/*.npz`` by RUNNING THE REFERENCE'S OWN CODE from ``/root/reference``.
+
+TEST INFRASTRUCTURE ONLY.  Run in the build container (``/root/reference`` does not exist on the GPU
+box): ``python oracle/make_golden.py``.  The reference modules are loaded by file path because the
+package ``__init__`` files import absent third-party packages.
+"""
+import importlib.util
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+REF = Path("/root/reference")
+OUT = Path(__file__).resolve().parent.parent / "tests" / "golden"
+
+
+def load(name, rel):
+    spec = importlib.util.spec_from_file_location(name, REF / rel)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def main():
+    OUT.mkdir(parents=True, exist_ok=True)
+    dh = load("ref_data_handling", "deadtrees/utils/data_handling.py")
+    losses = load("ref_losses_mod", "deadtrees/loss/losses.py")
+    gdl = load("ref_gdl_mod", "deadtrees/loss/gdl.py")
+
+    # ---- tiler: make/unmake blocks on seeded arrays (incl. the reference's own test vector) -------
+    rng = np.random.default_rng(1234)
+    cases = {}
+    for i, (p, m, n, d) in enumerate([(3, 4, 4, 2), (4, 32, 48, 8), (1, 64, 16, 16), (4, 96, 64, 32)]):
+        x = rng.integers(0, 256, size=(p, m, n), dtype=np.uint8) if i else np.array(
+            [np.arange(16).reshape(4, 4)] * 3, dtype=np.uint8)
+        blocks = dh.make_blocks_vectorized(x, d)
+        pred = rng.integers(0, 3, size=(blocks.shape[0], d, d), dtype=np.int64)
+        merged = dh.unmake_blocks_vectorized(pred, d, m, n)
+        cases[f"x{i}"], cases[f"d{i}"] = x, np.int64(d)
+        cases[f"blocks{i}"], cases[f"pred{i}"], cases[f"merged{i}"] = blocks, pred, merged
+    cases["ncases"] = np.int64(4)
+    np.savez_compressed(OUT / "tiler_blocks.npz", **cases)
+
+    # ---- losses on seeded probabilities ---------------------------------------------------------
+    g = torch.Generator().manual_seed(1234)
+    out = {}
+    for i, (B, K, H, W) in enumerate([(2, 3, 16, 16), (3, 2, 8, 24), (2, 3, 32, 32)]):
+        logits = torch.randn(B, K, H, W, generator=g) * 2.0
+        mask = torch.randint(0, K, (B, H, W), generator=g)
+        if i == 2:
+            mask[mask == 2] = 1  # class 2 absent -> GDL weight 1e9 path
+        probs = logits.softmax(dim=1)
+        onehot = losses.class2one_hot(mask, K)
+        dist = torch.randn(B, K, H, W, generator=g)
+        fg = list(range(1, K))
+        out[f"logits{i}"], out[f"mask{i}"] = logits.numpy(), mask.numpy()
+        out[f"onehot{i}"] = onehot.numpy()
+        out[f"dice{i}"] = losses.DiceLoss(idc=fg)(probs, onehot).numpy()
+        out[f"focal{i}"] = losses.FocalLoss(idc=list(range(K)), gamma=2)(probs, onehot).numpy()
+        out[f"gdl{i}"] = gdl.GeneralizedDiceLoss()(probs, onehot).numpy()
+        out[f"dist{i}"] = dist.numpy()
+        out[f"surface{i}"] = losses.BoundaryLoss(idc=fg)(probs, dist).numpy()
+        # gradients w.r.t. logits through the reference code (autograd), for the backward kernels
+        for name, fn in (("dice", lambda p: losses.DiceLoss(idc=fg)(p, onehot)),
+                         ("focal", lambda p: losses.FocalLoss(idc=list(range(K)), gamma=2)(p, onehot)),
+                         ("gdl", lambda p: gdl.GeneralizedDiceLoss()(p, onehot))):
+            z = logits.clone().requires_grad_(True)
+            fn(z.softmax(dim=1)).backward()
+            out[f"grad_{name}{i}"] = z.grad.numpy()
+    out["ncases"] = np.int64(3)
+    np.savez_compressed(OUT / "losses.npz", **out)
+    print("wrote", sorted(p.name for p in OUT.glob("*.npz")))
+
+
+if __name__ == "__main__":
+    main()

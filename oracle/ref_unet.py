@@ -1,0 +1,197 @@
+"""Oracle: CPU fp32 restatement of ``smp.Unet(encoder_name="resnet34")``.
+
+TEST INFRASTRUCTURE ONLY (see ``oracle/__init__.py``).
+
+The reference builds its model as ``smp.Unet(**network_conf, classes=n)``
+(``deadtrees/network/segmodel.py:62-63,79-85``) from the third-party package
+``segmentation_models_pytorch>=0.2.1`` (``setup.py:47``; unpinned, absent from
+``/root/reference``, not installable offline).  This file restates the published
+architecture with smp's state-dict key names so one state-dict feeds both the
+oracle and the CUDA engine:
+
+* encoder = torchvision ``resnet34`` trunk without avgpool/fc, returning the six
+  feature maps ``[x, relu(bn1(conv1)), layer1(maxpool), layer2, layer3, layer4]``
+* decoder = five blocks ``nearest x2 -> cat([x, skip]) -> Conv3x3+BN+ReLU -> Conv3x3+BN+ReLU``
+  (conventions evidenced in-tree by the vendored smp forks:
+  ``deadtrees/network/extra/resunet/decoder.py:41-43,93-104,121-134`` and
+  ``deadtrees/network/extra/modules.py:53-92``)
+* head = ``Conv2d(16 -> K, 3, padding=1)`` with bias, no activation
+  (``deadtrees/network/extra/efficientunetplusplus/model.py:85-90`` shows kernel 3).
+
+PARITY: unpinned by the reference's own tests (they only check output shapes and
+need an absent checkpoint, ``tests/test_inference.py:78-102``).  Pinned here against
+torchvision's ``resnet34`` (``tests/test_oracle.py``) and the documented parameter count.
+"""
+from __future__ import annotations
+
+from typing import List, Sequence
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+RESNET34_LAYERS = (3, 4, 6, 3)
+RESNET34_PLANES = (64, 128, 256, 512)
+
+
+class BasicBlock(nn.Module):
+    """torchvision BasicBlock: conv3x3-BN-ReLU-conv3x3-BN, + identity, ReLU (all convs bias-free)."""
+
+    def __init__(self, inplanes: int, planes: int, stride: int):
+        super().__init__()
+        self.conv1 = nn.Conv2d(inplanes, planes, 3, stride, 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(planes)
+        self.relu = nn.ReLU(inplace=True)
+        self.conv2 = nn.Conv2d(planes, planes, 3, 1, 1, bias=False)
+        self.bn2 = nn.BatchNorm2d(planes)
+        self.downsample = None
+        if stride != 1 or inplanes != planes:
+            self.downsample = nn.Sequential(
+                nn.Conv2d(inplanes, planes, 1, stride, bias=False), nn.BatchNorm2d(planes)
+            )
+
+    def forward(self, x):
+        identity = x if self.downsample is None else self.downsample(x)
+        out = self.relu(self.bn1(self.conv1(x)))
+        out = self.bn2(self.conv2(out))
+        return self.relu(out + identity)
+
+
+class ResNet34Encoder(nn.Module):
+    """smp ``ResNetEncoder`` (resnet34, depth 5): six feature maps, strides 1,2,4,8,16,32."""
+
+    out_channels = (None, 64, 64, 128, 256, 512)
+
+    def __init__(self, in_channels: int = 3):
+        super().__init__()
+        self.conv1 = nn.Conv2d(in_channels, 64, 7, 2, 3, bias=False)
+        self.bn1 = nn.BatchNorm2d(64)
+        self.relu = nn.ReLU(inplace=True)
+        self.maxpool = nn.MaxPool2d(3, 2, 1)
+        inplanes = 64
+        for li, (planes, nblk) in enumerate(zip(RESNET34_PLANES, RESNET34_LAYERS), start=1):
+            blocks = []
+            for b in range(nblk):
+                stride = 2 if (b == 0 and li > 1) else 1
+                blocks.append(BasicBlock(inplanes, planes, stride))
+                inplanes = planes
+            setattr(self, f"layer{li}", nn.Sequential(*blocks))
+
+    def forward(self, x) -> List[torch.Tensor]:
+        feats = [x]
+        x = self.relu(self.bn1(self.conv1(x)))
+        feats.append(x)
+        x = self.layer1(self.maxpool(x))
+        feats.append(x)
+        for name in ("layer2", "layer3", "layer4"):
+            x = getattr(self, name)(x)
+            feats.append(x)
+        return feats
+
+
+class Conv2dReLU(nn.Sequential):
+    """smp ``Conv2dReLU`` with batchnorm: Conv(bias=False) + BN + ReLU (modules.py:53-92)."""
+
+    def __init__(self, cin: int, cout: int):
+        super().__init__(
+            nn.Conv2d(cin, cout, 3, padding=1, bias=False), nn.BatchNorm2d(cout), nn.ReLU(inplace=True)
+        )
+
+
+class DecoderBlock(nn.Module):
+    def __init__(self, cin: int, cskip: int, cout: int):
+        super().__init__()
+        self.conv1 = Conv2dReLU(cin + cskip, cout)
+        self.conv2 = Conv2dReLU(cout, cout)
+
+    def forward(self, x, skip=None):
+        x = F.interpolate(x, scale_factor=2, mode="nearest")
+        if skip is not None:
+            x = torch.cat([x, skip], dim=1)
+        return self.conv2(self.conv1(x))
+
+
+class UnetDecoder(nn.Module):
+    def __init__(self, encoder_channels: Sequence[int], decoder_channels: Sequence[int]):
+        super().__init__()
+        enc = list(encoder_channels[1:])[::-1]  # drop the full-res skip, deepest first
+        in_ch = [enc[0]] + list(decoder_channels[:-1])
+        skip_ch = enc[1:] + [0]
+        self.blocks = nn.ModuleList(
+            DecoderBlock(i, s, o) for i, s, o in zip(in_ch, skip_ch, decoder_channels)
+        )
+
+    def forward(self, *features):
+        features = features[1:][::-1]
+        x, skips = features[0], features[1:]
+        for i, blk in enumerate(self.blocks):
+            x = blk(x, skips[i] if i < len(skips) else None)
+        return x
+
+
+class Unet(nn.Module):
+    """Restated ``smp.Unet``; attributes ``encoder / decoder / segmentation_head`` as in smp."""
+
+    def __init__(
+        self,
+        encoder_name: str = "resnet34",
+        encoder_depth: int = 5,
+        encoder_weights=None,
+        decoder_channels: Sequence[int] = (256, 128, 64, 32, 16),
+        in_channels: int = 3,
+        classes: int = 3,
+    ):
+        super().__init__()
+        if encoder_name != "resnet34" or encoder_depth != 5 or encoder_weights is not None:
+            raise NotImplementedError("oracle restates resnet34 / depth 5 / random init only")
+        self.encoder = ResNet34Encoder(in_channels)
+        self.decoder = UnetDecoder((in_channels, 64, 64, 128, 256, 512), decoder_channels)
+        self.segmentation_head = nn.Sequential(
+            nn.Conv2d(decoder_channels[-1], classes, 3, padding=1), nn.Identity(), nn.Identity()
+        )
+
+    def forward(self, x):
+        return self.segmentation_head(self.decoder(*self.encoder(x)))
+
+
+def initialize_weights(m: nn.Module) -> None:
+    """Reference init for ``encoder_weights=None`` (``segmodel.py:87-89,432-438``)."""
+    if getattr(m, "bias", None) is not None:
+        nn.init.constant_(m.bias, 0)
+    if isinstance(m, (nn.Conv2d, nn.Linear)):
+        nn.init.kaiming_normal_(m.weight)
+    for c in m.children():
+        initialize_weights(c)
+
+
+def build_reference_unet(in_channels: int = 3, classes: int = 3, seed: int = 0,
+                         randomize_bn: bool = True) -> Unet:
+    """Random-init oracle model as SURVEY §8d prescribes (shared state-dict with the CUDA engine)."""
+    g = torch.Generator().manual_seed(seed)
+    state = torch.random.get_rng_state()
+    torch.manual_seed(seed)
+    try:
+        model = Unet(in_channels=in_channels, classes=classes)
+        model.apply(initialize_weights)
+    finally:
+        torch.random.set_rng_state(state)
+    if randomize_bn:
+        # exercise BN folding: non-trivial running stats and affine parameters
+        for mod in model.modules():
+            if isinstance(mod, nn.BatchNorm2d):
+                mod.running_mean.copy_(torch.randn(mod.num_features, generator=g) * 0.1)
+                mod.running_var.copy_(torch.rand(mod.num_features, generator=g) + 0.5)
+                mod.weight.data.copy_(1.0 + 0.1 * torch.randn(mod.num_features, generator=g))
+                mod.bias.data.copy_(0.1 * torch.randn(mod.num_features, generator=g))
+    return model.eval()
+
+
+def run_inference(model: nn.Module, x: torch.Tensor, channels: int) -> torch.Tensor:
+    """``PyTorchInference.run`` semantics (``deployment/inference.py:47-62``) on CPU."""
+    if x.dim() == 3:
+        x = x.unsqueeze(0)
+    with torch.no_grad():
+        if channels == 3 and x.shape[1] == 4:
+            x = x[:, 0:3]
+        out = model(x)
+    return out.argmax(dim=1).squeeze()
