@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""Benchmark of the deadtrees hot path on B200: whole-mosaic Unet-resnet34 inference (BASELINE cfg 2/3).
+
+    python bench.py --gpus N --steps K --warmup W            # this framework (hand-written CUDA)
+    python bench.py --impl reference --gpus N ...            # the reference's CPU path (oracle port) on host cores
+
+One step = one pass of the hot path over the synthetic 10 000 x 10 000 RGB uint8 mosaic (tile 256,
+overlap 32 -> 45 x 45 = 2025 tiles): gather+normalise -> Unet -> head -> blended stitch -> uint8 mask.
+N > 1 (torchrun): the same mosaic sharded by tile rows, one boundary-logits send per shard boundary,
+masks gathered on rank 0; timing = max over ranks of the CUDA-event time, barrier on both sides.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "unet_mosaic_inference_tiles_per_s"
+UNIT = "tiles/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--size", type=int, default=10000, help="mosaic side in pixels")
+    ap.add_argument("--tile", type=int, default=256)
+    ap.add_argument("--overlap", type=int, default=32)
+    ap.add_argument("--batch-tiles", type=int, default=135)
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--cpu-sample-tiles", type=int, default=32)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-profile", action="store_true", help="skip the per-kernel CUDA-event instrumentation")
+    return ap.parse_args()
+
+
+def workload_config(a, n_tiles):
+    return {"workload": f"cfg2: sliding-window Unet-resnet34 inference over a synthetic {a.size}x{a.size} RGB uint8 "
+                        f"mosaic, tile {a.tile}, overlap {a.overlap} ({n_tiles} tiles), blended stitch",
+            "mosaic": [a.size, a.size, 3], "tile": a.tile, "overlap": a.overlap, "tiles": n_tiles,
+            "batch_tiles": a.batch_tiles, "classes": 3, "in_channels": 3,
+            "l2_policy": "inputs larger than L2 (300 MB mosaic, >1 GB of activations per step); no explicit flush"}
+
+
+def synthetic_mosaic(size: int, device, seed: int = 1234) -> torch.Tensor:
+    """low-frequency pattern + noise so the predicted masks are not constant."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    yy = torch.arange(size, device=device, dtype=torch.float32)[:, None]
+    xx = torch.arange(size, device=device, dtype=torch.float32)[None, :]
+    out = torch.empty((size, size, 3), dtype=torch.uint8, device=device)
+    for c, (fy, fx, amp) in enumerate([(97.0, 131.0, 80.0), (61.0, 173.0, 70.0), (149.0, 83.0, 90.0)]):
+        base = 127.0 + amp * torch.sin(yy / fy) * torch.cos(xx / fx)
+        noise = torch.randn((size, size), device=device, generator=g) * 20.0
+        out[..., c] = (base + noise).clamp_(0, 255).to(torch.uint8)
+    return out
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return {"hbm_gbs": d["hbm_gbs"], "tflops": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "source": "MEASURED_PEAKS.json (sustained bf16, copy HBM)"}
+    return {"hbm_gbs": 6650.0, "tflops": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler(threading.Thread):
+    """samples SM clock + throttle reasons during the timed region (pynvml; nvidia-smi as a fallback)."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt = threading.Event()
+        self.backend = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.backend = "nvml"
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "hw_power_brake": getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80)}
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        med = statistics.median(self.samples) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples), "backend": self.backend}
+
+
+# ---------------------------------------------------------------------------------------------------
+def cpu_reference_flow(model, tiles_u8: np.ndarray, tile: int):
+    """the reference's per-batch flow on the CPU (scripts/inference.py:93-105): per-tile normalise,
+    forward, argmax; returns class ids."""
+    from oracle import ref_normalize
+    x = torch.from_numpy(np.stack([ref_normalize.val_transform(t) for t in tiles_u8]))
+    with torch.no_grad():
+        return model(x).argmax(dim=1)
+
+
+def run_cpu_sample(a, n_tiles_sample: int, repeats: int, warm: int):
+    """times the oracle port (fp32 torch CPU, all host threads) on a bounded sample of the workload."""
+    from oracle import ref_tiler, ref_unet
+    torch.set_num_threads(os.cpu_count() or 1)
+    model = ref_unet.build_reference_unet(3, 3, seed=0)
+    rng = np.random.default_rng(1234)
+    side = int(np.ceil(np.sqrt(n_tiles_sample)))
+    crop = rng.integers(0, 256, size=(side * a.tile, side * a.tile, 3), dtype=np.uint8)
+    tiles = ref_tiler.extract_tiles(crop, a.tile, 0)[:n_tiles_sample]
+    times = []
+    for i in range(warm + repeats):
+        t0 = time.perf_counter()
+        cpu_reference_flow(model, tiles, a.tile)
+        dt = time.perf_counter() - t0
+        if i >= warm:
+            times.append(dt)
+    return n_tiles_sample / min(times), times
+
+
+def main_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from deadtrees_b200.deployment.inference import overlap_grid
+    gy, gx = overlap_grid(a.size, a.size, a.tile, a.overlap)
+    n_sample = a.cpu_sample_tiles
+    tps, times = run_cpu_sample(a, n_sample, repeats=a.steps, warm=a.warmup)
+    ms = 1000.0 * statistics.mean(times)
+    sample = f"{n_sample} tiles of {a.tile}x{a.tile} per step through the oracle port of the reference flow " \
+             f"(normalise -> Unet fp32 -> argmax), torch CPU, {torch.get_num_threads()} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": tps, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": workload_config(a, gy * gx),
+        "mpixel_per_s": tps * a.tile * a.tile / 1e6,
+        "cpu_baseline": {"value": tps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": tps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ---------------------------------------------------------------------------------------------------
+def main_b200(a):
+    import torch.distributed as dist
+    from deadtrees_b200 import ops
+    from deadtrees_b200._lib import require_device
+    from deadtrees_b200.deployment.inference import MosaicInference, overlap_grid
+    from deadtrees_b200.engine import UnetEngine, conv_flops_per_tile
+    from deadtrees_b200.sharding import make_halo_hook, split_tile_rows
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    require_device()
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    # random-init weights of the reference architecture (seeded; the oracle is only the INITIALISER here,
+    # so that bench, tests and the CPU baseline share one state-dict) -- built on CPU, then handed over
+    from deadtrees_b200.network.segmodel import SemSegment
+    net = dict(architecture="unet", encoder_name="resnet34", encoder_depth=5, encoder_weights=None,
+               decoder_channels=[256, 128, 64, 32, 16], losses=["DICE", "FOCAL"], classes=["bg", "a", "b"],
+               in_channels=3, precision=a.precision)
+    torch.manual_seed(0)
+    seg = SemSegment(net, dict(learning_rate=3e-4, cosineannealing_tmax=10)).eval()
+    g = torch.Generator().manual_seed(0)
+    for mod in seg.modules():
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.running_mean.copy_(torch.randn(mod.num_features, generator=g) * 0.1)
+            mod.running_var.copy_(torch.rand(mod.num_features, generator=g) + 0.5)
+    seg.cuda()
+    engine = seg.model.engine()
+
+    H = W = a.size
+    T, ov = a.tile, a.overlap
+    gy, gx = overlap_grid(H, W, T, ov)
+    n_tiles = gy * gx
+    parts = split_tile_rows(gy, world)
+    r0, r1 = parts[rank]
+    mi = MosaicInference(engine, tile=T, overlap=ov, batch_tiles=a.batch_tiles)
+    hook = make_halo_hook(T, ov, rank, world, has_rows=[b > c for c, b in parts]) if world > 1 else None
+    mosaic = synthetic_mosaic(a.size, dev)
+    host_mosaic = torch.empty(mosaic.shape, dtype=torch.uint8, pin_memory=True)
+    host_mosaic.copy_(mosaic)
+    host_mask = torch.empty((H, W), dtype=torch.uint8, pin_memory=True)
+    mask = torch.zeros((H, W), dtype=torch.uint8, device=dev)
+    y0, y1 = mi.owned_rows(H, T, ov, gy, r0, r1)
+    rows = [mi.owned_rows(H, T, ov, gy, c, b) for c, b in parts]
+
+    def gather_masks():
+        if world == 1:
+            return
+        if rank == 0:
+            reqs = [dist.irecv(mask[rows[k][0]: rows[k][1]], src=k) for k in range(1, world) if rows[k][1] > rows[k][0]]
+            for r in reqs:
+                r.wait()
+        elif y1 > y0:
+            dist.isend(mask[y0:y1], dst=0).wait()
+
+    def step_device():
+        if r1 > r0:
+            mi.run(mosaic, "hwc", tile_rows=(r0, r1) if world > 1 else None, out=mask, halo_hook=hook)
+        gather_masks()
+
+    def step_e2e():
+        # host buffers in and out: H2D of the uint8 mosaic rows this shard needs, D2H of its mask rows
+        s = T - ov
+        ya, yb = (0, H) if world == 1 else (min(H, r0 * s), min(H, (r1 - 1) * s + T))
+        if r1 > r0:
+            mosaic[ya:yb].copy_(host_mosaic[ya:yb], non_blocking=True)
+            mi.run(mosaic, "hwc", tile_rows=(r0, r1) if world > 1 else None, out=mask, halo_hook=hook)
+            host_mask[y0:y1].copy_(mask[y0:y1], non_blocking=True)
+        return (yb - ya) * W * 3, (y1 - y0) * W
+
+    def timed(fn, steps, profile=False):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ops.PROFILE = {} if profile else None
+        l0 = ops.LAUNCHES
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = e0.elapsed_time(e1)
+        prof, ops.PROFILE = ops.PROFILE, None
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, ops.LAUNCHES - l0, prof
+
+    for _ in range(max(a.warmup, 3)):
+        step_device()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms_total, launches, prof = timed(step_device, a.steps, profile=not a.no_profile)
+    clocks = sampler.stop()
+    ms_step = ms_total / a.steps
+    value = n_tiles / (ms_step / 1e3)
+
+    # end-to-end through the public pipeline with host buffers (pinned), same number of steps
+    for _ in range(2):
+        step_e2e()
+    ms_e2e_total, _, _ = timed(step_e2e, a.steps)
+    h2d, d2h = step_e2e()
+    torch.cuda.synchronize()
+    ms_e2e = ms_e2e_total / a.steps
+
+    pk = peaks()
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": a.precision if a.precision == "bf16" else "f32", "data": "synthetic",
+        "config": dict(workload_config(a, n_tiles), parallelism=f"tile-row shards x{world}"),
+        "mpixel_per_s": value * T * T / 1e6, "mosaic_mpixel_per_s": H * W / 1e6 / (ms_step / 1e3),
+        "e2e": {"value": n_tiles / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e},
+        "gpu_launches": int(launches), "clocks": clocks,
+    }
+    if prof:
+        def agg(kind):
+            evs = prof.get(kind, [])
+            t = sum(e0.elapsed_time(e1) for e0, e1, _ in evs) / 1e3
+            w = sum(wk for _, _, wk in evs)
+            return t, w, len(evs)
+        tc, wc, nc = agg("conv")
+        tg, wg, ng = agg("gather")
+        ts, ws, ns = agg("stitch")
+        if tc > 0:
+            ach = wc / tc / 1e12
+            out["roofline"] = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit GEMM, all conv layers)",
+                               "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"],
+                               "traffic": None, "launches": nc, "share_of_step": tc * 1e3 / ms_total,
+                               "flops_per_tile": conv_flops_per_tile(T, 3, 3), "peak_source": pk["source"]}
+        hb = {}
+        if tg > 0:
+            hb["gather_normalize"] = {"achieved": wg / tg / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                                      "frac": wg / tg / 1e9 / pk["hbm_gbs"], "launches": ng}
+        if ts > 0:
+            hb["stitch"] = {"achieved": ws / ts / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                            "frac": ws / ts / 1e9 / pk["hbm_gbs"], "launches": ns}
+        out["roofline_hbm"] = hb
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        tps, times = run_cpu_sample(a, a.cpu_sample_tiles, repeats=3, warm=1)
+        out["cpu_baseline"] = {"value": tps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                               "sample": f"{a.cpu_sample_tiles} tiles of {T}x{T} (normalise -> Unet fp32 -> argmax) "
+                                         f"through the oracle port, best of 3"}
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        main_reference(args)
+    else:
+        main_b200(args)

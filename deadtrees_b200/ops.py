@@ -11,9 +11,39 @@ from typing import Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import DT_BF16, DT_F32, ConvDesc, check, load, ptr, stream_ptr
+from ._lib import DT_BF16, DT_F32, ConvDesc, load, ptr, stream_ptr
 
 ACT_DTYPES = {DT_BF16: torch.bfloat16, DT_F32: torch.float32}
+
+# number of kernel launches issued through this module (bench.py reports it as `gpu_launches`);
+LAUNCHES = 0
+# bench instrumentation: when PROFILE is a dict, conv / gather / stitch launches are bracketed by CUDA
+# events on the launching stream and appended as (kind, start, end, algorithmic_work) tuples
+PROFILE = None
+
+
+class _Timed:
+    def __init__(self, kind: str, work: float):
+        self.kind, self.work = kind, work
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE is not None and exc[0] is None:
+            self.e1.record()
+            PROFILE.setdefault(self.kind, []).append((self.e0, self.e1, self.work))
+        return False
+
+
+def check(rc: int) -> None:
+    global LAUNCHES
+    _lib.check(rc)
+    LAUNCHES += 1
 
 
 def _dt(t: torch.Tensor) -> int:
@@ -74,9 +104,11 @@ def tile_gather_normalize(mosaic: torch.Tensor, layout: str, channels: int, tile
         out = torch.empty((ntiles, tile, tile, 4), dtype=dtype, device=mosaic.device)
     off = (C.c_float * 4)(*[float(v) for v in list(offset)[:channels]] + [0.0] * (4 - channels))
     sc = (C.c_float * 4)(*[float(v) for v in list(scale)[:channels]] + [0.0] * (4 - channels))
-    check(load().dt_tile_gather_normalize(mosaic.data_ptr(), H, W, channels, rs, ps, cs, tile, tile - overlap,
-                                          grid[1], tile0, ntiles, off, sc, 4, _dt(out), out.data_ptr(),
-                                          stream_ptr()))
+    # algorithmic bytes: N*T^2*C*(1 B in + elem out)
+    with _Timed("gather", float(ntiles) * tile * tile * channels * (1 + out.element_size())):
+        check(load().dt_tile_gather_normalize(mosaic.data_ptr(), H, W, channels, rs, ps, cs, tile, tile - overlap,
+                                              grid[1], tile0, ntiles, off, sc, 4, _dt(out), out.data_ptr(),
+                                              stream_ptr()))
     return out
 
 
@@ -96,8 +128,9 @@ def stitch_mask(tile_masks: torch.Tensor, grid_x: int, tile0: int, mosaic_mask: 
     tile_masks = _cuda(tile_masks, "tile_masks")
     ntiles, T, _ = tile_masks.shape
     H, W = mosaic_mask.shape
-    check(load().dt_stitch_mask_u8(tile_masks.data_ptr(), T, grid_x, tile0, ntiles, mosaic_mask.data_ptr(), H, W,
-                                   mosaic_mask.stride(0), stream_ptr()))
+    with _Timed("stitch", 2.0 * ntiles * T * T):  # 2 B / pixel
+        check(load().dt_stitch_mask_u8(tile_masks.data_ptr(), T, grid_x, tile0, ntiles, mosaic_mask.data_ptr(), H,
+                                       W, mosaic_mask.stride(0), stream_ptr()))
 
 
 def stitch_blend_argmax(logits: torch.Tensor, overlap: int, grid: Tuple[int, int], win: torch.Tensor,
@@ -108,9 +141,11 @@ def stitch_blend_argmax(logits: torch.Tensor, overlap: int, grid: Tuple[int, int
     _, T, _, K = logits.shape
     H, W = mosaic_mask.shape
     nrows = H - row0 if nrows is None else nrows
-    check(load().dt_stitch_blend_argmax(logits.data_ptr(), _dt(logits), K, T, overlap, grid[0], grid[1],
-                                        ty_base, win.data_ptr(), mosaic_mask.data_ptr(), ptr(blended), H, W, row0, nrows,
-                                        stream_ptr()))
+    # algorithmic bytes: every logit of the shard once + 1 B per output pixel
+    with _Timed("stitch", float(logits.numel()) * logits.element_size() + float(nrows) * W):
+        check(load().dt_stitch_blend_argmax(logits.data_ptr(), _dt(logits), K, T, overlap, grid[0], grid[1],
+                                            ty_base, win.data_ptr(), mosaic_mask.data_ptr(), ptr(blended), H, W,
+                                            row0, nrows, stream_ptr()))
 
 
 # ---- network ---------------------------------------------------------------------------------
@@ -118,15 +153,16 @@ def stitch_blend_argmax(logits: torch.Tensor, overlap: int, grid: Tuple[int, int
 def conv2d(x: torch.Tensor, w: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, *, N: int, H: int, W: int,
            C_in: int, C_x: int, C_out: int, R: int, S: int, stride: int, pad: int, relu: bool,
            skip: Optional[torch.Tensor] = None, upsample: bool = False, residual: Optional[torch.Tensor] = None,
-           out: Optional[torch.Tensor] = None, flags: int = 0) -> torch.Tensor:
+           out: Optional[torch.Tensor] = None, flags: int = 0, algo_cin: Optional[int] = None) -> torch.Tensor:
     Ho = (H + 2 * pad - R) // stride + 1
     Wo = (W + 2 * pad - S) // stride + 1
     if out is None:
         out = torch.empty((N, Ho, Wo, C_out), dtype=x.dtype, device=x.device)
     d = ConvDesc(N, H, W, C_in, C_x, int(upsample), C_out, R, S, stride, pad, int(relu), int(residual is not None),
                  _dt(x), flags)
-    check(load().dt_conv2d_fwd(C.byref(d), x.data_ptr(), ptr(skip), w.data_ptr(), scale.data_ptr(), shift.data_ptr(),
-                               ptr(residual), out.data_ptr(), stream_ptr()))
+    with _Timed("conv", 2.0 * N * Ho * Wo * C_out * (algo_cin or C_in) * R * S):
+        check(load().dt_conv2d_fwd(C.byref(d), x.data_ptr(), ptr(skip), w.data_ptr(), scale.data_ptr(),
+                                   shift.data_ptr(), ptr(residual), out.data_ptr(), stream_ptr()))
     return out
 
 

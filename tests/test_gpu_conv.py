@@ -1,0 +1,158 @@
+"""GPU parity: fused convolutions (fp32 check mode and the tcgen05 bf16 path) vs torch CPU fp32."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from deadtrees_b200 import ops
+from deadtrees_b200._lib import CONV_FORCE_DIRECT, CONV_FORCE_GATHER
+from deadtrees_b200.engine import pack_weight
+from gpu_util import report, to_nchw
+
+pytestmark = pytest.mark.gpu
+
+# name, N, H(in, virtual), C_x, C_skip, C_out, R, stride, pad, upsample, residual, relu
+LAYERS = [
+    ("l1.conv 64->64 @64 (TMA)", 2, 64, 64, 0, 64, 3, 1, 1, False, True, True),
+    ("l2.conv 128->128 @32 (TMA)", 4, 32, 128, 0, 128, 3, 1, 1, False, False, True),
+    ("l3.conv 256->256 @16 (TMA)", 8, 16, 256, 0, 256, 3, 1, 1, False, True, True),
+    ("l4.conv 512->512 @8 (TMA multi-image box)", 6, 8, 512, 0, 512, 3, 1, 1, False, True, True),
+    ("d2.conv2 64->64 @128 wide rows", 1, 128, 64, 0, 64, 3, 1, 1, False, False, True),
+    ("l2.0.conv1 64->128 s2", 2, 64, 64, 0, 128, 3, 2, 1, False, False, True),
+    ("l2.0.downsample 1x1 s2", 2, 64, 64, 0, 128, 1, 2, 0, False, False, False),
+    ("l4.0.conv1 256->512 s2 @16", 4, 16, 256, 0, 512, 3, 2, 1, False, False, True),
+    ("d0.conv1 up(512)+256 -> 256 @16", 2, 16, 512, 256, 256, 3, 1, 1, True, False, True),
+    ("d3.conv1 up(64)+64 -> 32 @128", 1, 128, 64, 64, 32, 3, 1, 1, True, False, True),
+    ("d3.conv2 32->32 @128", 1, 128, 32, 0, 32, 3, 1, 1, False, False, True),
+    ("d4.conv1 up(32) -> 16 @64", 2, 64, 32, 0, 16, 3, 1, 1, True, False, True),
+    ("d4.conv2 16->16 @64", 2, 64, 16, 0, 16, 3, 1, 1, False, False, True),
+    ("ragged M tail 64->64 @24", 3, 24, 64, 0, 64, 3, 1, 1, False, True, True),
+]
+
+
+def make_case(case, seed=0):
+    name, N, H, Cx, Cs, Co, R, stride, pad, ups, res, relu = case
+    g = torch.Generator().manual_seed(seed)
+    Hx = H // 2 if ups else H
+    x = torch.randn(N, Cx, Hx, Hx, generator=g)
+    skip = torch.randn(N, Cs, H, H, generator=g) if Cs else None
+    w = torch.randn(Co, Cx + Cs, R, R, generator=g) * (2.0 / ((Cx + Cs) * R * R)) ** 0.5
+    scale = 1.0 + 0.1 * torch.randn(Co, generator=g)
+    shift = 0.1 * torch.randn(Co, generator=g)
+    Ho = (H + 2 * pad - R) // stride + 1
+    residual = torch.randn(N, Co, Ho, Ho, generator=g) if res else None
+    return x, skip, w, scale, shift, residual
+
+
+def reference(case, x, skip, w, scale, shift, residual):
+    name, N, H, Cx, Cs, Co, R, stride, pad, ups, res, relu = case
+    xin = F.interpolate(x, scale_factor=2, mode="nearest") if ups else x
+    if skip is not None:
+        xin = torch.cat([xin, skip], dim=1)
+    y = F.conv2d(xin, w, None, stride, pad) * scale[None, :, None, None] + shift[None, :, None, None]
+    if residual is not None:
+        y = y + residual
+    return F.relu(y) if relu else y
+
+
+def run_cuda(case, x, skip, w, scale, shift, residual, dtype, flags=0):
+    name, N, H, Cx, Cs, Co, R, stride, pad, ups, res, relu = case
+    nhwc = lambda t: None if t is None else t.permute(0, 2, 3, 1).contiguous().to(dtype).cuda()
+    wp = pack_weight(w, "fp32" if dtype == torch.float32 else "bf16", False, "cuda")
+    y = ops.conv2d(nhwc(x), wp, scale.cuda(), shift.cuda(), N=N, H=H, W=H, C_in=Cx + Cs, C_x=Cx, C_out=Co, R=R, S=R,
+                   stride=stride, pad=pad, relu=relu, skip=nhwc(skip), upsample=ups, residual=nhwc(residual),
+                   flags=flags)
+    torch.cuda.synchronize()
+    return to_nchw(y)
+
+
+def bf16_round(*ts):
+    return [None if t is None else t.to(torch.bfloat16).float() for t in ts]
+
+
+@pytest.mark.parametrize("case", LAYERS, ids=[c[0] for c in LAYERS])
+def test_conv_fp32_check_mode(case):
+    args = make_case(case)
+    ref = reference(case, *args)
+    got = run_cuda(case, *args, dtype=torch.float32)
+    err, rel = report(case[0] + " fp32", got, ref)
+    assert err < 1e-4
+
+
+@pytest.mark.parametrize("case", LAYERS, ids=[c[0] for c in LAYERS])
+def test_conv_bf16_direct_validation_path(case):
+    """CUDA-core kernel on bf16 tensors with the tensor-core weight packing (validates the packing)."""
+    x, skip, w, scale, shift, residual = make_case(case)
+    xb, sb, wb, rb = bf16_round(x, skip, w, residual)
+    ref = reference(case, xb, sb, wb, scale, shift, rb)
+    got = run_cuda(case, x, skip, w, scale, shift, residual, dtype=torch.bfloat16, flags=CONV_FORCE_DIRECT)
+    err, rel = report(case[0] + " bf16-direct", got, ref)
+    assert rel < 1e-2  # output rounding to bf16 only
+
+
+@pytest.mark.parametrize("case", LAYERS, ids=[c[0] for c in LAYERS])
+def test_conv_tcgen05(case):
+    """tensor-core path: bf16 operands, fp32 accumulate; reference uses the same bf16-rounded operands."""
+    x, skip, w, scale, shift, residual = make_case(case)
+    xb, sb, wb, rb = bf16_round(x, skip, w, residual)
+    ref = reference(case, xb, sb, wb, scale, shift, rb)
+    got = run_cuda(case, x, skip, w, scale, shift, residual, dtype=torch.bfloat16)
+    err, rel = report(case[0] + " tcgen05", got, ref)
+    assert rel < 1e-2
+    # the generic gather producer must give the same bits as the TMA producer (same MMA sequence)
+    got_g = run_cuda(case, x, skip, w, scale, shift, residual, dtype=torch.bfloat16, flags=CONV_FORCE_GATHER)
+    assert torch.equal(got, got_g)
+
+
+def test_stem_tcgen05_and_fp32():
+    g = torch.Generator().manual_seed(3)
+    N, T, C = 2, 64, 3
+    x = torch.randn(N, C, T, T, generator=g)
+    w = torch.randn(64, C, 7, 7, generator=g) * (2.0 / (C * 49)) ** 0.5
+    scale, shift = 1.0 + 0.1 * torch.randn(64, generator=g), 0.1 * torch.randn(64, generator=g)
+    for dtype, tol_rel in ((torch.float32, 1e-5), (torch.bfloat16, 1e-2)):
+        rnd = (lambda t: t) if dtype == torch.float32 else (lambda t: t.to(torch.bfloat16).float())
+        ref = F.relu(F.conv2d(rnd(x), rnd(w), None, 2, 3) * scale[None, :, None, None] + shift[None, :, None, None])
+        x4 = torch.zeros(N, T, T, 4); x4[..., :C] = x.permute(0, 2, 3, 1)
+        wp = pack_weight(w, "fp32" if dtype == torch.float32 else "bf16", True, "cuda")
+        y = ops.conv2d(x4.to(dtype).cuda(), wp, scale.cuda(), shift.cuda(), N=N, H=T, W=T, C_in=4, C_x=4, C_out=64,
+                       R=7, S=7, stride=2, pad=3, relu=True)
+        torch.cuda.synchronize()
+        err, rel = report(f"stem {dtype}", to_nchw(y), ref)
+        assert rel < tol_rel
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_maxpool(dtype):
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(3, 64, 34, 34, generator=g).to(dtype).float()
+    ref = F.max_pool2d(x, 3, 2, 1)
+    y = ops.maxpool3x3s2(x.permute(0, 2, 3, 1).contiguous().to(dtype).cuda())
+    assert torch.equal(to_nchw(y), ref)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("K", [2, 3])
+def test_head_outputs(dtype, K):
+    g = torch.Generator().manual_seed(5)
+    N, H, C = 2, 32, 16
+    x = torch.randn(N, C, H, H, generator=g).to(dtype).float()
+    w = torch.randn(K, C, 3, 3, generator=g) * 0.1
+    b = torch.randn(K, generator=g)
+    ref = F.conv2d(x, w, b, 1, 1)
+    wp = w.permute(2, 3, 1, 0).reshape(9, C, K).contiguous().cuda()
+    nchw = torch.empty(N, K, H, H, device="cuda")
+    nhwc = torch.empty(N, H, H, K, dtype=dtype, device="cuda")
+    mask = torch.empty(N, H, H, dtype=torch.uint8, device="cuda")
+    ops.head(x.permute(0, 2, 3, 1).contiguous().to(dtype).cuda(), wp, b.cuda(), logits_nchw=nchw, logits_nhwc=nhwc, mask=mask)
+    err, _ = report(f"head {dtype}", nchw.cpu(), ref)
+    assert err < 1e-4
+    assert torch.equal(mask.cpu().long(), nchw.cpu().argmax(1))                 # first-max argmax of its own logits
+    assert torch.equal(ops.argmax_nchw(nchw).cpu(), mask.cpu())
+    assert torch.equal(nhwc.cpu(), nchw.cpu().permute(0, 2, 3, 1).to(dtype))
+
+
+def test_argmax_ties_first_index():
+    z = torch.zeros(1, 3, 4, 4, device="cuda")
+    z[0, 1, 0, 0] = 1.0; z[0, 2, 0, 0] = 1.0
+    m = ops.argmax_nchw(z).cpu()
+    assert m[0, 0, 0] == 1 and m[0, 1, 1] == 0

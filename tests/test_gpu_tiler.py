@@ -1,0 +1,136 @@
+"""GPU parity: tiler kernels against the oracle / reference golden vectors — bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from deadtrees_b200 import ops
+from deadtrees_b200.data.deadtreedata import normalize_constants, val_transform
+from deadtrees_b200.deployment.inference import blend_window, overlap_grid
+from deadtrees_b200.deployment.tiler import Tiler
+from deadtrees_b200.utils.data_handling import make_blocks_vectorized, unmake_blocks_vectorized
+from oracle import ref_normalize, ref_tiler
+
+pytestmark = pytest.mark.gpu
+
+
+def test_blocks_reference_known_answer():
+    """tests/test_tiler.py:56-77 through the drop-in functions."""
+    source = np.array([np.arange(16).reshape(4, 4)] * 3)
+    target = np.array([[[[0, 1], [4, 5]]] * 3, [[[2, 3], [6, 7]]] * 3, [[[8, 9], [12, 13]]] * 3,
+                       [[[10, 11], [14, 15]]] * 3])
+    np.testing.assert_array_equal(make_blocks_vectorized(source, 2), target)
+    np.testing.assert_array_equal(unmake_blocks_vectorized(target[:, 0, :, :], 2, 4, 4), source[0])
+
+
+def test_blocks_golden(golden_dir):
+    g = np.load(golden_dir / "tiler_blocks.npz")
+    for i in range(int(g["ncases"])):
+        d = int(g[f"d{i}"])
+        np.testing.assert_array_equal(make_blocks_vectorized(g[f"x{i}"], d), g[f"blocks{i}"])
+        m, n = g[f"x{i}"].shape[1:]
+        out = unmake_blocks_vectorized(g[f"pred{i}"], d, m, n)
+        assert out.dtype == np.int64
+        np.testing.assert_array_equal(out, g[f"merged{i}"])
+
+
+@pytest.mark.parametrize("dtype", [np.uint8, np.int16, np.float32, np.int64])
+@pytest.mark.parametrize("p,m,n,d", [(4, 2048, 2048, 256), (3, 96, 160, 32), (1, 7, 21, 7), (2, 30, 12, 6)])
+def test_blocks_vs_oracle(dtype, p, m, n, d):
+    rng = np.random.default_rng(7)
+    x = (rng.integers(0, 200, size=(p, m, n))).astype(dtype)
+    np.testing.assert_array_equal(make_blocks_vectorized(x, d), ref_tiler.make_blocks(x, d))
+    b = rng.integers(0, 200, size=((m // d) * (n // d), d, d)).astype(dtype)
+    np.testing.assert_array_equal(unmake_blocks_vectorized(b, d, m, n), ref_tiler.unmake_blocks(b, d, m, n))
+
+
+def test_blocks_errors():
+    with pytest.raises(ValueError):
+        make_blocks_vectorized(np.zeros((3, 10, 10), np.uint8), 4)
+
+
+@pytest.mark.parametrize("size", [(2048, 2048), (1900, 2048), (700, 513)])
+def test_tiler_roundtrip(size):
+    """edge tiles: ceil grid, zero padding, crop on the way back (tiler.py:105-170)."""
+    rng = np.random.default_rng(3)
+    sv = rng.integers(0, 256, size=(4, *size), dtype=np.uint8)
+    t, o = Tiler(), ref_tiler.TilerOracle()
+    t.load_array(sv); o.load_array(sv)
+    b = t.get_batches()
+    np.testing.assert_array_equal(b, o.get_batches())
+    pred = (b[:, 0] % 3).astype(np.int64)
+    t.put_batches(pred)
+    np.testing.assert_array_equal(t.result, o.put_batches(pred))
+    assert t.result.shape == size and t.result.dtype == np.uint8
+
+
+@pytest.mark.parametrize("layout", ["hwc", "chw"])
+@pytest.mark.parametrize("C,Cm", [(3, 3), (4, 4), (4, 3)])
+@pytest.mark.parametrize("H,W,T,ov", [(256, 256, 64, 0), (300, 203, 64, 16), (130, 77, 32, 8)])
+def test_gather_normalize_bit_exact(layout, C, Cm, H, W, T, ov):
+    rng = np.random.default_rng(11)
+    m = rng.integers(0, 256, size=(H, W, C), dtype=np.uint8)
+    tiles = ref_tiler.extract_tiles(m, T, ov)                      # raw uint8 zero padding
+    ref = np.zeros(tiles.shape[:3] + (4,), dtype=np.float32)
+    off, sc = ref_normalize.normalize_constants(Cm)
+    ref[..., :Cm] = (tiles[..., :Cm].astype(np.float32) - off) * sc
+    src = torch.from_numpy(m if layout == "hwc" else np.ascontiguousarray(m.transpose(2, 0, 1))).cuda()
+    gy, gx = overlap_grid(H, W, T, ov)
+    o2, s2 = normalize_constants(Cm)
+    np.testing.assert_array_equal(o2, off); np.testing.assert_array_equal(s2, sc)
+    got = ops.tile_gather_normalize(src, layout, Cm, T, ov, (gy, gx), 0, gy * gx, off, sc, dtype=torch.float32)
+    np.testing.assert_array_equal(got.cpu().numpy(), ref)
+    got16 = ops.tile_gather_normalize(src, layout, Cm, T, ov, (gy, gx), 0, gy * gx, off, sc, dtype=torch.bfloat16)
+    assert torch.equal(got16.cpu(), torch.from_numpy(ref).to(torch.bfloat16))
+    # a sub-range of tiles (sharding) equals the slice
+    if gy * gx > 2:
+        part = ops.tile_gather_normalize(src, layout, Cm, T, ov, (gy, gx), 1, gy * gx - 2, off, sc, dtype=torch.float32)
+        np.testing.assert_array_equal(part.cpu().numpy(), ref[1:-1])
+
+
+def test_val_transform_matches_oracle():
+    rng = np.random.default_rng(5)
+    img = rng.integers(0, 256, size=(256, 256, 4), dtype=np.uint8)
+    out = val_transform(image=img)["image"]
+    assert out.shape == (4, 256, 256) and out.dtype == torch.float32
+    np.testing.assert_array_equal(out.cpu().numpy(), ref_normalize.val_transform(img))
+
+
+@pytest.mark.parametrize("H,W,T", [(256, 256, 64), (300, 203, 64), (100, 50, 32)])
+def test_stitch_mask_bit_exact(H, W, T):
+    rng = np.random.default_rng(13)
+    gy, gx = overlap_grid(H, W, T, 0)
+    tm = rng.integers(0, 3, size=(gy * gx, T, T), dtype=np.uint8)
+    ref = ref_tiler.unmake_blocks(tm, T, gy * T, gx * T)[:H, :W]
+    out = torch.full((H, W), 255, dtype=torch.uint8, device="cuda")
+    ops.stitch_mask(torch.from_numpy(tm).cuda(), gx, 0, out)
+    np.testing.assert_array_equal(out.cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("H,W,T,ov,K", [(300, 203, 64, 16, 3), (256, 256, 64, 32, 2), (100, 90, 32, 0, 3), (64, 64, 64, 8, 3)])
+def test_stitch_blend_bit_exact(dtype, H, W, T, ov, K):
+    g = torch.Generator().manual_seed(17)
+    gy, gx = overlap_grid(H, W, T, ov)
+    logits = (torch.randn(gy * gx, T, T, K, generator=g) * 3).to(dtype)
+    ref_blend, ref_mask = ref_tiler.stitch_blend(logits.float().numpy(), H, W, T, ov)
+    mask = torch.empty((H, W), dtype=torch.uint8, device="cuda")
+    blended = torch.empty((H, W, K), dtype=torch.float32, device="cuda")
+    ops.stitch_blend_argmax(logits.cuda(), ov, (gy, gx), blend_window(T, ov, "cuda"), mask, blended)
+    np.testing.assert_array_equal(blended.cpu().numpy(), ref_blend)
+    np.testing.assert_array_equal(mask.cpu().numpy(), ref_mask)
+
+
+def test_full_size_mosaic_roundtrip_property():
+    """BASELINE cfg2 size: gather (overlap 0) then stitch of a per-pixel function reproduces it on 10k x 10k."""
+    H = W = 10000
+    T = 256
+    g = torch.Generator(device="cuda").manual_seed(1)
+    m = torch.randint(0, 256, (H, W, 3), dtype=torch.uint8, device="cuda", generator=g)
+    gy, gx = overlap_grid(H, W, T, 0)
+    out = torch.zeros((H, W), dtype=torch.uint8, device="cuda")
+    for t0 in range(0, gy * gx, 400):
+        n = min(400, gy * gx - t0)
+        tiles = ops.tile_gather_normalize(m, "hwc", 3, T, 0, (gy, gx), t0, n, [0, 0, 0], [1, 1, 1], dtype=torch.float32)
+        cls = (tiles[..., 0].to(torch.int32) % 3).to(torch.uint8)     # identity-normalised red channel mod 3
+        ops.stitch_mask(cls, gx, t0, out)
+    assert torch.equal(out, (m[..., 0] % 3))

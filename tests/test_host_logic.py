@@ -1,0 +1,164 @@
+"""CPU tests of the host-side mirror of the reference interface (no compute calls)."""
+import math
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from deadtrees_b200.deployment.inference import MosaicInference, overlap_grid, blend_window
+from deadtrees_b200.deployment.tiler import Tiler, TileInfo, divisible_without_remainder, inspect_array, inspect_tile
+from deadtrees_b200.engine import conv_flops_per_tile, fold_bn, pack_weight
+from deadtrees_b200.network.segmodel import Conf, SemSegment, create_combined_batch, to_conf
+from deadtrees_b200.sharding import make_halo_hook, split_tile_rows
+from oracle import ref_tiler, ref_unet
+
+NETWORK = dict(architecture="unet", encoder_name="resnet34", encoder_depth=5, encoder_weights=None,
+               decoder_channels=[256, 128, 64, 32, 16], losses=["DICE", "FOCAL"],
+               classes=["bg", "conifer", "broadleaf"], in_channels=3)
+TRAINING = dict(learning_rate=3e-4, cosineannealing_tmax=10)
+
+
+@pytest.mark.parametrize("a,b,result", [(10, 2, True), (5, 4, False), (2, 0, False)])
+def test_divisible_without_remainder(a, b, result):  # tests/test_tiler.py:51-53
+    assert divisible_without_remainder(a, b) == result
+
+
+@pytest.mark.parametrize("size,expect", [((8192, 8192), (16, 16)), ((8192, 7433), (16, 15)), ((2649, 8192), (6, 16))])
+def test_inspect(size, expect):
+    info = inspect_array(size)
+    assert info == TileInfo(size=size, subtiles=expect)
+    assert inspect_tile(np.zeros((1,) + size, dtype=np.uint8)[:, :1, :1].repeat(1, 0)).size == (1, 1)
+
+
+def test_tiler_errors():
+    with pytest.raises(ValueError):
+        Tiler(tile_shape=(8192, 8192), subtile_shape=(256, 250))  # tests/test_tiler.py:113-115
+    with pytest.raises(ValueError):
+        inspect_array((100, 100), subtile_shape=(512, 211))
+    t = Tiler(tile_shape=(64, 64), subtile_shape=(16, 16))
+    t.load_array(np.zeros((4, 40, 33), dtype=np.uint8))
+    assert t._subtiles_to_use.sum() == 3 * 3 and t._indata.shape == (4, 64, 64)
+
+
+def test_semsegment_constructor_contract():
+    m = SemSegment(NETWORK, TRAINING)
+    sd = m.state_dict()
+    assert len(sd) == 278 and next(iter(sd)) == "model.encoder.conv1.weight"
+    assert list(m.parameters())[0].shape[1] == 3
+    assert set(sd) == {"model." + k for k in ref_unet.Unet(in_channels=3, classes=3).state_dict()}
+    assert m.classes_int_wout_bg == [1, 2] and m.hparams.training.learning_rate == 3e-4
+    with pytest.raises(NotImplementedError):
+        SemSegment(dict(NETWORK, architecture="fancynet"), TRAINING)
+    with pytest.raises(AssertionError):
+        SemSegment(dict(NETWORK, losses=["GDICE", "DICE"]), TRAINING)
+    with pytest.raises(NotImplementedError):
+        SemSegment(dict(NETWORK, losses=["DICE", "BANANA"]), TRAINING)
+    with pytest.raises(AssertionError):
+        SemSegment(dict(NETWORK, losses=["FOCAL"]), TRAINING)  # a dice-type loss is required
+
+
+def test_checkpoint_roundtrip(tmp_path):
+    m = SemSegment(dict(NETWORK, in_channels=4), TRAINING)
+    p = tmp_path / "m.ckpt"
+    m.save_checkpoint(p)
+    ck = torch.load(p, weights_only=False)
+    assert set(ck) >= {"state_dict", "hyper_parameters"} and ck["hyper_parameters"]["network"]["in_channels"] == 4
+    m2 = SemSegment.load_from_checkpoint(p)
+    for (k1, v1), (k2, v2) in zip(m.state_dict().items(), m2.state_dict().items()):
+        assert k1 == k2 and torch.equal(v1, v2)
+    from deadtrees_b200.deployment.inference import PyTorchInference
+    with pytest.raises(ValueError):
+        PyTorchInference(tmp_path / "m.onnx")
+
+
+def test_create_combined_batch():
+    mk = lambda n: (torch.zeros(n, 3, 4, 4), torch.zeros(n, 4, 4), torch.zeros(n, 3, 4, 4), torch.zeros(n, 4, 4),
+                    [{"file": f"f{i}"} for i in range(n)])
+    img, mask, dist_, lu, stats = create_combined_batch({"main": mk(2), "extra_a": mk(3)})
+    assert img.shape[0] == 5 and len(stats) == 5
+
+
+def test_conf_access():
+    c = to_conf({"a": 1, "b": {"c": 2}})
+    assert c.a == 1 and c.b.c == 2
+    d = c.copy(); del d.a
+    assert "a" in c and "a" not in d
+
+
+def test_pack_weight_layouts():
+    g = torch.Generator().manual_seed(0)
+    w = torch.randn(32, 16, 3, 3, generator=g)
+    p32 = pack_weight(w, "fp32", False, "cpu")
+    assert p32.shape == (9, 16, 32) and torch.equal(p32[4, 5, 7], w[7, 5, 1, 1])
+    pb = pack_weight(w, "bf16", False, "cpu")
+    assert pb.shape == (32, 192) and pb.dtype == torch.bfloat16          # K = 144 -> padded to 192
+    assert torch.equal(pb[7, (1 * 3 + 2) * 16 + 5], w[7, 5, 1, 2].to(torch.bfloat16)) and float(pb[:, 144:].abs().max()) == 0
+    ws = torch.randn(64, 3, 7, 7, generator=g)
+    ps = pack_weight(ws, "bf16", True, "cpu")
+    assert ps.shape == (64, 256)
+    assert torch.equal(ps[9, 2 * 32 + 5 * 4 + 1], ws[9, 1, 2, 5].to(torch.bfloat16))
+    assert float(ps[:, 224:].abs().max()) == 0 and float(ps.view(64, 8, 8, 4)[:, :7, 7].abs().max()) == 0  # s = 7 column
+    assert float(ps.view(64, 8, 8, 4)[:, :7, :7, 3].abs().max()) == 0                                        # padded channel
+
+
+def test_fold_bn_matches_batchnorm_eval():
+    bn = torch.nn.BatchNorm2d(8).eval()
+    g = torch.Generator().manual_seed(0)
+    bn.weight.data = torch.randn(8, generator=g); bn.bias.data = torch.randn(8, generator=g)
+    bn.running_mean = torch.randn(8, generator=g); bn.running_var = torch.rand(8, generator=g) + 0.5
+    sd = {"b." + k: v for k, v in bn.state_dict().items()}
+    scale, shift = fold_bn(sd, "b", 8, "cpu")
+    x = torch.randn(2, 8, 5, 5, generator=g)
+    torch.testing.assert_close(x * scale[None, :, None, None] + shift[None, :, None, None], bn(x), rtol=1e-5, atol=1e-5)
+
+
+def test_flops_match_survey():
+    assert abs(conv_flops_per_tile(256, 3, 3) / 1e9 - 15.6657) < 1e-3
+    assert abs(conv_flops_per_tile(256, 4, 3) / 1e9 - 15.7685) < 1e-3
+    assert abs(conv_flops_per_tile(1024, 3, 3) / 1e9 - 250.65) < 1e-2
+
+
+def test_grid_window_match_oracle():
+    for H, W, T, ov in [(10000, 10000, 256, 32), (10000, 10000, 256, 0), (300, 200, 64, 16), (64, 64, 64, 8)]:
+        assert overlap_grid(H, W, T, ov) == ref_tiler.overlap_grid(H, W, T, ov)[:2]
+    np.testing.assert_array_equal(blend_window(256, 32, "cpu").numpy(), ref_tiler.blend_window(256, 32))
+
+
+def test_split_tile_rows_partition():
+    assert [b - a for a, b in split_tile_rows(45, 8)] == [6, 6, 6, 6, 6, 5, 5, 5]
+    for gy in (1, 3, 40, 45):
+        for ws in (1, 2, 4, 8):
+            parts = split_tile_rows(gy, ws)
+            assert parts[0][0] == 0 and parts[-1][1] == gy and all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+            rows = [MosaicInference.owned_rows(10000, 256, 32, 45, a, b) for a, b in split_tile_rows(45, ws)]
+            assert rows[0][0] == 0 and rows[-1][1] == 10000 and all(a[1] == b[0] for a, b in zip(rows, rows[1:]))
+
+
+def _halo_worker(rank, world, port, tmp):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    T, ov, gx, K, gy = 16, 4, 3, 2, 5
+    parts = split_tile_rows(gy, world)
+    full = torch.arange(gy * gx * T * T * K, dtype=torch.float32).reshape(gy * gx, T, T, K)
+    r0, r1 = parts[rank]
+    halo = 1 if r0 > 0 else 0
+    local = torch.full(((r1 - r0 + halo) * gx, T, T, K), -1.0)
+    local[halo * gx:] = full[r0 * gx: r1 * gx]
+    make_halo_hook(T, ov, rank, world, has_rows=[b > a for a, b in parts])(local, gx, halo)
+    if halo:
+        expect = full[(r0 - 1) * gx: r0 * gx, T - ov:]
+        assert torch.equal(local[:gx, T - ov:], expect), rank
+        assert float(local[:gx, : T - ov].max()) == -1.0
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_halo_exchange_gloo(world, tmp_path):
+    """the N>1 path on CPU: every shard receives the previous shard's boundary logits rows."""
+    port = 29500 + (os.getpid() % 2000) + world
+    mp.spawn(_halo_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
