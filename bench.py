@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-sample-tiles", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--layer-table", default=None, help="write per-layer conv timings (CUDA events) to this file")
     ap.add_argument("--no-profile", action="store_true", help="skip the per-kernel CUDA-event instrumentation")
     return ap.parse_args()
 
@@ -305,8 +306,8 @@ def main_b200(a):
     if prof:
         def agg(kind):
             evs = prof.get(kind, [])
-            t = sum(e0.elapsed_time(e1) for e0, e1, _ in evs) / 1e3
-            w = sum(wk for _, _, wk in evs)
+            t = sum(ev[0].elapsed_time(ev[1]) for ev in evs) / 1e3
+            w = sum(ev[2] for ev in evs)
             return t, w, len(evs)
         tc, wc, nc = agg("conv")
         tg, wg, ng = agg("gather")
@@ -325,6 +326,16 @@ def main_b200(a):
             hb["stitch"] = {"achieved": ws / ts / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
                             "frac": ws / ts / 1e9 / pk["hbm_gbs"], "launches": ns}
         out["roofline_hbm"] = hb
+        if a.layer_table and rank == 0:
+            per = {}
+            for e0, e1, wk, tag in prof.get("conv", []):
+                d = per.setdefault(tag, [0.0, 0.0, 0])
+                d[0] += e0.elapsed_time(e1); d[1] += wk; d[2] += 1
+            with open(a.layer_table, "w") as fh:
+                fh.write(f"{'layer':34s} {'launches':>8s} {'avg_us':>9s} {'TFLOP/s':>9s} {'share%':>7s}\n")
+                for tag, (ms, wk, n) in per.items():
+                    fh.write(f"{tag:34s} {n:8d} {1e3 * ms / n:9.1f} {wk / (ms / 1e3) / 1e12:9.1f} {100 * ms / ms_total:7.2f}\n")
+                fh.write(f"conv total {1e3 * tc:.1f} ms of {ms_total:.1f} ms; gather {1e3 * tg:.2f} ms; stitch {1e3 * ts:.2f} ms\n")
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         tps, times = run_cpu_sample(a, a.cpu_sample_tiles, repeats=3, warm=1)
         out["cpu_baseline"] = {"value": tps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",

@@ -138,7 +138,7 @@ class UnetEngine:
         return ops.conv2d(x, L.w, L.scale, L.shift, N=N, H=H, W=W, C_in=L.C_in, C_x=L.C_x, C_out=L.C_out, R=L.R,
                           S=L.S, stride=L.stride, pad=L.pad, relu=L.relu, skip=skip, upsample=L.upsample,
                           residual=residual, out=out, flags=self.conv_flags,
-                          algo_cin=self.in_channels if name == "stem" else None)
+                          algo_cin=self.in_channels if name == "stem" else None, tag=name)
 
     def _buf(self, ws, key, shape):
         t = ws.get(key)

@@ -23,8 +23,8 @@ PROFILE = None
 
 
 class _Timed:
-    def __init__(self, kind: str, work: float):
-        self.kind, self.work = kind, work
+    def __init__(self, kind: str, work: float, tag: str = ""):
+        self.kind, self.work, self.tag = kind, work, tag
 
     def __enter__(self):
         if PROFILE is not None:
@@ -36,7 +36,7 @@ class _Timed:
     def __exit__(self, *exc):
         if PROFILE is not None and exc[0] is None:
             self.e1.record()
-            PROFILE.setdefault(self.kind, []).append((self.e0, self.e1, self.work))
+            PROFILE.setdefault(self.kind, []).append((self.e0, self.e1, self.work, self.tag))
         return False
 
 
@@ -153,14 +153,14 @@ def stitch_blend_argmax(logits: torch.Tensor, overlap: int, grid: Tuple[int, int
 def conv2d(x: torch.Tensor, w: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, *, N: int, H: int, W: int,
            C_in: int, C_x: int, C_out: int, R: int, S: int, stride: int, pad: int, relu: bool,
            skip: Optional[torch.Tensor] = None, upsample: bool = False, residual: Optional[torch.Tensor] = None,
-           out: Optional[torch.Tensor] = None, flags: int = 0, algo_cin: Optional[int] = None) -> torch.Tensor:
+           out: Optional[torch.Tensor] = None, flags: int = 0, algo_cin: Optional[int] = None, tag: str = "") -> torch.Tensor:
     Ho = (H + 2 * pad - R) // stride + 1
     Wo = (W + 2 * pad - S) // stride + 1
     if out is None:
         out = torch.empty((N, Ho, Wo, C_out), dtype=x.dtype, device=x.device)
     d = ConvDesc(N, H, W, C_in, C_x, int(upsample), C_out, R, S, stride, pad, int(relu), int(residual is not None),
                  _dt(x), flags)
-    with _Timed("conv", 2.0 * N * Ho * Wo * C_out * (algo_cin or C_in) * R * S):
+    with _Timed("conv", 2.0 * N * Ho * Wo * C_out * (algo_cin or C_in) * R * S, tag):
         check(load().dt_conv2d_fwd(C.byref(d), x.data_ptr(), ptr(skip), w.data_ptr(), scale.data_ptr(),
                                    shift.data_ptr(), ptr(residual), out.data_ptr(), stream_ptr()))
     return out

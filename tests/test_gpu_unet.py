@@ -67,19 +67,33 @@ def test_unet_fp32_layerwise():
 
 @pytest.mark.parametrize("cin,k,n,T", [(3, 3, 2, 64), (3, 3, 16, 256), (4, 3, 2, 256)])
 def test_unet_bf16_tensor_core(cin, k, n, T):
-    """BASELINE cfg1 shape (16 x 256 x 256 RGB) among the cases."""
+    """BASELINE cfg1 shape (16 x 256 x 256 RGB) among the cases.
+
+    The tensor-core path is checked against the oracle's bf16-arithmetic forward (bf16 operands, fp32
+    accumulate, bf16 storage at the same points): logits within 2e-2 of the logit scale, masks >= 99.9 %.
+    Its distance to the fp32 oracle is the intrinsic rounding of that arithmetic on a random-init net
+    (bf16 WEIGHT rounding alone flips 0.3 % of the argmax pixels of this model; DESIGN.md "bf16 parity"):
+    it is reported and bounded by the bf16 oracle's own distance."""
     model = oracle_model(cin, k)
     _, x = normalized_tiles(n, T, cin)
     with torch.no_grad():
-        ref = model(x)
+        ref32 = model(x)
+    ref16 = ref_unet.forward_bf16(model, x)
     eng = UnetEngine(model.state_dict(), cin, k, precision="bf16")
     out = eng.forward(nhwc4(x, torch.bfloat16).cuda(), want_logits_nchw=True, want_mask=True)
     torch.cuda.synchronize()
-    err, rel = report(f"unet bf16 cin={cin} T={T}", out["logits_nchw"].cpu(), ref)
-    agree = agreement(out["mask"], ref.argmax(1))
-    print(f"mask agreement {agree:.5f}")
-    assert err < 2e-2 * max(1.0, ref.abs().max().item())
-    assert agree >= 0.999
+    got = out["logits_nchw"].cpu()
+    scale = max(1.0, ref32.abs().max().item())
+    err16, _ = report(f"unet bf16 vs bf16-oracle cin={cin} T={T}", got, ref16)
+    err32, _ = report(f"unet bf16 vs fp32-oracle cin={cin} T={T}", got, ref32)
+    base32, _ = report(f"bf16-oracle vs fp32-oracle cin={cin} T={T}", ref16, ref32)
+    a16, a32, b32 = agreement(out["mask"], ref16.argmax(1)), agreement(out["mask"], ref32.argmax(1)), \
+        agreement(ref16.argmax(1), ref32.argmax(1))
+    print(f"mask agreement: vs bf16-oracle {a16:.5f}  vs fp32-oracle {a32:.5f}  (bf16-oracle vs fp32-oracle {b32:.5f})")
+    assert err16 < 2e-2 * scale
+    assert a16 >= 0.999
+    assert err32 < 2.0 * base32 + 1e-3 * scale      # no worse than the arithmetic itself
+    assert a32 >= b32 - 0.003
 
 
 def test_pytorch_inference_api(tmp_path):
@@ -135,8 +149,13 @@ def test_mosaic_pipeline_vs_oracle(precision, H, W, T, ov, bt):
     mosaic = np.clip(base + rng.normal(0, 20, size=(H, W, 3)), 0, 255).astype(np.uint8)
     tiles = ref_tiler.extract_tiles(mosaic, T, ov)
     x = torch.from_numpy(np.stack([ref_normalize.val_transform(t) for t in tiles]))
-    with torch.no_grad():
-        logits = model(x)
+    if precision == "fp32":
+        with torch.no_grad():
+            logits = model(x)
+    else:  # same arithmetic as the tensor-core path, logits stored as bf16 before the blend
+        logits = ref_unet.forward_bf16(model, x)
+        if ov > 0:
+            logits = logits.to(torch.bfloat16).float()
     if ov == 0:
         gy, gx = overlap_grid(H, W, T, 0)
         ref_mask = ref_tiler.unmake_blocks(logits.argmax(1).numpy(), T, gy * T, gx * T)[:H, :W].astype(np.uint8)
