@@ -197,13 +197,15 @@ __device__ __forceinline__ void tmem_ld_wait() {
 // `sbo_bytes` apart).  Field layout per the sm_100 UMMA descriptor: start address [0,14) >>4,
 // leading byte offset [16,30) >>4, stride byte offset [32,46) >>4, version [46,48) = 1,
 // layout type [61,64) = 2 (SWIZZLE_128B).
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t sbo_bytes) {
+// `layout`: 2 = SWIZZLE_128B (128 B rows), 4 = SWIZZLE_64B (64 B rows), 6 = SWIZZLE_32B (32 B rows);
+// `sbo_bytes` = 8 * row bytes for densely packed 8-row groups.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t layout) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
   d |= static_cast<uint64_t>(1) << 16;                       // LBO (unused for swizzled K-major)
   d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
   d |= static_cast<uint64_t>(1) << 46;                       // descriptor version (Blackwell)
-  d |= static_cast<uint64_t>(2) << 61;                       // SWIZZLE_128B
+  d |= static_cast<uint64_t>(layout & 7u) << 61;
   return d;
 }
 // Instruction descriptor: bf16 A/B (K-major), fp32 accumulate, M x N tile.

@@ -171,6 +171,75 @@ __global__ void head_kernel(const TA* __restrict__ x, int N, int H, int W, int C
   }
 }
 
+// 16 input channels as one vector load per tap
+__device__ __forceinline__ void load16(const __nv_bfloat16* p, float (&a)[16]) {
+  const uint4 v0 = __ldg(reinterpret_cast<const uint4*>(p)), v1 = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+  const uint32_t u[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float2 t = unpack_bf16x2(u[j]);
+    a[2 * j] = t.x;
+    a[2 * j + 1] = t.y;
+  }
+}
+__device__ __forceinline__ void load16(const float* p, float (&a)[16]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p) + j);
+    a[4 * j] = t.x; a[4 * j + 1] = t.y; a[4 * j + 2] = t.z; a[4 * j + 3] = t.w;
+  }
+}
+
+// C == 16 fast path of the head: one thread = one pixel, vector loads, weights broadcast from smem.
+// Accumulation order (tap-major, channel-minor, fp32 FMA) is the same as head_kernel's.
+template <typename TA, int K>
+__global__ void __launch_bounds__(256) head16_kernel(const TA* __restrict__ x, int N, int H, int W,
+                                                     const float* __restrict__ w, const float* __restrict__ bias,
+                                                     float* __restrict__ logits_nchw, TA* __restrict__ logits_nhwc,
+                                                     uint8_t* __restrict__ mask) {
+  __shared__ float sw[9 * 16 * K];
+  for (int i = threadIdx.x; i < 9 * 16 * K; i += blockDim.x) sw[i] = w[i];
+  __syncthreads();
+  const int64_t total = static_cast<int64_t>(N) * H * W;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int xw = static_cast<int>(i % W);
+    const int yh = static_cast<int>((i / W) % H);
+    const int n = static_cast<int>(i / (static_cast<int64_t>(W) * H));
+    float acc[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) acc[k] = 0.f;
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      const int hi = yh + dy - 1;
+      if (hi < 0 || hi >= H) continue;
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const int wi = xw + dx - 1;
+        if (wi < 0 || wi >= W) continue;
+        float a[16];
+        load16(x + ((static_cast<int64_t>(n) * H + hi) * W + wi) * 16, a);
+        const float* wp = sw + (dy * 3 + dx) * 16 * K;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+#pragma unroll
+          for (int k = 0; k < K; ++k) acc[k] = fmaf(a[c], wp[c * K + k], acc[k]);
+        }
+      }
+    }
+    int best = 0;
+    float bv = 0.f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const float v = acc[k] + bias[k];
+      if (logits_nchw) logits_nchw[((static_cast<int64_t>(n) * K + k) * H + yh) * W + xw] = v;
+      if (logits_nhwc) logits_nhwc[i * K + k] = from_f<TA>(v);
+      if (k == 0 || v > bv) { bv = v; best = k; }
+    }
+    if (mask) mask[i] = static_cast<uint8_t>(best);
+  }
+}
+
 __global__ void argmax_nchw_kernel(const float* __restrict__ logits, int N, int K, int64_t HW,
                                    uint8_t* __restrict__ mask) {
   const int64_t total = static_cast<int64_t>(N) * HW;
@@ -251,9 +320,14 @@ int dt_head_fwd(const void* x, int x_dtype, int N, int H, int W, int C, int K, c
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int64_t total = static_cast<int64_t>(N) * H * W;
   const size_t smem = static_cast<size_t>(9) * C * K * sizeof(float);
-#define DT_HEAD(TA, KK)                                                                                   \
-  head_kernel<TA, KK><<<grid_for(total), kThreads, smem, s>>>(static_cast<const TA*>(x), N, H, W, C, w, bias, \
-                                                             logits_nchw, static_cast<TA*>(logits_nhwc), mask)
+  const bool fast = C == 16 && reinterpret_cast<uintptr_t>(x) % 16 == 0;
+#define DT_HEAD(TA, KK)                                                                                       \
+  if (fast)                                                                                                   \
+    head16_kernel<TA, KK><<<grid_for(total), kThreads, 0, s>>>(static_cast<const TA*>(x), N, H, W, w, bias,   \
+                                                               logits_nchw, static_cast<TA*>(logits_nhwc), mask); \
+  else                                                                                                        \
+    head_kernel<TA, KK><<<grid_for(total), kThreads, smem, s>>>(static_cast<const TA*>(x), N, H, W, C, w, bias, \
+                                                               logits_nchw, static_cast<TA*>(logits_nhwc), mask)
 #define DT_HEADK(TA)                 \
   switch (K) {                       \
     case 1: DT_HEAD(TA, 1); break;   \
