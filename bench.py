@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--overlap", type=int, default=32)
     ap.add_argument("--batch-tiles", type=int, default=135)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--cpu-sample-tiles", type=int, default=32)
+    ap.add_argument("--cpu-sample-tiles", type=int, default=36)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--layer-table", default=None, help="write per-layer conv timings (CUDA events) to this file")
     ap.add_argument("--no-profile", action="store_true", help="skip the per-kernel CUDA-event instrumentation")
@@ -126,32 +126,52 @@ class ClockSampler(threading.Thread):
 
 
 # ---------------------------------------------------------------------------------------------------
-def cpu_reference_flow(model, tiles_u8: np.ndarray, tile: int):
-    """the reference's per-batch flow on the CPU (scripts/inference.py:93-105): per-tile normalise,
-    forward, argmax; returns class ids."""
-    from oracle import ref_normalize
-    x = torch.from_numpy(np.stack([ref_normalize.val_transform(t) for t in tiles_u8]))
+def load_reference_tiler():
+    """the reference's own make/unmake_blocks_vectorized from baseline/_ref (pip-installed copy of the
+    unmodified reference; loaded by file path because the repo's `deadtrees` shim has the same package
+    name).  None when the install is absent."""
+    import importlib.util
+    f = ROOT / "baseline" / "_ref" / "deadtrees" / "utils" / "data_handling.py"
+    if not f.exists():
+        return None
+    spec = importlib.util.spec_from_file_location("_reference_data_handling", f)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def cpu_reference_flow(model, block_chw: np.ndarray, tile: int, ref_dh):
+    """the reference's per-file flow on the CPU (scripts/inference.py:85-111) for one (C, m, n) uint8 block:
+    make_blocks -> per-tile normalise -> Unet forward -> argmax -> unmake_blocks.  Tiling uses the reference's
+    own functions when baseline/_ref exists; normalise / Unet are the oracle port (smp, albumentations absent)."""
+    from oracle import ref_normalize, ref_tiler
+    mk = ref_dh.make_blocks_vectorized if ref_dh else ref_tiler.make_blocks
+    unmk = ref_dh.unmake_blocks_vectorized if ref_dh else ref_tiler.unmake_blocks
+    tiles = mk(block_chw, tile)
+    x = torch.stack([torch.from_numpy(ref_normalize.val_transform(t.transpose(1, 2, 0))) for t in tiles])
     with torch.no_grad():
-        return model(x).argmax(dim=1)
+        out = model(x).argmax(dim=1).numpy()
+    return unmk(out, tile, block_chw.shape[1], block_chw.shape[2])
 
 
 def run_cpu_sample(a, n_tiles_sample: int, repeats: int, warm: int):
-    """times the oracle port (fp32 torch CPU, all host threads) on a bounded sample of the workload."""
-    from oracle import ref_tiler, ref_unet
+    """times the reference flow (oracle port of the Unet, fp32 torch CPU, all host threads) on a bounded
+    sample of the workload: one square block of ~n_tiles_sample tiles."""
+    from oracle import ref_unet
     torch.set_num_threads(os.cpu_count() or 1)
     model = ref_unet.build_reference_unet(3, 3, seed=0)
+    ref_dh = load_reference_tiler()
     rng = np.random.default_rng(1234)
-    side = int(np.ceil(np.sqrt(n_tiles_sample)))
-    crop = rng.integers(0, 256, size=(side * a.tile, side * a.tile, 3), dtype=np.uint8)
-    tiles = ref_tiler.extract_tiles(crop, a.tile, 0)[:n_tiles_sample]
+    side = max(1, int(round(np.sqrt(n_tiles_sample))))
+    block = rng.integers(0, 256, size=(3, side * a.tile, side * a.tile), dtype=np.uint8)
     times = []
     for i in range(warm + repeats):
         t0 = time.perf_counter()
-        cpu_reference_flow(model, tiles, a.tile)
+        cpu_reference_flow(model, block, a.tile, ref_dh)
         dt = time.perf_counter() - t0
         if i >= warm:
             times.append(dt)
-    return n_tiles_sample / min(times), times
+    return side * side / min(times), times, side * side, ref_dh is not None
 
 
 def main_reference(a):
@@ -161,10 +181,12 @@ def main_reference(a):
     from deadtrees_b200.deployment.inference import overlap_grid
     gy, gx = overlap_grid(a.size, a.size, a.tile, a.overlap)
     n_sample = a.cpu_sample_tiles
-    tps, times = run_cpu_sample(a, n_sample, repeats=a.steps, warm=a.warmup)
+    tps, times, n_sample, used_ref = run_cpu_sample(a, n_sample, repeats=a.steps, warm=a.warmup)
     ms = 1000.0 * statistics.mean(times)
-    sample = f"{n_sample} tiles of {a.tile}x{a.tile} per step through the oracle port of the reference flow " \
-             f"(normalise -> Unet fp32 -> argmax), torch CPU, {torch.get_num_threads()} threads"
+    sample = f"one block of {n_sample} tiles of {a.tile}x{a.tile} per step through the reference flow " \
+             f"(make_blocks -> normalise -> Unet fp32 -> argmax -> unmake_blocks; tiler = " \
+             f"{'reference code from baseline/_ref' if used_ref else 'oracle port'}, Unet/normalise = oracle port), " \
+             f"torch CPU, {torch.get_num_threads()} threads"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": tps, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -337,10 +359,11 @@ def main_b200(a):
                     fh.write(f"{tag:34s} {n:8d} {1e3 * ms / n:9.1f} {wk / (ms / 1e3) / 1e12:9.1f} {100 * ms / ms_total:7.2f}\n")
                 fh.write(f"conv total {1e3 * tc:.1f} ms of {ms_total:.1f} ms; gather {1e3 * tg:.2f} ms; stitch {1e3 * ts:.2f} ms\n")
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        tps, times = run_cpu_sample(a, a.cpu_sample_tiles, repeats=3, warm=1)
+        tps, times, n_s, used_ref = run_cpu_sample(a, a.cpu_sample_tiles, repeats=3, warm=1)
         out["cpu_baseline"] = {"value": tps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                               "sample": f"{a.cpu_sample_tiles} tiles of {T}x{T} (normalise -> Unet fp32 -> argmax) "
-                                         f"through the oracle port, best of 3"}
+                               "sample": f"one block of {n_s} tiles of {T}x{T} through the reference flow (make_blocks -> "
+                                         f"normalise -> Unet fp32 -> argmax -> unmake_blocks; Unet = oracle port, tiler = "
+                                         f"{'reference code (baseline/_ref)' if used_ref else 'oracle port'}), best of 3"}
     if rank == 0:
         print(json.dumps(out))
     if world > 1:
