@@ -201,12 +201,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     // ===================== MMA issuer (one lane) =====================
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
-      // A operand layout: 128 B rows (swizzle 128), or 64 B / 32 B rows with one sub-tile per tap
+      // A operand layout: 128 B rows (swizzle 128), or 64 B / 32 B rows with one sub-tile per tap.
+      // This thread's instruction stream paces the tensor core, so everything that does not change per
+      // MMA is hoisted: descriptor high words and the four per-k-step A offsets are loop invariants.
       const bool gather = !A_TMA;
       const int cw = gather ? BK : p.a_cw;
       const uint32_t a_layout = cw == 64 ? 2u : (cw == 32 ? 4u : 6u);
-      const uint32_t a_sbo = 8u * cw * 2u;
       const int sub_bytes = BM * cw * 2;
+      const uint64_t a_hi = umma_desc(0u, 8u * cw * 2u, a_layout);
+      const uint64_t b_hi = umma_desc(0u, 1024u, 2u);
+      uint32_t a_off[BK / 16];
+#pragma unroll
+      for (int k = 0; k < BK / 16; ++k) a_off[k] = (((k * 16) / cw) * sub_bytes + ((k * 16) % cw) * 2) >> 4;
+      const int tail_steps = gather ? BK / 16 : (p.k_total - (p.num_k_chunks - 1) * BK) / 16;
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -218,15 +225,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         for (int kc = 0; kc < p.num_k_chunks; ++kc) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem_a + stage * A_STAGE_BYTES);
-          const uint32_t b_addr = smem_u32(smem_b + stage * Cfg::B_STAGE_BYTES);
+          const uint64_t a_d = a_hi + (smem_u32(smem_a + stage * A_STAGE_BYTES) >> 4);
+          const uint64_t b_d = b_hi + (smem_u32(smem_b + stage * Cfg::B_STAGE_BYTES) >> 4);
           // gather mode zero-fills the padded tail of K; TMA mode simply skips it
-          const int ksteps = gather ? BK / 16 : min(BK / 16, (p.k_total - kc * BK) / 16);
-          for (int k = 0; k < ksteps; ++k) {
-            const int e = k * 16;                            // K element inside the chunk
-            const uint32_t a_k = a_addr + (e / cw) * sub_bytes + (e % cw) * 2;
-            umma_bf16_ss(d_tmem, umma_desc(a_k, a_sbo, a_layout), umma_desc(b_addr + k * 32, 1024u, 2u), idesc,
-                         (kc | k) != 0 ? 1u : 0u);
+          const int ksteps = kc + 1 < p.num_k_chunks ? BK / 16 : tail_steps;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            if (k < ksteps) umma_bf16_ss(d_tmem, a_d + a_off[k], b_d + 2 * k, idesc, (kc | k) != 0 ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs above have read it
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -464,6 +469,13 @@ bool box_tiling(int Hg, int Wg, int* bw, int* bh, int* bn) {
 
 }  // namespace
 
+int dt_encode_bf16_map(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                       const uint32_t* box, const uint32_t* elem_strides) {
+  return encode_bf16_map(tm, base, rank, dims, strides_bytes, box, elem_strides);
+}
+int dt_conv_halo(const dt_conv_desc* d, int BN, const void* x, const void* w, int Kpad, const float* scale,
+                 const float* shift, const void* residual, void* y, cudaStream_t s);
+
 extern "C" int dt_conv2d_fwd(const dt_conv_desc* d, const void* x, const void* skip, const void* w,
                              const float* scale, const float* shift, const void* residual, void* y,
                              dt_stream_t stream) {
@@ -503,6 +515,11 @@ extern "C" int dt_conv2d_fwd(const dt_conv_desc* d, const void* x, const void* s
   if (BN > 128) BN = (d->C_out % 256 == 0 && M >= static_cast<int64_t>(dt_num_sms()) * 2 * BM) ? 256 : 128;
   DT_REQUIRE(d->C_out % BN == 0 && (BN == 16 || BN == 32 || BN == 64 || BN == 128 || BN == 256), DT_ERR_BAD_SHAPE,
              "dt_conv2d_fwd: unsupported C_out %d", d->C_out);
+
+  if (!(d->flags & (DT_CONV_NO_HALO | DT_CONV_FORCE_GATHER)) && !stem) {
+    const int rc = dt_conv_halo(d, BN, x, w, Kpad, scale, shift, residual, y, s);
+    if (rc != DT_ERR_UNSUPPORTED) return rc;   // not a 3x3/s1 layer of a fitting shape: per-tap path below
+  }
 
   TcParams p;
   memset(&p, 0, sizeof(p));
