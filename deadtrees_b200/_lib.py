@@ -15,7 +15,7 @@ _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "libdeadtrees_b200.so"
 
 DT_BF16, DT_F32 = 0, 1
-CONV_FORCE_GATHER, CONV_FORCE_DIRECT, CONV_NO_HALO, CONV_HALO_P16, CONV_HALO_BASEOFF = 1, 2, 4, 8, 16
+CONV_FORCE_GATHER, CONV_FORCE_DIRECT, CONV_NO_HALO = 1, 2, 4
 
 
 class DeadtreesB200Error(RuntimeError):

@@ -1,14 +1,25 @@
-// 3x3 / stride-1 / pad-1 convolution with a shared-memory resident input halo (tcgen05 implicit GEMM).
+// 3x3 / stride-1 / pad-1 convolution with shared-memory resident input patches (tcgen05 implicit GEMM).
 //
-// One tile = 8 (w) x 16 (h) output pixels of one image = the 128 rows of a UMMA M=128 tile.  For every slab of
-// `cw` input channels (64, or all of them when C_in is 32 / 16) ONE TMA box brings the (16+2) x (8+2) pixel halo
-// patch into shared memory; the nine filter taps then read it in place: the A-operand descriptor of tap (r,s)
-// starts (r*pitch + s) pixel rows into the patch and steps `pitch` pixel rows between 8-pixel groups
-// (stride-byte-offset), so the activations cross L2 -> SM once instead of nine times.  Weights stream through a
-// separate TMA ring, one 64-wide K chunk (tap, slab) at a time.
-//   warp 0: TMA producer (A patches + B chunks)   warp 1: TMEM alloc + MMA issuer   warps 2..5: epilogue
-// Persistent CTAs, one per SM, double-buffered TMEM accumulator (epilogue of tile i overlaps tile i+1).
-// K is accumulated slab-major (slab, tap, channel) - a different fp32 summation order than conv_tc.cu.
+// One tile = 8 (w) x 16 (h) output pixels = the 128 rows of a UMMA M=128 tile.  For every slab of `CW` input
+// channels ONE TMA box brings a (16+2) x (8+2) pixel halo patch into shared memory; the filter taps then read it
+// in place: the A-operand descriptor of a tap starts `off` pixel rows into the patch and steps PITCH pixel rows
+// between 8-pixel groups (stride-byte-offset).  This works because the UMMA shared-memory swizzle is a function
+// of the absolute smem address (measured: scripts/halo_exp.py, profiles/r01_halo_descriptor_experiment.txt), so
+// a shifted window of a TMA-swizzled patch is still a valid K-major operand.  Activations therefore cross
+// L2 -> SM once instead of nine times.  Weights stream through a separate TMA ring, one 64-wide K chunk at a time.
+//
+// Two tile families share the kernel:
+//   plain  : y = conv3x3(x)                      tile pixels = (h0+i, w0+j)
+//   parity : y = conv3x3(cat[up2(x), skip])      tile pixels = (2(h0+i)+a, 2(w0+j)+b) for one parity class (a,b);
+//            the up-sampled operand is the LOW-RES patch read at offset ((a+r-1)>>1, (b+s-1)>>1) - nine taps from
+//            one patch - and the skip operand comes from the four stride-2 "plane" patches
+//            skip[2i+pr, 2j+pc] (TMA traversal stride 2), each serving the taps with (a+r-1)&1 == pr, (b+s-1)&1 == pc.
+//            Neither the up-sampled nor the concatenated tensor is ever materialised.
+// The per-class tap lists / patch offsets are small tables in the kernel parameters.
+//
+//   warp 0: TMA producer (patches + weight chunks)   warp 1: TMEM alloc + MMA issuer   warps 2..5: epilogue
+// Persistent CTAs, double-buffered TMEM accumulator (epilogue of tile i overlaps the main loop of tile i+1).
+// K is accumulated patch-major - a different fp32 summation order than conv_tc.cu.
 #include <cstring>
 #include <mutex>
 
@@ -18,83 +29,65 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int TW = 8, TH = 16;       // tile of output pixels
+constexpr int TW = 8, TH = 16;       // tile of output pixels (of one parity class in parity mode)
 constexpr int kThreads = 192;
 constexpr int MAX_A = 3;
 constexpr int MAX_B = 8;
-constexpr int PITCH = 10;            // halo patch row pitch in pixels (TW + 2)
+constexpr int PITCH = TW + 2;        // patch row pitch in pixels
+constexpr int PATCH_PIX = (TH + 2) * PITCH;
+
+struct PatchDesc {                   // one patch kind of one parity class
+  uint8_t pr, pc, ntaps, pad;
+  uint8_t tap[9];                    // filter tap r*3+s served by this patch (wide: one weight chunk per entry)
+  uint8_t off[9];                    // pixel offset of that tap's window inside the patch, indexed like tap[]
+  uint8_t off_by_tap[9];             // same offsets indexed by the natural tap number (narrow layers)
+  uint8_t pad2[1];
+};
 
 struct HaloParams {
-  int N, H, W, C_in, C_out;
-  int cw;                // channels per slab (row bytes = 2*cw)
-  int nslab;             // C_in / cw
-  int chunks_per_slab;   // B chunks (64 K elements) per slab: 9 (cw = 64) or ceil(9*C_in/64)
-  int k_slab;            // K elements per slab = 9 * cw
-  int pitch;             // halo patch row pitch in pixels (10; 16 only in scripts/halo_exp.py)
-  int base_off;          // experiment: fill the descriptor's base-offset field from the start address
-  int a_slots;           // 2 or 3 halo patch slots
+  int N, H, W, C_in, C_x, C_out;     // H, W: output (= virtual input) size
+  int parity;                        // 0 plain, 1 parity classes
+  int Hg, Wg;                        // pixel grid the tiles walk: (H, W) or (H/2, W/2)
+  int n_xslab, n_sslab;              // slabs of the x operand / of the skip operand
+  int a_slots, b_slots, a_slot_bytes;
   int relu, has_residual;
-  int tiles_w, tiles_h, n_tiles, total_tiles;
-  int b_slots, a_slot_bytes;
+  int tiles_w, tiles_h, tiles_per_class, n_tiles, total_tiles;
   const __nv_bfloat16* residual;
   __nv_bfloat16* y;
   const float* scale;
   const float* shift;
+  PatchDesc patch[4][5];             // [class][0] = x patch, [class][1..4] = skip planes
 };
 
 struct Geo {
-  int n_tile, n, h0, w0;
+  int n_tile, cls, n, h0, w0;
 };
 __device__ __forceinline__ Geo geo(const HaloParams& p, int tile) {
   Geo g;
   g.n_tile = tile % p.n_tiles;
   int m = tile / p.n_tiles;
+  g.cls = m / p.tiles_per_class;
+  m -= g.cls * p.tiles_per_class;
   g.w0 = (m % p.tiles_w) * TW; m /= p.tiles_w;
   g.h0 = (m % p.tiles_h) * TH;
   g.n = m / p.tiles_h;
   return g;
 }
 
-__device__ __forceinline__ uint64_t umma_desc_bo(uint32_t addr, uint32_t sbo, uint32_t layout, uint32_t base_off) {
-  return umma_desc(addr, sbo, layout) | (static_cast<uint64_t>(base_off & 7u) << 49);
-}
-
-// issue the MMAs of one 64-wide K chunk; all offsets are compile-time when EXPERIMENT is false
-template <int BN, int CW, int Q, bool EXPERIMENT>
-__device__ __forceinline__ void issue_chunk(const HaloParams& p, uint32_t d_tmem, uint64_t a_d, uint32_t a_base,
-                                            uint64_t b_d, uint32_t first) {
-  constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
-  constexpr int K_SLAB = 9 * CW;
-  constexpr int KSTEPS = (K_SLAB - Q * BK) / 16 < BK / 16 ? (K_SLAB - Q * BK) / 16 : BK / 16;
-#pragma unroll
-  for (int k = 0; k < KSTEPS; ++k) {
-    constexpr int dummy = 0; (void)dummy;
-    const int kk = Q * BK + k * 16;                    // K index inside the slab: tap * CW + channel
-    const int tap = kk / CW, ch = kk % CW;
-    const int fr = tap / 3, fs = tap % 3;
-    const uint32_t acc = (Q == 0 && k == 0) ? (first ? 0u : 1u) : 1u;
-    if (EXPERIMENT) {
-      const uint32_t a_addr = a_base + (fr * p.pitch + fs) * (CW * 2) + ch * 2;
-      uint64_t d = umma_desc(a_addr, p.pitch * CW * 2, CW == 64 ? 2u : (CW == 32 ? 4u : 6u));
-      if (p.base_off) d |= static_cast<uint64_t>((a_addr >> 7) & 7u) << 49;
-      umma_bf16_ss(d_tmem, d, b_d + 2 * k, idesc, acc);
-    } else {
-      umma_bf16_ss(d_tmem, a_d + (((fr * PITCH + fs) * (CW * 2) + ch * 2) >> 4), b_d + 2 * k, idesc, acc);
-    }
-  }
-}
-
-template <int BN, int CW, bool EXPERIMENT>
+template <int BN, int CW>
 __global__ void __launch_bounds__(kThreads, BN <= 128 ? 2 : 1)
-conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-                 const HaloParams p) {
+conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_s,
+                 const __grid_constant__ CUtensorMap tm_b, const HaloParams p) {
   constexpr int B_BYTES = BN * BK * 2;
   constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
-  constexpr int CHUNKS = (9 * CW + BK - 1) / BK;
+  constexpr int ROW_BYTES = CW * 2;
+  constexpr int PATCH_BYTES = PATCH_PIX * ROW_BYTES;
+  constexpr int NARROW_CHUNKS = (9 * CW + BK - 1) / BK;    // weight chunks of a narrow (CW < 64) layer
+  constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
   const int A_SLOTS = p.a_slots;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smem_a = smem;                                   // A_SLOTS x a_slot_bytes (1024-aligned each)
+  uint8_t* smem_a = smem;                                   // a_slots x a_slot_bytes (1024-aligned each)
   uint8_t* smem_b = smem + A_SLOTS * p.a_slot_bytes;        // b_slots x B_BYTES
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + p.b_slots * B_BYTES);
   uint64_t* full_a = bars;                 // [MAX_A]
@@ -109,6 +102,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_a);
     tma_prefetch_desc(&tm_b);
+    if (p.n_sslab > 0) tma_prefetch_desc(&tm_s);
     for (int i = 0; i < A_SLOTS; ++i) { mbar_init(&full_a[i], 1u); mbar_init(&empty_a[i], 1u); }
     for (int i = 0; i < p.b_slots; ++i) { mbar_init(&full_b[i], 1u); mbar_init(&empty_b[i], 1u); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1u); mbar_init(&tmem_empty[i], 128u); }
@@ -122,44 +116,46 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  constexpr int row_bytes = CW * 2;
+  const int patches_per_tile = p.n_xslab + 4 * p.n_sslab;   // patch instance pi: x slabs first, then skip planes
 
   if (warp == 0) {
     if (lane == 0) {
-      // The A patch of slab i+1 is requested before the weight chunks of slab i so that it is in flight while the
-      // tensor core works through slab i (three A slots: previous / current / next).
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
-      const int halo_bytes = (TH + 2) * p.pitch * row_bytes;
+      // request patch instance `pi` of the tile with geometry `g`
+      auto load_patch = [&](const Geo& g, int pi) {
+        mbar_wait(&empty_a[sa], pa ^ 1u);
+        mbar_arrive_expect_tx(&full_a[sa], PATCH_BYTES);
+        uint8_t* dst = smem_a + sa * p.a_slot_bytes;
+        if (pi < p.n_xslab) {
+          tma_load_4d(dst, &tm_a, &full_a[sa], pi * CW, g.w0 - 1, g.h0 - 1, g.n);
+        } else {
+          const int s = pi - p.n_xslab;
+          const PatchDesc& pd = p.patch[g.cls][1 + (s & 3)];
+          tma_load_4d(dst, &tm_s, &full_a[sa], (s >> 2) * BK, 2 * (g.w0 - 1) + pd.pc, 2 * (g.h0 - 1) + pd.pr, g.n);
+        }
+        if (++sa == A_SLOTS) { sa = 0; pa ^= 1u; }
+      };
       bool primed = false;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const Geo g = geo(p, tile);
-        for (int slab = 0; slab < p.nslab; ++slab) {
-          if (!primed) {  // very first patch of this CTA
-            mbar_wait(&empty_a[sa], pa ^ 1u);
-            mbar_arrive_expect_tx(&full_a[sa], halo_bytes);
-            tma_load_4d(smem_a + sa * p.a_slot_bytes, &tm_a, &full_a[sa], slab * CW, g.w0 - 1, g.h0 - 1, g.n);
-            if (++sa == A_SLOTS) { sa = 0; pa ^= 1u; }
-            primed = true;
-          }
-          // With three patch slots the next patch (next slab, or slab 0 of this CTA's next tile) is requested
-          // before this slab's weight chunks; with two slots its slot is still being read, so it is requested
-          // after the first few weight chunks instead (by then the previous slab has been consumed).
-          const int prefetch_at = A_SLOTS >= 3 ? 0 : (CHUNKS > 5 ? 4 : CHUNKS - 1);
-          for (int q = 0; q < CHUNKS; ++q) {
+        for (int pi = 0; pi < patches_per_tile; ++pi) {
+          if (!primed) { load_patch(g, pi); primed = true; }   // very first patch of this CTA
+          const int kind = pi < p.n_xslab ? 0 : 1 + ((pi - p.n_xslab) & 3);
+          const PatchDesc& pd = p.patch[g.cls][kind];
+          // weight K coordinate of this patch's channels: k = tap * C_in + choff (+ channel)
+          const int choff = pi < p.n_xslab ? pi * CW : p.C_x + ((pi - p.n_xslab) >> 2) * BK;
+          const int nchunks = CW == BK ? pd.ntaps : NARROW_CHUNKS;
+          // With three patch slots the next patch is requested before this patch's weight chunks; with two its
+          // slot is still being read, so it is requested after the first few weight chunks instead.
+          const int prefetch_at = A_SLOTS >= 3 ? 0 : (nchunks > 5 ? 4 : nchunks - 1);
+          for (int q = 0; q < nchunks; ++q) {
             if (q == prefetch_at) {
-              int nslab_i = slab + 1, ntile = tile;
-              if (nslab_i == p.nslab) { nslab_i = 0; ntile = tile + gridDim.x; }
-              if (ntile < p.total_tiles) {
-                const Geo gn = geo(p, ntile);
-                mbar_wait(&empty_a[sa], pa ^ 1u);
-                mbar_arrive_expect_tx(&full_a[sa], halo_bytes);
-                tma_load_4d(smem_a + sa * p.a_slot_bytes, &tm_a, &full_a[sa], nslab_i * CW, gn.w0 - 1, gn.h0 - 1, gn.n);
-                if (++sa == A_SLOTS) { sa = 0; pa ^= 1u; }
-              }
+              int npi = pi + 1, ntile = tile;
+              if (npi == patches_per_tile) { npi = 0; ntile = tile + gridDim.x; }
+              if (ntile < p.total_tiles) load_patch(geo(p, ntile), npi);
             }
-            // wide: chunk q = tap q of this slab (k = q*C_in + slab*64); narrow: chunk q of the single slab
-            const int kcoord = CW == BK ? q * p.C_in + slab * BK : q * BK;
+            const int kcoord = CW == BK ? pd.tap[q] * p.C_in + choff : q * BK;
             mbar_wait(&empty_b[sb], pb ^ 1u);
             mbar_arrive_expect_tx(&full_b[sb], B_BYTES);
             tma_load_2d(smem_b + sb * B_BYTES, &tm_b, &full_b[sb], kcoord, g.n_tile * BN);
@@ -170,32 +166,51 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      // This thread's instruction stream paces the tensor core: descriptor high words are loop invariants
-      // and, with the chunk loop unrolled, every tap / k-step offset is an immediate.
-      const uint64_t a_hi = umma_desc(0u, PITCH * row_bytes, CW == 64 ? 2u : (CW == 32 ? 4u : 6u));
+      // This thread's instruction stream paces the tensor core: descriptor high words are loop invariants and the
+      // k-step offsets are immediates; per weight chunk only the tap's window offset is looked up.
+      const uint64_t a_hi = umma_desc(0u, PITCH * ROW_BYTES, CW == 64 ? 2u : (CW == 32 ? 4u : 6u));
       const uint64_t b_hi = umma_desc(0u, 1024u, 2u);
       int sa = 0, sb = 0, acc = 0;
       uint32_t pa = 0, pb = 0, pacc = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int cls = p.parity ? (tile / p.n_tiles) / p.tiles_per_class : 0;
         mbar_wait(&tmem_empty[acc], pacc ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int slab = 0; slab < p.nslab; ++slab) {
+        uint32_t accum = 0;
+        for (int pi = 0; pi < patches_per_tile; ++pi) {
+          const int kind = pi < p.n_xslab ? 0 : 1 + ((pi - p.n_xslab) & 3);
+          const PatchDesc& pd = p.patch[cls][kind];
           mbar_wait(&full_a[sa], pa);
-          const uint32_t a_base = smem_u32(smem_a + sa * p.a_slot_bytes);
-          const uint64_t a_d = a_hi + (a_base >> 4);
-          const uint32_t first = slab == 0 ? 1u : 0u;
-#define DT_CHUNK(Q)                                                                          \
-          if (Q < CHUNKS) {                                                                  \
-            mbar_wait(&full_b[sb], pb);                                                      \
-            tc_fence_after();                                                                \
-            const uint64_t b_d = b_hi + (smem_u32(smem_b + sb * B_BYTES) >> 4);              \
-            issue_chunk<BN, CW, (Q < CHUNKS ? Q : 0), EXPERIMENT>(p, d_tmem, a_d, a_base, b_d, first); \
-            umma_commit(&empty_b[sb]);                                                       \
-            if (++sb == p.b_slots) { sb = 0; pb ^= 1u; }                                     \
+          const uint64_t a_d = a_hi + (smem_u32(smem_a + sa * p.a_slot_bytes) >> 4);
+          const int nchunks = CW == BK ? pd.ntaps : NARROW_CHUNKS;
+          for (int q = 0; q < nchunks; ++q) {
+            mbar_wait(&full_b[sb], pb);
+            tc_fence_after();
+            const uint64_t b_d = b_hi + (smem_u32(smem_b + sb * B_BYTES) >> 4);
+            if (CW == BK) {
+              const uint64_t a_t = a_d + ((static_cast<uint32_t>(pd.off[q]) * ROW_BYTES) >> 4);
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) {
+                umma_bf16_ss(d_tmem, a_t + 2 * k, b_d + 2 * k, idesc, accum);
+                accum = 1;
+              }
+            } else {
+              // narrow layer: chunk q holds K elements [64q, 64q+64) = taps (64q+16k)/CW in natural order
+              const int ksteps = min(BK / 16, (9 * CW - q * BK) / 16);
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) {
+                if (k < ksteps) {
+                  const int kk = q * BK + k * 16;
+                  const uint32_t off = static_cast<uint32_t>(pd.off_by_tap[kk / CW]) * ROW_BYTES + (kk % CW) * 2;
+                  umma_bf16_ss(d_tmem, a_d + (off >> 4), b_d + 2 * k, idesc, accum);
+                  accum = 1;
+                }
+              }
+            }
+            umma_commit(&empty_b[sb]);
+            if (++sb == p.b_slots) { sb = 0; pb ^= 1u; }
           }
-          DT_CHUNK(0) DT_CHUNK(1) DT_CHUNK(2) DT_CHUNK(3) DT_CHUNK(4) DT_CHUNK(5) DT_CHUNK(6) DT_CHUNK(7) DT_CHUNK(8)
-#undef DT_CHUNK
           umma_commit(&empty_a[sa]);
           if (++sa == A_SLOTS) { sa = 0; pa ^= 1u; }
         }
@@ -211,8 +226,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     uint32_t pacc = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const Geo g = geo(p, tile);
-      const int64_t out_off =
-          ((static_cast<int64_t>(g.n) * p.H + g.h0 + (row >> 3)) * p.W + g.w0 + (row & 7)) * p.C_out + g.n_tile * BN;
+      int oy = g.h0 + (row >> 3), ox = g.w0 + (row & 7);
+      if (p.parity) { oy = 2 * oy + (g.cls >> 1); ox = 2 * ox + (g.cls & 1); }
+      const int64_t out_off = ((static_cast<int64_t>(g.n) * p.H + oy) * p.W + ox) * p.C_out + g.n_tile * BN;
       uint4 res[SC / 8];
       if (p.has_residual) {
 #pragma unroll
@@ -238,8 +254,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           float f[16];
           const int co = g.n_tile * BN + s0 + c0;
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            f[j] = fmaf(__uint_as_float(v[j]), __ldg(p.scale + co + j), __ldg(p.shift + co + j));
+          for (int j = 0; j < 16; j += 4) {
+            const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + co + j));
+            const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + co + j));
+            f[j] = fmaf(__uint_as_float(v[j]), sc.x, sh.x);
+            f[j + 1] = fmaf(__uint_as_float(v[j + 1]), sc.y, sh.y);
+            f[j + 2] = fmaf(__uint_as_float(v[j + 2]), sc.z, sh.z);
+            f[j + 3] = fmaf(__uint_as_float(v[j + 3]), sc.w, sh.w);
+          }
           if (p.has_residual) {
             const uint32_t rr[8] = {res[c0 / 8].x, res[c0 / 8].y, res[c0 / 8].z, res[c0 / 8].w,
                                     res[c0 / 8 + 1].x, res[c0 / 8 + 1].y, res[c0 / 8 + 1].z, res[c0 / 8 + 1].w};
@@ -279,8 +301,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   }
 }
 
-template <int BN, int CW, bool EXPERIMENT>
-int launch_halo_impl(const CUtensorMap& tm_a, const CUtensorMap& tm_b, HaloParams& p, cudaStream_t s) {
+template <int BN, int CW>
+int launch_halo(const CUtensorMap& tm_a, const CUtensorMap& tm_s, const CUtensorMap& tm_b, HaloParams& p,
+                cudaStream_t s) {
   constexpr int B_BYTES = BN * BK * 2;
   constexpr int CTAS = BN <= 128 ? 2 : 1;
   // shared memory per CTA: ~111 KB when two CTAs share an SM, ~200 KB otherwise
@@ -295,21 +318,42 @@ int launch_halo_impl(const CUtensorMap& tm_a, const CUtensorMap& tm_b, HaloParam
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(conv_halo_kernel<BN, CW, EXPERIMENT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    225 * 1024);
+    attr_err = cudaFuncSetAttribute(conv_halo_kernel<BN, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
   });
   DT_CUDA(attr_err);
   const int slots = dt_num_sms() * CTAS;
   const int grid = p.total_tiles < slots ? p.total_tiles : slots;
-  conv_halo_kernel<BN, CW, EXPERIMENT><<<grid, kThreads, smem, s>>>(tm_a, tm_b, p);
+  conv_halo_kernel<BN, CW><<<grid, kThreads, smem, s>>>(tm_a, tm_s, tm_b, p);
   DT_LAUNCH_CHECK();
   return DT_OK;
 }
 
-template <int BN, int CW>
-int launch_halo(const CUtensorMap& tm_a, const CUtensorMap& tm_b, HaloParams& p, cudaStream_t s) {
-  if (p.pitch != PITCH || p.base_off) return launch_halo_impl<BN, CW, true>(tm_a, tm_b, p, s);
-  return launch_halo_impl<BN, CW, false>(tm_a, tm_b, p, s);
+// tap lists and patch-window offsets of every (class, patch kind)
+void fill_patch_tables(HaloParams& p) {
+  memset(p.patch, 0, sizeof(p.patch));
+  for (int cls = 0; cls < 4; ++cls) {
+    const int a = cls >> 1, b = cls & 1;
+    for (int tap = 0; tap < 9; ++tap) {
+      const int fr = tap / 3, fs = tap % 3;
+      // x patch: plain conv reads the window shifted by (fr-1, fs-1); a parity class reads the low-res patch at
+      // floor((parity + tap - 1) / 2)
+      PatchDesc& px = p.patch[cls][0];
+      const int dy = p.parity ? ((a + fr - 1) >> 1) : fr - 1, dx = p.parity ? ((b + fs - 1) >> 1) : fs - 1;
+      px.tap[px.ntaps] = static_cast<uint8_t>(tap);
+      px.off[px.ntaps] = static_cast<uint8_t>((dy + 1) * PITCH + dx + 1);
+      px.off_by_tap[tap] = px.off[px.ntaps];
+      ++px.ntaps;
+      if (p.parity) {  // skip operand: plane (pr, pc) of the full-res tensor, shifted by (oy - pr) / 2
+        const int oy = a + fr - 1, ox = b + fs - 1;
+        const int pr = oy & 1, pc = ox & 1;
+        PatchDesc& ps = p.patch[cls][1 + pr * 2 + pc];
+        ps.pr = static_cast<uint8_t>(pr); ps.pc = static_cast<uint8_t>(pc);
+        ps.tap[ps.ntaps] = static_cast<uint8_t>(tap);
+        ps.off[ps.ntaps] = static_cast<uint8_t>(((oy - pr) / 2 + 1) * PITCH + (ox - pc) / 2 + 1);
+        ++ps.ntaps;
+      }
+    }
+  }
 }
 
 }  // namespace
@@ -318,31 +362,35 @@ int dt_encode_bf16_map(CUtensorMap* tm, const void* base, int rank, const uint64
                        const uint32_t* box, const uint32_t* elem_strides);
 
 // Returns DT_ERR_UNSUPPORTED when the layer does not fit the halo scheme (caller falls back to conv_tc.cu).
-int dt_conv_halo(const dt_conv_desc* d, int BN, const void* x, const void* w, int Kpad, const float* scale,
-                 const float* shift, const void* residual, void* y, cudaStream_t s) {
-  const bool wide = d->C_in % BK == 0;
-  const bool narrow = d->C_in == 32 || d->C_in == 16;
-  if (d->R != 3 || d->S != 3 || d->stride != 1 || d->pad != 1 || d->upsample || d->C_x != d->C_in ||
-      !(wide || narrow) || d->W % TW != 0 || d->H % TH != 0)
+int dt_conv_halo(const dt_conv_desc* d, int BN, const void* x, const void* skip, const void* w, int Kpad,
+                 const float* scale, const float* shift, const void* residual, void* y, cudaStream_t s) {
+  const int C_s = d->C_in - d->C_x;
+  const bool wide = d->C_in % BK == 0 && d->C_x % BK == 0;
+  const bool narrow = (d->C_in == 32 || d->C_in == 16) && C_s == 0;
+  const int parity = d->upsample ? 1 : 0;
+  const int Hg = parity ? d->H / 2 : d->H, Wg = parity ? d->W / 2 : d->W;
+  if (d->R != 3 || d->S != 3 || d->stride != 1 || d->pad != 1 || !(wide || narrow) || (!parity && C_s != 0) ||
+      Wg % TW != 0 || Hg % TH != 0)
     return DT_ERR_UNSUPPORTED;
   HaloParams p;
   memset(&p, 0, sizeof(p));
-  p.N = d->N; p.H = d->H; p.W = d->W; p.C_in = d->C_in; p.C_out = d->C_out;
-  p.cw = wide ? BK : d->C_in;
-  p.nslab = d->C_in / p.cw;
-  p.k_slab = 9 * p.cw;
-  p.chunks_per_slab = (p.k_slab + BK - 1) / BK;
-  p.pitch = (d->flags & DT_CONV_HALO_P16) ? 16 : 10;
-  p.base_off = (d->flags & DT_CONV_HALO_BASEOFF) ? 1 : 0;
+  const int cw = wide ? BK : d->C_in;
+  p.N = d->N; p.H = d->H; p.W = d->W; p.C_in = d->C_in; p.C_x = d->C_x; p.C_out = d->C_out;
+  p.parity = parity; p.Hg = Hg; p.Wg = Wg;
+  p.n_xslab = d->C_x / cw;
+  p.n_sslab = C_s / BK;
   p.relu = d->relu; p.has_residual = d->has_residual;
-  p.tiles_w = d->W / TW; p.tiles_h = d->H / TH; p.n_tiles = d->C_out / BN;
-  p.total_tiles = p.tiles_w * p.tiles_h * d->N * p.n_tiles;
-  p.a_slot_bytes = ((TH + 2) * p.pitch * p.cw * 2 + 1023) / 1024 * 1024;
+  p.tiles_w = Wg / TW; p.tiles_h = Hg / TH; p.n_tiles = d->C_out / BN;
+  p.tiles_per_class = p.tiles_w * p.tiles_h * d->N;
+  p.total_tiles = p.tiles_per_class * (parity ? 4 : 1) * p.n_tiles;
+  p.a_slot_bytes = (PATCH_PIX * cw * 2 + 1023) / 1024 * 1024;
   p.residual = static_cast<const __nv_bfloat16*>(residual);
   p.y = static_cast<__nv_bfloat16*>(y);
   p.scale = scale; p.shift = shift;
+  fill_patch_tables(p);
 
-  CUtensorMap tm_a, tm_b;
+  CUtensorMap tm_a, tm_s, tm_b;
+  memset(&tm_s, 0, sizeof(tm_s));
   {
     const uint64_t dims[2] = {static_cast<uint64_t>(Kpad), static_cast<uint64_t>(d->C_out)};
     const uint64_t strides[1] = {static_cast<uint64_t>(Kpad) * 2};
@@ -350,17 +398,27 @@ int dt_conv_halo(const dt_conv_desc* d, int BN, const void* x, const void* w, in
     int rc = dt_encode_bf16_map(&tm_b, w, 2, dims, strides, box, nullptr);
     if (rc != DT_OK) return rc;
   }
-  {
-    const uint64_t dims[4] = {static_cast<uint64_t>(d->C_in), static_cast<uint64_t>(d->W), static_cast<uint64_t>(d->H),
+  {  // x operand at the resolution it is stored in (low-res for parity tiles)
+    const uint64_t dims[4] = {static_cast<uint64_t>(d->C_x), static_cast<uint64_t>(Wg), static_cast<uint64_t>(Hg),
                               static_cast<uint64_t>(d->N)};
-    const uint64_t strides[3] = {static_cast<uint64_t>(d->C_in) * 2, static_cast<uint64_t>(d->W) * d->C_in * 2,
-                                 static_cast<uint64_t>(d->H) * d->W * d->C_in * 2};
-    const uint32_t box[4] = {static_cast<uint32_t>(p.cw), static_cast<uint32_t>(p.pitch), TH + 2, 1};
+    const uint64_t strides[3] = {static_cast<uint64_t>(d->C_x) * 2, static_cast<uint64_t>(Wg) * d->C_x * 2,
+                                 static_cast<uint64_t>(Hg) * Wg * d->C_x * 2};
+    const uint32_t box[4] = {static_cast<uint32_t>(cw), PITCH, TH + 2, 1};
     int rc = dt_encode_bf16_map(&tm_a, x, 4, dims, strides, box, nullptr);
     if (rc != DT_OK) return rc;
   }
+  if (p.n_sslab > 0) {  // skip operand: full-res tensor walked with traversal stride 2 (one parity plane per box)
+    const uint64_t dims[4] = {static_cast<uint64_t>(C_s), static_cast<uint64_t>(d->W), static_cast<uint64_t>(d->H),
+                              static_cast<uint64_t>(d->N)};
+    const uint64_t strides[3] = {static_cast<uint64_t>(C_s) * 2, static_cast<uint64_t>(d->W) * C_s * 2,
+                                 static_cast<uint64_t>(d->H) * d->W * C_s * 2};
+    const uint32_t box[4] = {BK, 2 * PITCH, 2 * (TH + 2), 1};
+    const uint32_t estr[4] = {1, 2, 2, 1};
+    int rc = dt_encode_bf16_map(&tm_s, skip, 4, dims, strides, box, estr);
+    if (rc != DT_OK) return rc;
+  }
 #define DT_HALO(BNV, CWV) \
-  if (BN == BNV && p.cw == CWV) return launch_halo<BNV, CWV>(tm_a, tm_b, p, s);
+  if (BN == BNV && cw == CWV) return launch_halo<BNV, CWV>(tm_a, tm_s, tm_b, p, s);
   DT_HALO(16, 64) DT_HALO(32, 64) DT_HALO(64, 64) DT_HALO(128, 64) DT_HALO(256, 64)
   DT_HALO(16, 32) DT_HALO(32, 32) DT_HALO(64, 32)
   DT_HALO(16, 16) DT_HALO(32, 16) DT_HALO(64, 16)

@@ -1,0 +1,312 @@
+// 3x3 / stride-1 / pad-1 convolution for layers whose whole weight tensor fits in shared memory
+// (C_in <= 64 and C_out <= 64: resnet layer1, the decoder's 64/32/16-channel tail) - tcgen05 implicit GEMM.
+//
+// The packed weights [C_out][9*C_in] are loaded ONCE per CTA and stay resident; the only per-tile traffic is
+// one TMA box with the input halo patch.  A "super tile" is 8 (w) x 16*MT (h) output pixels = MT UMMA M=128
+// tiles that share one patch of (16*MT+2) x (8+2) pixels and one set of pipeline hand-shakes, so the fixed cost
+// per tile (barrier round trips, instruction issue) is amortised over MT*128 pixels - these layers are
+// HBM / issue bound, not tensor bound.  Taps read the patch in place through shifted UMMA descriptors
+// (see conv_halo.cu).  Parity mode (nearest-x2 up-sampled input without skip, decoder block 4) reads the low-res
+// patch at ((a+r-1)>>1, (b+s-1)>>1) and writes the pixels of parity class (a,b).
+//
+//   warp 0: TMA producer   warp 1: TMEM alloc + MMA issuer   warps 2..5: epilogue (TMEM -> scale/shift/residual/ReLU)
+// Persistent CTAs; TMEM holds two buffers of MT accumulators so the epilogue overlaps the next super tile.
+#include <cstring>
+#include <mutex>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int TW = 8, TH = 16;
+constexpr int kThreads = 192;
+constexpr int MAX_A = 4;
+constexpr int PITCH = TW + 2;
+
+struct ResParams {
+  int N, H, W, C_out;            // H, W: output size
+  int parity, Hg, Wg;            // tile grid: (H, W) or (H/2, W/2)
+  int a_slots, a_slot_bytes;
+  int relu, has_residual;
+  int tiles_w, tiles_h, tiles_per_class, total_tiles;
+  const __nv_bfloat16* residual;
+  __nv_bfloat16* y;
+  const float* scale;
+  const float* shift;
+  uint8_t off[4][12];            // [class][tap] pixel offset of the tap's window inside the patch
+};
+
+struct Geo {
+  int cls, n, h0, w0;
+};
+template <int MT>
+__device__ __forceinline__ Geo geo(const ResParams& p, int tile) {
+  Geo g;
+  g.cls = tile / p.tiles_per_class;
+  int m = tile - g.cls * p.tiles_per_class;
+  g.w0 = (m % p.tiles_w) * TW; m /= p.tiles_w;
+  g.h0 = (m % p.tiles_h) * (TH * MT);
+  g.n = m / p.tiles_h;
+  return g;
+}
+
+template <int BN, int CW, int MT>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_res_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                const ResParams p) {
+  constexpr int B_BYTES = BN * BK * 2;
+  constexpr int NCH = (9 * CW + BK - 1) / BK;               // weight chunks of 64 K elements
+  constexpr int W_BYTES = NCH * B_BYTES;
+  constexpr int ROW_BYTES = CW * 2;
+  constexpr int PATCH_BYTES = (TH * MT + 2) * PITCH * ROW_BYTES;
+  constexpr int TMEM_USED = 2 * MT * BN;
+  constexpr int TMEM_COLS = TMEM_USED <= 32 ? 32 : (TMEM_USED <= 64 ? 64 : (TMEM_USED <= 128 ? 128 : (TMEM_USED <= 256 ? 256 : 512)));
+  constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_w = smem;                                   // resident weights, NCH chunks
+  uint8_t* smem_a = smem + ((W_BYTES + 1023) / 1024) * 1024;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + p.a_slots * p.a_slot_bytes);
+  uint64_t* w_full = bars;                 // [1]
+  uint64_t* full_a = w_full + 1;           // [MAX_A]
+  uint64_t* empty_a = full_a + MAX_A;      // [MAX_A]
+  uint64_t* tmem_full = empty_a + MAX_A;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_b);
+    mbar_init(w_full, 1u);
+    for (int i = 0; i < p.a_slots; ++i) { mbar_init(&full_a[i], 1u); mbar_init(&empty_a[i], 1u); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1u); mbar_init(&tmem_empty[i], 128u); }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(w_full, W_BYTES);
+      for (int q = 0; q < NCH; ++q) tma_load_2d(smem_w + q * B_BYTES, &tm_b, w_full, q * BK, 0);
+      int sa = 0;
+      uint32_t pa = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const Geo g = geo<MT>(p, tile);
+        mbar_wait(&empty_a[sa], pa ^ 1u);
+        mbar_arrive_expect_tx(&full_a[sa], PATCH_BYTES);
+        tma_load_4d(smem_a + sa * p.a_slot_bytes, &tm_a, &full_a[sa], 0, g.w0 - 1, g.h0 - 1, g.n);
+        if (++sa == p.a_slots) { sa = 0; pa ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint64_t a_hi = umma_desc(0u, PITCH * ROW_BYTES, CW == 64 ? 2u : (CW == 32 ? 4u : 6u));
+      const uint64_t b_d0 = umma_desc(smem_u32(smem_w), 1024u, 2u);
+      mbar_wait(w_full, 0);
+      int sa = 0, buf = 0;
+      uint32_t pa = 0, pbuf = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int cls = tile / p.tiles_per_class;
+        uint32_t off[9];                       // this class's tap window offsets, in 16-byte units
+#pragma unroll
+        for (int t = 0; t < 9; ++t) off[t] = (static_cast<uint32_t>(p.off[cls][t]) * ROW_BYTES) >> 4;
+        mbar_wait(&tmem_empty[buf], pbuf ^ 1u);
+        mbar_wait(&full_a[sa], pa);
+        tc_fence_after();
+        const uint64_t a_d = a_hi + (smem_u32(smem_a + sa * p.a_slot_bytes) >> 4);
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          const uint32_t d_tmem = tmem_base + (buf * MT + mt) * BN;
+          const uint64_t a_m = a_d + ((mt * TH * PITCH * ROW_BYTES) >> 4);
+#pragma unroll
+          for (int q = 0; q < NCH; ++q) {
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              const int kk = q * BK + k * 16;  // K index = tap * CW + channel (compile time)
+              if (kk < 9 * CW) {
+                const int tap = kk / CW, ch = kk % CW;
+                umma_bf16_ss(d_tmem, a_m + off[tap] + ((ch * 2) >> 4), b_d0 + ((q * B_BYTES + k * 32) >> 4), idesc,
+                             kk == 0 ? 0u : 1u);
+              }
+            }
+          }
+        }
+        umma_commit(&empty_a[sa]);
+        umma_commit(&tmem_full[buf]);
+        if (++sa == p.a_slots) { sa = 0; pa ^= 1u; }
+        if ((buf ^= 1) == 0) pbuf ^= 1u;
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    int buf = 0;
+    uint32_t pbuf = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const Geo g = geo<MT>(p, tile);
+      mbar_wait(&tmem_full[buf], pbuf);
+      tc_fence_after();
+#pragma unroll 1
+      for (int mt = 0; mt < MT; ++mt) {
+        int oy = g.h0 + mt * TH + (row >> 3), ox = g.w0 + (row & 7);
+        if (p.parity) { oy = 2 * oy + (g.cls >> 1); ox = 2 * ox + (g.cls & 1); }
+        const int64_t out_off = ((static_cast<int64_t>(g.n) * p.H + oy) * p.W + ox) * p.C_out;
+        const uint32_t t_row = tmem_base + (buf * MT + mt) * BN + (static_cast<uint32_t>(quarter * 32) << 16);
+        uint4 res[BN / 8];
+        if (p.has_residual) {
+#pragma unroll
+          for (int j = 0; j < BN / 8; ++j) res[j] = __ldg(reinterpret_cast<const uint4*>(p.residual + out_off) + j);
+        }
+#pragma unroll
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld_x16(t_row + c0, v);
+          tmem_ld_wait();
+          float f[16];
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + c0 + j));
+            const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + c0 + j));
+            f[j] = fmaf(__uint_as_float(v[j]), sc.x, sh.x);
+            f[j + 1] = fmaf(__uint_as_float(v[j + 1]), sc.y, sh.y);
+            f[j + 2] = fmaf(__uint_as_float(v[j + 2]), sc.z, sh.z);
+            f[j + 3] = fmaf(__uint_as_float(v[j + 3]), sc.w, sh.w);
+          }
+          if (p.has_residual) {
+            const uint32_t rr[8] = {res[c0 / 8].x, res[c0 / 8].y, res[c0 / 8].z, res[c0 / 8].w,
+                                    res[c0 / 8 + 1].x, res[c0 / 8 + 1].y, res[c0 / 8 + 1].z, res[c0 / 8 + 1].w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float2 t = unpack_bf16x2(rr[j]);
+              f[2 * j] += t.x;
+              f[2 * j + 1] += t.y;
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+          }
+          uint4* op = reinterpret_cast<uint4*>(p.y + out_off + c0);
+          op[0] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                             pack_bf16x2(f[6], f[7]));
+          op[1] = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]),
+                             pack_bf16x2(f[14], f[15]));
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[buf]);
+      if ((buf ^= 1) == 0) pbuf ^= 1u;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+template <int BN, int CW, int MT>
+int launch_res(const CUtensorMap& tm_a, const CUtensorMap& tm_b, ResParams& p, cudaStream_t s) {
+  constexpr int B_BYTES = BN * BK * 2;
+  constexpr int NCH = (9 * CW + BK - 1) / BK;
+  constexpr int W_BYTES = ((NCH * B_BYTES + 1023) / 1024) * 1024;
+  p.a_slot_bytes = (((TH * MT + 2) * PITCH * CW * 2) + 1023) / 1024 * 1024;
+  int a_slots = (200 * 1024 - W_BYTES) / p.a_slot_bytes;
+  if (a_slots > MAX_A) a_slots = MAX_A;
+  if (a_slots < 2) return DT_ERR_UNSUPPORTED;
+  p.a_slots = a_slots;
+  const int smem = W_BYTES + a_slots * p.a_slot_bytes + 1024 + 256;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(conv_res_kernel<BN, CW, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+  });
+  DT_CUDA(attr_err);
+  // co-resident CTAs (their issue threads work in parallel): limited by shared memory and TMEM columns
+  constexpr int TMEM_USED = 2 * MT * BN;
+  constexpr int TMEM_COLS = TMEM_USED <= 32 ? 32 : (TMEM_USED <= 64 ? 64 : (TMEM_USED <= 128 ? 128 : (TMEM_USED <= 256 ? 256 : 512)));
+  int ctas = (220 * 1024) / (smem + 1024);
+  if (ctas > 512 / TMEM_COLS) ctas = 512 / TMEM_COLS;
+  if (ctas > 3) ctas = 3;
+  if (ctas < 1) ctas = 1;
+  const int slots = dt_num_sms() * ctas;
+  const int grid = p.total_tiles < slots ? p.total_tiles : slots;
+  conv_res_kernel<BN, CW, MT><<<grid, kThreads, smem, s>>>(tm_a, tm_b, p);
+  DT_LAUNCH_CHECK();
+  return DT_OK;
+}
+
+}  // namespace
+
+int dt_encode_bf16_map(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                       const uint32_t* box, const uint32_t* elem_strides);
+
+// Returns DT_ERR_UNSUPPORTED when the layer does not fit (caller falls back to conv_halo.cu / conv_tc.cu).
+int dt_conv_res(const dt_conv_desc* d, const void* x, const void* w, int Kpad, const float* scale, const float* shift,
+                const void* residual, void* y, cudaStream_t s) {
+  const int parity = d->upsample ? 1 : 0;
+  const int Hg = parity ? d->H / 2 : d->H, Wg = parity ? d->W / 2 : d->W;
+  const int cw = d->C_in, bn = d->C_out;
+  if (d->R != 3 || d->S != 3 || d->stride != 1 || d->pad != 1 || d->C_x != d->C_in ||
+      !(cw == 64 || cw == 32 || cw == 16) || !(bn == 64 || bn == 32 || bn == 16) || Wg % TW != 0 || Hg % TH != 0)
+    return DT_ERR_UNSUPPORTED;
+  // M tiles per patch: as many as TMEM (2 buffers x MT x BN columns <= 512), the image height and smem allow
+  int mt = bn == 64 ? 2 : 4;
+  while (mt > 1 && Hg % (TH * mt) != 0) mt >>= 1;
+  ResParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = d->N; p.H = d->H; p.W = d->W; p.C_out = d->C_out;
+  p.parity = parity; p.Hg = Hg; p.Wg = Wg;
+  p.relu = d->relu; p.has_residual = d->has_residual;
+  p.tiles_w = Wg / TW; p.tiles_h = Hg / (TH * mt);
+  p.tiles_per_class = p.tiles_w * p.tiles_h * d->N;
+  p.total_tiles = p.tiles_per_class * (parity ? 4 : 1);
+  p.residual = static_cast<const __nv_bfloat16*>(residual);
+  p.y = static_cast<__nv_bfloat16*>(y);
+  p.scale = scale; p.shift = shift;
+  for (int cls = 0; cls < 4; ++cls) {
+    const int a = cls >> 1, b = cls & 1;
+    for (int tap = 0; tap < 9; ++tap) {
+      const int fr = tap / 3, fs = tap % 3;
+      const int dy = parity ? ((a + fr - 1) >> 1) : fr - 1, dx = parity ? ((b + fs - 1) >> 1) : fs - 1;
+      p.off[cls][tap] = static_cast<uint8_t>((dy + 1) * PITCH + dx + 1);
+    }
+  }
+  CUtensorMap tm_a, tm_b;
+  {
+    const uint64_t dims[2] = {static_cast<uint64_t>(Kpad), static_cast<uint64_t>(d->C_out)};
+    const uint64_t strides[1] = {static_cast<uint64_t>(Kpad) * 2};
+    const uint32_t box[2] = {BK, static_cast<uint32_t>(bn)};
+    int rc = dt_encode_bf16_map(&tm_b, w, 2, dims, strides, box, nullptr);
+    if (rc != DT_OK) return rc;
+  }
+  {
+    const uint64_t dims[4] = {static_cast<uint64_t>(cw), static_cast<uint64_t>(Wg), static_cast<uint64_t>(Hg),
+                              static_cast<uint64_t>(d->N)};
+    const uint64_t strides[3] = {static_cast<uint64_t>(cw) * 2, static_cast<uint64_t>(Wg) * cw * 2,
+                                 static_cast<uint64_t>(Hg) * Wg * cw * 2};
+    const uint32_t box[4] = {static_cast<uint32_t>(cw), PITCH, static_cast<uint32_t>(TH * mt + 2), 1};
+    int rc = dt_encode_bf16_map(&tm_a, x, 4, dims, strides, box, nullptr);
+    if (rc != DT_OK) return rc;
+  }
+#define DT_RES(BNV, CWV, MTV) \
+  if (bn == BNV && cw == CWV && mt == MTV) return launch_res<BNV, CWV, MTV>(tm_a, tm_b, p, s);
+#define DT_RES_MT(BNV, CWV) DT_RES(BNV, CWV, 1) DT_RES(BNV, CWV, 2) DT_RES(BNV, CWV, 4)
+  DT_RES(64, 64, 1) DT_RES(64, 64, 2)
+  DT_RES_MT(32, 64) DT_RES_MT(32, 32) DT_RES_MT(16, 32) DT_RES_MT(16, 16) DT_RES_MT(32, 16) DT_RES_MT(16, 64)
+#undef DT_RES_MT
+#undef DT_RES
+  return DT_ERR_UNSUPPORTED;
+}

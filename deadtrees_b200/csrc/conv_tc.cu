@@ -473,8 +473,11 @@ int dt_encode_bf16_map(CUtensorMap* tm, const void* base, int rank, const uint64
                        const uint32_t* box, const uint32_t* elem_strides) {
   return encode_bf16_map(tm, base, rank, dims, strides_bytes, box, elem_strides);
 }
-int dt_conv_halo(const dt_conv_desc* d, int BN, const void* x, const void* w, int Kpad, const float* scale,
-                 const float* shift, const void* residual, void* y, cudaStream_t s);
+int dt_conv_halo(const dt_conv_desc* d, int BN, const void* x, const void* skip, const void* w, int Kpad,
+                 const float* scale, const float* shift, const void* residual, void* y, cudaStream_t s);
+
+int dt_conv_res(const dt_conv_desc* d, const void* x, const void* w, int Kpad, const float* scale, const float* shift,
+                const void* residual, void* y, cudaStream_t s);
 
 extern "C" int dt_conv2d_fwd(const dt_conv_desc* d, const void* x, const void* skip, const void* w,
                              const float* scale, const float* shift, const void* residual, void* y,
@@ -517,7 +520,9 @@ extern "C" int dt_conv2d_fwd(const dt_conv_desc* d, const void* x, const void* s
              "dt_conv2d_fwd: unsupported C_out %d", d->C_out);
 
   if (!(d->flags & (DT_CONV_NO_HALO | DT_CONV_FORCE_GATHER)) && !stem) {
-    const int rc = dt_conv_halo(d, BN, x, w, Kpad, scale, shift, residual, y, s);
+    const int rc0 = dt_conv_res(d, x, w, Kpad, scale, shift, residual, y, s);   // weights resident in smem
+    if (rc0 != DT_ERR_UNSUPPORTED) return rc0;
+    const int rc = dt_conv_halo(d, BN, x, skip, w, Kpad, scale, shift, residual, y, s);
     if (rc != DT_ERR_UNSUPPORTED) return rc;   // not a 3x3/s1 layer of a fitting shape: per-tap path below
   }
 

@@ -115,11 +115,8 @@ typedef struct {
 enum {
   DT_CONV_FORCE_GATHER = 1, /* A operand through the generic gather producer even if TMA-eligible */
   DT_CONV_FORCE_DIRECT = 2, /* CUDA-core direct kernel for bf16 tensors (debug/validation) */
-  DT_CONV_NO_HALO = 4,      /* 3x3/s1 layers: per-tap TMA boxes (conv_tc.cu) instead of the smem-resident halo
-                               patch (conv_halo.cu, the default where the shape fits) */
-  DT_CONV_HALO_P16 = 8,     /* experiment (scripts/halo_exp.py): halo patch row pitch 16 pixels instead of 10 */
-  DT_CONV_HALO_BASEOFF = 16 /* experiment: fill the UMMA descriptor base-offset field (gives wrong results: the
-                               swizzle is a function of the absolute smem address) */
+  DT_CONV_NO_HALO = 4       /* 3x3/s1 layers: per-tap TMA boxes (conv_tc.cu) instead of the smem-resident halo
+                               patches (conv_halo.cu, the default where the shape fits) */
 };
 
 int dt_conv2d_fwd(const dt_conv_desc* desc, const void* x, const void* skip, const void* w, const float* scale,

@@ -21,6 +21,7 @@ LAYERS = [
     ("l2.0.downsample 1x1 s2", 2, 64, 64, 0, 128, 1, 2, 0, False, False, False),
     ("l4.0.conv1 256->512 s2 @16", 4, 16, 256, 0, 512, 3, 2, 1, False, False, True),
     ("d0.conv1 up(512)+256 -> 256 @16", 2, 16, 512, 256, 256, 3, 1, 1, True, False, True),
+    ("d1.conv1 up(256)+128 -> 128 @32", 2, 32, 256, 128, 128, 3, 1, 1, True, False, True),
     ("d3.conv1 up(64)+64 -> 32 @128", 1, 128, 64, 64, 32, 3, 1, 1, True, False, True),
     ("d3.conv2 32->32 @128", 1, 128, 32, 0, 32, 3, 1, 1, False, False, True),
     ("d4.conv1 up(32) -> 16 @64", 2, 64, 32, 0, 16, 3, 1, 1, True, False, True),
