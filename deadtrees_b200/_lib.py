@@ -15,7 +15,7 @@ _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "libdeadtrees_b200.so"
 
 DT_BF16, DT_F32 = 0, 1
-CONV_FORCE_GATHER, CONV_FORCE_DIRECT, CONV_NO_HALO = 1, 2, 4
+CONV_FORCE_GATHER, CONV_FORCE_DIRECT, CONV_NO_HALO, CONV_X_PAD3 = 1, 2, 4, 8
 
 
 class DeadtreesB200Error(RuntimeError):
@@ -37,7 +37,7 @@ _SIGNATURES = {
     "dt_make_blocks": ([_p, _i, _i, _i, _i, _i, _p, _p], C.c_int),
     "dt_unmake_blocks": ([_p, _i, _i, _i, _i, _p, _p], C.c_int),
     "dt_tile_gather_normalize": ([_p, _i, _i, _i, _i64, _i64, _i64, _i, _i, _i, _i, _i,
-                                  C.POINTER(_f), C.POINTER(_f), _i, _i, _p, _p], C.c_int),
+                                  C.POINTER(_f), C.POINTER(_f), _i, _i, _i, _p, _p], C.c_int),
     "dt_pack_input_nchw": ([_p, _i, _i, _i, _i, _i, _i, _p, _p], C.c_int),
     "dt_stitch_mask_u8": ([_p, _i, _i, _i, _i, _p, _i, _i, _i64, _p], C.c_int),
     "dt_stitch_blend_argmax": ([_p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _i, _i, _i, _i, _p], C.c_int),

@@ -6,8 +6,9 @@
 // tiles that share one patch of (16*MT+2) x (8+2) pixels and one set of pipeline hand-shakes, so the fixed cost
 // per tile (barrier round trips, instruction issue) is amortised over MT*128 pixels - these layers are
 // HBM / issue bound, not tensor bound.  Taps read the patch in place through shifted UMMA descriptors
-// (see conv_halo.cu).  Parity mode (nearest-x2 up-sampled input without skip, decoder block 4) reads the low-res
-// patch at ((a+r-1)>>1, (b+s-1)>>1) and writes the pixels of parity class (a,b).
+// (see conv_halo.cu).  Parity mode (nearest-x2 up-sampled input without skip, decoder block 4): the MT = 4 M tiles of
+// a super tile are the four output-pixel parity classes (a,b) of one 16 x 8 LOW-RES region; class (a,b) reads the
+// shared low-res patch at ((a+r-1)>>1, (b+s-1)>>1) and writes pixels (2i+a, 2j+b), so the low-res input is read once.
 //
 //   warp 0: TMA producer   warp 1: TMEM alloc + MMA issuer   warps 2..5: epilogue (TMEM -> scale/shift/residual/ReLU)
 // Persistent CTAs; TMEM holds two buffers of MT accumulators so the epilogue overlaps the next super tile.
@@ -30,29 +31,38 @@ struct ResParams {
   int parity, Hg, Wg;            // tile grid: (H, W) or (H/2, W/2)
   int a_slots, a_slot_bytes;
   int relu, has_residual;
-  int tiles_w, tiles_h, tiles_per_class, total_tiles;
+  int tiles_w, tiles_h, total_tiles;
   const __nv_bfloat16* residual;
   __nv_bfloat16* y;
   const float* scale;
   const float* shift;
-  uint8_t off[4][12];            // [class][tap] pixel offset of the tap's window inside the patch
 };
 
 struct Geo {
-  int cls, n, h0, w0;
+  int n, h0, w0;
 };
-template <int MT>
+template <int ROWS_PER_TILE>
 __device__ __forceinline__ Geo geo(const ResParams& p, int tile) {
   Geo g;
-  g.cls = tile / p.tiles_per_class;
-  int m = tile - g.cls * p.tiles_per_class;
+  int m = tile;
   g.w0 = (m % p.tiles_w) * TW; m /= p.tiles_w;
-  g.h0 = (m % p.tiles_h) * (TH * MT);
+  g.h0 = (m % p.tiles_h) * ROWS_PER_TILE;
   g.n = m / p.tiles_h;
   return g;
 }
 
-template <int BN, int CW, int MT>
+// pixel offset of tap (fr, fs)'s window inside the patch for M tile `mt` (compile-time in the unrolled issue loop)
+template <bool PAR>
+__device__ __forceinline__ constexpr int tap_pixel_offset(int mt, int tap) {
+  const int fr = tap / 3, fs = tap % 3;
+  if (PAR) {  // mt = parity class (a,b): floor((a + fr - 1) / 2) + 1 rows into the low-res patch
+    const int a = mt >> 1, b = mt & 1;
+    return (((a + fr + 1) >> 1)) * PITCH + ((b + fs + 1) >> 1);
+  }
+  return (mt * TH + fr) * PITCH + fs;
+}
+
+template <int BN, int CW, int MT, bool PAR>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_res_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                 const ResParams p) {
@@ -60,7 +70,8 @@ conv_res_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   constexpr int NCH = (9 * CW + BK - 1) / BK;               // weight chunks of 64 K elements
   constexpr int W_BYTES = NCH * B_BYTES;
   constexpr int ROW_BYTES = CW * 2;
-  constexpr int PATCH_BYTES = (TH * MT + 2) * PITCH * ROW_BYTES;
+  constexpr int TILE_ROWS = PAR ? TH : TH * MT;             // rows of the tile grid one super tile covers
+  constexpr int PATCH_BYTES = (TILE_ROWS + 2) * PITCH * ROW_BYTES;
   constexpr int TMEM_USED = 2 * MT * BN;
   constexpr int TMEM_COLS = TMEM_USED <= 32 ? 32 : (TMEM_USED <= 64 ? 64 : (TMEM_USED <= 128 ? 128 : (TMEM_USED <= 256 ? 256 : 512)));
   constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
@@ -101,7 +112,7 @@ conv_res_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       int sa = 0;
       uint32_t pa = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const Geo g = geo<MT>(p, tile);
+        const Geo g = geo<TILE_ROWS>(p, tile);
         mbar_wait(&empty_a[sa], pa ^ 1u);
         mbar_arrive_expect_tx(&full_a[sa], PATCH_BYTES);
         tma_load_4d(smem_a + sa * p.a_slot_bytes, &tm_a, &full_a[sa], 0, g.w0 - 1, g.h0 - 1, g.n);
@@ -116,28 +127,25 @@ conv_res_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       int sa = 0, buf = 0;
       uint32_t pa = 0, pbuf = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int cls = tile / p.tiles_per_class;
-        uint32_t off[9];                       // this class's tap window offsets, in 16-byte units
-#pragma unroll
-        for (int t = 0; t < 9; ++t) off[t] = (static_cast<uint32_t>(p.off[cls][t]) * ROW_BYTES) >> 4;
         mbar_wait(&tmem_empty[buf], pbuf ^ 1u);
         mbar_wait(&full_a[sa], pa);
         tc_fence_after();
         const uint64_t a_d = a_hi + (smem_u32(smem_a + sa * p.a_slot_bytes) >> 4);
+        // k-step outer, M tile inner: consecutive MMAs go to DIFFERENT accumulators, so the tensor pipe never
+        // waits on the read-modify-write latency of one accumulator (matters for the N = 16 / 32 layers)
 #pragma unroll
-        for (int mt = 0; mt < MT; ++mt) {
-          const uint32_t d_tmem = tmem_base + (buf * MT + mt) * BN;
-          const uint64_t a_m = a_d + ((mt * TH * PITCH * ROW_BYTES) >> 4);
+        for (int q = 0; q < NCH; ++q) {
 #pragma unroll
-          for (int q = 0; q < NCH; ++q) {
+          for (int k = 0; k < BK / 16; ++k) {
+            const int kk = q * BK + k * 16;  // K index = tap * CW + channel (compile time)
+            if (kk < 9 * CW) {
+              const int tap = kk / CW, ch = kk % CW;
+              const uint64_t b_k = b_d0 + ((q * B_BYTES + k * 32) >> 4);
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k) {
-              const int kk = q * BK + k * 16;  // K index = tap * CW + channel (compile time)
-              if (kk < 9 * CW) {
-                const int tap = kk / CW, ch = kk % CW;
-                umma_bf16_ss(d_tmem, a_m + off[tap] + ((ch * 2) >> 4), b_d0 + ((q * B_BYTES + k * 32) >> 4), idesc,
+              for (int mt = 0; mt < MT; ++mt)
+                umma_bf16_ss(tmem_base + (buf * MT + mt) * BN,
+                             a_d + ((tap_pixel_offset<PAR>(mt, tap) * ROW_BYTES + ch * 2) >> 4), b_k, idesc,
                              kk == 0 ? 0u : 1u);
-              }
             }
           }
         }
@@ -153,19 +161,28 @@ conv_res_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     int buf = 0;
     uint32_t pbuf = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const Geo g = geo<MT>(p, tile);
+      const Geo g = geo<TILE_ROWS>(p, tile);
+      auto pixel_off = [&](int mt) {
+        int oy = g.h0 + (PAR ? 0 : mt * TH) + (row >> 3), ox = g.w0 + (row & 7);
+        if (PAR) { oy = 2 * oy + (mt >> 1); ox = 2 * ox + (mt & 1); }
+        return ((static_cast<int64_t>(g.n) * p.H + oy) * p.W + ox) * p.C_out;
+      };
+      uint4 res[BN / 8], res_next[BN / 8];
+      if (p.has_residual) {   // first residual line is in flight while the MMAs of this super tile run
+        const int64_t o0 = pixel_off(0);
+#pragma unroll
+        for (int j = 0; j < BN / 8; ++j) res[j] = __ldg(reinterpret_cast<const uint4*>(p.residual + o0) + j);
+      }
       mbar_wait(&tmem_full[buf], pbuf);
       tc_fence_after();
 #pragma unroll 1
       for (int mt = 0; mt < MT; ++mt) {
-        int oy = g.h0 + mt * TH + (row >> 3), ox = g.w0 + (row & 7);
-        if (p.parity) { oy = 2 * oy + (g.cls >> 1); ox = 2 * ox + (g.cls & 1); }
-        const int64_t out_off = ((static_cast<int64_t>(g.n) * p.H + oy) * p.W + ox) * p.C_out;
+        const int64_t out_off = pixel_off(mt);
         const uint32_t t_row = tmem_base + (buf * MT + mt) * BN + (static_cast<uint32_t>(quarter * 32) << 16);
-        uint4 res[BN / 8];
-        if (p.has_residual) {
+        if (p.has_residual && mt + 1 < MT) {
+          const int64_t o1 = pixel_off(mt + 1);
 #pragma unroll
-          for (int j = 0; j < BN / 8; ++j) res[j] = __ldg(reinterpret_cast<const uint4*>(p.residual + out_off) + j);
+          for (int j = 0; j < BN / 8; ++j) res_next[j] = __ldg(reinterpret_cast<const uint4*>(p.residual + o1) + j);
         }
 #pragma unroll
         for (int c0 = 0; c0 < BN; c0 += 16) {
@@ -202,6 +219,10 @@ conv_res_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           op[1] = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]),
                              pack_bf16x2(f[14], f[15]));
         }
+        if (p.has_residual) {
+#pragma unroll
+          for (int j = 0; j < BN / 8; ++j) res[j] = res_next[j];
+        }
       }
       tc_fence_before();
       mbar_arrive(&tmem_empty[buf]);
@@ -217,33 +238,34 @@ conv_res_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   }
 }
 
-template <int BN, int CW, int MT>
+template <int BN, int CW, int MT, bool PAR>
 int launch_res(const CUtensorMap& tm_a, const CUtensorMap& tm_b, ResParams& p, cudaStream_t s) {
   constexpr int B_BYTES = BN * BK * 2;
   constexpr int NCH = (9 * CW + BK - 1) / BK;
   constexpr int W_BYTES = ((NCH * B_BYTES + 1023) / 1024) * 1024;
-  p.a_slot_bytes = (((TH * MT + 2) * PITCH * CW * 2) + 1023) / 1024 * 1024;
-  int a_slots = (200 * 1024 - W_BYTES) / p.a_slot_bytes;
-  if (a_slots > MAX_A) a_slots = MAX_A;
-  if (a_slots < 2) return DT_ERR_UNSUPPORTED;
-  p.a_slots = a_slots;
-  const int smem = W_BYTES + a_slots * p.a_slot_bytes + 1024 + 256;
+  constexpr int TMEM_USED = 2 * MT * BN;
+  constexpr int TMEM_COLS = TMEM_USED <= 32 ? 32 : (TMEM_USED <= 64 ? 64 : (TMEM_USED <= 128 ? 128 : (TMEM_USED <= 256 ? 256 : 512)));
+  constexpr int TILE_ROWS = PAR ? TH : TH * MT;
+  p.a_slot_bytes = (((TILE_ROWS + 2) * PITCH * CW * 2) + 1023) / 1024 * 1024;
+  // co-resident CTAs (their issue threads and epilogues work in parallel): as many as TMEM and shared memory allow
+  int ctas = 512 / TMEM_COLS < 2 ? 512 / TMEM_COLS : 2, a_slots = 0;   // 3 CTAs / SM measured slower (HBM-bound layers)
+  for (; ctas >= 1; --ctas) {
+    a_slots = (225 * 1024 / ctas - 2048 - W_BYTES - 1280) / p.a_slot_bytes;
+    if (a_slots >= 2) break;
+  }
+  if (ctas < 1) return DT_ERR_UNSUPPORTED;
+  p.a_slots = a_slots > MAX_A ? MAX_A : a_slots;
+  const int smem = W_BYTES + p.a_slots * p.a_slot_bytes + 1024 + 256;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(conv_res_kernel<BN, CW, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+    attr_err = cudaFuncSetAttribute(conv_res_kernel<BN, CW, MT, PAR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    225 * 1024);
   });
   DT_CUDA(attr_err);
-  // co-resident CTAs (their issue threads work in parallel): limited by shared memory and TMEM columns
-  constexpr int TMEM_USED = 2 * MT * BN;
-  constexpr int TMEM_COLS = TMEM_USED <= 32 ? 32 : (TMEM_USED <= 64 ? 64 : (TMEM_USED <= 128 ? 128 : (TMEM_USED <= 256 ? 256 : 512)));
-  int ctas = (220 * 1024) / (smem + 1024);
-  if (ctas > 512 / TMEM_COLS) ctas = 512 / TMEM_COLS;
-  if (ctas > 3) ctas = 3;
-  if (ctas < 1) ctas = 1;
   const int slots = dt_num_sms() * ctas;
   const int grid = p.total_tiles < slots ? p.total_tiles : slots;
-  conv_res_kernel<BN, CW, MT><<<grid, kThreads, smem, s>>>(tm_a, tm_b, p);
+  conv_res_kernel<BN, CW, MT, PAR><<<grid, kThreads, smem, s>>>(tm_a, tm_b, p);
   DT_LAUNCH_CHECK();
   return DT_OK;
 }
@@ -262,28 +284,22 @@ int dt_conv_res(const dt_conv_desc* d, const void* x, const void* w, int Kpad, c
   if (d->R != 3 || d->S != 3 || d->stride != 1 || d->pad != 1 || d->C_x != d->C_in ||
       !(cw == 64 || cw == 32 || cw == 16) || !(bn == 64 || bn == 32 || bn == 16) || Wg % TW != 0 || Hg % TH != 0)
     return DT_ERR_UNSUPPORTED;
-  // M tiles per patch: as many as TMEM (2 buffers x MT x BN columns <= 512), the image height and smem allow
-  int mt = bn == 64 ? 2 : 4;
-  while (mt > 1 && Hg % (TH * mt) != 0) mt >>= 1;
+  // M tiles per patch: the four parity classes, or as many row blocks as TMEM (2 buffers x MT x BN columns <= 512)
+  // and the image height allow
+  int mt = parity ? 4 : (bn == 64 ? 2 : 4);
+  while (!parity && mt > 1 && Hg % (TH * mt) != 0) mt >>= 1;
+  if (parity && bn > 32) return DT_ERR_UNSUPPORTED;
+  const int tile_rows = parity ? TH : TH * mt;
   ResParams p;
   memset(&p, 0, sizeof(p));
   p.N = d->N; p.H = d->H; p.W = d->W; p.C_out = d->C_out;
   p.parity = parity; p.Hg = Hg; p.Wg = Wg;
   p.relu = d->relu; p.has_residual = d->has_residual;
-  p.tiles_w = Wg / TW; p.tiles_h = Hg / (TH * mt);
-  p.tiles_per_class = p.tiles_w * p.tiles_h * d->N;
-  p.total_tiles = p.tiles_per_class * (parity ? 4 : 1);
+  p.tiles_w = Wg / TW; p.tiles_h = Hg / tile_rows;
+  p.total_tiles = p.tiles_w * p.tiles_h * d->N;
   p.residual = static_cast<const __nv_bfloat16*>(residual);
   p.y = static_cast<__nv_bfloat16*>(y);
   p.scale = scale; p.shift = shift;
-  for (int cls = 0; cls < 4; ++cls) {
-    const int a = cls >> 1, b = cls & 1;
-    for (int tap = 0; tap < 9; ++tap) {
-      const int fr = tap / 3, fs = tap % 3;
-      const int dy = parity ? ((a + fr - 1) >> 1) : fr - 1, dx = parity ? ((b + fs - 1) >> 1) : fs - 1;
-      p.off[cls][tap] = static_cast<uint8_t>((dy + 1) * PITCH + dx + 1);
-    }
-  }
   CUtensorMap tm_a, tm_b;
   {
     const uint64_t dims[2] = {static_cast<uint64_t>(Kpad), static_cast<uint64_t>(d->C_out)};
@@ -297,15 +313,17 @@ int dt_conv_res(const dt_conv_desc* d, const void* x, const void* w, int Kpad, c
                               static_cast<uint64_t>(d->N)};
     const uint64_t strides[3] = {static_cast<uint64_t>(cw) * 2, static_cast<uint64_t>(Wg) * cw * 2,
                                  static_cast<uint64_t>(Hg) * Wg * cw * 2};
-    const uint32_t box[4] = {static_cast<uint32_t>(cw), PITCH, static_cast<uint32_t>(TH * mt + 2), 1};
+    const uint32_t box[4] = {static_cast<uint32_t>(cw), PITCH, static_cast<uint32_t>(tile_rows + 2), 1};
     int rc = dt_encode_bf16_map(&tm_a, x, 4, dims, strides, box, nullptr);
     if (rc != DT_OK) return rc;
   }
-#define DT_RES(BNV, CWV, MTV) \
-  if (bn == BNV && cw == CWV && mt == MTV) return launch_res<BNV, CWV, MTV>(tm_a, tm_b, p, s);
-#define DT_RES_MT(BNV, CWV) DT_RES(BNV, CWV, 1) DT_RES(BNV, CWV, 2) DT_RES(BNV, CWV, 4)
-  DT_RES(64, 64, 1) DT_RES(64, 64, 2)
+#define DT_RES(BNV, CWV, MTV, PARV) \
+  if (bn == BNV && cw == CWV && mt == MTV && parity == (PARV ? 1 : 0)) \
+    return launch_res<BNV, CWV, MTV, PARV>(tm_a, tm_b, p, s);
+#define DT_RES_MT(BNV, CWV) DT_RES(BNV, CWV, 1, false) DT_RES(BNV, CWV, 2, false) DT_RES(BNV, CWV, 4, false)
+  DT_RES(64, 64, 1, false) DT_RES(64, 64, 2, false)
   DT_RES_MT(32, 64) DT_RES_MT(32, 32) DT_RES_MT(16, 32) DT_RES_MT(16, 16) DT_RES_MT(32, 16) DT_RES_MT(16, 64)
+  DT_RES(16, 32, 4, true) DT_RES(32, 32, 4, true) DT_RES(16, 16, 4, true) DT_RES(16, 64, 4, true) DT_RES(32, 64, 4, true)
 #undef DT_RES_MT
 #undef DT_RES
   return DT_ERR_UNSUPPORTED;

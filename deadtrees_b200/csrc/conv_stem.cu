@@ -1,0 +1,249 @@
+// ResNet stem: 7x7 / stride-2 / pad-3 convolution C_in(<=4, stored as 4) -> 64 with folded BN + ReLU,
+// as a tcgen05 implicit GEMM whose im2col operand is produced by TMA alone.
+//
+// The input lives in a zero-bordered NHWC4 bf16 buffer (N, H+6, W+8, 4): 3 border rows / columns on the top / left
+// (the conv padding - no out-of-bounds handling needed) and a row pitch of (W+8)*8 bytes.  A 5-D tensor map with
+// OVERLAPPING strides views it as the im2col matrix
+//     (32 elements, Wo, Ho, 7 filter rows, N)   strides: 2 B | 16 B | 2*pitch | pitch | image
+// i.e. element (e, wo, ho, r, n) = x_pad[n][2*ho + r][2*wo + e/4][e%4]: the 8 pixels x 4 channels under filter row r
+// of output pixel (ho, wo) are one contiguous 64-byte row (the 8th pixel meets a zero weight).  One TMA box per filter
+// row delivers a 128-pixel x 64-byte K-major SWIZZLE_64B operand tile (measured to work with overlapping strides:
+// scripts/exp/tma_overlap_exp.cu).  The 28 KB of weights [64][7*32] stay resident in shared memory.
+//
+//   warp 0: TMA producer   warp 1: TMEM alloc + MMA issuer (14 MMAs of K=16 per tile)   warps 2..5: epilogue
+#include <cstring>
+#include <mutex>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 128, BN = 64;
+constexpr int ROWS = 7;                         // filter rows = K chunks of 32 elements
+constexpr int A_SUB = BM * 64;                  // one filter row of one tile: 128 x 64 B
+constexpr int A_STAGE = ROWS * A_SUB;           // 56 KB
+constexpr int W_SUB = BN * 64;                  // 64 x 64 B
+constexpr int W_BYTES = ROWS * W_SUB;           // 28 KB
+constexpr int STAGES = 3;
+constexpr int kThreads = 192;
+
+struct StemParams {
+  int Ho, Wo, M_total, total_tiles, relu;
+  __nv_bfloat16* y;
+  const float* scale;
+  const float* shift;
+};
+
+__device__ __forceinline__ void tma_load_5d(void* dst, const void* tmap, uint64_t* bar, int c0, int c1, int c2, int c3,
+                                            int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      :: "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3),
+         "r"(c4)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_stem_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const StemParams p) {
+  constexpr int TMEM_COLS = 2 * BN;
+  constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_w = smem;
+  uint8_t* smem_a = smem + W_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + STAGES * A_STAGE);
+  uint64_t* w_full = bars;
+  uint64_t* full = w_full + 1;          // [STAGES]
+  uint64_t* empty = full + STAGES;      // [STAGES]
+  uint64_t* tmem_full = empty + STAGES; // [2]
+  uint64_t* tmem_empty = tmem_full + 2; // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_b);
+    mbar_init(w_full, 1u);
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1u); mbar_init(&empty[i], 1u); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1u); mbar_init(&tmem_empty[i], 128u); }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(w_full, W_BYTES);
+      for (int r = 0; r < ROWS; ++r) tma_load_2d(smem_w + r * W_SUB, &tm_b, w_full, r * 32, 0);
+      int st = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int m0 = tile * BM;
+        const int w0 = m0 % p.Wo, h0 = (m0 / p.Wo) % p.Ho, n0 = m0 / (p.Wo * p.Ho);
+        mbar_wait(&empty[st], ph ^ 1u);
+        mbar_arrive_expect_tx(&full[st], A_STAGE);
+        for (int r = 0; r < ROWS; ++r)
+          tma_load_5d(smem_a + st * A_STAGE + r * A_SUB, &tm_a, &full[st], 0, w0, h0, r, n0);
+        if (++st == STAGES) { st = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint64_t a_hi = umma_desc(0u, 512u, 4u);   // 64 B rows, SWIZZLE_64B
+      const uint64_t b_d0 = umma_desc(smem_u32(smem_w), 512u, 4u);
+      mbar_wait(w_full, 0);
+      int st = 0, buf = 0;
+      uint32_t ph = 0, pbuf = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[buf], pbuf ^ 1u);
+        mbar_wait(&full[st], ph);
+        tc_fence_after();
+        const uint64_t a_d = a_hi + (smem_u32(smem_a + st * A_STAGE) >> 4);
+        const uint32_t d_tmem = tmem_base + buf * BN;
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) {
+#pragma unroll
+          for (int k = 0; k < 2; ++k)
+            umma_bf16_ss(d_tmem, a_d + ((r * A_SUB + k * 32) >> 4), b_d0 + ((r * W_SUB + k * 32) >> 4), idesc,
+                         (r | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty[st]);
+        umma_commit(&tmem_full[buf]);
+        if (++st == STAGES) { st = 0; ph ^= 1u; }
+        if ((buf ^= 1) == 0) pbuf ^= 1u;
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    int buf = 0;
+    uint32_t pbuf = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int m = tile * BM + row;
+      const bool valid = m < p.M_total;
+      mbar_wait(&tmem_full[buf], pbuf);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + buf * BN + (static_cast<uint32_t>(quarter * 32) << 16);
+#pragma unroll
+      for (int c0 = 0; c0 < BN; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld_x16(t_row + c0, v);
+        tmem_ld_wait();
+        float f[16];
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + c0 + j));
+          const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + c0 + j));
+          f[j] = fmaf(__uint_as_float(v[j]), sc.x, sh.x);
+          f[j + 1] = fmaf(__uint_as_float(v[j + 1]), sc.y, sh.y);
+          f[j + 2] = fmaf(__uint_as_float(v[j + 2]), sc.z, sh.z);
+          f[j + 3] = fmaf(__uint_as_float(v[j + 3]), sc.w, sh.w);
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+        }
+        if (valid) {
+          uint4* op = reinterpret_cast<uint4*>(p.y + static_cast<int64_t>(m) * BN + c0);
+          op[0] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                             pack_bf16x2(f[6], f[7]));
+          op[1] = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]),
+                             pack_bf16x2(f[14], f[15]));
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[buf]);
+      if ((buf ^= 1) == 0) pbuf ^= 1u;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+}  // namespace
+
+// x: zero-bordered (N, H+6, W+8, 4) bf16; w: bf16 [64][256] with k = r*32 + s*4 + c; y: (N, H/2, W/2, 64) bf16.
+// Returns DT_ERR_UNSUPPORTED when the output grid cannot be tiled into 128-pixel boxes.
+int dt_conv_stem(const dt_conv_desc* d, const void* x, const void* w, const float* scale, const float* shift, void* y,
+                 cudaStream_t s) {
+  if (d->C_out != BN || d->H % 2 || d->W % 2) return DT_ERR_UNSUPPORTED;
+  const int Ho = d->H / 2, Wo = d->W / 2;
+  int bw, bh, bn;
+  if (Wo >= BM) {
+    if (Wo % BM) return DT_ERR_UNSUPPORTED;
+    bw = BM; bh = 1; bn = 1;
+  } else {
+    if (BM % Wo) return DT_ERR_UNSUPPORTED;
+    const int rows = BM / Wo;
+    bw = Wo;
+    if (Ho >= rows) { if (Ho % rows) return DT_ERR_UNSUPPORTED; bh = rows; bn = 1; }
+    else { if (rows % Ho) return DT_ERR_UNSUPPORTED; bh = Ho; bn = rows / Ho; }
+  }
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once_fn;
+  std::call_once(once_fn, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  });
+  DT_REQUIRE(fn != nullptr, DT_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  const uint64_t Hp = d->H + 6, Wp = d->W + 8;
+  CUtensorMap tm_a, tm_b;
+  {
+    const cuuint64_t dims[5] = {32, static_cast<cuuint64_t>(Wo), static_cast<cuuint64_t>(Ho), ROWS,
+                                static_cast<cuuint64_t>(d->N)};
+    const cuuint64_t str[4] = {16, 2 * Wp * 8, Wp * 8, Hp * Wp * 8};
+    const cuuint32_t box[5] = {32, static_cast<cuuint32_t>(bw), static_cast<cuuint32_t>(bh), 1,
+                               static_cast<cuuint32_t>(bn)};
+    const cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = fn(&tm_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), dims, str, box, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    DT_REQUIRE(r == CUDA_SUCCESS, DT_ERR_CUDA, "stem im2col tensor map: CUresult %d", static_cast<int>(r));
+  }
+  {
+    const cuuint64_t dims[2] = {256, BN};
+    const cuuint64_t str[1] = {512};
+    const cuuint32_t box[2] = {32, BN};
+    const cuuint32_t es[2] = {1, 1};
+    CUresult r = fn(&tm_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, str, box, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    DT_REQUIRE(r == CUDA_SUCCESS, DT_ERR_CUDA, "stem weight tensor map: CUresult %d", static_cast<int>(r));
+  }
+  StemParams p;
+  p.Ho = Ho; p.Wo = Wo;
+  p.M_total = d->N * Ho * Wo;
+  p.total_tiles = (p.M_total + BM - 1) / BM;
+  p.relu = d->relu;
+  p.y = static_cast<__nv_bfloat16*>(y);
+  p.scale = scale; p.shift = shift;
+  constexpr int smem = W_BYTES + STAGES * A_STAGE + 1024 + 256;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(conv_stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  });
+  DT_CUDA(attr_err);
+  const int grid = p.total_tiles < dt_num_sms() ? p.total_tiles : dt_num_sms();
+  conv_stem_kernel<<<grid, kThreads, smem, s>>>(tm_a, tm_b, p);
+  DT_LAUNCH_CHECK();
+  return DT_OK;
+}

@@ -476,6 +476,8 @@ int dt_encode_bf16_map(CUtensorMap* tm, const void* base, int rank, const uint64
 int dt_conv_halo(const dt_conv_desc* d, int BN, const void* x, const void* skip, const void* w, int Kpad,
                  const float* scale, const float* shift, const void* residual, void* y, cudaStream_t s);
 
+int dt_conv_stem(const dt_conv_desc* d, const void* x, const void* w, const float* scale, const float* shift, void* y,
+                 cudaStream_t s);
 int dt_conv_res(const dt_conv_desc* d, const void* x, const void* w, int Kpad, const float* scale, const float* shift,
                 const void* residual, void* y, cudaStream_t s);
 
@@ -501,6 +503,13 @@ extern "C" int dt_conv2d_fwd(const dt_conv_desc* d, const void* x, const void* s
   const int Ktot = stem ? 7 * 32 : d->R * d->S * d->C_in;
   const int Kpad = stem ? 256 : (Ktot + BK - 1) / BK * BK;
 
+  if (d->flags & DT_CONV_X_PAD3) {
+    DT_REQUIRE(stem && d->dtype == DT_BF16 && d->stride == 2 && d->pad == 3, DT_ERR_BAD_SHAPE,
+               "dt_conv2d_fwd: DT_CONV_X_PAD3 is the bf16 7x7/s2 stem layout");
+    const int rc = dt_conv_stem(d, x, w, scale, shift, y, s);
+    DT_REQUIRE(rc != DT_ERR_UNSUPPORTED, DT_ERR_BAD_SHAPE, "dt_conv2d_fwd: stem output %dx%d cannot be tiled", Ho, Wo);
+    return rc;
+  }
   if (d->dtype == DT_F32 || (d->flags & DT_CONV_FORCE_DIRECT))
     return dt_conv2d_direct(d, Ho, Wo, Kpad, stem, x, skip, w, scale, shift, residual, y, s);
 

@@ -74,7 +74,8 @@ struct NormParams {
 template <bool OUT_BF16>
 __global__ void gather_normalize_kernel(const uint8_t* __restrict__ mosaic, int H, int W, int C, int64_t row_stride,
                                         int64_t pix_stride, int64_t chan_stride, int T, int step, int gx, int tile0,
-                                        int ntiles, NormParams np, void* __restrict__ out) {
+                                        int ntiles, NormParams np, int pad, int out_hp, int out_wp,
+                                        void* __restrict__ out) {
   const int q = T >> 2;
   const int64_t total = static_cast<int64_t>(ntiles) * T * q;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
@@ -128,14 +129,22 @@ __global__ void gather_normalize_kernel(const uint8_t* __restrict__ mosaic, int 
         v[j][c] = (c < C) ? __fmul_rn(__fsub_rn(u, np.offset[c]), np.scale[c]) : 0.0f;
       }
     }
+    // output pixel index: dense (t, y, x) or inside a zero-bordered (t, out_hp, out_wp) frame at offset `pad`
+    const int64_t opix = pad ? (static_cast<int64_t>(t) * out_hp + y + pad) * out_wp + x4 * 4 + pad : i * 4;
     if (OUT_BF16) {
+      if (pad) {  // 8-byte aligned only
+        uint2* o = reinterpret_cast<uint2*>(out) + opix;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = make_uint2(pack_bf16x2(v[j][0], v[j][1]), pack_bf16x2(v[j][2], v[j][3]));
+        continue;
+      }
       uint4* o = reinterpret_cast<uint4*>(out) + i * 2;
       o[0] = make_uint4(pack_bf16x2(v[0][0], v[0][1]), pack_bf16x2(v[0][2], v[0][3]),
                         pack_bf16x2(v[1][0], v[1][1]), pack_bf16x2(v[1][2], v[1][3]));
       o[1] = make_uint4(pack_bf16x2(v[2][0], v[2][1]), pack_bf16x2(v[2][2], v[2][3]),
                         pack_bf16x2(v[3][0], v[3][1]), pack_bf16x2(v[3][2], v[3][3]));
     } else {
-      float4* o = reinterpret_cast<float4*>(out) + i * 4;
+      float4* o = reinterpret_cast<float4*>(out) + opix;
 #pragma unroll
       for (int j = 0; j < 4; ++j) o[j] = make_float4(v[j][0], v[j][1], v[j][2], v[j][3]);
     }
@@ -311,9 +320,11 @@ int dt_unmake_blocks(const void* src, int d, int m, int n, int elem_size, void* 
 
 int dt_tile_gather_normalize(const uint8_t* mosaic, int H, int W, int C, int64_t row_stride, int64_t pix_stride,
                              int64_t chan_stride, int tile, int step, int gx, int tile0, int ntiles,
-                             const float* offset, const float* scale, int c_out, int out_dtype, void* out,
+                             const float* offset, const float* scale, int c_out, int out_dtype, int out_pad, void* out,
                              dt_stream_t stream) {
   DT_ARCH_GUARD();
+  DT_REQUIRE(out_pad == 0 || out_pad == 3, DT_ERR_BAD_SHAPE, "dt_tile_gather_normalize: out_pad must be 0 or 3");
+  const int out_hp = tile + 6, out_wp = tile + 8;
   DT_REQUIRE(C >= 1 && C <= 4 && c_out == 4, DT_ERR_BAD_SHAPE, "dt_tile_gather_normalize: C=%d c_out=%d (need C<=4, c_out==4)", C, c_out);
   DT_REQUIRE(tile > 0 && tile % 4 == 0 && step > 0 && step <= tile && gx > 0 && ntiles >= 0 && tile0 >= 0,
              DT_ERR_BAD_SHAPE, "dt_tile_gather_normalize: tile=%d step=%d gx=%d", tile, step, gx);
@@ -329,10 +340,12 @@ int dt_tile_gather_normalize(const uint8_t* mosaic, int H, int W, int C, int64_t
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (out_dtype == DT_BF16)
     gather_normalize_kernel<true><<<grid_for(total), kThreads, 0, s>>>(mosaic, H, W, C, row_stride, pix_stride,
-                                                                      chan_stride, tile, step, gx, tile0, ntiles, np, out);
+                                                                      chan_stride, tile, step, gx, tile0, ntiles, np,
+                                                                      out_pad, out_hp, out_wp, out);
   else
     gather_normalize_kernel<false><<<grid_for(total), kThreads, 0, s>>>(mosaic, H, W, C, row_stride, pix_stride,
-                                                                       chan_stride, tile, step, gx, tile0, ntiles, np, out);
+                                                                       chan_stride, tile, step, gx, tile0, ntiles, np,
+                                                                       out_pad, out_hp, out_wp, out);
   DT_LAUNCH_CHECK();
   return DT_OK;
 }

@@ -155,7 +155,10 @@ class MosaicInference:
         mask = out if out is not None else self._buf("mask", (H, W), torch.uint8)
         ntiles = (r1 - r0) * gx
         bt = min(self.batch_tiles, max(ntiles, 1))
-        x = self._buf("x", (bt, T, T, 4), eng.act_dtype)
+        pad = 3 if eng.stem_padded(T) else 0
+        x = self._bufs.get(("x", bt, T))
+        if x is None:
+            x = self._bufs[("x", bt, T)] = eng.alloc_input(bt, T)   # padded frame: borders stay zero
         if ov == 0:
             tmask = self._buf("tmask", (bt, T, T), torch.uint8)
         else:
@@ -165,7 +168,7 @@ class MosaicInference:
             n = min(bt, r1 * gx - t0)
             xb = x[:n]
             ops.tile_gather_normalize(mosaic, layout, eng.in_channels, T, ov, (gy, gx), t0, n, self.offset,
-                                      self.scale, out=xb)
+                                      self.scale, out=xb, pad=pad)
             if ov == 0:
                 eng.forward(xb, mask_out=tmask[:n])
                 ops.stitch_mask(tmask[:n], gx, t0, mask)

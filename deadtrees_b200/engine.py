@@ -13,7 +13,7 @@ from typing import Dict, List, Optional
 import torch
 
 from . import ops
-from ._lib import require_device
+from ._lib import CONV_X_PAD3, require_device
 
 BN_EPS = 1e-5
 RESNET34_LAYERS = (3, 4, 6, 3)
@@ -133,11 +133,11 @@ class UnetEngine:
         self.head_b = sd["segmentation_head.0.bias"].float().contiguous().to(self.device)
 
     # ------------------------------------------------------------------------------------------
-    def _run(self, name, x, N, H, W, skip=None, residual=None, out=None):
+    def _run(self, name, x, N, H, W, skip=None, residual=None, out=None, flags=0):
         L = self.layers[name]
         return ops.conv2d(x, L.w, L.scale, L.shift, N=N, H=H, W=W, C_in=L.C_in, C_x=L.C_x, C_out=L.C_out, R=L.R,
                           S=L.S, stride=L.stride, pad=L.pad, relu=L.relu, skip=skip, upsample=L.upsample,
-                          residual=residual, out=out, flags=self.conv_flags,
+                          residual=residual, out=out, flags=self.conv_flags | flags,
                           algo_cin=self.in_channels if name == "stem" else None, tag=name)
 
     def _buf(self, ws, key, shape):
@@ -147,15 +147,30 @@ class UnetEngine:
             ws[key] = t
         return t
 
+    def stem_padded(self, T: int) -> bool:
+        """True when the stem can take its input as a zero-bordered (N, T+6, T+8, 4) frame and build the im2col
+        operand with TMA (conv_stem.cu): bf16 path and an output grid that tiles into 128-pixel boxes."""
+        wo = T // 2
+        return self.precision == "bf16" and not self.conv_flags and (wo % 128 == 0 or wo in (16, 32, 64))
+
+    def alloc_input(self, N: int, T: int) -> torch.Tensor:
+        """input buffer for `forward(...)`: padded frame (borders zeroed once) or dense (N, T, T, 4)."""
+        if self.stem_padded(T):
+            return torch.zeros((N, T + 6, T + 8, 4), dtype=self.act_dtype, device=self.device)
+        return torch.empty((N, T, T, 4), dtype=self.act_dtype, device=self.device)
+
     def forward_features(self, x: torch.Tensor, keep: Optional[Dict[str, torch.Tensor]] = None) -> torch.Tensor:
-        """x: (N, T, T, 4) NHWC in the engine's activation dtype -> decoder output (N, T, T, 16)."""
-        N, T, T2, C4 = x.shape
-        if C4 != 4 or T != T2 or T % 32:
-            raise ValueError(f"input must be (N, T, T, 4) with T % 32 == 0, got {tuple(x.shape)}")
+        """x: (N, T, T, 4) NHWC in the engine's activation dtype, or the padded frame (N, T+6, T+8, 4) from
+        `alloc_input` -> decoder output (N, T, T, 16)."""
+        N, H_in, W_in, C4 = x.shape
+        padded = W_in == H_in + 2
+        T = H_in - 6 if padded else H_in
+        if C4 != 4 or (not padded and H_in != W_in) or T % 32 or (padded and not self.stem_padded(T)):
+            raise ValueError(f"input must be (N, T, T, 4) or (N, T+6, T+8, 4) with T % 32 == 0, got {tuple(x.shape)}")
         ws = self._ws.setdefault((N, T), {})
         buf = lambda key, h, c: self._buf(ws, key, (N, h, h, c))
         f = {}
-        f[1] = self._run("stem", x, N, T, T, out=buf("f1", T // 2, 64))
+        f[1] = self._run("stem", x, N, T, T, out=buf("f1", T // 2, 64), flags=CONV_X_PAD3 if padded else 0)
         cur = ops.maxpool3x3s2(f[1], out=buf("pool", T // 4, 64))
         H = T // 4
         for li, (planes, nblk) in enumerate(zip(RESNET34_PLANES, RESNET34_LAYERS), start=1):
@@ -190,7 +205,7 @@ class UnetEngine:
                 want_mask: bool = False, mask_out: Optional[torch.Tensor] = None,
                 logits_nhwc_out: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
         d = self.forward_features(x)
-        N, T = x.shape[0], x.shape[1]
+        N, T = d.shape[0], d.shape[1]
         out: Dict[str, torch.Tensor] = {}
         if want_logits_nchw:
             out["logits_nchw"] = torch.empty((N, self.classes, T, T), dtype=torch.float32, device=self.device)

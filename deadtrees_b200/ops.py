@@ -86,8 +86,9 @@ def unmake_blocks(x: torch.Tensor, d: int, m: int, n: int) -> torch.Tensor:
 def tile_gather_normalize(mosaic: torch.Tensor, layout: str, channels: int, tile: int, overlap: int,
                           grid: Tuple[int, int], tile0: int, ntiles: int, offset: Sequence[float],
                           scale: Sequence[float], dtype: torch.dtype = torch.bfloat16,
-                          out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """uint8 mosaic ("hwc": (H, W, C) or "chw": (C, H, W)) -> normalised NHWC tiles (ntiles, T, T, 4)."""
+                          out: Optional[torch.Tensor] = None, pad: int = 0) -> torch.Tensor:
+    """uint8 mosaic ("hwc": (H, W, C) or "chw": (C, H, W)) -> normalised NHWC tiles (ntiles, T, T, 4);
+    with pad=3 into a caller-zeroed (ntiles, T+6, T+8, 4) frame at offset (3, 3)."""
     if mosaic.dtype != torch.uint8 or not mosaic.is_cuda:
         raise TypeError("mosaic must be a CUDA uint8 tensor")
     if layout == "hwc":
@@ -101,14 +102,15 @@ def tile_gather_normalize(mosaic: torch.Tensor, layout: str, channels: int, tile
     if channels > Csrc:
         raise ValueError(f"model wants {channels} channels, mosaic has {Csrc}")
     if out is None:
-        out = torch.empty((ntiles, tile, tile, 4), dtype=dtype, device=mosaic.device)
+        out = (torch.zeros((ntiles, tile + 6, tile + 8, 4), dtype=dtype, device=mosaic.device) if pad else
+               torch.empty((ntiles, tile, tile, 4), dtype=dtype, device=mosaic.device))
     off = (C.c_float * 4)(*[float(v) for v in list(offset)[:channels]] + [0.0] * (4 - channels))
     sc = (C.c_float * 4)(*[float(v) for v in list(scale)[:channels]] + [0.0] * (4 - channels))
     # algorithmic bytes: N*T^2*C*(1 B in + elem out)
     with _Timed("gather", float(ntiles) * tile * tile * channels * (1 + out.element_size())):
         check(load().dt_tile_gather_normalize(mosaic.data_ptr(), H, W, channels, rs, ps, cs, tile, tile - overlap,
-                                              grid[1], tile0, ntiles, off, sc, 4, _dt(out), out.data_ptr(),
-                                              stream_ptr()))
+                                              grid[1], tile0, ntiles, off, sc, 4, _dt(out), pad,
+                                              out.data_ptr(), stream_ptr()))
     return out
 
 

@@ -63,10 +63,11 @@ int dt_unmake_blocks(const void* src, int d, int m, int n, int elem_size, void* 
  * as raw 0 (the reference zero-pads the uint8 array, tiler.py:106-111).
  * out[t, y, x, c] = (u8 - offset[c]) * scale[c] for c < C, 0 for C <= c < c_out; fp32 arithmetic
  * (subtract, then multiply), rounded to bf16 when out_dtype == DT_BF16.  offset/scale are HOST
- * pointers to 4 floats. */
+ * pointers to 4 floats.  out_pad == 3 writes each tile into a (tile+6) x (tile+8) pixel frame at offset (3, 3)
+ * whose border the caller has zeroed: the input layout of the TMA-im2col stem (DT_CONV_X_PAD3). */
 int dt_tile_gather_normalize(const uint8_t* mosaic, int H, int W, int C, int64_t row_stride, int64_t pix_stride,
                              int64_t chan_stride, int tile, int step, int gx, int tile0, int ntiles,
-                             const float* offset, const float* scale, int c_out, int out_dtype, void* out,
+                             const float* offset, const float* scale, int c_out, int out_dtype, int out_pad, void* out,
                              dt_stream_t stream);
 
 /* NCHW fp32 batch (what callers hand to `PyTorchInference.run` / `self.model(img)`) -> NHWC with 4
@@ -115,6 +116,8 @@ typedef struct {
 enum {
   DT_CONV_FORCE_GATHER = 1, /* A operand through the generic gather producer even if TMA-eligible */
   DT_CONV_FORCE_DIRECT = 2, /* CUDA-core direct kernel for bf16 tensors (debug/validation) */
+  DT_CONV_X_PAD3 = 8,       /* 7x7 stem: x is a zero-bordered (N, H+6, W+8, 4) frame (see dt_tile_gather_normalize);
+                               im2col through a TMA tensor map with overlapping strides (conv_stem.cu) */
   DT_CONV_NO_HALO = 4       /* 3x3/s1 layers: per-tap TMA boxes (conv_tc.cu) instead of the smem-resident halo
                                patches (conv_halo.cu, the default where the shape fits) */
 };

@@ -4,7 +4,7 @@ import torch
 import torch.nn.functional as F
 
 from deadtrees_b200 import ops
-from deadtrees_b200._lib import CONV_FORCE_DIRECT, CONV_FORCE_GATHER, CONV_NO_HALO
+from deadtrees_b200._lib import CONV_FORCE_DIRECT, CONV_FORCE_GATHER, CONV_NO_HALO, CONV_X_PAD3
 from deadtrees_b200.engine import pack_weight
 from gpu_util import report, to_nchw
 
@@ -124,6 +124,27 @@ def test_stem_tcgen05_and_fp32():
         torch.cuda.synchronize()
         err, rel = report(f"stem {dtype}", to_nchw(y), ref)
         assert rel < tol_rel
+
+
+@pytest.mark.parametrize("N,T", [(3, 64), (2, 256), (5, 32)])
+def test_stem_tma_im2col_padded_input(N, T):
+    """7x7/s2 stem with the im2col operand built by TMA from a zero-bordered frame == the gather path, bit for bit."""
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(N, 3, T, T, generator=g)
+    w = torch.randn(64, 3, 7, 7, generator=g) * (2.0 / 147) ** 0.5
+    scale, shift = 1.0 + 0.1 * torch.randn(64, generator=g), 0.1 * torch.randn(64, generator=g)
+    x4 = torch.zeros(N, T, T, 4); x4[..., :3] = x.permute(0, 2, 3, 1)
+    xpad = torch.zeros(N, T + 6, T + 8, 4); xpad[:, 3:3 + T, 3:3 + T] = x4
+    wp = pack_weight(w, "bf16", True, "cuda")
+    kw = dict(N=N, H=T, W=T, C_in=4, C_x=4, C_out=64, R=7, S=7, stride=2, pad=3, relu=True)
+    y_g = ops.conv2d(x4.to(torch.bfloat16).cuda(), wp, scale.cuda(), shift.cuda(), **kw)
+    y_t = ops.conv2d(xpad.to(torch.bfloat16).cuda(), wp, scale.cuda(), shift.cuda(), flags=CONV_X_PAD3, **kw)
+    torch.cuda.synchronize()
+    rnd = lambda t: t.to(torch.bfloat16).float()
+    ref = F.relu(F.conv2d(rnd(x), rnd(w), None, 2, 3) * scale[None, :, None, None] + shift[None, :, None, None])
+    err, rel = report(f"stem TMA-im2col N={N} T={T}", to_nchw(y_t), ref)
+    assert rel < 1e-2
+    assert torch.equal(y_t, y_g)
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])

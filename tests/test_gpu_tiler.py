@@ -87,6 +87,22 @@ def test_gather_normalize_bit_exact(layout, C, Cm, H, W, T, ov):
         np.testing.assert_array_equal(part.cpu().numpy(), ref[1:-1])
 
 
+def test_gather_normalize_padded_frame():
+    """pad=3: tiles land at offset (3, 3) of a zero-bordered (T+6, T+8) frame (input layout of the TMA stem)."""
+    rng = np.random.default_rng(12)
+    H, W, T, ov = 150, 130, 64, 16
+    m = rng.integers(0, 256, size=(H, W, 3), dtype=np.uint8)
+    gy, gx = overlap_grid(H, W, T, ov)
+    off, sc = normalize_constants(3)
+    src = torch.from_numpy(m).cuda()
+    dense = ops.tile_gather_normalize(src, "hwc", 3, T, ov, (gy, gx), 0, gy * gx, off, sc, dtype=torch.bfloat16)
+    frame = ops.tile_gather_normalize(src, "hwc", 3, T, ov, (gy, gx), 0, gy * gx, off, sc, dtype=torch.bfloat16, pad=3)
+    assert frame.shape == (gy * gx, T + 6, T + 8, 4)
+    assert torch.equal(frame[:, 3:3 + T, 3:3 + T], dense)
+    border = frame.clone(); border[:, 3:3 + T, 3:3 + T] = 0
+    assert float(border.float().abs().max()) == 0.0
+
+
 def test_val_transform_matches_oracle():
     rng = np.random.default_rng(5)
     img = rng.integers(0, 256, size=(256, 256, 4), dtype=np.uint8)
