@@ -44,6 +44,7 @@ _SIGNATURES = {
     "dt_conv2d_fwd": ([C.POINTER(ConvDesc), _p, _p, _p, _p, _p, _p, _p, _p], C.c_int),
     "dt_maxpool3x3s2": ([_p, _i, _i, _i, _i, _i, _p, _p], C.c_int),
     "dt_head_fwd": ([_p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p], C.c_int),
+    "dt_head_fwd_tc": ([_p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p], C.c_int),
     "dt_argmax_nchw": ([_p, _i, _i, _i, _i, _p, _p], C.c_int),
     "dt_seg_loss_partials": ([_p, _p, _i, _i, _i, _i, _p, _p, _p, _p], C.c_int),
     "dt_seg_loss_finalize": ([_p, _p, _i, _i, _i, _i, _p, _p, _p, _p], C.c_int),

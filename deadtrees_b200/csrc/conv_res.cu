@@ -36,6 +36,11 @@ struct ResParams {
   __nv_bfloat16* y;
   const float* scale;
   const float* shift;
+  // head epilogue (EPI == 1): the first K of the 16 output channels are the class logits
+  int K;
+  float* logits_nchw;
+  __nv_bfloat16* logits_nhwc;
+  uint8_t* mask;
 };
 
 struct Geo {
@@ -62,7 +67,7 @@ __device__ __forceinline__ constexpr int tap_pixel_offset(int mt, int tap) {
   return (mt * TH + fr) * PITCH + fs;
 }
 
-template <int BN, int CW, int MT, bool PAR>
+template <int BN, int CW, int MT, bool PAR, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_res_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                 const ResParams p) {
@@ -179,6 +184,29 @@ conv_res_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       for (int mt = 0; mt < MT; ++mt) {
         const int64_t out_off = pixel_off(mt);
         const uint32_t t_row = tmem_base + (buf * MT + mt) * BN + (static_cast<uint32_t>(quarter * 32) << 16);
+        if (EPI == 1) {
+          // segmentation head: logits = acc + bias; first-max argmax on the fp32 values; three optional outputs
+          uint32_t v[16];
+          tmem_ld_x16(t_row, v);
+          tmem_ld_wait();
+          const int64_t pix = out_off / p.C_out;                 // (n*H + y)*W + x
+          int best = 0;
+          float bv = 0.f;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (k >= p.K) break;
+            const float z = __uint_as_float(v[k]) + __ldg(p.shift + k);
+            if (p.logits_nhwc) p.logits_nhwc[pix * p.K + k] = __float2bfloat16_rn(z);
+            if (p.logits_nchw) {
+              const int64_t hw = static_cast<int64_t>(p.H) * p.W;
+              const int64_t n = pix / hw;
+              p.logits_nchw[(n * p.K + k) * hw + (pix - n * hw)] = z;
+            }
+            if (k == 0 || z > bv) { bv = z; best = k; }
+          }
+          if (p.mask) p.mask[pix] = static_cast<uint8_t>(best);
+          continue;
+        }
         if (p.has_residual && mt + 1 < MT) {
           const int64_t o1 = pixel_off(mt + 1);
 #pragma unroll
@@ -238,7 +266,7 @@ conv_res_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   }
 }
 
-template <int BN, int CW, int MT, bool PAR>
+template <int BN, int CW, int MT, bool PAR, int EPI = 0>
 int launch_res(const CUtensorMap& tm_a, const CUtensorMap& tm_b, ResParams& p, cudaStream_t s) {
   constexpr int B_BYTES = BN * BK * 2;
   constexpr int NCH = (9 * CW + BK - 1) / BK;
@@ -259,13 +287,13 @@ int launch_res(const CUtensorMap& tm_a, const CUtensorMap& tm_b, ResParams& p, c
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(conv_res_kernel<BN, CW, MT, PAR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    attr_err = cudaFuncSetAttribute(conv_res_kernel<BN, CW, MT, PAR, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     225 * 1024);
   });
   DT_CUDA(attr_err);
   const int slots = dt_num_sms() * ctas;
   const int grid = p.total_tiles < slots ? p.total_tiles : slots;
-  conv_res_kernel<BN, CW, MT, PAR><<<grid, kThreads, smem, s>>>(tm_a, tm_b, p);
+  conv_res_kernel<BN, CW, MT, PAR, EPI><<<grid, kThreads, smem, s>>>(tm_a, tm_b, p);
   DT_LAUNCH_CHECK();
   return DT_OK;
 }
@@ -327,4 +355,43 @@ int dt_conv_res(const dt_conv_desc* d, const void* x, const void* w, int Kpad, c
 #undef DT_RES_MT
 #undef DT_RES
   return DT_ERR_UNSUPPORTED;
+}
+
+
+// Segmentation head on the tensor cores: 3x3 conv 16 -> K (K <= 4, weights padded to 16 output channels, bf16
+// [16][192]) + bias, with the argmax / layout outputs of dt_head_fwd fused into the epilogue.
+int dt_head_res(const void* x, int N, int H, int W, int K, const void* w_packed, const float* bias16,
+                float* logits_nchw, void* logits_nhwc, uint8_t* mask, cudaStream_t s) {
+  if (W % TW != 0 || H % TH != 0 || K < 1 || K > 4) return DT_ERR_UNSUPPORTED;
+  int mt = 4;
+  while (mt > 1 && H % (TH * mt) != 0) mt >>= 1;
+  ResParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = N; p.H = H; p.W = W; p.C_out = 16;
+  p.Hg = H; p.Wg = W;
+  p.tiles_w = W / TW; p.tiles_h = H / (TH * mt);
+  p.total_tiles = p.tiles_w * p.tiles_h * N;
+  p.shift = bias16;
+  p.K = K;
+  p.logits_nchw = logits_nchw;
+  p.logits_nhwc = static_cast<__nv_bfloat16*>(logits_nhwc);
+  p.mask = mask;
+  CUtensorMap tm_a, tm_b;
+  {
+    const uint64_t dims[2] = {192, 16};
+    const uint64_t strides[1] = {192 * 2};
+    const uint32_t box[2] = {BK, 16};
+    int rc = dt_encode_bf16_map(&tm_b, w_packed, 2, dims, strides, box, nullptr);
+    if (rc != DT_OK) return rc;
+  }
+  {
+    const uint64_t dims[4] = {16, static_cast<uint64_t>(W), static_cast<uint64_t>(H), static_cast<uint64_t>(N)};
+    const uint64_t strides[3] = {32, static_cast<uint64_t>(W) * 32, static_cast<uint64_t>(H) * W * 32};
+    const uint32_t box[4] = {16, PITCH, static_cast<uint32_t>(TH * mt + 2), 1};
+    int rc = dt_encode_bf16_map(&tm_a, x, 4, dims, strides, box, nullptr);
+    if (rc != DT_OK) return rc;
+  }
+  if (mt == 4) return launch_res<16, 16, 4, false, 1>(tm_a, tm_b, p, s);
+  if (mt == 2) return launch_res<16, 16, 2, false, 1>(tm_a, tm_b, p, s);
+  return launch_res<16, 16, 1, false, 1>(tm_a, tm_b, p, s);
 }

@@ -131,6 +131,15 @@ class UnetEngine:
             raise ValueError("segmentation head does not match `classes`")
         self.head_w = hw.permute(2, 3, 1, 0).reshape(9, hw.shape[1], hw.shape[0]).contiguous().to(self.device)
         self.head_b = sd["segmentation_head.0.bias"].float().contiguous().to(self.device)
+        # tensor-core head (bf16 path): weights padded to 16 output channels in the conv packing, bias to 16 floats
+        self.head_w_tc = self.head_b16 = None
+        if self.precision == "bf16" and hw.shape[1] == 16 and not self.conv_flags:
+            hw16 = torch.zeros(16, 16, 3, 3)
+            hw16[: hw.shape[0]] = hw.cpu()
+            self.head_w_tc = pack_weight(hw16, "bf16", False, self.device)
+            b16 = torch.zeros(16)
+            b16[: hw.shape[0]] = sd["segmentation_head.0.bias"].float().cpu()
+            self.head_b16 = b16.to(self.device)
 
     # ------------------------------------------------------------------------------------------
     def _run(self, name, x, N, H, W, skip=None, residual=None, out=None, flags=0):
@@ -215,8 +224,12 @@ class UnetEngine:
         if want_mask or mask_out is not None:
             out["mask"] = mask_out if mask_out is not None else torch.empty((N, T, T), dtype=torch.uint8,
                                                                             device=self.device)
-        ops.head(d, self.head_w, self.head_b, logits_nchw=out.get("logits_nchw"), logits_nhwc=out.get("logits_nhwc"),
-                 mask=out.get("mask"))
+        if self.head_w_tc is not None:
+            ops.head_tc(d, self.head_w_tc, self.head_b16, self.classes, logits_nchw=out.get("logits_nchw"),
+                        logits_nhwc=out.get("logits_nhwc"), mask=out.get("mask"))
+        else:
+            ops.head(d, self.head_w, self.head_b, logits_nchw=out.get("logits_nchw"),
+                     logits_nhwc=out.get("logits_nhwc"), mask=out.get("mask"))
         return out
 
 

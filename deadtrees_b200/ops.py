@@ -184,6 +184,15 @@ def head(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, *, logits_nchw: O
                              ptr(logits_nhwc), ptr(mask), stream_ptr()))
 
 
+def head_tc(x: torch.Tensor, w_packed: torch.Tensor, bias16: torch.Tensor, K: int, *,
+            logits_nchw: Optional[torch.Tensor] = None, logits_nhwc: Optional[torch.Tensor] = None,
+            mask: Optional[torch.Tensor] = None) -> None:
+    """tensor-core head (bf16 activations, 16 input channels)."""
+    N, H, W, Cc = x.shape
+    check(load().dt_head_fwd_tc(x.data_ptr(), N, H, W, K, w_packed.data_ptr(), bias16.data_ptr(), ptr(logits_nchw),
+                                ptr(logits_nhwc), ptr(mask), stream_ptr()))
+
+
 def argmax_nchw(logits: torch.Tensor) -> torch.Tensor:
     logits = _cuda(logits, "logits")
     N, K, H, W = logits.shape

@@ -137,6 +137,11 @@ int dt_maxpool3x3s2(const void* x, int N, int H, int W, int C, int dtype, void* 
 int dt_head_fwd(const void* x, int x_dtype, int N, int H, int W, int C, int K, const float* w, const float* bias,
                 float* logits_nchw, void* logits_nhwc, uint8_t* mask, dt_stream_t stream);
 
+/* The same head on the tensor cores (bf16 path, C == 16, H % 16 == 0, W % 8 == 0): w_packed = bf16 [16][192],
+ * row k < K = class k in the dt_conv2d_fwd packing (k = tap*16 + c), rows >= K zero; bias16 = float[16]. */
+int dt_head_fwd_tc(const void* x, int N, int H, int W, int K, const void* w_packed, const float* bias16,
+                   float* logits_nchw, void* logits_nhwc, uint8_t* mask, dt_stream_t stream);
+
 /* argmax over the class dim of NCHW fp32 logits -> uint8 (first max wins) */
 int dt_argmax_nchw(const float* logits, int N, int K, int H, int W, uint8_t* mask, dt_stream_t stream);
 

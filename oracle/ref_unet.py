@@ -245,4 +245,5 @@ def forward_bf16(model: Unet, x: torch.Tensor) -> torch.Tensor:
                 y = torch.cat([y, skips[i + 1]], dim=1)
             y = _fused(blk.conv1[0], blk.conv1[1], y)
             y = _fused(blk.conv2[0], blk.conv2[1], y)
-        return model.segmentation_head(y)  # head runs in fp32 on the bf16-stored decoder output
+        head = model.segmentation_head[0]   # tensor-core head: bf16 weights, fp32 accumulate, fp32 bias
+        return F.conv2d(y, _rb(head.weight), head.bias, 1, 1)

@@ -177,6 +177,29 @@ def test_head_outputs(dtype, K):
     assert torch.equal(nhwc.cpu(), nchw.cpu().permute(0, 2, 3, 1).to(dtype))
 
 
+@pytest.mark.parametrize("K,N,H", [(3, 2, 64), (2, 1, 32), (3, 1, 16)])
+def test_head_tensor_core(K, N, H):
+    """tcgen05 head (bf16 weights, fp32 accumulate) with the fused argmax / layout epilogue."""
+    g = torch.Generator().manual_seed(8)
+    C = 16
+    x = torch.randn(N, C, H, H, generator=g).to(torch.bfloat16).float()
+    w = torch.randn(K, C, 3, 3, generator=g) * 0.1
+    b = torch.randn(K, generator=g)
+    ref = F.conv2d(x, w.to(torch.bfloat16).float(), b, 1, 1)
+    w16 = torch.zeros(16, C, 3, 3); w16[:K] = w
+    b16 = torch.zeros(16); b16[:K] = b
+    nchw = torch.empty(N, K, H, H, device="cuda")
+    nhwc = torch.empty(N, H, H, K, dtype=torch.bfloat16, device="cuda")
+    mask = torch.empty(N, H, H, dtype=torch.uint8, device="cuda")
+    ops.head_tc(x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).cuda(), pack_weight(w16, "bf16", False, "cuda"),
+                b16.cuda(), K, logits_nchw=nchw, logits_nhwc=nhwc, mask=mask)
+    torch.cuda.synchronize()
+    err, _ = report(f"head tcgen05 K={K}", nchw.cpu(), ref)
+    assert err < 1e-4
+    assert torch.equal(mask.cpu().long(), nchw.cpu().argmax(1))
+    assert torch.equal(nhwc.cpu(), nchw.cpu().permute(0, 2, 3, 1).to(torch.bfloat16))
+
+
 def test_argmax_ties_first_index():
     z = torch.zeros(1, 3, 4, 4, device="cuda")
     z[0, 1, 0, 0] = 1.0; z[0, 2, 0, 0] = 1.0
