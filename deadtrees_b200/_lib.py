@@ -52,6 +52,19 @@ _SIGNATURES = {
     "dt_class2one_hot": ([_p, _i, _i, _i, _i, _p, _p, _p], C.c_int),
     "dt_softmax_nchw": ([_p, _i, _i, _i, _i, _p, _p], C.c_int),
     "dt_prob_loss_partials": ([_p, _p, _i, _i, _i, _i, _i, _f, _p, _p], C.c_int),
+    "dt_reduce_blocks": ([_i64, _i, _i], C.c_int),
+    "dt_bn_train_stats": ([_p, _i64, _i, _i, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _p, _p], C.c_int),
+    "dt_bn_apply": ([_p, _i64, _i, _i, _p, _p, _p, _i, _p, _p], C.c_int),
+    "dt_bn_train_bwd": ([_p, _p, _p, _i64, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p], C.c_int),
+    "dt_add": ([_p, _p, _i64, _i, _p, _p], C.c_int),
+    "dt_maxpool3x3s2_bwd": ([_p, _p, _p, _i, _i, _i, _i, _i, _p, _p], C.c_int),
+    "dt_upsample_concat": ([_p, _p, _i, _i, _i, _i, _i, _i, _p, _p], C.c_int),
+    "dt_upsample_concat_bwd": ([_p, _i, _i, _i, _i, _i, _i, _p, _p, _p], C.c_int),
+    "dt_nchw_to_nhwc": ([_p, _i, _i, _i, _i, _i, _i, _p, _p], C.c_int),
+    "dt_pack_conv_weight": ([_p, _i, _i, _i, _i, _i, _i, _i, _p, _p], C.c_int),
+    "dt_conv2d_dgrad_direct": ([_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p], C.c_int),
+    "dt_conv2d_wgrad_direct": ([_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p], C.c_int),
+    "dt_conv2d_wgrad_tc": ([_p, _p, _i, _i, _i, _i, _i, _p, _p], C.c_int),
     "dt_sumsq": ([_p, _i64, _p, _p], C.c_int),
     "dt_adam_step": ([_p, _p, _p, _p, _i64, _f, _f, _f, _f, _i, _p, _f, _p], C.c_int),
 }

@@ -1,0 +1,251 @@
+// Weight gradient of a 3x3 / stride-1 / pad-1 convolution on the sm_100a tensor cores (tcgen05, TMEM accumulators).
+//
+//   dW[co][ci][r][s] = sum over pixels p of  gy[p][co] * x[p + (r-1, s-1)][ci]
+//
+// GEMM view per filter tap: D_tap[M = co][N = ci] += A[co][K = pixel] * B_tap[ci][K = pixel].  Both operands are read
+// straight from the NHWC bf16 tensors as **MN-major** UMMA operands: a TMA box (64 channels x pixels, SWIZZLE_128B)
+// lands in shared memory as rows of 128 B (one pixel each) - exactly the MN-major canonical atom (64 MN elements x 8 K
+// rows), with the pixel index as K.  No transposed copies of activations or gradients are ever made.
+//   A  = gy tile: 8 (w) x 16 (h) pixels (= K 128) x 64-channel slabs, two slabs (leading-byte-offset apart) give M = 128
+//   B  = x halo patch: (16+2) x (8+2) pixels x one 64-channel slab, loaded ONCE per tile; the nine taps read it in place
+//        through descriptors whose start is shifted by (r*10 + s) pixel rows and whose stride-byte-offset (distance
+//        between the 8-pixel K groups = image rows) is 10 pixel rows - the same absolute-address-swizzle property the
+//        forward halo kernel relies on (profiles/r01_halo_descriptor_experiment.txt).
+// Channel counts below 64 are handled by TMA out-of-bounds zero fill (box wider than the tensor), so one kernel
+// configuration (M 128, N 64) serves every layer; rows / columns beyond C_out / C_in are never written back.
+// Images smaller than 16 rows (8x8 at the bottom of the encoder) put two images in one tile.
+//
+// Work decomposition: job = (128-wide co block, 64-wide ci slab, tap group {0..4} | {5..8}); the pixel tiles are split
+// over `splits` CTAs per job; every CTA keeps its 5 (4) tap accumulators of 128 x 64 fp32 in TMEM across all its
+// tiles and adds them to dW (fp32 atomics) once at the end.
+//   warp 0: TMA producer   warp 1: TMEM alloc + MMA issuer   warps 2..5: epilogue
+//
+// Replaces the cuDNN wgrad kernels autograd reaches from SemSegment.training_step
+// (deadtrees/network/segmodel.py:210-229).
+#include <cstring>
+#include <mutex>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int TW = 8, TH = 16, PITCH = TW + 2;
+constexpr int kThreads = 192;
+constexpr int A_SLAB = 128 * 128;            // one 64-channel slab of a 128-pixel gy tile
+constexpr int A_STAGE = 2 * A_SLAB;          // 32 KB
+constexpr int B_STAGE = 26 * 1024;           // >= 2 images x 10 x 10 pixels x 128 B
+constexpr int STAGES = 3;
+constexpr int TMEM_COLS = 512;
+constexpr int NCOL = 64;                     // UMMA N (one ci slab)
+
+struct WgParams {
+  int N, H, W, C_in, C_out;
+  int th_img, imgs;                 // image rows per tile (8 or 16), images per tile (2 or 1)
+  int tiles_w, tiles_h, total_tiles;
+  int ci_slabs, jobs, tiles_per_cta;
+  int patch_bytes;
+  float* dw;
+};
+
+// MN-major, 128-byte-swizzled operand descriptor: rows of 64 bf16 (one K index each), 8-row K groups `sbo` bytes
+// apart, 64-element MN blocks `lbo` bytes apart.
+__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;   // SWIZZLE_128B
+  return d;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ CUtensorMap tm_x, const WgParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * A_STAGE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + STAGES * B_STAGE);
+  uint64_t* full = bars;                 // [STAGES]
+  uint64_t* empty = full + STAGES;       // [STAGES]
+  uint64_t* done = empty + STAGES;       // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int job = blockIdx.x % p.jobs, split = blockIdx.x / p.jobs;
+  const int tg = job & 1;
+  const int ci_slab = (job >> 1) % p.ci_slabs;
+  const int co_block = (job >> 1) / p.ci_slabs;
+  const int tap0 = tg ? 5 : 0, ntaps = tg ? 4 : 5;
+  const int tile_begin = split * p.tiles_per_cta;
+  const int tile_end = min(p.total_tiles, tile_begin + p.tiles_per_cta);
+  const int a_slabs = min(2, (p.C_out - co_block * 128 + 63) / 64);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_g);
+    tma_prefetch_desc(&tm_x);
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1u); mbar_init(&empty[i], 1u); }
+    mbar_init(done, 1u);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int st = 0;
+      uint32_t ph = 0;
+      for (int tile = tile_begin; tile < tile_end; ++tile) {
+        int m = tile;
+        const int w0 = (m % p.tiles_w) * TW; m /= p.tiles_w;
+        const int h0 = (m % p.tiles_h) * p.th_img;
+        const int n0 = (m / p.tiles_h) * p.imgs;
+        mbar_wait(&empty[st], ph ^ 1u);
+        mbar_arrive_expect_tx(&full[st], a_slabs * A_SLAB + p.patch_bytes);
+        for (int s = 0; s < a_slabs; ++s)
+          tma_load_4d(smem_a + st * A_STAGE + s * A_SLAB, &tm_g, &full[st], co_block * 128 + s * 64, w0, h0, n0);
+        tma_load_4d(smem_b + st * B_STAGE, &tm_x, &full[st], ci_slab * 64, w0 - 1, h0 - 1, n0);
+        if (++st == STAGES) { st = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // bf16 x bf16 -> fp32, A and B MN-major (bits 15 / 16), M = 128, N = 64
+      constexpr uint32_t idesc = umma_idesc_bf16(128, NCOL) | (1u << 15) | (1u << 16);
+      const uint64_t a_hi = umma_desc_mn(0u, A_SLAB, 1024u);
+      const uint64_t b_hi = umma_desc_mn(0u, 16u, PITCH * 128u);
+      // pixel-row offset of K step k8 (two image rows of 8 pixels) inside the patch
+      uint32_t krow[8];
+#pragma unroll
+      for (int k8 = 0; k8 < 8; ++k8) {
+        const int img = (2 * k8) / p.th_img, row = (2 * k8) % p.th_img;
+        krow[k8] = static_cast<uint32_t>((img * (p.th_img + 2) + row) * PITCH);
+      }
+      int st = 0;
+      uint32_t ph = 0, accum = 0;
+      for (int tile = tile_begin; tile < tile_end; ++tile) {
+        mbar_wait(&full[st], ph);
+        tc_fence_after();
+        const uint64_t a_d = a_hi + (smem_u32(smem_a + st * A_STAGE) >> 4);
+        const uint32_t b_addr = smem_u32(smem_b + st * B_STAGE);
+#pragma unroll 1
+        for (int t = 0; t < ntaps; ++t) {
+          const int tap = tap0 + t;
+          const uint32_t toff = static_cast<uint32_t>((tap / 3) * PITCH + tap % 3);
+          const uint32_t d_tmem = tmem_base + t * NCOL;
+#pragma unroll
+          for (int k8 = 0; k8 < 8; ++k8) {
+            const uint64_t b_d = b_hi + ((b_addr + (krow[k8] + toff) * 128u) >> 4);
+            umma_bf16_ss(d_tmem, a_d + ((k8 * 2048) >> 4), b_d, idesc, (accum | k8) != 0 ? 1u : 0u);
+          }
+        }
+        accum = 1;
+        umma_commit(&empty[st]);
+        if (++st == STAGES) { st = 0; ph ^= 1u; }
+      }
+      umma_commit(done);
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int co = co_block * 128 + quarter * 32 + lane;
+    mbar_wait(done, 0);
+    tc_fence_after();
+    for (int t = 0; t < ntaps; ++t) {
+      const int tap = tap0 + t;
+#pragma unroll
+      for (int c0 = 0; c0 < NCOL; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld_x16(tmem_base + t * NCOL + c0 + (static_cast<uint32_t>(quarter * 32) << 16), v);
+        tmem_ld_wait();
+        if (co < p.C_out) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int ci = ci_slab * 64 + c0 + j;
+            if (ci < p.C_in) atomicAdd(p.dw + (static_cast<int64_t>(co) * p.C_in + ci) * 9 + tap, __uint_as_float(v[j]));
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+}  // namespace
+
+int dt_encode_bf16_map(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                       const uint32_t* box, const uint32_t* elem_strides);
+
+extern "C" int dt_conv2d_wgrad_tc(const void* x, const void* gy, int N, int H, int W, int C_in, int C_out, float* dw_oihw,
+                                  dt_stream_t stream) {
+  DT_ARCH_GUARD();
+  DT_REQUIRE(N > 0 && H > 0 && W > 0 && C_in > 0 && C_out > 0, DT_ERR_BAD_SHAPE, "dt_conv2d_wgrad_tc: bad shape");
+  const bool rows_ok = (H % TH == 0) || (H == 8 && N % 2 == 0);
+  if (W % TW != 0 || !rows_ok || C_in % 8 != 0 || C_out % 8 != 0) {
+    dt_set_error("dt_conv2d_wgrad_tc: unsupported shape N=%d H=%d W=%d C_in=%d C_out=%d", N, H, W, C_in, C_out);
+    return DT_ERR_UNSUPPORTED;
+  }
+  DT_REQUIRE((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(gy)) % 16 == 0, DT_ERR_BAD_ALIGN,
+             "dt_conv2d_wgrad_tc: tensors must be 16-byte aligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  WgParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = N; p.H = H; p.W = W; p.C_in = C_in; p.C_out = C_out;
+  p.th_img = H >= TH ? TH : H;
+  p.imgs = TH / p.th_img;
+  p.tiles_w = W / TW;
+  p.tiles_h = H / p.th_img;
+  p.total_tiles = p.tiles_w * p.tiles_h * (N / p.imgs);
+  p.ci_slabs = (C_in + 63) / 64;
+  const int co_blocks = (C_out + 127) / 128;
+  p.jobs = co_blocks * p.ci_slabs * 2;
+  p.patch_bytes = p.imgs * (p.th_img + 2) * PITCH * 128;
+  int splits = (2 * dt_num_sms() + p.jobs - 1) / p.jobs;      // about two waves of CTAs
+  if (splits > p.total_tiles) splits = p.total_tiles;
+  if (splits < 1) splits = 1;
+  p.tiles_per_cta = (p.total_tiles + splits - 1) / splits;
+  splits = (p.total_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
+  p.dw = dw_oihw;
+  DT_CUDA(cudaMemsetAsync(dw_oihw, 0, sizeof(float) * static_cast<size_t>(C_out) * C_in * 9, s));
+
+  CUtensorMap tm_g, tm_x;
+  {
+    const uint64_t dims[4] = {static_cast<uint64_t>(C_out), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
+                              static_cast<uint64_t>(N)};
+    const uint64_t strides[3] = {static_cast<uint64_t>(C_out) * 2, static_cast<uint64_t>(W) * C_out * 2,
+                                 static_cast<uint64_t>(H) * W * C_out * 2};
+    const uint32_t box[4] = {64, TW, static_cast<uint32_t>(p.th_img), static_cast<uint32_t>(p.imgs)};
+    int rc = dt_encode_bf16_map(&tm_g, gy, 4, dims, strides, box, nullptr);
+    if (rc != DT_OK) return rc;
+  }
+  {
+    const uint64_t dims[4] = {static_cast<uint64_t>(C_in), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
+                              static_cast<uint64_t>(N)};
+    const uint64_t strides[3] = {static_cast<uint64_t>(C_in) * 2, static_cast<uint64_t>(W) * C_in * 2,
+                                 static_cast<uint64_t>(H) * W * C_in * 2};
+    const uint32_t box[4] = {64, PITCH, static_cast<uint32_t>(p.th_img + 2), static_cast<uint32_t>(p.imgs)};
+    int rc = dt_encode_bf16_map(&tm_x, x, 4, dims, strides, box, nullptr);
+    if (rc != DT_OK) return rc;
+  }
+  constexpr int SMEM = STAGES * (A_STAGE + B_STAGE) + 1024 + 256;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+  });
+  DT_CUDA(attr_err);
+  conv_wgrad_kernel<<<p.jobs * splits, kThreads, SMEM, s>>>(tm_g, tm_x, p);
+  DT_LAUNCH_CHECK();
+  return DT_OK;
+}

@@ -1,0 +1,706 @@
+// Training-step kernels that are HBM-bound or generic (CUDA cores): train-mode BatchNorm forward / backward
+// (two-stage deterministic per-channel reductions), ReLU masks, maxpool backward, nearest-x2 + concat and its
+// backward, weight repacking, and generic direct dgrad / wgrad used by the fp32 check mode and by the layer
+// shapes the tcgen05 kernels do not cover.
+//
+// Reference behaviour: autograd of smp.Unet(resnet34) in train mode as driven by SemSegment.training_step
+// (deadtrees/network/segmodel.py:210-229): nn.BatchNorm2d (batch statistics, biased variance for the
+// normalisation, unbiased for running_var, momentum 0.1, eps 1e-5), ReLU, MaxPool2d(3, 2, 1),
+// F.interpolate(nearest x2) + torch.cat (decoder convention: network/extra/resunet/decoder.py:41-43).
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+template <typename T> struct VecOf;
+template <> struct VecOf<float> { static constexpr int N = 4; };
+template <> struct VecOf<__nv_bfloat16> { static constexpr int N = 8; };
+
+template <typename T> __device__ __forceinline__ void load_vec(const T* p, float* f);
+template <> __device__ __forceinline__ void load_vec<float>(const float* p, float* f) {
+  const float4 v = *reinterpret_cast<const float4*>(p);
+  f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+}
+template <> __device__ __forceinline__ void load_vec<__nv_bfloat16>(const __nv_bfloat16* p, float* f) {
+  const uint4 v = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 t = unpack_bf16x2(w[j]);
+    f[2 * j] = t.x; f[2 * j + 1] = t.y;
+  }
+}
+template <typename T> __device__ __forceinline__ void store_vec(T* p, const float* f);
+template <> __device__ __forceinline__ void store_vec<float>(float* p, const float* f) {
+  *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+}
+template <> __device__ __forceinline__ void store_vec<__nv_bfloat16>(__nv_bfloat16* p, const float* f) {
+  *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                                             pack_bf16x2(f[6], f[7]));
+}
+template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+inline int grid_for(int64_t work, int per_sm = 8) {
+  int64_t blocks = (work + kThreads - 1) / kThreads;
+  const int64_t cap = static_cast<int64_t>(dt_num_sms()) * per_sm;
+  return static_cast<int>(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
+}
+
+// ---- per-channel two-value reductions over an NHWC tensor ---------------------------------------------------
+// MODE 0: (sum y, sum y^2)                      -> BatchNorm batch statistics
+// MODE 1: (sum gz, sum gz * yhat), gz = g * [a > 0], yhat = (y - mean) * invstd  -> BatchNorm backward
+// Thread = one 16-byte vector of channels, walking pixels; block partials are written to part[2][gridDim.x][C]
+// and summed in a fixed order by the finalize kernels (deterministic, no atomics).
+template <typename T, int MODE>
+__global__ void channel_reduce_kernel(const T* __restrict__ y, const T* __restrict__ g, const T* __restrict__ a,
+                                      const float* __restrict__ mean, const float* __restrict__ invstd, int64_t M, int C,
+                                      float* __restrict__ part) {
+  constexpr int VN = VecOf<T>::N;
+  const int V = C / VN;                    // vectors per pixel (divides kThreads)
+  const int lanes = kThreads / V;
+  const int v = threadIdx.x % V, lane = threadIdx.x / V;
+  float s[VN], q[VN], mu[VN], is[VN];
+#pragma unroll
+  for (int j = 0; j < VN; ++j) { s[j] = q[j] = 0.f; mu[j] = 0.f; is[j] = 1.f; }
+  if (MODE == 1) {
+#pragma unroll
+    for (int j = 0; j < VN; ++j) { mu[j] = mean[v * VN + j]; is[j] = invstd[v * VN + j]; }
+  }
+  for (int64_t p = static_cast<int64_t>(blockIdx.x) * lanes + lane; p < M; p += static_cast<int64_t>(gridDim.x) * lanes) {
+    float fy[VN];
+    load_vec<T>(y + p * C + v * VN, fy);
+    if (MODE == 0) {
+#pragma unroll
+      for (int j = 0; j < VN; ++j) { s[j] += fy[j]; q[j] = fmaf(fy[j], fy[j], q[j]); }
+    } else {
+      float fg[VN], fa[VN];
+      load_vec<T>(g + p * C + v * VN, fg);
+      if (a) load_vec<T>(a + p * C + v * VN, fa);
+#pragma unroll
+      for (int j = 0; j < VN; ++j) {
+        const float gz = (a == nullptr || fa[j] > 0.f) ? fg[j] : 0.f;
+        s[j] += gz;
+        q[j] = fmaf(gz, (fy[j] - mu[j]) * is[j], q[j]);
+      }
+    }
+  }
+  __shared__ float sh[2][kThreads][VN + 1];
+#pragma unroll
+  for (int j = 0; j < VN; ++j) { sh[0][threadIdx.x][j] = s[j]; sh[1][threadIdx.x][j] = q[j]; }
+  __syncthreads();
+  if (lane == 0) {
+#pragma unroll
+    for (int j = 0; j < VN; ++j) {
+      float ts = 0.f, tq = 0.f;
+      for (int l = 0; l < lanes; ++l) { ts += sh[0][l * V + v][j]; tq += sh[1][l * V + v][j]; }
+      part[static_cast<int64_t>(blockIdx.x) * C + v * VN + j] = ts;
+      part[(static_cast<int64_t>(gridDim.x) + blockIdx.x) * C + v * VN + j] = tq;
+    }
+  }
+}
+
+// batch statistics -> (scale, shift) of the normalisation, saved (mean, invstd), running-stat update
+__global__ void bn_finalize_kernel(const float* __restrict__ part, int nblocks, int C, double M, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float eps, float momentum,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var,
+                                   float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
+                                   float* __restrict__ invstd_out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0, q = 0.0;
+  for (int b = 0; b < nblocks; ++b) {
+    s += part[static_cast<int64_t>(b) * C + c];
+    q += part[(static_cast<int64_t>(nblocks) + b) * C + c];
+  }
+  const double mean = s / M;
+  double var = q / M - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float invstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  const float sc = gamma[c] * invstd;
+  scale[c] = sc;
+  shift[c] = beta[c] - static_cast<float>(mean) * sc;
+  mean_out[c] = static_cast<float>(mean);
+  invstd_out[c] = invstd;
+  if (running_mean) {
+    const double unbiased = M > 1.0 ? var * M / (M - 1.0) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * static_cast<float>(mean);
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * static_cast<float>(unbiased);
+  }
+}
+
+// BatchNorm backward coefficients: dgamma, dbeta and c1 = dbeta / M, c2 = dgamma / M
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ part, int nblocks, int C, double M,
+                                       float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ c1,
+                                       float* __restrict__ c2) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0, q = 0.0;
+  for (int b = 0; b < nblocks; ++b) {
+    s += part[static_cast<int64_t>(b) * C + c];
+    q += part[(static_cast<int64_t>(nblocks) + b) * C + c];
+  }
+  dbeta[c] = static_cast<float>(s);
+  dgamma[c] = static_cast<float>(q);
+  c1[c] = static_cast<float>(s / M);
+  c2[c] = static_cast<float>(q / M);
+}
+
+// a = [relu]( y * scale + shift (+ residual) )
+template <typename T>
+__global__ void bn_apply_kernel(const T* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
+                                const T* __restrict__ residual, int relu, int64_t nvec, int C, T* __restrict__ out) {
+  constexpr int VN = VecOf<T>::N;
+  const int V = C / VN;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < nvec;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c0 = static_cast<int>(i % V) * VN;
+    float f[VN], r[VN];
+    load_vec<T>(y + i * VN, f);
+    if (residual) load_vec<T>(residual + i * VN, r);
+#pragma unroll
+    for (int j = 0; j < VN; ++j) {
+      float t = fmaf(f[j], __ldg(scale + c0 + j), __ldg(shift + c0 + j));
+      if (residual) t += r[j];
+      f[j] = relu ? fmaxf(t, 0.f) : t;
+    }
+    store_vec<T>(out + i * VN, f);
+  }
+}
+
+// gz = g * [a > 0];  gy = scale * (gz - c1 - yhat * c2);  optional second output gz (identity branch of a block)
+template <typename T>
+__global__ void bn_bwd_apply_kernel(const T* __restrict__ g, const T* __restrict__ a, const T* __restrict__ y,
+                                    const float* __restrict__ mean, const float* __restrict__ invstd,
+                                    const float* __restrict__ scale, const float* __restrict__ c1,
+                                    const float* __restrict__ c2, int64_t nvec, int C, T* __restrict__ gy,
+                                    T* __restrict__ gz_out) {
+  constexpr int VN = VecOf<T>::N;
+  const int V = C / VN;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < nvec;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c0 = static_cast<int>(i % V) * VN;
+    float fg[VN], fa[VN], fy[VN], o[VN];
+    load_vec<T>(g + i * VN, fg);
+    if (a) load_vec<T>(a + i * VN, fa);
+    load_vec<T>(y + i * VN, fy);
+#pragma unroll
+    for (int j = 0; j < VN; ++j) {
+      const float gz = (a == nullptr || fa[j] > 0.f) ? fg[j] : 0.f;
+      fg[j] = gz;
+      const float yhat = (fy[j] - __ldg(mean + c0 + j)) * __ldg(invstd + c0 + j);
+      o[j] = __ldg(scale + c0 + j) * (gz - __ldg(c1 + c0 + j) - yhat * __ldg(c2 + c0 + j));
+    }
+    store_vec<T>(gy + i * VN, o);
+    if (gz_out) store_vec<T>(gz_out + i * VN, fg);
+  }
+}
+
+// out = a + b (vectorised), used to merge gradient contributions
+template <typename T>
+__global__ void add_kernel(const T* __restrict__ a, const T* __restrict__ b, int64_t nvec, T* __restrict__ out) {
+  constexpr int VN = VecOf<T>::N;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < nvec;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float fa[VN], fb[VN];
+    load_vec<T>(a + i * VN, fa);
+    load_vec<T>(b + i * VN, fb);
+#pragma unroll
+    for (int j = 0; j < VN; ++j) fa[j] += fb[j];
+    store_vec<T>(out + i * VN, fa);
+  }
+}
+
+// MaxPool2d(3, 2, 1) backward, gather form: every input element sums the gradients of the (<= 4) windows whose
+// FIRST maximum (row-major scan, as ATen's max_pool2d_with_indices) it is; plus an optional addend.
+template <typename T>
+__global__ void maxpool_bwd_kernel(const T* __restrict__ x, const T* __restrict__ gout, const T* __restrict__ addend,
+                                   int N, int H, int W, int C, int Ho, int Wo, T* __restrict__ gx) {
+  const int64_t total = static_cast<int64_t>(N) * H * W * C;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    int64_t r = i / C;
+    const int w = static_cast<int>(r % W); r /= W;
+    const int h = static_cast<int>(r % H);
+    const int n = static_cast<int>(r / H);
+    const T* xn = x + static_cast<int64_t>(n) * H * W * C + c;
+    float acc = addend ? to_f<T>(addend[i]) : 0.f;
+    // windows (ho, wo) with 2*ho - 1 <= h <= 2*ho + 1
+    for (int ho = (h >> 1); ho <= ((h + 1) >> 1); ++ho) {
+      if (ho < 0 || ho >= Ho) continue;
+      for (int wo = (w >> 1); wo <= ((w + 1) >> 1); ++wo) {
+        if (wo < 0 || wo >= Wo) continue;
+        float best = -INFINITY;
+        int bh = -1, bw = -1;
+        for (int dy = 0; dy < 3; ++dy) {
+          const int hi = 2 * ho + dy - 1;
+          if (hi < 0 || hi >= H) continue;
+          for (int dx = 0; dx < 3; ++dx) {
+            const int wi = 2 * wo + dx - 1;
+            if (wi < 0 || wi >= W) continue;
+            const float v = to_f<T>(xn[(static_cast<int64_t>(hi) * W + wi) * C]);
+            if (v > best || bh < 0) { best = v; bh = hi; bw = wi; }
+          }
+        }
+        if (bh == h && bw == w) acc += to_f<T>(gout[((static_cast<int64_t>(n) * Ho + ho) * Wo + wo) * C + c]);
+      }
+    }
+    gx[i] = from_f<T>(acc);
+  }
+}
+
+// cat([nearest_x2(x_low), skip], C): (N, H/2, W/2, Cx) + (N, H, W, Cs) -> (N, H, W, Cx + Cs); 16-byte vectors
+template <typename T>
+__global__ void upsample_concat_kernel(const T* __restrict__ xl, const T* __restrict__ skip, int N, int H, int W, int Cx,
+                                       int Cs, T* __restrict__ out) {
+  constexpr int VN = VecOf<T>::N;
+  const int Cv = (Cx + Cs) / VN, Cxv = Cx / VN;
+  const int64_t total = static_cast<int64_t>(N) * H * W * Cv;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int cv = static_cast<int>(i % Cv);
+    int64_t r = i / Cv;
+    const int w = static_cast<int>(r % W); r /= W;
+    const int h = static_cast<int>(r % H);
+    const int n = static_cast<int>(r / H);
+    const uint4* src = cv < Cxv
+        ? reinterpret_cast<const uint4*>(xl + ((static_cast<int64_t>(n) * (H >> 1) + (h >> 1)) * (W >> 1) + (w >> 1)) * Cx) + cv
+        : reinterpret_cast<const uint4*>(skip + ((static_cast<int64_t>(n) * H + h) * W + w) * Cs) + (cv - Cxv);
+    reinterpret_cast<uint4*>(out)[i] = *src;
+  }
+}
+
+// backward of the above: g_xl = sum over the 2x2 block of g_cat[..., :Cx]; g_skip = g_cat[..., Cx:]
+template <typename T>
+__global__ void unconcat_bwd_kernel(const T* __restrict__ gcat, int N, int H, int W, int Cx, int Cs, T* __restrict__ gxl,
+                                    T* __restrict__ gskip) {
+  constexpr int VN = VecOf<T>::N;
+  const int C = Cx + Cs, Cxv = Cx / VN, Csv = Cs / VN;
+  const int Hl = H >> 1, Wl = W >> 1;
+  const int64_t n_low = static_cast<int64_t>(N) * Hl * Wl * Cxv;
+  const int64_t n_skip = static_cast<int64_t>(N) * H * W * Csv;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n_low + n_skip;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    if (i < n_low) {
+      const int cv = static_cast<int>(i % Cxv);
+      int64_t r = i / Cxv;
+      const int wl = static_cast<int>(r % Wl); r /= Wl;
+      const int hl = static_cast<int>(r % Hl);
+      const int n = static_cast<int>(r / Hl);
+      float acc[VN];
+#pragma unroll
+      for (int j = 0; j < VN; ++j) acc[j] = 0.f;
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          float f[VN];
+          load_vec<T>(gcat + ((static_cast<int64_t>(n) * H + 2 * hl + dy) * W + 2 * wl + dx) * C + cv * VN, f);
+#pragma unroll
+          for (int j = 0; j < VN; ++j) acc[j] += f[j];
+        }
+      store_vec<T>(gxl + i * VN, acc);
+    } else {
+      const int64_t k = i - n_low;
+      const int cv = static_cast<int>(k % Csv);
+      const int64_t pix = k / Csv;
+      reinterpret_cast<uint4*>(gskip)[k] = *(reinterpret_cast<const uint4*>(gcat + pix * C + Cx) + cv);
+    }
+  }
+}
+
+// (N, K, H, W) fp32 -> (N, H, W, Kp) in T, channels >= K zero
+template <typename T>
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int N, int K, int64_t HW, int Kp, T* __restrict__ out) {
+  const int64_t total = static_cast<int64_t>(N) * HW * Kp;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int k = static_cast<int>(i % Kp);
+    const int64_t r = i / Kp;
+    const int64_t px = r % HW, n = r / HW;
+    out[i] = from_f<T>(k < K ? x[(n * K + k) * HW + px] : 0.f);
+  }
+}
+
+// ---- weight repacking (fp32 OIHW master -> kernel layouts) ----------------------------------------------------
+// mode 0: fp32 [tap][C_in_p][C_out]                                   (direct forward; C_in_p >= C_in, zero padded)
+// mode 1: bf16 [C_out][Kpad], k = tap * C_in + ci                      (tcgen05 forward)
+// mode 2: bf16 [C_out][256],  k = r * 32 + s * 4 + ci                  (tcgen05 stem, C_in <= 4, 7x7)
+// mode 3: bf16 [C_in][Kpad],  k = (RS - 1 - tap) * C_out + co          (dgrad of a stride-1 conv run as a forward conv)
+__global__ void pack_weight_kernel(const float* __restrict__ w, int C_out, int C_in, int R, int S, int mode, int C_in_p,
+                                   int Kpad, void* __restrict__ out, int64_t total) {
+  const int RS = R * S;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    if (mode == 0) {
+      const int co = static_cast<int>(i % C_out);
+      const int ci = static_cast<int>((i / C_out) % C_in_p);
+      const int tap = static_cast<int>(i / (static_cast<int64_t>(C_out) * C_in_p));
+      static_cast<float*>(out)[i] = ci < C_in ? w[(static_cast<int64_t>(co) * C_in + ci) * RS + tap] : 0.f;
+    } else if (mode == 1) {
+      const int k = static_cast<int>(i % Kpad), co = static_cast<int>(i / Kpad);
+      float v = 0.f;
+      if (k < RS * C_in) { const int tap = k / C_in, ci = k % C_in; v = w[(static_cast<int64_t>(co) * C_in + ci) * RS + tap]; }
+      static_cast<__nv_bfloat16*>(out)[i] = __float2bfloat16_rn(v);
+    } else if (mode == 2) {
+      const int k = static_cast<int>(i % Kpad), co = static_cast<int>(i / Kpad);
+      const int r = k >> 5, s = (k & 31) >> 2, ci = k & 3;
+      float v = 0.f;
+      if (r < R && s < S && ci < C_in) v = w[(static_cast<int64_t>(co) * C_in + ci) * RS + r * S + s];
+      static_cast<__nv_bfloat16*>(out)[i] = __float2bfloat16_rn(v);
+    } else {
+      const int k = static_cast<int>(i % Kpad), ci = static_cast<int>(i / Kpad);
+      float v = 0.f;
+      if (k < RS * C_out) { const int tf = k / C_out, co = k % C_out; v = w[(static_cast<int64_t>(co) * C_in + ci) * RS + (RS - 1 - tf)]; }
+      static_cast<__nv_bfloat16*>(out)[i] = __float2bfloat16_rn(v);
+    }
+  }
+}
+
+// ---- generic direct dgrad / wgrad (CUDA cores) ------------------------------------------------------------------
+struct BwdGeo {
+  int N, H, W, C_in, C_x;   // conv input (N, H, W, C_x) storage, C_in <= C_x real channels
+  int C_out, R, S, stride, pad, Ho, Wo;
+};
+
+// gx[n,h,w,ci] = addend + sum_{r,s,co} gy[n,(h+pad-r)/st,(w+pad-s)/st,co] * w[co,ci,r,s]   (w: fp32 OIHW master)
+template <typename T>
+__global__ void dgrad_direct_kernel(BwdGeo p, const T* __restrict__ gy, const float* __restrict__ w,
+                                    const T* __restrict__ addend, T* __restrict__ gx) {
+  const int64_t total = static_cast<int64_t>(p.N) * p.H * p.W * p.C_x;
+  const int RS = p.R * p.S;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int ci = static_cast<int>(i % p.C_x);
+    int64_t r = i / p.C_x;
+    const int wx = static_cast<int>(r % p.W); r /= p.W;
+    const int hx = static_cast<int>(r % p.H);
+    const int n = static_cast<int>(r / p.H);
+    float acc = addend ? to_f<T>(addend[i]) : 0.f;
+    if (ci < p.C_in) {
+      for (int fr = 0; fr < p.R; ++fr) {
+        const int hn = hx + p.pad - fr;
+        if (hn < 0 || hn % p.stride) continue;
+        const int ho = hn / p.stride;
+        if (ho >= p.Ho) continue;
+        for (int fs = 0; fs < p.S; ++fs) {
+          const int wn = wx + p.pad - fs;
+          if (wn < 0 || wn % p.stride) continue;
+          const int wo = wn / p.stride;
+          if (wo >= p.Wo) continue;
+          const T* gp = gy + ((static_cast<int64_t>(n) * p.Ho + ho) * p.Wo + wo) * p.C_out;
+          const float* wp = w + static_cast<int64_t>(ci) * RS + fr * p.S + fs;
+          for (int co = 0; co < p.C_out; ++co) acc = fmaf(to_f<T>(gp[co]), wp[static_cast<int64_t>(co) * p.C_in * RS], acc);
+        }
+      }
+    }
+    gx[i] = from_f<T>(acc);
+  }
+}
+
+// dw[co,ci,r,s] += sum_{n,ho,wo} gy[n,ho,wo,co] * x[n,ho*st+r-pad,wo*st+s-pad,ci]   (dw: fp32 OIHW, caller zeroes)
+// grid = (pixel chunks, co tiles * ci tiles, taps); block tile 32 co x 32 ci, thread = 1 co x 4 ci; the pixel chunk is
+// staged through shared memory 32 output pixels at a time.
+template <typename T>
+__global__ void wgrad_direct_kernel(BwdGeo p, const T* __restrict__ x, const T* __restrict__ gy, float* __restrict__ dw,
+                                    int ci_tiles, int64_t M) {
+  constexpr int TP = 32;
+  __shared__ float sg[TP][33];
+  __shared__ float sx[TP][33];
+  const int tap = blockIdx.z, fr = tap / p.S, fs = tap % p.S;
+  const int co0 = (blockIdx.y / ci_tiles) * 32, ci0 = (blockIdx.y % ci_tiles) * 32;
+  const int col = threadIdx.x >> 3, cig = (threadIdx.x & 7) * 4;   // compute role
+  const int lp = threadIdx.x >> 3, lc = (threadIdx.x & 7) * 4;     // load role: pixel lp, channels lc..lc+3
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const int64_t per = (M + gridDim.x - 1) / gridDim.x;
+  const int64_t m0 = blockIdx.x * per, m1 = min(M, m0 + per);
+  for (int64_t mb = m0; mb < m1; mb += TP) {
+    {
+      const int64_t m = mb + lp;
+      float g4[4] = {0.f, 0.f, 0.f, 0.f}, x4[4] = {0.f, 0.f, 0.f, 0.f};
+      if (m < m1) {
+        const int wo = static_cast<int>(m % p.Wo);
+        const int64_t t = m / p.Wo;
+        const int ho = static_cast<int>(t % p.Ho);
+        const int n = static_cast<int>(t / p.Ho);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (co0 + lc + j < p.C_out) g4[j] = to_f<T>(gy[m * p.C_out + co0 + lc + j]);
+        const int hi = ho * p.stride + fr - p.pad, wi = wo * p.stride + fs - p.pad;
+        if (hi >= 0 && hi < p.H && wi >= 0 && wi < p.W) {
+          const T* xp = x + ((static_cast<int64_t>(n) * p.H + hi) * p.W + wi) * p.C_x;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (ci0 + lc + j < p.C_in) x4[j] = to_f<T>(xp[ci0 + lc + j]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { sg[lp][lc + j] = g4[j]; sx[lp][lc + j] = x4[j]; }
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int q = 0; q < TP; ++q) {
+      const float g = sg[q][col];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[j] = fmaf(g, sx[q][cig + j], acc[j]);
+    }
+    __syncthreads();
+  }
+  const int co = co0 + col;
+  if (co < p.C_out) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int ci = ci0 + cig + j;
+      if (ci < p.C_in) atomicAdd(dw + (static_cast<int64_t>(co) * p.C_in + ci) * (p.R * p.S) + tap, acc[j]);
+    }
+  }
+}
+
+// db[k] += sum over pixels of g[pix][k]  (bias gradient of the head; C small)
+template <typename T>
+__global__ void bias_grad_kernel(const T* __restrict__ g, int64_t M, int C, int K, float* __restrict__ db) {
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int64_t m = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; m < M;
+       m += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    for (int k = 0; k < K; ++k) acc[k] += to_f<T>(g[m * C + k]);
+  }
+  for (int k = 0; k < K; ++k) {
+    const float t = warp_sum(acc[k]);
+    if ((threadIdx.x & 31) == 0) atomicAdd(db + k, t);
+  }
+}
+
+int reduce_blocks(int64_t M, int C, int vn) {
+  const int lanes = kThreads / (C / vn);
+  int64_t b = (M + lanes * 16 - 1) / (static_cast<int64_t>(lanes) * 16);
+  const int64_t cap = static_cast<int64_t>(dt_num_sms()) * 4;
+  if (b > cap) b = cap;
+  return static_cast<int>(b < 1 ? 1 : b);
+}
+
+bool vec_ok(int C, int dtype) {
+  const int vn = dtype == DT_BF16 ? 8 : 4;
+  return C % vn == 0 && C / vn <= kThreads && kThreads % (C / vn) == 0;
+}
+
+}  // namespace
+
+#define DT_DTYPE_SWITCH(dtype, CALL_F32, CALL_BF16) \
+  do { if ((dtype) == DT_F32) { CALL_F32; } else { CALL_BF16; } } while (0)
+
+extern "C" {
+
+int dt_reduce_blocks(int64_t M, int C, int dtype) {
+  if (M <= 0 || !vec_ok(C, dtype)) return DT_ERR_BAD_SHAPE;
+  return reduce_blocks(M, C, dtype == DT_BF16 ? 8 : 4);
+}
+
+int dt_bn_train_stats(const void* y, int64_t M, int C, int dtype, const float* gamma, const float* beta, float eps,
+                      float momentum, float* running_mean, float* running_var, float* scale, float* shift, float* mean,
+                      float* invstd, float* workspace, dt_stream_t stream) {
+  DT_ARCH_GUARD();
+  DT_REQUIRE(M > 0 && (dtype == DT_F32 || dtype == DT_BF16) && vec_ok(C, dtype), DT_ERR_BAD_SHAPE,
+             "dt_bn_train_stats: M=%lld C=%d dtype=%d", static_cast<long long>(M), C, dtype);
+  DT_REQUIRE(reinterpret_cast<uintptr_t>(y) % 16 == 0, DT_ERR_BAD_ALIGN, "dt_bn_train_stats: y must be 16-byte aligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int nb = reduce_blocks(M, C, dtype == DT_BF16 ? 8 : 4);
+  DT_DTYPE_SWITCH(dtype,
+      (channel_reduce_kernel<float, 0><<<nb, kThreads, 0, s>>>(static_cast<const float*>(y), nullptr, nullptr, nullptr, nullptr, M, C, workspace)),
+      (channel_reduce_kernel<__nv_bfloat16, 0><<<nb, kThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(y), nullptr, nullptr, nullptr, nullptr, M, C, workspace)));
+  DT_LAUNCH_CHECK();
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(workspace, nb, C, static_cast<double>(M), gamma, beta, eps, momentum,
+                                                     running_mean, running_var, scale, shift, mean, invstd);
+  DT_LAUNCH_CHECK();
+  return DT_OK;
+}
+
+int dt_bn_apply(const void* y, int64_t M, int C, int dtype, const float* scale, const float* shift, const void* residual,
+                int relu, void* out, dt_stream_t stream) {
+  DT_ARCH_GUARD();
+  DT_REQUIRE(M > 0 && (dtype == DT_F32 || dtype == DT_BF16) && vec_ok(C, dtype), DT_ERR_BAD_SHAPE,
+             "dt_bn_apply: M=%lld C=%d dtype=%d", static_cast<long long>(M), C, dtype);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int64_t nvec = M * C / (dtype == DT_BF16 ? 8 : 4);
+  DT_DTYPE_SWITCH(dtype,
+      (bn_apply_kernel<float><<<grid_for(nvec), kThreads, 0, s>>>(static_cast<const float*>(y), scale, shift, static_cast<const float*>(residual), relu, nvec, C, static_cast<float*>(out))),
+      (bn_apply_kernel<__nv_bfloat16><<<grid_for(nvec), kThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(y), scale, shift, static_cast<const __nv_bfloat16*>(residual), relu, nvec, C, static_cast<__nv_bfloat16*>(out))));
+  DT_LAUNCH_CHECK();
+  return DT_OK;
+}
+
+int dt_bn_train_bwd(const void* g, const void* a, const void* y, int64_t M, int C, int dtype, const float* mean,
+                    const float* invstd, const float* scale, float* dgamma, float* dbeta, void* gy, void* gz_out,
+                    float* workspace, dt_stream_t stream) {
+  DT_ARCH_GUARD();
+  DT_REQUIRE(M > 0 && (dtype == DT_F32 || dtype == DT_BF16) && vec_ok(C, dtype), DT_ERR_BAD_SHAPE,
+             "dt_bn_train_bwd: M=%lld C=%d dtype=%d", static_cast<long long>(M), C, dtype);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int vn = dtype == DT_BF16 ? 8 : 4;
+  const int nb = reduce_blocks(M, C, vn);
+  float* c1 = workspace + static_cast<int64_t>(2) * nb * C;
+  float* c2 = c1 + C;
+  const int64_t nvec = M * C / vn;
+  DT_DTYPE_SWITCH(dtype,
+      (channel_reduce_kernel<float, 1><<<nb, kThreads, 0, s>>>(static_cast<const float*>(y), static_cast<const float*>(g), static_cast<const float*>(a), mean, invstd, M, C, workspace)),
+      (channel_reduce_kernel<__nv_bfloat16, 1><<<nb, kThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(y), static_cast<const __nv_bfloat16*>(g), static_cast<const __nv_bfloat16*>(a), mean, invstd, M, C, workspace)));
+  DT_LAUNCH_CHECK();
+  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(workspace, nb, C, static_cast<double>(M), dgamma, dbeta, c1, c2);
+  DT_LAUNCH_CHECK();
+  DT_DTYPE_SWITCH(dtype,
+      (bn_bwd_apply_kernel<float><<<grid_for(nvec), kThreads, 0, s>>>(static_cast<const float*>(g), static_cast<const float*>(a), static_cast<const float*>(y), mean, invstd, scale, c1, c2, nvec, C, static_cast<float*>(gy), static_cast<float*>(gz_out))),
+      (bn_bwd_apply_kernel<__nv_bfloat16><<<grid_for(nvec), kThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(g), static_cast<const __nv_bfloat16*>(a), static_cast<const __nv_bfloat16*>(y), mean, invstd, scale, c1, c2, nvec, C, static_cast<__nv_bfloat16*>(gy), static_cast<__nv_bfloat16*>(gz_out))));
+  DT_LAUNCH_CHECK();
+  return DT_OK;
+}
+
+int dt_add(const void* a, const void* b, int64_t n, int dtype, void* out, dt_stream_t stream) {
+  DT_ARCH_GUARD();
+  const int vn = dtype == DT_BF16 ? 8 : 4;
+  DT_REQUIRE(n > 0 && n % vn == 0 && (dtype == DT_F32 || dtype == DT_BF16), DT_ERR_BAD_SHAPE, "dt_add: n=%lld", static_cast<long long>(n));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int64_t nvec = n / vn;
+  DT_DTYPE_SWITCH(dtype,
+      (add_kernel<float><<<grid_for(nvec), kThreads, 0, s>>>(static_cast<const float*>(a), static_cast<const float*>(b), nvec, static_cast<float*>(out))),
+      (add_kernel<__nv_bfloat16><<<grid_for(nvec), kThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(a), static_cast<const __nv_bfloat16*>(b), nvec, static_cast<__nv_bfloat16*>(out))));
+  DT_LAUNCH_CHECK();
+  return DT_OK;
+}
+
+int dt_maxpool3x3s2_bwd(const void* x, const void* gout, const void* addend, int N, int H, int W, int C, int dtype,
+                        void* gx, dt_stream_t stream) {
+  DT_ARCH_GUARD();
+  DT_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && (dtype == DT_F32 || dtype == DT_BF16), DT_ERR_BAD_SHAPE,
+             "dt_maxpool3x3s2_bwd: bad shape");
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int64_t total = static_cast<int64_t>(N) * H * W * C;
+  DT_DTYPE_SWITCH(dtype,
+      (maxpool_bwd_kernel<float><<<grid_for(total, 16), kThreads, 0, s>>>(static_cast<const float*>(x), static_cast<const float*>(gout), static_cast<const float*>(addend), N, H, W, C, Ho, Wo, static_cast<float*>(gx))),
+      (maxpool_bwd_kernel<__nv_bfloat16><<<grid_for(total, 16), kThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(gout), static_cast<const __nv_bfloat16*>(addend), N, H, W, C, Ho, Wo, static_cast<__nv_bfloat16*>(gx))));
+  DT_LAUNCH_CHECK();
+  return DT_OK;
+}
+
+int dt_upsample_concat(const void* x_low, const void* skip, int N, int H, int W, int Cx, int Cs, int dtype, void* out,
+                       dt_stream_t stream) {
+  DT_ARCH_GUARD();
+  const int vn = dtype == DT_BF16 ? 8 : 4;
+  DT_REQUIRE(N > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0 && Cx > 0 && Cx % vn == 0 && Cs >= 0 && Cs % vn == 0 &&
+                 (Cs == 0 || skip != nullptr) && (dtype == DT_F32 || dtype == DT_BF16),
+             DT_ERR_BAD_SHAPE, "dt_upsample_concat: bad shape (H=%d W=%d Cx=%d Cs=%d)", H, W, Cx, Cs);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int64_t total = static_cast<int64_t>(N) * H * W * ((Cx + Cs) / vn);
+  DT_DTYPE_SWITCH(dtype,
+      (upsample_concat_kernel<float><<<grid_for(total, 16), kThreads, 0, s>>>(static_cast<const float*>(x_low), static_cast<const float*>(skip), N, H, W, Cx, Cs, static_cast<float*>(out))),
+      (upsample_concat_kernel<__nv_bfloat16><<<grid_for(total, 16), kThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(x_low), static_cast<const __nv_bfloat16*>(skip), N, H, W, Cx, Cs, static_cast<__nv_bfloat16*>(out))));
+  DT_LAUNCH_CHECK();
+  return DT_OK;
+}
+
+int dt_upsample_concat_bwd(const void* g_cat, int N, int H, int W, int Cx, int Cs, int dtype, void* g_x_low, void* g_skip,
+                           dt_stream_t stream) {
+  DT_ARCH_GUARD();
+  const int vn = dtype == DT_BF16 ? 8 : 4;
+  DT_REQUIRE(N > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0 && Cx > 0 && Cx % vn == 0 && Cs >= 0 && Cs % vn == 0 &&
+                 (Cs == 0 || g_skip != nullptr) && (dtype == DT_F32 || dtype == DT_BF16),
+             DT_ERR_BAD_SHAPE, "dt_upsample_concat_bwd: bad shape (H=%d W=%d Cx=%d Cs=%d)", H, W, Cx, Cs);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int64_t total = static_cast<int64_t>(N) * (H / 2) * (W / 2) * (Cx / vn) + static_cast<int64_t>(N) * H * W * (Cs / vn);
+  DT_DTYPE_SWITCH(dtype,
+      (unconcat_bwd_kernel<float><<<grid_for(total, 16), kThreads, 0, s>>>(static_cast<const float*>(g_cat), N, H, W, Cx, Cs, static_cast<float*>(g_x_low), static_cast<float*>(g_skip))),
+      (unconcat_bwd_kernel<__nv_bfloat16><<<grid_for(total, 16), kThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(g_cat), N, H, W, Cx, Cs, static_cast<__nv_bfloat16*>(g_x_low), static_cast<__nv_bfloat16*>(g_skip))));
+  DT_LAUNCH_CHECK();
+  return DT_OK;
+}
+
+int dt_nchw_to_nhwc(const float* x, int N, int K, int H, int W, int Kp, int dtype, void* out, dt_stream_t stream) {
+  DT_ARCH_GUARD();
+  DT_REQUIRE(N > 0 && K > 0 && Kp >= K && H > 0 && W > 0 && (dtype == DT_F32 || dtype == DT_BF16), DT_ERR_BAD_SHAPE,
+             "dt_nchw_to_nhwc: bad shape");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int64_t HW = static_cast<int64_t>(H) * W, total = N * HW * Kp;
+  DT_DTYPE_SWITCH(dtype,
+      (nchw_to_nhwc_kernel<float><<<grid_for(total, 16), kThreads, 0, s>>>(x, N, K, HW, Kp, static_cast<float*>(out))),
+      (nchw_to_nhwc_kernel<__nv_bfloat16><<<grid_for(total, 16), kThreads, 0, s>>>(x, N, K, HW, Kp, static_cast<__nv_bfloat16*>(out))));
+  DT_LAUNCH_CHECK();
+  return DT_OK;
+}
+
+int dt_pack_conv_weight(const float* w_oihw, int C_out, int C_in, int R, int S, int mode, int C_in_p, int Kpad, void* out,
+                        dt_stream_t stream) {
+  DT_ARCH_GUARD();
+  DT_REQUIRE(C_out > 0 && C_in > 0 && R > 0 && S > 0 && mode >= 0 && mode <= 3, DT_ERR_BAD_SHAPE, "dt_pack_conv_weight: bad arguments");
+  int64_t total = 0;
+  if (mode == 0) {
+    DT_REQUIRE(C_in_p >= C_in, DT_ERR_BAD_SHAPE, "dt_pack_conv_weight: C_in_p < C_in");
+    total = static_cast<int64_t>(R) * S * C_in_p * C_out;
+  } else if (mode == 1) {
+    DT_REQUIRE(Kpad >= R * S * C_in, DT_ERR_BAD_SHAPE, "dt_pack_conv_weight: Kpad too small");
+    total = static_cast<int64_t>(C_out) * Kpad;
+  } else if (mode == 2) {
+    DT_REQUIRE(Kpad == 256 && C_in <= 4 && R == 7 && S == 7, DT_ERR_BAD_SHAPE, "dt_pack_conv_weight: stem packing needs 7x7, C_in <= 4, Kpad 256");
+    total = static_cast<int64_t>(C_out) * Kpad;
+  } else {
+    DT_REQUIRE(Kpad >= R * S * C_out, DT_ERR_BAD_SHAPE, "dt_pack_conv_weight: Kpad too small");
+    total = static_cast<int64_t>(C_in) * Kpad;
+  }
+  pack_weight_kernel<<<grid_for(total), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(w_oihw, C_out, C_in, R, S, mode,
+                                                                                         C_in_p, Kpad, out, total);
+  DT_LAUNCH_CHECK();
+  return DT_OK;
+}
+
+int dt_conv2d_dgrad_direct(const void* gy, const float* w_oihw, const void* addend, int N, int H, int W, int C_in, int C_x,
+                           int C_out, int R, int S, int stride, int pad, int dtype, void* gx, dt_stream_t stream) {
+  DT_ARCH_GUARD();
+  DT_REQUIRE(N > 0 && H > 0 && W > 0 && C_in > 0 && C_x >= C_in && C_out > 0 && R > 0 && S > 0 && stride > 0 && pad >= 0 &&
+                 (dtype == DT_F32 || dtype == DT_BF16),
+             DT_ERR_BAD_SHAPE, "dt_conv2d_dgrad_direct: bad arguments");
+  BwdGeo p{N, H, W, C_in, C_x, C_out, R, S, stride, pad, (H + 2 * pad - R) / stride + 1, (W + 2 * pad - S) / stride + 1};
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int64_t total = static_cast<int64_t>(N) * H * W * C_x;
+  DT_DTYPE_SWITCH(dtype,
+      (dgrad_direct_kernel<float><<<grid_for(total, 16), kThreads, 0, s>>>(p, static_cast<const float*>(gy), w_oihw, static_cast<const float*>(addend), static_cast<float*>(gx))),
+      (dgrad_direct_kernel<__nv_bfloat16><<<grid_for(total, 16), kThreads, 0, s>>>(p, static_cast<const __nv_bfloat16*>(gy), w_oihw, static_cast<const __nv_bfloat16*>(addend), static_cast<__nv_bfloat16*>(gx))));
+  DT_LAUNCH_CHECK();
+  return DT_OK;
+}
+
+int dt_conv2d_wgrad_direct(const void* x, const void* gy, int N, int H, int W, int C_in, int C_x, int C_out, int R, int S,
+                           int stride, int pad, int dtype, float* dw_oihw, float* dbias, dt_stream_t stream) {
+  DT_ARCH_GUARD();
+  DT_REQUIRE(N > 0 && H > 0 && W > 0 && C_in > 0 && C_x >= C_in && C_out > 0 && R > 0 && S > 0 && R * S <= 65535 &&
+                 stride > 0 && pad >= 0 && (dtype == DT_F32 || dtype == DT_BF16),
+             DT_ERR_BAD_SHAPE, "dt_conv2d_wgrad_direct: bad arguments");
+  BwdGeo p{N, H, W, C_in, C_x, C_out, R, S, stride, pad, (H + 2 * pad - R) / stride + 1, (W + 2 * pad - S) / stride + 1};
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int64_t M = static_cast<int64_t>(N) * p.Ho * p.Wo;
+  const int co_tiles = (C_out + 31) / 32, ci_tiles = (C_in + 31) / 32;
+  int64_t chunks = (static_cast<int64_t>(dt_num_sms()) * 8 + co_tiles * ci_tiles * R * S - 1) / (co_tiles * ci_tiles * R * S);
+  const int64_t max_chunks = (M + 255) / 256;
+  if (chunks > max_chunks) chunks = max_chunks;
+  if (chunks < 1) chunks = 1;
+  DT_CUDA(cudaMemsetAsync(dw_oihw, 0, sizeof(float) * static_cast<size_t>(C_out) * C_in * R * S, s));
+  dim3 grid(static_cast<unsigned>(chunks), co_tiles * ci_tiles, R * S);
+  DT_DTYPE_SWITCH(dtype,
+      (wgrad_direct_kernel<float><<<grid, kThreads, 0, s>>>(p, static_cast<const float*>(x), static_cast<const float*>(gy), dw_oihw, ci_tiles, M)),
+      (wgrad_direct_kernel<__nv_bfloat16><<<grid, kThreads, 0, s>>>(p, static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(gy), dw_oihw, ci_tiles, M)));
+  DT_LAUNCH_CHECK();
+  if (dbias) {
+    DT_REQUIRE(C_out <= 4, DT_ERR_BAD_SHAPE, "dt_conv2d_wgrad_direct: bias gradient supports C_out <= 4 (the head)");
+    DT_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * C_out, s));
+    DT_DTYPE_SWITCH(dtype,
+        (bias_grad_kernel<float><<<grid_for(M, 2), kThreads, 0, s>>>(static_cast<const float*>(gy), M, C_out, C_out, dbias)),
+        (bias_grad_kernel<__nv_bfloat16><<<grid_for(M, 2), kThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(gy), M, C_out, C_out, dbias)));
+    DT_LAUNCH_CHECK();
+  }
+  return DT_OK;
+}
+
+}  // extern "C"

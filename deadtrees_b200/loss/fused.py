@@ -35,3 +35,23 @@ class SegLossTerms:
 
     def grad_logits(self, upstream: float = 1.0) -> torch.Tensor:
         return ops.seg_loss_backward(self.logits, self.labels, self.coef, self.focal_scale, upstream)
+
+
+class _SegLossFn(torch.autograd.Function):
+    """total loss of ``SemSegment.calculate_loss`` on the logits; backward = ``dt_seg_loss_backward``."""
+
+    @staticmethod
+    def forward(ctx, logits: torch.Tensor, terms: "SegLossTerms"):
+        ctx.terms = terms
+        return terms.total_loss.clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        grad = ctx.terms.grad_logits(1.0)
+        return grad.mul_(g), None
+
+
+def seg_loss(logits: torch.Tensor, labels: torch.Tensor, dice_mode: int, use_focal: bool):
+    """-> (differentiable total loss, SegLossTerms with the individual scalars and metrics)."""
+    terms = SegLossTerms(logits.detach(), labels, dice_mode, use_focal)
+    return _SegLossFn.apply(logits, terms), terms

@@ -223,9 +223,26 @@ class SemSegment(_Base):  # type: ignore[misc]
         return logits, loss, terms
 
     def training_step(self, batch, batch_idx):
-        raise NotImplementedError(
-            "the training step (train-mode BatchNorm + backward kernels) is scheduled for the next round; "
-            "validation_step / test_step and inference run on the B200 kernels")
+        """forward (train-mode BatchNorm) + compound loss + metrics, as ``segmodel.py:210-229``; the returned loss is
+        differentiable: ``loss.backward()`` runs the CUDA backward pass and fills ``.grad`` of every parameter."""
+        img, mask, distmap, _, stats = create_combined_batch(batch)
+        if self.boundary_loss and distmap is not None:
+            raise NotImplementedError("the boundary loss has no backward kernel yet (next tier, SURVEY.md §8f-2)")
+        logits = self.model(img)
+        dice_mode = 2 if isinstance(self.dice_loss, GeneralizedDiceLoss) else 1
+        loss, terms = fused.seg_loss(logits, mask, dice_mode, self.focal_loss is not None)
+        terms.check_labels()  # class2one_hot's assert (losses.py:129); also the host sync the reference has there
+        self.log("train/dice_loss", terms.dice_loss, on_step=False, on_epoch=True)
+        if self.focal_loss:
+            self.log("train/focal_loss", terms.focal_loss, on_step=False, on_epoch=True)
+        self.log("train/total_loss", loss.detach(), on_step=False, on_epoch=True)
+        if torch.isnan(loss) or torch.isinf(loss):
+            log.warning("Train loss is NaN! What is going on?")
+            return None
+        self.log("train/dice", terms.fscore, on_step=False, on_epoch=True)
+        self.log("train/dice_with_bg", terms.fscore_with_bg, on_step=False, on_epoch=True)
+        self.stats["train"].update([x["file"] for x in stats])
+        return loss
 
     def validation_step(self, batch, batch_idx):
         img, mask, distmap, lu, stats = create_combined_batch(batch)

@@ -80,6 +80,7 @@ class Unet(nn.Module):
                                                nn.Identity(), nn.Identity())
         self._engine: Optional[UnetEngine] = None
         self._engine_key = None
+        self._train_engine = None
 
     # -- engine management -------------------------------------------------------------------
     def _param_version(self):
@@ -97,7 +98,16 @@ class Unet(nn.Module):
 
     def set_precision(self, precision: str) -> "Unet":
         self.precision = precision
+        self._train_engine = None
         return self
+
+    def train_engine(self):
+        """engine of the train-mode forward / backward (batch-statistics BatchNorm, autograd through the CUDA library)."""
+        from ..train_engine import UnetTrainEngine
+        dev = next(self.parameters()).device
+        if self._train_engine is None or self._train_engine.device != dev or self._train_engine.precision != self.precision:
+            self._train_engine = UnetTrainEngine(self, precision=self.precision)
+        return self._train_engine
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         """(N, C, H, W) float -> (N, classes, H, W) fp32 logits, as ``smp.Unet.forward``."""
@@ -106,6 +116,9 @@ class Unet(nn.Module):
             raise DeadtreesB200Error("deadtrees_b200.Unet runs on a CUDA (B200) device only; move the input with .cuda()")
         if x.dim() != 4 or x.shape[1] < self.in_channels:
             raise ValueError(f"expected (N, >={self.in_channels}, H, W), got {tuple(x.shape)}")
+        if self.training:
+            from ..train_engine import unet_train_forward
+            return unet_train_forward(self.train_engine(), x)
         eng = self.engine()
         xin = ops.pack_input_nchw(x, self.in_channels, eng.act_dtype)
         return eng.forward(xin, want_logits_nchw=True)["logits_nchw"]

@@ -281,3 +281,156 @@ def adam_step(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor
               beta2: float, eps: float, step: int, sumsq_acc: Optional[torch.Tensor], max_norm: float) -> None:
     check(load().dt_adam_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, beta1, beta2,
                               eps, step, ptr(sumsq_acc), max_norm, stream_ptr()))
+
+
+# ---- training step (train-mode BatchNorm, backward) -----------------------------------------------
+
+_WS = {}
+
+
+def _reduce_ws(device) -> torch.Tensor:
+    """workspace for the two-stage per-channel reductions (dt_bn_train_stats / dt_bn_train_bwd)."""
+    ws = _WS.get(device)
+    if ws is None:
+        ws = _WS[device] = torch.empty(2 * 148 * 8 * 1024 + 2048, dtype=torch.float32, device=device)
+    return ws
+
+
+def bn_train_stats(y: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, running_mean: Optional[torch.Tensor],
+                   running_var: Optional[torch.Tensor], eps: float = 1e-5, momentum: float = 0.1):
+    """y (N, H, W, C) raw conv output -> (scale, shift, mean, invstd) float (C,); updates the running stats."""
+    Cc = y.shape[-1]
+    M = y.numel() // Cc
+    scale, shift, mean, invstd = (torch.empty(Cc, dtype=torch.float32, device=y.device) for _ in range(4))
+    check(load().dt_bn_train_stats(y.data_ptr(), M, Cc, _dt(y), gamma.data_ptr(), beta.data_ptr(), eps, momentum,
+                                   ptr(running_mean), ptr(running_var), scale.data_ptr(), shift.data_ptr(),
+                                   mean.data_ptr(), invstd.data_ptr(), _reduce_ws(y.device).data_ptr(), stream_ptr()))
+    return scale, shift, mean, invstd
+
+
+def bn_apply(y: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, residual: Optional[torch.Tensor] = None,
+             relu: bool = True, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    Cc = y.shape[-1]
+    if out is None:
+        out = torch.empty_like(y)
+    check(load().dt_bn_apply(y.data_ptr(), y.numel() // Cc, Cc, _dt(y), scale.data_ptr(), shift.data_ptr(),
+                             ptr(residual), int(relu), out.data_ptr(), stream_ptr()))
+    return out
+
+
+def bn_train_bwd(g: torch.Tensor, a: Optional[torch.Tensor], y: torch.Tensor, mean: torch.Tensor, invstd: torch.Tensor,
+                 scale: torch.Tensor, want_gz: bool = False):
+    """-> (gy, gz or None, dgamma, dbeta)."""
+    Cc = y.shape[-1]
+    gy = torch.empty_like(y)
+    gz = torch.empty_like(y) if want_gz else None
+    dgamma = torch.empty(Cc, dtype=torch.float32, device=y.device)
+    dbeta = torch.empty(Cc, dtype=torch.float32, device=y.device)
+    check(load().dt_bn_train_bwd(g.data_ptr(), ptr(a), y.data_ptr(), y.numel() // Cc, Cc, _dt(y), mean.data_ptr(),
+                                 invstd.data_ptr(), scale.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(),
+                                 gy.data_ptr(), ptr(gz), _reduce_ws(y.device).data_ptr(), stream_ptr()))
+    return gy, gz, dgamma, dbeta
+
+
+def add(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    if out is None:
+        out = torch.empty_like(a)
+    check(load().dt_add(a.data_ptr(), b.data_ptr(), a.numel(), _dt(a), out.data_ptr(), stream_ptr()))
+    return out
+
+
+def maxpool3x3s2_bwd(x: torch.Tensor, gout: torch.Tensor, addend: Optional[torch.Tensor] = None) -> torch.Tensor:
+    N, H, W, Cc = x.shape
+    gx = torch.empty_like(x)
+    check(load().dt_maxpool3x3s2_bwd(x.data_ptr(), gout.data_ptr(), ptr(addend), N, H, W, Cc, _dt(x), gx.data_ptr(),
+                                     stream_ptr()))
+    return gx
+
+
+def upsample_concat(x_low: torch.Tensor, skip: Optional[torch.Tensor]) -> torch.Tensor:
+    N, Hl, Wl, Cx = x_low.shape
+    Cs = 0 if skip is None else skip.shape[-1]
+    out = torch.empty((N, 2 * Hl, 2 * Wl, Cx + Cs), dtype=x_low.dtype, device=x_low.device)
+    check(load().dt_upsample_concat(x_low.data_ptr(), ptr(skip), N, 2 * Hl, 2 * Wl, Cx, Cs, _dt(x_low), out.data_ptr(),
+                                    stream_ptr()))
+    return out
+
+
+def upsample_concat_bwd(g_cat: torch.Tensor, Cx: int):
+    N, H, W, Cc = g_cat.shape
+    Cs = Cc - Cx
+    g_low = torch.empty((N, H // 2, W // 2, Cx), dtype=g_cat.dtype, device=g_cat.device)
+    g_skip = torch.empty((N, H, W, Cs), dtype=g_cat.dtype, device=g_cat.device) if Cs else None
+    check(load().dt_upsample_concat_bwd(g_cat.data_ptr(), N, H, W, Cx, Cs, _dt(g_cat), g_low.data_ptr(), ptr(g_skip),
+                                        stream_ptr()))
+    return g_low, g_skip
+
+
+def nchw_to_nhwc(x: torch.Tensor, Kp: int, dtype: torch.dtype) -> torch.Tensor:
+    N, K, H, W = x.shape
+    out = torch.empty((N, H, W, Kp), dtype=dtype, device=x.device)
+    check(load().dt_nchw_to_nhwc(x.data_ptr(), N, K, H, W, Kp, _dt(out), out.data_ptr(), stream_ptr()))
+    return out
+
+
+def pack_conv_weight(w: torch.Tensor, mode: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp32 OIHW master weights -> kernel layout (see dt_pack_conv_weight): 0 direct fp32, 1 tcgen05 forward,
+    2 tcgen05 stem, 3 dgrad-as-forward."""
+    C_out, C_in, R, S = w.shape
+    cinp, kpad = C_in, 0
+    if mode == 0:
+        cinp = 4 if (R == 7 and C_in < 4) else C_in
+        shape, dtype = (R * S, cinp, C_out), torch.float32
+    elif mode == 1:
+        kpad = (R * S * C_in + 63) // 64 * 64
+        shape, dtype = (C_out, kpad), torch.bfloat16
+    elif mode == 2:
+        kpad = 256
+        shape, dtype = (C_out, kpad), torch.bfloat16
+    else:
+        kpad = (R * S * C_out + 63) // 64 * 64
+        shape, dtype = (C_in, kpad), torch.bfloat16
+    if out is None:
+        out = torch.empty(shape, dtype=dtype, device=w.device)
+    check(load().dt_pack_conv_weight(w.data_ptr(), C_out, C_in, R, S, mode, cinp, kpad, out.data_ptr(), stream_ptr()))
+    return out
+
+
+def conv2d_dgrad_direct(gy: torch.Tensor, w: torch.Tensor, x_shape, stride: int, pad: int,
+                        addend: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """gy (N, Ho, Wo, C_out), w fp32 OIHW -> gx of shape x_shape = (N, H, W, C_x)."""
+    N, H, W, Cx = x_shape
+    C_out, C_in, R, S = w.shape
+    gx = torch.empty(tuple(x_shape), dtype=gy.dtype, device=gy.device)
+    check(load().dt_conv2d_dgrad_direct(gy.data_ptr(), w.data_ptr(), ptr(addend), N, H, W, C_in, Cx, C_out, R, S, stride,
+                                        pad, _dt(gy), gx.data_ptr(), stream_ptr()))
+    return gx
+
+
+def conv2d_wgrad_direct(x: torch.Tensor, gy: torch.Tensor, w_shape, stride: int, pad: int, want_bias: bool = False):
+    """x (N, H, W, C_x), gy (N, Ho, Wo, C_out) -> dw fp32 OIHW (and dbias)."""
+    N, H, W, Cx = x.shape
+    C_out, C_in, R, S = w_shape
+    dw = torch.empty(tuple(w_shape), dtype=torch.float32, device=x.device)
+    db = torch.empty(C_out, dtype=torch.float32, device=x.device) if want_bias else None
+    check(load().dt_conv2d_wgrad_direct(x.data_ptr(), gy.data_ptr(), N, H, W, C_in, Cx, C_out, R, S, stride, pad, _dt(x),
+                                        dw.data_ptr(), ptr(db), stream_ptr()))
+    return dw, db
+
+
+def wgrad_tc_supported(x: torch.Tensor, gy: torch.Tensor, w_shape, stride: int, pad: int) -> bool:
+    """True when the tcgen05 weight-gradient kernel covers this layer shape (dt_conv2d_wgrad_tc)."""
+    C_out, C_in, R, S = w_shape
+    N, H, W, Cx = x.shape
+    return (x.dtype == torch.bfloat16 and R == 3 and S == 3 and stride == 1 and pad == 1 and Cx == C_in and W % 8 == 0
+            and (H % 16 == 0 or (H == 8 and N % 2 == 0)) and C_in % 8 == 0 and C_out % 8 == 0)
+
+
+def conv2d_wgrad_tc(x: torch.Tensor, gy: torch.Tensor, w_shape) -> torch.Tensor:
+    """tensor-core weight gradient of a 3x3/s1/p1 conv: x (N, H, W, C_in), gy (N, H, W, C_out) bf16 -> dw fp32 OIHW."""
+    N, H, W, C_in = x.shape
+    C_out = gy.shape[-1]
+    dw = torch.empty(tuple(w_shape), dtype=torch.float32, device=x.device)
+    with _Timed("wgrad", 2.0 * N * H * W * C_out * C_in * 9):
+        check(load().dt_conv2d_wgrad_tc(x.data_ptr(), gy.data_ptr(), N, H, W, C_in, C_out, dw.data_ptr(), stream_ptr()))
+    return dw

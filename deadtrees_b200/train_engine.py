@@ -1,0 +1,211 @@
+"""Training-step engine for Unet(resnet34): train-mode forward (batch-statistics BatchNorm) and the backward pass,
+sequenced over the CUDA library.
+
+Follows autograd of ``smp.Unet.forward`` as ``SemSegment.training_step`` drives it in the reference
+(``deadtrees/network/segmodel.py:210-229``; layer list SURVEY.md Appendix A; formulas SURVEY.md Appendix D).
+Precision modes: ``"fp32"`` (CUDA-core check mode, every tensor fp32) and ``"bf16"`` (activations and activation
+gradients in bf16, fp32 accumulation; convolutions, data gradients and weight gradients on the tcgen05 kernels where
+the layer shape allows, generic CUDA-core kernels otherwise).  Master weights, BatchNorm parameters and all parameter
+gradients are fp32.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+
+from . import ops
+from ._lib import require_device
+from .engine import RESNET34_LAYERS, RESNET34_PLANES
+
+BN_EPS, BN_MOMENTUM = 1e-5, 0.1
+
+
+class _ConvBN:
+    """tape entry of one conv (+ BatchNorm (+ residual) (+ ReLU))."""
+    __slots__ = ("conv", "bn", "x", "y", "a", "relu", "stride", "pad", "mean", "invstd", "scale", "residual")
+
+    def __init__(self, **kw):
+        for k in self.__slots__:
+            setattr(self, k, kw.get(k))
+
+
+class UnetTrainEngine:
+    def __init__(self, model, precision: str = "bf16", wgrad_tc: bool = True, dgrad_tc: bool = True):
+        require_device()
+        if precision not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16' or 'fp32'")
+        self.model = model
+        self.precision = precision
+        self.act_dtype = torch.bfloat16 if precision == "bf16" else torch.float32
+        self.in_channels, self.classes = model.in_channels, model.classes
+        self.wgrad_tc, self.dgrad_tc = wgrad_tc, dgrad_tc
+        self.params = dict(model.named_parameters())
+        self.buffers = dict(model.named_buffers())
+        self.param_names = list(self.params)
+        dev = next(model.parameters()).device
+        self.device = dev
+        self._ones = torch.ones(1024, dtype=torch.float32, device=dev)
+        self._zeros = torch.zeros(1024, dtype=torch.float32, device=dev)
+
+    # ---- forward pieces --------------------------------------------------------------------------------
+    def _conv_raw(self, x: torch.Tensor, wname: str, stride: int, pad: int) -> torch.Tensor:
+        """raw convolution output (no BN / activation) of x (N, H, W, C_x) with the master weights `wname`."""
+        w = self.params[wname]
+        C_out, C_in, R, S = w.shape
+        N, H, W, Cx = x.shape
+        stem = R == 7
+        if self.precision == "fp32":
+            wp = ops.pack_conv_weight(w, 0)
+        else:
+            wp = ops.pack_conv_weight(w, 2 if stem else 1)
+        return ops.conv2d(x, wp, self._ones, self._zeros, N=N, H=H, W=W, C_in=Cx, C_x=Cx, C_out=C_out, R=R, S=S,
+                          stride=stride, pad=pad, relu=False, algo_cin=C_in, tag="train." + wname)
+
+    def _conv_bn(self, tape: List, x: torch.Tensor, conv: str, bn: str, stride: int, pad: int, relu: bool = True,
+                 residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+        y = self._conv_raw(x, conv + ".weight", stride, pad)
+        scale, shift, mean, invstd = ops.bn_train_stats(
+            y, self.params[bn + ".weight"], self.params[bn + ".bias"], self.buffers.get(bn + ".running_mean"),
+            self.buffers.get(bn + ".running_var"), BN_EPS, BN_MOMENTUM)
+        nbt = self.buffers.get(bn + ".num_batches_tracked")
+        if nbt is not None:
+            nbt += 1
+        a = ops.bn_apply(y, scale, shift, residual=residual, relu=relu)
+        tape.append(_ConvBN(conv=conv, bn=bn, x=x, y=y, a=a, relu=relu, stride=stride, pad=pad, mean=mean,
+                            invstd=invstd, scale=scale, residual=residual))
+        return a
+
+    def forward(self, x_nchw: torch.Tensor):
+        """(N, C, T, T) float -> (logits (N, K, T, T) fp32, tape)."""
+        N, _, T, _ = x_nchw.shape
+        if T % 32:
+            raise ValueError("tile size must be a multiple of 32")
+        tape: List = []
+        x4 = ops.pack_input_nchw(x_nchw, self.in_channels, self.act_dtype)
+        f = {1: self._conv_bn(tape, x4, "encoder.conv1", "encoder.bn1", 2, 3)}
+        pool = ops.maxpool3x3s2(f[1])
+        tape.append(("pool", f[1]))
+        cur = pool
+        for li, (planes, nblk) in enumerate(zip(RESNET34_PLANES, RESNET34_LAYERS), start=1):
+            for b in range(nblk):
+                p = f"encoder.layer{li}.{b}"
+                stride = 2 if (b == 0 and li > 1) else 1
+                a1 = self._conv_bn(tape, cur, p + ".conv1", p + ".bn1", stride, 1)
+                if stride == 2:
+                    idn = self._conv_bn(tape, cur, p + ".downsample.0", p + ".downsample.1", 2, 0, relu=False)
+                else:
+                    idn = cur
+                cur = self._conv_bn(tape, a1, p + ".conv2", p + ".bn2", 1, 1, residual=idn)
+            f[li + 1] = cur
+        xcur = f[5]
+        skips = [f[4], f[3], f[2], f[1], None]
+        for i in range(5):
+            p = f"decoder.blocks.{i}"
+            cat = ops.upsample_concat(xcur, skips[i])
+            tape.append(("cat", xcur.shape[-1]))
+            a1 = self._conv_bn(tape, cat, p + ".conv1.0", p + ".conv1.1", 1, 1)
+            xcur = self._conv_bn(tape, a1, p + ".conv2.0", p + ".conv2.1", 1, 1)
+        hw = self.params["segmentation_head.0.weight"]
+        logits = torch.empty((N, self.classes, T, T), dtype=torch.float32, device=self.device)
+        ops.head(xcur, ops.pack_conv_weight(hw, 0), self.params["segmentation_head.0.bias"], logits_nchw=logits)
+        tape.append(("head", xcur))
+        return logits, tape
+
+    # ---- backward pieces -------------------------------------------------------------------------------
+    def _dgrad(self, gy: torch.Tensor, wname: str, x_shape, stride: int, pad: int,
+               addend: Optional[torch.Tensor] = None) -> torch.Tensor:
+        w = self.params[wname]
+        C_out, C_in, R, S = w.shape
+        N, H, W, Cx = x_shape
+        if (self.precision == "bf16" and self.dgrad_tc and R == 3 and S == 3 and stride == 1 and pad == 1 and
+                C_in % 16 == 0 and C_out % 16 == 0 and Cx == C_in):
+            # the data gradient of a stride-1 conv is a stride-1 conv of gy with the flipped, transposed weights
+            wp = ops.pack_conv_weight(w, 3)
+            return ops.conv2d(gy, wp, self._ones, self._zeros, N=N, H=H, W=W, C_in=C_out, C_x=C_out, C_out=C_in, R=3,
+                              S=3, stride=1, pad=1, relu=False, residual=addend, tag="dgrad." + wname)
+        return ops.conv2d_dgrad_direct(gy, w, x_shape, stride, pad, addend=addend)
+
+    def _wgrad(self, x: torch.Tensor, gy: torch.Tensor, wname: str, stride: int, pad: int, want_bias: bool = False):
+        w = self.params[wname]
+        C_out, C_in, R, S = w.shape
+        if (self.precision == "bf16" and self.wgrad_tc and not want_bias and ops.wgrad_tc_supported(x, gy, w.shape, stride, pad)):
+            return ops.conv2d_wgrad_tc(x, gy, w.shape), None
+        return ops.conv2d_wgrad_direct(x, gy, w.shape, stride, pad, want_bias=want_bias)
+
+    def _conv_bn_bwd(self, e: _ConvBN, g: torch.Tensor, grads: Dict[str, torch.Tensor], want_gz: bool = False,
+                     need_dx: bool = True, addend: Optional[torch.Tensor] = None):
+        """g = dL/d(a) -> (dL/d(x) (+ addend), gz); fills grads for the conv weight and the BN affine pair."""
+        gy, gz, dgamma, dbeta = ops.bn_train_bwd(g, e.a if e.relu else None, e.y, e.mean, e.invstd, e.scale,
+                                                 want_gz=want_gz)
+        grads[e.bn + ".weight"], grads[e.bn + ".bias"] = dgamma, dbeta
+        grads[e.conv + ".weight"], _ = self._wgrad(e.x, gy, e.conv + ".weight", e.stride, e.pad)
+        gx = self._dgrad(gy, e.conv + ".weight", e.x.shape, e.stride, e.pad, addend=addend) if need_dx else None
+        return gx, gz
+
+    def backward(self, tape: List, grad_logits: torch.Tensor) -> Dict[str, torch.Tensor]:
+        grads: Dict[str, torch.Tensor] = {}
+        it = list(tape)
+        kind, d4 = it.pop()
+        assert kind == "head"
+        hw = self.params["segmentation_head.0.weight"]
+        K = hw.shape[0]
+        g = ops.nchw_to_nhwc(grad_logits, K, self.act_dtype)
+        dw, db = ops.conv2d_wgrad_direct(d4, g, hw.shape, 1, 1, want_bias=True)
+        grads["segmentation_head.0.weight"], grads["segmentation_head.0.bias"] = dw, db
+        g = ops.conv2d_dgrad_direct(g, hw, d4.shape, 1, 1)
+        # decoder, last block first
+        g_skip: Dict[int, torch.Tensor] = {}
+        for i in reversed(range(5)):
+            e2, e1 = it.pop(), it.pop()
+            kind, cx = it.pop()
+            assert kind == "cat"
+            g, _ = self._conv_bn_bwd(e2, g, grads)
+            g_cat, _ = self._conv_bn_bwd(e1, g, grads)
+            g, gs = ops.upsample_concat_bwd(g_cat, cx)
+            if gs is not None:
+                g_skip[4 - i] = gs          # skips = [f4, f3, f2, f1, None]
+        # encoder, deepest block first; g = dL/d(f5)
+        for li in reversed(range(1, 5)):
+            nblk = RESNET34_LAYERS[li - 1]
+            for b in reversed(range(nblk)):
+                strided = b == 0 and li > 1
+                e2 = it.pop()
+                ed = it.pop() if strided else None
+                e1 = it.pop()
+                # out = relu(bn2(conv2(a1)) + idn): gz is the gradient of the sum, shared by both branches
+                g_a1, gz = self._conv_bn_bwd(e2, g, grads, want_gz=True)
+                if strided:
+                    # the block input is f_li (a decoder skip for li >= 2): merge that gradient here
+                    gx, _ = self._conv_bn_bwd(e1, g_a1, grads, addend=g_skip.get(li))
+                    g, _ = self._conv_bn_bwd(ed, gz, grads, addend=gx)
+                else:
+                    g, _ = self._conv_bn_bwd(e1, g_a1, grads, addend=gz)
+        kind, f1 = it.pop()
+        assert kind == "pool"
+        g = ops.maxpool3x3s2_bwd(f1, g, addend=g_skip.get(1))
+        e0 = it.pop()
+        self._conv_bn_bwd(e0, g, grads, need_dx=False)
+        assert not it
+        return grads
+
+
+class _UnetTrainFn(torch.autograd.Function):
+    """autograd node of the whole train-mode Unet: forward / backward run in the CUDA library."""
+
+    @staticmethod
+    def forward(ctx, engine: UnetTrainEngine, x: torch.Tensor, *params):
+        logits, tape = engine.forward(x)
+        ctx.engine, ctx.tape = engine, tape
+        return logits
+
+    @staticmethod
+    def backward(ctx, grad_logits):
+        eng = ctx.engine
+        grads = eng.backward(ctx.tape, grad_logits.contiguous().float())
+        ctx.tape = None
+        return (None, None) + tuple(grads[n] for n in eng.param_names)
+
+
+def unet_train_forward(engine: UnetTrainEngine, x: torch.Tensor) -> torch.Tensor:
+    return _UnetTrainFn.apply(engine, x, *[engine.params[n] for n in engine.param_names])

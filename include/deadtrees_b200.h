@@ -183,6 +183,61 @@ int dt_softmax_nchw(const float* logits, int N, int K, int H, int W, float* prob
 int dt_prob_loss_partials(const float* probs, const void* target, int target_is_float, int N, int K, int H, int W,
                           float gamma, double* sums, dt_stream_t stream);
 
+/* ---- S1 / K13: training step ----------------------------------------------------------------------
+ * Autograd of smp.Unet(resnet34) in train mode as SemSegment.training_step drives it
+ * (deadtrees/network/segmodel.py:210-229).  Activations / gradients are NHWC in `dtype`
+ * (DT_BF16 or DT_F32); M = N*H*W pixels; per-channel vectors are float[C].
+ *
+ * dt_bn_train_stats: nn.BatchNorm2d in train mode on the raw conv output y (M, C): batch mean / biased variance
+ *   -> scale = gamma*invstd, shift = beta - mean*scale, saved (mean, invstd); running stats updated with
+ *   `momentum` and the unbiased variance (running_* may be NULL).  workspace: float[2 * dt_reduce_blocks() * C].
+ * dt_bn_apply: out = [relu]( y*scale + shift (+ residual) ).
+ * dt_bn_train_bwd: gz = g * [a > 0] (a == NULL: no ReLU); dbeta = sum gz; dgamma = sum gz*yhat;
+ *   gy = scale * (gz - dbeta/M - yhat*dgamma/M); optional gz_out (gradient of the identity branch of a
+ *   BasicBlock).  workspace: float[2 * dt_reduce_blocks() * C + 2 * C].
+ * dt_reduce_blocks: number of partial-sum rows the two calls above use (or DT_ERR_BAD_SHAPE). */
+int dt_reduce_blocks(int64_t M, int C, int dtype);
+int dt_bn_train_stats(const void* y, int64_t M, int C, int dtype, const float* gamma, const float* beta, float eps,
+                      float momentum, float* running_mean, float* running_var, float* scale, float* shift, float* mean,
+                      float* invstd, float* workspace, dt_stream_t stream);
+int dt_bn_apply(const void* y, int64_t M, int C, int dtype, const float* scale, const float* shift, const void* residual,
+                int relu, void* out, dt_stream_t stream);
+int dt_bn_train_bwd(const void* g, const void* a, const void* y, int64_t M, int C, int dtype, const float* mean,
+                    const float* invstd, const float* scale, float* dgamma, float* dbeta, void* gy, void* gz_out,
+                    float* workspace, dt_stream_t stream);
+/* out = a + b over n elements (gradient merges) */
+int dt_add(const void* a, const void* b, int64_t n, int dtype, void* out, dt_stream_t stream);
+/* MaxPool2d(3, 2, 1) backward: gradient goes to the FIRST maximum of each window (ATen semantics);
+ * x (N, H, W, C) is the pool input, gout (N, Ho, Wo, C); gx = addend (may be NULL) + pooled gradient. */
+int dt_maxpool3x3s2_bwd(const void* x, const void* gout, const void* addend, int N, int H, int W, int C, int dtype,
+                        void* gx, dt_stream_t stream);
+/* cat([nearest_x2(x_low), skip], C) materialised for the training path, and its backward
+ * (g_x_low = 2x2 block sums of g_cat[..., :Cx]; g_skip = g_cat[..., Cx:]).  H, W: full resolution. */
+int dt_upsample_concat(const void* x_low, const void* skip, int N, int H, int W, int Cx, int Cs, int dtype, void* out,
+                       dt_stream_t stream);
+int dt_upsample_concat_bwd(const void* g_cat, int N, int H, int W, int Cx, int Cs, int dtype, void* g_x_low, void* g_skip,
+                           dt_stream_t stream);
+/* (N, K, H, W) fp32 -> (N, H, W, Kp) `dtype`, channels >= K zero (gradient of the logits into the head backward) */
+int dt_nchw_to_nhwc(const float* x, int N, int K, int H, int W, int Kp, int dtype, void* out, dt_stream_t stream);
+/* fp32 OIHW master weights -> kernel layouts.  mode 0: float [tap][C_in_p][C_out]; 1: bf16 [C_out][Kpad]
+ * (dt_conv2d_fwd); 2: bf16 stem packing [C_out][256]; 3: bf16 [C_in][Kpad], k = (R*S-1-tap)*C_out + co — the
+ * weights with which dt_conv2d_fwd computes the data gradient of a stride-1 convolution. */
+int dt_pack_conv_weight(const float* w_oihw, int C_out, int C_in, int R, int S, int mode, int C_in_p, int Kpad, void* out,
+                        dt_stream_t stream);
+/* Generic (CUDA-core) data / weight gradients of conv2d, any stride: fp32 check mode and the layer shapes the
+ * tcgen05 kernels do not cover.  x / gx: (N, H, W, C_x) with C_in <= C_x real channels; gy: (N, Ho, Wo, C_out);
+ * weights and dw: fp32 OIHW (C_out, C_in, R, S); gx = addend (may be NULL) + dgrad; dbias (may be NULL): float[C_out]. */
+int dt_conv2d_dgrad_direct(const void* gy, const float* w_oihw, const void* addend, int N, int H, int W, int C_in, int C_x,
+                           int C_out, int R, int S, int stride, int pad, int dtype, void* gx, dt_stream_t stream);
+int dt_conv2d_wgrad_direct(const void* x, const void* gy, int N, int H, int W, int C_in, int C_x, int C_out, int R, int S,
+                           int stride, int pad, int dtype, float* dw_oihw, float* dbias, dt_stream_t stream);
+
+/* Weight gradient of a 3x3 / stride-1 / pad-1 convolution on the tensor cores (bf16 NHWC x (N, H, W, C_in) and
+ * gy (N, H, W, C_out), fp32 accumulation in TMEM, dw fp32 OIHW overwritten).  Needs W % 8 == 0, H % 16 == 0 (or H == 8
+ * with N even) and channel counts that are multiples of 8; returns DT_ERR_UNSUPPORTED otherwise (use the direct kernel). */
+int dt_conv2d_wgrad_tc(const void* x, const void* gy, int N, int H, int W, int C_in, int C_out, float* dw_oihw,
+                       dt_stream_t stream);
+
 /* ---- O1: optimizer ------------------------------------------------------------------------------
  * torch.optim.Adam step (segmodel.py:420-425 defaults) with the Lightning global-norm clip
  * (configs/trainer/default.yaml:18) folded in: g *= min(1, max_norm / (norm + 1e-6)).
