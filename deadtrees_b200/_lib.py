@@ -62,7 +62,7 @@ _SIGNATURES = {
     "dt_upsample_concat_bwd": ([_p, _i, _i, _i, _i, _i, _i, _p, _p, _p], C.c_int),
     "dt_nchw_to_nhwc": ([_p, _i, _i, _i, _i, _i, _i, _p, _p], C.c_int),
     "dt_pack_conv_weight": ([_p, _i, _i, _i, _i, _i, _i, _i, _p, _p], C.c_int),
-    "dt_conv2d_dgrad_direct": ([_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p], C.c_int),
+    "dt_conv2d_dgrad_direct": ([_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p], C.c_int),
     "dt_conv2d_wgrad_direct": ([_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p], C.c_int),
     "dt_conv2d_wgrad_tc": ([_p, _p, _i, _i, _i, _i, _i, _p, _p], C.c_int),
     "dt_sumsq": ([_p, _i64, _p, _p], C.c_int),

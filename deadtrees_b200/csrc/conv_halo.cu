@@ -66,8 +66,10 @@ __device__ __forceinline__ Geo geo(const HaloParams& p, int tile) {
   Geo g;
   g.n_tile = tile % p.n_tiles;
   int m = tile / p.n_tiles;
-  g.cls = m / p.tiles_per_class;
-  m -= g.cls * p.tiles_per_class;
+  // parity layers: the four classes of one region are consecutive tiles (they run on neighbouring CTAs at the same
+  // time and share the x patch and the four skip planes in L2)
+  g.cls = p.parity ? (m & 3) : 0;
+  if (p.parity) m >>= 2;
   g.w0 = (m % p.tiles_w) * TW; m /= p.tiles_w;
   g.h0 = (m % p.tiles_h) * TH;
   g.n = m / p.tiles_h;
@@ -173,7 +175,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       int sa = 0, sb = 0, acc = 0;
       uint32_t pa = 0, pb = 0, pacc = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int cls = p.parity ? (tile / p.n_tiles) / p.tiles_per_class : 0;
+        const int cls = p.parity ? ((tile / p.n_tiles) & 3) : 0;
         mbar_wait(&tmem_empty[acc], pacc ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;

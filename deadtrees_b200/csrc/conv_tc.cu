@@ -65,9 +65,9 @@ __device__ __forceinline__ TileGeo tile_geo(const TcParams& p, int tile) {
   g.n_tile = tile % p.n_tiles;
   int m_tile = tile / p.n_tiles;
   int cls = 0;
-  if (p.parity) {
-    cls = m_tile / p.m_tiles_per_class;
-    m_tile -= cls * p.m_tiles_per_class;
+  if (p.parity) {   // the four classes of one region are consecutive tiles (shared operands stay in L2)
+    cls = m_tile & 3;
+    m_tile >>= 2;
   }
   g.a = cls >> 1;
   g.b = cls & 1;
@@ -525,6 +525,7 @@ extern "C" int dt_conv2d_fwd(const dt_conv_desc* d, const void* x, const void* s
   DT_REQUIRE(M < (1LL << 31) - BM, DT_ERR_BAD_SHAPE, "dt_conv2d_fwd: too many output pixels");
   int BN = d->C_out;
   if (BN > 128) BN = (d->C_out % 256 == 0 && M >= static_cast<int64_t>(dt_num_sms()) * 2 * BM) ? 256 : 128;
+  while (BN > 16 && d->C_out % BN != 0) BN >>= 1;   // e.g. 192 output channels (a data gradient): 3 tiles of 64
   DT_REQUIRE(d->C_out % BN == 0 && (BN == 16 || BN == 32 || BN == 64 || BN == 128 || BN == 256), DT_ERR_BAD_SHAPE,
              "dt_conv2d_fwd: unsupported C_out %d", d->C_out);
 

@@ -226,6 +226,88 @@ __global__ void stitch_blend_kernel(const LT* __restrict__ logits, int T, int st
   }
 }
 
+// Vectorised form for bf16 logits with T, step multiples of 8: one thread = 8 consecutive mosaic pixels (the same
+// covering tiles for all eight), 16-byte loads of 8 pixels x K logits per covering tile, one 8-byte mask store.
+// Per-pixel arithmetic (order of the fp32 operations) is identical to stitch_blend_kernel.
+template <int K>
+__global__ void stitch_blend_v8_kernel(const __nv_bfloat16* __restrict__ logits, int T, int step, int gy, int gx,
+                                       int ty_base, const float* __restrict__ win, uint8_t* __restrict__ mask,
+                                       float* __restrict__ blended, int H, int W, int row0, int nrows) {
+  const int W8 = (W + 7) >> 3;
+  const int64_t total = static_cast<int64_t>(nrows) * W8;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int x0 = static_cast<int>(i % W8) << 3;
+    const int y = row0 + static_cast<int>(i / W8);
+    int ty0 = (y - T + step) / step;
+    if (y - T + 1 <= 0) ty0 = 0;
+    int tx0 = (x0 - T + step) / step;
+    if (x0 - T + 1 <= 0) tx0 = 0;
+    const int ty1 = min(gy - 1, y / step), tx1 = min(gx - 1, x0 / step);
+    float acc[8][K], wsum[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      wsum[j] = 0.f;
+#pragma unroll
+      for (int k = 0; k < K; ++k) acc[j][k] = 0.f;
+    }
+    for (int ty = ty0; ty <= ty1; ++ty) {
+      const int ly = y - ty * step;
+      const float wy = __ldg(win + ly);
+      for (int tx = tx0; tx <= tx1; ++tx) {
+        const int lx = x0 - tx * step;
+        const float4 wa = __ldg(reinterpret_cast<const float4*>(win + lx));
+        const float4 wb = __ldg(reinterpret_cast<const float4*>(win + lx) + 1);
+        const float wx[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+        const uint4* src = reinterpret_cast<const uint4*>(
+            logits + ((static_cast<int64_t>(ty - ty_base) * gx + tx) * T * T + static_cast<int64_t>(ly) * T + lx) * K);
+        uint32_t raw[4 * K];   // 8 pixels x K bf16 = K uint4
+#pragma unroll
+        for (int q = 0; q < K; ++q) {
+          const uint4 v = ld_nc_v4(src + q);
+          raw[4 * q] = v.x; raw[4 * q + 1] = v.y; raw[4 * q + 2] = v.z; raw[4 * q + 3] = v.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float w = __fmul_rn(wy, wx[j]);
+#pragma unroll
+          for (int k = 0; k < K; ++k) {
+            const int e = j * K + k;
+            const uint32_t word = raw[e >> 1];
+            const float z = (e & 1) ? __uint_as_float(word & 0xffff0000u) : __uint_as_float(word << 16);
+            acc[j][k] = __fadd_rn(acc[j][k], __fmul_rn(z, w));
+          }
+          wsum[j] = __fadd_rn(wsum[j], w);
+        }
+      }
+    }
+    uint8_t best[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int b = 0;
+      float bv = __fdiv_rn(acc[j][0], wsum[j]);
+      const bool live = x0 + j < W;
+      if (blended && live) blended[(static_cast<int64_t>(y) * W + x0 + j) * K] = bv;
+#pragma unroll
+      for (int k = 1; k < K; ++k) {
+        const float v = __fdiv_rn(acc[j][k], wsum[j]);
+        if (blended && live) blended[(static_cast<int64_t>(y) * W + x0 + j) * K + k] = v;
+        if (v > bv) { bv = v; b = k; }
+      }
+      best[j] = static_cast<uint8_t>(b);
+    }
+    uint8_t* dst = mask + static_cast<int64_t>(y) * W + x0;
+    if (x0 + 8 <= W && (reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
+      uint2 pk;
+      pk.x = best[0] | (best[1] << 8) | (best[2] << 16) | (static_cast<uint32_t>(best[3]) << 24);
+      pk.y = best[4] | (best[5] << 8) | (best[6] << 16) | (static_cast<uint32_t>(best[7]) << 24);
+      *reinterpret_cast<uint2*>(dst) = pk;
+    } else {
+      for (int j = 0; j < 8 && x0 + j < W; ++j) dst[j] = best[j];
+    }
+  }
+}
+
 // (N, C_src, H, W) fp32 planes -> (N, H, W, 4) NHWC, first C channels kept (RGB slice), rest zero.
 template <bool OUT_BF16>
 __global__ void pack_nchw_kernel(const float* __restrict__ x, int N, int C_src, int C, int64_t HW,
@@ -394,7 +476,17 @@ int dt_stitch_blend_argmax(const void* logits, int dtype, int K, int T, int over
     case 3: DT_SB(LT, 3); break;       \
     default: DT_SB(LT, 4); break;      \
   }
-  if (dtype == DT_BF16) { DT_SBK(__nv_bfloat16) } else if (dtype == DT_F32) { DT_SBK(float) } else {
+  if (dtype == DT_BF16 && T % 8 == 0 && step % 8 == 0 && reinterpret_cast<uintptr_t>(logits) % 16 == 0 &&
+      reinterpret_cast<uintptr_t>(win) % 16 == 0) {
+    const int64_t total8 = static_cast<int64_t>(nrows) * ((W + 7) / 8);
+    const __nv_bfloat16* lg = static_cast<const __nv_bfloat16*>(logits);
+    switch (K) {
+      case 1: stitch_blend_v8_kernel<1><<<grid_for(total8), kThreads, 0, s>>>(lg, T, step, gy, gx, ty_base, win, mosaic_mask, blended, H, W, row0, nrows); break;
+      case 2: stitch_blend_v8_kernel<2><<<grid_for(total8), kThreads, 0, s>>>(lg, T, step, gy, gx, ty_base, win, mosaic_mask, blended, H, W, row0, nrows); break;
+      case 3: stitch_blend_v8_kernel<3><<<grid_for(total8), kThreads, 0, s>>>(lg, T, step, gy, gx, ty_base, win, mosaic_mask, blended, H, W, row0, nrows); break;
+      default: stitch_blend_v8_kernel<4><<<grid_for(total8), kThreads, 0, s>>>(lg, T, step, gy, gx, ty_base, win, mosaic_mask, blended, H, W, row0, nrows); break;
+    }
+  } else if (dtype == DT_BF16) { DT_SBK(__nv_bfloat16) } else if (dtype == DT_F32) { DT_SBK(float) } else {
     DT_REQUIRE(false, DT_ERR_BAD_SHAPE, "dt_stitch_blend_argmax: dtype %d", dtype);
   }
 #undef DT_SBK

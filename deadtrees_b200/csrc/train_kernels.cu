@@ -372,7 +372,7 @@ struct BwdGeo {
 // gx[n,h,w,ci] = addend + sum_{r,s,co} gy[n,(h+pad-r)/st,(w+pad-s)/st,co] * w[co,ci,r,s]   (w: fp32 OIHW master)
 template <typename T>
 __global__ void dgrad_direct_kernel(BwdGeo p, const T* __restrict__ gy, const float* __restrict__ w,
-                                    const T* __restrict__ addend, T* __restrict__ gx) {
+                                    const T* __restrict__ addend, T* __restrict__ gx, int round_w) {
   const int64_t total = static_cast<int64_t>(p.N) * p.H * p.W * p.C_x;
   const int RS = p.R * p.S;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
@@ -396,7 +396,11 @@ __global__ void dgrad_direct_kernel(BwdGeo p, const T* __restrict__ gy, const fl
           if (wo >= p.Wo) continue;
           const T* gp = gy + ((static_cast<int64_t>(n) * p.Ho + ho) * p.Wo + wo) * p.C_out;
           const float* wp = w + static_cast<int64_t>(ci) * RS + fr * p.S + fs;
-          for (int co = 0; co < p.C_out; ++co) acc = fmaf(to_f<T>(gp[co]), wp[static_cast<int64_t>(co) * p.C_in * RS], acc);
+          // bf16 mode: weights rounded to bf16 like the tensor-core operands (fp32 accumulation either way)
+          for (int co = 0; co < p.C_out; ++co) {
+            const float wv = wp[static_cast<int64_t>(co) * p.C_in * RS];
+            acc = fmaf(to_f<T>(gp[co]), round_w ? __bfloat162float(__float2bfloat16_rn(wv)) : wv, acc);
+          }
         }
       }
     }
@@ -657,7 +661,8 @@ int dt_pack_conv_weight(const float* w_oihw, int C_out, int C_in, int R, int S, 
 }
 
 int dt_conv2d_dgrad_direct(const void* gy, const float* w_oihw, const void* addend, int N, int H, int W, int C_in, int C_x,
-                           int C_out, int R, int S, int stride, int pad, int dtype, void* gx, dt_stream_t stream) {
+                           int C_out, int R, int S, int stride, int pad, int dtype, int round_weights, void* gx,
+                           dt_stream_t stream) {
   DT_ARCH_GUARD();
   DT_REQUIRE(N > 0 && H > 0 && W > 0 && C_in > 0 && C_x >= C_in && C_out > 0 && R > 0 && S > 0 && stride > 0 && pad >= 0 &&
                  (dtype == DT_F32 || dtype == DT_BF16),
@@ -666,8 +671,8 @@ int dt_conv2d_dgrad_direct(const void* gy, const float* w_oihw, const void* adde
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int64_t total = static_cast<int64_t>(N) * H * W * C_x;
   DT_DTYPE_SWITCH(dtype,
-      (dgrad_direct_kernel<float><<<grid_for(total, 16), kThreads, 0, s>>>(p, static_cast<const float*>(gy), w_oihw, static_cast<const float*>(addend), static_cast<float*>(gx))),
-      (dgrad_direct_kernel<__nv_bfloat16><<<grid_for(total, 16), kThreads, 0, s>>>(p, static_cast<const __nv_bfloat16*>(gy), w_oihw, static_cast<const __nv_bfloat16*>(addend), static_cast<__nv_bfloat16*>(gx))));
+      (dgrad_direct_kernel<float><<<grid_for(total, 16), kThreads, 0, s>>>(p, static_cast<const float*>(gy), w_oihw, static_cast<const float*>(addend), static_cast<float*>(gx), 0)),
+      (dgrad_direct_kernel<__nv_bfloat16><<<grid_for(total, 16), kThreads, 0, s>>>(p, static_cast<const __nv_bfloat16*>(gy), w_oihw, static_cast<const __nv_bfloat16*>(addend), static_cast<__nv_bfloat16*>(gx), round_weights)));
   DT_LAUNCH_CHECK();
   return DT_OK;
 }

@@ -397,13 +397,13 @@ def pack_conv_weight(w: torch.Tensor, mode: int, out: Optional[torch.Tensor] = N
 
 
 def conv2d_dgrad_direct(gy: torch.Tensor, w: torch.Tensor, x_shape, stride: int, pad: int,
-                        addend: Optional[torch.Tensor] = None) -> torch.Tensor:
+                        addend: Optional[torch.Tensor] = None, round_weights: bool = False) -> torch.Tensor:
     """gy (N, Ho, Wo, C_out), w fp32 OIHW -> gx of shape x_shape = (N, H, W, C_x)."""
     N, H, W, Cx = x_shape
     C_out, C_in, R, S = w.shape
     gx = torch.empty(tuple(x_shape), dtype=gy.dtype, device=gy.device)
     check(load().dt_conv2d_dgrad_direct(gy.data_ptr(), w.data_ptr(), ptr(addend), N, H, W, C_in, Cx, C_out, R, S, stride,
-                                        pad, _dt(gy), gx.data_ptr(), stream_ptr()))
+                                        pad, _dt(gy), int(round_weights), gx.data_ptr(), stream_ptr()))
     return gx
 
 

@@ -47,6 +47,13 @@ class UnetTrainEngine:
         self.device = dev
         self._ones = torch.ones(1024, dtype=torch.float32, device=dev)
         self._zeros = torch.zeros(1024, dtype=torch.float32, device=dev)
+        # when a list, every kernel-level operation appends (kind, name, inputs..., outputs...) so tests can check
+        # each op of the real pipeline against the oracle on the SAME inputs (layer-wise, teacher-forced parity)
+        self.trace: Optional[List] = None
+
+    def _rec(self, kind: str, name: str, **tensors) -> None:
+        if self.trace is not None:
+            self.trace.append((kind, name, tensors))
 
     # ---- forward pieces --------------------------------------------------------------------------------
     def _conv_raw(self, x: torch.Tensor, wname: str, stride: int, pad: int) -> torch.Tensor:
@@ -72,6 +79,8 @@ class UnetTrainEngine:
         if nbt is not None:
             nbt += 1
         a = ops.bn_apply(y, scale, shift, residual=residual, relu=relu)
+        self._rec("conv_bn_fwd", conv, x=x, y=y, a=a, residual=residual, mean=mean, invstd=invstd, scale=scale, shift=shift,
+                  relu=relu, stride=stride, pad=pad)
         tape.append(_ConvBN(conv=conv, bn=bn, x=x, y=y, a=a, relu=relu, stride=stride, pad=pad, mean=mean,
                             invstd=invstd, scale=scale, residual=residual))
         return a
@@ -85,6 +94,7 @@ class UnetTrainEngine:
         x4 = ops.pack_input_nchw(x_nchw, self.in_channels, self.act_dtype)
         f = {1: self._conv_bn(tape, x4, "encoder.conv1", "encoder.bn1", 2, 3)}
         pool = ops.maxpool3x3s2(f[1])
+        self._rec("maxpool_fwd", "pool", x=f[1], y=pool)
         tape.append(("pool", f[1]))
         cur = pool
         for li, (planes, nblk) in enumerate(zip(RESNET34_PLANES, RESNET34_LAYERS), start=1):
@@ -103,12 +113,14 @@ class UnetTrainEngine:
         for i in range(5):
             p = f"decoder.blocks.{i}"
             cat = ops.upsample_concat(xcur, skips[i])
+            self._rec("upcat_fwd", p, x=xcur, skip=skips[i], y=cat)
             tape.append(("cat", xcur.shape[-1]))
             a1 = self._conv_bn(tape, cat, p + ".conv1.0", p + ".conv1.1", 1, 1)
             xcur = self._conv_bn(tape, a1, p + ".conv2.0", p + ".conv2.1", 1, 1)
         hw = self.params["segmentation_head.0.weight"]
         logits = torch.empty((N, self.classes, T, T), dtype=torch.float32, device=self.device)
         ops.head(xcur, ops.pack_conv_weight(hw, 0), self.params["segmentation_head.0.bias"], logits_nchw=logits)
+        self._rec("head_fwd", "segmentation_head.0", x=xcur, y=logits)
         tape.append(("head", xcur))
         return logits, tape
 
@@ -122,16 +134,23 @@ class UnetTrainEngine:
                 C_in % 16 == 0 and C_out % 16 == 0 and Cx == C_in):
             # the data gradient of a stride-1 conv is a stride-1 conv of gy with the flipped, transposed weights
             wp = ops.pack_conv_weight(w, 3)
-            return ops.conv2d(gy, wp, self._ones, self._zeros, N=N, H=H, W=W, C_in=C_out, C_x=C_out, C_out=C_in, R=3,
-                              S=3, stride=1, pad=1, relu=False, residual=addend, tag="dgrad." + wname)
-        return ops.conv2d_dgrad_direct(gy, w, x_shape, stride, pad, addend=addend)
+            gx = ops.conv2d(gy, wp, self._ones, self._zeros, N=N, H=H, W=W, C_in=C_out, C_x=C_out, C_out=C_in, R=3,
+                            S=3, stride=1, pad=1, relu=False, residual=addend, tag="dgrad." + wname)
+        else:
+            gx = ops.conv2d_dgrad_direct(gy, w, x_shape, stride, pad, addend=addend,
+                                         round_weights=self.precision == "bf16")
+        self._rec("dgrad", wname, gy=gy, addend=addend, gx=gx, stride=stride, pad=pad)
+        return gx
 
     def _wgrad(self, x: torch.Tensor, gy: torch.Tensor, wname: str, stride: int, pad: int, want_bias: bool = False):
         w = self.params[wname]
         C_out, C_in, R, S = w.shape
         if (self.precision == "bf16" and self.wgrad_tc and not want_bias and ops.wgrad_tc_supported(x, gy, w.shape, stride, pad)):
-            return ops.conv2d_wgrad_tc(x, gy, w.shape), None
-        return ops.conv2d_wgrad_direct(x, gy, w.shape, stride, pad, want_bias=want_bias)
+            dw, db = ops.conv2d_wgrad_tc(x, gy, w.shape), None
+        else:
+            dw, db = ops.conv2d_wgrad_direct(x, gy, w.shape, stride, pad, want_bias=want_bias)
+        self._rec("wgrad", wname, x=x, gy=gy, dw=dw, db=db, stride=stride, pad=pad)
+        return dw, db
 
     def _conv_bn_bwd(self, e: _ConvBN, g: torch.Tensor, grads: Dict[str, torch.Tensor], want_gz: bool = False,
                      need_dx: bool = True, addend: Optional[torch.Tensor] = None):
@@ -139,6 +158,8 @@ class UnetTrainEngine:
         gy, gz, dgamma, dbeta = ops.bn_train_bwd(g, e.a if e.relu else None, e.y, e.mean, e.invstd, e.scale,
                                                  want_gz=want_gz)
         grads[e.bn + ".weight"], grads[e.bn + ".bias"] = dgamma, dbeta
+        self._rec("bn_bwd", e.bn, g=g, a=e.a if e.relu else None, y=e.y, mean=e.mean, invstd=e.invstd, scale=e.scale,
+                  gy=gy, gz=gz, dgamma=dgamma, dbeta=dbeta)
         grads[e.conv + ".weight"], _ = self._wgrad(e.x, gy, e.conv + ".weight", e.stride, e.pad)
         gx = self._dgrad(gy, e.conv + ".weight", e.x.shape, e.stride, e.pad, addend=addend) if need_dx else None
         return gx, gz
@@ -151,9 +172,11 @@ class UnetTrainEngine:
         hw = self.params["segmentation_head.0.weight"]
         K = hw.shape[0]
         g = ops.nchw_to_nhwc(grad_logits, K, self.act_dtype)
-        dw, db = ops.conv2d_wgrad_direct(d4, g, hw.shape, 1, 1, want_bias=True)
+        dw, db = self._wgrad(d4, g, "segmentation_head.0.weight", 1, 1, want_bias=True)
         grads["segmentation_head.0.weight"], grads["segmentation_head.0.bias"] = dw, db
-        g = ops.conv2d_dgrad_direct(g, hw, d4.shape, 1, 1)
+        gh = g
+        g = ops.conv2d_dgrad_direct(gh, hw, d4.shape, 1, 1)          # the head keeps fp32 weights
+        self._rec("dgrad", "segmentation_head.0.weight", gy=gh, addend=None, gx=g, stride=1, pad=1, fp32_weights=True)
         # decoder, last block first
         g_skip: Dict[int, torch.Tensor] = {}
         for i in reversed(range(5)):
@@ -163,6 +186,7 @@ class UnetTrainEngine:
             g, _ = self._conv_bn_bwd(e2, g, grads)
             g_cat, _ = self._conv_bn_bwd(e1, g, grads)
             g, gs = ops.upsample_concat_bwd(g_cat, cx)
+            self._rec("upcat_bwd", f"decoder.blocks.{i}", g_cat=g_cat, g_low=g, g_skip=gs, cx=cx)
             if gs is not None:
                 g_skip[4 - i] = gs          # skips = [f4, f3, f2, f1, None]
         # encoder, deepest block first; g = dL/d(f5)
@@ -183,7 +207,9 @@ class UnetTrainEngine:
                     g, _ = self._conv_bn_bwd(e1, g_a1, grads, addend=gz)
         kind, f1 = it.pop()
         assert kind == "pool"
-        g = ops.maxpool3x3s2_bwd(f1, g, addend=g_skip.get(1))
+        gp = g
+        g = ops.maxpool3x3s2_bwd(f1, gp, addend=g_skip.get(1))
+        self._rec("maxpool_bwd", "pool", x=f1, gout=gp, addend=g_skip.get(1), gx=g)
         e0 = it.pop()
         self._conv_bn_bwd(e0, g, grads, need_dx=False)
         assert not it

@@ -226,9 +226,11 @@ int dt_pack_conv_weight(const float* w_oihw, int C_out, int C_in, int R, int S, 
                         dt_stream_t stream);
 /* Generic (CUDA-core) data / weight gradients of conv2d, any stride: fp32 check mode and the layer shapes the
  * tcgen05 kernels do not cover.  x / gx: (N, H, W, C_x) with C_in <= C_x real channels; gy: (N, Ho, Wo, C_out);
- * weights and dw: fp32 OIHW (C_out, C_in, R, S); gx = addend (may be NULL) + dgrad; dbias (may be NULL): float[C_out]. */
+ * weights and dw: fp32 OIHW (C_out, C_in, R, S); gx = addend (may be NULL) + dgrad; dbias (may be NULL): float[C_out];
+ * round_weights (bf16 tensors only): use the weights rounded to bf16, as the tensor-core kernels do. */
 int dt_conv2d_dgrad_direct(const void* gy, const float* w_oihw, const void* addend, int N, int H, int W, int C_in, int C_x,
-                           int C_out, int R, int S, int stride, int pad, int dtype, void* gx, dt_stream_t stream);
+                           int C_out, int R, int S, int stride, int pad, int dtype, int round_weights, void* gx,
+                           dt_stream_t stream);
 int dt_conv2d_wgrad_direct(const void* x, const void* gy, int N, int H, int W, int C_in, int C_x, int C_out, int R, int S,
                            int stride, int pad, int dtype, float* dw_oihw, float* dbias, dt_stream_t stream);
 

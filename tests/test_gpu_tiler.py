@@ -123,7 +123,8 @@ def test_stitch_mask_bit_exact(H, W, T):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("H,W,T,ov,K", [(300, 203, 64, 16, 3), (256, 256, 64, 32, 2), (100, 90, 32, 0, 3), (64, 64, 64, 8, 3)])
+@pytest.mark.parametrize("H,W,T,ov,K", [(300, 203, 64, 16, 3), (256, 256, 64, 32, 2), (100, 90, 32, 0, 3), (64, 64, 64, 8, 3),
+                                        (128, 100, 64, 12, 4), (96, 83, 32, 8, 1)])
 def test_stitch_blend_bit_exact(dtype, H, W, T, ov, K):
     g = torch.Generator().manual_seed(17)
     gy, gx = overlap_grid(H, W, T, ov)

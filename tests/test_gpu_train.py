@@ -156,67 +156,228 @@ def _batch(n, cin, T, K, seed=11):
     return img, mask
 
 
-@pytest.mark.parametrize("cin,n,T,losses", [(4, 2, 64, ["DICE", "FOCAL"]), (3, 3, 32, ["GDICE", "FOCAL"])])
+def _grad_errors(params, ref_grads):
+    """per-parameter (relative L2 error, cosine similarity) against the oracle gradients."""
+    out = {}
+    for name, p in params:
+        r = ref_grads[name].double().flatten()
+        g = p.grad.detach().cpu().double().flatten()
+        out[name] = (float((g - r).norm() / (r.norm() + 1e-30)), float((g @ r) / (g.norm() * r.norm() + 1e-30)))
+    return out
+
+
+@pytest.mark.parametrize("cin,n,T,losses", [(4, 2, 64, ["DICE", "FOCAL"]), (3, 2, 64, ["GDICE", "FOCAL"])])
 def test_training_step_fp32_matches_autograd(cin, n, T, losses):
+    """fp32 check mode against float64 autograd of the oracle.  Tolerance: torch's own fp32 CPU autograd differs from
+    float64 by up to 1.6e-2 (max-abs / max) on these gradients - ReLU masks flip on pre-activations within rounding
+    of zero and the small per-channel batches of the deep layers amplify it - so the bar is per-tensor relative
+    L2 error < 1e-2 and cosine > 0.9999, with the loss itself within 1e-5."""
     oracle = oracle_model(cin, 3)
-    ref_model = copy.deepcopy(oracle)
+    ref_model = copy.deepcopy(oracle).double()
     img, mask = _batch(n, cin, T, 3)
-    ref = ref_train.train_step(ref_model, img, mask, losses=losses, lr=3e-4, clip=0.5)
+    ref = ref_train.train_step(ref_model, img.double(), mask, losses=losses, lr=0, clip=0)
 
     seg = _semsegment(oracle, cin, "fp32")
-    seg.loss_names = losses
     if "GDICE" in losses:
         from deadtrees_b200.loss.gdl import GeneralizedDiceLoss
         seg.dice_loss = GeneralizedDiceLoss()
     batch = {"main": (img.cuda(), mask.cuda(), None, torch.zeros(n), [{"file": f"t{i}"} for i in range(n)])}
     loss = seg.training_step(batch, 0)
-    assert abs(float(loss) - ref["loss"]) < 1e-4 * max(1.0, abs(ref["loss"]))
+    assert abs(float(loss.detach()) - ref["loss"]) < 1e-5 * max(1.0, abs(ref["loss"]))
     loss.backward()
     torch.cuda.synchronize()
-    worst = 0.0
-    for name, p in seg.model.named_parameters():
-        r = ref["grads"][name]
-        d = (p.grad.cpu() - r).abs().max().item()
-        scale = r.abs().max().item() + 1e-12
-        worst = max(worst, d / scale)
-        assert d / scale < 2e-3, (name, d, scale)
-    print(f"[train fp32] worst relative gradient error {worst:.3e}; loss {float(loss):.6f} vs {ref['loss']:.6f}")
+    errs = _grad_errors(seg.model.named_parameters(), ref["grads"])
+    worst = max(errs.items(), key=lambda kv: kv[1][0])
+    print(f"[train fp32] loss {float(loss.detach()):.7f} vs {ref['loss']:.7f}; worst rel-L2 {worst[1][0]:.3e} cos {worst[1][1]:.6f} ({worst[0]})")
+    for name, (rel, cos) in errs.items():
+        assert rel < 1e-2 and cos > 0.9999, (name, rel, cos)
     # running statistics follow nn.BatchNorm2d
     sd_ref = ref_model.state_dict()
     for name, b in seg.model.named_buffers():
         if name.endswith("running_var") or name.endswith("running_mean"):
-            assert (b.cpu() - sd_ref[name]).abs().max().item() < 1e-4 * (sd_ref[name].abs().max().item() + 1)
+            assert (b.cpu().double() - sd_ref[name]).abs().max().item() < 1e-4 * (sd_ref[name].abs().max().item() + 1)
         if name.endswith("num_batches_tracked"):
             assert int(b) == int(sd_ref[name])
-    # clip 0.5 + Adam
-    opt = FusedAdam(seg.model.parameters(), lr=3e-4, max_grad_norm=0.5)
-    opt.step()
-    torch.cuda.synchronize()
-    for name, p in seg.model.named_parameters():
-        r = dict(ref_model.named_parameters())[name].detach()
-        assert (p.detach().cpu() - r).abs().max().item() < 2e-5, name
 
 
-def test_training_step_bf16_tracks_fp32():
+def test_clip_and_adam_step_matches_torch():
+    """global-norm clip 0.5 + Adam on the gradients of one training step: same update as clip_grad_norm_ + torch.optim.Adam
+    applied to the SAME gradients."""
     cin, n, T = 4, 2, 64
     oracle = oracle_model(cin, 3)
-    ref_model = copy.deepcopy(oracle)
     img, mask = _batch(n, cin, T, 3)
-    ref = ref_train.train_step(ref_model, img, mask, lr=0, clip=0)
+    seg = _semsegment(oracle, cin, "fp32")
+    batch = {"main": (img.cuda(), mask.cuda(), None, torch.zeros(n), [{"file": f"t{i}"} for i in range(n)])}
+    seg.training_step(batch, 0).backward()
+    ref_model = copy.deepcopy(oracle)
+    for (name, p), (_, q) in zip(ref_model.named_parameters(), seg.model.named_parameters()):
+        p.grad = q.grad.detach().cpu().clone()
+    torch.nn.utils.clip_grad_norm_(ref_model.parameters(), 0.5)
+    torch.optim.Adam(ref_model.parameters(), lr=3e-4).step()
+    FusedAdam(seg.model.parameters(), lr=3e-4, max_grad_norm=0.5).step()
+    torch.cuda.synchronize()
+    for (name, p), (_, q) in zip(ref_model.named_parameters(), seg.model.named_parameters()):
+        assert (q.detach().cpu() - p.detach()).abs().max().item() < 1e-6, name
+
+
+def test_training_step_bf16_matches_bf16_arithmetic():
+    """bf16 mode (tcgen05 forward / dgrad / wgrad) against the CPU restatement with the same bf16 storage points
+    (oracle/ref_train.py::train_step_bf16).  Remaining differences are fp32 summation order and the bf16 roundings it
+    flips; the distance of BOTH to the float64 step is much larger (cosine ~0.6 at the stem on this random-init net)."""
+    cin, n, T = 4, 2, 128
+    oracle = oracle_model(cin, 3)
+    img, mask = _batch(n, cin, T, 3)
+    ref = ref_train.train_step_bf16(copy.deepcopy(oracle), img, mask)
     seg = _semsegment(oracle, cin, "bf16")
     batch = {"main": (img.cuda(), mask.cuda(), None, torch.zeros(n), [{"file": f"t{i}"} for i in range(n)])}
     loss = seg.training_step(batch, 0)
     loss.backward()
     torch.cuda.synchronize()
-    print(f"[train bf16] loss {float(loss):.5f} vs fp32 oracle {ref['loss']:.5f}")
-    assert abs(float(loss) - ref["loss"]) < 2e-2
-    low = []
-    for name, p in seg.model.named_parameters():
-        r = ref["grads"][name].flatten().double()
-        gq = p.grad.cpu().flatten().double()
-        cos = float((gq @ r) / (gq.norm() * r.norm() + 1e-30))
-        if r.numel() >= 1024:
-            low.append((cos, name))
-    low.sort()
-    print("[train bf16] lowest gradient cosine similarities:", low[:5])
-    assert low[0][0] > 0.98, low[:5]
+    errs = _grad_errors(seg.model.named_parameters(), ref["grads"])
+    big = {k: v for k, v in errs.items() if ref["grads"][k].numel() >= 1024}
+    worst = min(big.items(), key=lambda kv: kv[1][1])
+    print(f"[train bf16] loss {float(loss.detach()):.5f} vs bf16 oracle {ref['loss']:.5f}; lowest cosine {worst[1][1]:.5f} ({worst[0]})")
+    # whole-step agreement is bounded by the chaos of this random-init net under bf16 storage: two CPU emulations that
+    # differ only in accumulation precision (fp32 vs fp64) already diverge to cosine ~0.73 at the stem and 0.45 on the
+    # logits (measured, DESIGN.md section 5); the tight statement is test_training_step_layerwise_teacher_forced
+    assert abs(float(loss.detach()) - ref["loss"]) < 5e-3
+    assert errs["segmentation_head.0.weight"][1] > 0.999
+    assert errs["decoder.blocks.4.conv1.0.weight"][1] > 0.97
+    assert worst[1][1] > 0.5, worst
+
+
+@pytest.mark.parametrize("cin,cout,N,H,W", [(64, 64, 2, 16, 8), (64, 128, 2, 32, 16), (128, 64, 1, 16, 16), (256, 256, 4, 8, 8),
+                                            (192, 64, 1, 16, 24), (16, 16, 1, 32, 32), (32, 16, 2, 16, 16), (128, 32, 1, 16, 8),
+                                            (512, 512, 2, 8, 8)])
+def test_wgrad_tensor_core(cin, cout, N, H, W):
+    """tcgen05 weight gradient (MN-major operands straight from NHWC) against torch autograd on the bf16-rounded operands."""
+    g = torch.Generator().manual_seed(cin + cout + H)
+    x = torch.randn(N, cin, H, W, generator=g).to(torch.bfloat16).float()
+    gy = torch.randn(N, cout, H, W, generator=g).to(torch.bfloat16).float()
+    w = torch.zeros(cout, cin, 3, 3, requires_grad=True)
+    F.conv2d(x, w, None, 1, 1).backward(gy)
+    assert ops.wgrad_tc_supported(nhwc(x, torch.bfloat16), nhwc(gy, torch.bfloat16), w.shape, 1, 1)
+    dw = ops.conv2d_wgrad_tc(nhwc(x, torch.bfloat16), nhwc(gy, torch.bfloat16), w.shape)
+    torch.cuda.synchronize()
+    err, rel = report(f"wgrad tcgen05 {cin}->{cout} N={N} {H}x{W}", dw.cpu(), w.grad)
+    assert rel < 1e-4
+
+
+@pytest.mark.parametrize("cin,cout,N,H", [(64, 64, 2, 32), (192, 64, 1, 16), (32, 16, 1, 32), (768, 256, 2, 16)])
+def test_dgrad_through_forward_kernel(cin, cout, N, H):
+    """data gradient of a 3x3/s1 conv = forward tcgen05 conv of gy with the flipped, transposed weights (+ addend)."""
+    g = torch.Generator().manual_seed(cin + cout)
+    x = torch.zeros(N, cin, H, H, requires_grad=True)
+    w = (torch.randn(cout, cin, 3, 3, generator=g) * 0.05)
+    gy = torch.randn(N, cout, H, H, generator=g).to(torch.bfloat16).float()
+    F.conv2d(x, w.to(torch.bfloat16).float(), None, 1, 1).backward(gy)
+    add = torch.randn(N, cin, H, H, generator=g).to(torch.bfloat16).float()
+    wp = ops.pack_conv_weight(w.cuda(), 3)
+    ones, zeros = torch.ones(cin, device="cuda"), torch.zeros(cin, device="cuda")
+    gx = ops.conv2d(nhwc(gy, torch.bfloat16), wp, ones, zeros, N=N, H=H, W=H, C_in=cout, C_x=cout, C_out=cin, R=3, S=3,
+                    stride=1, pad=1, relu=False, residual=nhwc(add, torch.bfloat16))
+    torch.cuda.synchronize()
+    ref = x.grad + add
+    err, rel = report(f"dgrad via fwd kernel {cin}<-{cout}", nchw(gx), ref)
+    assert rel < 1e-2
+
+
+def _rel(got, ref):
+    ref = ref.double()
+    return float((got.double() - ref).abs().max() / (ref.abs().max() + 1e-30))
+
+
+@pytest.mark.parametrize("precision,n,T", [("bf16", 2, 256), ("fp32", 2, 64)])
+def test_training_step_layerwise_teacher_forced(precision, n, T):
+    """Every kernel-level operation of ONE real training step (forward and backward, all 47 layers) re-computed by
+    torch on the CPU from the operation's own device inputs.  This is the parity statement for the bf16 path: errors
+    cannot compound across layers, so each op must agree to fp32-accumulation accuracy (statistics, weight gradients)
+    or to one bf16 rounding of the stored result (activations, activation gradients)."""
+    cin = 4
+    oracle = oracle_model(cin, 3)
+    img, mask = _batch(n, cin, T, 3)
+    seg = _semsegment(oracle, cin, precision)
+    eng = seg.model.train_engine()
+    eng.trace = []
+    batch = {"main": (img.cuda(), mask.cuda(), None, torch.zeros(n), [{"file": f"t{i}"} for i in range(n)])}
+    seg.training_step(batch, 0).backward()
+    torch.cuda.synchronize()
+    trace, eng.trace = eng.trace, None
+    params = {k: v.detach().cpu() for k, v in seg.model.named_parameters()}
+    bf = precision == "bf16"
+    act_tol = 1e-2 if bf else 1e-5          # one bf16 rounding of the stored tensor
+    acc_tol = 2e-4                          # fp32 accumulation order
+    rw = (lambda w: w.to(torch.bfloat16).float()) if bf else (lambda w: w)
+    cpu = lambda t: None if t is None else nchw(t)
+    worst = {}
+
+    def note(kind, v):
+        worst[kind] = max(worst.get(kind, 0.0), v)
+
+    kinds = set()
+    for kind, name, t in trace:
+        kinds.add(kind)
+        if kind == "conv_bn_fwd":
+            w = params[name + ".weight"]
+            x = cpu(t["x"])[:, : w.shape[1]]
+            y_ref = F.conv2d(x, rw(w), None, t["stride"], t["pad"])
+            note("conv y", _rel(cpu(t["y"]), y_ref)); assert worst["conv y"] < act_tol, name
+            y = cpu(t["y"])
+            mean, var = y.mean((0, 2, 3)), y.var((0, 2, 3), unbiased=False)
+            note("bn mean", float((t["mean"].cpu() - mean).abs().max() / (mean.abs().max() + 1e-6)))
+            note("bn invstd", _rel(t["invstd"].cpu(), 1.0 / torch.sqrt(var + 1e-5)))
+            assert worst["bn mean"] < 1e-3 and worst["bn invstd"] < 1e-3, name
+            z = y * t["scale"].cpu()[None, :, None, None] + t["shift"].cpu()[None, :, None, None]
+            if t["residual"] is not None:
+                z = z + cpu(t["residual"])
+            note("bn apply", _rel(cpu(t["a"]), F.relu(z) if t["relu"] else z)); assert worst["bn apply"] < act_tol, name
+        elif kind == "bn_bwd":
+            g, y = cpu(t["g"]).double(), cpu(t["y"]).double()
+            gz = g * (cpu(t["a"]) > 0) if t["a"] is not None else g
+            mean, invstd, scale = (t[k].cpu().double()[None, :, None, None] for k in ("mean", "invstd", "scale"))
+            yhat = (y - mean) * invstd
+            M = y.numel() / y.shape[1]
+            dbeta, dgamma = gz.sum((0, 2, 3)), (gz * yhat).sum((0, 2, 3))
+            gy = scale * (gz - dbeta[None, :, None, None] / M - yhat * dgamma[None, :, None, None] / M)
+            note("bn dgamma", _rel(t["dgamma"].cpu(), dgamma)); note("bn dbeta", _rel(t["dbeta"].cpu(), dbeta))
+            note("bn gy", _rel(cpu(t["gy"]), gy))
+            assert worst["bn dgamma"] < acc_tol and worst["bn dbeta"] < acc_tol and worst["bn gy"] < act_tol, name
+            if t["gz"] is not None:
+                note("bn gz", _rel(cpu(t["gz"]), gz)); assert worst["bn gz"] < act_tol, name
+        elif kind == "wgrad":
+            w = params[name]
+            x = cpu(t["x"])[:, : w.shape[1]]
+            dw = torch.nn.grad.conv2d_weight(x, w.shape, cpu(t["gy"]), t["stride"], t["pad"])
+            note("wgrad", _rel(t["dw"].cpu(), dw)); assert worst["wgrad"] < acc_tol, name
+            if t["db"] is not None:
+                note("bias grad", _rel(t["db"].cpu(), cpu(t["gy"]).sum((0, 2, 3)))); assert worst["bias grad"] < acc_tol
+        elif kind == "dgrad":
+            w = params[name]
+            gx_shape = (t["gx"].shape[0], w.shape[1], t["gx"].shape[1], t["gx"].shape[2])
+            wr = w if t.get("fp32_weights") else rw(w)
+            gx = torch.nn.grad.conv2d_input(gx_shape, wr, cpu(t["gy"]), t["stride"], t["pad"])
+            if t["addend"] is not None:
+                gx = gx + cpu(t["addend"])[:, : w.shape[1]]
+            note("dgrad", _rel(cpu(t["gx"])[:, : w.shape[1]], gx)); assert worst["dgrad"] < act_tol, name
+        elif kind == "maxpool_fwd":
+            assert torch.equal(cpu(t["y"]), F.max_pool2d(cpu(t["x"]), 3, 2, 1))
+        elif kind == "maxpool_bwd":
+            x = cpu(t["x"]).requires_grad_(True)
+            F.max_pool2d(x, 3, 2, 1).backward(cpu(t["gout"]))
+            ref = x.grad + (cpu(t["addend"]) if t["addend"] is not None else 0)
+            note("maxpool bwd", _rel(cpu(t["gx"]), ref)); assert worst["maxpool bwd"] < act_tol
+        elif kind == "upcat_fwd":
+            up = F.interpolate(cpu(t["x"]), scale_factor=2, mode="nearest")
+            assert torch.equal(cpu(t["y"]), torch.cat([up, cpu(t["skip"])], 1) if t["skip"] is not None else up)
+        elif kind == "upcat_bwd":
+            gc, cx = cpu(t["g_cat"]), t["cx"]
+            note("unconcat", _rel(cpu(t["g_low"]), F.avg_pool2d(gc[:, :cx], 2) * 4)); assert worst["unconcat"] < act_tol
+            if t["g_skip"] is not None:
+                assert torch.equal(cpu(t["g_skip"]), gc[:, cx:])
+        elif kind == "head_fwd":
+            ref = F.conv2d(cpu(t["x"]), params["segmentation_head.0.weight"], params["segmentation_head.0.bias"], 1, 1)
+            note("head", _rel(t["y"].cpu(), ref)); assert worst["head"] < acc_tol
+    assert kinds == {"conv_bn_fwd", "bn_bwd", "wgrad", "dgrad", "maxpool_fwd", "maxpool_bwd", "upcat_fwd", "upcat_bwd", "head_fwd"}
+    assert sum(1 for k, _, _ in trace if k == "wgrad") == 47 and sum(1 for k, _, _ in trace if k == "dgrad") == 46
+    print(f"[train {precision} layerwise T={T}] worst relative errors per op kind: " +
+          ", ".join(f"{k}={v:.2e}" for k, v in sorted(worst.items())))
