@@ -37,6 +37,10 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="infer", choices=["infer", "train"],
+                    help="infer: cfg2/cfg3 whole-mosaic inference (the headline metric); train: cfg4 training step, "
+                         "64 RGB+NIR tiles of 256x256 per GPU, Dice+Focal, clip 0.5, Adam, data parallel")
+    ap.add_argument("--train-batch", type=int, default=64, help="tiles per GPU per training step (cfg4)")
     ap.add_argument("--size", type=int, default=10000, help="mosaic side in pixels")
     ap.add_argument("--tile", type=int, default=256)
     ap.add_argument("--overlap", type=int, default=32)
@@ -370,9 +374,193 @@ def main_b200(a):
         dist.destroy_process_group()
 
 
+# ---------------------------------------------------------------------------------------------------
+def train_flops_per_tile(T: int, cin: int, classes: int) -> float:
+    """algorithmic conv FLOPs of one training step per tile: forward + data gradient + weight gradient of every conv
+    (3 x forward) minus the stem's data gradient, which is never needed."""
+    from deadtrees_b200.engine import conv_flops_per_tile
+    return 3.0 * conv_flops_per_tile(T, cin, classes) - 2.0 * (T // 2) ** 2 * 64 * cin * 49
+
+
+def synthetic_train_batch(B: int, T: int, cin: int, K: int, seed: int):
+    g = torch.Generator().manual_seed(seed)
+    u8 = torch.randint(0, 256, (B, cin, T, T), generator=g, dtype=torch.uint8)
+    from deadtrees_b200.data.deadtreedata import normalize_constants
+    off, sc = normalize_constants(cin, None, None)
+    img = (u8.float() - torch.tensor(off[:cin]).view(1, cin, 1, 1)) * torch.tensor(sc[:cin]).view(1, cin, 1, 1)
+    yy, xx = torch.meshgrid(torch.arange(T), torch.arange(T), indexing="ij")
+    mask = torch.stack([(((yy + 7 * i) // 23 + (xx + 3 * i) // 17) % K) for i in range(B)]).long()
+    return img.contiguous(), mask.contiguous()
+
+
+def main_train_reference(a):
+    """cfg4 on the host cores: the oracle's training step (torch CPU autograd + the reference's loss terms + clip + Adam)."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    from oracle import ref_train, ref_unet
+    torch.set_num_threads(os.cpu_count() or 1)
+    B, T, cin, K = 8, a.tile, 4, 3
+    model = ref_unet.build_reference_unet(cin, K, seed=0)
+    img, mask = synthetic_train_batch(B, T, cin, K, 1234)
+    opt = torch.optim.Adam(model.parameters(), lr=3e-4)
+    times = []
+    for i in range(a.warmup + a.steps):
+        t0 = time.perf_counter()
+        ref_train.train_step(model, img, mask, lr=3e-4, clip=0.5, optimizer=opt)
+        if i >= a.warmup:
+            times.append(time.perf_counter() - t0)
+    tps = B / statistics.mean(times)
+    sample = f"one training step on {B} RGB+NIR tiles of {T}x{T} per timed step (oracle Unet autograd fp32 + reference loss " \
+             f"terms + clip_grad_norm_(0.5) + torch.optim.Adam), torch CPU, {torch.get_num_threads()} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": "unet_train_tiles_per_s", "value": tps, "unit": UNIT, "n_gpus": a.gpus,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * statistics.mean(times), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"cfg4: Unet-resnet34 training step, {a.train_batch} RGB+NIR {T}x{T} tiles per GPU, Dice+Focal, "
+                               f"clip 0.5, Adam lr 3e-4", "tile": T, "batch_per_gpu": a.train_batch, "in_channels": 4, "classes": 3},
+        "cpu_baseline": {"value": tps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": tps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+
+
+def main_train(a):
+    import torch.distributed as dist
+    from deadtrees_b200 import ops
+    from deadtrees_b200._lib import require_device
+    from deadtrees_b200.network.segmodel import SemSegment
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    require_device()
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    B, T, cin, K = a.train_batch, a.tile, 4, 3
+    net = dict(architecture="unet", encoder_name="resnet34", encoder_depth=5, encoder_weights=None,
+               decoder_channels=[256, 128, 64, 32, 16], losses=["DICE", "FOCAL"], classes=["bg", "a", "b"],
+               in_channels=cin, precision=a.precision)
+    torch.manual_seed(0)                       # identical replicas on every rank
+    seg = SemSegment(net, dict(learning_rate=3e-4, cosineannealing_tmax=10, gradient_clip_val=0.5)).cuda().train()
+    eng = seg.model.train_engine()
+    if world > 1:
+        eng.set_process_group(None, world_size=world)
+    (opt,), _ = seg.configure_optimizers()
+    img_h, mask_h = synthetic_train_batch(B, T, cin, K, 1234 + rank)       # per-rank batch
+    img_h, mask_h = img_h.pin_memory(), mask_h.pin_memory()
+    img_d, mask_d = img_h.to(dev), mask_h.to(dev)
+    lu = torch.zeros(B)
+    stats = [{"file": f"r{rank}t{i}"} for i in range(B)]
+    loss_h = torch.zeros((), pin_memory=True)
+
+    def step_device():
+        loss = seg.training_step({"main": (img_d, mask_d, None, lu, stats)}, 0)
+        loss.backward()
+        opt.step()
+        return loss
+
+    def step_e2e():
+        img_d.copy_(img_h, non_blocking=True)
+        mask_d.copy_(mask_h, non_blocking=True)
+        loss = step_device()
+        loss_h.copy_(loss.detach(), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(loss_h)
+
+    def timed(fn, steps, profile=False):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ops.PROFILE = {} if profile else None
+        l0 = ops.LAUNCHES
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = e0.elapsed_time(e1)
+        prof, ops.PROFILE = ops.PROFILE, None
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, ops.LAUNCHES - l0, prof
+
+    for _ in range(max(a.warmup, 3)):
+        step_device()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms_total, launches, prof = timed(step_device, a.steps, profile=not a.no_profile)
+    clocks = sampler.stop()
+    ms_step = ms_total / a.steps
+    for _ in range(2):
+        step_e2e()
+    ms_e2e_total, _, _ = timed(step_e2e, a.steps)
+    ms_e2e = ms_e2e_total / a.steps
+    last_loss = step_e2e()
+    pk = peaks()
+    fl = train_flops_per_tile(T, cin, K)
+    out = {
+        "metric": "unet_train_tiles_per_s", "value": world * B / (ms_step / 1e3), "unit": UNIT, "n_gpus": world,
+        "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": a.precision if a.precision == "bf16" else "f32", "data": "synthetic",
+        "config": {"workload": f"cfg4: Unet-resnet34 training step (train-mode BN fwd + Dice/Focal + bwd + clip 0.5 + Adam), "
+                               f"{B} RGB+NIR {T}x{T} tiles per GPU, data parallel x{world}",
+                   "tile": T, "batch_per_gpu": B, "in_channels": cin, "classes": K,
+                   "l2_policy": "per-step working set (activations + gradients, > 5 GB) far larger than L2; no explicit flush",
+                   "parallelism": f"dp{world}, bucketed NCCL gradient all-reduce overlapped with backward"},
+        "mpixel_per_s": world * B * T * T / 1e6 / (ms_step / 1e3),
+        "e2e": {"value": world * B / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(img_h.numel() * 4 + mask_h.numel() * 8),
+                "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e},
+        "gpu_launches": int(launches), "clocks": clocks, "final_loss": last_loss,
+        "step_tflops": B * fl / (ms_step / 1e3) / 1e12, "flops_per_tile": fl,
+    }
+    if prof:
+        def agg(evs):
+            return sum(e[0].elapsed_time(e[1]) for e in evs) / 1e3, sum(e[2] for e in evs), len(evs)
+        conv = prof.get("conv", [])
+        tf, wf, nf = agg([e for e in conv if e[3].startswith("train.")])
+        td, wd, nd = agg([e for e in conv if e[3].startswith("dgrad.")])
+        tw, ww, nw = agg(prof.get("wgrad", []))
+        t_all, w_all = tf + td + tw, wf + wd + ww
+        if t_all > 0:
+            ach = w_all / t_all / 1e12
+            out["roofline"] = {"bound": "tensor", "kernel": "tcgen05 conv forward + dgrad (forward kernels on transposed weights) + MN-major wgrad",
+                               "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"],
+                               "traffic": None, "launches": nf + nd + nw, "share_of_step": t_all * 1e3 / ms_total,
+                               "peak_source": pk["source"],
+                               "breakdown": {"forward": {"ms_per_step": 1e3 * tf / a.steps, "tflops": wf / max(tf, 1e-12) / 1e12, "launches": nf},
+                                             "dgrad_tc": {"ms_per_step": 1e3 * td / a.steps, "tflops": wd / max(td, 1e-12) / 1e12, "launches": nd},
+                                             "wgrad_tc": {"ms_per_step": 1e3 * tw / a.steps, "tflops": ww / max(tw, 1e-12) / 1e12, "launches": nw}}}
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        from oracle import ref_train, ref_unet
+        torch.set_num_threads(os.cpu_count() or 1)
+        model = ref_unet.build_reference_unet(cin, K, seed=0)
+        ci, cm = synthetic_train_batch(8, T, cin, K, 1234)
+        copt = torch.optim.Adam(model.parameters(), lr=3e-4)
+        ts = []
+        for i in range(3):
+            t0 = time.perf_counter()
+            ref_train.train_step(model, ci, cm, lr=3e-4, clip=0.5, optimizer=copt)
+            ts.append(time.perf_counter() - t0)
+        out["cpu_baseline"] = {"value": 8 / min(ts[1:]), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                               "sample": f"one oracle training step on 8 RGB+NIR tiles of {T}x{T} (torch CPU autograd fp32 + reference "
+                                         f"loss terms + clip + Adam), best of 2 after 1 warm-up"}
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 if __name__ == "__main__":
     args = parse()
-    if args.impl == "reference":
+    if args.workload == "train":
+        (main_train_reference if args.impl == "reference" else main_train)(args)
+    elif args.impl == "reference":
         main_reference(args)
     else:
         main_b200(args)

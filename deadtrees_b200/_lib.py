@@ -15,7 +15,7 @@ _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "libdeadtrees_b200.so"
 
 DT_BF16, DT_F32 = 0, 1
-CONV_FORCE_GATHER, CONV_FORCE_DIRECT, CONV_NO_HALO, CONV_X_PAD3 = 1, 2, 4, 8
+CONV_FORCE_GATHER, CONV_FORCE_DIRECT, CONV_NO_HALO, CONV_X_PAD3, CONV_TRANSPOSED = 1, 2, 4, 8, 16
 
 
 class DeadtreesB200Error(RuntimeError):
@@ -61,10 +61,12 @@ _SIGNATURES = {
     "dt_upsample_concat": ([_p, _p, _i, _i, _i, _i, _i, _i, _p, _p], C.c_int),
     "dt_upsample_concat_bwd": ([_p, _i, _i, _i, _i, _i, _i, _p, _p, _p], C.c_int),
     "dt_nchw_to_nhwc": ([_p, _i, _i, _i, _i, _i, _i, _p, _p], C.c_int),
+    "dt_channel_sum": ([_p, _i64, _i, _i, _i, _p, _p], C.c_int),
     "dt_pack_conv_weight": ([_p, _i, _i, _i, _i, _i, _i, _i, _p, _p], C.c_int),
     "dt_conv2d_dgrad_direct": ([_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p], C.c_int),
     "dt_conv2d_wgrad_direct": ([_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p], C.c_int),
-    "dt_conv2d_wgrad_tc": ([_p, _p, _i, _i, _i, _i, _i, _p, _p], C.c_int),
+    "dt_conv2d_wgrad_tc_workspace": ([_i, _i, _i, _i, _i, _i, _i], C.c_int64),
+    "dt_conv2d_wgrad_tc": ([_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _i64, _p], C.c_int),
     "dt_sumsq": ([_p, _i64, _p, _p], C.c_int),
     "dt_adam_step": ([_p, _p, _p, _p, _i64, _f, _f, _f, _f, _i, _p, _f, _p], C.c_int),
 }

@@ -43,6 +43,7 @@ struct TcParams {
   int relu, has_residual, stem;
   int num_k_chunks, k_total;              // Kpad / 64, un-padded K
   int a_cw;                               // channels per A TMA load: min(64, C_in)
+  int transposed;                         // 1: data gradient of a stride-2 conv (gather producer): x is gy, taps scatter
   int parity;                             // 1: tiles enumerate output-pixel parity classes (upsample convs)
   int Hg, Wg;                             // pixel grid the M tiles walk (output grid, or low-res grid in parity mode)
   int M_lim;                              // pixels per class (parity) or in total
@@ -325,8 +326,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         const int m = g.m0 + rsub + 16 * it;
         if (m < p.M_lim) {
           const int wo = m % p.Wo, t = m / p.Wo;
-          hb[it] = (t % p.Ho) * p.stride - p.pad;
-          wb[it] = wo * p.stride - p.pad;
+          if (p.transposed) {   // output pixel (h, w) of the data gradient: source row = (h + pad - r) / stride
+            hb[it] = (t % p.Ho) + p.pad;
+            wb[it] = wo + p.pad;
+          } else {
+            hb[it] = (t % p.Ho) * p.stride - p.pad;
+            wb[it] = wo * p.stride - p.pad;
+          }
           nb[it] = t / p.Ho;
         } else {
           hb[it] = -100000; wb[it] = 0; nb[it] = 0;   // every tap lands out of bounds -> zeros
@@ -357,9 +363,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           const bool from_x = ci < p.C_x;
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
-            const int hi = hb[it] + fr, wi = wb[it] + fs;
+            int hi = hb[it] + fr, wi = wb[it] + fs;
+            bool ok = kvalid;
+            if (p.transposed) {   // stride-2 data gradient: only taps whose source coordinate is even contribute
+              hi = hb[it] - fr; wi = wb[it] - fs;
+              ok = ok && hi >= 0 && wi >= 0 && ((hi | wi) & 1) == 0;
+              hi >>= 1; wi >>= 1;
+            }
             val[it] = make_uint4(0u, 0u, 0u, 0u);
-            if (kvalid && hi >= 0 && hi < p.H && wi >= 0 && wi < p.W) {
+            if (ok && hi >= 0 && hi < p.H && wi >= 0 && wi < p.W) {
               const __nv_bfloat16* src =
                   from_x ? p.x + ((static_cast<int64_t>(nb[it]) * p.Hx + (hi >> p.ups)) * p.Wx + (wi >> p.ups)) * p.C_x + ci
                          : p.skip + ((static_cast<int64_t>(nb[it]) * p.H + hi) * p.W + wi) * p.C_s + (ci - p.C_x);
@@ -494,9 +506,14 @@ extern "C" int dt_conv2d_fwd(const dt_conv_desc* d, const void* x, const void* s
   DT_REQUIRE(d->C_x == d->C_in || skip != nullptr, DT_ERR_BAD_SHAPE, "dt_conv2d_fwd: skip tensor missing");
   DT_REQUIRE(!d->has_residual || residual != nullptr, DT_ERR_BAD_SHAPE, "dt_conv2d_fwd: residual tensor missing");
   DT_REQUIRE(d->dtype == DT_BF16 || d->dtype == DT_F32, DT_ERR_BAD_SHAPE, "dt_conv2d_fwd: dtype %d", d->dtype);
-  const int Ho = (d->H + 2 * d->pad - d->R) / d->stride + 1;
-  const int Wo = (d->W + 2 * d->pad - d->S) / d->stride + 1;
-  DT_REQUIRE(Ho > 0 && Wo > 0, DT_ERR_BAD_SHAPE, "dt_conv2d_fwd: empty output");
+  const bool transposed = (d->flags & DT_CONV_TRANSPOSED) != 0;
+  // transposed: desc H, W are the OUTPUT size (the conv input whose gradient is computed); x is gy at the conv's output size
+  const int Hsrc = (d->H + 2 * d->pad - d->R) / d->stride + 1, Wsrc = (d->W + 2 * d->pad - d->S) / d->stride + 1;
+  const int Ho = transposed ? d->H : Hsrc, Wo = transposed ? d->W : Wsrc;
+  DT_REQUIRE(Ho > 0 && Wo > 0 && Hsrc > 0 && Wsrc > 0, DT_ERR_BAD_SHAPE, "dt_conv2d_fwd: empty output");
+  DT_REQUIRE(!transposed || (d->dtype == DT_BF16 && d->stride == 2 && !d->upsample && d->C_x == d->C_in &&
+                             !(d->flags & (DT_CONV_X_PAD3 | DT_CONV_FORCE_DIRECT))),
+             DT_ERR_BAD_SHAPE, "dt_conv2d_fwd: DT_CONV_TRANSPOSED is the bf16 data gradient of a stride-2 conv");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
 
   const int stem = (d->C_in == 4 && d->R == 7 && d->S == 7) ? 1 : 0;
@@ -529,7 +546,7 @@ extern "C" int dt_conv2d_fwd(const dt_conv_desc* d, const void* x, const void* s
   DT_REQUIRE(d->C_out % BN == 0 && (BN == 16 || BN == 32 || BN == 64 || BN == 128 || BN == 256), DT_ERR_BAD_SHAPE,
              "dt_conv2d_fwd: unsupported C_out %d", d->C_out);
 
-  if (!(d->flags & (DT_CONV_NO_HALO | DT_CONV_FORCE_GATHER)) && !stem) {
+  if (!(d->flags & (DT_CONV_NO_HALO | DT_CONV_FORCE_GATHER)) && !stem && !transposed) {
     const int rc0 = dt_conv_res(d, x, w, Kpad, scale, shift, residual, y, s);   // weights resident in smem
     if (rc0 != DT_ERR_UNSUPPORTED) return rc0;
     const int rc = dt_conv_halo(d, BN, x, skip, w, Kpad, scale, shift, residual, y, s);
@@ -540,6 +557,7 @@ extern "C" int dt_conv2d_fwd(const dt_conv_desc* d, const void* x, const void* s
   memset(&p, 0, sizeof(p));
   p.H = d->H; p.W = d->W; p.C_in = d->C_in; p.C_x = d->C_x; p.C_s = d->C_in - d->C_x; p.ups = d->upsample ? 1 : 0;
   p.Hx = d->upsample ? d->H / 2 : d->H; p.Wx = d->upsample ? d->W / 2 : d->W;
+  if (transposed) { p.transposed = 1; p.H = p.Hx = Hsrc; p.W = p.Wx = Wsrc; }
   p.Ho = Ho; p.Wo = Wo; p.C_out = d->C_out; p.R = d->R; p.S = d->S; p.stride = d->stride; p.pad = d->pad;
   p.relu = d->relu; p.has_residual = d->has_residual; p.stem = stem;
   p.num_k_chunks = Kpad / BK;
@@ -554,7 +572,7 @@ extern "C" int dt_conv2d_fwd(const dt_conv_desc* d, const void* x, const void* s
 
   // ---- can the A operand come through TMA? ----
   int bw = 0, bh = 0, bn = 0;
-  bool use_tma = !(d->flags & DT_CONV_FORCE_GATHER) && !stem;
+  bool use_tma = !(d->flags & DT_CONV_FORCE_GATHER) && !stem && !transposed;
   const bool wide = d->C_in % BK == 0 && d->C_x % BK == 0;                       // 128 B rows, slabs of 64 channels
   const bool narrow = (d->C_in == 32 || d->C_in == 16) && d->C_x == d->C_in;     // 64 B / 32 B rows, one box per tap
   use_tma = use_tma && (wide || narrow) && (d->stride == 1 || d->stride == 2);

@@ -1,23 +1,28 @@
-// Weight gradient of a 3x3 / stride-1 / pad-1 convolution on the sm_100a tensor cores (tcgen05, TMEM accumulators).
+// Weight gradient of the 3x3 (stride 1 or 2, pad 1) and 1x1 / stride-2 convolutions on the sm_100a tensor cores
+// (tcgen05, TMEM accumulators).
 //
-//   dW[co][ci][r][s] = sum over pixels p of  gy[p][co] * x[p + (r-1, s-1)][ci]
+//   dW[co][ci][r][s] = sum over output pixels p of  gy[p][co] * x[stride * p + (r - pad, s - pad)][ci]
 //
 // GEMM view per filter tap: D_tap[M = co][N = ci] += A[co][K = pixel] * B_tap[ci][K = pixel].  Both operands are read
 // straight from the NHWC bf16 tensors as **MN-major** UMMA operands: a TMA box (64 channels x pixels, SWIZZLE_128B)
 // lands in shared memory as rows of 128 B (one pixel each) - exactly the MN-major canonical atom (64 MN elements x 8 K
 // rows), with the pixel index as K.  No transposed copies of activations or gradients are ever made.
 //   A  = gy tile: 8 (w) x 16 (h) pixels (= K 128) x 64-channel slabs, two slabs (leading-byte-offset apart) give M = 128
-//   B  = x halo patch: (16+2) x (8+2) pixels x one 64-channel slab, loaded ONCE per tile; the nine taps read it in place
-//        through descriptors whose start is shifted by (r*10 + s) pixel rows and whose stride-byte-offset (distance
-//        between the 8-pixel K groups = image rows) is 10 pixel rows - the same absolute-address-swizzle property the
-//        forward halo kernel relies on (profiles/r01_halo_descriptor_experiment.txt).
+//   B  = x halo patch: (16+2) x (8+2) pixels x one 64-channel slab, loaded ONCE per tile; the taps of a tap group read it
+//        in place through descriptors whose start is shifted by (dr*10 + ds) pixel rows and whose stride-byte-offset
+//        (distance between the 8-pixel K groups = image rows) is 10 pixel rows - the same absolute-address-swizzle
+//        property the forward halo kernel relies on (profiles/r01_halo_descriptor_experiment.txt).
+//        stride 1: tap groups {0..4}, {5..8} of the one patch.   stride 2: one tap group per input parity plane
+//        x[2i+pr][2j+pc] (TMA traversal stride 2): plane (1,1) serves taps (0,0) (0,2) (2,0) (2,2), (1,0) -> (0,1) (2,1),
+//        (0,1) -> (1,0) (1,2), (0,0) -> (1,1); the 1x1 / stride-2 downsample is plane (0,0) alone.
 // Channel counts below 64 are handled by TMA out-of-bounds zero fill (box wider than the tensor), so one kernel
 // configuration (M 128, N 64) serves every layer; rows / columns beyond C_out / C_in are never written back.
 // Images smaller than 16 rows (8x8 at the bottom of the encoder) put two images in one tile.
 //
-// Work decomposition: job = (128-wide co block, 64-wide ci slab, tap group {0..4} | {5..8}); the pixel tiles are split
-// over `splits` CTAs per job; every CTA keeps its 5 (4) tap accumulators of 128 x 64 fp32 in TMEM across all its
-// tiles and adds them to dW (fp32 atomics) once at the end.
+// Work decomposition: job = (128-wide co block, 64-wide ci slab, tap group); the pixel tiles are split over `splits`
+// CTAs per job; every CTA keeps its <= 5 tap accumulators of 128 x 64 fp32 in TMEM across all its tiles and writes them
+// once, with coalesced stores, to partial[split][tap][co][ci]; a second kernel sums the splits in a fixed order into the
+// fp32 OIHW gradient (deterministic: no atomics).
 //   warp 0: TMA producer   warp 1: TMEM alloc + MMA issuer   warps 2..5: epilogue
 //
 // Replaces the cuDNN wgrad kernels autograd reaches from SemSegment.training_step
@@ -37,14 +42,23 @@ constexpr int B_STAGE = 26 * 1024;           // >= 2 images x 10 x 10 pixels x 1
 constexpr int STAGES = 3;
 constexpr int TMEM_COLS = 512;
 constexpr int NCOL = 64;                     // UMMA N (one ci slab)
+constexpr int MAX_GROUPS = 4, MAX_TAPS = 5;
+
+struct WgGroup {
+  int ntaps, pr, pc, pad_;
+  int tap[MAX_TAPS];                // filter tap r*S+s this accumulator belongs to
+  int off[MAX_TAPS];                // pixel-row offset of the tap's window inside the patch
+};
 
 struct WgParams {
-  int N, H, W, C_in, C_out;
+  int N, H, W, C_in, C_out;         // H, W: OUTPUT (= gy) size
+  int RS, stride;
   int th_img, imgs;                 // image rows per tile (8 or 16), images per tile (2 or 1)
   int tiles_w, tiles_h, total_tiles;
-  int ci_slabs, jobs, tiles_per_cta;
+  int ci_slabs, ngroups, jobs, tiles_per_cta;
   int patch_bytes;
-  float* dw;
+  float* partial;                   // [splits][RS][C_out][C_in]
+  WgGroup grp[MAX_GROUPS];
 };
 
 // MN-major, 128-byte-swizzled operand descriptor: rows of 64 bf16 (one K index each), 8-row K groups `sbo` bytes
@@ -73,10 +87,11 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constan
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int job = blockIdx.x % p.jobs, split = blockIdx.x / p.jobs;
-  const int tg = job & 1;
-  const int ci_slab = (job >> 1) % p.ci_slabs;
-  const int co_block = (job >> 1) / p.ci_slabs;
-  const int tap0 = tg ? 5 : 0, ntaps = tg ? 4 : 5;
+  const int gi = job % p.ngroups;
+  const int ci_slab = (job / p.ngroups) % p.ci_slabs;
+  const int co_block = (job / p.ngroups) / p.ci_slabs;
+  const WgGroup& grp = p.grp[gi];
+  const int ntaps = grp.ntaps;
   const int tile_begin = split * p.tiles_per_cta;
   const int tile_end = min(p.total_tiles, tile_begin + p.tiles_per_cta);
   const int a_slabs = min(2, (p.C_out - co_block * 128 + 63) / 64);
@@ -101,6 +116,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constan
     if (lane == 0) {
       int st = 0;
       uint32_t ph = 0;
+      const int s = p.stride;
       for (int tile = tile_begin; tile < tile_end; ++tile) {
         int m = tile;
         const int w0 = (m % p.tiles_w) * TW; m /= p.tiles_w;
@@ -108,9 +124,10 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constan
         const int n0 = (m / p.tiles_h) * p.imgs;
         mbar_wait(&empty[st], ph ^ 1u);
         mbar_arrive_expect_tx(&full[st], a_slabs * A_SLAB + p.patch_bytes);
-        for (int s = 0; s < a_slabs; ++s)
-          tma_load_4d(smem_a + st * A_STAGE + s * A_SLAB, &tm_g, &full[st], co_block * 128 + s * 64, w0, h0, n0);
-        tma_load_4d(smem_b + st * B_STAGE, &tm_x, &full[st], ci_slab * 64, w0 - 1, h0 - 1, n0);
+        for (int sl = 0; sl < a_slabs; ++sl)
+          tma_load_4d(smem_a + st * A_STAGE + sl * A_SLAB, &tm_g, &full[st], co_block * 128 + sl * 64, w0, h0, n0);
+        // patch origin (h0 - 1, w0 - 1) in the coordinates of the (parity plane of the) input
+        tma_load_4d(smem_b + st * B_STAGE, &tm_x, &full[st], ci_slab * 64, s * (w0 - 1) + grp.pc, s * (h0 - 1) + grp.pr, n0);
         if (++st == STAGES) { st = 0; ph ^= 1u; }
       }
     }
@@ -136,8 +153,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constan
         const uint32_t b_addr = smem_u32(smem_b + st * B_STAGE);
 #pragma unroll 1
         for (int t = 0; t < ntaps; ++t) {
-          const int tap = tap0 + t;
-          const uint32_t toff = static_cast<uint32_t>((tap / 3) * PITCH + tap % 3);
+          const uint32_t toff = static_cast<uint32_t>(grp.off[t]);
           const uint32_t d_tmem = tmem_base + t * NCOL;
 #pragma unroll
           for (int k8 = 0; k8 < 8; ++k8) {
@@ -157,7 +173,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constan
     mbar_wait(done, 0);
     tc_fence_after();
     for (int t = 0; t < ntaps; ++t) {
-      const int tap = tap0 + t;
+      float* dst = p.partial + ((static_cast<int64_t>(split) * p.RS + grp.tap[t]) * p.C_out + co) * p.C_in + ci_slab * 64;
 #pragma unroll
       for (int c0 = 0; c0 < NCOL; c0 += 16) {
         uint32_t v[16];
@@ -165,9 +181,10 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constan
         tmem_ld_wait();
         if (co < p.C_out) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int ci = ci_slab * 64 + c0 + j;
-            if (ci < p.C_in) atomicAdd(p.dw + (static_cast<int64_t>(co) * p.C_in + ci) * 9 + tap, __uint_as_float(v[j]));
+          for (int j = 0; j < 16; j += 4) {   // C_in is a multiple of 4: whole float4s are inside or outside
+            if (ci_slab * 64 + c0 + j < p.C_in)
+              *reinterpret_cast<float4*>(dst + c0 + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                     __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
           }
         }
       }
@@ -182,60 +199,129 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constan
   }
 }
 
-}  // namespace
-
-int dt_encode_bf16_map(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                       const uint32_t* box, const uint32_t* elem_strides);
-
-extern "C" int dt_conv2d_wgrad_tc(const void* x, const void* gy, int N, int H, int W, int C_in, int C_out, float* dw_oihw,
-                                  dt_stream_t stream) {
-  DT_ARCH_GUARD();
-  DT_REQUIRE(N > 0 && H > 0 && W > 0 && C_in > 0 && C_out > 0, DT_ERR_BAD_SHAPE, "dt_conv2d_wgrad_tc: bad shape");
-  const bool rows_ok = (H % TH == 0) || (H == 8 && N % 2 == 0);
-  if (W % TW != 0 || !rows_ok || C_in % 8 != 0 || C_out % 8 != 0) {
-    dt_set_error("dt_conv2d_wgrad_tc: unsupported shape N=%d H=%d W=%d C_in=%d C_out=%d", N, H, W, C_in, C_out);
-    return DT_ERR_UNSUPPORTED;
+// dw[co][ci][tap] = sum over splits (fixed order) of partial[split][tap][co][ci]
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int RS, int C_out, int C_in,
+                                    float* __restrict__ dw) {
+  const int64_t plane = static_cast<int64_t>(C_out) * C_in;
+  const int64_t total = plane * RS;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t cc = i % plane;      // co * C_in + ci (ci fastest: coalesced reads)
+    const int tap = static_cast<int>(i / plane);
+    float acc = 0.f;
+    for (int s = 0; s < splits; ++s) acc += partial[(static_cast<int64_t>(s) * RS + tap) * plane + cc];
+    dw[cc * RS + tap] = acc;
   }
-  DT_REQUIRE((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(gy)) % 16 == 0, DT_ERR_BAD_ALIGN,
-             "dt_conv2d_wgrad_tc: tensors must be 16-byte aligned");
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
+}
+
+struct WgPlan {
   WgParams p;
-  memset(&p, 0, sizeof(p));
-  p.N = N; p.H = H; p.W = W; p.C_in = C_in; p.C_out = C_out;
-  p.th_img = H >= TH ? TH : H;
+  int splits;
+  bool ok;
+};
+
+WgPlan make_plan(int N, int Ho, int Wo, int C_in, int C_out, int ksize, int stride) {
+  WgPlan pl;
+  memset(&pl, 0, sizeof(pl));
+  WgParams& p = pl.p;
+  const bool rows_ok = (Ho % TH == 0) || (Ho == 8 && N % 2 == 0);
+  const bool kind_ok = (ksize == 3 && (stride == 1 || stride == 2)) || (ksize == 1 && stride == 2);
+  pl.ok = N > 0 && Wo > 0 && Wo % TW == 0 && rows_ok && kind_ok && C_in > 0 && C_out > 0 && C_in % 4 == 0;
+  if (!pl.ok) return pl;
+  p.N = N; p.H = Ho; p.W = Wo; p.C_in = C_in; p.C_out = C_out;
+  p.RS = ksize * ksize; p.stride = stride;
+  p.th_img = Ho >= TH ? TH : Ho;
   p.imgs = TH / p.th_img;
-  p.tiles_w = W / TW;
-  p.tiles_h = H / p.th_img;
+  p.tiles_w = Wo / TW;
+  p.tiles_h = Ho / p.th_img;
   p.total_tiles = p.tiles_w * p.tiles_h * (N / p.imgs);
   p.ci_slabs = (C_in + 63) / 64;
+  if (ksize == 3 && stride == 1) {
+    p.ngroups = 2;
+    for (int tap = 0; tap < 9; ++tap) {
+      WgGroup& g = p.grp[tap < 5 ? 0 : 1];
+      g.tap[g.ntaps] = tap;
+      g.off[g.ntaps] = (tap / 3) * PITCH + tap % 3;
+      ++g.ntaps;
+    }
+  } else if (ksize == 3) {      // stride 2: one group per parity plane of the input
+    p.ngroups = 4;
+    for (int tap = 0; tap < 9; ++tap) {
+      const int r = tap / 3, s = tap % 3;
+      const int pr = (r + 1) & 1, pc = (s + 1) & 1;
+      WgGroup& g = p.grp[pr * 2 + pc];
+      g.pr = pr; g.pc = pc;
+      g.tap[g.ntaps] = tap;
+      g.off[g.ntaps] = ((r - 1 - pr) / 2 + 1) * PITCH + (s - 1 - pc) / 2 + 1;
+      ++g.ntaps;
+    }
+  } else {                      // 1x1 / stride 2 / pad 0: plane (0, 0), window = the tile itself
+    p.ngroups = 1;
+    p.grp[0].ntaps = 1;
+    p.grp[0].tap[0] = 0;
+    p.grp[0].off[0] = PITCH + 1;
+  }
   const int co_blocks = (C_out + 127) / 128;
-  p.jobs = co_blocks * p.ci_slabs * 2;
+  p.jobs = co_blocks * p.ci_slabs * p.ngroups;
   p.patch_bytes = p.imgs * (p.th_img + 2) * PITCH * 128;
   int splits = (2 * dt_num_sms() + p.jobs - 1) / p.jobs;      // about two waves of CTAs
   if (splits > p.total_tiles) splits = p.total_tiles;
   if (splits < 1) splits = 1;
   p.tiles_per_cta = (p.total_tiles + splits - 1) / splits;
-  splits = (p.total_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
-  p.dw = dw_oihw;
-  DT_CUDA(cudaMemsetAsync(dw_oihw, 0, sizeof(float) * static_cast<size_t>(C_out) * C_in * 9, s));
+  pl.splits = (p.total_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
+  return pl;
+}
+
+}  // namespace
+
+int dt_encode_bf16_map(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                       const uint32_t* box, const uint32_t* elem_strides);
+
+extern "C" int64_t dt_conv2d_wgrad_tc_workspace(int N, int Ho, int Wo, int C_in, int C_out, int ksize, int stride) {
+  const WgPlan pl = make_plan(N, Ho, Wo, C_in, C_out, ksize, stride);
+  if (!pl.ok) return DT_ERR_UNSUPPORTED;
+  return static_cast<int64_t>(pl.splits) * pl.p.RS * C_out * C_in * static_cast<int64_t>(sizeof(float));
+}
+
+extern "C" int dt_conv2d_wgrad_tc(const void* x, const void* gy, int N, int Ho, int Wo, int C_in, int x_cstride, int C_out,
+                                  int gy_cstride, int ksize, int stride, float* dw_oihw, float* workspace,
+                                  int64_t workspace_bytes, dt_stream_t stream) {
+  DT_ARCH_GUARD();
+  WgPlan pl = make_plan(N, Ho, Wo, C_in, C_out, ksize, stride);
+  if (!pl.ok || x_cstride < C_in || gy_cstride < C_out || x_cstride % 8 != 0 || gy_cstride % 8 != 0) {
+    dt_set_error("dt_conv2d_wgrad_tc: unsupported shape N=%d Ho=%d Wo=%d C_in=%d C_out=%d k=%d s=%d", N, Ho, Wo, C_in, C_out,
+                 ksize, stride);
+    return DT_ERR_UNSUPPORTED;
+  }
+  WgParams& p = pl.p;
+  const int64_t need = static_cast<int64_t>(pl.splits) * p.RS * C_out * C_in * static_cast<int64_t>(sizeof(float));
+  DT_REQUIRE(workspace != nullptr && workspace_bytes >= need, DT_ERR_BAD_SHAPE,
+             "dt_conv2d_wgrad_tc: workspace of %lld bytes needed (dt_conv2d_wgrad_tc_workspace)", static_cast<long long>(need));
+  DT_REQUIRE((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(gy) | reinterpret_cast<uintptr_t>(workspace)) % 16 == 0,
+             DT_ERR_BAD_ALIGN, "dt_conv2d_wgrad_tc: tensors must be 16-byte aligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  p.partial = workspace;
+  const int Hi = Ho * stride, Wi = Wo * stride;
 
   CUtensorMap tm_g, tm_x;
   {
-    const uint64_t dims[4] = {static_cast<uint64_t>(C_out), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
+    const uint64_t dims[4] = {static_cast<uint64_t>(gy_cstride), static_cast<uint64_t>(Wo), static_cast<uint64_t>(Ho),
                               static_cast<uint64_t>(N)};
-    const uint64_t strides[3] = {static_cast<uint64_t>(C_out) * 2, static_cast<uint64_t>(W) * C_out * 2,
-                                 static_cast<uint64_t>(H) * W * C_out * 2};
+    const uint64_t strides[3] = {static_cast<uint64_t>(gy_cstride) * 2, static_cast<uint64_t>(Wo) * gy_cstride * 2,
+                                 static_cast<uint64_t>(Ho) * Wo * gy_cstride * 2};
     const uint32_t box[4] = {64, TW, static_cast<uint32_t>(p.th_img), static_cast<uint32_t>(p.imgs)};
     int rc = dt_encode_bf16_map(&tm_g, gy, 4, dims, strides, box, nullptr);
     if (rc != DT_OK) return rc;
   }
   {
-    const uint64_t dims[4] = {static_cast<uint64_t>(C_in), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
+    const uint32_t st = static_cast<uint32_t>(stride);
+    const uint64_t dims[4] = {static_cast<uint64_t>(x_cstride), static_cast<uint64_t>(Wi), static_cast<uint64_t>(Hi),
                               static_cast<uint64_t>(N)};
-    const uint64_t strides[3] = {static_cast<uint64_t>(C_in) * 2, static_cast<uint64_t>(W) * C_in * 2,
-                                 static_cast<uint64_t>(H) * W * C_in * 2};
-    const uint32_t box[4] = {64, PITCH, static_cast<uint32_t>(p.th_img + 2), static_cast<uint32_t>(p.imgs)};
-    int rc = dt_encode_bf16_map(&tm_x, x, 4, dims, strides, box, nullptr);
+    const uint64_t strides[3] = {static_cast<uint64_t>(x_cstride) * 2, static_cast<uint64_t>(Wi) * x_cstride * 2,
+                                 static_cast<uint64_t>(Hi) * Wi * x_cstride * 2};
+    const uint32_t box[4] = {64, PITCH * st, static_cast<uint32_t>(p.th_img + 2) * st, static_cast<uint32_t>(p.imgs)};
+    const uint32_t estr[4] = {1, st, st, 1};
+    int rc = dt_encode_bf16_map(&tm_x, x, 4, dims, strides, box, estr);
     if (rc != DT_OK) return rc;
   }
   constexpr int SMEM = STAGES * (A_STAGE + B_STAGE) + 1024 + 256;
@@ -245,7 +331,12 @@ extern "C" int dt_conv2d_wgrad_tc(const void* x, const void* gy, int N, int H, i
     attr_err = cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
   });
   DT_CUDA(attr_err);
-  conv_wgrad_kernel<<<p.jobs * splits, kThreads, SMEM, s>>>(tm_g, tm_x, p);
+  conv_wgrad_kernel<<<p.jobs * pl.splits, kThreads, SMEM, s>>>(tm_g, tm_x, p);
+  DT_LAUNCH_CHECK();
+  const int64_t total = static_cast<int64_t>(C_out) * C_in * p.RS;
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > dt_num_sms() * 8) blocks = dt_num_sms() * 8;
+  wgrad_reduce_kernel<<<static_cast<int>(blocks), 256, 0, s>>>(workspace, pl.splits, p.RS, C_out, C_in, dw_oihw);
   DT_LAUNCH_CHECK();
   return DT_OK;
 }

@@ -105,19 +105,29 @@ __global__ void channel_reduce_kernel(const T* __restrict__ y, const T* __restri
   }
 }
 
+// sum of the block partials of channel c (one warp per channel, fixed lane order -> deterministic)
+__device__ __forceinline__ void warp_channel_sums(const float* __restrict__ part, int nblocks, int C, int c, double& s, double& q) {
+  const int lane = threadIdx.x & 31;
+  s = 0.0; q = 0.0;
+  for (int b = lane; b < nblocks; b += 32) {
+    s += part[static_cast<int64_t>(b) * C + c];
+    q += part[(static_cast<int64_t>(nblocks) + b) * C + c];
+  }
+  s = warp_sum(s);
+  q = warp_sum(q);
+}
+
 // batch statistics -> (scale, shift) of the normalisation, saved (mean, invstd), running-stat update
 __global__ void bn_finalize_kernel(const float* __restrict__ part, int nblocks, int C, double M, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, float eps, float momentum,
                                    float* __restrict__ running_mean, float* __restrict__ running_var,
                                    float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
                                    float* __restrict__ invstd_out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (c >= C) return;
-  double s = 0.0, q = 0.0;
-  for (int b = 0; b < nblocks; ++b) {
-    s += part[static_cast<int64_t>(b) * C + c];
-    q += part[(static_cast<int64_t>(nblocks) + b) * C + c];
-  }
+  double s, q;
+  warp_channel_sums(part, nblocks, C, c, s, q);
+  if ((threadIdx.x & 31) != 0) return;
   const double mean = s / M;
   double var = q / M - mean * mean;
   if (var < 0.0) var = 0.0;
@@ -138,13 +148,11 @@ __global__ void bn_finalize_kernel(const float* __restrict__ part, int nblocks, 
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ part, int nblocks, int C, double M,
                                        float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ c1,
                                        float* __restrict__ c2) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (c >= C) return;
-  double s = 0.0, q = 0.0;
-  for (int b = 0; b < nblocks; ++b) {
-    s += part[static_cast<int64_t>(b) * C + c];
-    q += part[(static_cast<int64_t>(nblocks) + b) * C + c];
-  }
+  double s, q;
+  warp_channel_sums(part, nblocks, C, c, s, q);
+  if ((threadIdx.x & 31) != 0) return;
   dbeta[c] = static_cast<float>(s);
   dgamma[c] = static_cast<float>(q);
   c1[c] = static_cast<float>(s / M);
@@ -332,7 +340,8 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int N, int K, i
 // mode 0: fp32 [tap][C_in_p][C_out]                                   (direct forward; C_in_p >= C_in, zero padded)
 // mode 1: bf16 [C_out][Kpad], k = tap * C_in + ci                      (tcgen05 forward)
 // mode 2: bf16 [C_out][256],  k = r * 32 + s * 4 + ci                  (tcgen05 stem, C_in <= 4, 7x7)
-// mode 3: bf16 [C_in][Kpad],  k = (RS - 1 - tap) * C_out + co          (dgrad of a stride-1 conv run as a forward conv)
+// mode 3: bf16 [C_in][Kpad],  k = (RS - 1 - tap) * Cop + co            (dgrad of a stride-1 conv run as a forward conv)
+// mode 4: bf16 [C_in][Kpad],  k = tap * Cop + co                       (dgrad of a stride-2 conv, DT_CONV_TRANSPOSED)
 __global__ void pack_weight_kernel(const float* __restrict__ w, int C_out, int C_in, int R, int S, int mode, int C_in_p,
                                    int Kpad, void* __restrict__ out, int64_t total) {
   const int RS = R * S;
@@ -354,10 +363,13 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int C_out, int C
       float v = 0.f;
       if (r < R && s < S && ci < C_in) v = w[(static_cast<int64_t>(co) * C_in + ci) * RS + r * S + s];
       static_cast<__nv_bfloat16*>(out)[i] = __float2bfloat16_rn(v);
-    } else {
+    } else {   // modes 3 / 4: C_in_p = channel stride Cop of the gradient tensor (>= C_out)
       const int k = static_cast<int>(i % Kpad), ci = static_cast<int>(i / Kpad);
       float v = 0.f;
-      if (k < RS * C_out) { const int tf = k / C_out, co = k % C_out; v = w[(static_cast<int64_t>(co) * C_in + ci) * RS + (RS - 1 - tf)]; }
+      if (k < RS * C_in_p) {
+        const int tf = k / C_in_p, co = k % C_in_p;
+        if (co < C_out) v = w[(static_cast<int64_t>(co) * C_in + ci) * RS + (mode == 3 ? RS - 1 - tf : tf)];
+      }
       static_cast<__nv_bfloat16*>(out)[i] = __float2bfloat16_rn(v);
     }
   }
@@ -518,7 +530,7 @@ int dt_bn_train_stats(const void* y, int64_t M, int C, int dtype, const float* g
       (channel_reduce_kernel<float, 0><<<nb, kThreads, 0, s>>>(static_cast<const float*>(y), nullptr, nullptr, nullptr, nullptr, M, C, workspace)),
       (channel_reduce_kernel<__nv_bfloat16, 0><<<nb, kThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(y), nullptr, nullptr, nullptr, nullptr, M, C, workspace)));
   DT_LAUNCH_CHECK();
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(workspace, nb, C, static_cast<double>(M), gamma, beta, eps, momentum,
+  bn_finalize_kernel<<<(C + 7) / 8, 256, 0, s>>>(workspace, nb, C, static_cast<double>(M), gamma, beta, eps, momentum,
                                                      running_mean, running_var, scale, shift, mean, invstd);
   DT_LAUNCH_CHECK();
   return DT_OK;
@@ -554,7 +566,7 @@ int dt_bn_train_bwd(const void* g, const void* a, const void* y, int64_t M, int 
       (channel_reduce_kernel<float, 1><<<nb, kThreads, 0, s>>>(static_cast<const float*>(y), static_cast<const float*>(g), static_cast<const float*>(a), mean, invstd, M, C, workspace)),
       (channel_reduce_kernel<__nv_bfloat16, 1><<<nb, kThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(y), static_cast<const __nv_bfloat16*>(g), static_cast<const __nv_bfloat16*>(a), mean, invstd, M, C, workspace)));
   DT_LAUNCH_CHECK();
-  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(workspace, nb, C, static_cast<double>(M), dgamma, dbeta, c1, c2);
+  bn_bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, s>>>(workspace, nb, C, static_cast<double>(M), dgamma, dbeta, c1, c2);
   DT_LAUNCH_CHECK();
   DT_DTYPE_SWITCH(dtype,
       (bn_bwd_apply_kernel<float><<<grid_for(nvec), kThreads, 0, s>>>(static_cast<const float*>(g), static_cast<const float*>(a), static_cast<const float*>(y), mean, invstd, scale, c1, c2, nvec, C, static_cast<float*>(gy), static_cast<float*>(gz_out))),
@@ -636,10 +648,23 @@ int dt_nchw_to_nhwc(const float* x, int N, int K, int H, int W, int Kp, int dtyp
   return DT_OK;
 }
 
+int dt_channel_sum(const void* g, int64_t M, int C, int K, int dtype, float* out, dt_stream_t stream) {
+  DT_ARCH_GUARD();
+  DT_REQUIRE(M > 0 && C > 0 && K >= 1 && K <= 4 && K <= C && (dtype == DT_F32 || dtype == DT_BF16), DT_ERR_BAD_SHAPE,
+             "dt_channel_sum: M=%lld C=%d K=%d (K <= 4)", static_cast<long long>(M), C, K);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  DT_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * K, s));
+  DT_DTYPE_SWITCH(dtype,
+      (bias_grad_kernel<float><<<grid_for(M, 2), kThreads, 0, s>>>(static_cast<const float*>(g), M, C, K, out)),
+      (bias_grad_kernel<__nv_bfloat16><<<grid_for(M, 2), kThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(g), M, C, K, out)));
+  DT_LAUNCH_CHECK();
+  return DT_OK;
+}
+
 int dt_pack_conv_weight(const float* w_oihw, int C_out, int C_in, int R, int S, int mode, int C_in_p, int Kpad, void* out,
                         dt_stream_t stream) {
   DT_ARCH_GUARD();
-  DT_REQUIRE(C_out > 0 && C_in > 0 && R > 0 && S > 0 && mode >= 0 && mode <= 3, DT_ERR_BAD_SHAPE, "dt_pack_conv_weight: bad arguments");
+  DT_REQUIRE(C_out > 0 && C_in > 0 && R > 0 && S > 0 && mode >= 0 && mode <= 4, DT_ERR_BAD_SHAPE, "dt_pack_conv_weight: bad arguments");
   int64_t total = 0;
   if (mode == 0) {
     DT_REQUIRE(C_in_p >= C_in, DT_ERR_BAD_SHAPE, "dt_pack_conv_weight: C_in_p < C_in");
@@ -651,7 +676,7 @@ int dt_pack_conv_weight(const float* w_oihw, int C_out, int C_in, int R, int S, 
     DT_REQUIRE(Kpad == 256 && C_in <= 4 && R == 7 && S == 7, DT_ERR_BAD_SHAPE, "dt_pack_conv_weight: stem packing needs 7x7, C_in <= 4, Kpad 256");
     total = static_cast<int64_t>(C_out) * Kpad;
   } else {
-    DT_REQUIRE(Kpad >= R * S * C_out, DT_ERR_BAD_SHAPE, "dt_pack_conv_weight: Kpad too small");
+    DT_REQUIRE(C_in_p >= C_out && Kpad >= R * S * C_in_p, DT_ERR_BAD_SHAPE, "dt_pack_conv_weight: Cop / Kpad too small");
     total = static_cast<int64_t>(C_in) * Kpad;
   }
   pack_weight_kernel<<<grid_for(total), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(w_oihw, C_out, C_in, R, S, mode,

@@ -259,7 +259,12 @@ class SemSegment(_Base):  # type: ignore[misc]
     def configure_optimizers(self):
         from ..optim import FusedAdam
 
-        opt = FusedAdam(self.parameters(), lr=self.hparams.training.learning_rate)
+        # the reference leaves clipping to the Lightning trainer (configs/trainer/default.yaml:18, gradient_clip_val 0.5);
+        # without a trainer, `training.gradient_clip_val` folds the same global-norm clip into the fused Adam step
+        opt = FusedAdam(self.parameters(), lr=self.hparams.training.learning_rate,
+                        max_grad_norm=float(self.hparams.training.get("gradient_clip_val", 0.0) or 0.0))
+        if next(self.parameters()).is_cuda:
+            opt.attach_engine(self.model.train_engine())     # one flat clip + Adam launch per step
         sch = torch.optim.lr_scheduler.CosineAnnealingLR(opt, T_max=self.hparams.training.cosineannealing_tmax)
         return [opt], [sch]
 

@@ -158,11 +158,15 @@ def conv2d(x: torch.Tensor, w: torch.Tensor, scale: torch.Tensor, shift: torch.T
            out: Optional[torch.Tensor] = None, flags: int = 0, algo_cin: Optional[int] = None, tag: str = "") -> torch.Tensor:
     Ho = (H + 2 * pad - R) // stride + 1
     Wo = (W + 2 * pad - S) // stride + 1
+    if flags & _lib.CONV_TRANSPOSED:      # data gradient of a stride-2 conv: H, W are the output size, x is gy (N, Ho, Wo, C_in)
+        Hs, Ws, Ho, Wo = Ho, Wo, H, W
+    else:
+        Hs, Ws = Ho, Wo
     if out is None:
         out = torch.empty((N, Ho, Wo, C_out), dtype=x.dtype, device=x.device)
     d = ConvDesc(N, H, W, C_in, C_x, int(upsample), C_out, R, S, stride, pad, int(relu), int(residual is not None),
                  _dt(x), flags)
-    with _Timed("conv", 2.0 * N * Ho * Wo * C_out * (algo_cin or C_in) * R * S, tag):
+    with _Timed("conv", 2.0 * N * Hs * Ws * C_out * (algo_cin or C_in) * R * S, tag):
         check(load().dt_conv2d_fwd(C.byref(d), x.data_ptr(), ptr(skip), w.data_ptr(), scale.data_ptr(),
                                    shift.data_ptr(), ptr(residual), out.data_ptr(), stream_ptr()))
     return out
@@ -319,13 +323,16 @@ def bn_apply(y: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, residual
 
 
 def bn_train_bwd(g: torch.Tensor, a: Optional[torch.Tensor], y: torch.Tensor, mean: torch.Tensor, invstd: torch.Tensor,
-                 scale: torch.Tensor, want_gz: bool = False):
+                 scale: torch.Tensor, want_gz: bool = False, dgamma: Optional[torch.Tensor] = None,
+                 dbeta: Optional[torch.Tensor] = None):
     """-> (gy, gz or None, dgamma, dbeta)."""
     Cc = y.shape[-1]
     gy = torch.empty_like(y)
     gz = torch.empty_like(y) if want_gz else None
-    dgamma = torch.empty(Cc, dtype=torch.float32, device=y.device)
-    dbeta = torch.empty(Cc, dtype=torch.float32, device=y.device)
+    if dgamma is None:
+        dgamma = torch.empty(Cc, dtype=torch.float32, device=y.device)
+    if dbeta is None:
+        dbeta = torch.empty(Cc, dtype=torch.float32, device=y.device)
     check(load().dt_bn_train_bwd(g.data_ptr(), ptr(a), y.data_ptr(), y.numel() // Cc, Cc, _dt(y), mean.data_ptr(),
                                  invstd.data_ptr(), scale.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(),
                                  gy.data_ptr(), ptr(gz), _reduce_ws(y.device).data_ptr(), stream_ptr()))
@@ -373,9 +380,20 @@ def nchw_to_nhwc(x: torch.Tensor, Kp: int, dtype: torch.dtype) -> torch.Tensor:
     return out
 
 
-def pack_conv_weight(w: torch.Tensor, mode: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+def channel_sum(g: torch.Tensor, K: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """sum over all pixels of the first K channels of an NHWC tensor -> float (K,)."""
+    Cc = g.shape[-1]
+    if out is None:
+        out = torch.empty(K, dtype=torch.float32, device=g.device)
+    check(load().dt_channel_sum(g.data_ptr(), g.numel() // Cc, Cc, K, _dt(g), out.data_ptr(), stream_ptr()))
+    return out
+
+
+def pack_conv_weight(w: torch.Tensor, mode: int, out: Optional[torch.Tensor] = None,
+                     cout_pad: Optional[int] = None) -> torch.Tensor:
     """fp32 OIHW master weights -> kernel layout (see dt_pack_conv_weight): 0 direct fp32, 1 tcgen05 forward,
-    2 tcgen05 stem, 3 dgrad-as-forward."""
+    2 tcgen05 stem, 3 dgrad-as-forward (stride 1), 4 dgrad of a stride-2 conv (DT_CONV_TRANSPOSED).
+    cout_pad: channel stride of the gradient tensor for modes 3 / 4 (>= C_out)."""
     C_out, C_in, R, S = w.shape
     cinp, kpad = C_in, 0
     if mode == 0:
@@ -388,7 +406,8 @@ def pack_conv_weight(w: torch.Tensor, mode: int, out: Optional[torch.Tensor] = N
         kpad = 256
         shape, dtype = (C_out, kpad), torch.bfloat16
     else:
-        kpad = (R * S * C_out + 63) // 64 * 64
+        cinp = C_out if cout_pad is None else cout_pad
+        kpad = (R * S * cinp + 63) // 64 * 64
         shape, dtype = (C_in, kpad), torch.bfloat16
     if out is None:
         out = torch.empty(shape, dtype=dtype, device=w.device)
@@ -407,12 +426,13 @@ def conv2d_dgrad_direct(gy: torch.Tensor, w: torch.Tensor, x_shape, stride: int,
     return gx
 
 
-def conv2d_wgrad_direct(x: torch.Tensor, gy: torch.Tensor, w_shape, stride: int, pad: int, want_bias: bool = False):
+def conv2d_wgrad_direct(x: torch.Tensor, gy: torch.Tensor, w_shape, stride: int, pad: int, want_bias: bool = False,
+                        out: Optional[torch.Tensor] = None, bias_out: Optional[torch.Tensor] = None):
     """x (N, H, W, C_x), gy (N, Ho, Wo, C_out) -> dw fp32 OIHW (and dbias)."""
     N, H, W, Cx = x.shape
     C_out, C_in, R, S = w_shape
-    dw = torch.empty(tuple(w_shape), dtype=torch.float32, device=x.device)
-    db = torch.empty(C_out, dtype=torch.float32, device=x.device) if want_bias else None
+    dw = out if out is not None else torch.empty(tuple(w_shape), dtype=torch.float32, device=x.device)
+    db = bias_out if bias_out is not None else (torch.empty(C_out, dtype=torch.float32, device=x.device) if want_bias else None)
     check(load().dt_conv2d_wgrad_direct(x.data_ptr(), gy.data_ptr(), N, H, W, C_in, Cx, C_out, R, S, stride, pad, _dt(x),
                                         dw.data_ptr(), ptr(db), stream_ptr()))
     return dw, db
@@ -421,16 +441,25 @@ def conv2d_wgrad_direct(x: torch.Tensor, gy: torch.Tensor, w_shape, stride: int,
 def wgrad_tc_supported(x: torch.Tensor, gy: torch.Tensor, w_shape, stride: int, pad: int) -> bool:
     """True when the tcgen05 weight-gradient kernel covers this layer shape (dt_conv2d_wgrad_tc)."""
     C_out, C_in, R, S = w_shape
-    N, H, W, Cx = x.shape
-    return (x.dtype == torch.bfloat16 and R == 3 and S == 3 and stride == 1 and pad == 1 and Cx == C_in and W % 8 == 0
-            and (H % 16 == 0 or (H == 8 and N % 2 == 0)) and C_in % 8 == 0 and C_out % 8 == 0)
+    N, Ho, Wo, Cg = gy.shape
+    kind = (R == 3 and S == 3 and pad == 1 and stride in (1, 2)) or (R == 1 and S == 1 and pad == 0 and stride == 2)
+    return bool(x.dtype == torch.bfloat16 and kind and x.shape[1] == Ho * stride and x.shape[2] == Wo * stride
+                and Wo % 8 == 0 and (Ho % 16 == 0 or (Ho == 8 and N % 2 == 0)) and C_in % 4 == 0
+                and x.shape[-1] % 8 == 0 and Cg % 8 == 0 and x.shape[-1] >= C_in and Cg >= C_out)
 
 
-def conv2d_wgrad_tc(x: torch.Tensor, gy: torch.Tensor, w_shape) -> torch.Tensor:
-    """tensor-core weight gradient of a 3x3/s1/p1 conv: x (N, H, W, C_in), gy (N, H, W, C_out) bf16 -> dw fp32 OIHW."""
-    N, H, W, C_in = x.shape
-    C_out = gy.shape[-1]
-    dw = torch.empty(tuple(w_shape), dtype=torch.float32, device=x.device)
-    with _Timed("wgrad", 2.0 * N * H * W * C_out * C_in * 9):
-        check(load().dt_conv2d_wgrad_tc(x.data_ptr(), gy.data_ptr(), N, H, W, C_in, C_out, dw.data_ptr(), stream_ptr()))
+def conv2d_wgrad_tc(x: torch.Tensor, gy: torch.Tensor, w_shape, stride: int = 1,
+                    out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """tensor-core weight gradient: x (N, s*Ho, s*Wo, >=C_in), gy (N, Ho, Wo, >=C_out) bf16 -> dw fp32 OIHW."""
+    C_out, C_in, R, S = w_shape
+    N, Ho, Wo, Cg = gy.shape
+    lib = load()
+    need = lib.dt_conv2d_wgrad_tc_workspace(N, Ho, Wo, C_in, C_out, R, stride)
+    if need < 0:
+        raise _lib.DeadtreesB200Error(f"dt_conv2d_wgrad_tc does not support x {tuple(x.shape)} gy {tuple(gy.shape)} w {tuple(w_shape)}")
+    ws = torch.empty((need + 3) // 4, dtype=torch.float32, device=x.device)
+    dw = out if out is not None else torch.empty(tuple(w_shape), dtype=torch.float32, device=x.device)
+    with _Timed("wgrad", 2.0 * N * Ho * Wo * C_out * C_in * R * S, "wgrad"):
+        check(lib.dt_conv2d_wgrad_tc(x.data_ptr(), gy.data_ptr(), N, Ho, Wo, C_in, x.shape[-1], C_out, Cg, R, stride,
+                                     dw.data_ptr(), ws.data_ptr(), need, stream_ptr()))
     return dw

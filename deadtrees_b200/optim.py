@@ -8,11 +8,36 @@ from . import ops
 
 
 class FusedAdam(torch.optim.Optimizer):
+    """torch.optim.Adam semantics (no weight decay, no amsgrad) with the global-norm clip folded into the update.
+
+    Two paths: per-parameter launches (any parameter list), or - after :meth:`attach_engine` - ONE ``dt_sumsq`` and ONE
+    ``dt_adam_step`` over the train engine's flat parameter / gradient buffers."""
+
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, max_grad_norm: float = 0.0):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, max_grad_norm=max_grad_norm))
+        self._flat = None
+
+    def attach_engine(self, engine) -> "FusedAdam":
+        """use the flat buffers of a ``UnetTrainEngine`` (all of its parameters must be in this optimizer)."""
+        mine = {id(p) for g in self.param_groups for p in g["params"]}
+        if len(self.param_groups) != 1 or any(id(p) not in mine for p in engine.params.values()):
+            raise ValueError("attach_engine needs one param group holding every parameter of the engine")
+        fp = engine.flatten_parameters()
+        self._flat = dict(p=fp, g=engine.reducer.flat, m=torch.zeros_like(fp), v=torch.zeros_like(fp), step=0)
+        return self
 
     @torch.no_grad()
     def step(self, closure=None):
+        if self._flat is not None:
+            f, group = self._flat, self.param_groups[0]
+            f["step"] += 1
+            acc = None
+            if group["max_grad_norm"] > 0:
+                acc = torch.zeros((1,), dtype=torch.float64, device=f["p"].device)
+                ops.sumsq(f["g"], acc)
+            ops.adam_step(f["p"], f["g"], f["m"], f["v"], lr=group["lr"], beta1=group["betas"][0], beta2=group["betas"][1],
+                          eps=group["eps"], step=f["step"], sumsq_acc=acc, max_norm=group["max_grad_norm"])
+            return
         for group in self.param_groups:
             params = [p for p in group["params"] if p.grad is not None]
             acc = None

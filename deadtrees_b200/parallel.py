@@ -25,25 +25,34 @@ class GradBucketReducer:
         self.world = world_size if world_size is not None else (dist.get_world_size(group) if dist.is_initialized() else 1)
         self.device = torch.device(device)
         self.cuda = self.device.type == "cuda"
-        self.slots: Dict[str, Tuple[int, int, torch.Size]] = {}   # name -> (bucket, offset, shape)
+        self.slots: Dict[str, Tuple[int, int, torch.Size]] = {}   # name -> (bucket, offset inside the bucket, shape)
         sizes: List[int] = []
         cur, off = 0, 0
         for name, shape in named_shapes:
             n = int(torch.Size(shape).numel())
-            if off > 0 and (off + n) * 4 > bucket_bytes:
+            n_pad = (n + 3) // 4 * 4                               # keep every gradient 16-byte aligned
+            if off > 0 and (off + n_pad) * 4 > bucket_bytes:
                 sizes.append(off)
                 cur, off = cur + 1, 0
             self.slots[name] = (cur, off, torch.Size(shape))
-            off += n
+            off += n_pad
         sizes.append(off)
-        self.buckets = [torch.zeros(n, dtype=torch.float32, device=self.device) for n in sizes]
+        # ONE flat fp32 buffer holds every gradient in backward order; a bucket is a contiguous slice of it, so the
+        # optimizer can run a single fused clip + Adam launch over `flat`
+        self.flat = torch.zeros(sum(sizes), dtype=torch.float32, device=self.device)
+        self.bucket_offsets = [sum(sizes[:i]) for i in range(len(sizes))]
+        self.buckets = [self.flat[o: o + n] for o, n in zip(self.bucket_offsets, sizes)]
         self.expect = [0] * len(sizes)
         for b, _, _ in self.slots.values():
             self.expect[b] += 1
-        self.comm_stream = torch.cuda.Stream(device=self.device) if self.cuda else None
+        self.comm_stream = torch.cuda.Stream(device=self.device) if (self.cuda and self.world > 1) else None
         self._pending = [0] * len(sizes)
         self._works: List = []
         self.launched: List[int] = []          # bucket indices in launch order (observable by tests)
+
+    def flat_offset(self, name: str) -> int:
+        b, off, _ = self.slots[name]
+        return self.bucket_offsets[b] + off
 
     def begin(self) -> None:
         self._pending = list(self.expect)
@@ -54,9 +63,13 @@ class GradBucketReducer:
         return self.buckets[b][off: off + shape.numel()].view(shape)
 
     def add(self, name: str, grad: torch.Tensor) -> None:
-        """called by the backward engine right after the kernel producing `grad` has been launched."""
-        b, _, _ = self.slots[name]
+        """copy a finished gradient into its slot (callers that cannot write into ``view(name)`` directly)."""
         self.view(name).copy_(grad)
+        self.mark(name)
+
+    def mark(self, name: str) -> None:
+        """called by the backward engine right after the kernel writing ``view(name)`` has been launched."""
+        b, _, _ = self.slots[name]
         self._pending[b] -= 1
         if self._pending[b] == 0:
             self._launch(b)

@@ -15,8 +15,9 @@ from typing import Dict, List, Optional
 import torch
 
 from . import ops
-from ._lib import require_device
+from ._lib import CONV_TRANSPOSED, require_device
 from .engine import RESNET34_LAYERS, RESNET34_PLANES
+from .parallel import GradBucketReducer, backward_param_order
 
 BN_EPS, BN_MOMENTUM = 1e-5, 0.1
 
@@ -50,10 +51,33 @@ class UnetTrainEngine:
         # when a list, every kernel-level operation appends (kind, name, inputs..., outputs...) so tests can check
         # each op of the real pipeline against the oracle on the SAME inputs (layer-wise, teacher-forced parity)
         self.trace: Optional[List] = None
+        # every parameter gradient is written straight into one flat fp32 buffer laid out in backward order; with a
+        # process group its buckets are all-reduced on a side stream while the backward pass continues
+        self.reducer: Optional[GradBucketReducer] = None
+        self.set_process_group(None, world_size=1)
+
+    def set_process_group(self, group, world_size: Optional[int] = None, bucket_bytes: int = 25 << 20) -> None:
+        order = backward_param_order(self.param_names)
+        self.reducer = GradBucketReducer([(n, self.params[n].shape) for n in order], self.device, bucket_bytes=bucket_bytes,
+                                         group=group, world_size=world_size)
 
     def _rec(self, kind: str, name: str, **tensors) -> None:
         if self.trace is not None:
             self.trace.append((kind, name, tensors))
+
+    def flatten_parameters(self) -> torch.Tensor:
+        """re-points every parameter into ONE flat fp32 buffer with the layout of the flat gradient buffer, so the
+        optimizer is a single fused clip + Adam launch (``FusedAdam.attach_engine``).  Idempotent."""
+        if getattr(self, "flat_params", None) is None or self.flat_params.numel() != self.reducer.flat.numel():
+            flat = torch.zeros_like(self.reducer.flat)
+            with torch.no_grad():
+                for n, p in self.params.items():
+                    off = self.reducer.flat_offset(n)
+                    v = flat[off: off + p.numel()].view(p.shape)
+                    v.copy_(p.data)
+                    p.data = v
+            self.flat_params = flat
+        return self.flat_params
 
     # ---- forward pieces --------------------------------------------------------------------------------
     def _conv_raw(self, x: torch.Tensor, wname: str, stride: int, pad: int) -> torch.Tensor:
@@ -126,29 +150,42 @@ class UnetTrainEngine:
 
     # ---- backward pieces -------------------------------------------------------------------------------
     def _dgrad(self, gy: torch.Tensor, wname: str, x_shape, stride: int, pad: int,
-               addend: Optional[torch.Tensor] = None) -> torch.Tensor:
+               addend: Optional[torch.Tensor] = None, fp32_weights: bool = False) -> torch.Tensor:
+        """data gradient: gy (N, Ho, Wo, Cg >= C_out) -> gx of shape x_shape (+ addend)."""
         w = self.params[wname]
         C_out, C_in, R, S = w.shape
         N, H, W, Cx = x_shape
-        if (self.precision == "bf16" and self.dgrad_tc and R == 3 and S == 3 and stride == 1 and pad == 1 and
-                C_in % 16 == 0 and C_out % 16 == 0 and Cx == C_in):
+        Cg = gy.shape[-1]
+        tc = self.precision == "bf16" and self.dgrad_tc and not fp32_weights and Cx == C_in and C_in % 16 == 0
+        if tc and R == 3 and S == 3 and stride == 1 and pad == 1 and Cg % 16 == 0:
             # the data gradient of a stride-1 conv is a stride-1 conv of gy with the flipped, transposed weights
-            wp = ops.pack_conv_weight(w, 3)
-            gx = ops.conv2d(gy, wp, self._ones, self._zeros, N=N, H=H, W=W, C_in=C_out, C_x=C_out, C_out=C_in, R=3,
-                            S=3, stride=1, pad=1, relu=False, residual=addend, tag="dgrad." + wname)
+            wp = ops.pack_conv_weight(w, 3, cout_pad=Cg)
+            gx = ops.conv2d(gy, wp, self._ones, self._zeros, N=N, H=H, W=W, C_in=Cg, C_x=Cg, C_out=C_in, R=3, S=3, stride=1,
+                            pad=1, relu=False, residual=addend, tag="dgrad." + wname)
+        elif tc and stride == 2 and ((R == 3 and pad == 1) or (R == 1 and pad == 0)) and Cg % 64 == 0 and Cg == C_out:
+            # stride-2 conv: every output pixel gathers the taps whose source coordinate is even (gather producer)
+            wp = ops.pack_conv_weight(w, 4, cout_pad=Cg)
+            gx = ops.conv2d(gy, wp, self._ones, self._zeros, N=N, H=H, W=W, C_in=Cg, C_x=Cg, C_out=C_in, R=R, S=S, stride=2,
+                            pad=pad, relu=False, residual=addend, flags=CONV_TRANSPOSED, tag="dgrad." + wname)
         else:
             gx = ops.conv2d_dgrad_direct(gy, w, x_shape, stride, pad, addend=addend,
-                                         round_weights=self.precision == "bf16")
-        self._rec("dgrad", wname, gy=gy, addend=addend, gx=gx, stride=stride, pad=pad)
+                                         round_weights=self.precision == "bf16" and not fp32_weights)
+        self._rec("dgrad", wname, gy=gy, addend=addend, gx=gx, stride=stride, pad=pad, fp32_weights=fp32_weights)
         return gx
 
     def _wgrad(self, x: torch.Tensor, gy: torch.Tensor, wname: str, stride: int, pad: int, want_bias: bool = False):
         w = self.params[wname]
-        C_out, C_in, R, S = w.shape
-        if (self.precision == "bf16" and self.wgrad_tc and not want_bias and ops.wgrad_tc_supported(x, gy, w.shape, stride, pad)):
-            dw, db = ops.conv2d_wgrad_tc(x, gy, w.shape), None
+        out = self.reducer.view(wname)
+        bname = wname[:-len("weight")] + "bias"
+        if self.precision == "bf16" and self.wgrad_tc and ops.wgrad_tc_supported(x, gy, w.shape, stride, pad):
+            dw = ops.conv2d_wgrad_tc(x, gy, w.shape, stride, out=out)
+            db = ops.channel_sum(gy, w.shape[0], out=self.reducer.view(bname)) if want_bias else None
         else:
-            dw, db = ops.conv2d_wgrad_direct(x, gy, w.shape, stride, pad, want_bias=want_bias)
+            dw, db = ops.conv2d_wgrad_direct(x, gy, w.shape, stride, pad, want_bias=want_bias, out=out,
+                                             bias_out=self.reducer.view(bname) if want_bias else None)
+        self.reducer.mark(wname)
+        if want_bias:
+            self.reducer.mark(bname)
         self._rec("wgrad", wname, x=x, gy=gy, dw=dw, db=db, stride=stride, pad=pad)
         return dw, db
 
@@ -156,7 +193,10 @@ class UnetTrainEngine:
                      need_dx: bool = True, addend: Optional[torch.Tensor] = None):
         """g = dL/d(a) -> (dL/d(x) (+ addend), gz); fills grads for the conv weight and the BN affine pair."""
         gy, gz, dgamma, dbeta = ops.bn_train_bwd(g, e.a if e.relu else None, e.y, e.mean, e.invstd, e.scale,
-                                                 want_gz=want_gz)
+                                                 want_gz=want_gz, dgamma=self.reducer.view(e.bn + ".weight"),
+                                                 dbeta=self.reducer.view(e.bn + ".bias"))
+        self.reducer.mark(e.bn + ".weight")
+        self.reducer.mark(e.bn + ".bias")
         grads[e.bn + ".weight"], grads[e.bn + ".bias"] = dgamma, dbeta
         self._rec("bn_bwd", e.bn, g=g, a=e.a if e.relu else None, y=e.y, mean=e.mean, invstd=e.invstd, scale=e.scale,
                   gy=gy, gz=gz, dgamma=dgamma, dbeta=dbeta)
@@ -166,17 +206,18 @@ class UnetTrainEngine:
 
     def backward(self, tape: List, grad_logits: torch.Tensor) -> Dict[str, torch.Tensor]:
         grads: Dict[str, torch.Tensor] = {}
+        self.reducer.begin()
         it = list(tape)
         kind, d4 = it.pop()
         assert kind == "head"
         hw = self.params["segmentation_head.0.weight"]
         K = hw.shape[0]
-        g = ops.nchw_to_nhwc(grad_logits, K, self.act_dtype)
+        # bf16 mode: the logits gradient is stored with 16 channels (3 real) so the head runs on the tensor-core kernels
+        tc_head = self.precision == "bf16" and self.wgrad_tc and self.dgrad_tc
+        g = ops.nchw_to_nhwc(grad_logits, 16 if tc_head else K, self.act_dtype)
         dw, db = self._wgrad(d4, g, "segmentation_head.0.weight", 1, 1, want_bias=True)
         grads["segmentation_head.0.weight"], grads["segmentation_head.0.bias"] = dw, db
-        gh = g
-        g = ops.conv2d_dgrad_direct(gh, hw, d4.shape, 1, 1)          # the head keeps fp32 weights
-        self._rec("dgrad", "segmentation_head.0.weight", gy=gh, addend=None, gx=g, stride=1, pad=1, fp32_weights=True)
+        g = self._dgrad(g, "segmentation_head.0.weight", d4.shape, 1, 1, fp32_weights=not tc_head)
         # decoder, last block first
         g_skip: Dict[int, torch.Tensor] = {}
         for i in reversed(range(5)):
@@ -213,7 +254,7 @@ class UnetTrainEngine:
         e0 = it.pop()
         self._conv_bn_bwd(e0, g, grads, need_dx=False)
         assert not it
-        return grads
+        return self.reducer.finish()      # joins the all-reduce stream; views into the flat gradient buffer
 
 
 class _UnetTrainFn(torch.autograd.Function):
@@ -227,10 +268,14 @@ class _UnetTrainFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_logits):
+        """runs the CUDA backward pass; parameter gradients are views into the engine's flat gradient buffer and are
+        assigned to ``.grad`` here (each backward OVERWRITES them - zero_grad / accumulation is not needed or supported)."""
         eng = ctx.engine
         grads = eng.backward(ctx.tape, grad_logits.contiguous().float())
         ctx.tape = None
-        return (None, None) + tuple(grads[n] for n in eng.param_names)
+        for n in eng.param_names:
+            eng.params[n].grad = grads[n]
+        return (None, None) + (None,) * len(eng.param_names)
 
 
 def unet_train_forward(engine: UnetTrainEngine, x: torch.Tensor) -> torch.Tensor:

@@ -118,8 +118,12 @@ enum {
   DT_CONV_FORCE_DIRECT = 2, /* CUDA-core direct kernel for bf16 tensors (debug/validation) */
   DT_CONV_X_PAD3 = 8,       /* 7x7 stem: x is a zero-bordered (N, H+6, W+8, 4) frame (see dt_tile_gather_normalize);
                                im2col through a TMA tensor map with overlapping strides (conv_stem.cu) */
-  DT_CONV_NO_HALO = 4       /* 3x3/s1 layers: per-tap TMA boxes (conv_tc.cu) instead of the smem-resident halo
+  DT_CONV_NO_HALO = 4,      /* 3x3/s1 layers: per-tap TMA boxes (conv_tc.cu) instead of the smem-resident halo
                                patches (conv_halo.cu, the default where the shape fits) */
+  DT_CONV_TRANSPOSED = 16   /* data gradient of a stride-2 conv: desc.H, W = size of the OUTPUT (the conv's input), x = gy
+                               (N, Ho, Wo, C_in) at the conv's output size, out[h][w] = sum over taps with (h + pad - r)
+                               even of gy[(h + pad - r) / 2][..] * w; weights in the dt_conv2d_fwd packing with
+                               k = (r*S + s) * C_in + c (dt_pack_conv_weight mode 4) */
 };
 
 int dt_conv2d_fwd(const dt_conv_desc* desc, const void* x, const void* skip, const void* w, const float* scale,
@@ -219,9 +223,12 @@ int dt_upsample_concat_bwd(const void* g_cat, int N, int H, int W, int Cx, int C
                            dt_stream_t stream);
 /* (N, K, H, W) fp32 -> (N, H, W, Kp) `dtype`, channels >= K zero (gradient of the logits into the head backward) */
 int dt_nchw_to_nhwc(const float* x, int N, int K, int H, int W, int Kp, int dtype, void* out, dt_stream_t stream);
+/* out[k] = sum over the M pixels of g[pixel][k] for k < K (g: (M, C) NHWC rows) — the bias gradient of the head */
+int dt_channel_sum(const void* g, int64_t M, int C, int K, int dtype, float* out, dt_stream_t stream);
 /* fp32 OIHW master weights -> kernel layouts.  mode 0: float [tap][C_in_p][C_out]; 1: bf16 [C_out][Kpad]
- * (dt_conv2d_fwd); 2: bf16 stem packing [C_out][256]; 3: bf16 [C_in][Kpad], k = (R*S-1-tap)*C_out + co — the
- * weights with which dt_conv2d_fwd computes the data gradient of a stride-1 convolution. */
+ * (dt_conv2d_fwd); 2: bf16 stem packing [C_out][256]; 3: bf16 [C_in][Kpad], k = (R*S-1-tap)*Cop + co — the
+ * weights with which dt_conv2d_fwd computes the data gradient of a stride-1 convolution; 4: the same without the tap
+ * flip, k = tap*Cop + co (DT_CONV_TRANSPOSED).  Modes 3 / 4 take Cop (>= C_out, channel stride of gy) in `C_in_p`. */
 int dt_pack_conv_weight(const float* w_oihw, int C_out, int C_in, int R, int S, int mode, int C_in_p, int Kpad, void* out,
                         dt_stream_t stream);
 /* Generic (CUDA-core) data / weight gradients of conv2d, any stride: fp32 check mode and the layer shapes the
@@ -234,10 +241,16 @@ int dt_conv2d_dgrad_direct(const void* gy, const float* w_oihw, const void* adde
 int dt_conv2d_wgrad_direct(const void* x, const void* gy, int N, int H, int W, int C_in, int C_x, int C_out, int R, int S,
                            int stride, int pad, int dtype, float* dw_oihw, float* dbias, dt_stream_t stream);
 
-/* Weight gradient of a 3x3 / stride-1 / pad-1 convolution on the tensor cores (bf16 NHWC x (N, H, W, C_in) and
- * gy (N, H, W, C_out), fp32 accumulation in TMEM, dw fp32 OIHW overwritten).  Needs W % 8 == 0, H % 16 == 0 (or H == 8
- * with N even) and channel counts that are multiples of 8; returns DT_ERR_UNSUPPORTED otherwise (use the direct kernel). */
-int dt_conv2d_wgrad_tc(const void* x, const void* gy, int N, int H, int W, int C_in, int C_out, float* dw_oihw,
+/* Weight gradient on the tensor cores (tcgen05, MN-major operands straight from the NHWC tensors, fp32 accumulation in
+ * TMEM, deterministic split reduction): 3x3 / pad 1 with stride 1 or 2, and 1x1 / stride 2 / pad 0.
+ * x (N, stride*Ho, stride*Wo, x_cstride) and gy (N, Ho, Wo, gy_cstride) bf16 with C_in <= x_cstride, C_out <= gy_cstride real
+ * channels (channels beyond them must be zero or are ignored); dw fp32 OIHW (C_out, C_in, k, k) overwritten.
+ * Needs Wo % 8 == 0, Ho % 16 == 0 (or Ho == 8 with N even), C_in % 4 == 0, channel strides multiples of 8;
+ * returns DT_ERR_UNSUPPORTED otherwise (use the direct kernel).  workspace: dt_conv2d_wgrad_tc_workspace() bytes
+ * (that function returns DT_ERR_UNSUPPORTED for unsupported shapes). */
+int64_t dt_conv2d_wgrad_tc_workspace(int N, int Ho, int Wo, int C_in, int C_out, int ksize, int stride);
+int dt_conv2d_wgrad_tc(const void* x, const void* gy, int N, int Ho, int Wo, int C_in, int x_cstride, int C_out,
+                       int gy_cstride, int ksize, int stride, float* dw_oihw, float* workspace, int64_t workspace_bytes,
                        dt_stream_t stream);
 
 /* ---- O1: optimizer ------------------------------------------------------------------------------

@@ -20,7 +20,7 @@ def lib():
 
 def declared_symbols():
     text = (ROOT / "include" / "deadtrees_b200.h").read_text()
-    return sorted(set(re.findall(r"^\s*int\s+(dt_\w+)\s*\(", text, flags=re.M)))
+    return sorted(set(re.findall(r"^\s*(?:int|int64_t)\s+(dt_\w+)\s*\(", text, flags=re.M)))
 
 
 def test_header_and_binding_agree(lib):

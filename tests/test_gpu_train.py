@@ -246,21 +246,39 @@ def test_training_step_bf16_matches_bf16_arithmetic():
     assert worst[1][1] > 0.5, worst
 
 
-@pytest.mark.parametrize("cin,cout,N,H,W", [(64, 64, 2, 16, 8), (64, 128, 2, 32, 16), (128, 64, 1, 16, 16), (256, 256, 4, 8, 8),
-                                            (192, 64, 1, 16, 24), (16, 16, 1, 32, 32), (32, 16, 2, 16, 16), (128, 32, 1, 16, 8),
-                                            (512, 512, 2, 8, 8)])
-def test_wgrad_tensor_core(cin, cout, N, H, W):
-    """tcgen05 weight gradient (MN-major operands straight from NHWC) against torch autograd on the bf16-rounded operands."""
-    g = torch.Generator().manual_seed(cin + cout + H)
-    x = torch.randn(N, cin, H, W, generator=g).to(torch.bfloat16).float()
+@pytest.mark.parametrize("cin,cout,N,H,W,k,stride", [
+    (64, 64, 2, 16, 8, 3, 1), (64, 128, 2, 32, 16, 3, 1), (128, 64, 1, 16, 16, 3, 1), (256, 256, 4, 8, 8, 3, 1),
+    (192, 64, 1, 16, 24, 3, 1), (16, 16, 1, 32, 32, 3, 1), (32, 16, 2, 16, 16, 3, 1), (128, 32, 1, 16, 8, 3, 1),
+    (512, 512, 2, 8, 8, 3, 1), (64, 128, 2, 16, 16, 3, 2), (256, 512, 2, 8, 8, 3, 2), (128, 256, 1, 16, 8, 3, 2),
+    (64, 128, 2, 16, 16, 1, 2), (256, 512, 4, 8, 8, 1, 2)])
+def test_wgrad_tensor_core(cin, cout, N, H, W, k, stride):
+    """tcgen05 weight gradient (MN-major operands straight from NHWC; H, W = output size) against torch autograd on the
+    bf16-rounded operands: 3x3 stride 1 / 2 and the 1x1 stride-2 downsample."""
+    g = torch.Generator().manual_seed(cin + cout + H + k + stride)
+    pad = 1 if k == 3 else 0
+    x = torch.randn(N, cin, H * stride, W * stride, generator=g).to(torch.bfloat16).float()
     gy = torch.randn(N, cout, H, W, generator=g).to(torch.bfloat16).float()
-    w = torch.zeros(cout, cin, 3, 3, requires_grad=True)
-    F.conv2d(x, w, None, 1, 1).backward(gy)
-    assert ops.wgrad_tc_supported(nhwc(x, torch.bfloat16), nhwc(gy, torch.bfloat16), w.shape, 1, 1)
-    dw = ops.conv2d_wgrad_tc(nhwc(x, torch.bfloat16), nhwc(gy, torch.bfloat16), w.shape)
+    w = torch.zeros(cout, cin, k, k, requires_grad=True)
+    F.conv2d(x, w, None, stride, pad).backward(gy)
+    assert ops.wgrad_tc_supported(nhwc(x, torch.bfloat16), nhwc(gy, torch.bfloat16), w.shape, stride, pad)
+    dw = ops.conv2d_wgrad_tc(nhwc(x, torch.bfloat16), nhwc(gy, torch.bfloat16), w.shape, stride)
     torch.cuda.synchronize()
-    err, rel = report(f"wgrad tcgen05 {cin}->{cout} N={N} {H}x{W}", dw.cpu(), w.grad)
+    err, rel = report(f"wgrad tcgen05 {cin}->{cout} k{k}s{stride} N={N} {H}x{W}", dw.cpu(), w.grad)
     assert rel < 1e-4
+
+
+def test_wgrad_tensor_core_padded_channels():
+    """the head's shape: 3 real gradient channels stored in a 16-channel NHWC tensor."""
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 16, 32, 32, generator=g).to(torch.bfloat16).float()
+    gy = torch.randn(2, 3, 32, 32, generator=g).to(torch.bfloat16).float()
+    w = torch.zeros(3, 16, 3, 3, requires_grad=True)
+    F.conv2d(x, w, None, 1, 1).backward(gy)
+    gp = torch.zeros(2, 16, 32, 32)
+    gp[:, :3] = gy
+    dw = ops.conv2d_wgrad_tc(nhwc(x, torch.bfloat16), nhwc(gp, torch.bfloat16), w.shape, 1)
+    torch.cuda.synchronize()
+    assert report("wgrad tcgen05 head 16->3", dw.cpu(), w.grad)[1] < 1e-4
 
 
 @pytest.mark.parametrize("cin,cout,N,H", [(64, 64, 2, 32), (192, 64, 1, 16), (32, 16, 1, 32), (768, 256, 2, 16)])
@@ -347,15 +365,16 @@ def test_training_step_layerwise_teacher_forced(precision, n, T):
         elif kind == "wgrad":
             w = params[name]
             x = cpu(t["x"])[:, : w.shape[1]]
-            dw = torch.nn.grad.conv2d_weight(x, w.shape, cpu(t["gy"]), t["stride"], t["pad"])
+            gyc = cpu(t["gy"])[:, : w.shape[0]]          # the head's gradient is stored with padded channels
+            dw = torch.nn.grad.conv2d_weight(x, w.shape, gyc, t["stride"], t["pad"])
             note("wgrad", _rel(t["dw"].cpu(), dw)); assert worst["wgrad"] < acc_tol, name
             if t["db"] is not None:
-                note("bias grad", _rel(t["db"].cpu(), cpu(t["gy"]).sum((0, 2, 3)))); assert worst["bias grad"] < acc_tol
+                note("bias grad", _rel(t["db"].cpu(), gyc.sum((0, 2, 3)))); assert worst["bias grad"] < acc_tol
         elif kind == "dgrad":
             w = params[name]
             gx_shape = (t["gx"].shape[0], w.shape[1], t["gx"].shape[1], t["gx"].shape[2])
             wr = w if t.get("fp32_weights") else rw(w)
-            gx = torch.nn.grad.conv2d_input(gx_shape, wr, cpu(t["gy"]), t["stride"], t["pad"])
+            gx = torch.nn.grad.conv2d_input(gx_shape, wr, cpu(t["gy"])[:, : w.shape[0]], t["stride"], t["pad"])
             if t["addend"] is not None:
                 gx = gx + cpu(t["addend"])[:, : w.shape[1]]
             note("dgrad", _rel(cpu(t["gx"])[:, : w.shape[1]], gx)); assert worst["dgrad"] < act_tol, name
@@ -381,3 +400,55 @@ def test_training_step_layerwise_teacher_forced(precision, n, T):
     assert sum(1 for k, _, _ in trace if k == "wgrad") == 47 and sum(1 for k, _, _ in trace if k == "dgrad") == 46
     print(f"[train {precision} layerwise T={T}] worst relative errors per op kind: " +
           ", ".join(f"{k}={v:.2e}" for k, v in sorted(worst.items())))
+
+
+def test_flat_adam_path_equals_per_parameter_path():
+    """`configure_optimizers` (flat clip + Adam over the engine's buffers) updates exactly like the per-parameter launches."""
+    cin, n, T = 4, 2, 64
+    oracle = oracle_model(cin, 3)
+    img, mask = _batch(n, cin, T, 3)
+    batch = {"main": (img.cuda(), mask.cuda(), None, torch.zeros(n), [{"file": f"t{i}"} for i in range(n)])}
+    segs = []
+    for flat in (False, True):
+        net = dict(NETWORK, in_channels=cin, precision="fp32")
+        seg = SemSegment(net, dict(TRAINING, gradient_clip_val=0.5))
+        seg.model.load_state_dict(oracle.state_dict())
+        seg.cuda().train()
+        if flat:
+            (opt,), _ = seg.configure_optimizers()
+        else:
+            opt = FusedAdam(seg.model.parameters(), lr=3e-4, max_grad_norm=0.5)
+        for _ in range(2):
+            seg.training_step(batch, 0).backward()
+            opt.step()
+        segs.append(seg)
+    torch.cuda.synchronize()
+    for (name, p), (_, q) in zip(segs[0].model.named_parameters(), segs[1].model.named_parameters()):
+        # two Adam steps of 3e-4; fp32 atomics in the generic wgrad make the gradients differ in the last bits
+        assert (p.detach() - q.detach()).abs().max().item() < 2e-5, name
+    # the flattened parameters still serve the inference engine
+    segs[1].eval()
+    with torch.no_grad():
+        out = segs[1].model(img.cuda())
+    assert out.shape == (n, 3, T, T) and torch.isfinite(out).all()
+
+
+@pytest.mark.parametrize("cin,cout,k,N,H", [(64, 128, 3, 2, 32), (256, 512, 3, 2, 16), (128, 256, 1, 1, 32), (64, 128, 1, 2, 16)])
+def test_dgrad_stride2_gather_kernel(cin, cout, k, N, H):
+    """data gradient of the stride-2 convs (3x3 pad 1, 1x1 pad 0) through the tcgen05 gather producer (DT_CONV_TRANSPOSED)."""
+    from deadtrees_b200._lib import CONV_TRANSPOSED
+    g = torch.Generator().manual_seed(cin + cout + k)
+    pad = 1 if k == 3 else 0
+    x = torch.zeros(N, cin, H, H, requires_grad=True)
+    w = torch.randn(cout, cin, k, k, generator=g) * 0.05
+    gy = torch.randn(N, cout, H // 2, H // 2, generator=g).to(torch.bfloat16).float()
+    F.conv2d(x, w.to(torch.bfloat16).float(), None, 2, pad).backward(gy)
+    add = torch.randn(N, cin, H, H, generator=g).to(torch.bfloat16).float()
+    wp = ops.pack_conv_weight(w.cuda(), 4)
+    ones, zeros = torch.ones(cin, device="cuda"), torch.zeros(cin, device="cuda")
+    gx = ops.conv2d(nhwc(gy, torch.bfloat16), wp, ones, zeros, N=N, H=H, W=H, C_in=cout, C_x=cout, C_out=cin, R=k, S=k,
+                    stride=2, pad=pad, relu=False, residual=nhwc(add, torch.bfloat16), flags=CONV_TRANSPOSED)
+    torch.cuda.synchronize()
+    assert gx.shape == (N, H, H, cin)
+    err, rel = report(f"dgrad s2 k{k} {cin}<-{cout}", nchw(gx), x.grad + add)
+    assert rel < 1e-2

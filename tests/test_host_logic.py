@@ -162,3 +162,67 @@ def test_halo_exchange_gloo(world, tmp_path):
     """the N>1 path on CPU: every shard receives the previous shard's boundary logits rows."""
     port = 29500 + (os.getpid() % 2000) + world
     mp.spawn(_halo_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+
+
+# ---- data-parallel training: bucketed gradient all-reduce (deadtrees_b200/parallel.py) ----------------------------
+
+def _param_shapes():
+    """parameter names / shapes of the Unet without building tensors on a GPU."""
+    from deadtrees_b200.network.unet import Unet
+    m = Unet(in_channels=4, classes=3)
+    return [(n, p.shape) for n, p in m.named_parameters()]
+
+
+def test_backward_param_order_and_buckets():
+    from deadtrees_b200.parallel import GradBucketReducer, backward_param_order
+    shapes = dict(_param_shapes())
+    order = backward_param_order(list(shapes))
+    assert sorted(order) == sorted(shapes) and len(order) == len(shapes)
+    assert order[0].startswith("segmentation_head") and order[-1] in ("encoder.conv1.weight", "encoder.bn1.weight", "encoder.bn1.bias")
+    first = {k: i for i, k in enumerate(order)}
+    assert first["decoder.blocks.4.conv2.0.weight"] < first["decoder.blocks.4.conv1.0.weight"] < first["decoder.blocks.0.conv1.0.weight"]
+    assert first["decoder.blocks.0.conv1.0.weight"] < first["encoder.layer4.2.conv2.weight"] < first["encoder.layer4.0.downsample.0.weight"]
+    assert first["encoder.layer4.0.downsample.0.weight"] < first["encoder.layer3.5.conv2.weight"] < first["encoder.layer1.0.conv1.weight"]
+    red = GradBucketReducer([(n, shapes[n]) for n in order], "cpu", bucket_bytes=25 << 20, world_size=1)
+    assert red.flat.numel() >= sum(s.numel() for s in shapes.values())
+    assert len(red.buckets) == 5                      # 24.44 M fp32 parameters (97.8 MB) in buckets of at most 25 MiB
+    for n in order:                                   # every slot 16-byte aligned, disjoint, inside its bucket
+        assert red.flat_offset(n) % 4 == 0
+    red.begin()
+    for n in order:
+        red.view(n).fill_(1.0)
+        red.mark(n)
+    assert red.launched == [0, 1, 2, 3, 4]            # buckets complete in backward order
+    out = red.finish()
+    assert all(float(out[n].sum()) == shapes[n].numel() for n in order)
+    red.begin()
+    red.mark(order[0])
+    with pytest.raises(RuntimeError):
+        red.finish()
+
+
+def _reducer_worker(rank, world, port):
+    from deadtrees_b200.parallel import GradBucketReducer
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    shapes = [("a", torch.Size([300, 7])), ("b", torch.Size([5])), ("c", torch.Size([1000, 3, 3])), ("d", torch.Size([64]))]
+    red = GradBucketReducer(shapes, "cpu", bucket_bytes=12000, world_size=world)
+    assert len(red.buckets) == 3
+    for step in range(2):
+        red.begin()
+        for i, (n, s) in enumerate(shapes):
+            red.add(n, torch.full(tuple(s), float((rank + 1) * (i + 1) + step)))
+        out = red.finish()
+        for i, (n, s) in enumerate(shapes):
+            want = sum((r + 1) * (i + 1) + step for r in range(world)) / world      # mean over ranks
+            assert out[n].shape == s and torch.allclose(out[n], torch.full(tuple(s), want)), (n, rank)
+        assert red.launched == [0, 1, 2]
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2])
+def test_gradient_bucket_allreduce_gloo(world):
+    """the N>1 training path on CPU: every rank ends with the mean gradient, buckets launched as they complete."""
+    port = 31500 + (os.getpid() % 2000) + world
+    mp.spawn(_reducer_worker, args=(world, port), nprocs=world, join=True)
