@@ -41,6 +41,8 @@ def parse():
                     help="infer: cfg2/cfg3 whole-mosaic inference (the headline metric); train: cfg4 training step, "
                          "64 RGB+NIR tiles of 256x256 per GPU, Dice+Focal, clip 0.5, Adam, data parallel")
     ap.add_argument("--train-batch", type=int, default=64, help="tiles per GPU per training step (cfg4)")
+    ap.add_argument("--no-graph", action="store_true", help="train workload: launch the ~400 kernels of a step one by one "
+                                                            "from Python instead of replaying the captured CUDA graph")
     ap.add_argument("--size", type=int, default=10000, help="mosaic side in pixels")
     ap.add_argument("--tile", type=int, default=256)
     ap.add_argument("--overlap", type=int, default=32)
@@ -454,16 +456,35 @@ def main_train(a):
     stats = [{"file": f"r{rank}t{i}"} for i in range(B)]
     loss_h = torch.zeros((), pin_memory=True)
 
-    def step_device():
+    use_graph = world == 1 and not a.no_graph
+    launches_per_replay = 0
+    if use_graph:
+        from deadtrees_b200.train_graph import GraphedTrainStep
+        l0 = ops.LAUNCHES
+        gstep = GraphedTrainStep(seg, opt, B, T)
+        launches_per_replay = (ops.LAUNCHES - l0) // 3        # two warm-up passes + the captured one
+        gstep.img.copy_(img_d)
+        gstep.mask.copy_(mask_d)
+
+    def eager_step():
         loss = seg.training_step({"main": (img_d, mask_d, None, lu, stats)}, 0)
         loss.backward()
         opt.step()
         return loss
 
+    def step_device():
+        if use_graph:                        # inputs already in the graph's static buffers
+            gstep.graph.replay()
+            return gstep.terms.total_loss
+        return eager_step()
+
     def step_e2e():
-        img_d.copy_(img_h, non_blocking=True)
-        mask_d.copy_(mask_h, non_blocking=True)
-        loss = step_device()
+        if use_graph:
+            loss = gstep(img_h, mask_h)      # H2D into the static buffers + replay
+        else:
+            img_d.copy_(img_h, non_blocking=True)
+            mask_d.copy_(mask_h, non_blocking=True)
+            loss = eager_step()
         loss_h.copy_(loss.detach(), non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return float(loss_h)
@@ -494,9 +515,16 @@ def main_train(a):
         step_device()
     sampler = ClockSampler(local)
     sampler.start()
-    ms_total, launches, prof = timed(step_device, a.steps, profile=not a.no_profile)
+    ms_total, launches, _ = timed(step_device, a.steps)
     clocks = sampler.stop()
+    if use_graph:
+        launches = launches_per_replay * a.steps          # kernels replayed by the graph (no per-kernel Python call)
     ms_step = ms_total / a.steps
+    # per-kernel CUDA events need individually launched kernels: a separate, eager, instrumented pass
+    prof = None
+    if not a.no_profile:
+        eager_step()
+        _, _, prof = timed(eager_step, a.steps, profile=True)
     for _ in range(2):
         step_e2e()
     ms_e2e_total, _, _ = timed(step_e2e, a.steps)
@@ -512,7 +540,8 @@ def main_train(a):
                                f"{B} RGB+NIR {T}x{T} tiles per GPU, data parallel x{world}",
                    "tile": T, "batch_per_gpu": B, "in_channels": cin, "classes": K,
                    "l2_policy": "per-step working set (activations + gradients, > 5 GB) far larger than L2; no explicit flush",
-                   "parallelism": f"dp{world}, bucketed NCCL gradient all-reduce overlapped with backward"},
+                   "parallelism": f"dp{world}, bucketed NCCL gradient all-reduce overlapped with backward",
+                   "launch": "whole step replayed from one CUDA graph" if use_graph else "kernels launched one by one"},
         "mpixel_per_s": world * B * T * T / 1e6 / (ms_step / 1e3),
         "e2e": {"value": world * B / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(img_h.numel() * 4 + mask_h.numel() * 8),
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e},
@@ -531,11 +560,21 @@ def main_train(a):
             ach = w_all / t_all / 1e12
             out["roofline"] = {"bound": "tensor", "kernel": "tcgen05 conv forward + dgrad (forward kernels on transposed weights) + MN-major wgrad",
                                "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"],
-                               "traffic": None, "launches": nf + nd + nw, "share_of_step": t_all * 1e3 / ms_total,
+                               "traffic": None, "launches": nf + nd + nw, "share_of_step": (t_all * 1e3 / a.steps) / ms_step,
                                "peak_source": pk["source"],
                                "breakdown": {"forward": {"ms_per_step": 1e3 * tf / a.steps, "tflops": wf / max(tf, 1e-12) / 1e12, "launches": nf},
                                              "dgrad_tc": {"ms_per_step": 1e3 * td / a.steps, "tflops": wd / max(td, 1e-12) / 1e12, "launches": nd},
                                              "wgrad_tc": {"ms_per_step": 1e3 * tw / a.steps, "tflops": ww / max(tw, 1e-12) / 1e12, "launches": nw}}}
+        if a.layer_table and rank == 0:
+            per = {}
+            for e0, e1, wk, tag in conv + prof.get("wgrad", []):
+                d = per.setdefault(tag, [0.0, 0.0, 0])
+                d[0] += e0.elapsed_time(e1); d[1] += wk; d[2] += 1
+            with open(a.layer_table, "w") as fh:
+                fh.write(f"{'op.layer':58s} {'launches':>8s} {'avg_us':>9s} {'TFLOP/s':>9s} {'share%':>7s}\n")
+                for tag, (ms, wk, n) in per.items():
+                    fh.write(f"{tag:58s} {n:8d} {1e3 * ms / n:9.1f} {wk / (ms / 1e3) / 1e12:9.1f} {100 * (ms / a.steps) / ms_step:7.2f}\n")
+                fh.write(f"tensor-core kernels {1e3 * t_all / a.steps:.2f} ms of {ms_step:.2f} ms per step\n")
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         from oracle import ref_train, ref_unet
         torch.set_num_threads(os.cpu_count() or 1)

@@ -68,6 +68,7 @@ _SIGNATURES = {
     "dt_conv2d_wgrad_tc_workspace": ([_i, _i, _i, _i, _i, _i, _i], C.c_int64),
     "dt_conv2d_wgrad_tc": ([_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _i64, _p], C.c_int),
     "dt_sumsq": ([_p, _i64, _p, _p], C.c_int),
+    "dt_adam_step_dev": ([_p, _p, _p, _p, _i64, _p, _f, _f, _f, _p, _f, _p, _p, _p], C.c_int),
     "dt_adam_step": ([_p, _p, _p, _p, _i64, _f, _f, _f, _f, _i, _p, _f, _p], C.c_int),
 }
 

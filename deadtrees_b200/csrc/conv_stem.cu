@@ -247,3 +247,250 @@ int dt_conv_stem(const dt_conv_desc* d, const void* x, const void* w, const floa
   DT_LAUNCH_CHECK();
   return DT_OK;
 }
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// Weight gradient of the stem on the tensor cores.
+//
+//   dW[co][ci][r][s] = sum over output pixels p of gy[p][co] * x_pad[2*ho + r][2*wo + s][ci]
+//
+// The SAME overlapping-stride im2col tensor map as the forward kernel delivers, per filter row r, a tile of
+// 128 pixels x 32 elements (8 pixels x 4 channels under the filter row) as 64-byte rows; read as an **MN-major**
+// SWIZZLE_64B operand (N = 32, K = pixel) it multiplies the gy tile (MN-major SWIZZLE_128B, M = co, K = pixel):
+// D_r[co][e] += gy^T . xcol_r.  Seven accumulators of 128 x 32 fp32 stay in TMEM across all tiles of a CTA;
+// partial[split][r][co][e] is then reduced in a fixed order into the OIHW gradient (e = s*4 + ci; s = 7 and ci >= C_in
+// are padding).   warp 0: TMA producer   warp 1: MMA issuer   warps 2..5: epilogue
+// ------------------------------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int WG_A = 128 * 128;                // gy tile: 128 pixels x 64 channels
+constexpr int WG_BSUB = 128 * 64;              // one filter row of the im2col tile: 128 pixels x 64 B
+constexpr int WG_STAGE = WG_A + ROWS * WG_BSUB;   // 72 KB
+constexpr int WG_STAGES = 3;
+constexpr int WG_TMEM = 256;                   // 7 x 32 columns
+
+struct StemWgParams {
+  int Ho, Wo, total_tiles, tiles_per_cta;
+  float* partial;                              // [splits][7][64][32]
+};
+
+__device__ __forceinline__ uint64_t umma_desc_mn_sw(uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(layout & 7u) << 61;
+  return d;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_stem_wgrad_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ CUtensorMap tm_x,
+                       const StemWgParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WG_STAGES * WG_STAGE);
+  uint64_t* full = bars;
+  uint64_t* empty = full + WG_STAGES;
+  uint64_t* done = empty + WG_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile_begin = blockIdx.x * p.tiles_per_cta;
+  const int tile_end = min(p.total_tiles, tile_begin + p.tiles_per_cta);
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_g);
+    tma_prefetch_desc(&tm_x);
+    for (int i = 0; i < WG_STAGES; ++i) { mbar_init(&full[i], 1u); mbar_init(&empty[i], 1u); }
+    mbar_init(done, 1u);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, WG_TMEM);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int st = 0;
+      uint32_t ph = 0;
+      for (int tile = tile_begin; tile < tile_end; ++tile) {
+        const int m0 = tile * BM;
+        const int w0 = m0 % p.Wo, h0 = (m0 / p.Wo) % p.Ho, n0 = m0 / (p.Wo * p.Ho);
+        uint8_t* stage = smem + st * WG_STAGE;
+        mbar_wait(&empty[st], ph ^ 1u);
+        mbar_arrive_expect_tx(&full[st], WG_STAGE);
+        tma_load_4d(stage, &tm_g, &full[st], 0, w0, h0, n0);
+        for (int r = 0; r < ROWS; ++r)
+          tma_load_5d(stage + WG_A + r * WG_BSUB, &tm_x, &full[st], 0, w0, h0, r, n0);
+        if (++st == WG_STAGES) { st = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // bf16, A and B MN-major, M = 128 (rows 64..127 read whatever follows the gy tile and are discarded), N = 32
+      constexpr uint32_t idesc_w = umma_idesc_bf16(128, 32) | (1u << 15) | (1u << 16);
+      const uint64_t a_hi = umma_desc_mn_sw(WG_A, 1024u, 2u);      // 128 B rows, 8-row K groups 1024 B apart
+      const uint64_t b_hi = umma_desc_mn_sw(16u, 512u, 4u);        // 64 B rows, 8-row K groups 512 B apart
+      int st = 0;
+      uint32_t ph = 0, accum = 0;
+      for (int tile = tile_begin; tile < tile_end; ++tile) {
+        mbar_wait(&full[st], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + st * WG_STAGE);
+        const uint32_t b_addr = a_addr + WG_A;
+#pragma unroll 1
+        for (int r = 0; r < ROWS; ++r) {
+#pragma unroll
+          for (int k8 = 0; k8 < 8; ++k8)
+            umma_bf16_ss(tmem_base + r * 32, a_hi + ((a_addr + k8 * 2048) >> 4),
+                         b_hi + ((b_addr + r * WG_BSUB + k8 * 1024) >> 4), idesc_w, (accum | k8) != 0 ? 1u : 0u);
+        }
+        accum = 1;
+        umma_commit(&empty[st]);
+        if (++st == WG_STAGES) { st = 0; ph ^= 1u; }
+      }
+      umma_commit(done);
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int co = quarter * 32 + lane;
+    mbar_wait(done, 0);
+    tc_fence_after();
+    for (int r = 0; r < ROWS; ++r) {
+#pragma unroll
+      for (int c0 = 0; c0 < 32; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld_x16(tmem_base + r * 32 + c0 + (static_cast<uint32_t>(quarter * 32) << 16), v);
+        tmem_ld_wait();
+        if (co < BN) {
+          float4* dst = reinterpret_cast<float4*>(p.partial + ((static_cast<int64_t>(blockIdx.x) * ROWS + r) * BN + co) * 32 + c0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                 __uint_as_float(v[4 * j + 3]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, WG_TMEM);
+  }
+}
+
+// dw[co][ci][r][s] = sum over splits of partial[split][r][co][s*4 + ci]
+__global__ void stem_wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int C_in, float* __restrict__ dw) {
+  const int total = BN * C_in * 49;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int s = i % 7, r = (i / 7) % 7, ci = (i / 49) % C_in, co = i / (49 * C_in);
+    float acc = 0.f;
+    for (int sp = 0; sp < splits; ++sp) acc += partial[((static_cast<int64_t>(sp) * ROWS + r) * BN + co) * 32 + s * 4 + ci];
+    dw[i] = acc;
+  }
+}
+
+int stem_tiling(int Ho, int Wo, int* bw, int* bh, int* bn) {
+  if (Wo >= BM) {
+    if (Wo % BM) return DT_ERR_UNSUPPORTED;
+    *bw = BM; *bh = 1; *bn = 1;
+    return DT_OK;
+  }
+  if (BM % Wo) return DT_ERR_UNSUPPORTED;
+  const int rows = BM / Wo;
+  *bw = Wo;
+  if (Ho >= rows) { if (Ho % rows) return DT_ERR_UNSUPPORTED; *bh = rows; *bn = 1; }
+  else { if (rows % Ho) return DT_ERR_UNSUPPORTED; *bh = Ho; *bn = rows / Ho; }
+  return DT_OK;
+}
+
+int stem_wgrad_splits(int total_tiles, int* tiles_per_cta) {
+  int splits = 2 * dt_num_sms();
+  if (splits > total_tiles) splits = total_tiles;
+  *tiles_per_cta = (total_tiles + splits - 1) / splits;
+  return (total_tiles + *tiles_per_cta - 1) / *tiles_per_cta;
+}
+
+}  // namespace
+
+extern "C" int64_t dt_stem_wgrad_tc_workspace(int N, int H, int W) {
+  int bw, bh, bn;
+  if (N <= 0 || H <= 0 || W <= 0 || H % 2 || W % 2 || stem_tiling(H / 2, W / 2, &bw, &bh, &bn) != DT_OK || N % bn)
+    return DT_ERR_UNSUPPORTED;
+  int per;
+  const int splits = stem_wgrad_splits(N * (H / 2) * (W / 2) / BM, &per);
+  return static_cast<int64_t>(splits) * ROWS * BN * 32 * static_cast<int64_t>(sizeof(float));
+}
+
+// x_pad: zero-bordered (N, H+6, W+8, 4) bf16 frame; gy: (N, H/2, W/2, 64) bf16; dw: fp32 (64, C_in, 7, 7).
+extern "C" int dt_stem_wgrad_tc(const void* x_pad, const void* gy, int N, int H, int W, int C_in, float* dw_oihw,
+                                float* workspace, int64_t workspace_bytes, dt_stream_t stream) {
+  DT_ARCH_GUARD();
+  int bw, bh, bn;
+  if (N <= 0 || H <= 0 || W <= 0 || H % 2 || W % 2 || C_in < 1 || C_in > 4 ||
+      stem_tiling(H / 2, W / 2, &bw, &bh, &bn) != DT_OK || N % bn) {
+    dt_set_error("dt_stem_wgrad_tc: unsupported shape N=%d H=%d W=%d C_in=%d", N, H, W, C_in);
+    return DT_ERR_UNSUPPORTED;
+  }
+  const int Ho = H / 2, Wo = W / 2;
+  StemWgParams p;
+  p.Ho = Ho; p.Wo = Wo;
+  p.total_tiles = N * Ho * Wo / BM;
+  const int splits = stem_wgrad_splits(p.total_tiles, &p.tiles_per_cta);
+  const int64_t need = static_cast<int64_t>(splits) * ROWS * BN * 32 * static_cast<int64_t>(sizeof(float));
+  DT_REQUIRE(workspace != nullptr && workspace_bytes >= need, DT_ERR_BAD_SHAPE,
+             "dt_stem_wgrad_tc: workspace of %lld bytes needed", static_cast<long long>(need));
+  DT_REQUIRE((reinterpret_cast<uintptr_t>(x_pad) | reinterpret_cast<uintptr_t>(gy) | reinterpret_cast<uintptr_t>(workspace)) % 16 == 0,
+             DT_ERR_BAD_ALIGN, "dt_stem_wgrad_tc: tensors must be 16-byte aligned");
+  p.partial = workspace;
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once_fn;
+  std::call_once(once_fn, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  });
+  DT_REQUIRE(fn != nullptr, DT_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  const uint64_t Hp = H + 6, Wp = W + 8;
+  CUtensorMap tm_x, tm_g;
+  {
+    const cuuint64_t dims[5] = {32, static_cast<cuuint64_t>(Wo), static_cast<cuuint64_t>(Ho), ROWS, static_cast<cuuint64_t>(N)};
+    const cuuint64_t str[4] = {16, 2 * Wp * 8, Wp * 8, Hp * Wp * 8};
+    const cuuint32_t box[5] = {32, static_cast<cuuint32_t>(bw), static_cast<cuuint32_t>(bh), 1, static_cast<cuuint32_t>(bn)};
+    const cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = fn(&tm_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x_pad), dims, str, box, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    DT_REQUIRE(r == CUDA_SUCCESS, DT_ERR_CUDA, "stem wgrad im2col tensor map: CUresult %d", static_cast<int>(r));
+  }
+  {
+    const cuuint64_t dims[4] = {BN, static_cast<cuuint64_t>(Wo), static_cast<cuuint64_t>(Ho), static_cast<cuuint64_t>(N)};
+    const cuuint64_t str[3] = {BN * 2, static_cast<cuuint64_t>(Wo) * BN * 2, static_cast<cuuint64_t>(Ho) * Wo * BN * 2};
+    const cuuint32_t box[4] = {BN, static_cast<cuuint32_t>(bw), static_cast<cuuint32_t>(bh), static_cast<cuuint32_t>(bn)};
+    const cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = fn(&tm_g, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(gy), dims, str, box, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    DT_REQUIRE(r == CUDA_SUCCESS, DT_ERR_CUDA, "stem wgrad gy tensor map: CUresult %d", static_cast<int>(r));
+  }
+  constexpr int smem = WG_STAGES * WG_STAGE + 1024 + 256;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(conv_stem_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  });
+  DT_CUDA(attr_err);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  conv_stem_wgrad_kernel<<<splits, kThreads, smem, s>>>(tm_g, tm_x, p);
+  DT_LAUNCH_CHECK();
+  stem_wgrad_reduce_kernel<<<(BN * C_in * 49 + 255) / 256, 256, 0, s>>>(workspace, splits, C_in, dw_oihw);
+  DT_LAUNCH_CHECK();
+  return DT_OK;
+}

@@ -279,6 +279,54 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
 }
 
+// Adam with ALL step state on the device, so the launch can live in a CUDA graph: state = {step (as float), lr};
+// the step is skipped entirely (state untouched) when *loss is not finite - SemSegment.training_step returning None.
+__global__ void adam_prepare_kernel(float* __restrict__ state, const float* __restrict__ loss, const double* __restrict__ sumsq,
+                                    float b1, float b2, float max_norm, float* __restrict__ scal) {
+  const bool apply = loss == nullptr || isfinite(*loss);
+  float step = state[0];
+  if (apply) { step += 1.f; state[0] = step; }
+  const double bc1 = 1.0 - pow(static_cast<double>(b1), static_cast<double>(step));
+  const double bc2 = 1.0 - pow(static_cast<double>(b2), static_cast<double>(step));
+  float clip = 1.f;
+  if (max_norm > 0.f) clip = fminf(1.f, max_norm / (static_cast<float>(sqrt(*sumsq)) + 1e-6f));
+  scal[0] = apply ? 1.f : 0.f;
+  scal[1] = clip;
+  scal[2] = state[1] / static_cast<float>(bc1);        // step size = lr / bias_correction1
+  scal[3] = static_cast<float>(sqrt(bc2));
+}
+
+__global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                float* __restrict__ v, int64_t n, float b1, float b2, float eps,
+                                const float* __restrict__ scal) {
+  if (scal[0] == 0.f) return;
+  const float clip = scal[1], step_size = scal[2], bc2_sqrt = scal[3];
+  for (int64_t i = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) * 4; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x * 4) {
+    if (i + 3 < n) {
+      float4 p4 = *reinterpret_cast<float4*>(p + i), m4 = *reinterpret_cast<float4*>(m + i), v4 = *reinterpret_cast<float4*>(v + i);
+      const float4 g4 = *reinterpret_cast<const float4*>(g + i);
+      float* pp = &p4.x; float* mm = &m4.x; float* vv = &v4.x; const float* gg = &g4.x;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float gi = gg[j] * clip;
+        mm[j] = mm[j] + (1.f - b1) * (gi - mm[j]);
+        vv[j] = b2 * vv[j] + (1.f - b2) * gi * gi;
+        pp[j] -= step_size * (mm[j] / (sqrtf(vv[j]) / bc2_sqrt + eps));
+      }
+      *reinterpret_cast<float4*>(p + i) = p4; *reinterpret_cast<float4*>(m + i) = m4; *reinterpret_cast<float4*>(v + i) = v4;
+    } else {
+      for (int64_t k = i; k < n; ++k) {
+        const float gi = g[k] * clip;
+        const float mi = m[k] + (1.f - b1) * (gi - m[k]);
+        const float vi = b2 * v[k] + (1.f - b2) * gi * gi;
+        m[k] = mi; v[k] = vi;
+        p[k] -= step_size * (mi / (sqrtf(vi) / bc2_sqrt + eps));
+      }
+    }
+  }
+}
+
 inline int grid_for(int64_t work) {
   int64_t blocks = (work + kThreads - 1) / kThreads;
   const int64_t cap = static_cast<int64_t>(dt_num_sms()) * 8;
@@ -401,6 +449,23 @@ int dt_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float 
   const float bc2_sqrt = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(beta2), step)));
   adam_kernel<<<grid_for(n), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps,
                                                                                bc1, bc2_sqrt, sumsq, max_norm);
+  DT_LAUNCH_CHECK();
+  return DT_OK;
+}
+
+int dt_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, float* state, float beta1, float beta2,
+                     float eps, const double* sumsq, float max_norm, const float* loss, float* scratch4,
+                     dt_stream_t stream) {
+  DT_ARCH_GUARD();
+  DT_REQUIRE(n >= 0 && state != nullptr && scratch4 != nullptr, DT_ERR_BAD_SHAPE, "dt_adam_step_dev: bad arguments");
+  DT_REQUIRE(max_norm <= 0.f || sumsq != nullptr, DT_ERR_BAD_SHAPE, "dt_adam_step_dev: clipping needs sumsq");
+  DT_REQUIRE((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+              reinterpret_cast<uintptr_t>(v)) % 16 == 0, DT_ERR_BAD_ALIGN, "dt_adam_step_dev: buffers must be 16-byte aligned");
+  if (n == 0) return DT_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  adam_prepare_kernel<<<1, 1, 0, s>>>(state, loss, sumsq, beta1, beta2, max_norm, scratch4);
+  DT_LAUNCH_CHECK();
+  adam_dev_kernel<<<grid_for((n + 3) / 4), kThreads, 0, s>>>(p, g, m, v, n, beta1, beta2, eps, scratch4);
   DT_LAUNCH_CHECK();
   return DT_OK;
 }

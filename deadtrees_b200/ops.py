@@ -277,6 +277,14 @@ def prob_loss_partials(probs: torch.Tensor, target: torch.Tensor, gamma: float =
     return sums
 
 
+def adam_step_dev(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor, state: torch.Tensor, *, beta1: float,
+                  beta2: float, eps: float, sumsq_acc: Optional[torch.Tensor], max_norm: float,
+                  loss: Optional[torch.Tensor], scratch: torch.Tensor) -> None:
+    """graph-capturable Adam: state = float (2,) {step, lr} on the device; skipped when `loss` is not finite."""
+    check(load().dt_adam_step_dev(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), state.data_ptr(),
+                                  beta1, beta2, eps, ptr(sumsq_acc), max_norm, ptr(loss), scratch.data_ptr(), stream_ptr()))
+
+
 def sumsq(g: torch.Tensor, acc: torch.Tensor) -> None:
     check(load().dt_sumsq(g.data_ptr(), g.numel(), acc.data_ptr(), stream_ptr()))
 
@@ -449,7 +457,7 @@ def wgrad_tc_supported(x: torch.Tensor, gy: torch.Tensor, w_shape, stride: int, 
 
 
 def conv2d_wgrad_tc(x: torch.Tensor, gy: torch.Tensor, w_shape, stride: int = 1,
-                    out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                    out: Optional[torch.Tensor] = None, tag: str = "wgrad") -> torch.Tensor:
     """tensor-core weight gradient: x (N, s*Ho, s*Wo, >=C_in), gy (N, Ho, Wo, >=C_out) bf16 -> dw fp32 OIHW."""
     C_out, C_in, R, S = w_shape
     N, Ho, Wo, Cg = gy.shape
@@ -459,7 +467,7 @@ def conv2d_wgrad_tc(x: torch.Tensor, gy: torch.Tensor, w_shape, stride: int = 1,
         raise _lib.DeadtreesB200Error(f"dt_conv2d_wgrad_tc does not support x {tuple(x.shape)} gy {tuple(gy.shape)} w {tuple(w_shape)}")
     ws = torch.empty((need + 3) // 4, dtype=torch.float32, device=x.device)
     dw = out if out is not None else torch.empty(tuple(w_shape), dtype=torch.float32, device=x.device)
-    with _Timed("wgrad", 2.0 * N * Ho * Wo * C_out * C_in * R * S, "wgrad"):
+    with _Timed("wgrad", 2.0 * N * Ho * Wo * C_out * C_in * R * S, tag):
         check(lib.dt_conv2d_wgrad_tc(x.data_ptr(), gy.data_ptr(), N, Ho, Wo, C_in, x.shape[-1], C_out, Cg, R, stride,
                                      dw.data_ptr(), ws.data_ptr(), need, stream_ptr()))
     return dw

@@ -23,20 +23,30 @@ class FusedAdam(torch.optim.Optimizer):
         if len(self.param_groups) != 1 or any(id(p) not in mine for p in engine.params.values()):
             raise ValueError("attach_engine needs one param group holding every parameter of the engine")
         fp = engine.flatten_parameters()
-        self._flat = dict(p=fp, g=engine.reducer.flat, m=torch.zeros_like(fp), v=torch.zeros_like(fp), step=0)
+        dev = fp.device
+        self._flat = dict(p=fp, g=engine.reducer.flat, m=torch.zeros_like(fp), v=torch.zeros_like(fp),
+                          state=torch.tensor([0.0, self.param_groups[0]["lr"]], dtype=torch.float32, device=dev),
+                          scratch=torch.zeros(4, dtype=torch.float32, device=dev),
+                          acc=torch.zeros(1, dtype=torch.float64, device=dev), lr=self.param_groups[0]["lr"])
         return self
 
     @torch.no_grad()
-    def step(self, closure=None):
+    def step(self, closure=None, loss: torch.Tensor = None):
+        """``loss`` (flat path only): a device scalar; the update is skipped on the device when it is not finite."""
         if self._flat is not None:
+            # every piece of step state lives on the device (step count, lr, clip factor): the launches below can be
+            # captured in a CUDA graph and replayed; a changed learning rate is pushed with one tiny copy
             f, group = self._flat, self.param_groups[0]
-            f["step"] += 1
+            if group["lr"] != f["lr"]:
+                f["lr"] = group["lr"]
+                f["state"][1:2].fill_(group["lr"])
             acc = None
             if group["max_grad_norm"] > 0:
-                acc = torch.zeros((1,), dtype=torch.float64, device=f["p"].device)
+                acc = f["acc"]
+                acc.zero_()
                 ops.sumsq(f["g"], acc)
-            ops.adam_step(f["p"], f["g"], f["m"], f["v"], lr=group["lr"], beta1=group["betas"][0], beta2=group["betas"][1],
-                          eps=group["eps"], step=f["step"], sumsq_acc=acc, max_norm=group["max_grad_norm"])
+            ops.adam_step_dev(f["p"], f["g"], f["m"], f["v"], f["state"], beta1=group["betas"][0], beta2=group["betas"][1],
+                              eps=group["eps"], sumsq_acc=acc, max_norm=group["max_grad_norm"], loss=loss, scratch=f["scratch"])
             return
         for group in self.param_groups:
             params = [p for p in group["params"] if p.grad is not None]

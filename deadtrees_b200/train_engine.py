@@ -178,7 +178,7 @@ class UnetTrainEngine:
         out = self.reducer.view(wname)
         bname = wname[:-len("weight")] + "bias"
         if self.precision == "bf16" and self.wgrad_tc and ops.wgrad_tc_supported(x, gy, w.shape, stride, pad):
-            dw = ops.conv2d_wgrad_tc(x, gy, w.shape, stride, out=out)
+            dw = ops.conv2d_wgrad_tc(x, gy, w.shape, stride, out=out, tag="wgrad." + wname)
             db = ops.channel_sum(gy, w.shape[0], out=self.reducer.view(bname)) if want_bias else None
         else:
             dw, db = ops.conv2d_wgrad_direct(x, gy, w.shape, stride, pad, want_bias=want_bias, out=out,

@@ -1,0 +1,97 @@
+"""One whole training step (forward, loss, backward, clip + Adam) captured in a CUDA graph.
+
+At the reference's batch sizes the step is ~400 short kernels; launched one by one from Python the host, not the GPU,
+sets the step time.  ``GraphedTrainStep`` records the kernel sequence of ``SemSegment.training_step`` +
+``loss.backward()`` + ``optimizer.step()`` (``deadtrees/network/segmodel.py:210-229``, ``:420-429``) once and replays it;
+everything that varies from step to step lives on the device (inputs in static buffers, Adam's step count and learning
+rate, the clip factor, the NaN-skip decision), so no host synchronisation remains inside a step.  The label-range check
+of ``class2one_hot`` (``losses.py:129``) and the NaN warning are evaluated from device flags AFTER the replay
+(``check()``), instead of stalling the pipeline in the middle of the step as the reference does.
+"""
+from __future__ import annotations
+
+from typing import Dict
+
+import torch
+
+from .loss.fused import SegLossTerms
+from .loss.gdl import GeneralizedDiceLoss
+from .optim import FusedAdam
+
+
+class GraphedTrainStep:
+    def __init__(self, seg, optimizer: FusedAdam, batch: int, tile: int):
+        if seg.boundary_loss is not None:
+            raise NotImplementedError("the boundary loss has no backward kernel yet (next tier, SURVEY.md 8f-2)")
+        self.seg, self.opt = seg, optimizer
+        self.engine = seg.model.train_engine()
+        if optimizer._flat is None:
+            optimizer.attach_engine(self.engine)
+        if self.engine.reducer.world != 1:
+            raise NotImplementedError("graph capture of the NCCL gradient all-reduce is not enabled; use the eager step")
+        dev = self.engine.device
+        self.dice_mode = 2 if isinstance(seg.dice_loss, GeneralizedDiceLoss) else 1
+        self.use_focal = seg.focal_loss is not None
+        cin = seg.model.in_channels
+        self.img = torch.zeros((batch, cin, tile, tile), dtype=torch.float32, device=dev)
+        self.mask = torch.zeros((batch, tile, tile), dtype=torch.int64, device=dev)
+        self.terms: SegLossTerms = None
+        # warm-up on a side stream (lazy allocations, cudaFuncSetAttribute calls, tensor-map encodes), then capture;
+        # the warm-up steps must not train: snapshot and restore every piece of state they touch
+        snap = self._snapshot()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self._body()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._body()
+        self._restore(snap)
+
+    def _state_tensors(self) -> Dict[str, torch.Tensor]:
+        f = self.opt._flat
+        st = {"p": f["p"], "m": f["m"], "v": f["v"], "state": f["state"]}
+        for n, b in self.seg.model.named_buffers():
+            st["buf." + n] = b
+        return st
+
+    def _snapshot(self):
+        return {k: v.clone() for k, v in self._state_tensors().items()}
+
+    def _restore(self, snap) -> None:
+        with torch.no_grad():
+            for k, v in self._state_tensors().items():
+                v.copy_(snap[k])
+
+    def _body(self) -> None:
+        with torch.no_grad():
+            logits, tape = self.engine.forward(self.img)
+            self.terms = SegLossTerms(logits, self.mask, self.dice_mode, self.use_focal)
+            grads = self.engine.backward(tape, self.terms.grad_logits(1.0))
+            self.opt.step(loss=self.terms.out[2:3])         # skipped on the device when the loss is not finite
+        for n, p in self.engine.params.items():
+            p.grad = grads[n]
+
+    def __call__(self, img: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+        """copies the batch into the static buffers, replays the step, returns the (device) total loss."""
+        self.img.copy_(img, non_blocking=True)
+        self.mask.copy_(mask, non_blocking=True)
+        self.graph.replay()
+        return self.terms.total_loss
+
+    def check(self) -> float:
+        """host-side checks of the last replayed step (one synchronisation): label range, finite loss."""
+        self.terms.check_labels()
+        loss = float(self.terms.total_loss)
+        if loss != loss or loss in (float("inf"), float("-inf")):
+            import logging
+            logging.getLogger(__name__).warning("Train loss is NaN! What is going on? (optimizer step skipped)")
+        return loss
+
+    def log_terms(self) -> Dict[str, torch.Tensor]:
+        t = self.terms
+        return {"train/dice_loss": t.dice_loss, "train/focal_loss": t.focal_loss, "train/total_loss": t.total_loss,
+                "train/dice": t.fscore, "train/dice_with_bg": t.fscore_with_bg}

@@ -262,6 +262,14 @@ int dt_sumsq(const float* g, int64_t n, double* sumsq, dt_stream_t stream);
 int dt_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                  float eps, int step, const double* sumsq, float max_norm, dt_stream_t stream);
 
+/* The same update with every piece of step state on the device, so the launch can be captured in a CUDA graph:
+ * state = float[2] {step count, learning rate} (step incremented here; the caller updates lr between replays);
+ * loss (may be NULL): the step is skipped - parameters, moments and the step count untouched - when *loss is not finite
+ * (SemSegment.training_step returns None for a NaN / Inf loss, segmodel.py:219-221); scratch4: float[4] work area. */
+int dt_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, float* state, float beta1, float beta2,
+                     float eps, const double* sumsq, float max_norm, const float* loss, float* scratch4,
+                     dt_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
