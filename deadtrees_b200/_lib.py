@@ -39,6 +39,7 @@ _SIGNATURES = {
     "dt_tile_gather_normalize": ([_p, _i, _i, _i, _i64, _i64, _i64, _i, _i, _i, _i, _i,
                                   C.POINTER(_f), C.POINTER(_f), _i, _i, _i, _p, _p], C.c_int),
     "dt_pack_input_nchw": ([_p, _i, _i, _i, _i, _i, _i, _p, _p], C.c_int),
+    "dt_pack_input_nchw_frame": ([_p, _i, _i, _i, _i, _i, _p, _p], C.c_int),
     "dt_stitch_mask_u8": ([_p, _i, _i, _i, _i, _p, _i, _i, _i64, _p], C.c_int),
     "dt_stitch_blend_argmax": ([_p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _i, _i, _i, _i, _p], C.c_int),
     "dt_conv2d_fwd": ([C.POINTER(ConvDesc), _p, _p, _p, _p, _p, _p, _p, _p], C.c_int),
@@ -58,6 +59,8 @@ _SIGNATURES = {
     "dt_bn_train_bwd": ([_p, _p, _p, _i64, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p], C.c_int),
     "dt_add": ([_p, _p, _i64, _i, _p, _p], C.c_int),
     "dt_maxpool3x3s2_bwd": ([_p, _p, _p, _i, _i, _i, _i, _i, _p, _p], C.c_int),
+    "dt_maxpool3x3s2_idx": ([_p, _i, _i, _i, _i, _i, _p, _p, _p], C.c_int),
+    "dt_maxpool3x3s2_bwd_idx": ([_p, _p, _p, _i, _i, _i, _i, _i, _p, _p], C.c_int),
     "dt_upsample_concat": ([_p, _p, _i, _i, _i, _i, _i, _i, _p, _p], C.c_int),
     "dt_upsample_concat_bwd": ([_p, _i, _i, _i, _i, _i, _i, _p, _p, _p], C.c_int),
     "dt_nchw_to_nhwc": ([_p, _i, _i, _i, _i, _i, _i, _p, _p], C.c_int),
@@ -67,6 +70,8 @@ _SIGNATURES = {
     "dt_conv2d_wgrad_direct": ([_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p], C.c_int),
     "dt_conv2d_wgrad_tc_workspace": ([_i, _i, _i, _i, _i, _i, _i], C.c_int64),
     "dt_conv2d_wgrad_tc": ([_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _i64, _p], C.c_int),
+    "dt_stem_wgrad_tc_workspace": ([_i, _i, _i], C.c_int64),
+    "dt_stem_wgrad_tc": ([_p, _p, _i, _i, _i, _i, _p, _p, _i64, _p], C.c_int),
     "dt_sumsq": ([_p, _i64, _p, _p], C.c_int),
     "dt_adam_step_dev": ([_p, _p, _p, _p, _i64, _p, _f, _f, _f, _p, _f, _p, _p, _p], C.c_int),
     "dt_adam_step": ([_p, _p, _p, _p, _i64, _f, _f, _f, _f, _i, _p, _f, _p], C.c_int),

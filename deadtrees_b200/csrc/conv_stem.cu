@@ -410,7 +410,7 @@ int stem_tiling(int Ho, int Wo, int* bw, int* bh, int* bn) {
 }
 
 int stem_wgrad_splits(int total_tiles, int* tiles_per_cta) {
-  int splits = 2 * dt_num_sms();
+  int splits = dt_num_sms();           // one wave of single-CTA-per-SM (216 KB of shared memory each)
   if (splits > total_tiles) splits = total_tiles;
   *tiles_per_cta = (total_tiles + splits - 1) / splits;
   return (total_tiles + *tiles_per_cta - 1) / *tiles_per_cta;

@@ -325,6 +325,26 @@ __global__ void pack_nchw_kernel(const float* __restrict__ x, int N, int C_src, 
   }
 }
 
+// Same conversion into the stem's zero-bordered bf16 frame (N, H+6, W+8, 4) (conv_stem.cu): the interior sits at
+// offset (3, 3); the kernel writes the WHOLE frame, borders included, so the caller need not clear it.
+__global__ void pack_nchw_frame_kernel(const float* __restrict__ x, int N, int C_src, int C, int H, int W,
+                                       uint2* __restrict__ out) {
+  const int Hp = H + 6, Wp = W + 8;
+  const int64_t HW = static_cast<int64_t>(H) * W;
+  const int64_t total = static_cast<int64_t>(N) * Hp * Wp;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int wp = static_cast<int>(i % Wp);
+    const int hp = static_cast<int>((i / Wp) % Hp);
+    const int64_t n = i / (static_cast<int64_t>(Wp) * Hp);
+    const int h = hp - 3, w = wp - 3;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (h >= 0 && h < H && w >= 0 && w < W)
+      for (int c = 0; c < C; ++c) v[c] = __ldg(x + (n * C_src + c) * HW + static_cast<int64_t>(h) * W + w);
+    out[i] = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -342,6 +362,18 @@ int dt_pack_input_nchw(const float* x, int N, int C_src, int C, int H, int W, in
     pack_nchw_kernel<true><<<grid_for(N * HW), kThreads, 0, s>>>(x, N, C_src, C, HW, out);
   else
     pack_nchw_kernel<false><<<grid_for(N * HW), kThreads, 0, s>>>(x, N, C_src, C, HW, out);
+  DT_LAUNCH_CHECK();
+  return DT_OK;
+}
+
+int dt_pack_input_nchw_frame(const float* x, int N, int C_src, int C, int H, int W, void* out, dt_stream_t stream) {
+  DT_ARCH_GUARD();
+  DT_REQUIRE(N > 0 && H > 0 && W > 0 && C >= 1 && C <= 4 && C_src >= C, DT_ERR_BAD_SHAPE,
+             "dt_pack_input_nchw_frame: N=%d C_src=%d C=%d", N, C_src, C);
+  DT_REQUIRE(reinterpret_cast<uintptr_t>(out) % 16 == 0, DT_ERR_BAD_ALIGN, "dt_pack_input_nchw_frame: out alignment");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  pack_nchw_frame_kernel<<<grid_for(static_cast<int64_t>(N) * (H + 6) * (W + 8)), kThreads, 0, s>>>(
+      x, N, C_src, C, H, W, static_cast<uint2*>(out));
   DT_LAUNCH_CHECK();
   return DT_OK;
 }

@@ -263,6 +263,98 @@ __global__ void maxpool_bwd_kernel(const T* __restrict__ x, const T* __restrict_
   }
 }
 
+// MaxPool2d(3, 2, 1) for the training step, index form.  Forward: one thread = one 16-byte channel vector of one
+// output pixel; also stores, per element, the window position (dy * 3 + dx, 0..8) of the FIRST maximum in row-major
+// scan order (ATen's max_pool2d_with_indices).  Backward (gather, no atomics, no re-read of the pool input): one thread
+// = one channel vector of one INPUT pixel; it belongs to 1, 2 or 4 windows and takes the gradient of each window
+// whose stored position names it.  Algorithmic bytes per input element-vector: <= 4 x (VN index bytes + 16 B gout)
+// + 16 B addend + 16 B gx, against 9 x 16 B of x per window in the recompute form above.
+template <typename T>
+__global__ void maxpool_idx_fwd_kernel(const T* __restrict__ x, int N, int H, int W, int C, int Ho, int Wo,
+                                       T* __restrict__ y, uint8_t* __restrict__ idx) {
+  constexpr int VN = VecOf<T>::N;
+  const int Cv = C / VN;
+  const int64_t total = static_cast<int64_t>(N) * Ho * Wo * Cv;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int cv = static_cast<int>(i % Cv);
+    int64_t r = i / Cv;
+    const int wo = static_cast<int>(r % Wo); r /= Wo;
+    const int ho = static_cast<int>(r % Ho);
+    const int n = static_cast<int>(r / Ho);
+    float best[VN];
+    uint32_t code[VN];
+#pragma unroll
+    for (int j = 0; j < VN; ++j) { best[j] = 0.f; code[j] = 255u; }
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      const int hi = 2 * ho + dy - 1;
+      if (hi < 0 || hi >= H) continue;
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const int wi = 2 * wo + dx - 1;
+        if (wi < 0 || wi >= W) continue;
+        float v[VN];
+        load_vec<T>(x + ((static_cast<int64_t>(n) * H + hi) * W + wi) * C + cv * VN, v);
+#pragma unroll
+        for (int j = 0; j < VN; ++j)
+          if (code[j] == 255u || v[j] > best[j]) { best[j] = v[j]; code[j] = dy * 3 + dx; }
+      }
+    }
+    store_vec<T>(y + i * VN, best);
+    uint32_t packed[VN / 4];
+#pragma unroll
+    for (int q = 0; q < VN / 4; ++q)
+      packed[q] = code[4 * q] | (code[4 * q + 1] << 8) | (code[4 * q + 2] << 16) | (code[4 * q + 3] << 24);
+    if (VN == 8) *reinterpret_cast<uint2*>(idx + i * VN) = make_uint2(packed[0], packed[VN / 4 - 1]);
+    else *reinterpret_cast<uint32_t*>(idx + i * VN) = packed[0];
+  }
+}
+
+template <typename T>
+__global__ void maxpool_idx_bwd_kernel(const uint8_t* __restrict__ idx, const T* __restrict__ gout,
+                                       const T* __restrict__ addend, int N, int H, int W, int C, int Ho, int Wo,
+                                       T* __restrict__ gx) {
+  constexpr int VN = VecOf<T>::N;
+  const int Cv = C / VN;
+  const int64_t total = static_cast<int64_t>(N) * H * W * Cv;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int cv = static_cast<int>(i % Cv);
+    int64_t r = i / Cv;
+    const int w = static_cast<int>(r % W); r /= W;
+    const int h = static_cast<int>(r % H);
+    const int n = static_cast<int>(r / H);
+    float acc[VN];
+    if (addend != nullptr) {
+      load_vec<T>(addend + i * VN, acc);
+    } else {
+#pragma unroll
+      for (int j = 0; j < VN; ++j) acc[j] = 0.f;
+    }
+    // windows (ho, wo) with 2*ho - 1 <= h <= 2*ho + 1: ho = h/2 and, for odd h, also (h+1)/2
+    const int ho1 = (h + 1) >> 1, wo1 = (w + 1) >> 1;
+    for (int ho = h >> 1; ho <= ho1; ++ho) {
+      if (ho >= Ho) continue;
+      const uint32_t cy = static_cast<uint32_t>(h - 2 * ho + 1) * 3u;
+      for (int wo = w >> 1; wo <= wo1; ++wo) {
+        if (wo >= Wo) continue;
+        const uint32_t want = cy + static_cast<uint32_t>(w - 2 * wo + 1);
+        const int64_t o = (((static_cast<int64_t>(n) * Ho + ho) * Wo + wo) * Cv + cv) * VN;
+        uint32_t packed[2];
+        if (VN == 8) { const uint2 t = __ldg(reinterpret_cast<const uint2*>(idx + o)); packed[0] = t.x; packed[1] = t.y; }
+        else { packed[0] = __ldg(reinterpret_cast<const uint32_t*>(idx + o)); packed[1] = 0u; }
+        float g[VN];
+        load_vec<T>(gout + o, g);
+#pragma unroll
+        for (int j = 0; j < VN; ++j)
+          if (((packed[j >> 2] >> (8 * (j & 3))) & 255u) == want) acc[j] += g[j];
+      }
+    }
+    store_vec<T>(gx + i * VN, acc);
+  }
+}
+
 // cat([nearest_x2(x_low), skip], C): (N, H/2, W/2, Cx) + (N, H, W, Cs) -> (N, H, W, Cx + Cs); 16-byte vectors
 template <typename T>
 __global__ void upsample_concat_kernel(const T* __restrict__ xl, const T* __restrict__ skip, int N, int H, int W, int Cx,
@@ -599,6 +691,41 @@ int dt_maxpool3x3s2_bwd(const void* x, const void* gout, const void* addend, int
   DT_DTYPE_SWITCH(dtype,
       (maxpool_bwd_kernel<float><<<grid_for(total, 16), kThreads, 0, s>>>(static_cast<const float*>(x), static_cast<const float*>(gout), static_cast<const float*>(addend), N, H, W, C, Ho, Wo, static_cast<float*>(gx))),
       (maxpool_bwd_kernel<__nv_bfloat16><<<grid_for(total, 16), kThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(gout), static_cast<const __nv_bfloat16*>(addend), N, H, W, C, Ho, Wo, static_cast<__nv_bfloat16*>(gx))));
+  DT_LAUNCH_CHECK();
+  return DT_OK;
+}
+
+int dt_maxpool3x3s2_idx(const void* x, int N, int H, int W, int C, int dtype, void* y, uint8_t* idx, dt_stream_t stream) {
+  DT_ARCH_GUARD();
+  const int vn = dtype == DT_BF16 ? 8 : 4;
+  DT_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && C % vn == 0 && (dtype == DT_F32 || dtype == DT_BF16), DT_ERR_BAD_SHAPE,
+             "dt_maxpool3x3s2_idx: bad shape (C=%d must be a multiple of %d)", C, vn);
+  DT_REQUIRE((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(idx)) % 16 == 0,
+             DT_ERR_BAD_ALIGN, "dt_maxpool3x3s2_idx: tensors must be 16-byte aligned");
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int64_t total = static_cast<int64_t>(N) * Ho * Wo * (C / vn);
+  DT_DTYPE_SWITCH(dtype,
+      (maxpool_idx_fwd_kernel<float><<<grid_for(total, 16), kThreads, 0, s>>>(static_cast<const float*>(x), N, H, W, C, Ho, Wo, static_cast<float*>(y), idx)),
+      (maxpool_idx_fwd_kernel<__nv_bfloat16><<<grid_for(total, 16), kThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(x), N, H, W, C, Ho, Wo, static_cast<__nv_bfloat16*>(y), idx)));
+  DT_LAUNCH_CHECK();
+  return DT_OK;
+}
+
+int dt_maxpool3x3s2_bwd_idx(const uint8_t* idx, const void* gout, const void* addend, int N, int H, int W, int C, int dtype,
+                            void* gx, dt_stream_t stream) {
+  DT_ARCH_GUARD();
+  const int vn = dtype == DT_BF16 ? 8 : 4;
+  DT_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && C % vn == 0 && (dtype == DT_F32 || dtype == DT_BF16), DT_ERR_BAD_SHAPE,
+             "dt_maxpool3x3s2_bwd_idx: bad shape (C=%d must be a multiple of %d)", C, vn);
+  DT_REQUIRE((reinterpret_cast<uintptr_t>(idx) | reinterpret_cast<uintptr_t>(gout) | reinterpret_cast<uintptr_t>(addend) |
+              reinterpret_cast<uintptr_t>(gx)) % 16 == 0, DT_ERR_BAD_ALIGN, "dt_maxpool3x3s2_bwd_idx: tensors must be 16-byte aligned");
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int64_t total = static_cast<int64_t>(N) * H * W * (C / vn);
+  DT_DTYPE_SWITCH(dtype,
+      (maxpool_idx_bwd_kernel<float><<<grid_for(total, 16), kThreads, 0, s>>>(idx, static_cast<const float*>(gout), static_cast<const float*>(addend), N, H, W, C, Ho, Wo, static_cast<float*>(gx))),
+      (maxpool_idx_bwd_kernel<__nv_bfloat16><<<grid_for(total, 16), kThreads, 0, s>>>(idx, static_cast<const __nv_bfloat16*>(gout), static_cast<const __nv_bfloat16*>(addend), N, H, W, C, Ho, Wo, static_cast<__nv_bfloat16*>(gx))));
   DT_LAUNCH_CHECK();
   return DT_OK;
 }

@@ -125,6 +125,18 @@ def pack_input_nchw(x: torch.Tensor, channels: int, dtype: torch.dtype) -> torch
     return out
 
 
+def pack_input_nchw_frame(x: torch.Tensor, channels: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(N, C_src, H, W) fp32 -> the stem's zero-bordered bf16 frame (N, H+6, W+8, 4), interior at (3, 3)."""
+    x = _cuda(x, "x")
+    if x.dtype != torch.float32:
+        x = x.float()
+    N, Csrc, H, W = x.shape
+    if out is None:
+        out = torch.empty((N, H + 6, W + 8, 4), dtype=torch.bfloat16, device=x.device)
+    check(load().dt_pack_input_nchw_frame(x.data_ptr(), N, Csrc, channels, H, W, out.data_ptr(), stream_ptr()))
+    return out
+
+
 def stitch_mask(tile_masks: torch.Tensor, grid_x: int, tile0: int, mosaic_mask: torch.Tensor) -> None:
     """overlap-0 stitch of (ntiles, T, T) uint8 class ids into the (H, W) uint8 mosaic mask."""
     tile_masks = _cuda(tile_masks, "tile_masks")
@@ -362,6 +374,23 @@ def maxpool3x3s2_bwd(x: torch.Tensor, gout: torch.Tensor, addend: Optional[torch
     return gx
 
 
+def maxpool3x3s2_idx(x: torch.Tensor):
+    """training-step maxpool: (y, idx) with idx (N, Ho, Wo, C) uint8 = window position of the first maximum."""
+    N, H, W, Cc = x.shape
+    y = torch.empty((N, (H - 1) // 2 + 1, (W - 1) // 2 + 1, Cc), dtype=x.dtype, device=x.device)
+    idx = torch.empty(y.shape, dtype=torch.uint8, device=x.device)
+    check(load().dt_maxpool3x3s2_idx(x.data_ptr(), N, H, W, Cc, _dt(x), y.data_ptr(), idx.data_ptr(), stream_ptr()))
+    return y, idx
+
+
+def maxpool3x3s2_bwd_idx(idx: torch.Tensor, gout: torch.Tensor, x_shape, addend: Optional[torch.Tensor] = None) -> torch.Tensor:
+    N, H, W, Cc = x_shape
+    gx = torch.empty(tuple(x_shape), dtype=gout.dtype, device=gout.device)
+    check(load().dt_maxpool3x3s2_bwd_idx(idx.data_ptr(), gout.data_ptr(), ptr(addend), N, H, W, Cc, _dt(gout), gx.data_ptr(),
+                                         stream_ptr()))
+    return gx
+
+
 def upsample_concat(x_low: torch.Tensor, skip: Optional[torch.Tensor]) -> torch.Tensor:
     N, Hl, Wl, Cx = x_low.shape
     Cs = 0 if skip is None else skip.shape[-1]
@@ -470,4 +499,27 @@ def conv2d_wgrad_tc(x: torch.Tensor, gy: torch.Tensor, w_shape, stride: int = 1,
     with _Timed("wgrad", 2.0 * N * Ho * Wo * C_out * C_in * R * S, tag):
         check(lib.dt_conv2d_wgrad_tc(x.data_ptr(), gy.data_ptr(), N, Ho, Wo, C_in, x.shape[-1], C_out, Cg, R, stride,
                                      dw.data_ptr(), ws.data_ptr(), need, stream_ptr()))
+    return dw
+
+
+def stem_wgrad_tc_supported(N: int, H: int, W: int) -> bool:
+    return load().dt_stem_wgrad_tc_workspace(N, H, W) > 0
+
+
+def stem_wgrad_tc(x_frame: torch.Tensor, gy: torch.Tensor, w_shape, out: Optional[torch.Tensor] = None,
+                  tag: str = "wgrad.stem") -> torch.Tensor:
+    """tensor-core weight gradient of the 7x7/s2 stem: x_frame (N, H+6, W+8, 4) bf16 zero-bordered, gy (N, H/2, W/2, 64)
+    bf16 -> dw fp32 (64, C_in, 7, 7)."""
+    C_out, C_in, R, S = w_shape
+    N, Hp, Wp, _ = x_frame.shape
+    H, W = Hp - 6, Wp - 8
+    lib = load()
+    need = lib.dt_stem_wgrad_tc_workspace(N, H, W)
+    if need <= 0 or C_out != 64 or R != 7 or S != 7 or tuple(gy.shape) != (N, H // 2, W // 2, 64):
+        raise _lib.DeadtreesB200Error(f"dt_stem_wgrad_tc does not support frame {tuple(x_frame.shape)} gy {tuple(gy.shape)}")
+    ws = torch.empty((need + 3) // 4, dtype=torch.float32, device=gy.device)
+    dw = out if out is not None else torch.empty(tuple(w_shape), dtype=torch.float32, device=gy.device)
+    with _Timed("wgrad", 2.0 * N * (H // 2) * (W // 2) * C_out * C_in * R * S, tag):
+        check(lib.dt_stem_wgrad_tc(x_frame.data_ptr(), gy.data_ptr(), N, H, W, C_in, dw.data_ptr(), ws.data_ptr(), need,
+                                   stream_ptr()))
     return dw

@@ -15,7 +15,7 @@ from typing import Dict, List, Optional
 import torch
 
 from . import ops
-from ._lib import CONV_TRANSPOSED, require_device
+from ._lib import CONV_TRANSPOSED, CONV_X_PAD3, require_device
 from .engine import RESNET34_LAYERS, RESNET34_PLANES
 from .parallel import GradBucketReducer, backward_param_order
 
@@ -24,7 +24,7 @@ BN_EPS, BN_MOMENTUM = 1e-5, 0.1
 
 class _ConvBN:
     """tape entry of one conv (+ BatchNorm (+ residual) (+ ReLU))."""
-    __slots__ = ("conv", "bn", "x", "y", "a", "relu", "stride", "pad", "mean", "invstd", "scale", "residual")
+    __slots__ = ("conv", "bn", "x", "y", "a", "relu", "stride", "pad", "mean", "invstd", "scale", "residual", "frame")
 
     def __init__(self, **kw):
         for k in self.__slots__:
@@ -80,12 +80,17 @@ class UnetTrainEngine:
         return self.flat_params
 
     # ---- forward pieces --------------------------------------------------------------------------------
-    def _conv_raw(self, x: torch.Tensor, wname: str, stride: int, pad: int) -> torch.Tensor:
-        """raw convolution output (no BN / activation) of x (N, H, W, C_x) with the master weights `wname`."""
+    def _conv_raw(self, x: torch.Tensor, wname: str, stride: int, pad: int, frame: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """raw convolution output (no BN / activation) of x (N, H, W, C_x) with the master weights `wname`; `frame`: the
+        stem's zero-bordered input frame (x is then its interior view)."""
         w = self.params[wname]
         C_out, C_in, R, S = w.shape
         N, H, W, Cx = x.shape
         stem = R == 7
+        if frame is not None:
+            wp = ops.pack_conv_weight(w, 2)
+            return ops.conv2d(frame, wp, self._ones, self._zeros, N=N, H=H, W=W, C_in=Cx, C_x=Cx, C_out=C_out, R=R, S=S,
+                              stride=stride, pad=pad, relu=False, algo_cin=C_in, flags=CONV_X_PAD3, tag="train." + wname)
         if self.precision == "fp32":
             wp = ops.pack_conv_weight(w, 0)
         else:
@@ -94,8 +99,8 @@ class UnetTrainEngine:
                           stride=stride, pad=pad, relu=False, algo_cin=C_in, tag="train." + wname)
 
     def _conv_bn(self, tape: List, x: torch.Tensor, conv: str, bn: str, stride: int, pad: int, relu: bool = True,
-                 residual: Optional[torch.Tensor] = None) -> torch.Tensor:
-        y = self._conv_raw(x, conv + ".weight", stride, pad)
+                 residual: Optional[torch.Tensor] = None, frame: Optional[torch.Tensor] = None) -> torch.Tensor:
+        y = self._conv_raw(x, conv + ".weight", stride, pad, frame=frame)
         scale, shift, mean, invstd = ops.bn_train_stats(
             y, self.params[bn + ".weight"], self.params[bn + ".bias"], self.buffers.get(bn + ".running_mean"),
             self.buffers.get(bn + ".running_var"), BN_EPS, BN_MOMENTUM)
@@ -106,7 +111,7 @@ class UnetTrainEngine:
         self._rec("conv_bn_fwd", conv, x=x, y=y, a=a, residual=residual, mean=mean, invstd=invstd, scale=scale, shift=shift,
                   relu=relu, stride=stride, pad=pad)
         tape.append(_ConvBN(conv=conv, bn=bn, x=x, y=y, a=a, relu=relu, stride=stride, pad=pad, mean=mean,
-                            invstd=invstd, scale=scale, residual=residual))
+                            invstd=invstd, scale=scale, residual=residual, frame=frame))
         return a
 
     def forward(self, x_nchw: torch.Tensor):
@@ -115,11 +120,16 @@ class UnetTrainEngine:
         if T % 32:
             raise ValueError("tile size must be a multiple of 32")
         tape: List = []
-        x4 = ops.pack_input_nchw(x_nchw, self.in_channels, self.act_dtype)
-        f = {1: self._conv_bn(tape, x4, "encoder.conv1", "encoder.bn1", 2, 3)}
-        pool = ops.maxpool3x3s2(f[1])
+        if self.precision == "bf16" and self.wgrad_tc and ops.stem_wgrad_tc_supported(N, T, T):
+            # zero-bordered stem frame: the TMA im2col map over it feeds the forward conv AND the weight gradient
+            frame = ops.pack_input_nchw_frame(x_nchw, self.in_channels)
+            x4 = frame[:, 3:3 + T, 3:3 + T, :]
+        else:
+            frame, x4 = None, ops.pack_input_nchw(x_nchw, self.in_channels, self.act_dtype)
+        f = {1: self._conv_bn(tape, x4, "encoder.conv1", "encoder.bn1", 2, 3, frame=frame)}
+        pool, pool_idx = ops.maxpool3x3s2_idx(f[1])
         self._rec("maxpool_fwd", "pool", x=f[1], y=pool)
-        tape.append(("pool", f[1]))
+        tape.append(("pool", (f[1], pool_idx)))
         cur = pool
         for li, (planes, nblk) in enumerate(zip(RESNET34_PLANES, RESNET34_LAYERS), start=1):
             for b in range(nblk):
@@ -173,11 +183,14 @@ class UnetTrainEngine:
         self._rec("dgrad", wname, gy=gy, addend=addend, gx=gx, stride=stride, pad=pad, fp32_weights=fp32_weights)
         return gx
 
-    def _wgrad(self, x: torch.Tensor, gy: torch.Tensor, wname: str, stride: int, pad: int, want_bias: bool = False):
+    def _wgrad(self, x: torch.Tensor, gy: torch.Tensor, wname: str, stride: int, pad: int, want_bias: bool = False,
+               frame: Optional[torch.Tensor] = None):
         w = self.params[wname]
         out = self.reducer.view(wname)
         bname = wname[:-len("weight")] + "bias"
-        if self.precision == "bf16" and self.wgrad_tc and ops.wgrad_tc_supported(x, gy, w.shape, stride, pad):
+        if frame is not None:
+            dw, db = ops.stem_wgrad_tc(frame, gy, w.shape, out=out, tag="wgrad." + wname), None
+        elif self.precision == "bf16" and self.wgrad_tc and ops.wgrad_tc_supported(x, gy, w.shape, stride, pad):
             dw = ops.conv2d_wgrad_tc(x, gy, w.shape, stride, out=out, tag="wgrad." + wname)
             db = ops.channel_sum(gy, w.shape[0], out=self.reducer.view(bname)) if want_bias else None
         else:
@@ -200,7 +213,7 @@ class UnetTrainEngine:
         grads[e.bn + ".weight"], grads[e.bn + ".bias"] = dgamma, dbeta
         self._rec("bn_bwd", e.bn, g=g, a=e.a if e.relu else None, y=e.y, mean=e.mean, invstd=e.invstd, scale=e.scale,
                   gy=gy, gz=gz, dgamma=dgamma, dbeta=dbeta)
-        grads[e.conv + ".weight"], _ = self._wgrad(e.x, gy, e.conv + ".weight", e.stride, e.pad)
+        grads[e.conv + ".weight"], _ = self._wgrad(e.x, gy, e.conv + ".weight", e.stride, e.pad, frame=e.frame)
         gx = self._dgrad(gy, e.conv + ".weight", e.x.shape, e.stride, e.pad, addend=addend) if need_dx else None
         return gx, gz
 
@@ -246,10 +259,10 @@ class UnetTrainEngine:
                     g, _ = self._conv_bn_bwd(ed, gz, grads, addend=gx)
                 else:
                     g, _ = self._conv_bn_bwd(e1, g_a1, grads, addend=gz)
-        kind, f1 = it.pop()
+        kind, (f1, pool_idx) = it.pop()
         assert kind == "pool"
         gp = g
-        g = ops.maxpool3x3s2_bwd(f1, gp, addend=g_skip.get(1))
+        g = ops.maxpool3x3s2_bwd_idx(pool_idx, gp, f1.shape, addend=g_skip.get(1))
         self._rec("maxpool_bwd", "pool", x=f1, gout=gp, addend=g_skip.get(1), gx=g)
         e0 = it.pop()
         self._conv_bn_bwd(e0, g, grads, need_dx=False)

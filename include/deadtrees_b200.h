@@ -75,6 +75,9 @@ int dt_tile_gather_normalize(const uint8_t* mosaic, int H, int W, int C, int64_t
  * deadtrees/deployment/inference.py:57-59), zero-fills the rest. */
 int dt_pack_input_nchw(const float* x, int N, int C_src, int C, int H, int W, int out_dtype, void* out,
                        dt_stream_t stream);
+/* The same conversion into the bf16 stem frame (N, H+6, W+8, 4) of dt_conv2d_fwd's DT_CONV_X_PAD3 layout: interior at
+ * offset (3, 3), the zero border written by the kernel (the caller need not clear the frame). */
+int dt_pack_input_nchw_frame(const float* x, int N, int C_src, int C, int H, int W, void* out, dt_stream_t stream);
 
 /* ---- K12: stitching ----------------------------------------------------------------------------
  * dt_stitch_mask_u8: Tiler.put_batches at overlap 0 (deadtrees/deployment/tiler.py:147-170 ->
@@ -215,6 +218,12 @@ int dt_add(const void* a, const void* b, int64_t n, int dtype, void* out, dt_str
  * x (N, H, W, C) is the pool input, gout (N, Ho, Wo, C); gx = addend (may be NULL) + pooled gradient. */
 int dt_maxpool3x3s2_bwd(const void* x, const void* gout, const void* addend, int N, int H, int W, int C, int dtype,
                         void* gx, dt_stream_t stream);
+/* Index form used by the training step (C a multiple of 8 for bf16 / 4 for fp32): the forward also stores, per output
+ * element, the window position dy*3+dx (0..8) of its first maximum in idx (N, Ho, Wo, C) uint8; the backward gathers
+ * gout through idx without re-reading the pool input.  Same results as dt_maxpool3x3s2 / dt_maxpool3x3s2_bwd. */
+int dt_maxpool3x3s2_idx(const void* x, int N, int H, int W, int C, int dtype, void* y, uint8_t* idx, dt_stream_t stream);
+int dt_maxpool3x3s2_bwd_idx(const uint8_t* idx, const void* gout, const void* addend, int N, int H, int W, int C, int dtype,
+                            void* gx, dt_stream_t stream);
 /* cat([nearest_x2(x_low), skip], C) materialised for the training path, and its backward
  * (g_x_low = 2x2 block sums of g_cat[..., :Cx]; g_skip = g_cat[..., Cx:]).  H, W: full resolution. */
 int dt_upsample_concat(const void* x_low, const void* skip, int N, int H, int W, int Cx, int Cs, int dtype, void* out,
@@ -252,6 +261,16 @@ int64_t dt_conv2d_wgrad_tc_workspace(int N, int Ho, int Wo, int C_in, int C_out,
 int dt_conv2d_wgrad_tc(const void* x, const void* gy, int N, int Ho, int Wo, int C_in, int x_cstride, int C_out,
                        int gy_cstride, int ksize, int stride, float* dw_oihw, float* workspace, int64_t workspace_bytes,
                        dt_stream_t stream);
+
+/* Weight gradient of the 7x7 / stride-2 / pad-3 stem (encoder.conv1) on the tensor cores.  x_frame is the zero-bordered
+ * bf16 frame (N, H+6, W+8, 4) the forward stem reads (DT_CONV_X_PAD3); the SAME overlapping-stride im2col tensor map is
+ * the B operand, gy (N, H/2, W/2, 64) bf16 the A operand (both MN-major, K = output pixels); seven 64 x 32 fp32
+ * accumulators (one per filter row) stay in TMEM over all tiles of a CTA, per-CTA partials are reduced in a fixed order
+ * (deterministic).  dw fp32 OIHW (64, C_in, 7, 7) overwritten, C_in <= 4.  DT_ERR_UNSUPPORTED when the output grid does
+ * not tile into 128-pixel boxes (as dt_conv2d_fwd's stem path). */
+int64_t dt_stem_wgrad_tc_workspace(int N, int H, int W);
+int dt_stem_wgrad_tc(const void* x_frame, const void* gy, int N, int H, int W, int C_in, float* dw_oihw, float* workspace,
+                     int64_t workspace_bytes, dt_stream_t stream);
 
 /* ---- O1: optimizer ------------------------------------------------------------------------------
  * torch.optim.Adam step (segmodel.py:420-425 defaults) with the Lightning global-norm clip

@@ -281,6 +281,53 @@ def test_wgrad_tensor_core_padded_channels():
     assert report("wgrad tcgen05 head 16->3", dw.cpu(), w.grad)[1] < 1e-4
 
 
+@pytest.mark.parametrize("cin,N,T", [(4, 2, 256), (3, 1, 256), (4, 4, 64), (4, 8, 32), (3, 2, 128)])
+def test_stem_wgrad_tensor_core(cin, N, T):
+    """tcgen05 weight gradient of the 7x7/s2 stem (TMA im2col map as the MN-major B operand) against torch autograd on
+    the bf16-rounded operands."""
+    g = torch.Generator().manual_seed(cin * 100 + N + T)
+    x = torch.randn(N, cin, T, T, generator=g).to(torch.bfloat16).float()
+    gy = torch.randn(N, 64, T // 2, T // 2, generator=g).to(torch.bfloat16).float()
+    w = torch.zeros(64, cin, 7, 7, requires_grad=True)
+    F.conv2d(x, w, None, 2, 3).backward(gy)
+    assert ops.stem_wgrad_tc_supported(N, T, T)
+    frame = ops.pack_input_nchw_frame(x.cuda(), cin)
+    assert frame.shape == (N, T + 6, T + 8, 4)
+    assert torch.equal(frame[:, 3:3 + T, 3:3 + T, :cin].float().cpu(), x.permute(0, 2, 3, 1))
+    border = frame.clone()
+    border[:, 3:3 + T, 3:3 + T, :cin] = 0
+    assert not bool(border.any())        # zero border and zero padding channels, written by the kernel
+    dw = ops.stem_wgrad_tc(frame, nhwc(gy, torch.bfloat16), w.shape)
+    torch.cuda.synchronize()
+    err, rel = report(f"stem wgrad tcgen05 cin={cin} N={N} T={T}", dw.cpu(), w.grad)
+    assert rel < 1e-4
+    dw2 = ops.stem_wgrad_tc(frame, nhwc(gy, torch.bfloat16), w.shape)
+    assert torch.equal(dw, dw2)          # fixed-order split reduction: deterministic
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("N,H,W,C,add", [(2, 16, 12, 64, True), (1, 7, 9, 8, False), (3, 32, 32, 16, True)])
+def test_maxpool_index_form(dtype, N, H, W, C, add):
+    """maxpool 3x3/s2/p1 forward with first-maximum positions + gather backward through them, against torch
+    (values in a small set so that ties are frequent: the gradient must go to the FIRST maximum)."""
+    g = torch.Generator().manual_seed(N * H + C)
+    x = torch.randint(-3, 4, (N, C, H, W), generator=g).float().requires_grad_(True)
+    y_ref = F.max_pool2d(x, 3, 2, 1)
+    gout = torch.randn(y_ref.shape, generator=g).to(dtype).float()
+    y_ref.backward(gout)
+    addend = torch.randn(N, C, H, W, generator=g).to(dtype).float() if add else None
+    y, idx = ops.maxpool3x3s2_idx(nhwc(x.detach(), dtype))
+    gx = ops.maxpool3x3s2_bwd_idx(idx, nhwc(gout, dtype), (N, H, W, C), addend=nhwc(addend, dtype) if add else None)
+    old = ops.maxpool3x3s2_bwd(nhwc(x.detach(), dtype), nhwc(gout, dtype), addend=nhwc(addend, dtype) if add else None)
+    torch.cuda.synchronize()
+    assert torch.equal(nchw(y), y_ref.detach())
+    assert int(idx.max()) <= 8
+    ref = x.grad + (addend if add else 0)
+    tol = 1e-6 if dtype == torch.float32 else 1e-2
+    assert report("maxpool idx bwd", nchw(gx), ref)[1] < tol
+    assert report("maxpool idx vs recompute kernel", nchw(gx), nchw(old))[1] < tol
+
+
 @pytest.mark.parametrize("cin,cout,N,H", [(64, 64, 2, 32), (192, 64, 1, 16), (32, 16, 1, 32), (768, 256, 2, 16)])
 def test_dgrad_through_forward_kernel(cin, cout, N, H):
     """data gradient of a 3x3/s1 conv = forward tcgen05 conv of gy with the flipped, transposed weights (+ addend)."""
