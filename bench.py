@@ -307,10 +307,15 @@ def main_b200(a):
         step_device()
     sampler = ClockSampler(local)
     sampler.start()
-    ms_total, launches, prof = timed(step_device, a.steps, profile=not a.no_profile)
+    ms_total, launches, _ = timed(step_device, a.steps)
     clocks = sampler.stop()
     ms_step = ms_total / a.steps
     value = n_tiles / (ms_step / 1e3)
+    # per-launch CUDA events (the roofline numbers) are taken in a separate pass so that the ~1500 event records of a
+    # step do not sit inside the headline's timed region
+    prof, ms_prof_total = None, ms_total
+    if not a.no_profile:
+        ms_prof_total, _, prof = timed(step_device, a.steps, profile=True)
 
     # end-to-end through the public pipeline with host buffers (pinned), same number of steps
     for _ in range(2):
@@ -344,7 +349,7 @@ def main_b200(a):
             ach = wc / tc / 1e12
             out["roofline"] = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit GEMM, all conv layers)",
                                "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"],
-                               "traffic": None, "launches": nc, "share_of_step": tc * 1e3 / ms_total,
+                               "traffic": None, "launches": nc, "share_of_step": tc * 1e3 / ms_prof_total,
                                "flops_per_tile": conv_flops_per_tile(T, 3, 3), "peak_source": pk["source"]}
         hb = {}
         if tg > 0:
@@ -353,6 +358,26 @@ def main_b200(a):
         if ts > 0:
             hb["stitch"] = {"achieved": ws / ts / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
                             "frac": ws / ts / 1e9 / pk["hbm_gbs"], "launches": ns}
+        if world == 1 and n_tiles * (T + 6) * (T + 8) * 8 < (8 << 30):
+            # the same gather kernel over the WHOLE mosaic in one launch (the pipeline launches it per batch of
+            # batch_tiles tiles, ~80 MB, where launch ramp and tail are a third of the kernel's 20 us)
+            frame = torch.zeros((n_tiles, T + 6, T + 8, 4), dtype=torch.bfloat16, device=dev)
+            from deadtrees_b200.data.deadtreedata import normalize_constants
+            off, sc = normalize_constants(3, None, None)
+            best = None
+            for i in range(5):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                ops.tile_gather_normalize(mosaic, "hwc", 3, T, ov, (gy, gx), 0, n_tiles, off, sc, out=frame, pad=3)
+                e1.record()
+                torch.cuda.synchronize()
+                if i >= 2:
+                    best = min(best, e0.elapsed_time(e1)) if best else e0.elapsed_time(e1)
+            gb = n_tiles * T * T * 3 * (1 + 2) / 1e9
+            hb["gather_normalize_whole_mosaic"] = {"achieved": gb / (best / 1e3), "peak": pk["hbm_gbs"], "unit": "GB/s",
+                                                   "frac": gb / (best / 1e3) / pk["hbm_gbs"], "launches": 1,
+                                                   "us": 1e3 * best, "bytes": gb * 1e9}
+            del frame
         out["roofline_hbm"] = hb
         if a.layer_table and rank == 0:
             per = {}
@@ -362,8 +387,8 @@ def main_b200(a):
             with open(a.layer_table, "w") as fh:
                 fh.write(f"{'layer':34s} {'launches':>8s} {'avg_us':>9s} {'TFLOP/s':>9s} {'share%':>7s}\n")
                 for tag, (ms, wk, n) in per.items():
-                    fh.write(f"{tag:34s} {n:8d} {1e3 * ms / n:9.1f} {wk / (ms / 1e3) / 1e12:9.1f} {100 * ms / ms_total:7.2f}\n")
-                fh.write(f"conv total {1e3 * tc:.1f} ms of {ms_total:.1f} ms; gather {1e3 * tg:.2f} ms; stitch {1e3 * ts:.2f} ms\n")
+                    fh.write(f"{tag:34s} {n:8d} {1e3 * ms / n:9.1f} {wk / (ms / 1e3) / 1e12:9.1f} {100 * ms / ms_prof_total:7.2f}\n")
+                fh.write(f"conv total {1e3 * tc:.1f} ms of {ms_prof_total:.1f} ms; gather {1e3 * tg:.2f} ms; stitch {1e3 * ts:.2f} ms\n")
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         tps, times, n_s, used_ref = run_cpu_sample(a, a.cpu_sample_tiles, repeats=3, warm=1)
         out["cpu_baseline"] = {"value": tps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",

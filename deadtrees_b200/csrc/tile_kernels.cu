@@ -151,6 +151,107 @@ __global__ void gather_normalize_kernel(const uint8_t* __restrict__ mosaic, int 
   }
 }
 
+// bf16 fast path of the gather (the inference pipeline's K1): same arithmetic, organised for the memory system.
+// The generic kernel is issue-bound (ncu: 221 instructions per 4 pixels, 76 % issue-active, 19 % DRAM); here
+//   * blockIdx.y = tile and each thread walks R rows of it, so the tile -> mosaic coordinate math (one division by the
+//     grid width through a host-side magic multiplier) is paid once per R rows;
+//   * the source layout is a template parameter (the untaken paths and their address checks disappear);
+//   * uint8 -> fp32 through PRMT + FADD (0x4B000000 | byte is the float 2^23 + byte; minus 2^23 is exact) instead of
+//     I2F conversions; then the reference's subtract and multiply-by-reciprocal, unfused;
+//   * a thread owns 4 consecutive pixels = 32 contiguous output bytes; in the stem frame those start 8 bytes off a
+//     16-byte boundary (3 border pixels), so the first pixel of each lane travels to the previous lane and every lane
+//     stores two ALIGNED 16-byte vectors {p1,p2} {p3,next p0}; only row ends store single 8-byte pixels.
+// LAYOUT: 0 any strides (guarded byte loads)  1 interleaved RGB, 4-byte aligned rows  2 interleaved RGBA, 16-byte
+// aligned  3 planar, 4-byte aligned rows and planes.  Requires q = T/4 to divide 256 (q_shift = log2 q).
+template <int LAYOUT>
+__global__ void __launch_bounds__(256)
+gather_normalize_bf16_kernel(const uint8_t* __restrict__ mosaic, int H, int W, int C, int64_t row_stride,
+                             int64_t pix_stride, int64_t chan_stride, int T, int q_shift, int step, int gx,
+                             uint32_t gx_magic, int tile0, NormParams np, int pad, int out_hp, int out_wp,
+                             uint2* __restrict__ out) {
+  constexpr int R = 4;
+  const int q = T >> 2;
+  const int t = blockIdx.y;
+  const int cell = tile0 + t;
+  const int ty = static_cast<int>(__umulhi(static_cast<uint32_t>(cell), gx_magic));
+  const int tx = cell - ty * gx;
+  const int lin = blockIdx.x * 256 + threadIdx.x;
+  const int x4 = lin & (q - 1);
+  const int y0 = lin >> q_shift;
+  const int ystep = (gridDim.x * 256) >> q_shift;
+  const int gx0 = tx * step + x4 * 4;
+  const bool col_in = gx0 < W;
+  const bool full = gx0 + 3 < W;
+  const int lane = threadIdx.x & 31;
+  const uint8_t* col_base = mosaic + gx0 * pix_stride;
+#pragma unroll 1
+  for (int it = 0; it < R; ++it) {
+    const int y = y0 + it * ystep;
+    const bool live = y < T;
+    const int gy0 = ty * step + y;
+    uint32_t px[4] = {0u, 0u, 0u, 0u};  // px[j] = bytes c0..c3 of pixel j
+    if (live && col_in && gy0 < H) {
+      const uint8_t* base = col_base + gy0 * row_stride;
+      if (LAYOUT == 1 && full) {
+        const uint32_t a = __ldg(reinterpret_cast<const uint32_t*>(base));
+        const uint32_t b = __ldg(reinterpret_cast<const uint32_t*>(base) + 1);
+        const uint32_t c = __ldg(reinterpret_cast<const uint32_t*>(base) + 2);
+        px[0] = a;                                  // byte 3 of each word is ignored below (C == 3)
+        px[1] = __byte_perm(a, b, 0x4543);          // a.b3 b.b0 b.b1
+        px[2] = __byte_perm(b, c, 0x4432);          // b.b2 b.b3 c.b0
+        px[3] = c >> 8;
+      } else if (LAYOUT == 2 && full) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(base));
+        px[0] = v.x; px[1] = v.y; px[2] = v.z; px[3] = v.w;
+      } else if (LAYOUT == 3 && full) {
+        for (int c = 0; c < C; ++c) {               // planar: one aligned 32-bit load per channel
+          const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(base + c * chan_stride));
+#pragma unroll
+          for (int j = 0; j < 4; ++j) px[j] |= ((v >> (8 * j)) & 0xffu) << (8 * c);
+        }
+      } else {
+        for (int j = 0; j < 4; ++j) {
+          if (gx0 + j < W) {
+            for (int c = 0; c < C; ++c)
+              px[j] |= static_cast<uint32_t>(__ldg(base + j * pix_stride + c * chan_stride)) << (8 * c);
+          }
+        }
+      }
+    }
+    uint2 o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float v[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (LAYOUT == 1 && c == 3) { v[c] = 0.f; continue; }      // RGB: the fourth channel is padding
+        const float u = __fadd_rn(__uint_as_float(__byte_perm(px[j], 0x4B000000u, 0x7650 + c)), -8388608.0f);
+        // subtract, then multiply by the reciprocal (albumentations Normalize); no FMA contraction.  Channels >= C
+        // have offset = scale = 0: (u - 0) * 0 = +0, the padding value, whatever byte sits there
+        v[c] = __fmul_rn(__fsub_rn(u, np.offset[c]), np.scale[c]);
+      }
+      o[j] = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
+    }
+    if (!pad) {          // dense (ntiles, T, T, 4): 32 aligned bytes per thread
+      if (live) {
+        uint4* dst = reinterpret_cast<uint4*>(out + ((static_cast<int64_t>(t) * T + y) * q + x4) * 4);
+        dst[0] = make_uint4(o[0].x, o[0].y, o[1].x, o[1].y);
+        dst[1] = make_uint4(o[2].x, o[2].y, o[3].x, o[3].y);
+      }
+      continue;
+    }
+    const uint32_t nx = __shfl_down_sync(0xffffffffu, o[0].x, 1);
+    const uint32_t ny = __shfl_down_sync(0xffffffffu, o[0].y, 1);
+    if (live) {
+      uint2* dst = out + (static_cast<int64_t>(t) * out_hp + y + pad) * out_wp + x4 * 4 + pad;   // p0: 8 mod 16 bytes
+      if (lane == 0 || x4 == 0) dst[0] = o[0];
+      *reinterpret_cast<uint4*>(dst + 1) = make_uint4(o[1].x, o[1].y, o[2].x, o[2].y);
+      if (lane < 31 && x4 + 1 < q) *reinterpret_cast<uint4*>(dst + 3) = make_uint4(o[3].x, o[3].y, nx, ny);
+      else dst[3] = o[3];
+    }
+  }
+}
+
 // overlap-0 stitch: one thread = V consecutive pixels of one tile row.
 template <int V>
 __global__ void stitch_mask_kernel(const uint8_t* __restrict__ tiles, int T, int gx, int tile0, int ntiles,
@@ -264,7 +365,7 @@ __global__ void stitch_blend_v8_kernel(const __nv_bfloat16* __restrict__ logits,
         uint32_t raw[4 * K];   // 8 pixels x K bf16 = K uint4
 #pragma unroll
         for (int q = 0; q < K; ++q) {
-          const uint4 v = ld_nc_v4(src + q);
+          const uint4 v = __ldg(src + q);     // L1-allocating: the K vectors of a thread share 32-byte sectors
           raw[4 * q] = v.x; raw[4 * q + 1] = v.y; raw[4 * q + 2] = v.z; raw[4 * q + 3] = v.w;
         }
 #pragma unroll
@@ -282,19 +383,46 @@ __global__ void stitch_blend_v8_kernel(const __nv_bfloat16* __restrict__ logits,
       }
     }
     uint8_t best[8];
+    if (blended == nullptr) {
+      // mask only: x -> fl(x / wsum) is monotone, so the class is the first maximum of the un-normalised sums - except
+      // that an EARLIER class whose sum is within rounding distance of the maximum can tie with it after the division
+      // (first maximum wins, as np.argmax over the blended logits); only such near-ties pay for the IEEE divisions.
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      int b = 0;
-      float bv = __fdiv_rn(acc[j][0], wsum[j]);
-      const bool live = x0 + j < W;
-      if (blended && live) blended[(static_cast<int64_t>(y) * W + x0 + j) * K] = bv;
+      for (int j = 0; j < 8; ++j) {
+        int b = 0;
+        float bv = acc[j][0];
 #pragma unroll
-      for (int k = 1; k < K; ++k) {
-        const float v = __fdiv_rn(acc[j][k], wsum[j]);
-        if (blended && live) blended[(static_cast<int64_t>(y) * W + x0 + j) * K + k] = v;
-        if (v > bv) { bv = v; b = k; }
+        for (int k = 1; k < K; ++k)
+          if (acc[j][k] > bv) { bv = acc[j][k]; b = k; }
+        bool near = false;
+#pragma unroll
+        for (int k = 0; k < K - 1; ++k)
+          near = near || (k < b && bv - acc[j][k] <= 4.76837158e-7f * fmaxf(fabsf(bv), fabsf(acc[j][k])));
+        if (near) {
+          const float qb = __fdiv_rn(bv, wsum[j]);
+          int nb = b;
+#pragma unroll
+          for (int k = K - 2; k >= 0; --k)       // static indices: acc stays in registers
+            if (k < b && __fdiv_rn(acc[j][k], wsum[j]) == qb) nb = k;
+          b = nb;
+        }
+        best[j] = static_cast<uint8_t>(b);
       }
-      best[j] = static_cast<uint8_t>(b);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        int b = 0;
+        float bv = __fdiv_rn(acc[j][0], wsum[j]);
+        const bool live = x0 + j < W;
+        if (live) blended[(static_cast<int64_t>(y) * W + x0 + j) * K] = bv;
+#pragma unroll
+        for (int k = 1; k < K; ++k) {
+          const float v = __fdiv_rn(acc[j][k], wsum[j]);
+          if (live) blended[(static_cast<int64_t>(y) * W + x0 + j) * K + k] = v;
+          if (v > bv) { bv = v; b = k; }
+        }
+        best[j] = static_cast<uint8_t>(b);
+      }
     }
     uint8_t* dst = mask + static_cast<int64_t>(y) * W + x0;
     if (x0 + 8 <= W && (reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
@@ -305,6 +433,234 @@ __global__ void stitch_blend_v8_kernel(const __nv_bfloat16* __restrict__ logits,
     } else {
       for (int j = 0; j < 8 && x0 + j < W; ++j) dst[j] = best[j];
     }
+  }
+}
+
+// ---- mask-only blended stitch in two warp-uniform passes (bf16 logits, T and step multiples of 8) ----------------
+// ncu of the one-pass kernel above: 695 instructions per 8 pixels, local-memory traffic, 2 TB/s.  77 % of the pixels
+// of the cfg2 mosaic are covered by ONE tile; for them  argmax_k fl(fl(z_k * w) / w)  is the first maximum of the raw
+// bf16 logits (two different bf16 values differ by >= 2^-8 relative, the two fp32 roundings move them by 2^-24).
+//   pass 1  every 8-pixel group covered by a single tile: K 16-byte loads, compares, one 8-byte store; groups inside
+//           an overlap strip return at once (whole rows of blocks for the horizontal strips);
+//   pass 2  only the overlap strips (rows [ty*step, ty*step+ov) and column groups [tx*step, tx*step+ov)): the blend
+//           arithmetic of the reference order (multiply, add; first maximum of the sums; IEEE division on near-ties).
+// Both passes are warp-uniform; the results equal stitch_blend_kernel bit for bit.
+struct FastDiv {
+  uint32_t magic;
+  int d;
+  __device__ __forceinline__ int div(int x) const { return static_cast<int>(__umulhi(static_cast<uint32_t>(x), magic)); }
+};
+
+template <int K>
+__device__ __forceinline__ void unpack_group(const uint4* __restrict__ src, float (&z)[8][K]) {
+  uint32_t raw[4 * K];
+#pragma unroll
+  for (int q = 0; q < K; ++q) {
+    const uint4 v = __ldg(src + q);
+    raw[4 * q] = v.x; raw[4 * q + 1] = v.y; raw[4 * q + 2] = v.z; raw[4 * q + 3] = v.w;
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const int e = j * K + k;
+      const uint32_t word = raw[e >> 1];
+      z[j][k] = (e & 1) ? __uint_as_float(word & 0xffff0000u) : __uint_as_float(word << 16);
+    }
+  }
+}
+
+__device__ __forceinline__ void store_mask8(uint8_t* __restrict__ mask, int y, int x0, int W, const uint32_t (&best)[8]) {
+  uint8_t* dst = mask + static_cast<int64_t>(y) * W + x0;
+  if (x0 + 8 <= W && (reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
+    uint2 pk;
+    pk.x = best[0] | (best[1] << 8) | (best[2] << 16) | (best[3] << 24);
+    pk.y = best[4] | (best[5] << 8) | (best[6] << 16) | (best[7] << 24);
+    *reinterpret_cast<uint2*>(dst) = pk;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) if (x0 + j < W) dst[j] = static_cast<uint8_t>(best[j]);
+  }
+}
+
+// Thread blocks are (256 / cb) rows x cb column groups, cb a power of two chosen by the host to fit the row length.
+template <int K>
+__global__ void __launch_bounds__(256)
+stitch_single_kernel(const __nv_bfloat16* __restrict__ logits, int T, int step, FastDiv fd, int gy, int gx, int ty_base,
+                     uint8_t* __restrict__ mask, int W, int row0, int nrows, int cb_shift) {
+  const int r = blockIdx.y * (256 >> cb_shift) + (threadIdx.x >> cb_shift);
+  if (r >= nrows) return;
+  const int y = row0 + r;
+  const int ty0 = (y - T + 1 <= 0) ? 0 : fd.div(y - T + step);
+  const int ty1 = min(gy - 1, fd.div(y));
+  if (ty0 != ty1) return;                                  // a row of a horizontal overlap strip: pass 2
+  const int x0 = ((blockIdx.x << cb_shift) + (threadIdx.x & ((1 << cb_shift) - 1))) << 3;
+  if (x0 >= W) return;
+  const int tx0 = (x0 - T + 1 <= 0) ? 0 : fd.div(x0 - T + step);
+  const int tx1 = min(gx - 1, fd.div(x0));
+  if (tx0 != tx1) return;                                  // a column group of a vertical overlap strip: pass 2
+  const int ly = y - ty0 * step, lx = x0 - tx0 * step;
+  float z[8][K];
+  unpack_group<K>(reinterpret_cast<const uint4*>(
+      logits + ((static_cast<int64_t>(ty0 - ty_base) * gx + tx0) * T * T + static_cast<int64_t>(ly) * T + lx) * K), z);
+  uint32_t best[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    uint32_t b = 0;
+    float bv = z[j][0];
+#pragma unroll
+    for (int k = 1; k < K; ++k)
+      if (z[j][k] > bv) { bv = z[j][k]; b = k; }
+    best[j] = b;
+  }
+  store_mask8(mask, y, x0, W, best);
+}
+
+template <int K>
+__device__ __forceinline__ void load_raw(const __nv_bfloat16* __restrict__ p, uint4 (&raw)[K]) {
+#pragma unroll
+  for (int q = 0; q < K; ++q) raw[q] = __ldg(reinterpret_cast<const uint4*>(p) + q);
+}
+
+template <int K>
+__device__ __forceinline__ void blend_accumulate(const uint4 (&raw)[K], float wy, const float* __restrict__ winx,
+                                                 float (&acc)[8][K], float (&wsum)[8]) {
+  const float4 wa = __ldg(reinterpret_cast<const float4*>(winx));
+  const float4 wb = __ldg(reinterpret_cast<const float4*>(winx) + 1);
+  const float wx[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+  uint32_t words[4 * K];
+#pragma unroll
+  for (int q = 0; q < K; ++q) { words[4 * q] = raw[q].x; words[4 * q + 1] = raw[q].y; words[4 * q + 2] = raw[q].z; words[4 * q + 3] = raw[q].w; }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float w = __fmul_rn(wy, wx[j]);
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const int e = j * K + k;
+      const uint32_t word = words[e >> 1];
+      const float z = (e & 1) ? __uint_as_float(word & 0xffff0000u) : __uint_as_float(word << 16);
+      acc[j][k] = __fadd_rn(acc[j][k], __fmul_rn(z, w));
+    }
+    wsum[j] = __fadd_rn(wsum[j], w);
+  }
+}
+
+// part 0: rows = the rows of the horizontal strips (strip-major), columns = all column groups of the row;
+// part 1: rows = mosaic rows (rows of horizontal strips return), columns = the column groups of the vertical strips.
+// The covering tiles are visited in (ty, tx) order two at a time, both tiles' loads in flight together.
+template <int K>
+__global__ void __launch_bounds__(256)
+stitch_strips_kernel(const __nv_bfloat16* __restrict__ logits, int T, int step, FastDiv fd, int gy, int gx, int ty_base,
+                     const float* __restrict__ win, uint8_t* __restrict__ mask, int H, int W, int row0, int nrows,
+                     int part, int first_strip, int nstrip_rows, int cb_shift) {
+  const int ov = T - step;
+  const int r = blockIdx.y * (256 >> cb_shift) + (threadIdx.x >> cb_shift);
+  const int c = (blockIdx.x << cb_shift) + (threadIdx.x & ((1 << cb_shift) - 1));
+  int y, x0;
+  if (part == 0) {
+    if (r >= nstrip_rows) return;
+    const int sq = r / ov;
+    y = (first_strip + sq) * step + (r - sq * ov);          // tile row first_strip+sq overlaps the previous one here
+    if (y < row0 || y >= row0 + nrows) return;
+    x0 = c << 3;
+    if (x0 >= W) return;
+  } else {
+    if (r >= nrows) return;
+    y = row0 + r;
+    const int ty0r = (y - T + 1 <= 0) ? 0 : fd.div(y - T + step);
+    if (ty0r != min(gy - 1, fd.div(y))) return;             // done by part 0
+    const int ov8 = ov >> 3;
+    if (c >= (gx - 1) * ov8) return;
+    const int strip = c / ov8;
+    x0 = (strip + 1) * step + ((c - strip * ov8) << 3);
+    if (x0 >= W) return;
+  }
+  const int ty0 = (y - T + 1 <= 0) ? 0 : fd.div(y - T + step);
+  const int tx0 = (x0 - T + 1 <= 0) ? 0 : fd.div(x0 - T + step);
+  const int ty1 = min(gy - 1, fd.div(y)), tx1 = min(gx - 1, fd.div(x0));
+  const int ntx = tx1 - tx0 + 1, n = (ty1 - ty0 + 1) * ntx;
+  float acc[8][K], wsum[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    wsum[j] = 0.f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) acc[j][k] = 0.f;
+  }
+  auto tile_ptr = [&](int i, int& ly, int& lx) {
+    const int ty = ty0 + i / ntx, tx = tx0 + i % ntx;
+    ly = y - ty * step; lx = x0 - tx * step;
+    return logits + ((static_cast<int64_t>(ty - ty_base) * gx + tx) * T * T + static_cast<int64_t>(ly) * T + lx) * K;
+  };
+  for (int i = 0; i < n; i += 2) {
+    int ly0, lx0, ly1 = 0, lx1 = 0;
+    uint4 raw0[K], raw1[K];
+    load_raw<K>(tile_ptr(i, ly0, lx0), raw0);
+    const bool two = i + 1 < n;
+    if (two) load_raw<K>(tile_ptr(i + 1, ly1, lx1), raw1);
+    blend_accumulate<K>(raw0, __ldg(win + ly0), win + lx0, acc, wsum);
+    if (two) blend_accumulate<K>(raw1, __ldg(win + ly1), win + lx1, acc, wsum);
+  }
+  uint32_t best[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    int b = 0;
+    float bv = acc[j][0];
+#pragma unroll
+    for (int k = 1; k < K; ++k)
+      if (acc[j][k] > bv) { bv = acc[j][k]; b = k; }
+    bool near = false;
+#pragma unroll
+    for (int k = 0; k < K - 1; ++k)
+      near = near || (k < b && bv - acc[j][k] <= 4.76837158e-7f * fmaxf(fabsf(bv), fabsf(acc[j][k])));
+    if (near) {        // an earlier class can tie with the maximum after the division: first maximum wins
+      const float qb = __fdiv_rn(bv, wsum[j]);
+      int nb = b;
+#pragma unroll
+      for (int k = K - 2; k >= 0; --k)       // static indices: acc stays in registers
+        if (k < b && __fdiv_rn(acc[j][k], wsum[j]) == qb) nb = k;
+      b = nb;
+    }
+    best[j] = static_cast<uint32_t>(b);
+  }
+  store_mask8(mask, y, x0, W, best);
+}
+
+// smallest waste of ceil(n / cb) * cb over cb in {32, 64, 128, 256}; ties go to the wider block row
+inline int pick_cb_shift(int n) {
+  int best_shift = 8, best_waste = (n + 255) / 256 * 256;
+  for (int sh = 7; sh >= 5; --sh) {
+    const int cb = 1 << sh, tot = (n + cb - 1) / cb * cb;
+    if (tot < best_waste) { best_waste = tot; best_shift = sh; }
+  }
+  return best_shift;
+}
+
+template <int K>
+void launch_stitch_two_pass(const __nv_bfloat16* lg, int T, int step, int gy, int gx, int ty_base, const float* win,
+                            uint8_t* mask, int H, int W, int row0, int nrows, cudaStream_t s) {
+  FastDiv fd;
+  fd.d = step;
+  fd.magic = static_cast<uint32_t>(((1ull << 32) + step - 1) / step);
+  const int W8 = (W + 7) / 8, ov = T - step;
+  const int sh = pick_cb_shift(W8), rows_pb = 256 >> sh;
+  stitch_single_kernel<K><<<dim3((W8 + (1 << sh) - 1) >> sh, (nrows + rows_pb - 1) / rows_pb), 256, 0, s>>>(
+      lg, T, step, fd, gy, gx, ty_base, mask, W, row0, nrows, sh);
+  if (ov == 0) return;
+  // horizontal strips that intersect [row0, row0 + nrows): tile rows `first`..`last` (>= 1)
+  int first = (row0 - ov + 1 <= 0) ? 1 : (row0 - ov + step) / step;          // smallest ty with ty*step + ov > row0
+  if (first < 1) first = 1;
+  int last = (row0 + nrows - 1) / step;
+  if (last > gy - 1) last = gy - 1;
+  if (last >= first) {
+    const int srows = (last - first + 1) * ov;
+    stitch_strips_kernel<K><<<dim3((W8 + (1 << sh) - 1) >> sh, (srows + rows_pb - 1) / rows_pb), 256, 0, s>>>(
+        lg, T, step, fd, gy, gx, ty_base, win, mask, H, W, row0, nrows, 0, first, srows, sh);
+  }
+  if (gx > 1) {
+    const int groups = (gx - 1) * (ov / 8);
+    const int sh1 = pick_cb_shift(groups), rows1 = 256 >> sh1;
+    stitch_strips_kernel<K><<<dim3((groups + (1 << sh1) - 1) >> sh1, (nrows + rows1 - 1) / rows1), 256, 0, s>>>(
+        lg, T, step, fd, gy, gx, ty_base, win, mask, H, W, row0, nrows, 1, 0, 0, sh1);
   }
 }
 
@@ -452,7 +808,34 @@ int dt_tile_gather_normalize(const uint8_t* mosaic, int H, int W, int C, int64_t
   }
   const int64_t total = static_cast<int64_t>(ntiles) * tile * (tile / 4);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (out_dtype == DT_BF16)
+  const int q = tile / 4;
+  int q_shift = -1;
+  for (int b = 0; b <= 8; ++b) if ((1 << b) == q) q_shift = b;
+  // magic multiplier for cell / gx (exact while cell * gx < 2^32)
+  const uint64_t cells = static_cast<uint64_t>(tile0) + ntiles;
+  if (out_dtype == DT_BF16 && ntiles <= 65535 && q_shift >= 0 && cells * gx < (1ull << 32) && gx > 1) {
+    const uint32_t magic = static_cast<uint32_t>(((1ull << 32) + gx - 1) / gx);
+    const int rows_per_pass = 256 >> q_shift;
+    const dim3 grid((tile + 4 * rows_per_pass - 1) / (4 * rows_per_pass), ntiles);
+    const uintptr_t mp = reinterpret_cast<uintptr_t>(mosaic);
+    int layout = 0;
+    if (step % 4 == 0) {
+      if (chan_stride == 1 && pix_stride == 3 && C == 3 && mp % 4 == 0 && row_stride % 4 == 0) layout = 1;
+      else if (chan_stride == 1 && pix_stride == 4 && C == 4 && mp % 16 == 0 && row_stride % 16 == 0) layout = 2;
+      else if (pix_stride == 1 && mp % 4 == 0 && row_stride % 4 == 0 && chan_stride % 4 == 0) layout = 3;
+    }
+#define DT_GATHER(L)                                                                                              \
+  gather_normalize_bf16_kernel<L><<<grid, kThreads, 0, s>>>(mosaic, H, W, C, row_stride, pix_stride, chan_stride, tile, \
+                                                           q_shift, step, gx, magic, tile0, np, out_pad, out_hp,  \
+                                                           out_wp, static_cast<uint2*>(out))
+    switch (layout) {
+      case 1: DT_GATHER(1); break;
+      case 2: DT_GATHER(2); break;
+      case 3: DT_GATHER(3); break;
+      default: DT_GATHER(0); break;
+    }
+#undef DT_GATHER
+  } else if (out_dtype == DT_BF16)
     gather_normalize_kernel<true><<<grid_for(total), kThreads, 0, s>>>(mosaic, H, W, C, row_stride, pix_stride,
                                                                       chan_stride, tile, step, gx, tile0, ntiles, np,
                                                                       out_pad, out_hp, out_wp, out);
@@ -508,8 +891,18 @@ int dt_stitch_blend_argmax(const void* logits, int dtype, int K, int T, int over
     case 3: DT_SB(LT, 3); break;       \
     default: DT_SB(LT, 4); break;      \
   }
-  if (dtype == DT_BF16 && T % 8 == 0 && step % 8 == 0 && reinterpret_cast<uintptr_t>(logits) % 16 == 0 &&
-      reinterpret_cast<uintptr_t>(win) % 16 == 0) {
+  const bool vec8 = dtype == DT_BF16 && T % 8 == 0 && step % 8 == 0 && reinterpret_cast<uintptr_t>(logits) % 16 == 0 &&
+                    reinterpret_cast<uintptr_t>(win) % 16 == 0;
+  if (vec8 && blended == nullptr && step > 1 &&
+      static_cast<int64_t>(H > W ? H : W) * step < (1ll << 32)) {
+    const __nv_bfloat16* lg = static_cast<const __nv_bfloat16*>(logits);
+    switch (K) {
+      case 1: launch_stitch_two_pass<1>(lg, T, step, gy, gx, ty_base, win, mosaic_mask, H, W, row0, nrows, s); break;
+      case 2: launch_stitch_two_pass<2>(lg, T, step, gy, gx, ty_base, win, mosaic_mask, H, W, row0, nrows, s); break;
+      case 3: launch_stitch_two_pass<3>(lg, T, step, gy, gx, ty_base, win, mosaic_mask, H, W, row0, nrows, s); break;
+      default: launch_stitch_two_pass<4>(lg, T, step, gy, gx, ty_base, win, mosaic_mask, H, W, row0, nrows, s); break;
+    }
+  } else if (vec8) {
     const int64_t total8 = static_cast<int64_t>(nrows) * ((W + 7) / 8);
     const __nv_bfloat16* lg = static_cast<const __nv_bfloat16*>(logits);
     switch (K) {

@@ -87,16 +87,19 @@ def test_gather_normalize_bit_exact(layout, C, Cm, H, W, T, ov):
         np.testing.assert_array_equal(part.cpu().numpy(), ref[1:-1])
 
 
-def test_gather_normalize_padded_frame():
+@pytest.mark.parametrize("layout,C", [("hwc", 3), ("hwc", 4), ("chw", 3)])
+@pytest.mark.parametrize("H,W,T,ov", [(150, 130, 64, 16), (600, 520, 256, 32), (70, 90, 32, 4), (100, 40, 36, 0)])
+def test_gather_normalize_padded_frame(layout, C, H, W, T, ov):
     """pad=3: tiles land at offset (3, 3) of a zero-bordered (T+6, T+8) frame (input layout of the TMA stem)."""
     rng = np.random.default_rng(12)
-    H, W, T, ov = 150, 130, 64, 16
-    m = rng.integers(0, 256, size=(H, W, 3), dtype=np.uint8)
+    m = rng.integers(0, 256, size=(H, W, C), dtype=np.uint8)
     gy, gx = overlap_grid(H, W, T, ov)
-    off, sc = normalize_constants(3)
-    src = torch.from_numpy(m).cuda()
-    dense = ops.tile_gather_normalize(src, "hwc", 3, T, ov, (gy, gx), 0, gy * gx, off, sc, dtype=torch.bfloat16)
-    frame = ops.tile_gather_normalize(src, "hwc", 3, T, ov, (gy, gx), 0, gy * gx, off, sc, dtype=torch.bfloat16, pad=3)
+    off, sc = normalize_constants(C)
+    src = torch.from_numpy(m if layout == "hwc" else np.ascontiguousarray(m.transpose(2, 0, 1))).cuda()
+    dense = ops.tile_gather_normalize(src, layout, C, T, ov, (gy, gx), 0, gy * gx, off, sc, dtype=torch.bfloat16)
+    ref32 = ops.tile_gather_normalize(src, layout, C, T, ov, (gy, gx), 0, gy * gx, off, sc, dtype=torch.float32)
+    assert torch.equal(dense, ref32.to(torch.bfloat16))        # fast bf16 kernel == generic kernel, rounded once
+    frame = ops.tile_gather_normalize(src, layout, C, T, ov, (gy, gx), 0, gy * gx, off, sc, dtype=torch.bfloat16, pad=3)
     assert frame.shape == (gy * gx, T + 6, T + 8, 4)
     assert torch.equal(frame[:, 3:3 + T, 3:3 + T], dense)
     border = frame.clone(); border[:, 3:3 + T, 3:3 + T] = 0
@@ -134,6 +137,25 @@ def test_stitch_blend_bit_exact(dtype, H, W, T, ov, K):
     blended = torch.empty((H, W, K), dtype=torch.float32, device="cuda")
     ops.stitch_blend_argmax(logits.cuda(), ov, (gy, gx), blend_window(T, ov, "cuda"), mask, blended)
     np.testing.assert_array_equal(blended.cpu().numpy(), ref_blend)
+    np.testing.assert_array_equal(mask.cpu().numpy(), ref_mask)
+    # mask-only form (what MosaicInference runs): class chosen from the un-normalised sums, divisions only on near-ties
+    mask2 = torch.full((H, W), 255, dtype=torch.uint8, device="cuda")
+    ops.stitch_blend_argmax(logits.cuda(), ov, (gy, gx), blend_window(T, ov, "cuda"), mask2, None)
+    np.testing.assert_array_equal(mask2.cpu().numpy(), ref_mask)
+
+
+@pytest.mark.parametrize("T,ov", [(64, 32), (64, 12), (32, 8)])
+def test_stitch_blend_mask_only_with_ties(T, ov):
+    """logits drawn from three values: exact ties between classes are everywhere (first maximum must win) and the
+    sums of different classes are often within a few ulps of each other."""
+    H, W, K = 150, 170, 3
+    g = torch.Generator().manual_seed(T + ov)
+    gy, gx = overlap_grid(H, W, T, ov)
+    vals = torch.tensor([1.0, 1.0078125, -0.5])
+    logits = vals[torch.randint(0, 3, (gy * gx, T, T, K), generator=g)].to(torch.bfloat16)
+    _, ref_mask = ref_tiler.stitch_blend(logits.float().numpy(), H, W, T, ov)
+    mask = torch.full((H, W), 255, dtype=torch.uint8, device="cuda")
+    ops.stitch_blend_argmax(logits.cuda(), ov, (gy, gx), blend_window(T, ov, "cuda"), mask, None)
     np.testing.assert_array_equal(mask.cpu().numpy(), ref_mask)
 
 
