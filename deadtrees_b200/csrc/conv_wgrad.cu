@@ -277,7 +277,216 @@ WgPlan make_plan(int N, int Ho, int Wo, int C_in, int C_out, int ksize, int stri
 int dt_encode_bf16_map(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                        const uint32_t* box, const uint32_t* elem_strides);
 
+// ------------------------------------------------------------------------------------------------------------------
+// Narrow layers (C_out <= 32, 3x3 / stride 1): all nine taps of a ci slab from ONE tcgen05.mma per 16 pixels.
+//
+// With <= 32 channels a pixel is a 32- or 64-byte row, so the MN-major canonical layout (SWIZZLE_32B / _64B) has one
+// "MN block" per pixel row and the block stride (leading byte offset) is free to ALIAS the same patch at a shifted pixel:
+//   A = gy halo patch (18 rows x 8 px x CA ch), block i (i = 0..2) starts i image rows further: rows of A are
+//       (i, co) = gy[q + (i-1) rows][co];  blocks 3.. of the M = 128 tile read further rows (garbage, never stored);
+//   B = x halo patch (18 x 10 px x CB ch), block s' starts s' pixels further: columns (s', ci) = x[q + (s'-1) px][ci];
+//   D[(i, co)][(s', ci)] += sum over the tile's pixels q  =  this tile's share of dW[co][ci][r = 2 - i][s = s']
+// (every (gy pixel, x pixel) pair of a tap is met in exactly one tile; pairs that reach outside the image meet the zero
+// fill of the TMA boxes).  The generic kernel above spends 9 MMAs of M 128 x N 64 on the same 16 pixels - for a 16-channel
+// layer 32x more tensor work than the real 16 x 16 block; it ran the three 256^2-resolution decoder layers at 4..40
+// TFLOP/s (890 us each).  This kernel is bound by reading x and gy once.
+// The swizzle of both operands is a function of the absolute shared-memory address (profiles/
+// r01_halo_descriptor_experiment.txt), which is what makes the aliased block strides legal.
+// ------------------------------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int NW_STAGES = 4;
+
+struct NwParams {
+  int N, H, W, C_in, C_out;
+  int tiles_w, tiles_h, total_tiles, tiles_per_cta, n_slabs;
+  float* partial;                   // [splits][9][C_out][C_in]
+};
+
+__device__ __forceinline__ uint64_t umma_desc_mn_any(uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(layout & 7u) << 61;
+  return d;
+}
+
+template <int CA, int CB>
+struct NwCfg {
+  static constexpr int RA = CA * 2, RB = CB * 2;                      // bytes per pixel row
+  static constexpr int A_PATCH = (TH + 2) * TW * RA;                  // 18 x 8 pixels
+  static constexpr int B_PATCH = (TH + 2) * PITCH * RB;               // 18 x 10 pixels
+  static constexpr int A_REGION = (A_PATCH + 1023) / 1024 * 1024;
+  static constexpr int B_REGION = (B_PATCH + 1023) / 1024 * 1024;     // also absorbs the garbage blocks' over-read
+  static constexpr int STAGE = A_REGION + B_REGION;
+  static constexpr int NCOLS = 3 * CB;
+  static constexpr int TMEM = NCOLS <= 64 ? 64 : (NCOLS <= 128 ? 128 : 256);
+  static constexpr int SMEM = NW_STAGES * STAGE + 1024 + 256;
+  static constexpr uint32_t LAYOUT_A = CA == 16 ? 6u : 4u;             // SWIZZLE_32B / SWIZZLE_64B
+  static constexpr uint32_t LAYOUT_B = CB == 16 ? 6u : (CB == 32 ? 4u : 2u);
+  static_assert((TH + 128 / CA) * TW * RA <= A_REGION + B_REGION, "garbage rows must stay inside the stage");
+};
+
+template <int CA, int CB>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_wgrad_narrow_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ CUtensorMap tm_x,
+                         const NwParams p) {
+  using Cfg = NwCfg<CA, CB>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NW_STAGES * Cfg::STAGE);
+  uint64_t* full = bars;
+  uint64_t* empty = full + NW_STAGES;
+  uint64_t* done = empty + NW_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int slab = blockIdx.x % p.n_slabs, split = blockIdx.x / p.n_slabs;
+  const int tile_begin = split * p.tiles_per_cta;
+  const int tile_end = min(p.total_tiles, tile_begin + p.tiles_per_cta);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_g);
+    tma_prefetch_desc(&tm_x);
+    for (int i = 0; i < NW_STAGES; ++i) { mbar_init(&full[i], 1u); mbar_init(&empty[i], 1u); }
+    mbar_init(done, 1u);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::TMEM);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int st = 0;
+      uint32_t ph = 0;
+      for (int tile = tile_begin; tile < tile_end; ++tile) {
+        int m = tile;
+        const int w0 = (m % p.tiles_w) * TW; m /= p.tiles_w;
+        const int h0 = (m % p.tiles_h) * TH;
+        const int n0 = m / p.tiles_h;
+        uint8_t* stage = smem + st * Cfg::STAGE;
+        mbar_wait(&empty[st], ph ^ 1u);
+        mbar_arrive_expect_tx(&full[st], Cfg::A_PATCH + Cfg::B_PATCH);
+        tma_load_4d(stage, &tm_g, &full[st], 0, w0, h0 - 1, n0);
+        tma_load_4d(stage + Cfg::A_REGION, &tm_x, &full[st], slab * CB, w0 - 1, h0 - 1, n0);
+        if (++st == NW_STAGES) { st = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, Cfg::NCOLS) | (1u << 15) | (1u << 16);
+      // A: MN blocks one image row (8 px) apart = the K groups' own stride; B: MN blocks one pixel apart
+      const uint64_t a_hi = umma_desc_mn_any(TW * Cfg::RA, TW * Cfg::RA, Cfg::LAYOUT_A);
+      const uint64_t b_hi = umma_desc_mn_any(Cfg::RB, PITCH * Cfg::RB, Cfg::LAYOUT_B);
+      int st = 0;
+      uint32_t ph = 0, accum = 0;
+      for (int tile = tile_begin; tile < tile_end; ++tile) {
+        mbar_wait(&full[st], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + st * Cfg::STAGE);
+        const uint32_t b_addr = a_addr + Cfg::A_REGION;
+#pragma unroll
+        for (int k8 = 0; k8 < 8; ++k8) {      // 16 pixels = tile rows 2*k8, 2*k8 + 1
+          const uint64_t a_d = a_hi + (((a_addr + 2 * k8 * TW * Cfg::RA) & 0x3FFFFu) >> 4);
+          const uint64_t b_d = b_hi + (((b_addr + (2 * k8 + 1) * PITCH * Cfg::RB) & 0x3FFFFu) >> 4);
+          umma_bf16_ss(tmem_base, a_d, b_d, idesc, (accum | k8) != 0 ? 1u : 0u);
+        }
+        accum = 1;
+        umma_commit(&empty[st]);
+        if (++st == NW_STAGES) { st = 0; ph ^= 1u; }
+      }
+      umma_commit(done);
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;                 // accumulator row = (i, co)
+    const int i = row / CA, co = row % CA;
+    mbar_wait(done, 0);
+    tc_fence_after();
+    if (quarter * 32 < 3 * CA) {                         // warp-uniform: this quarter holds real rows
+#pragma unroll
+      for (int sp = 0; sp < 3; ++sp) {
+        const int tap = (2 - i) * 3 + sp;
+        float* dst = p.partial + ((static_cast<int64_t>(split) * 9 + tap) * p.C_out + co) * p.C_in + slab * CB;
+#pragma unroll
+        for (int c0 = 0; c0 < CB; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld_x16(tmem_base + sp * CB + c0 + (static_cast<uint32_t>(quarter * 32) << 16), v);
+          tmem_ld_wait();
+          if (i < 3 && co < p.C_out) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              if (slab * CB + c0 + j < p.C_in)
+                *reinterpret_cast<float4*>(dst + c0 + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                       __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM);
+  }
+}
+
+struct NwPlan {
+  NwParams p;
+  int ca, cb, splits;
+  bool ok;
+};
+
+NwPlan make_narrow_plan(int N, int Ho, int Wo, int C_in, int C_out, int ksize, int stride) {
+  NwPlan pl;
+  memset(&pl, 0, sizeof(pl));
+  pl.ok = ksize == 3 && stride == 1 && N > 0 && Ho % TH == 0 && Wo % TW == 0 && C_out > 0 && C_out <= 32 && C_in > 0 &&
+          C_in % 4 == 0;
+  if (!pl.ok) return pl;
+  NwParams& p = pl.p;
+  pl.ca = C_out <= 16 ? 16 : 32;
+  pl.cb = C_in <= 16 ? 16 : (C_in <= 32 || C_in % 64 != 0 ? 32 : 64);
+  p.N = N; p.H = Ho; p.W = Wo; p.C_in = C_in; p.C_out = C_out;
+  p.tiles_w = Wo / TW; p.tiles_h = Ho / TH;
+  p.total_tiles = p.tiles_w * p.tiles_h * N;
+  p.n_slabs = (C_in + pl.cb - 1) / pl.cb;
+  int splits = dt_num_sms() / p.n_slabs;                 // one wave of one CTA per SM
+  if (splits < 1) splits = 1;
+  if (splits > p.total_tiles) splits = p.total_tiles;
+  p.tiles_per_cta = (p.total_tiles + splits - 1) / splits;
+  pl.splits = (p.total_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
+  return pl;
+}
+
+template <int CA, int CB>
+int launch_narrow(const CUtensorMap& tm_g, const CUtensorMap& tm_x, const NwParams& p, int splits, cudaStream_t s) {
+  using Cfg = NwCfg<CA, CB>;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(conv_wgrad_narrow_kernel<CA, CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+  });
+  DT_CUDA(attr_err);
+  conv_wgrad_narrow_kernel<CA, CB><<<p.n_slabs * splits, kThreads, Cfg::SMEM, s>>>(tm_g, tm_x, p);
+  DT_LAUNCH_CHECK();
+  return DT_OK;
+}
+
+}  // namespace
+
 extern "C" int64_t dt_conv2d_wgrad_tc_workspace(int N, int Ho, int Wo, int C_in, int C_out, int ksize, int stride) {
+  const NwPlan nw = make_narrow_plan(N, Ho, Wo, C_in, C_out, ksize, stride);
+  if (nw.ok) return static_cast<int64_t>(nw.splits) * 9 * C_out * C_in * static_cast<int64_t>(sizeof(float));
   const WgPlan pl = make_plan(N, Ho, Wo, C_in, C_out, ksize, stride);
   if (!pl.ok) return DT_ERR_UNSUPPORTED;
   return static_cast<int64_t>(pl.splits) * pl.p.RS * C_out * C_in * static_cast<int64_t>(sizeof(float));
@@ -287,6 +496,50 @@ extern "C" int dt_conv2d_wgrad_tc(const void* x, const void* gy, int N, int Ho, 
                                   int gy_cstride, int ksize, int stride, float* dw_oihw, float* workspace,
                                   int64_t workspace_bytes, dt_stream_t stream) {
   DT_ARCH_GUARD();
+  NwPlan nw = make_narrow_plan(N, Ho, Wo, C_in, C_out, ksize, stride);
+  if (nw.ok && x_cstride >= C_in && gy_cstride >= C_out && x_cstride % 8 == 0 && gy_cstride % 8 == 0) {
+    NwParams& q = nw.p;
+    const int64_t need = static_cast<int64_t>(nw.splits) * 9 * C_out * C_in * static_cast<int64_t>(sizeof(float));
+    DT_REQUIRE(workspace != nullptr && workspace_bytes >= need, DT_ERR_BAD_SHAPE,
+               "dt_conv2d_wgrad_tc: workspace of %lld bytes needed (dt_conv2d_wgrad_tc_workspace)", static_cast<long long>(need));
+    DT_REQUIRE((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(gy) | reinterpret_cast<uintptr_t>(workspace)) % 16 == 0,
+               DT_ERR_BAD_ALIGN, "dt_conv2d_wgrad_tc: tensors must be 16-byte aligned");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    q.partial = workspace;
+    CUtensorMap tm_g, tm_x;
+    {
+      const uint64_t dims[4] = {static_cast<uint64_t>(gy_cstride), static_cast<uint64_t>(Wo), static_cast<uint64_t>(Ho),
+                                static_cast<uint64_t>(N)};
+      const uint64_t strides[3] = {static_cast<uint64_t>(gy_cstride) * 2, static_cast<uint64_t>(Wo) * gy_cstride * 2,
+                                   static_cast<uint64_t>(Ho) * Wo * gy_cstride * 2};
+      const uint32_t box[4] = {static_cast<uint32_t>(nw.ca), TW, TH + 2, 1};
+      int rc = dt_encode_bf16_map(&tm_g, gy, 4, dims, strides, box, nullptr);
+      if (rc != DT_OK) return rc;
+    }
+    {
+      const uint64_t dims[4] = {static_cast<uint64_t>(x_cstride), static_cast<uint64_t>(Wo), static_cast<uint64_t>(Ho),
+                                static_cast<uint64_t>(N)};
+      const uint64_t strides[3] = {static_cast<uint64_t>(x_cstride) * 2, static_cast<uint64_t>(Wo) * x_cstride * 2,
+                                   static_cast<uint64_t>(Ho) * Wo * x_cstride * 2};
+      const uint32_t box[4] = {static_cast<uint32_t>(nw.cb), PITCH, TH + 2, 1};
+      int rc = dt_encode_bf16_map(&tm_x, x, 4, dims, strides, box, nullptr);
+      if (rc != DT_OK) return rc;
+    }
+    int rc;
+    if (nw.ca == 16 && nw.cb == 16) rc = launch_narrow<16, 16>(tm_g, tm_x, q, nw.splits, s);
+    else if (nw.ca == 16 && nw.cb == 32) rc = launch_narrow<16, 32>(tm_g, tm_x, q, nw.splits, s);
+    else if (nw.ca == 16) rc = launch_narrow<16, 64>(tm_g, tm_x, q, nw.splits, s);
+    else if (nw.cb == 16) rc = launch_narrow<32, 16>(tm_g, tm_x, q, nw.splits, s);
+    else if (nw.cb == 32) rc = launch_narrow<32, 32>(tm_g, tm_x, q, nw.splits, s);
+    else rc = launch_narrow<32, 64>(tm_g, tm_x, q, nw.splits, s);
+    if (rc != DT_OK) return rc;
+    const int64_t total = static_cast<int64_t>(C_out) * C_in * 9;
+    int64_t blocks = (total + 255) / 256;
+    if (blocks > dt_num_sms() * 8) blocks = dt_num_sms() * 8;
+    wgrad_reduce_kernel<<<static_cast<int>(blocks), 256, 0, s>>>(workspace, nw.splits, 9, C_out, C_in, dw_oihw);
+    DT_LAUNCH_CHECK();
+    return DT_OK;
+  }
   WgPlan pl = make_plan(N, Ho, Wo, C_in, C_out, ksize, stride);
   if (!pl.ok || x_cstride < C_in || gy_cstride < C_out || x_cstride % 8 != 0 || gy_cstride % 8 != 0) {
     dt_set_error("dt_conv2d_wgrad_tc: unsupported shape N=%d Ho=%d Wo=%d C_in=%d C_out=%d k=%d s=%d", N, Ho, Wo, C_in, C_out,

@@ -250,7 +250,10 @@ def test_training_step_bf16_matches_bf16_arithmetic():
     (64, 64, 2, 16, 8, 3, 1), (64, 128, 2, 32, 16, 3, 1), (128, 64, 1, 16, 16, 3, 1), (256, 256, 4, 8, 8, 3, 1),
     (192, 64, 1, 16, 24, 3, 1), (16, 16, 1, 32, 32, 3, 1), (32, 16, 2, 16, 16, 3, 1), (128, 32, 1, 16, 8, 3, 1),
     (512, 512, 2, 8, 8, 3, 1), (64, 128, 2, 16, 16, 3, 2), (256, 512, 2, 8, 8, 3, 2), (128, 256, 1, 16, 8, 3, 2),
-    (64, 128, 2, 16, 16, 1, 2), (256, 512, 4, 8, 8, 1, 2)])
+    (64, 128, 2, 16, 16, 1, 2), (256, 512, 4, 8, 8, 1, 2),
+    # narrow layers (C_out <= 32): the nine-taps-per-MMA kernel with aliased MN blocks (SWIZZLE_32B / 64B / 128B operands)
+    (96, 32, 2, 32, 32, 3, 1), (32, 32, 1, 32, 16, 3, 1), (64, 16, 1, 16, 16, 3, 1), (16, 8, 3, 16, 24, 3, 1),
+    (192, 32, 1, 16, 16, 3, 1), (16, 32, 2, 48, 8, 3, 1), (24, 24, 1, 16, 8, 3, 1)])
 def test_wgrad_tensor_core(cin, cout, N, H, W, k, stride):
     """tcgen05 weight gradient (MN-major operands straight from NHWC; H, W = output size) against torch autograd on the
     bf16-rounded operands: 3x3 stride 1 / 2 and the 1x1 stride-2 downsample."""
