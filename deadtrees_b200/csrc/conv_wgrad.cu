@@ -278,7 +278,8 @@ int dt_encode_bf16_map(CUtensorMap* tm, const void* base, int rank, const uint64
                        const uint32_t* box, const uint32_t* elem_strides);
 
 // ------------------------------------------------------------------------------------------------------------------
-// Narrow layers (C_out <= 32, 3x3 / stride 1): all nine taps of a ci slab from ONE tcgen05.mma per 16 pixels.
+// 3x3 / stride-1 layers with whole 16-row tiles: all nine taps of a (co block, ci slab) from ONE (C_out <= 32) or TWO
+// (64-wide co blocks) tcgen05.mma per 16 pixels.
 //
 // With <= 32 channels a pixel is a 32- or 64-byte row, so the MN-major canonical layout (SWIZZLE_32B / _64B) has one
 // "MN block" per pixel row and the block stride (leading byte offset) is free to ALIAS the same patch at a shifted pixel:
@@ -286,6 +287,8 @@ int dt_encode_bf16_map(CUtensorMap* tm, const void* base, int rank, const uint64
 //       (i, co) = gy[q + (i-1) rows][co];  blocks 3.. of the M = 128 tile read further rows (garbage, never stored);
 //   B = x halo patch (18 x 10 px x CB ch), block s' starts s' pixels further: columns (s', ci) = x[q + (s'-1) px][ci];
 //   D[(i, co)][(s', ci)] += sum over the tile's pixels q  =  this tile's share of dW[co][ci][r = 2 - i][s = s']
+// For 64-channel co blocks (SWIZZLE_128B rows) three blocks are 192 rows: a second MMA starts at block 2 (its upper
+// half is garbage) and accumulates into its own TMEM columns.
 // (every (gy pixel, x pixel) pair of a tap is met in exactly one tile; pairs that reach outside the image meet the zero
 // fill of the TMA boxes).  The generic kernel above spends 9 MMAs of M 128 x N 64 on the same 16 pixels - for a 16-channel
 // layer 32x more tensor work than the real 16 x 16 block; it ran the three 256^2-resolution decoder layers at 4..40
@@ -299,7 +302,7 @@ constexpr int NW_STAGES = 4;
 
 struct NwParams {
   int N, H, W, C_in, C_out;
-  int tiles_w, tiles_h, total_tiles, tiles_per_cta, n_slabs;
+  int tiles_w, tiles_h, total_tiles, tiles_per_cta, n_slabs, co_blocks;
   float* partial;                   // [splits][9][C_out][C_in]
 };
 
@@ -315,17 +318,19 @@ __device__ __forceinline__ uint64_t umma_desc_mn_any(uint32_t lbo_bytes, uint32_
 template <int CA, int CB>
 struct NwCfg {
   static constexpr int RA = CA * 2, RB = CB * 2;                      // bytes per pixel row
+  static constexpr int BLK = 128 / CA;                                // MN blocks (image-row shifts) per M = 128 tile
+  static constexpr int NM = (3 + BLK - 1) / BLK;                      // MMAs per 16 pixels: 1, or 2 for 64-wide co blocks
   static constexpr int A_PATCH = (TH + 2) * TW * RA;                  // 18 x 8 pixels
   static constexpr int B_PATCH = (TH + 2) * PITCH * RB;               // 18 x 10 pixels
   static constexpr int A_REGION = (A_PATCH + 1023) / 1024 * 1024;
   static constexpr int B_REGION = (B_PATCH + 1023) / 1024 * 1024;     // also absorbs the garbage blocks' over-read
   static constexpr int STAGE = A_REGION + B_REGION;
   static constexpr int NCOLS = 3 * CB;
-  static constexpr int TMEM = NCOLS <= 64 ? 64 : (NCOLS <= 128 ? 128 : 256);
+  static constexpr int TMEM = NM * NCOLS <= 64 ? 64 : (NM * NCOLS <= 128 ? 128 : (NM * NCOLS <= 256 ? 256 : 512));
   static constexpr int SMEM = NW_STAGES * STAGE + 1024 + 256;
-  static constexpr uint32_t LAYOUT_A = CA == 16 ? 6u : 4u;             // SWIZZLE_32B / SWIZZLE_64B
+  static constexpr uint32_t LAYOUT_A = CA == 16 ? 6u : (CA == 32 ? 4u : 2u);   // SWIZZLE_32B / 64B / 128B
   static constexpr uint32_t LAYOUT_B = CB == 16 ? 6u : (CB == 32 ? 4u : 2u);
-  static_assert((TH + 128 / CA) * TW * RA <= A_REGION + B_REGION, "garbage rows must stay inside the stage");
+  static_assert((TH + NM * BLK) * TW * RA <= A_REGION + B_REGION, "garbage rows must stay inside the stage");
 };
 
 template <int CA, int CB>
@@ -342,7 +347,8 @@ conv_wgrad_narrow_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int slab = blockIdx.x % p.n_slabs, split = blockIdx.x / p.n_slabs;
+  const int slab = blockIdx.x % p.n_slabs;
+  const int cob = (blockIdx.x / p.n_slabs) % p.co_blocks, split = blockIdx.x / (p.n_slabs * p.co_blocks);
   const int tile_begin = split * p.tiles_per_cta;
   const int tile_end = min(p.total_tiles, tile_begin + p.tiles_per_cta);
 
@@ -374,7 +380,7 @@ conv_wgrad_narrow_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_
         uint8_t* stage = smem + st * Cfg::STAGE;
         mbar_wait(&empty[st], ph ^ 1u);
         mbar_arrive_expect_tx(&full[st], Cfg::A_PATCH + Cfg::B_PATCH);
-        tma_load_4d(stage, &tm_g, &full[st], 0, w0, h0 - 1, n0);
+        tma_load_4d(stage, &tm_g, &full[st], cob * CA, w0, h0 - 1, n0);
         tma_load_4d(stage + Cfg::A_REGION, &tm_x, &full[st], slab * CB, w0 - 1, h0 - 1, n0);
         if (++st == NW_STAGES) { st = 0; ph ^= 1u; }
       }
@@ -396,7 +402,10 @@ conv_wgrad_narrow_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_
         for (int k8 = 0; k8 < 8; ++k8) {      // 16 pixels = tile rows 2*k8, 2*k8 + 1
           const uint64_t a_d = a_hi + (((a_addr + 2 * k8 * TW * Cfg::RA) & 0x3FFFFu) >> 4);
           const uint64_t b_d = b_hi + (((b_addr + (2 * k8 + 1) * PITCH * Cfg::RB) & 0x3FFFFu) >> 4);
-          umma_bf16_ss(tmem_base, a_d, b_d, idesc, (accum | k8) != 0 ? 1u : 0u);
+#pragma unroll
+          for (int a = 0; a < Cfg::NM; ++a)   // second MMA: blocks BLK.. (image rows BLK further)
+            umma_bf16_ss(tmem_base + a * Cfg::NCOLS, a_d + ((a * Cfg::BLK * TW * Cfg::RA) >> 4), b_d, idesc,
+                         (accum | k8) != 0 ? 1u : 0u);
         }
         accum = 1;
         umma_commit(&empty[st]);
@@ -406,11 +415,14 @@ conv_wgrad_narrow_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_
     }
   } else {
     const int quarter = warp & 3;
-    const int row = quarter * 32 + lane;                 // accumulator row = (i, co)
-    const int i = row / CA, co = row % CA;
+    const int row = quarter * 32 + lane;                 // accumulator row = (block, channel of the co block)
     mbar_wait(done, 0);
     tc_fence_after();
-    if (quarter * 32 < 3 * CA) {                         // warp-uniform: this quarter holds real rows
+#pragma unroll
+    for (int a = 0; a < Cfg::NM; ++a) {
+      const int i = a * Cfg::BLK + row / CA;             // image-row shift of this accumulator row: tap row r = 2 - i
+      const int co = cob * CA + row % CA;
+      if (a * Cfg::BLK + (quarter * 32) / CA >= 3) continue;     // warp-uniform: only garbage rows in this quarter
 #pragma unroll
       for (int sp = 0; sp < 3; ++sp) {
         const int tap = (2 - i) * 3 + sp;
@@ -418,7 +430,7 @@ conv_wgrad_narrow_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_
 #pragma unroll
         for (int c0 = 0; c0 < CB; c0 += 16) {
           uint32_t v[16];
-          tmem_ld_x16(tmem_base + sp * CB + c0 + (static_cast<uint32_t>(quarter * 32) << 16), v);
+          tmem_ld_x16(tmem_base + a * Cfg::NCOLS + sp * CB + c0 + (static_cast<uint32_t>(quarter * 32) << 16), v);
           tmem_ld_wait();
           if (i < 3 && co < p.C_out) {
 #pragma unroll
@@ -450,17 +462,17 @@ struct NwPlan {
 NwPlan make_narrow_plan(int N, int Ho, int Wo, int C_in, int C_out, int ksize, int stride) {
   NwPlan pl;
   memset(&pl, 0, sizeof(pl));
-  pl.ok = ksize == 3 && stride == 1 && N > 0 && Ho % TH == 0 && Wo % TW == 0 && C_out > 0 && C_out <= 32 && C_in > 0 &&
-          C_in % 4 == 0;
+  pl.ok = ksize == 3 && stride == 1 && N > 0 && Ho % TH == 0 && Wo % TW == 0 && C_out > 0 && C_in > 0 && C_in % 4 == 0;
   if (!pl.ok) return pl;
   NwParams& p = pl.p;
-  pl.ca = C_out <= 16 ? 16 : 32;
+  pl.ca = C_out <= 16 ? 16 : (C_out <= 32 ? 32 : 64);
   pl.cb = C_in <= 16 ? 16 : (C_in <= 32 || C_in % 64 != 0 ? 32 : 64);
   p.N = N; p.H = Ho; p.W = Wo; p.C_in = C_in; p.C_out = C_out;
   p.tiles_w = Wo / TW; p.tiles_h = Ho / TH;
   p.total_tiles = p.tiles_w * p.tiles_h * N;
   p.n_slabs = (C_in + pl.cb - 1) / pl.cb;
-  int splits = dt_num_sms() / p.n_slabs;                 // one wave of one CTA per SM
+  p.co_blocks = (C_out + pl.ca - 1) / pl.ca;
+  int splits = dt_num_sms() / (p.n_slabs * p.co_blocks);   // one wave of one CTA per SM
   if (splits < 1) splits = 1;
   if (splits > p.total_tiles) splits = p.total_tiles;
   p.tiles_per_cta = (p.total_tiles + splits - 1) / splits;
@@ -477,7 +489,7 @@ int launch_narrow(const CUtensorMap& tm_g, const CUtensorMap& tm_x, const NwPara
     attr_err = cudaFuncSetAttribute(conv_wgrad_narrow_kernel<CA, CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
   });
   DT_CUDA(attr_err);
-  conv_wgrad_narrow_kernel<CA, CB><<<p.n_slabs * splits, kThreads, Cfg::SMEM, s>>>(tm_g, tm_x, p);
+  conv_wgrad_narrow_kernel<CA, CB><<<p.n_slabs * p.co_blocks * splits, kThreads, Cfg::SMEM, s>>>(tm_g, tm_x, p);
   DT_LAUNCH_CHECK();
   return DT_OK;
 }
@@ -529,9 +541,12 @@ extern "C" int dt_conv2d_wgrad_tc(const void* x, const void* gy, int N, int Ho, 
     if (nw.ca == 16 && nw.cb == 16) rc = launch_narrow<16, 16>(tm_g, tm_x, q, nw.splits, s);
     else if (nw.ca == 16 && nw.cb == 32) rc = launch_narrow<16, 32>(tm_g, tm_x, q, nw.splits, s);
     else if (nw.ca == 16) rc = launch_narrow<16, 64>(tm_g, tm_x, q, nw.splits, s);
-    else if (nw.cb == 16) rc = launch_narrow<32, 16>(tm_g, tm_x, q, nw.splits, s);
-    else if (nw.cb == 32) rc = launch_narrow<32, 32>(tm_g, tm_x, q, nw.splits, s);
-    else rc = launch_narrow<32, 64>(tm_g, tm_x, q, nw.splits, s);
+    else if (nw.ca == 32 && nw.cb == 16) rc = launch_narrow<32, 16>(tm_g, tm_x, q, nw.splits, s);
+    else if (nw.ca == 32 && nw.cb == 32) rc = launch_narrow<32, 32>(tm_g, tm_x, q, nw.splits, s);
+    else if (nw.ca == 32) rc = launch_narrow<32, 64>(tm_g, tm_x, q, nw.splits, s);
+    else if (nw.cb == 16) rc = launch_narrow<64, 16>(tm_g, tm_x, q, nw.splits, s);
+    else if (nw.cb == 32) rc = launch_narrow<64, 32>(tm_g, tm_x, q, nw.splits, s);
+    else rc = launch_narrow<64, 64>(tm_g, tm_x, q, nw.splits, s);
     if (rc != DT_OK) return rc;
     const int64_t total = static_cast<int64_t>(C_out) * C_in * 9;
     int64_t blocks = (total + 255) / 256;
