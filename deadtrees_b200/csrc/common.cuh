@@ -82,6 +82,23 @@ __device__ __forceinline__ void st_na_v4(void* p, uint4 v) {
                :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+// 32-byte (256-bit) global accesses (sm_100: LDG/STG.E.ENL2.256): one full 32-byte sector per lane and instruction -
+// the conv epilogues hold 16 bf16 channels of one pixel per thread, which two 16-byte stores would write as two
+// half-sector requests (ncu, stem kernel: twice the L2 write sector operations of the bytes stored).
+__device__ __forceinline__ void st_global_v8(void* p, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t a4,
+                                             uint32_t a5, uint32_t a6, uint32_t a7) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               :: "l"(p), "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(a4), "r"(a5), "r"(a6), "r"(a7) : "memory");
+}
+__device__ __forceinline__ void store_bf16x16(void* dst, const float (&f)[16]) {
+  st_global_v8(dst, pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]),
+               pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
+}
+__device__ __forceinline__ void ldg_v8(const void* p, uint4& lo, uint4& hi) {
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w) : "l"(p));
+}
+
 template <typename T>
 __device__ __forceinline__ T warp_sum(T v) {
 #pragma unroll

@@ -234,7 +234,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       uint4 res[SC / 8];
       if (p.has_residual) {
 #pragma unroll
-        for (int j = 0; j < SC / 8; ++j) res[j] = __ldg(reinterpret_cast<const uint4*>(p.residual + out_off) + j);
+        for (int j = 0; j < SC / 16; ++j) ldg_v8(p.residual + out_off + 16 * j, res[2 * j], res[2 * j + 1]);
       }
       mbar_wait(&tmem_full[acc], pacc);
       tc_fence_after();
@@ -245,8 +245,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         const bool more = s0 + SC < BN;
         if (p.has_residual && more) {
 #pragma unroll
-          for (int j = 0; j < SC / 8; ++j)
-            res_next[j] = __ldg(reinterpret_cast<const uint4*>(p.residual + out_off + s0 + SC) + j);
+          for (int j = 0; j < SC / 16; ++j) ldg_v8(p.residual + out_off + s0 + SC + 16 * j, res_next[2 * j], res_next[2 * j + 1]);
         }
 #pragma unroll
         for (int c0 = 0; c0 < SC; c0 += 16) {
@@ -278,11 +277,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 #pragma unroll
             for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
           }
-          uint4* op = reinterpret_cast<uint4*>(p.y + out_off + s0 + c0);
-          op[0] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
-                             pack_bf16x2(f[6], f[7]));
-          op[1] = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]),
-                             pack_bf16x2(f[14], f[15]));
+          store_bf16x16(p.y + out_off + s0 + c0, f);
         }
         if (more) {
 #pragma unroll

@@ -176,7 +176,7 @@ conv_res_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       if (p.has_residual) {   // first residual line is in flight while the MMAs of this super tile run
         const int64_t o0 = pixel_off(0);
 #pragma unroll
-        for (int j = 0; j < BN / 8; ++j) res[j] = __ldg(reinterpret_cast<const uint4*>(p.residual + o0) + j);
+        for (int j = 0; j < BN / 16; ++j) ldg_v8(p.residual + o0 + 16 * j, res[2 * j], res[2 * j + 1]);
       }
       mbar_wait(&tmem_full[buf], pbuf);
       tc_fence_after();
@@ -210,7 +210,7 @@ conv_res_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         if (p.has_residual && mt + 1 < MT) {
           const int64_t o1 = pixel_off(mt + 1);
 #pragma unroll
-          for (int j = 0; j < BN / 8; ++j) res_next[j] = __ldg(reinterpret_cast<const uint4*>(p.residual + o1) + j);
+          for (int j = 0; j < BN / 16; ++j) ldg_v8(p.residual + o1 + 16 * j, res_next[2 * j], res_next[2 * j + 1]);
         }
 #pragma unroll
         for (int c0 = 0; c0 < BN; c0 += 16) {
@@ -241,11 +241,7 @@ conv_res_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
 #pragma unroll
             for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
           }
-          uint4* op = reinterpret_cast<uint4*>(p.y + out_off + c0);
-          op[0] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
-                             pack_bf16x2(f[6], f[7]));
-          op[1] = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]),
-                             pack_bf16x2(f[14], f[15]));
+          store_bf16x16(p.y + out_off + c0, f);
         }
         if (p.has_residual) {
 #pragma unroll

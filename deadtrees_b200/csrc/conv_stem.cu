@@ -150,11 +150,7 @@ conv_stem_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
         }
         if (valid) {
-          uint4* op = reinterpret_cast<uint4*>(p.y + static_cast<int64_t>(m) * BN + c0);
-          op[0] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
-                             pack_bf16x2(f[6], f[7]));
-          op[1] = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]),
-                             pack_bf16x2(f[14], f[15]));
+          store_bf16x16(p.y + static_cast<int64_t>(m) * BN + c0, f);
         }
       }
       tc_fence_before();

@@ -256,7 +256,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       uint4 res[SC / 8];
       if (p.has_residual && valid) {       // issue the first residual line before waiting for the MMAs
 #pragma unroll
-        for (int j = 0; j < SC / 8; ++j) res[j] = __ldg(reinterpret_cast<const uint4*>(p.residual + out_off) + j);
+        for (int j = 0; j < SC / 16; ++j) ldg_v8(p.residual + out_off + 16 * j, res[2 * j], res[2 * j + 1]);
       }
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
@@ -267,8 +267,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         const bool more = s0 + SC < BN;
         if (p.has_residual && valid && more) {
 #pragma unroll
-          for (int j = 0; j < SC / 8; ++j)
-            res_next[j] = __ldg(reinterpret_cast<const uint4*>(p.residual + out_off + s0 + SC) + j);
+          for (int j = 0; j < SC / 16; ++j) ldg_v8(p.residual + out_off + s0 + SC + 16 * j, res_next[2 * j], res_next[2 * j + 1]);
         }
 #pragma unroll
         for (int c0 = 0; c0 < SC; c0 += 16) {
@@ -295,11 +294,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
           }
           if (valid) {
-            uint4* op = reinterpret_cast<uint4*>(p.y + out_off + s0 + c0);
-            op[0] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
-                               pack_bf16x2(f[6], f[7]));
-            op[1] = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]),
-                               pack_bf16x2(f[14], f[15]));
+            store_bf16x16(p.y + out_off + s0 + c0, f);
           }
         }
         if (more) {
@@ -523,6 +518,8 @@ extern "C" int dt_conv2d_fwd(const dt_conv_desc* d, const void* x, const void* s
   if (d->flags & DT_CONV_X_PAD3) {
     DT_REQUIRE(stem && d->dtype == DT_BF16 && d->stride == 2 && d->pad == 3, DT_ERR_BAD_SHAPE,
                "dt_conv2d_fwd: DT_CONV_X_PAD3 is the bf16 7x7/s2 stem layout");
+    DT_REQUIRE(reinterpret_cast<uintptr_t>(y) % 32 == 0, DT_ERR_BAD_ALIGN,
+               "dt_conv2d_fwd: the bf16 output must be 32-byte aligned (256-bit epilogue stores)");
     const int rc = dt_conv_stem(d, x, w, scale, shift, y, s);
     DT_REQUIRE(rc != DT_ERR_UNSUPPORTED, DT_ERR_BAD_SHAPE, "dt_conv2d_fwd: stem output %dx%d cannot be tiled", Ho, Wo);
     return rc;
@@ -538,6 +535,8 @@ extern "C" int dt_conv2d_fwd(const dt_conv_desc* d, const void* x, const void* s
   DT_REQUIRE((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(w) |
               reinterpret_cast<uintptr_t>(skip) | reinterpret_cast<uintptr_t>(residual)) % 16 == 0,
              DT_ERR_BAD_ALIGN, "dt_conv2d_fwd: tensors must be 16-byte aligned");
+  DT_REQUIRE((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(residual)) % 32 == 0, DT_ERR_BAD_ALIGN,
+             "dt_conv2d_fwd: the bf16 output and residual must be 32-byte aligned (256-bit epilogue accesses)");
   const int64_t M = static_cast<int64_t>(d->N) * Ho * Wo;
   DT_REQUIRE(M < (1LL << 31) - BM, DT_ERR_BAD_SHAPE, "dt_conv2d_fwd: too many output pixels");
   int BN = d->C_out;
