@@ -15,7 +15,7 @@ _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "libdeadtrees_b200.so"
 
 DT_BF16, DT_F32 = 0, 1
-CONV_FORCE_GATHER, CONV_FORCE_DIRECT, CONV_NO_HALO, CONV_X_PAD3, CONV_TRANSPOSED = 1, 2, 4, 8, 16
+CONV_FORCE_GATHER, CONV_FORCE_DIRECT, CONV_NO_HALO, CONV_X_PAD3, CONV_TRANSPOSED, CONV_NO_QUAD = 1, 2, 4, 8, 16, 32
 
 
 class DeadtreesB200Error(RuntimeError):
@@ -29,6 +29,12 @@ class ConvDesc(C.Structure):
 
 
 _i, _i64, _f, _p = C.c_int, C.c_int64, C.c_float, C.c_void_p
+
+
+class PackJob(C.Structure):
+    """dt_pack_job (include/deadtrees_b200.h)"""
+    _fields_ = [("w", C.c_void_p), ("out", C.c_void_p)] + [(n, C.c_int32) for n in (
+        "C_out", "C_in", "R", "S", "mode", "C_in_p", "Kpad", "reserved")] + [("start", C.c_int64)]
 
 _SIGNATURES = {
     "dt_version": ([], C.c_int),
@@ -66,6 +72,7 @@ _SIGNATURES = {
     "dt_nchw_to_nhwc": ([_p, _i, _i, _i, _i, _i, _i, _p, _p], C.c_int),
     "dt_channel_sum": ([_p, _i64, _i, _i, _i, _p, _p], C.c_int),
     "dt_pack_conv_weight": ([_p, _i, _i, _i, _i, _i, _i, _i, _p, _p], C.c_int),
+    "dt_pack_conv_weights_batched": ([_p, _i, _i64, _p], C.c_int),
     "dt_conv2d_dgrad_direct": ([_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p], C.c_int),
     "dt_conv2d_wgrad_direct": ([_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p], C.c_int),
     "dt_conv2d_wgrad_tc_workspace": ([_i, _i, _i, _i, _i, _i, _i], C.c_int64),

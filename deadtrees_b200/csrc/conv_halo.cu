@@ -325,6 +325,251 @@ int launch_halo(const CUtensorMap& tm_a, const CUtensorMap& tm_s, const CUtensor
   return DT_OK;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Class-fused variant for the up-sample + concat layers with C_out <= 64: ONE tile = the four parity classes of a
+// low-res region (4 x 128 output pixels, four TMEM accumulators).  The five patches of the region (low-res x patch and
+// the four stride-2 skip planes) and - for the x patch - the nine weight chunks are loaded once and shared by the four
+// classes; in the class-per-tile kernel above every class re-loads all five patches (ncu, decoder.blocks.3.conv1:
+// 1.4 GB of DRAM reads for 0.35 GB of operands, 187 KB of TMA traffic per 128 output pixels).  Per class the K order
+// (x slabs, then planes, taps in table order) is unchanged, so the results are bit-identical to the kernel above.
+// ------------------------------------------------------------------------------------------------------------------
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 2)
+conv_halo_quad_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_s,
+                      const __grid_constant__ CUtensorMap tm_b, const HaloParams p) {
+  constexpr int CW = BK;
+  constexpr int B_BYTES = BN * BK * 2;
+  constexpr int NBUF = 8 * BN <= 256 ? 2 : 1;              // two CTAs share the 512 TMEM columns of an SM
+  constexpr int TMEM_COLS = NBUF * 4 * BN;
+  constexpr int ROW_BYTES = CW * 2;
+  constexpr int PATCH_BYTES = PATCH_PIX * ROW_BYTES;
+  constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+  const int A_SLOTS = p.a_slots;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + A_SLOTS * p.a_slot_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + p.b_slots * B_BYTES);
+  uint64_t* full_a = bars;
+  uint64_t* empty_a = full_a + MAX_A;
+  uint64_t* full_b = empty_a + MAX_A;
+  uint64_t* empty_b = full_b + MAX_B;
+  uint64_t* tmem_full = empty_b + MAX_B;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_b);
+    if (p.n_sslab > 0) tma_prefetch_desc(&tm_s);
+    for (int i = 0; i < A_SLOTS; ++i) { mbar_init(&full_a[i], 1u); mbar_init(&empty_a[i], 1u); }
+    for (int i = 0; i < p.b_slots; ++i) { mbar_init(&full_b[i], 1u); mbar_init(&empty_b[i], 1u); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1u); mbar_init(&tmem_empty[i], 128u); }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int patches_per_tile = p.n_xslab + 4 * p.n_sslab;
+  // region geometry: total_tiles = tiles_w * tiles_h * N (C_out == BN: one channel tile)
+  auto region = [&](int tile, int& n, int& h0, int& w0) {
+    w0 = (tile % p.tiles_w) * TW;
+    const int m = tile / p.tiles_w;
+    h0 = (m % p.tiles_h) * TH;
+    n = m / p.tiles_h;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      auto load_patch = [&](int tile, int pi) {
+        int n, h0, w0;
+        region(tile, n, h0, w0);
+        mbar_wait(&empty_a[sa], pa ^ 1u);
+        mbar_arrive_expect_tx(&full_a[sa], PATCH_BYTES);
+        uint8_t* dst = smem_a + sa * p.a_slot_bytes;
+        if (pi < p.n_xslab) {
+          tma_load_4d(dst, &tm_a, &full_a[sa], pi * CW, w0 - 1, h0 - 1, n);
+        } else {
+          const int sidx = pi - p.n_xslab, plane = sidx & 3;
+          tma_load_4d(dst, &tm_s, &full_a[sa], (sidx >> 2) * BK, 2 * (w0 - 1) + (plane & 1), 2 * (h0 - 1) + (plane >> 1), n);
+        }
+        if (++sa == A_SLOTS) { sa = 0; pa ^= 1u; }
+      };
+      auto load_chunk = [&](int kcoord) {
+        mbar_wait(&empty_b[sb], pb ^ 1u);
+        mbar_arrive_expect_tx(&full_b[sb], B_BYTES);
+        tma_load_2d(smem_b + sb * B_BYTES, &tm_b, &full_b[sb], kcoord, 0);
+        if (++sb == p.b_slots) { sb = 0; pb ^= 1u; }
+      };
+      bool primed = false;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        for (int pi = 0; pi < patches_per_tile; ++pi) {
+          if (!primed) { load_patch(tile, pi); primed = true; }
+          const int kind = pi < p.n_xslab ? 0 : 1 + ((pi - p.n_xslab) & 3);
+          const int choff = pi < p.n_xslab ? pi * CW : p.C_x + ((pi - p.n_xslab) >> 2) * BK;
+          const int prefetch_at = A_SLOTS >= 3 ? 0 : 4;
+          int q = 0;
+          auto maybe_prefetch = [&]() {
+            if (q == prefetch_at) {
+              int npi = pi + 1, ntile = tile;
+              if (npi == patches_per_tile) { npi = 0; ntile = tile + gridDim.x; }
+              if (ntile < p.total_tiles) load_patch(ntile, npi);
+            }
+            ++q;
+          };
+          if (kind == 0) {
+            for (int tap = 0; tap < 9; ++tap) { maybe_prefetch(); load_chunk(tap * p.C_in + choff); }
+          } else {
+            for (int cls = 0; cls < 4; ++cls) {
+              const PatchDesc& pd = p.patch[cls][kind];
+              for (int j = 0; j < pd.ntaps; ++j) { maybe_prefetch(); load_chunk(pd.tap[j] * p.C_in + choff); }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint64_t a_hi = umma_desc(0u, PITCH * ROW_BYTES, 2u);
+      const uint64_t b_hi = umma_desc(0u, 1024u, 2u);
+      int sa = 0, sb = 0, acc = 0;
+      uint32_t pa = 0, pb = 0, pacc = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], pacc ^ 1u);
+        tc_fence_after();
+        uint32_t started = 0;
+        for (int pi = 0; pi < patches_per_tile; ++pi) {
+          const int kind = pi < p.n_xslab ? 0 : 1 + ((pi - p.n_xslab) & 3);
+          mbar_wait(&full_a[sa], pa);
+          tc_fence_after();
+          const uint64_t a_d = a_hi + (smem_u32(smem_a + sa * p.a_slot_bytes) >> 4);
+          if (kind == 0) {
+            for (int tap = 0; tap < 9; ++tap) {
+              mbar_wait(&full_b[sb], pb);
+              tc_fence_after();
+              const uint64_t b_d = b_hi + (smem_u32(smem_b + sb * B_BYTES) >> 4);
+#pragma unroll
+              for (int cls = 0; cls < 4; ++cls) {
+                const uint64_t a_t = a_d + ((static_cast<uint32_t>(p.patch[cls][0].off_by_tap[tap]) * ROW_BYTES) >> 4);
+                const uint32_t d_tmem = tmem_base + (acc * 4 + cls) * BN;
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k)
+                  umma_bf16_ss(d_tmem, a_t + 2 * k, b_d + 2 * k, idesc, (((started >> cls) & 1u) | k) != 0 ? 1u : 0u);
+              }
+              started = 0xFu;
+              umma_commit(&empty_b[sb]);
+              if (++sb == p.b_slots) { sb = 0; pb ^= 1u; }
+            }
+          } else {
+            for (int cls = 0; cls < 4; ++cls) {
+              const PatchDesc& pd = p.patch[cls][kind];
+              const uint32_t d_tmem = tmem_base + (acc * 4 + cls) * BN;
+              for (int j = 0; j < pd.ntaps; ++j) {
+                mbar_wait(&full_b[sb], pb);
+                tc_fence_after();
+                const uint64_t b_d = b_hi + (smem_u32(smem_b + sb * B_BYTES) >> 4);
+                const uint64_t a_t = a_d + ((static_cast<uint32_t>(pd.off[j]) * ROW_BYTES) >> 4);
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k)
+                  umma_bf16_ss(d_tmem, a_t + 2 * k, b_d + 2 * k, idesc, (((started >> cls) & 1u) | k) != 0 ? 1u : 0u);
+                started |= 1u << cls;
+                umma_commit(&empty_b[sb]);
+                if (++sb == p.b_slots) { sb = 0; pb ^= 1u; }
+              }
+            }
+          }
+          umma_commit(&empty_a[sa]);
+          if (++sa == A_SLOTS) { sa = 0; pa ^= 1u; }
+        }
+        umma_commit(&tmem_full[acc]);
+        if (NBUF == 2) { if ((acc ^= 1) == 0) pacc ^= 1u; } else { pacc ^= 1u; }
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    int acc = 0;
+    uint32_t pacc = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      int n, h0, w0;
+      region(tile, n, h0, w0);
+      mbar_wait(&tmem_full[acc], pacc);
+      tc_fence_after();
+#pragma unroll 1
+      for (int cls = 0; cls < 4; ++cls) {
+        const int oy = 2 * (h0 + (row >> 3)) + (cls >> 1), ox = 2 * (w0 + (row & 7)) + (cls & 1);
+        const int64_t out_off = ((static_cast<int64_t>(n) * p.H + oy) * p.W + ox) * p.C_out;
+        const uint32_t t_row = tmem_base + (acc * 4 + cls) * BN + (static_cast<uint32_t>(quarter * 32) << 16);
+#pragma unroll
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld_x16(t_row + c0, v);
+          tmem_ld_wait();
+          float f[16];
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + c0 + j));
+            const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + c0 + j));
+            f[j] = fmaf(__uint_as_float(v[j]), sc.x, sh.x);
+            f[j + 1] = fmaf(__uint_as_float(v[j + 1]), sc.y, sh.y);
+            f[j + 2] = fmaf(__uint_as_float(v[j + 2]), sc.z, sh.z);
+            f[j + 3] = fmaf(__uint_as_float(v[j + 3]), sc.w, sh.w);
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+          }
+          store_bf16x16(p.y + out_off + c0, f);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[acc]);
+      if (NBUF == 2) { if ((acc ^= 1) == 0) pacc ^= 1u; } else { pacc ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+template <int BN>
+int launch_halo_quad(const CUtensorMap& tm_a, const CUtensorMap& tm_s, const CUtensorMap& tm_b, HaloParams& p,
+                     cudaStream_t s) {
+  constexpr int B_BYTES = BN * BK * 2;
+  const int budget = 111 * 1024 - 1024 - 512;
+  p.a_slots = 3;
+  int b_slots = (budget - 3 * p.a_slot_bytes) / B_BYTES;
+  if (b_slots < 4) { p.a_slots = 2; b_slots = (budget - 2 * p.a_slot_bytes) / B_BYTES; }
+  if (b_slots > MAX_B) b_slots = MAX_B;
+  if (b_slots < 2) return DT_ERR_UNSUPPORTED;
+  p.b_slots = b_slots;
+  p.total_tiles = p.tiles_per_class;                   // one tile = the four classes of a region
+  const int smem = p.a_slots * p.a_slot_bytes + b_slots * B_BYTES + 1024 + 512;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(conv_halo_quad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+  });
+  DT_CUDA(attr_err);
+  const int slots = dt_num_sms() * 2;
+  const int grid = p.total_tiles < slots ? p.total_tiles : slots;
+  conv_halo_quad_kernel<BN><<<grid, kThreads, smem, s>>>(tm_a, tm_s, tm_b, p);
+  DT_LAUNCH_CHECK();
+  return DT_OK;
+}
+
 // tap lists and patch-window offsets of every (class, patch kind)
 void fill_patch_tables(HaloParams& p) {
   memset(p.patch, 0, sizeof(p.patch));
@@ -413,6 +658,10 @@ int dt_conv_halo(const dt_conv_desc* d, int BN, const void* x, const void* skip,
     const uint32_t estr[4] = {1, 2, 2, 1};
     int rc = dt_encode_bf16_map(&tm_s, skip, 4, dims, strides, box, estr);
     if (rc != DT_OK) return rc;
+  }
+  if (parity && wide && !d->has_residual && d->C_out == BN && !(d->flags & DT_CONV_NO_QUAD)) {
+    if (BN == 32) return launch_halo_quad<32>(tm_a, tm_s, tm_b, p, s);
+    if (BN == 64) return launch_halo_quad<64>(tm_a, tm_s, tm_b, p, s);
   }
 #define DT_HALO(BNV, CWV) \
   if (BN == BNV && cw == CWV) return launch_halo<BNV, CWV>(tm_a, tm_s, tm_b, p, s);

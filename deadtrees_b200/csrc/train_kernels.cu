@@ -434,36 +434,55 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int N, int K, i
 // mode 2: bf16 [C_out][256],  k = r * 32 + s * 4 + ci                  (tcgen05 stem, C_in <= 4, 7x7)
 // mode 3: bf16 [C_in][Kpad],  k = (RS - 1 - tap) * Cop + co            (dgrad of a stride-1 conv run as a forward conv)
 // mode 4: bf16 [C_in][Kpad],  k = tap * Cop + co                       (dgrad of a stride-2 conv, DT_CONV_TRANSPOSED)
+__device__ __forceinline__ void pack_weight_element(const float* __restrict__ w, int C_out, int C_in, int R, int S, int mode,
+                                                    int C_in_p, int Kpad, void* __restrict__ out, int64_t i) {
+  const int RS = R * S;
+  if (mode == 0) {
+    const int co = static_cast<int>(i % C_out);
+    const int ci = static_cast<int>((i / C_out) % C_in_p);
+    const int tap = static_cast<int>(i / (static_cast<int64_t>(C_out) * C_in_p));
+    static_cast<float*>(out)[i] = ci < C_in ? w[(static_cast<int64_t>(co) * C_in + ci) * RS + tap] : 0.f;
+  } else if (mode == 1) {
+    const int k = static_cast<int>(i % Kpad), co = static_cast<int>(i / Kpad);
+    float v = 0.f;
+    if (k < RS * C_in) { const int tap = k / C_in, ci = k % C_in; v = w[(static_cast<int64_t>(co) * C_in + ci) * RS + tap]; }
+    static_cast<__nv_bfloat16*>(out)[i] = __float2bfloat16_rn(v);
+  } else if (mode == 2) {
+    const int k = static_cast<int>(i % Kpad), co = static_cast<int>(i / Kpad);
+    const int r = k >> 5, s = (k & 31) >> 2, ci = k & 3;
+    float v = 0.f;
+    if (r < R && s < S && ci < C_in) v = w[(static_cast<int64_t>(co) * C_in + ci) * RS + r * S + s];
+    static_cast<__nv_bfloat16*>(out)[i] = __float2bfloat16_rn(v);
+  } else {   // modes 3 / 4: C_in_p = channel stride Cop of the gradient tensor (>= C_out)
+    const int k = static_cast<int>(i % Kpad), ci = static_cast<int>(i / Kpad);
+    float v = 0.f;
+    if (k < RS * C_in_p) {
+      const int tf = k / C_in_p, co = k % C_in_p;
+      if (co < C_out) v = w[(static_cast<int64_t>(co) * C_in + ci) * RS + (mode == 3 ? RS - 1 - tf : tf)];
+    }
+    static_cast<__nv_bfloat16*>(out)[i] = __float2bfloat16_rn(v);
+  }
+}
+
 __global__ void pack_weight_kernel(const float* __restrict__ w, int C_out, int C_in, int R, int S, int mode, int C_in_p,
                                    int Kpad, void* __restrict__ out, int64_t total) {
-  const int RS = R * S;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    pack_weight_element(w, C_out, C_in, R, S, mode, C_in_p, Kpad, out, i);
+}
+
+// every layout of every layer in ONE launch (the training step repacks ~93 weight tensors after each optimizer step):
+// jobs[j] covers the output elements [start_j, start_{j+1}); a thread finds its job by binary search.
+__global__ void pack_weights_batched_kernel(const dt_pack_job* __restrict__ jobs, int njobs, int64_t total) {
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    if (mode == 0) {
-      const int co = static_cast<int>(i % C_out);
-      const int ci = static_cast<int>((i / C_out) % C_in_p);
-      const int tap = static_cast<int>(i / (static_cast<int64_t>(C_out) * C_in_p));
-      static_cast<float*>(out)[i] = ci < C_in ? w[(static_cast<int64_t>(co) * C_in + ci) * RS + tap] : 0.f;
-    } else if (mode == 1) {
-      const int k = static_cast<int>(i % Kpad), co = static_cast<int>(i / Kpad);
-      float v = 0.f;
-      if (k < RS * C_in) { const int tap = k / C_in, ci = k % C_in; v = w[(static_cast<int64_t>(co) * C_in + ci) * RS + tap]; }
-      static_cast<__nv_bfloat16*>(out)[i] = __float2bfloat16_rn(v);
-    } else if (mode == 2) {
-      const int k = static_cast<int>(i % Kpad), co = static_cast<int>(i / Kpad);
-      const int r = k >> 5, s = (k & 31) >> 2, ci = k & 3;
-      float v = 0.f;
-      if (r < R && s < S && ci < C_in) v = w[(static_cast<int64_t>(co) * C_in + ci) * RS + r * S + s];
-      static_cast<__nv_bfloat16*>(out)[i] = __float2bfloat16_rn(v);
-    } else {   // modes 3 / 4: C_in_p = channel stride Cop of the gradient tensor (>= C_out)
-      const int k = static_cast<int>(i % Kpad), ci = static_cast<int>(i / Kpad);
-      float v = 0.f;
-      if (k < RS * C_in_p) {
-        const int tf = k / C_in_p, co = k % C_in_p;
-        if (co < C_out) v = w[(static_cast<int64_t>(co) * C_in + ci) * RS + (mode == 3 ? RS - 1 - tf : tf)];
-      }
-      static_cast<__nv_bfloat16*>(out)[i] = __float2bfloat16_rn(v);
+    int lo = 0, hi = njobs - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (jobs[mid].start <= i) lo = mid; else hi = mid - 1;
     }
+    const dt_pack_job jb = jobs[lo];
+    pack_weight_element(jb.w, jb.C_out, jb.C_in, jb.R, jb.S, jb.mode, jb.C_in_p, jb.Kpad, jb.out, i - jb.start);
   }
 }
 
@@ -808,6 +827,14 @@ int dt_pack_conv_weight(const float* w_oihw, int C_out, int C_in, int R, int S, 
   }
   pack_weight_kernel<<<grid_for(total), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(w_oihw, C_out, C_in, R, S, mode,
                                                                                          C_in_p, Kpad, out, total);
+  DT_LAUNCH_CHECK();
+  return DT_OK;
+}
+
+int dt_pack_conv_weights_batched(const dt_pack_job* jobs_device, int njobs, int64_t total, dt_stream_t stream) {
+  DT_ARCH_GUARD();
+  DT_REQUIRE(jobs_device != nullptr && njobs > 0 && total > 0, DT_ERR_BAD_SHAPE, "dt_pack_conv_weights_batched: empty job list");
+  pack_weights_batched_kernel<<<grid_for(total), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(jobs_device, njobs, total);
   DT_LAUNCH_CHECK();
   return DT_OK;
 }

@@ -452,6 +452,59 @@ def pack_conv_weight(w: torch.Tensor, mode: int, out: Optional[torch.Tensor] = N
     return out
 
 
+def pack_conv_weight_geometry(w_shape, mode: int, cout_pad: Optional[int] = None):
+    """(C_in_p, Kpad, output shape, dtype) of dt_pack_conv_weight for OIHW weights of shape w_shape."""
+    C_out, C_in, R, S = w_shape
+    cinp, kpad = C_in, 0
+    if mode == 0:
+        cinp = 4 if (R == 7 and C_in < 4) else C_in
+        return cinp, kpad, (R * S, cinp, C_out), torch.float32
+    if mode == 1:
+        kpad = (R * S * C_in + 63) // 64 * 64
+        return cinp, kpad, (C_out, kpad), torch.bfloat16
+    if mode == 2:
+        return cinp, 256, (C_out, 256), torch.bfloat16
+    cinp = C_out if cout_pad is None else cout_pad
+    kpad = (R * S * cinp + 63) // 64 * 64
+    return cinp, kpad, (C_in, kpad), torch.bfloat16
+
+
+class WeightPacker:
+    """kernel-layout copies of the fp32 master weights of many layers, refreshed by ONE launch
+    (dt_pack_conv_weights_batched).  ``get`` registers a layout on first use (packing it at once);
+    ``refresh`` repacks every registered layout from the current master weights."""
+
+    def __init__(self, device):
+        self.device = device
+        self.entries = {}           # key -> (w, out, mode, cinp, kpad)
+        self._table = None
+
+    def get(self, key, w: torch.Tensor, mode: int, cout_pad: Optional[int] = None) -> torch.Tensor:
+        ent = self.entries.get(key)
+        if ent is not None and ent[0].data_ptr() == w.data_ptr():
+            return ent[1]
+        out = pack_conv_weight(w, mode, cout_pad=cout_pad)
+        cinp, kpad, _, _ = pack_conv_weight_geometry(w.shape, mode, cout_pad)
+        self.entries[key] = (w, out, mode, cinp, kpad)
+        self._table = None
+        return out
+
+    def refresh(self) -> None:
+        if not self.entries:
+            return
+        if self._table is None:
+            jobs = (_lib.PackJob * len(self.entries))()
+            start = 0
+            for j, (w, out, mode, cinp, kpad) in enumerate(self.entries.values()):
+                C_out, C_in, R, S = w.shape
+                jobs[j] = _lib.PackJob(w.data_ptr(), out.data_ptr(), C_out, C_in, R, S, mode, cinp, kpad, 0, start)
+                start += out.numel()
+            raw = torch.frombuffer(bytearray(bytes(jobs)), dtype=torch.uint8)
+            self._table = (raw.to(self.device), len(self.entries), start)
+        table, n, total = self._table
+        check(load().dt_pack_conv_weights_batched(table.data_ptr(), n, total, stream_ptr()))
+
+
 def conv2d_dgrad_direct(gy: torch.Tensor, w: torch.Tensor, x_shape, stride: int, pad: int,
                         addend: Optional[torch.Tensor] = None, round_weights: bool = False) -> torch.Tensor:
     """gy (N, Ho, Wo, C_out), w fp32 OIHW -> gx of shape x_shape = (N, H, W, C_x)."""

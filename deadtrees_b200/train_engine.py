@@ -55,6 +55,8 @@ class UnetTrainEngine:
         # process group its buckets are all-reduced on a side stream while the backward pass continues
         self.reducer: Optional[GradBucketReducer] = None
         self.set_process_group(None, world_size=1)
+        # kernel layouts (bf16 forward / data-gradient packings) of every conv weight: one batched repack per step
+        self.packer = ops.WeightPacker(dev)
 
     def set_process_group(self, group, world_size: Optional[int] = None, bucket_bytes: int = 25 << 20) -> None:
         order = backward_param_order(self.param_names)
@@ -88,13 +90,11 @@ class UnetTrainEngine:
         N, H, W, Cx = x.shape
         stem = R == 7
         if frame is not None:
-            wp = ops.pack_conv_weight(w, 2)
+            wp = self.packer.get((wname, 2, None), w, 2)
             return ops.conv2d(frame, wp, self._ones, self._zeros, N=N, H=H, W=W, C_in=Cx, C_x=Cx, C_out=C_out, R=R, S=S,
                               stride=stride, pad=pad, relu=False, algo_cin=C_in, flags=CONV_X_PAD3, tag="train." + wname)
-        if self.precision == "fp32":
-            wp = ops.pack_conv_weight(w, 0)
-        else:
-            wp = ops.pack_conv_weight(w, 2 if stem else 1)
+        mode = 0 if self.precision == "fp32" else (2 if stem else 1)
+        wp = self.packer.get((wname, mode, None), w, mode)
         return ops.conv2d(x, wp, self._ones, self._zeros, N=N, H=H, W=W, C_in=Cx, C_x=Cx, C_out=C_out, R=R, S=S,
                           stride=stride, pad=pad, relu=False, algo_cin=C_in, tag="train." + wname)
 
@@ -106,7 +106,7 @@ class UnetTrainEngine:
             self.buffers.get(bn + ".running_var"), BN_EPS, BN_MOMENTUM)
         nbt = self.buffers.get(bn + ".num_batches_tracked")
         if nbt is not None:
-            nbt += 1
+            self._nbt.append(nbt)       # bumped together at the end of the forward pass (one multi-tensor launch)
         a = ops.bn_apply(y, scale, shift, residual=residual, relu=relu)
         self._rec("conv_bn_fwd", conv, x=x, y=y, a=a, residual=residual, mean=mean, invstd=invstd, scale=scale, shift=shift,
                   relu=relu, stride=stride, pad=pad)
@@ -120,6 +120,8 @@ class UnetTrainEngine:
         if T % 32:
             raise ValueError("tile size must be a multiple of 32")
         tape: List = []
+        self._nbt: List[torch.Tensor] = []
+        self.packer.refresh()       # the master weights changed in the optimizer step: repack every layout, one launch
         if self.precision == "bf16" and self.wgrad_tc and ops.stem_wgrad_tc_supported(N, T, T):
             # zero-bordered stem frame: the TMA im2col map over it feeds the forward conv AND the weight gradient
             frame = ops.pack_input_nchw_frame(x_nchw, self.in_channels)
@@ -153,9 +155,12 @@ class UnetTrainEngine:
             xcur = self._conv_bn(tape, a1, p + ".conv2.0", p + ".conv2.1", 1, 1)
         hw = self.params["segmentation_head.0.weight"]
         logits = torch.empty((N, self.classes, T, T), dtype=torch.float32, device=self.device)
-        ops.head(xcur, ops.pack_conv_weight(hw, 0), self.params["segmentation_head.0.bias"], logits_nchw=logits)
+        ops.head(xcur, self.packer.get(("segmentation_head.0.weight", 0, None), hw, 0),
+                 self.params["segmentation_head.0.bias"], logits_nchw=logits)
         self._rec("head_fwd", "segmentation_head.0", x=xcur, y=logits)
         tape.append(("head", xcur))
+        if self._nbt:
+            torch._foreach_add_(self._nbt, 1)
         return logits, tape
 
     # ---- backward pieces -------------------------------------------------------------------------------
@@ -169,12 +174,12 @@ class UnetTrainEngine:
         tc = self.precision == "bf16" and self.dgrad_tc and not fp32_weights and Cx == C_in and C_in % 16 == 0
         if tc and R == 3 and S == 3 and stride == 1 and pad == 1 and Cg % 16 == 0:
             # the data gradient of a stride-1 conv is a stride-1 conv of gy with the flipped, transposed weights
-            wp = ops.pack_conv_weight(w, 3, cout_pad=Cg)
+            wp = self.packer.get((wname, 3, Cg), w, 3, cout_pad=Cg)
             gx = ops.conv2d(gy, wp, self._ones, self._zeros, N=N, H=H, W=W, C_in=Cg, C_x=Cg, C_out=C_in, R=3, S=3, stride=1,
                             pad=1, relu=False, residual=addend, tag="dgrad." + wname)
         elif tc and stride == 2 and ((R == 3 and pad == 1) or (R == 1 and pad == 0)) and Cg % 64 == 0 and Cg == C_out:
             # stride-2 conv: every output pixel gathers the taps whose source coordinate is even (gather producer)
-            wp = ops.pack_conv_weight(w, 4, cout_pad=Cg)
+            wp = self.packer.get((wname, 4, Cg), w, 4, cout_pad=Cg)
             gx = ops.conv2d(gy, wp, self._ones, self._zeros, N=N, H=H, W=W, C_in=Cg, C_x=Cg, C_out=C_in, R=R, S=S, stride=2,
                             pad=pad, relu=False, residual=addend, flags=CONV_TRANSPOSED, tag="dgrad." + wname)
         else:

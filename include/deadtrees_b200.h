@@ -123,6 +123,8 @@ enum {
                                im2col through a TMA tensor map with overlapping strides (conv_stem.cu) */
   DT_CONV_NO_HALO = 4,      /* 3x3/s1 layers: per-tap TMA boxes (conv_tc.cu) instead of the smem-resident halo
                                patches (conv_halo.cu, the default where the shape fits) */
+  DT_CONV_NO_QUAD = 32,     /* up-sample + concat layers with C_out <= 64: one parity class per tile instead of the
+                               class-fused tiles that share the five patches of a region (same results; A/B testing) */
   DT_CONV_TRANSPOSED = 16   /* data gradient of a stride-2 conv: desc.H, W = size of the OUTPUT (the conv's input), x = gy
                                (N, Ho, Wo, C_in) at the conv's output size, out[h][w] = sum over taps with (h + pad - r)
                                even of gy[(h + pad - r) / 2][..] * w; weights in the dt_conv2d_fwd packing with
@@ -240,6 +242,16 @@ int dt_channel_sum(const void* g, int64_t M, int C, int K, int dtype, float* out
  * flip, k = tap*Cop + co (DT_CONV_TRANSPOSED).  Modes 3 / 4 take Cop (>= C_out, channel stride of gy) in `C_in_p`. */
 int dt_pack_conv_weight(const float* w_oihw, int C_out, int C_in, int R, int S, int mode, int C_in_p, int Kpad, void* out,
                         dt_stream_t stream);
+/* The same for many tensors in one launch.  jobs_device: DEVICE array of njobs records sorted by `start` (the running
+ * sum of the output element counts, jobs[0].start = 0); total = sum of all output element counts.  Arguments per
+ * record as dt_pack_conv_weight (not validated here: build the records from calls that passed its checks). */
+typedef struct dt_pack_job {
+  const float* w;
+  void* out;
+  int32_t C_out, C_in, R, S, mode, C_in_p, Kpad, reserved;
+  int64_t start;
+} dt_pack_job;
+int dt_pack_conv_weights_batched(const dt_pack_job* jobs_device, int njobs, int64_t total, dt_stream_t stream);
 /* Generic (CUDA-core) data / weight gradients of conv2d, any stride: fp32 check mode and the layer shapes the
  * tcgen05 kernels do not cover.  x / gx: (N, H, W, C_x) with C_in <= C_x real channels; gy: (N, Ho, Wo, C_out);
  * weights and dw: fp32 OIHW (C_out, C_in, R, S); gx = addend (may be NULL) + dgrad; dbias (may be NULL): float[C_out];

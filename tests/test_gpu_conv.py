@@ -4,7 +4,7 @@ import torch
 import torch.nn.functional as F
 
 from deadtrees_b200 import ops
-from deadtrees_b200._lib import CONV_FORCE_DIRECT, CONV_FORCE_GATHER, CONV_NO_HALO, CONV_X_PAD3
+from deadtrees_b200._lib import CONV_FORCE_DIRECT, CONV_FORCE_GATHER, CONV_NO_HALO, CONV_NO_QUAD, CONV_X_PAD3
 from deadtrees_b200.engine import pack_weight
 from gpu_util import report, to_nchw
 
@@ -22,7 +22,9 @@ LAYERS = [
     ("l4.0.conv1 256->512 s2 @16", 4, 16, 256, 0, 512, 3, 2, 1, False, False, True),
     ("d0.conv1 up(512)+256 -> 256 @16", 2, 16, 512, 256, 256, 3, 1, 1, True, False, True),
     ("d1.conv1 up(256)+128 -> 128 @32", 2, 32, 256, 128, 128, 3, 1, 1, True, False, True),
+    ("d2.conv1 up(128)+64 -> 64 @64", 3, 64, 128, 64, 64, 3, 1, 1, True, False, True),
     ("d3.conv1 up(64)+64 -> 32 @128", 1, 128, 64, 64, 32, 3, 1, 1, True, False, True),
+    ("d3.conv1 up(64)+64 -> 32 @64 x5 images", 5, 64, 64, 64, 32, 3, 1, 1, True, False, False),
     ("d3.conv2 32->32 @128", 1, 128, 32, 0, 32, 3, 1, 1, False, False, True),
     ("d4.conv1 up(32) -> 16 @64", 2, 64, 32, 0, 16, 3, 1, 1, True, False, True),
     ("d4.conv2 16->16 @64", 2, 64, 16, 0, 16, 3, 1, 1, False, False, True),
@@ -106,6 +108,11 @@ def test_conv_tcgen05(case):
     # the halo kernel (default for 3x3/s1 layers) sums K slab-major: equal up to fp32 summation order
     same = (got == got_g).float().mean().item()
     assert same > 0.995 and (got - got_g).abs().max() <= 2.0 ** -7 * ref.abs().max()
+    if case[9]:
+        # up-sample + concat: the class-fused tiles (four parity classes share the region's patches) keep every
+        # class's K order - identical bits to the class-per-tile kernel
+        got_nq = run_cuda(case, x, skip, w, scale, shift, residual, dtype=torch.bfloat16, flags=CONV_NO_QUAD)
+        assert torch.equal(got, got_nq)
 
 
 def test_stem_tcgen05_and_fp32():
