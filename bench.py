@@ -276,9 +276,10 @@ def main_b200(a):
         s = T - ov
         ya, yb = (0, H) if world == 1 else (min(H, r0 * s), min(H, (r1 - 1) * s + T))
         if r1 > r0:
-            mosaic[ya:yb].copy_(host_mosaic[ya:yb], non_blocking=True)
-            mi.run(mosaic, "hwc", tile_rows=(r0, r1) if world > 1 else None, out=mask, halo_hook=hook)
-            host_mask[y0:y1].copy_(mask[y0:y1], non_blocking=True)
+            # MosaicInference's host pipeline: row bands go up on a copy stream while earlier batches compute, finished
+            # mask bands come back behind the compute (single GPU; with shards the mask rows follow the halo exchange)
+            mi.run(mosaic, "hwc", tile_rows=(r0, r1) if world > 1 else None, out=mask, halo_hook=hook,
+                   host_src=host_mosaic, host_out=host_mask)
         return (yb - ya) * W * 3, (y1 - y0) * W
 
     def timed(fn, steps, profile=False):

@@ -143,11 +143,17 @@ class MosaicInference:
         return t
 
     def run(self, mosaic: torch.Tensor, layout: str = "hwc", tile_rows: Optional[Tuple[int, int]] = None,
-            out: Optional[torch.Tensor] = None, halo_hook=None) -> torch.Tensor:
+            out: Optional[torch.Tensor] = None, halo_hook=None, host_src: Optional[torch.Tensor] = None,
+            host_out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """mosaic: CUDA uint8 (H, W, C) ["hwc"] or (C, H, W) ["chw"] -> uint8 class ids (H, W).
 
         ``tile_rows=(r0, r1)`` restricts the work to that range of tile rows (multi-GPU sharding); the
-        returned mask is then only valid on the mosaic rows this shard owns, ``owned_rows(...)``."""
+        returned mask is then only valid on the mosaic rows this shard owns, ``owned_rows(...)``.
+
+        Host pipeline ("hwc" only): with ``host_src`` (pinned uint8 (H, W, C)) the rows a batch of tiles needs are copied
+        into ``mosaic`` on a copy stream while the previous batches compute; with ``host_out`` (pinned uint8 (H, W)) and
+        no ``halo_hook`` the mask is stitched in bands as soon as their tile rows are done and each band goes back to the
+        host behind the compute.  Only the first band's upload and the last band's download are exposed."""
         H, W = (mosaic.shape[0], mosaic.shape[1]) if layout == "hwc" else (mosaic.shape[1], mosaic.shape[2])
         T, ov, eng = self.tile, self.overlap, self.engine
         gy, gx = overlap_grid(H, W, T, ov)
@@ -164,9 +170,31 @@ class MosaicInference:
         else:
             halo = 1 if r0 > 0 else 0  # room for the neighbour's last tile row (only its bottom rows are read)
             logits = self._buf("logits", ((r1 - r0 + halo) * gx, T, T, eng.classes), eng.act_dtype)
+        step = T - ov
+        piped_in = host_src is not None
+        piped_out = host_out is not None and halo_hook is None
+        if (piped_in or host_out is not None) and layout != "hwc":
+            raise ValueError("the host pipeline takes interleaved (H, W, C) mosaics")
+        main = torch.cuda.current_stream()
+        if piped_in or piped_out:
+            if getattr(self, "_copy_streams", None) is None:
+                self._copy_streams = (torch.cuda.Stream(device=eng.device), torch.cuda.Stream(device=eng.device))
+            cs_in, cs_out = self._copy_streams    # uploads never queue behind a download that waits for compute
+            cs_in.wait_stream(main)               # earlier work on `mosaic` / `mask` is done before they are overwritten
+            cs_out.wait_stream(main)
+        y_own0, y_own1 = self.owned_rows(H, T, ov, gy, r0, r1)
+        copied = min(H, r0 * step)                # mosaic rows [r0 * step, copied) are on the device
+        stitched = y_own0                         # mask rows [y_own0, stitched) are final
         for t0 in range(r0 * gx, r1 * gx, bt):
             n = min(bt, r1 * gx - t0)
             xb = x[:n]
+            if piped_in:
+                need = min(H, ((t0 + n - 1) // gx) * step + T)
+                if need > copied:
+                    with torch.cuda.stream(cs_in):
+                        mosaic[copied:need].copy_(host_src[copied:need], non_blocking=True)
+                    copied = need
+                    main.wait_stream(cs_in)
             ops.tile_gather_normalize(mosaic, layout, eng.in_channels, T, ov, (gy, gx), t0, n, self.offset,
                                       self.scale, out=xb, pad=pad)
             if ov == 0:
@@ -175,11 +203,26 @@ class MosaicInference:
             else:
                 lo = t0 - (r0 - halo) * gx
                 eng.forward(xb, logits_nhwc_out=logits[lo: lo + n])
-        if ov > 0:
+            if piped_out:
+                rows_done = (t0 + n) // gx           # complete tile rows so far: mask rows below rows_done * step are final
+                y_end = y_own1 if t0 + n >= r1 * gx else min(y_own1, rows_done * step)
+                if y_end > stitched:
+                    if ov > 0:
+                        ops.stitch_blend_argmax(logits, ov, (gy, gx), self.win, mask, row0=stitched, nrows=y_end - stitched,
+                                                ty_base=r0 - halo)
+                    cs_out.wait_stream(main)
+                    with torch.cuda.stream(cs_out):
+                        host_out[stitched:y_end].copy_(mask[stitched:y_end], non_blocking=True)
+                    stitched = y_end
+        if ov > 0 and not piped_out:
             if halo_hook is not None:
                 halo_hook(logits, gx, halo)  # multi-GPU: exchange boundary logits rows with the neighbours
-            y0, y1 = self.owned_rows(H, T, ov, gy, r0, r1)
-            ops.stitch_blend_argmax(logits, ov, (gy, gx), self.win, mask, row0=y0, nrows=y1 - y0, ty_base=r0 - halo)
+            ops.stitch_blend_argmax(logits, ov, (gy, gx), self.win, mask, row0=y_own0, nrows=y_own1 - y_own0, ty_base=r0 - halo)
+        if host_out is not None and not piped_out:
+            host_out[y_own0:y_own1].copy_(mask[y_own0:y_own1], non_blocking=True)
+        if piped_in or piped_out:
+            main.wait_stream(cs_in)               # callers synchronise the current stream only
+            main.wait_stream(cs_out)
         return mask
 
     @staticmethod
@@ -191,6 +234,13 @@ class MosaicInference:
     def run_host(self, mosaic: np.ndarray, layout: str = "hwc") -> np.ndarray:
         """host ndarray in, host ndarray out (pinned staging; the end-to-end path of ``scripts/inference.py``)."""
         src = torch.from_numpy(np.ascontiguousarray(mosaic))
+        src = src if src.is_pinned() else src.pin_memory()
         dev = self._buf("mosaic_dev", tuple(src.shape), torch.uint8)
-        dev.copy_(src.pin_memory() if not src.is_pinned() else src, non_blocking=True)
-        return self.run(dev, layout).cpu().numpy()
+        if layout != "hwc":
+            dev.copy_(src, non_blocking=True)
+            return self.run(dev, layout).cpu().numpy()
+        H, W = src.shape[0], src.shape[1]
+        host_mask = torch.empty((H, W), dtype=torch.uint8, pin_memory=True)
+        self.run(dev, layout, host_src=src, host_out=host_mask)
+        torch.cuda.current_stream().synchronize()
+        return host_mask.numpy()
