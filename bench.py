@@ -506,7 +506,12 @@ def main_train(a):
 
     def step_e2e():
         if use_graph:
-            loss = gstep(img_h, mask_h)      # H2D into the static buffers + replay
+            # double-buffered input: this step's batch was uploaded (pinned host -> staging) behind the previous step;
+            # hand it over, replay, and start the upload of the next step's batch - one upload per step
+            if not getattr(gstep, "_staged", False):
+                gstep.prefetch(img_h, mask_h)
+            loss = gstep.step_prefetched()
+            gstep.prefetch(img_h, mask_h)
         else:
             img_d.copy_(img_h, non_blocking=True)
             mask_d.copy_(mask_h, non_blocking=True)

@@ -82,6 +82,35 @@ class GraphedTrainStep:
         self.graph.replay()
         return self.terms.total_loss
 
+    def prefetch(self, img: torch.Tensor, mask: torch.Tensor) -> None:
+        """starts the upload of the NEXT batch (pinned host tensors) into staging buffers on a copy stream; it runs
+        behind the step that is being replayed.  ``step_prefetched()`` then consumes it."""
+        if getattr(self, "_stage", None) is None:
+            dev = self.img.device
+            self._stage = (torch.empty_like(self.img), torch.empty_like(self.mask))
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._stage_free = torch.cuda.Event()
+            self._stage_free.record()
+        cs = self._copy_stream
+        cs.wait_event(self._stage_free)                # the previous hand-over out of the staging buffers is done
+        with torch.cuda.stream(cs):
+            self._stage[0].copy_(img, non_blocking=True)
+            self._stage[1].copy_(mask, non_blocking=True)
+        self._staged = True
+
+    def step_prefetched(self) -> torch.Tensor:
+        """hands the prefetched batch over to the graph's static buffers (device-to-device) and replays the step."""
+        if not getattr(self, "_staged", False):
+            raise RuntimeError("step_prefetched() needs a prefetch() first")
+        main = torch.cuda.current_stream()
+        main.wait_stream(self._copy_stream)
+        self.img.copy_(self._stage[0], non_blocking=True)
+        self.mask.copy_(self._stage[1], non_blocking=True)
+        self._stage_free.record(main)
+        self._staged = False
+        self.graph.replay()
+        return self.terms.total_loss
+
     def check(self) -> float:
         """host-side checks of the last replayed step (one synchronisation): label range, finite loss."""
         self.terms.check_labels()

@@ -483,6 +483,51 @@ def test_flat_adam_path_equals_per_parameter_path():
     assert out.shape == (n, 3, T, T) and torch.isfinite(out).all()
 
 
+def test_graphed_training_step_equals_eager():
+    """the whole step replayed from one CUDA graph (deadtrees_b200/train_graph.py) against the same step launched kernel
+    by kernel: three steps, the graph fed once through __call__ and twice through the prefetch pipeline.  The losses
+    must agree to the last bit; the parameters to 1e-6 (the head's bias gradient and the gradient norm of the clip are
+    atomic sums, so the clip factor - and with it every update - may differ in the last bit between two runs)."""
+    from deadtrees_b200.train_graph import GraphedTrainStep
+    cin, n, T = 4, 2, 128
+    oracle = oracle_model(cin, 3)
+    img, mask = _batch(n, cin, T, 3)
+    img2, mask2 = _batch(n, cin, T, 3, seed=12)
+    batches = [(img, mask), (img2, mask2), (img, mask)]
+    stats = [{"file": f"t{i}"} for i in range(n)]
+    segs, losses = [], []
+    for graphed in (False, True):
+        seg = SemSegment(dict(NETWORK, in_channels=cin, precision="bf16"), dict(TRAINING, gradient_clip_val=0.5))
+        seg.model.load_state_dict(oracle.state_dict())
+        seg.cuda().train()
+        (opt,), _ = seg.configure_optimizers()
+        ls = []
+        if graphed:
+            gs = GraphedTrainStep(seg, opt, n, T)
+            pinned = [(a.pin_memory(), b.pin_memory()) for a, b in batches]
+            ls.append(float(gs(*pinned[0])))
+            gs.prefetch(*pinned[1])
+            ls.append(float(gs.step_prefetched()))
+            gs.prefetch(*pinned[2])
+            ls.append(float(gs.step_prefetched()))
+            assert gs.check() == ls[-1]
+        else:
+            for a, b in batches:
+                loss = seg.training_step({"main": (a.cuda(), b.cuda(), None, torch.zeros(n), stats)}, 0)
+                loss.backward()
+                opt.step()
+                ls.append(float(loss.detach()))
+        torch.cuda.synchronize()
+        segs.append(seg)
+        losses.append(ls)
+    print("losses eager", losses[0], "graph", losses[1])
+    assert losses[0] == losses[1]
+    for (name, p), (_, q) in zip(segs[0].model.named_parameters(), segs[1].model.named_parameters()):
+        assert (p.detach() - q.detach()).abs().max().item() < 1e-6, name
+    for (name, p), (_, q) in zip(segs[0].model.named_buffers(), segs[1].model.named_buffers()):
+        assert (p.double() - q.double()).abs().max().item() < 1e-6, name
+
+
 @pytest.mark.parametrize("cin,cout,k,N,H", [(64, 128, 3, 2, 32), (256, 512, 3, 2, 16), (128, 256, 1, 1, 32), (64, 128, 1, 2, 16)])
 def test_dgrad_stride2_gather_kernel(cin, cout, k, N, H):
     """data gradient of the stride-2 convs (3x3 pad 1, 1x1 pad 0) through the tcgen05 gather producer (DT_CONV_TRANSPOSED)."""
