@@ -53,6 +53,7 @@ _SIGNATURES = {
     "dt_head_fwd": ([_p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p], C.c_int),
     "dt_head_fwd_tc": ([_p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p], C.c_int),
     "dt_argmax_nchw": ([_p, _i, _i, _i, _i, _p, _p], C.c_int),
+    "dt_mode_vote": ([_p, _i, _i64, _i, _p, _p], C.c_int),
     "dt_seg_loss_partials": ([_p, _p, _i, _i, _i, _i, _p, _p, _p, _p], C.c_int),
     "dt_seg_loss_finalize": ([_p, _p, _i, _i, _i, _i, _p, _p, _p, _p], C.c_int),
     "dt_seg_loss_backward": ([_p, _p, _i, _i, _i, _i, _p, _p, _f, _p, _p], C.c_int),

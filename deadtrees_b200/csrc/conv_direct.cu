@@ -257,6 +257,38 @@ __global__ void argmax_nchw_kernel(const float* __restrict__ logits, int N, int 
   }
 }
 
+// Per-pixel majority vote over M class-id masks (PyTorchEnsembleInference.run, deadtrees/deployment/inference.py:96-116:
+// torch.mode over the stacked argmax masks).  torch.mode returns the SMALLEST of the most frequent values; class ids
+// are < 256.  One thread = 16 consecutive pixels: one 16-byte load per model, counts by pairwise comparison
+// (M <= 15), int64 (what the reference returns) or uint8 output.
+template <typename OUT>
+__global__ void mode_vote_kernel(const uint8_t* __restrict__ masks, int M, int64_t n, OUT* __restrict__ out) {
+  const int64_t nvec = (n + 15) / 16;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < nvec;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t p0 = i * 16;
+    uint8_t v[15][16];
+    const bool fast = p0 + 16 <= n && n % 16 == 0;
+    for (int m = 0; m < M; ++m) {
+      if (fast) {
+        *reinterpret_cast<uint4*>(v[m]) = __ldg(reinterpret_cast<const uint4*>(masks + m * n + p0));
+      } else {
+        for (int j = 0; j < 16; ++j) v[m][j] = p0 + j < n ? masks[m * n + p0 + j] : 0;
+      }
+    }
+    for (int j = 0; j < 16; ++j) {
+      if (p0 + j >= n) break;
+      int best_count = 0, best_val = 256;
+      for (int a = 0; a < M; ++a) {
+        int c = 0;
+        for (int b = 0; b < M; ++b) c += v[b][j] == v[a][j];
+        if (c > best_count || (c == best_count && v[a][j] < best_val)) { best_count = c; best_val = v[a][j]; }
+      }
+      out[p0 + j] = static_cast<OUT>(best_val);
+    }
+  }
+}
+
 inline int grid_for(int64_t work) {
   int64_t blocks = (work + kThreads - 1) / kThreads;
   const int64_t cap = static_cast<int64_t>(dt_num_sms()) * 16;
@@ -362,6 +394,20 @@ int dt_argmax_nchw(const float* logits, int N, int K, int H, int W, uint8_t* mas
   DT_REQUIRE(N > 0 && K > 0 && K <= 255 && H > 0 && W > 0, DT_ERR_BAD_SHAPE, "dt_argmax_nchw: bad shape");
   const int64_t HW = static_cast<int64_t>(H) * W;
   argmax_nchw_kernel<<<grid_for(N * HW), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(logits, N, K, HW, mask);
+  DT_LAUNCH_CHECK();
+  return DT_OK;
+}
+
+int dt_mode_vote(const uint8_t* masks, int M, int64_t n, int out_int64, void* out, dt_stream_t stream) {
+  DT_ARCH_GUARD();
+  DT_REQUIRE(masks != nullptr && out != nullptr && M >= 1 && M <= 15 && n > 0, DT_ERR_BAD_SHAPE,
+             "dt_mode_vote: M=%d (1..15) masks of n=%lld pixels", M, static_cast<long long>(n));
+  DT_REQUIRE(reinterpret_cast<uintptr_t>(masks) % 16 == 0, DT_ERR_BAD_ALIGN, "dt_mode_vote: masks must be 16-byte aligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (out_int64)
+    mode_vote_kernel<int64_t><<<grid_for((n + 15) / 16), kThreads, 0, s>>>(masks, M, n, static_cast<int64_t*>(out));
+  else
+    mode_vote_kernel<uint8_t><<<grid_for((n + 15) / 16), kThreads, 0, s>>>(masks, M, n, static_cast<uint8_t*>(out));
   DT_LAUNCH_CHECK();
   return DT_OK;
 }

@@ -89,12 +89,19 @@ class PyTorchEnsembleInference:
         require_device()
         if input_tensor.dim() == 3:
             input_tensor.unsqueeze_(0)
-        outs = []
-        for model in self._models:
+        if len(self._models) > 15:
+            raise ValueError("the majority-vote kernel takes at most 15 models")
+        x = input_tensor.to(device)
+        masks = None
+        for i, model in enumerate(self._models):
             model.to(device)
             with torch.no_grad():
-                outs.append(ops.argmax_nchw(model(input_tensor.to(device))).long().squeeze())
-        return torch.mode(torch.stack(outs, dim=1), axis=1)[0]
+                m = ops.argmax_nchw(model(x))             # uint8 (N, H, W)
+            if masks is None:
+                masks = torch.empty((len(self._models),) + tuple(m.shape), dtype=torch.uint8, device=m.device)
+            masks[i].copy_(m)
+        # torch.mode(torch.stack(outs, dim=1), axis=1)[0] of the reference, one fused pass: int64 (N, H, W) / (H, W)
+        return ops.mode_vote(masks).squeeze()
 
 
 # --------------------------------------------------------------------------------------------------

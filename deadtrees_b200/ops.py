@@ -217,6 +217,18 @@ def argmax_nchw(logits: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def mode_vote(masks: torch.Tensor, out_int64: bool = True) -> torch.Tensor:
+    """(M, ...) uint8 class-id masks of M models -> per-pixel majority class (smallest on ties, as torch.mode)."""
+    masks = _cuda(masks, "masks")
+    if masks.dtype != torch.uint8:
+        raise TypeError("masks must be uint8")
+    M = masks.shape[0]
+    n = masks[0].numel()
+    out = torch.empty(masks.shape[1:], dtype=torch.int64 if out_int64 else torch.uint8, device=masks.device)
+    check(load().dt_mode_vote(masks.data_ptr(), M, n, int(out_int64), out.data_ptr(), stream_ptr()))
+    return out
+
+
 # ---- loss / optimizer ------------------------------------------------------------------------
 
 def seg_loss_partials(logits: torch.Tensor, labels: torch.Tensor):

@@ -154,6 +154,12 @@ int dt_head_fwd_tc(const void* x, int N, int H, int W, int K, const void* w_pack
 /* argmax over the class dim of NCHW fp32 logits -> uint8 (first max wins) */
 int dt_argmax_nchw(const float* logits, int N, int K, int H, int W, uint8_t* mask, dt_stream_t stream);
 
+/* Majority vote of an ensemble (PyTorchEnsembleInference.run, deadtrees/deployment/inference.py:96-116: torch.mode over
+ * the models' argmax masks): masks = M stacked uint8 class-id masks of n pixels each (M * n bytes, M <= 15);
+ * out[p] = the most frequent class of pixel p, the smallest one on ties (torch.mode), as int64 (out_int64 != 0, the
+ * reference's return type) or uint8. */
+int dt_mode_vote(const uint8_t* masks, int M, int64_t n, int out_int64, void* out, dt_stream_t stream);
+
 /* ---- K11: losses and metric ----------------------------------------------------------------------
  * One pass over logits (N, K, H, W) fp32 + labels (N, H, W) int64 computing softmax in registers and
  * the partial sums every reference loss needs (deadtrees/loss/losses.py:226-247 DiceLoss, :273-291

@@ -122,6 +122,44 @@ def test_pytorch_inference_api(tmp_path):
     with pytest.raises(TypeError):
         inf.run(np.zeros((3, 64, 64), np.float32))
 
+@pytest.mark.parametrize("M,shape,K", [(3, (2, 37, 29), 3), (5, (1, 64, 64), 4), (1, (5,), 2), (7, (3, 16, 16), 3), (15, (33,), 5)])
+def test_mode_vote_matches_torch_mode(M, shape, K):
+    """dt_mode_vote (majority class, smallest on ties) against torch.mode over the stacked masks."""
+    g = torch.Generator().manual_seed(M * 7 + K)
+    masks = torch.randint(0, K, (M,) + shape, generator=g, dtype=torch.uint8)
+    ref = torch.mode(masks.long(), dim=0)[0]
+    got = ops.mode_vote(masks.cuda())
+    assert got.dtype == torch.int64 and torch.equal(got.cpu(), ref)
+    assert torch.equal(ops.mode_vote(masks.cuda(), out_int64=False).cpu(), ref.to(torch.uint8))
+
+
+def test_ensemble_inference_api(tmp_path):
+    """PyTorchEnsembleInference (deadtrees/deployment/inference.py:65-116): three checkpoints, majority vote == torch.mode
+    over the single-model results; even model counts and mixed channel configurations raise ValueError."""
+    from deadtrees_b200.deployment.inference import PyTorchEnsembleInference
+    files = []
+    for seed in range(3):
+        model = oracle_model(3, 3, seed=seed)
+        m = SemSegment(dict(NETWORK, precision="fp32"), TRAINING)
+        m.model.load_state_dict(model.state_dict())
+        f = tmp_path / f"m{seed}.ckpt"
+        m.save_checkpoint(f)
+        files.append(f)
+    _, x = normalized_tiles(2, 64, 4)
+    singles = [PyTorchInference(f).run(x.clone().cuda(), device="cuda") for f in files]
+    ref = torch.mode(torch.stack(singles, dim=1), axis=1)[0]
+    ens = PyTorchEnsembleInference(*files)
+    out = ens.run(x.clone().cuda(), device="cuda")
+    assert out.dtype == torch.int64 and out.shape == (2, 64, 64) and torch.equal(out, ref)
+    assert not torch.equal(singles[0], singles[1])             # the vote is not trivial
+    one = ens.run(x[0].clone().cuda(), device="cuda")          # 3-d input -> 2-d output
+    assert one.shape == (64, 64) and torch.equal(one, ref[0])
+    with pytest.raises(ValueError):
+        PyTorchEnsembleInference(files[0], files[1])
+    with pytest.raises(TypeError):
+        ens.run(np.zeros((3, 64, 64), np.float32))
+
+
 
 def test_semsegment_val_step_losses():
     model = oracle_model(3, 3)
