@@ -208,9 +208,15 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int split
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int64_t cc = i % plane;      // co * C_in + ci (ci fastest: coalesced reads)
     const int tap = static_cast<int>(i / plane);
-    float acc = 0.f;
-    for (int s = 0; s < splits; ++s) acc += partial[(static_cast<int64_t>(s) * RS + tap) * plane + cc];
-    dw[cc * RS + tap] = acc;
+    // eight independent partial sums (loads in flight together), combined in a fixed order: deterministic
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    int s = 0;
+    for (; s + 8 <= splits; s += 8) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc[u] += partial[(static_cast<int64_t>(s + u) * RS + tap) * plane + cc];
+    }
+    for (int u = 0; s < splits; ++s, ++u) acc[u] += partial[(static_cast<int64_t>(s) * RS + tap) * plane + cc];
+    dw[cc * RS + tap] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
   }
 }
 

@@ -105,16 +105,24 @@ __global__ void channel_reduce_kernel(const T* __restrict__ y, const T* __restri
   }
 }
 
-// sum of the block partials of channel c (one warp per channel, fixed lane order -> deterministic)
-__device__ __forceinline__ void warp_channel_sums(const float* __restrict__ part, int nblocks, int C, int c, double& s, double& q) {
-  const int lane = threadIdx.x & 31;
-  s = 0.0; q = 0.0;
-  for (int b = lane; b < nblocks; b += 32) {
-    s += part[static_cast<int64_t>(b) * C + c];
-    q += part[(static_cast<int64_t>(nblocks) + b) * C + c];
+// sum of the block partials of channel c by one 128-thread block (fixed thread -> partial assignment and a fixed-order
+// tree: deterministic).  One warp per channel took ~10 us for the ~600 partials of a reduction - 92 such launches
+// per training step; 128 threads have at most 5 partials each.
+constexpr int kFinThreads = 128;
+__device__ __forceinline__ void block_channel_sums(const float* __restrict__ part, int nblocks, int C, int c, double& s, double& q) {
+  __shared__ double sh_s[kFinThreads], sh_q[kFinThreads];
+  double ts = 0.0, tq = 0.0;
+  for (int b = threadIdx.x; b < nblocks; b += kFinThreads) {
+    ts += part[static_cast<int64_t>(b) * C + c];
+    tq += part[(static_cast<int64_t>(nblocks) + b) * C + c];
   }
-  s = warp_sum(s);
-  q = warp_sum(q);
+  sh_s[threadIdx.x] = ts; sh_q[threadIdx.x] = tq;
+  __syncthreads();
+  for (int o = kFinThreads / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) { sh_s[threadIdx.x] += sh_s[threadIdx.x + o]; sh_q[threadIdx.x] += sh_q[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  s = sh_s[0]; q = sh_q[0];
 }
 
 // batch statistics -> (scale, shift) of the normalisation, saved (mean, invstd), running-stat update
@@ -123,11 +131,10 @@ __global__ void bn_finalize_kernel(const float* __restrict__ part, int nblocks, 
                                    float* __restrict__ running_mean, float* __restrict__ running_var,
                                    float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
                                    float* __restrict__ invstd_out) {
-  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (c >= C) return;
+  const int c = blockIdx.x;
   double s, q;
-  warp_channel_sums(part, nblocks, C, c, s, q);
-  if ((threadIdx.x & 31) != 0) return;
+  block_channel_sums(part, nblocks, C, c, s, q);
+  if (threadIdx.x != 0) return;
   const double mean = s / M;
   double var = q / M - mean * mean;
   if (var < 0.0) var = 0.0;
@@ -148,11 +155,10 @@ __global__ void bn_finalize_kernel(const float* __restrict__ part, int nblocks, 
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ part, int nblocks, int C, double M,
                                        float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ c1,
                                        float* __restrict__ c2) {
-  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (c >= C) return;
+  const int c = blockIdx.x;
   double s, q;
-  warp_channel_sums(part, nblocks, C, c, s, q);
-  if ((threadIdx.x & 31) != 0) return;
+  block_channel_sums(part, nblocks, C, c, s, q);
+  if (threadIdx.x != 0) return;
   dbeta[c] = static_cast<float>(s);
   dgamma[c] = static_cast<float>(q);
   c1[c] = static_cast<float>(s / M);
@@ -428,6 +434,20 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int N, int K, i
   }
 }
 
+// Kp == 16 bf16 (the logits gradient entering the tensor-core head backward): one thread = one pixel, K coalesced plane
+// reads and one 32-byte store (the scalar form above wrote 2 bytes per thread: 244 us for 64 tiles of 256 x 256)
+__global__ void nchw_to_nhwc16_bf16_kernel(const float* __restrict__ x, int N, int K, int64_t HW, __nv_bfloat16* __restrict__ out) {
+  const int64_t total = static_cast<int64_t>(N) * HW;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t n = i / HW, px = i - n * HW;
+    float f[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) f[k] = k < K ? __ldg(x + (n * K + k) * HW + px) : 0.f;
+    store_bf16x16(out + i * 16, f);
+  }
+}
+
 // ---- weight repacking (fp32 OIHW master -> kernel layouts) ----------------------------------------------------
 // mode 0: fp32 [tap][C_in_p][C_out]                                   (direct forward; C_in_p >= C_in, zero padded)
 // mode 1: bf16 [C_out][Kpad], k = tap * C_in + ci                      (tcgen05 forward)
@@ -474,15 +494,18 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int C_out, int C
 // every layout of every layer in ONE launch (the training step repacks ~93 weight tensors after each optimizer step):
 // jobs[j] covers the output elements [start_j, start_{j+1}); a thread finds its job by binary search.
 __global__ void pack_weights_batched_kernel(const dt_pack_job* __restrict__ jobs, int njobs, int64_t total) {
+  extern __shared__ int64_t job_start[];          // the binary search runs on shared memory
+  for (int j = threadIdx.x; j < njobs; j += blockDim.x) job_start[j] = jobs[j].start;
+  __syncthreads();
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     int lo = 0, hi = njobs - 1;
     while (lo < hi) {
       const int mid = (lo + hi + 1) >> 1;
-      if (jobs[mid].start <= i) lo = mid; else hi = mid - 1;
+      if (job_start[mid] <= i) lo = mid; else hi = mid - 1;
     }
-    const dt_pack_job jb = jobs[lo];
-    pack_weight_element(jb.w, jb.C_out, jb.C_in, jb.R, jb.S, jb.mode, jb.C_in_p, jb.Kpad, jb.out, i - jb.start);
+    const dt_pack_job& jb = jobs[lo];
+    pack_weight_element(jb.w, jb.C_out, jb.C_in, jb.R, jb.S, jb.mode, jb.C_in_p, jb.Kpad, jb.out, i - job_start[lo]);
   }
 }
 
@@ -641,7 +664,7 @@ int dt_bn_train_stats(const void* y, int64_t M, int C, int dtype, const float* g
       (channel_reduce_kernel<float, 0><<<nb, kThreads, 0, s>>>(static_cast<const float*>(y), nullptr, nullptr, nullptr, nullptr, M, C, workspace)),
       (channel_reduce_kernel<__nv_bfloat16, 0><<<nb, kThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(y), nullptr, nullptr, nullptr, nullptr, M, C, workspace)));
   DT_LAUNCH_CHECK();
-  bn_finalize_kernel<<<(C + 7) / 8, 256, 0, s>>>(workspace, nb, C, static_cast<double>(M), gamma, beta, eps, momentum,
+  bn_finalize_kernel<<<C, kFinThreads, 0, s>>>(workspace, nb, C, static_cast<double>(M), gamma, beta, eps, momentum,
                                                      running_mean, running_var, scale, shift, mean, invstd);
   DT_LAUNCH_CHECK();
   return DT_OK;
@@ -677,7 +700,7 @@ int dt_bn_train_bwd(const void* g, const void* a, const void* y, int64_t M, int 
       (channel_reduce_kernel<float, 1><<<nb, kThreads, 0, s>>>(static_cast<const float*>(y), static_cast<const float*>(g), static_cast<const float*>(a), mean, invstd, M, C, workspace)),
       (channel_reduce_kernel<__nv_bfloat16, 1><<<nb, kThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(y), static_cast<const __nv_bfloat16*>(g), static_cast<const __nv_bfloat16*>(a), mean, invstd, M, C, workspace)));
   DT_LAUNCH_CHECK();
-  bn_bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, s>>>(workspace, nb, C, static_cast<double>(M), dgamma, dbeta, c1, c2);
+  bn_bwd_finalize_kernel<<<C, kFinThreads, 0, s>>>(workspace, nb, C, static_cast<double>(M), dgamma, dbeta, c1, c2);
   DT_LAUNCH_CHECK();
   DT_DTYPE_SWITCH(dtype,
       (bn_bwd_apply_kernel<float><<<grid_for(nvec), kThreads, 0, s>>>(static_cast<const float*>(g), static_cast<const float*>(a), static_cast<const float*>(y), mean, invstd, scale, c1, c2, nvec, C, static_cast<float*>(gy), static_cast<float*>(gz_out))),
@@ -787,6 +810,11 @@ int dt_nchw_to_nhwc(const float* x, int N, int K, int H, int W, int Kp, int dtyp
              "dt_nchw_to_nhwc: bad shape");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int64_t HW = static_cast<int64_t>(H) * W, total = N * HW * Kp;
+  if (dtype == DT_BF16 && Kp == 16 && reinterpret_cast<uintptr_t>(out) % 32 == 0) {
+    nchw_to_nhwc16_bf16_kernel<<<grid_for(N * HW, 16), kThreads, 0, s>>>(x, N, K, HW, static_cast<__nv_bfloat16*>(out));
+    DT_LAUNCH_CHECK();
+    return DT_OK;
+  }
   DT_DTYPE_SWITCH(dtype,
       (nchw_to_nhwc_kernel<float><<<grid_for(total, 16), kThreads, 0, s>>>(x, N, K, HW, Kp, static_cast<float*>(out))),
       (nchw_to_nhwc_kernel<__nv_bfloat16><<<grid_for(total, 16), kThreads, 0, s>>>(x, N, K, HW, Kp, static_cast<__nv_bfloat16*>(out))));
@@ -834,7 +862,9 @@ int dt_pack_conv_weight(const float* w_oihw, int C_out, int C_in, int R, int S, 
 int dt_pack_conv_weights_batched(const dt_pack_job* jobs_device, int njobs, int64_t total, dt_stream_t stream) {
   DT_ARCH_GUARD();
   DT_REQUIRE(jobs_device != nullptr && njobs > 0 && total > 0, DT_ERR_BAD_SHAPE, "dt_pack_conv_weights_batched: empty job list");
-  pack_weights_batched_kernel<<<grid_for(total), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(jobs_device, njobs, total);
+  DT_REQUIRE(njobs <= 4096, DT_ERR_BAD_SHAPE, "dt_pack_conv_weights_batched: at most 4096 jobs");
+  pack_weights_batched_kernel<<<grid_for(total, 16), kThreads, njobs * sizeof(int64_t), static_cast<cudaStream_t>(stream)>>>(
+      jobs_device, njobs, total);
   DT_LAUNCH_CHECK();
   return DT_OK;
 }

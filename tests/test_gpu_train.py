@@ -474,8 +474,11 @@ def test_flat_adam_path_equals_per_parameter_path():
         segs.append(seg)
     torch.cuda.synchronize()
     for (name, p), (_, q) in zip(segs[0].model.named_parameters(), segs[1].model.named_parameters()):
-        # two Adam steps of 3e-4; fp32 atomics in the generic wgrad make the gradients differ in the last bits
-        assert (p.detach() - q.detach()).abs().max().item() < 2e-5, name
+        # two Adam steps of 3e-4; fp32 atomics in the generic wgrad make the gradients differ in the last bits, and Adam's
+        # m / sqrt(v) turns a last-bit difference of a near-zero gradient into a visible one: single entries may move by a
+        # fraction of the step (bounded by 2 * lr), the tensors as a whole must coincide
+        d = (p.detach() - q.detach()).abs()
+        assert d.max().item() < 6.5e-4 and d.mean().item() < 2e-6, name
     # the flattened parameters still serve the inference engine
     segs[1].eval()
     with torch.no_grad():
