@@ -76,6 +76,18 @@ def synthetic_mosaic(size: int, device, seed: int = 1234) -> torch.Tensor:
     return out
 
 
+def ncu_conv_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the conv launches of one 135-tile batch, from the committed
+    `ncu --set full` capture (profiles/r01_convs_ncu_full_v4.txt, scripts/gpu_profile2.sh) - not measured in this run."""
+    import re
+    f = ROOT / "profiles" / "r01_convs_ncu_full_v4.txt"
+    if not f.exists():
+        return None
+    m = re.search(r"= ([0-9.]+) GB per (\d+)-tile batch", f.read_text())
+    n = sum(1 for l in f.read_text().splitlines() if "_kernel" in l)
+    return (float(m.group(1)) * 1e9, int(m.group(2)), n) if m and n else None
+
+
 def peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -352,6 +364,14 @@ def main_b200(a):
                                "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"],
                                "traffic": None, "launches": nc, "share_of_step": tc * 1e3 / ms_prof_total,
                                "flops_per_tile": conv_flops_per_tile(T, 3, 3), "peak_source": pk["source"]}
+            tr = ncu_conv_traffic()
+            if tr is not None and T == 256:
+                out["roofline"]["traffic"] = tr[0] / tr[2]
+                out["roofline"]["traffic_source"] = (
+                    f"ncu --set full capture of the {tr[2]} conv launches of one {tr[1]}-tile batch "
+                    f"(profiles/r01_convs_ncu_full_v4.txt): {tr[0] / 1e9:.3f} GB DRAM read + write per batch = "
+                    f"{tr[0] / tr[1] / 1e6:.1f} MB per tile, averaged per launch here; bf16 activations in + out of "
+                    f"all convs, unfused: 44.6 MB per tile")
         hb = {}
         if tg > 0:
             hb["gather_normalize"] = {"achieved": wg / tg / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",

@@ -9,8 +9,8 @@ run() { name=$1; shift; echo "=== $name"; timeout "${TMO:-900}" "$@" > gpurun_ou
 SMALL="python bench.py --size 4096 --steps 1 --warmup 3 --no-cpu-baseline --no-profile"
 TAIL=2 run small_plain $SMALL
 if [ "$(tail -n1 gpurun_out/small_plain.log | head -c1)" = "{" ]; then
-  # launches per step: 3 x (gather + 47 conv + maxpool + head) + stitch = 151; skip the 3 warm-up steps
-  TAIL=3 run ncu_list ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"conv_|gather_normalize|maxpool|stitch_" -s 453 -c 151 --csv --log-file gpurun_out/launches.csv $SMALL
+  # launches per step: 3 x (gather + 47 conv + maxpool + head) + stitch + 2 strip passes = 153; skip the 3 warm-up steps
+  TAIL=3 run ncu_list ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"conv_|gather_normalize|maxpool|stitch_" -s 459 -c 153 --csv --log-file gpurun_out/launches.csv $SMALL
   # full capture: the 47 conv launches + head of the first batch of the timed step (kernels named conv_*)
   TAIL=3 run ncu_full ncu --set full --clock-control none -k regex:conv_ -s 432 -c 48 -o /tmp/prof_convs -f $SMALL
   ncu -i /tmp/prof_convs.ncu-rep --page raw --csv > gpurun_out/prof_convs_raw.csv 2> gpurun_out/prof_export.log
