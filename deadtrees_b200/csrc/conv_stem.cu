@@ -173,6 +173,167 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 
 }  // namespace
 
+// ------------------------------------------------------------------------------------------------------------------
+// Row form of the stem (output width a multiple of 128): the im2col operand is read IN PLACE from the raw input rows.
+//
+// The im2col tensor map above fetches 7 x (128 px x 64 B) = 56 KB per 128 output pixels - every input pixel crosses
+// L2 -> SM up to 28 times (ncu: 1.06 GB of L2 reads per 135-tile launch, l1tex 70 % busy, 180 us against ~50 us for
+// the 0.36 GB the layer reads and writes).  In the zero-bordered frame the 8 pixels x 4 channels under filter row r of
+// output pixel wo start at byte 16*wo of input row 2*ho + r: consecutive output pixels are 16 bytes apart and the two
+// 16-byte halves of a K = 16 step are 16 bytes apart - exactly the NO-SWIZZLE K-major canonical layout
+// ((8 rows at 16 B, row groups at SBO = 128 B), (8 elements, chunks at LBO = 16 B)) with overlapping core matrices.
+// So ONE bulk copy brings the 7 (contiguous) input rows of an output row into shared memory (14.8 KB at T = 256,
+// 3.8x less than the im2col boxes) and the 14 MMAs of a tile point their A descriptors into it:
+// start = row r + 16 * wo0 (+ 32 B for the second K step).  Weights stay SWIZZLE_64B as above.
+//   warp 0: bulk-copy producer   warp 1: MMA issuer   warps 2..5: epilogue (same as above)
+// ------------------------------------------------------------------------------------------------------------------
+namespace {
+
+struct StemRowParams {
+  int Ho, Wo, total_rows, tiles_per_row, relu, stages;
+  int row_bytes, stage_bytes;            // one input row of the frame, 7 rows rounded up to 128 B
+  int64_t image_bytes;                   // one frame image
+  const uint8_t* x;
+  __nv_bfloat16* y;
+  const float* scale;
+  const float* shift;
+};
+
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+constexpr int ROW_MAX_STAGES = 8;
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_stem_rows_kernel(const __grid_constant__ CUtensorMap tm_b, const StemRowParams p) {
+  constexpr int TMEM_COLS = 2 * BN;
+  constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_w = smem;
+  uint8_t* smem_a = smem + W_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + static_cast<size_t>(p.stages) * p.stage_bytes);
+  uint64_t* w_full = bars;
+  uint64_t* full = w_full + 1;                   // [ROW_MAX_STAGES]
+  uint64_t* empty = full + ROW_MAX_STAGES;       // [ROW_MAX_STAGES]
+  uint64_t* tmem_full = empty + ROW_MAX_STAGES;  // [2]
+  uint64_t* tmem_empty = tmem_full + 2;          // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_b);
+    mbar_init(w_full, 1u);
+    for (int i = 0; i < p.stages; ++i) { mbar_init(&full[i], 1u); mbar_init(&empty[i], 1u); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1u); mbar_init(&tmem_empty[i], 128u); }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(w_full, W_BYTES);
+      for (int r = 0; r < ROWS; ++r) tma_load_2d(smem_w + r * W_SUB, &tm_b, w_full, r * 32, 0);
+      int st = 0;
+      uint32_t ph = 0;
+      const uint32_t bytes = static_cast<uint32_t>(ROWS * p.row_bytes);
+      for (int row = blockIdx.x; row < p.total_rows; row += gridDim.x) {
+        const int n = row / p.Ho, ho = row - n * p.Ho;
+        mbar_wait(&empty[st], ph ^ 1u);
+        mbar_arrive_expect_tx(&full[st], bytes);
+        bulk_load(smem_a + static_cast<size_t>(st) * p.stage_bytes,
+                  p.x + n * p.image_bytes + static_cast<int64_t>(2 * ho) * p.row_bytes, bytes, &full[st]);
+        if (++st == p.stages) { st = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint64_t a_hi = umma_desc(0u, 128u, 0u);   // no swizzle: rows 16 B apart, 8-row groups 128 B, K chunks 16 B
+      const uint64_t b_d0 = umma_desc(smem_u32(smem_w), 512u, 4u);
+      mbar_wait(w_full, 0);
+      int st = 0, buf = 0;
+      uint32_t ph = 0, pbuf = 0;
+      for (int row = blockIdx.x; row < p.total_rows; row += gridDim.x) {
+        mbar_wait(&full[st], ph);
+        tc_fence_after();
+        const uint32_t a_stage = smem_u32(smem_a + static_cast<size_t>(st) * p.stage_bytes);
+        for (int t = 0; t < p.tiles_per_row; ++t) {
+          mbar_wait(&tmem_empty[buf], pbuf ^ 1u);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + buf * BN;
+          const uint32_t a_tile = a_stage + t * (BM * 16);
+#pragma unroll
+          for (int r = 0; r < ROWS; ++r) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+              umma_bf16_ss(d_tmem, a_hi + (((a_tile + r * p.row_bytes + k * 32) & 0x3FFFFu) >> 4),
+                           b_d0 + ((r * W_SUB + k * 32) >> 4), idesc, (r | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&tmem_full[buf]);
+          if ((buf ^= 1) == 0) pbuf ^= 1u;
+        }
+        umma_commit(&empty[st]);
+        if (++st == p.stages) { st = 0; ph ^= 1u; }
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int lrow = quarter * 32 + lane;
+    int buf = 0;
+    uint32_t pbuf = 0;
+    for (int row = blockIdx.x; row < p.total_rows; row += gridDim.x) {
+      for (int t = 0; t < p.tiles_per_row; ++t) {
+        const int64_t m = static_cast<int64_t>(row) * p.Wo + t * BM + lrow;
+        mbar_wait(&tmem_full[buf], pbuf);
+        tc_fence_after();
+        const uint32_t t_row = tmem_base + buf * BN + (static_cast<uint32_t>(quarter * 32) << 16);
+#pragma unroll
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld_x16(t_row + c0, v);
+          tmem_ld_wait();
+          float f[16];
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + c0 + j));
+            const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + c0 + j));
+            f[j] = fmaf(__uint_as_float(v[j]), sc.x, sh.x);
+            f[j + 1] = fmaf(__uint_as_float(v[j + 1]), sc.y, sh.y);
+            f[j + 2] = fmaf(__uint_as_float(v[j + 2]), sc.z, sh.z);
+            f[j + 3] = fmaf(__uint_as_float(v[j + 3]), sc.w, sh.w);
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+          }
+          store_bf16x16(p.y + m * BN + c0, f);
+        }
+        tc_fence_before();
+        mbar_arrive(&tmem_empty[buf]);
+        if ((buf ^= 1) == 0) pbuf ^= 1u;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+}  // namespace
+
 // x: zero-bordered (N, H+6, W+8, 4) bf16; w: bf16 [64][256] with k = r*32 + s*4 + c; y: (N, H/2, W/2, 64) bf16.
 // Returns DT_ERR_UNSUPPORTED when the output grid cannot be tiled into 128-pixel boxes.
 int dt_conv_stem(const dt_conv_desc* d, const void* x, const void* w, const float* scale, const float* shift, void* y,
@@ -223,6 +384,32 @@ int dt_conv_stem(const dt_conv_desc* d, const void* x, const void* w, const floa
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     DT_REQUIRE(r == CUDA_SUCCESS, DT_ERR_CUDA, "stem weight tensor map: CUresult %d", static_cast<int>(r));
+  }
+  if (Wo % BM == 0 && !(d->flags & DT_CONV_NO_HALO)) {
+    // row form: the im2col operand is read in place from the raw input rows (no-swizzle descriptors)
+    StemRowParams q;
+    q.Ho = Ho; q.Wo = Wo; q.total_rows = d->N * Ho; q.tiles_per_row = Wo / BM; q.relu = d->relu;
+    q.row_bytes = static_cast<int>(Wp * 8);
+    q.stage_bytes = (ROWS * q.row_bytes + 127) / 128 * 128;
+    q.image_bytes = static_cast<int64_t>(Hp) * Wp * 8;
+    q.stages = (200 * 1024 - W_BYTES) / q.stage_bytes;
+    if (q.stages > ROW_MAX_STAGES) q.stages = ROW_MAX_STAGES;
+    if (q.stages >= 2 && (ROWS * q.row_bytes) % 16 == 0 && ROWS * q.row_bytes < (1 << 20)) {
+      q.x = static_cast<const uint8_t*>(x);
+      q.y = static_cast<__nv_bfloat16*>(y);
+      q.scale = scale; q.shift = shift;
+      const int smem_rows = W_BYTES + q.stages * q.stage_bytes + 1024 + 256;
+      static std::once_flag once_rows;
+      static cudaError_t attr_rows = cudaSuccess;
+      std::call_once(once_rows, [] {
+        attr_rows = cudaFuncSetAttribute(conv_stem_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+      });
+      DT_CUDA(attr_rows);
+      const int grid_rows = q.total_rows < dt_num_sms() ? q.total_rows : dt_num_sms();
+      conv_stem_rows_kernel<<<grid_rows, kThreads, smem_rows, s>>>(tm_b, q);
+      DT_LAUNCH_CHECK();
+      return DT_OK;
+    }
   }
   StemParams p;
   p.Ho = Ho; p.Wo = Wo;

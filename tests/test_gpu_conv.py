@@ -133,9 +133,11 @@ def test_stem_tcgen05_and_fp32():
         assert rel < tol_rel
 
 
-@pytest.mark.parametrize("N,T", [(3, 64), (2, 256), (5, 32)])
+@pytest.mark.parametrize("N,T", [(3, 64), (2, 256), (5, 32), (3, 512), (1, 1024)])
 def test_stem_tma_im2col_padded_input(N, T):
-    """7x7/s2 stem with the im2col operand built by TMA from a zero-bordered frame == the gather path, bit for bit."""
+    """7x7/s2 stem with the im2col operand built by TMA from a zero-bordered frame == the gather path, bit for bit;
+    for output widths that are multiples of 128 (T >= 256) the default is the row form (operand read in place from the
+    raw input rows through no-swizzle descriptors), which must equal the im2col-map kernel (CONV_NO_HALO) bit for bit."""
     g = torch.Generator().manual_seed(6)
     x = torch.randn(N, 3, T, T, generator=g)
     w = torch.randn(64, 3, 7, 7, generator=g) * (2.0 / 147) ** 0.5
@@ -152,6 +154,9 @@ def test_stem_tma_im2col_padded_input(N, T):
     err, rel = report(f"stem TMA-im2col N={N} T={T}", to_nchw(y_t), ref)
     assert rel < 1e-2
     assert torch.equal(y_t, y_g)
+    y_m = ops.conv2d(xpad.to(torch.bfloat16).cuda(), wp, scale.cuda(), shift.cuda(), flags=CONV_X_PAD3 | CONV_NO_HALO, **kw)
+    torch.cuda.synchronize()
+    assert torch.equal(y_t, y_m)
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
