@@ -178,6 +178,70 @@ __global__ void loss_backward_kernel(const float* __restrict__ logits, const int
   }
 }
 
+// Boundary (surface) loss on the logits: L = scale_v * sum over (b, k in idc, pixels) softmax(z)_k * dist_k with
+// scale_v = 1 / (N * |idc| * H * W)  (SurfaceLoss: mean of probs[:, idc] * dist_maps[:, idc], losses.py:250-270).
+//   value pass:    one double partial per block, summed in a fixed order by the caller's tiny reduction
+//   gradient pass: grad_j += scale_g * p_j * (dist_j [j in idc] - S),  S = sum_{k in idc} dist_k * p_k
+template <int K>
+__global__ void boundary_partials_kernel(const float* __restrict__ logits, const float* __restrict__ dist, int64_t HW,
+                                         unsigned idc_mask, double* __restrict__ part) {
+  const int n = blockIdx.y;
+  const float* zl = logits + static_cast<int64_t>(n) * K * HW;
+  const float* dl = dist + static_cast<int64_t>(n) * K * HW;
+  float acc = 0.f;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < HW;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float p[K];
+    softmax_px<K>(zl + i, HW, p);
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+      if ((idc_mask >> k) & 1u) acc += p[k] * __ldg(dl + k * HW + i);
+  }
+  __shared__ double sh[kThreads];
+  sh[threadIdx.x] = static_cast<double>(acc);
+  __syncthreads();
+  for (int o = kThreads / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) part[static_cast<int64_t>(blockIdx.y) * gridDim.x + blockIdx.x] = sh[0];
+}
+
+__global__ void boundary_reduce_kernel(const double* __restrict__ part, int n, double scale, float* __restrict__ out) {
+  __shared__ double sh[kThreads];
+  double a = 0.0;
+  for (int i = threadIdx.x; i < n; i += kThreads) a += part[i];
+  sh[threadIdx.x] = a;
+  __syncthreads();
+  for (int o = kThreads / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = static_cast<float>(sh[0] * scale);
+}
+
+template <int K>
+__global__ void boundary_backward_kernel(const float* __restrict__ logits, const float* __restrict__ dist, int64_t HW,
+                                         unsigned idc_mask, float scale, float* __restrict__ grad) {
+  const int n = blockIdx.y;
+  const float* zl = logits + static_cast<int64_t>(n) * K * HW;
+  const float* dl = dist + static_cast<int64_t>(n) * K * HW;
+  float* gl = grad + static_cast<int64_t>(n) * K * HW;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < HW;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float p[K], d[K];
+    softmax_px<K>(zl + i, HW, p);
+    float S = 0.f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      d[k] = ((idc_mask >> k) & 1u) ? __ldg(dl + k * HW + i) : 0.f;
+      S += d[k] * p[k];
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) gl[k * HW + i] += scale * p[k] * (d[k] - S);
+  }
+}
+
 // ---- probability / one-hot API (the reference's loss callables take softmax output + one-hot) ----
 
 __global__ void one_hot_kernel(const int64_t* __restrict__ labels, int K, int64_t HW, int64_t total,
@@ -384,6 +448,49 @@ int dt_seg_loss_backward(const float* logits, const int64_t* labels, int N, int 
     case 2: loss_backward_kernel<2><<<grid, kThreads, 0, s>>>(logits, labels, HW, coef, focal_scale, upstream, grad_logits); break;
     case 3: loss_backward_kernel<3><<<grid, kThreads, 0, s>>>(logits, labels, HW, coef, focal_scale, upstream, grad_logits); break;
     default: loss_backward_kernel<4><<<grid, kThreads, 0, s>>>(logits, labels, HW, coef, focal_scale, upstream, grad_logits); break;
+  }
+  DT_LAUNCH_CHECK();
+  return DT_OK;
+}
+
+int dt_boundary_loss(const float* logits, const float* dist, int N, int K, int H, int W, unsigned idc_mask,
+                     double* workspace, float* loss_out, dt_stream_t stream) {
+  DT_ARCH_GUARD();
+  DT_REQUIRE(N > 0 && N <= 65535 && H > 0 && W > 0 && K >= 2 && K <= KMAX && idc_mask != 0 && (idc_mask >> K) == 0,
+             DT_ERR_BAD_SHAPE, "dt_boundary_loss: bad shape / class subset");
+  const int64_t HW = static_cast<int64_t>(H) * W;
+  int chunks = static_cast<int>((HW + kThreads * 4 - 1) / (kThreads * 4));
+  if (chunks > 64) chunks = 64;
+  if (chunks < 1) chunks = 1;
+  dim3 grid(chunks, N);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (K) {
+    case 2: boundary_partials_kernel<2><<<grid, kThreads, 0, s>>>(logits, dist, HW, idc_mask, workspace); break;
+    case 3: boundary_partials_kernel<3><<<grid, kThreads, 0, s>>>(logits, dist, HW, idc_mask, workspace); break;
+    default: boundary_partials_kernel<4><<<grid, kThreads, 0, s>>>(logits, dist, HW, idc_mask, workspace); break;
+  }
+  DT_LAUNCH_CHECK();
+  const double cnt = static_cast<double>(N) * __builtin_popcount(idc_mask) * static_cast<double>(HW);
+  boundary_reduce_kernel<<<1, kThreads, 0, s>>>(workspace, chunks * N, 1.0 / cnt, loss_out);
+  DT_LAUNCH_CHECK();
+  return DT_OK;
+}
+
+int dt_boundary_loss_backward(const float* logits, const float* dist, int N, int K, int H, int W, unsigned idc_mask,
+                              float weight, float* grad_logits, dt_stream_t stream) {
+  DT_ARCH_GUARD();
+  DT_REQUIRE(N > 0 && N <= 65535 && H > 0 && W > 0 && K >= 2 && K <= KMAX && idc_mask != 0 && (idc_mask >> K) == 0,
+             DT_ERR_BAD_SHAPE, "dt_boundary_loss_backward: bad shape / class subset");
+  const int64_t HW = static_cast<int64_t>(H) * W;
+  int chunks = static_cast<int>((HW + kThreads * 4 - 1) / (kThreads * 4));
+  if (chunks < 1) chunks = 1;
+  dim3 grid(chunks, N);
+  const float scale = weight / (static_cast<float>(N) * __builtin_popcount(idc_mask) * static_cast<float>(HW));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (K) {
+    case 2: boundary_backward_kernel<2><<<grid, kThreads, 0, s>>>(logits, dist, HW, idc_mask, scale, grad_logits); break;
+    case 3: boundary_backward_kernel<3><<<grid, kThreads, 0, s>>>(logits, dist, HW, idc_mask, scale, grad_logits); break;
+    default: boundary_backward_kernel<4><<<grid, kThreads, 0, s>>>(logits, dist, HW, idc_mask, scale, grad_logits); break;
   }
   DT_LAUNCH_CHECK();
   return DT_OK;

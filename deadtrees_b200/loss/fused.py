@@ -38,20 +38,34 @@ class SegLossTerms:
 
 
 class _SegLossFn(torch.autograd.Function):
-    """total loss of ``SemSegment.calculate_loss`` on the logits; backward = ``dt_seg_loss_backward``."""
+    """total loss of ``SemSegment.calculate_loss`` on the logits; backward = ``dt_seg_loss_backward``
+    (+ ``dt_boundary_loss_backward`` when a boundary term is present)."""
 
     @staticmethod
     def forward(ctx, logits: torch.Tensor, terms: "SegLossTerms"):
         ctx.terms = terms
-        return terms.total_loss.clone()
+        total = terms.total_loss.clone()
+        if terms.boundary is not None:
+            total = total + terms.boundary_weight * terms.boundary
+        return total
 
     @staticmethod
     def backward(ctx, g):
-        grad = ctx.terms.grad_logits(1.0)
+        t = ctx.terms
+        grad = t.grad_logits(1.0)
+        if t.boundary is not None:
+            ops.boundary_loss_backward(t.logits, t.distmap, t.boundary_idc, t.boundary_weight, grad)
         return grad.mul_(g), None
 
 
-def seg_loss(logits: torch.Tensor, labels: torch.Tensor, dice_mode: int, use_focal: bool):
-    """-> (differentiable total loss, SegLossTerms with the individual scalars and metrics)."""
+def seg_loss(logits: torch.Tensor, labels: torch.Tensor, dice_mode: int, use_focal: bool, distmap: torch.Tensor = None,
+             boundary_idc=None, boundary_weight: float = 1.0):
+    """-> (differentiable total loss, SegLossTerms with the individual scalars and metrics).  With ``distmap`` the
+    boundary loss over the classes ``boundary_idc`` is added with ``boundary_weight`` (1, or alpha when ramped)."""
     terms = SegLossTerms(logits.detach(), labels, dice_mode, use_focal)
+    terms.boundary = None
+    if distmap is not None and boundary_idc:
+        terms.distmap = distmap.float().contiguous()
+        terms.boundary_idc, terms.boundary_weight = list(boundary_idc), float(boundary_weight)
+        terms.boundary = ops.boundary_loss(terms.logits, terms.distmap, terms.boundary_idc)
     return _SegLossFn.apply(logits, terms), terms

@@ -226,13 +226,17 @@ class SemSegment(_Base):  # type: ignore[misc]
         """forward (train-mode BatchNorm) + compound loss + metrics, as ``segmodel.py:210-229``; the returned loss is
         differentiable: ``loss.backward()`` runs the CUDA backward pass and fills ``.grad`` of every parameter."""
         img, mask, distmap, _, stats = create_combined_batch(batch)
-        if self.boundary_loss and distmap is not None:
-            raise NotImplementedError("the boundary loss has no backward kernel yet (next tier, SURVEY.md §8f-2)")
         logits = self.model(img)
         dice_mode = 2 if isinstance(self.dice_loss, GeneralizedDiceLoss) else 1
-        loss, terms = fused.seg_loss(logits, mask, dice_mode, self.focal_loss is not None)
+        use_bd = bool(self.boundary_loss) and distmap is not None
+        loss, terms = fused.seg_loss(logits, mask, dice_mode, self.focal_loss is not None,
+                                     distmap=distmap if use_bd else None,
+                                     boundary_idc=self.boundary_loss.idc if use_bd else None,
+                                     boundary_weight=self.alpha if self.boundary_loss_ramped else 1.0)
         terms.check_labels()  # class2one_hot's assert (losses.py:129); also the host sync the reference has there
         self.log("train/dice_loss", terms.dice_loss, on_step=False, on_epoch=True)
+        if use_bd:
+            self.log("train/boundary_loss", terms.boundary, on_step=False, on_epoch=True)
         if self.focal_loss:
             self.log("train/focal_loss", terms.focal_loss, on_step=False, on_epoch=True)
         self.log("train/total_loss", loss.detach(), on_step=False, on_epoch=True)

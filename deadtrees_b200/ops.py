@@ -263,6 +263,39 @@ def seg_loss_backward(logits: torch.Tensor, labels: torch.Tensor, coef: torch.Te
     return grad
 
 
+def _idc_mask(idc, K: int) -> int:
+    m = 0
+    for k in idc:
+        if not 0 <= int(k) < K:
+            raise ValueError(f"class {k} outside [0, {K})")
+        m |= 1 << int(k)
+    return m
+
+
+def boundary_loss(logits: torch.Tensor, dist: torch.Tensor, idc) -> torch.Tensor:
+    """mean over (b, k in idc, h, w) of softmax(logits)_k * dist_k -> 0-dim fp32 tensor."""
+    logits, dist = _cuda(logits, "logits"), _cuda(dist, "dist")
+    if dist.dtype != torch.float32:
+        dist = dist.float()
+    N, K, H, W = logits.shape
+    if tuple(dist.shape) != (N, K, H, W):
+        raise ValueError(f"distance maps {tuple(dist.shape)} do not match the logits {tuple(logits.shape)}")
+    ws = torch.empty(64 * N, dtype=torch.float64, device=logits.device)
+    out = torch.empty((), dtype=torch.float32, device=logits.device)
+    check(load().dt_boundary_loss(logits.data_ptr(), dist.data_ptr(), N, K, H, W, _idc_mask(idc, K), ws.data_ptr(),
+                                  out.data_ptr(), stream_ptr()))
+    return out
+
+
+def boundary_loss_backward(logits: torch.Tensor, dist: torch.Tensor, idc, weight: float, grad_logits: torch.Tensor) -> None:
+    """grad_logits += weight * d(boundary_loss)/d(logits)"""
+    if dist.dtype != torch.float32:
+        dist = dist.float()
+    N, K, H, W = logits.shape
+    check(load().dt_boundary_loss_backward(logits.data_ptr(), dist.contiguous().data_ptr(), N, K, H, W, _idc_mask(idc, K),
+                                           float(weight), grad_logits.data_ptr(), stream_ptr()))
+
+
 def class2one_hot(labels: torch.Tensor, K: int):
     """-> (int32 one-hot (N, K, H, W), bad_label int32 (1,))."""
     labels = _cuda(labels, "labels")

@@ -22,7 +22,7 @@ from .optim import FusedAdam
 class GraphedTrainStep:
     def __init__(self, seg, optimizer: FusedAdam, batch: int, tile: int):
         if seg.boundary_loss is not None:
-            raise NotImplementedError("the boundary loss has no backward kernel yet (next tier, SURVEY.md 8f-2)")
+            raise NotImplementedError("the graphed step takes (img, mask) batches: run boundary-loss training through training_step()")
         self.seg, self.opt = seg, optimizer
         self.engine = seg.model.train_engine()
         if optimizer._flat is None:

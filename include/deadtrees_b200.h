@@ -185,6 +185,16 @@ int dt_seg_loss_finalize(const double* sums, const int64_t* counts, int N, int K
 int dt_seg_loss_backward(const float* logits, const int64_t* labels, int N, int K, int H, int W, const float* coef,
                          const float* focal_scale, float upstream, float* grad_logits, dt_stream_t stream);
 
+/* Boundary (surface) loss on the logits (SurfaceLoss / BoundaryLoss, deadtrees/loss/losses.py:250-270, added to the total in
+ * SemSegment.calculate_loss, segmodel.py:188-191): loss = mean over (b, k in idc, h, w) of softmax(logits)_k * dist_k.
+ * logits, dist: (N, K, H, W) fp32; idc_mask: bit k set = class k in idc; workspace: 64 * N doubles.
+ * dt_boundary_loss_backward ADDS weight * d(loss)/d(logits) to grad_logits (weight = upstream gradient times the ramp
+ * factor alpha of BOUNDARY-RAMPED, segmodel.py:157-160). */
+int dt_boundary_loss(const float* logits, const float* dist, int N, int K, int H, int W, unsigned idc_mask,
+                     double* workspace, float* loss_out, dt_stream_t stream);
+int dt_boundary_loss_backward(const float* logits, const float* dist, int N, int K, int H, int W, unsigned idc_mask,
+                              float weight, float* grad_logits, dt_stream_t stream);
+
 /* The reference's loss callables take softmax probabilities and an int32 one-hot target
  * (segmodel.py:215-216); these three entry points serve that API:
  * dt_class2one_hot: losses.py:124-141 (int32 scatter; bad_label flag = its label-range assert)

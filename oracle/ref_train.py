@@ -21,7 +21,8 @@ from . import ref_losses
 
 
 def train_step(model: torch.nn.Module, img: torch.Tensor, mask: torch.Tensor, losses: Sequence[str] = ("DICE", "FOCAL"),
-               lr: float = 3e-4, clip: float = 0.5, optimizer=None) -> Dict[str, object]:
+               lr: float = 3e-4, clip: float = 0.5, optimizer=None, distmap: torch.Tensor = None,
+               alpha: float = 0.01) -> Dict[str, object]:
     """runs forward + loss + backward (+ clip + Adam when `optimizer` is given or lr > 0) on `model` in place."""
     model.train()
     for p in model.parameters():
@@ -30,7 +31,7 @@ def train_step(model: torch.nn.Module, img: torch.Tensor, mask: torch.Tensor, lo
     K = logits.shape[1]
     onehot = ref_losses.class2one_hot(mask, K)
     probs = logits.softmax(dim=1)
-    terms = ref_losses.calculate_loss(probs, onehot, list(losses))
+    terms = ref_losses.calculate_loss(probs, onehot, list(losses), distmap=distmap, alpha=alpha)
     loss = terms["total_loss"]
     loss.backward()
     grads = {n: p.grad.detach().clone() for n, p in model.named_parameters()}

@@ -486,6 +486,36 @@ def test_flat_adam_path_equals_per_parameter_path():
     assert out.shape == (n, 3, T, T) and torch.isfinite(out).all()
 
 
+@pytest.mark.parametrize("losses,ramped", [(["DICE", "BOUNDARY", "FOCAL"], False), (["GDICE", "BOUNDARY-RAMPED", "FOCAL"], True)])
+def test_training_step_with_boundary_loss(losses, ramped):
+    """the reference's default loss family adds the boundary (surface) loss on the dataloader's distance maps
+    (losses.py:250-270, segmodel.py:188-191): fp32 check mode, loss terms and gradients against oracle autograd."""
+    cin, n, T = 4, 2, 64
+    oracle = oracle_model(cin, 3)
+    img, mask = _batch(n, cin, T, 3)
+    g = torch.Generator().manual_seed(5)
+    distmap = torch.randn(n, 3, T, T, generator=g) * 4.0          # signed distances (one_hot2dist), any real values
+    ref_model = copy.deepcopy(oracle).double()
+    ref = ref_train.train_step(ref_model, img.double(), mask, losses=losses, lr=0.0, clip=0.0, distmap=distmap.double(),
+                               alpha=0.01)
+    net = dict(NETWORK, in_channels=cin, precision="fp32", losses=losses)
+    seg = SemSegment(net, TRAINING)
+    seg.model.load_state_dict(oracle.state_dict())
+    seg.cuda().train()
+    batch = {"main": (img.cuda(), mask.cuda(), distmap.cuda(), torch.zeros(n), [{"file": f"t{i}"} for i in range(n)])}
+    loss = seg.training_step(batch, 0)
+    loss.backward()
+    torch.cuda.synchronize()
+    bd = float(seg.logged["train/boundary_loss"])
+    print(f"[boundary] loss {float(loss.detach()):.6f} vs {ref['loss']:.6f}; boundary term {bd:.6f} vs {ref['terms']['boundary_loss']:.6f}")
+    assert abs(bd - ref["terms"]["boundary_loss"]) < 1e-5 * max(1.0, abs(ref["terms"]["boundary_loss"]))
+    assert abs(float(loss.detach()) - ref["loss"]) < 1e-4
+    errs = _grad_errors(seg.model.named_parameters(), ref["grads"])
+    worst = max(errs.items(), key=lambda kv: kv[1][0])
+    print(f"[boundary] worst relative L2 gradient error {worst[1][0]:.3e} ({worst[0]})")
+    assert worst[1][0] < 2e-2 and min(v[1] for v in errs.values()) > 0.999
+
+
 def test_graphed_training_step_equals_eager():
     """the whole step replayed from one CUDA graph (deadtrees_b200/train_graph.py) against the same step launched kernel
     by kernel: three steps, the graph fed once through __call__ and twice through the prefetch pipeline.  The losses
