@@ -180,6 +180,9 @@ class MosaicInference:
         step = T - ov
         piped_in = host_src is not None
         piped_out = host_out is not None and halo_hook is None
+        # single GPU: the mask is stitched band by band as soon as the tile rows of a band are done - the logits a band
+        # needs were written by the last batches and are still in L2 (a batch of 135 tiles holds 53 MB of logits)
+        banded = halo_hook is None
         if (piped_in or host_out is not None) and layout != "hwc":
             raise ValueError("the host pipeline takes interleaved (H, W, C) mosaics")
         main = torch.cuda.current_stream()
@@ -210,18 +213,19 @@ class MosaicInference:
             else:
                 lo = t0 - (r0 - halo) * gx
                 eng.forward(xb, logits_nhwc_out=logits[lo: lo + n])
-            if piped_out:
+            if banded:
                 rows_done = (t0 + n) // gx           # complete tile rows so far: mask rows below rows_done * step are final
                 y_end = y_own1 if t0 + n >= r1 * gx else min(y_own1, rows_done * step)
                 if y_end > stitched:
                     if ov > 0:
                         ops.stitch_blend_argmax(logits, ov, (gy, gx), self.win, mask, row0=stitched, nrows=y_end - stitched,
                                                 ty_base=r0 - halo)
-                    cs_out.wait_stream(main)
-                    with torch.cuda.stream(cs_out):
-                        host_out[stitched:y_end].copy_(mask[stitched:y_end], non_blocking=True)
+                    if piped_out:
+                        cs_out.wait_stream(main)
+                        with torch.cuda.stream(cs_out):
+                            host_out[stitched:y_end].copy_(mask[stitched:y_end], non_blocking=True)
                     stitched = y_end
-        if ov > 0 and not piped_out:
+        if ov > 0 and not banded:
             if halo_hook is not None:
                 halo_hook(logits, gx, halo)  # multi-GPU: exchange boundary logits rows with the neighbours
             ops.stitch_blend_argmax(logits, ov, (gy, gx), self.win, mask, row0=y_own0, nrows=y_own1 - y_own0, ty_base=r0 - halo)

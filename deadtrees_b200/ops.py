@@ -155,8 +155,9 @@ def stitch_blend_argmax(logits: torch.Tensor, overlap: int, grid: Tuple[int, int
     _, T, _, K = logits.shape
     H, W = mosaic_mask.shape
     nrows = H - row0 if nrows is None else nrows
-    # algorithmic bytes: every logit of the shard once + 1 B per output pixel
-    with _Timed("stitch", float(logits.numel()) * logits.element_size() + float(nrows) * W):
+    # algorithmic bytes of THIS call (the mask may be stitched band by band): K logits in + 1 B out per mosaic pixel of the
+    # rows written - a lower bound of SURVEY.md §8d's "every logit once" (pixels under an overlap read 2 or 4 tiles)
+    with _Timed("stitch", float(nrows) * W * (K * logits.element_size() + 1)):
         check(load().dt_stitch_blend_argmax(logits.data_ptr(), _dt(logits), K, T, overlap, grid[0], grid[1],
                                             ty_base, win.data_ptr(), mosaic_mask.data_ptr(), ptr(blended), H, W,
                                             row0, nrows, stream_ptr()))
