@@ -502,12 +502,12 @@ def main_train(a):
     stats = [{"file": f"r{rank}t{i}"} for i in range(B)]
     loss_h = torch.zeros((), pin_memory=True)
 
-    use_graph = world == 1 and not a.no_graph
+    use_graph = not a.no_graph
     launches_per_replay = 0
     if use_graph:
         from deadtrees_b200.train_graph import GraphedTrainStep
         l0 = ops.LAUNCHES
-        gstep = GraphedTrainStep(seg, opt, B, T)
+        gstep = GraphedTrainStep(seg, opt, B, T)              # world > 1: the NCCL bucket all-reduces are graph nodes too
         launches_per_replay = (ops.LAUNCHES - l0) // 3        # two warm-up passes + the captured one
         gstep.img.copy_(img_d)
         gstep.mask.copy_(mask_d)
@@ -641,8 +641,19 @@ def main_train(a):
                                "sample": f"one oracle training step on 8 RGB+NIR tiles of {T}x{T} (torch CPU autograd fp32 + reference "
                                          f"loss terms + clip + Adam), best of 2 after 1 warm-up"}
     if rank == 0:
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
     if world > 1:
+        # a CUDA graph that holds NCCL nodes must be gone before the communicator is torn down (destroy_process_group
+        # waited forever with the graph alive); leave the process without the teardown once every rank is done
+        torch.cuda.synchronize()
+        dist.barrier()
+        if use_graph:
+            gstep.graph.reset()
+            del gstep
+            torch.cuda.synchronize()
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
         dist.destroy_process_group()
 
 

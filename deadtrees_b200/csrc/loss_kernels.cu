@@ -347,7 +347,9 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 // the step is skipped entirely (state untouched) when *loss is not finite - SemSegment.training_step returning None.
 __global__ void adam_prepare_kernel(float* __restrict__ state, const float* __restrict__ loss, const double* __restrict__ sumsq,
                                     float b1, float b2, float max_norm, float* __restrict__ scal) {
-  const bool apply = loss == nullptr || isfinite(*loss);
+  // skipped when the loss is not finite; with data parallelism the decision must be the same on every rank: a rank with a
+  // non-finite loss contributes non-finite gradients, the all-reduced gradient norm is then non-finite everywhere
+  const bool apply = (loss == nullptr || isfinite(*loss)) && (max_norm <= 0.f || isfinite(*sumsq));
   float step = state[0];
   if (apply) { step += 1.f; state[0] = step; }
   const double bc1 = 1.0 - pow(static_cast<double>(b1), static_cast<double>(step));

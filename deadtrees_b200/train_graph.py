@@ -27,8 +27,8 @@ class GraphedTrainStep:
         self.engine = seg.model.train_engine()
         if optimizer._flat is None:
             optimizer.attach_engine(self.engine)
-        if self.engine.reducer.world != 1:
-            raise NotImplementedError("graph capture of the NCCL gradient all-reduce is not enabled; use the eager step")
+        # data parallel: the bucketed NCCL all-reduces run on the reducer's side stream, which forks from and joins the
+        # capturing stream through events, so they become nodes of the same graph (every rank captures the same sequence)
         dev = self.engine.device
         self.dice_mode = 2 if isinstance(seg.dice_loss, GeneralizedDiceLoss) else 1
         self.use_focal = seg.focal_loss is not None
