@@ -66,6 +66,7 @@ _SIGNATURES = {
     "dt_bn_train_stats": ([_p, _i64, _i, _i, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _p, _p], C.c_int),
     "dt_bn_apply": ([_p, _i64, _i, _i, _p, _p, _p, _i, _p, _p], C.c_int),
     "dt_bn_train_bwd": ([_p, _p, _p, _i64, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p], C.c_int),
+    "dt_bn_train_bwd_relu": ([_p, _p, _i64, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p], C.c_int),
     "dt_add": ([_p, _p, _i64, _i, _p, _p], C.c_int),
     "dt_maxpool3x3s2_bwd": ([_p, _p, _p, _i, _i, _i, _i, _i, _p, _p], C.c_int),
     "dt_maxpool3x3s2_idx": ([_p, _i, _i, _i, _i, _i, _p, _p, _p], C.c_int),

@@ -59,18 +59,26 @@ inline int grid_for(int64_t work, int per_sm = 8) {
 // and summed in a fixed order by the finalize kernels (deterministic, no atomics).
 template <typename T, int MODE>
 __global__ void channel_reduce_kernel(const T* __restrict__ y, const T* __restrict__ g, const T* __restrict__ a,
-                                      const float* __restrict__ mean, const float* __restrict__ invstd, int64_t M, int C,
+                                      const float* __restrict__ mean, const float* __restrict__ invstd,
+                                      const float* __restrict__ fscale, const float* __restrict__ fshift, int64_t M, int C,
                                       float* __restrict__ part) {
   constexpr int VN = VecOf<T>::N;
   const int V = C / VN;                    // vectors per pixel (divides kThreads)
   const int lanes = kThreads / V;
   const int v = threadIdx.x % V, lane = threadIdx.x / V;
-  float s[VN], q[VN], mu[VN], is[VN];
+  float s[VN], q[VN], mu[VN], is[VN], fsc[VN], fsh[VN];
 #pragma unroll
-  for (int j = 0; j < VN; ++j) { s[j] = q[j] = 0.f; mu[j] = 0.f; is[j] = 1.f; }
+  for (int j = 0; j < VN; ++j) { s[j] = q[j] = 0.f; mu[j] = 0.f; is[j] = 1.f; fsc[j] = 0.f; fsh[j] = 1.f; }
+  // ReLU mask recomputed from y when the forward had no residual: a > 0  <=>  fma(y, scale, shift) > 0 (the value
+  // bn_apply_kernel clamped), so the activation tensor is not read again
+  const bool mask_y = MODE == 1 && a == nullptr && fshift != nullptr;
   if (MODE == 1) {
 #pragma unroll
     for (int j = 0; j < VN; ++j) { mu[j] = mean[v * VN + j]; is[j] = invstd[v * VN + j]; }
+    if (mask_y) {
+#pragma unroll
+      for (int j = 0; j < VN; ++j) { fsc[j] = fscale[v * VN + j]; fsh[j] = fshift[v * VN + j]; }
+    }
   }
   for (int64_t p = static_cast<int64_t>(blockIdx.x) * lanes + lane; p < M; p += static_cast<int64_t>(gridDim.x) * lanes) {
     float fy[VN];
@@ -84,7 +92,8 @@ __global__ void channel_reduce_kernel(const T* __restrict__ y, const T* __restri
       if (a) load_vec<T>(a + p * C + v * VN, fa);
 #pragma unroll
       for (int j = 0; j < VN; ++j) {
-        const float gz = (a == nullptr || fa[j] > 0.f) ? fg[j] : 0.f;
+        const bool on = mask_y ? fmaf(fy[j], fsc[j], fsh[j]) > 0.f : (a == nullptr || fa[j] > 0.f);
+        const float gz = on ? fg[j] : 0.f;
         s[j] += gz;
         q[j] = fmaf(gz, (fy[j] - mu[j]) * is[j], q[j]);
       }
@@ -192,8 +201,8 @@ template <typename T>
 __global__ void bn_bwd_apply_kernel(const T* __restrict__ g, const T* __restrict__ a, const T* __restrict__ y,
                                     const float* __restrict__ mean, const float* __restrict__ invstd,
                                     const float* __restrict__ scale, const float* __restrict__ c1,
-                                    const float* __restrict__ c2, int64_t nvec, int C, T* __restrict__ gy,
-                                    T* __restrict__ gz_out) {
+                                    const float* __restrict__ c2, const float* __restrict__ fshift, int64_t nvec, int C,
+                                    T* __restrict__ gy, T* __restrict__ gz_out) {
   constexpr int VN = VecOf<T>::N;
   const int V = C / VN;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < nvec;
@@ -205,7 +214,9 @@ __global__ void bn_bwd_apply_kernel(const T* __restrict__ g, const T* __restrict
     load_vec<T>(y + i * VN, fy);
 #pragma unroll
     for (int j = 0; j < VN; ++j) {
-      const float gz = (a == nullptr || fa[j] > 0.f) ? fg[j] : 0.f;
+      const bool on = (a == nullptr && fshift != nullptr) ? fmaf(fy[j], __ldg(scale + c0 + j), __ldg(fshift + c0 + j)) > 0.f
+                                                           : (a == nullptr || fa[j] > 0.f);
+      const float gz = on ? fg[j] : 0.f;
       fg[j] = gz;
       const float yhat = (fy[j] - __ldg(mean + c0 + j)) * __ldg(invstd + c0 + j);
       o[j] = __ldg(scale + c0 + j) * (gz - __ldg(c1 + c0 + j) - yhat * __ldg(c2 + c0 + j));
@@ -661,8 +672,8 @@ int dt_bn_train_stats(const void* y, int64_t M, int C, int dtype, const float* g
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int nb = reduce_blocks(M, C, dtype == DT_BF16 ? 8 : 4);
   DT_DTYPE_SWITCH(dtype,
-      (channel_reduce_kernel<float, 0><<<nb, kThreads, 0, s>>>(static_cast<const float*>(y), nullptr, nullptr, nullptr, nullptr, M, C, workspace)),
-      (channel_reduce_kernel<__nv_bfloat16, 0><<<nb, kThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(y), nullptr, nullptr, nullptr, nullptr, M, C, workspace)));
+      (channel_reduce_kernel<float, 0><<<nb, kThreads, 0, s>>>(static_cast<const float*>(y), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, M, C, workspace)),
+      (channel_reduce_kernel<__nv_bfloat16, 0><<<nb, kThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(y), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, M, C, workspace)));
   DT_LAUNCH_CHECK();
   bn_finalize_kernel<<<C, kFinThreads, 0, s>>>(workspace, nb, C, static_cast<double>(M), gamma, beta, eps, momentum,
                                                      running_mean, running_var, scale, shift, mean, invstd);
@@ -684,9 +695,9 @@ int dt_bn_apply(const void* y, int64_t M, int C, int dtype, const float* scale, 
   return DT_OK;
 }
 
-int dt_bn_train_bwd(const void* g, const void* a, const void* y, int64_t M, int C, int dtype, const float* mean,
-                    const float* invstd, const float* scale, float* dgamma, float* dbeta, void* gy, void* gz_out,
-                    float* workspace, dt_stream_t stream) {
+static int bn_train_bwd_impl(const void* g, const void* a, const void* y, int64_t M, int C, int dtype, const float* mean,
+                             const float* invstd, const float* scale, const float* fshift, float* dgamma, float* dbeta,
+                             void* gy, void* gz_out, float* workspace, dt_stream_t stream) {
   DT_ARCH_GUARD();
   DT_REQUIRE(M > 0 && (dtype == DT_F32 || dtype == DT_BF16) && vec_ok(C, dtype), DT_ERR_BAD_SHAPE,
              "dt_bn_train_bwd: M=%lld C=%d dtype=%d", static_cast<long long>(M), C, dtype);
@@ -697,16 +708,29 @@ int dt_bn_train_bwd(const void* g, const void* a, const void* y, int64_t M, int 
   float* c2 = c1 + C;
   const int64_t nvec = M * C / vn;
   DT_DTYPE_SWITCH(dtype,
-      (channel_reduce_kernel<float, 1><<<nb, kThreads, 0, s>>>(static_cast<const float*>(y), static_cast<const float*>(g), static_cast<const float*>(a), mean, invstd, M, C, workspace)),
-      (channel_reduce_kernel<__nv_bfloat16, 1><<<nb, kThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(y), static_cast<const __nv_bfloat16*>(g), static_cast<const __nv_bfloat16*>(a), mean, invstd, M, C, workspace)));
+      (channel_reduce_kernel<float, 1><<<nb, kThreads, 0, s>>>(static_cast<const float*>(y), static_cast<const float*>(g), static_cast<const float*>(a), mean, invstd, scale, fshift, M, C, workspace)),
+      (channel_reduce_kernel<__nv_bfloat16, 1><<<nb, kThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(y), static_cast<const __nv_bfloat16*>(g), static_cast<const __nv_bfloat16*>(a), mean, invstd, scale, fshift, M, C, workspace)));
   DT_LAUNCH_CHECK();
   bn_bwd_finalize_kernel<<<C, kFinThreads, 0, s>>>(workspace, nb, C, static_cast<double>(M), dgamma, dbeta, c1, c2);
   DT_LAUNCH_CHECK();
   DT_DTYPE_SWITCH(dtype,
-      (bn_bwd_apply_kernel<float><<<grid_for(nvec), kThreads, 0, s>>>(static_cast<const float*>(g), static_cast<const float*>(a), static_cast<const float*>(y), mean, invstd, scale, c1, c2, nvec, C, static_cast<float*>(gy), static_cast<float*>(gz_out))),
-      (bn_bwd_apply_kernel<__nv_bfloat16><<<grid_for(nvec), kThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(g), static_cast<const __nv_bfloat16*>(a), static_cast<const __nv_bfloat16*>(y), mean, invstd, scale, c1, c2, nvec, C, static_cast<__nv_bfloat16*>(gy), static_cast<__nv_bfloat16*>(gz_out))));
+      (bn_bwd_apply_kernel<float><<<grid_for(nvec), kThreads, 0, s>>>(static_cast<const float*>(g), static_cast<const float*>(a), static_cast<const float*>(y), mean, invstd, scale, c1, c2, fshift, nvec, C, static_cast<float*>(gy), static_cast<float*>(gz_out))),
+      (bn_bwd_apply_kernel<__nv_bfloat16><<<grid_for(nvec), kThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(g), static_cast<const __nv_bfloat16*>(a), static_cast<const __nv_bfloat16*>(y), mean, invstd, scale, c1, c2, fshift, nvec, C, static_cast<__nv_bfloat16*>(gy), static_cast<__nv_bfloat16*>(gz_out))));
   DT_LAUNCH_CHECK();
   return DT_OK;
+}
+
+int dt_bn_train_bwd(const void* g, const void* a, const void* y, int64_t M, int C, int dtype, const float* mean,
+                    const float* invstd, const float* scale, float* dgamma, float* dbeta, void* gy, void* gz_out,
+                    float* workspace, dt_stream_t stream) {
+  return bn_train_bwd_impl(g, a, y, M, C, dtype, mean, invstd, scale, nullptr, dgamma, dbeta, gy, gz_out, workspace, stream);
+}
+
+int dt_bn_train_bwd_relu(const void* g, const void* y, int64_t M, int C, int dtype, const float* mean, const float* invstd,
+                         const float* scale, const float* shift, float* dgamma, float* dbeta, void* gy, void* gz_out,
+                         float* workspace, dt_stream_t stream) {
+  DT_REQUIRE(shift != nullptr, DT_ERR_BAD_SHAPE, "dt_bn_train_bwd_relu: the forward shift vector is required");
+  return bn_train_bwd_impl(g, nullptr, y, M, C, dtype, mean, invstd, scale, shift, dgamma, dbeta, gy, gz_out, workspace, stream);
 }
 
 int dt_add(const void* a, const void* b, int64_t n, int dtype, void* out, dt_stream_t stream) {

@@ -390,8 +390,9 @@ def bn_apply(y: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, residual
 
 def bn_train_bwd(g: torch.Tensor, a: Optional[torch.Tensor], y: torch.Tensor, mean: torch.Tensor, invstd: torch.Tensor,
                  scale: torch.Tensor, want_gz: bool = False, dgamma: Optional[torch.Tensor] = None,
-                 dbeta: Optional[torch.Tensor] = None):
-    """-> (gy, gz or None, dgamma, dbeta)."""
+                 dbeta: Optional[torch.Tensor] = None, relu_shift: Optional[torch.Tensor] = None):
+    """-> (gy, gz or None, dgamma, dbeta).  ``relu_shift`` (with ``a=None``): the layer was relu(y*scale + shift) without a
+    residual - the ReLU mask is recomputed from y instead of reading the activation."""
     Cc = y.shape[-1]
     gy = torch.empty_like(y)
     gz = torch.empty_like(y) if want_gz else None
@@ -399,6 +400,14 @@ def bn_train_bwd(g: torch.Tensor, a: Optional[torch.Tensor], y: torch.Tensor, me
         dgamma = torch.empty(Cc, dtype=torch.float32, device=y.device)
     if dbeta is None:
         dbeta = torch.empty(Cc, dtype=torch.float32, device=y.device)
+    if relu_shift is not None:
+        if a is not None:
+            raise ValueError("relu_shift replaces the activation tensor: pass a=None")
+        check(load().dt_bn_train_bwd_relu(g.data_ptr(), y.data_ptr(), y.numel() // Cc, Cc, _dt(y), mean.data_ptr(),
+                                          invstd.data_ptr(), scale.data_ptr(), relu_shift.data_ptr(), dgamma.data_ptr(),
+                                          dbeta.data_ptr(), gy.data_ptr(), ptr(gz), _reduce_ws(y.device).data_ptr(),
+                                          stream_ptr()))
+        return gy, gz, dgamma, dbeta
     check(load().dt_bn_train_bwd(g.data_ptr(), ptr(a), y.data_ptr(), y.numel() // Cc, Cc, _dt(y), mean.data_ptr(),
                                  invstd.data_ptr(), scale.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(),
                                  gy.data_ptr(), ptr(gz), _reduce_ws(y.device).data_ptr(), stream_ptr()))

@@ -230,6 +230,11 @@ int dt_bn_apply(const void* y, int64_t M, int C, int dtype, const float* scale, 
 int dt_bn_train_bwd(const void* g, const void* a, const void* y, int64_t M, int C, int dtype, const float* mean,
                     const float* invstd, const float* scale, float* dgamma, float* dbeta, void* gy, void* gz_out,
                     float* workspace, dt_stream_t stream);
+/* dt_bn_train_bwd for a layer whose forward was relu(y*scale + shift) WITHOUT a residual: the ReLU mask is recomputed from
+ * y (a > 0 <=> fma(y, scale, shift) > 0, the value dt_bn_apply clamped), so the activation tensor is not read. */
+int dt_bn_train_bwd_relu(const void* g, const void* y, int64_t M, int C, int dtype, const float* mean, const float* invstd,
+                         const float* scale, const float* shift, float* dgamma, float* dbeta, void* gy, void* gz_out,
+                         float* workspace, dt_stream_t stream);
 /* out = a + b over n elements (gradient merges) */
 int dt_add(const void* a, const void* b, int64_t n, int dtype, void* out, dt_stream_t stream);
 /* MaxPool2d(3, 2, 1) backward: gradient goes to the FIRST maximum of each window (ATen semantics);

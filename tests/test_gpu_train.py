@@ -66,6 +66,12 @@ def test_bn_train_forward_backward(dtype, C, relu, res):
     assert report("bn dbeta", dbeta.cpu(), beta.grad)[1] < (1e-4 if dtype == torch.float32 else 2e-2)
     if res:
         assert report("bn gz", nchw(gz), r.grad)[1] < tol
+    if relu and not res:
+        # relu(bn(y)) without a residual: the mask recomputed from y (no read of the activation) gives the same bits
+        gy2, gz2, dgamma2, dbeta2 = ops.bn_train_bwd(nhwc(gout, dtype), None, yd, mean, invstd, scale, want_gz=True,
+                                                     relu_shift=shift)
+        torch.cuda.synchronize()
+        assert torch.equal(gy2, gy) and torch.equal(gz2, gz) and torch.equal(dgamma2, dgamma) and torch.equal(dbeta2, dbeta)
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
