@@ -369,12 +369,13 @@ def main_b200(a):
                                "flops_per_tile": conv_flops_per_tile(T, 3, 3), "peak_source": pk["source"]}
             tr = ncu_conv_traffic()
             if tr is not None and T == 256:
-                out["roofline"]["traffic"] = tr[0] / tr[2]
+                bt = min(a.batch_tiles, max((r1 - r0) * gx, 1))
+                out["roofline"]["traffic"] = tr[0] / tr[1] * bt / tr[2]
                 out["roofline"]["traffic_source"] = (
                     f"ncu --set full capture of the {tr[2]} conv launches of one {tr[1]}-tile batch "
                     f"(profiles/r01_convs_ncu_full_v4.txt): {tr[0] / 1e9:.3f} GB DRAM read + write per batch = "
-                    f"{tr[0] / tr[1] / 1e6:.1f} MB per tile, averaged per launch here; bf16 activations in + out of "
-                    f"all convs, unfused: 44.6 MB per tile")
+                    f"{tr[0] / tr[1] / 1e6:.1f} MB per tile; scaled to this run's {bt}-tile batches and averaged per "
+                    f"launch; bf16 activations in + out of all convs, unfused: 44.6 MB per tile")
         hb = {}
         if tg > 0:
             hb["gather_normalize"] = {"achieved": wg / tg / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
