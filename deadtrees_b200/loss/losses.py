@@ -31,6 +31,28 @@ def class2one_hot(seg: Tensor, K: int) -> Tensor:
     return res
 
 
+def one_hot2dist(seg, resolution=None, dtype=None):
+    """signed distance maps of the boundary loss, drop-in for ``one_hot2dist`` (``deadtrees/loss/losses.py:159-178``):
+    ``seg`` one-hot ``(K, H, W)`` ndarray -> ndarray of ``seg``'s dtype (or ``dtype``).  Computed on the device
+    (``dt_one_hot2dist``, exact Euclidean distance transform); as in the reference the float64 expression is truncated
+    towards zero when the result dtype is an integer type (the dataloader passes the int32 one-hot,
+    ``deadtrees/data/deadtreedata.py:182-185``).  Only unit pixel spacing is implemented."""
+    import numpy as np
+    require_device()
+    seg = np.asarray(seg)
+    if resolution is not None and any(float(r) != 1.0 for r in resolution):
+        raise NotImplementedError("one_hot2dist: only resolution None / [1, 1] (the dataloader's) is implemented")
+    if seg.ndim != 3:
+        raise ValueError("one_hot2dist expects a one-hot (K, H, W) array")
+    onehot = seg.astype(bool)
+    assert (onehot.sum(axis=0) == 1).all() and ((seg == 0) | (seg == 1)).all(), "one_hot2dist: seg is not one-hot"
+    K = seg.shape[0]
+    res_dtype = np.dtype(seg.dtype if dtype is None else dtype)
+    labels = torch.from_numpy(onehot.argmax(axis=0).astype(np.int64))[None].cuda()
+    dist = ops.one_hot2dist(labels, K, truncate=np.issubdtype(res_dtype, np.integer))[0]
+    return dist.cpu().numpy().astype(res_dtype)
+
+
 class DiceLoss:
     def __init__(self, **kwargs):
         self.idc: List[int] = kwargs["idc"]

@@ -273,6 +273,22 @@ def _idc_mask(idc, K: int) -> int:
     return m
 
 
+def one_hot2dist(labels: torch.Tensor, K: int, truncate: bool = True) -> torch.Tensor:
+    """(N, H, W) int64 labels -> (N, K, H, W) fp32 signed distance maps of the boundary loss (the dataloader's
+    one_hot2dist per sample); ``truncate``: integer truncation of the reference's int32 path."""
+    labels = _cuda(labels, "labels")
+    if labels.dtype != torch.int64:
+        labels = labels.long()
+    labels = labels.contiguous()
+    N, H, W = labels.shape
+    lib = load()
+    need = lib.dt_one_hot2dist_workspace(N, K, H, W)
+    ws = torch.empty((need + 3) // 4, dtype=torch.int32, device=labels.device)
+    out = torch.empty((N, K, H, W), dtype=torch.float32, device=labels.device)
+    check(lib.dt_one_hot2dist(labels.data_ptr(), N, K, H, W, int(truncate), out.data_ptr(), ws.data_ptr(), need, stream_ptr()))
+    return out
+
+
 def boundary_loss(logits: torch.Tensor, dist: torch.Tensor, idc) -> torch.Tensor:
     """mean over (b, k in idc, h, w) of softmax(logits)_k * dist_k -> 0-dim fp32 tensor."""
     logits, dist = _cuda(logits, "logits"), _cuda(dist, "dist")

@@ -185,6 +185,16 @@ int dt_seg_loss_finalize(const double* sums, const int64_t* counts, int N, int K
 int dt_seg_loss_backward(const float* logits, const int64_t* labels, int N, int K, int H, int W, const float* coef,
                          const float* focal_scale, float upstream, float* grad_logits, dt_stream_t stream);
 
+/* The dataloader's signed distance maps for the boundary loss (one_hot2dist, deadtrees/loss/losses.py:159-178, called at
+ * deadtrees/data/deadtreedata.py:182-185): labels (N, H, W) int64 -> out (N, K, H, W) fp32 with, for every class k that has
+ * a pixel in image n, edt(not k) outside the class and -(edt(k) - 1) inside it (scipy's exact Euclidean distance transform,
+ * including its convention for a class that covers the whole image); absent classes stay 0.  truncate != 0: values
+ * truncated towards zero as by the reference's assignment into the int32 one-hot dtype; 0: rounded to fp32
+ * (dtype=np.float32).  workspace: dt_one_hot2dist_workspace() bytes. */
+int64_t dt_one_hot2dist_workspace(int N, int K, int H, int W);
+int dt_one_hot2dist(const int64_t* labels, int N, int K, int H, int W, int truncate, float* out, void* workspace,
+                    int64_t workspace_bytes, dt_stream_t stream);
+
 /* Boundary (surface) loss on the logits (SurfaceLoss / BoundaryLoss, deadtrees/loss/losses.py:250-270, added to the total in
  * SemSegment.calculate_loss, segmodel.py:188-191): loss = mean over (b, k in idc, h, w) of softmax(logits)_k * dist_k.
  * logits, dist: (N, K, H, W) fp32; idc_mask: bit k set = class k in idc; workspace: 64 * N doubles.

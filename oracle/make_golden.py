@@ -71,6 +71,27 @@ def main():
             out[f"grad_{name}{i}"] = z.grad.numpy()
     out["ncases"] = np.int64(3)
     np.savez_compressed(OUT / "losses.npz", **out)
+
+    # ---- distance maps of the boundary loss: the reference's one_hot2dist (np.bool alias restored for numpy >= 1.24) ----
+    if not hasattr(np, "bool"):
+        np.bool = bool
+    rng = np.random.default_rng(77)
+    dm = {}
+    shapes = [(3, 24, 20), (3, 32, 32), (2, 16, 40), (3, 12, 12), (3, 9, 7)]
+    for i, (K, H, W) in enumerate(shapes):
+        if i == 0:      # blobs
+            yy, xx = np.mgrid[0:H, 0:W]
+            lab = ((np.hypot(yy - 8, xx - 6) < 5).astype(np.int64) + 2 * (np.hypot(yy - 17, xx - 14) < 4)).clip(0, K - 1)
+        elif i == 3:    # a single class everywhere (no background pixel for that class) and two absent classes
+            lab = np.zeros((H, W), dtype=np.int64)
+        else:
+            lab = rng.integers(0, K, size=(H, W)) if i != 1 else (rng.random((H, W)) < 0.03).astype(np.int64) * 2
+        onehot = losses.class2one_hot(torch.from_numpy(lab)[None], K)[0].numpy()          # int32, as in the dataloader
+        dm[f"labels{i}"], dm[f"K{i}"] = lab, np.int64(K)
+        dm[f"dist_int{i}"] = losses.one_hot2dist(onehot, resolution=[1, 1])                # dtype of seg: truncating
+        dm[f"dist_f32{i}"] = losses.one_hot2dist(onehot, resolution=[1, 1], dtype=np.float32)
+    dm["ncases"] = np.int64(len(shapes))
+    np.savez_compressed(OUT / "dist.npz", **dm)
     print("wrote", sorted(p.name for p in OUT.glob("*.npz")))
 
 

@@ -145,3 +145,20 @@ def test_unet_forward_shape_and_decoder_wiring():
     # PyTorchInference.run semantics: 3-d in -> 2-d out, rgb model on rgbn data slices channels
     out = ref_unet.run_inference(m, torch.randn(4, 64, 64), channels=3)
     assert out.shape == (64, 64) and out.dtype == torch.int64
+
+
+def test_distance_maps_against_reference_outputs(golden_dir):
+    """oracle/ref_dist.one_hot2dist == the reference's own one_hot2dist (losses.py:159-178) on the committed fixtures:
+    the truncating form the dataloader uses (int32 one-hot in) and the exact float32 form; includes a class that covers the
+    whole tile (scipy's no-background convention) and absent classes (left at 0)."""
+    from oracle import ref_dist
+    g = np.load(golden_dir / "dist.npz")
+    for i in range(int(g["ncases"])):
+        lab, K = g[f"labels{i}"], int(g[f"K{i}"])
+        onehot = (lab[None] == np.arange(K)[:, None, None]).astype(np.int32)
+        got_int = ref_dist.one_hot2dist(onehot, resolution=[1, 1])
+        assert got_int.dtype == np.int32
+        np.testing.assert_array_equal(got_int, g[f"dist_int{i}"])
+        np.testing.assert_array_equal(ref_dist.one_hot2dist(onehot, resolution=[1, 1], dtype=np.float32), g[f"dist_f32{i}"])
+        np.testing.assert_array_equal(ref_dist.labels_to_dist(lab[None], K, truncate=True)[0], g[f"dist_int{i}"].astype(np.float32))
+        np.testing.assert_array_equal(ref_dist.labels_to_dist(lab[None], K, truncate=False)[0], g[f"dist_f32{i}"])
