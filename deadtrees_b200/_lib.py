@@ -73,6 +73,7 @@ _SIGNATURES = {
     "dt_maxpool3x3s2_bwd": ([_p, _p, _p, _i, _i, _i, _i, _i, _p, _p], C.c_int),
     "dt_maxpool3x3s2_idx": ([_p, _i, _i, _i, _i, _i, _p, _p, _p], C.c_int),
     "dt_maxpool3x3s2_bwd_idx": ([_p, _p, _p, _i, _i, _i, _i, _i, _p, _p], C.c_int),
+    "dt_zero_insert2x": ([_p, _i, _i, _i, _i, _i, _p, _p], C.c_int),
     "dt_upsample_concat": ([_p, _p, _i, _i, _i, _i, _i, _i, _p, _p], C.c_int),
     "dt_upsample_concat_bwd": ([_p, _i, _i, _i, _i, _i, _i, _p, _p, _p], C.c_int),
     "dt_nchw_to_nhwc": ([_p, _i, _i, _i, _i, _i, _i, _p, _p], C.c_int),

@@ -462,6 +462,14 @@ def maxpool3x3s2_bwd_idx(idx: torch.Tensor, gout: torch.Tensor, x_shape, addend:
     return gx
 
 
+def zero_insert2x(gy: torch.Tensor) -> torch.Tensor:
+    """(N, Ho, Wo, C) -> (N, 2Ho, 2Wo, C) with gy at the even positions and zeros elsewhere."""
+    N, Ho, Wo, Cc = gy.shape
+    out = torch.empty((N, 2 * Ho, 2 * Wo, Cc), dtype=gy.dtype, device=gy.device)
+    check(load().dt_zero_insert2x(gy.data_ptr(), N, Ho, Wo, Cc, _dt(gy), out.data_ptr(), stream_ptr()))
+    return out
+
+
 def upsample_concat(x_low: torch.Tensor, skip: Optional[torch.Tensor]) -> torch.Tensor:
     N, Hl, Wl, Cx = x_low.shape
     Cs = 0 if skip is None else skip.shape[-1]

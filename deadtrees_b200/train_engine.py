@@ -62,6 +62,7 @@ class UnetTrainEngine:
         # (dt_bn_train_bwd_relu); measured on B200 it is not faster (11.67 vs 11.60 ms per step: these passes are not
         # bound by the bytes of that one tensor), so it stays opt-in
         self.bn_mask_from_y = os.environ.get("DT_BN_MASK_FROM_Y", "0") == "1"
+        self.dgrad_s2_zero_insert = os.environ.get("DT_DGRAD_S2_ZERO_INSERT", "1") != "0"
 
     def set_process_group(self, group, world_size: Optional[int] = None, bucket_bytes: int = 25 << 20) -> None:
         order = backward_param_order(self.param_names)
@@ -182,6 +183,13 @@ class UnetTrainEngine:
             wp = self.packer.get((wname, 3, Cg), w, 3, cout_pad=Cg)
             gx = ops.conv2d(gy, wp, self._ones, self._zeros, N=N, H=H, W=W, C_in=Cg, C_x=Cg, C_out=C_in, R=3, S=3, stride=1,
                             pad=1, relu=False, residual=addend, tag="dgrad." + wname)
+        elif (tc and self.dgrad_s2_zero_insert and stride == 2 and ((R == 3 and pad == 1) or (R == 1 and pad == 0))
+              and Cg % 64 == 0 and H == 2 * gy.shape[1] and W == 2 * gy.shape[2]):
+            # stride-2 conv: zero-insert gy to the input resolution, then the stride-1 form on the fast halo / TMA kernels
+            G = ops.zero_insert2x(gy)
+            wp = self.packer.get((wname, 3, Cg), w, 3, cout_pad=Cg)
+            gx = ops.conv2d(G, wp, self._ones, self._zeros, N=N, H=H, W=W, C_in=Cg, C_x=Cg, C_out=C_in, R=R, S=S, stride=1,
+                            pad=pad, relu=False, residual=addend, algo_cin=Cg // 4, tag="dgrad." + wname)   # algorithmic FLOPs
         elif tc and stride == 2 and ((R == 3 and pad == 1) or (R == 1 and pad == 0)) and Cg % 64 == 0 and Cg == C_out:
             # stride-2 conv: every output pixel gathers the taps whose source coordinate is even (gather producer)
             wp = self.packer.get((wname, 4, Cg), w, 4, cout_pad=Cg)

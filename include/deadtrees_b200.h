@@ -257,6 +257,9 @@ int dt_maxpool3x3s2_bwd(const void* x, const void* gout, const void* addend, int
 int dt_maxpool3x3s2_idx(const void* x, int N, int H, int W, int C, int dtype, void* y, uint8_t* idx, dt_stream_t stream);
 int dt_maxpool3x3s2_bwd_idx(const uint8_t* idx, const void* gout, const void* addend, int N, int H, int W, int C, int dtype,
                             void* gx, dt_stream_t stream);
+/* out (N, 2Ho, 2Wo, C) = gy (N, Ho, Wo, C) at the even positions, zero elsewhere: the data gradient of a stride-2
+ * convolution is dt_conv2d_fwd (stride 1) of this tensor with the dt_pack_conv_weight mode-3 weights. */
+int dt_zero_insert2x(const void* gy, int N, int Ho, int Wo, int C, int dtype, void* out, dt_stream_t stream);
 /* cat([nearest_x2(x_low), skip], C) materialised for the training path, and its backward
  * (g_x_low = 2x2 block sums of g_cat[..., :Cx]; g_skip = g_cat[..., Cx:]).  H, W: full resolution. */
 int dt_upsample_concat(const void* x_low, const void* skip, int N, int H, int W, int Cx, int Cs, int dtype, void* out,
