@@ -205,16 +205,21 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t b
 }
 
 constexpr int ROW_MAX_STAGES = 8;
+constexpr int OUT_TILE = BM * BN * 2;        // 16 KB staging tile of the TMA output store
 
 __global__ void __launch_bounds__(kThreads, 1)
-conv_stem_rows_kernel(const __grid_constant__ CUtensorMap tm_b, const StemRowParams p) {
+conv_stem_rows_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ CUtensorMap tm_y,
+                      const StemRowParams p) {
   constexpr int TMEM_COLS = 2 * BN;
   constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_w = smem;
   uint8_t* smem_a = smem + W_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + static_cast<size_t>(p.stages) * p.stage_bytes);
+  // two 16 KB staging tiles for the TMA output store (1024-byte aligned: SWIZZLE_128B), then the barriers
+  uint8_t* smem_o = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_a + static_cast<size_t>(p.stages) * p.stage_bytes) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_o + 2 * OUT_TILE);
   uint64_t* w_full = bars;
   uint64_t* full = w_full + 1;                   // [ROW_MAX_STAGES]
   uint64_t* empty = full + ROW_MAX_STAGES;       // [ROW_MAX_STAGES]
@@ -225,6 +230,7 @@ conv_stem_rows_kernel(const __grid_constant__ CUtensorMap tm_b, const StemRowPar
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_b);
+    tma_prefetch_desc(&tm_y);
     mbar_init(w_full, 1u);
     for (int i = 0; i < p.stages; ++i) { mbar_init(&full[i], 1u); mbar_init(&empty[i], 1u); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1u); mbar_init(&tmem_empty[i], 128u); }
@@ -286,16 +292,23 @@ conv_stem_rows_kernel(const __grid_constant__ CUtensorMap tm_b, const StemRowPar
       }
     }
   } else {
+    // The 128 x 64 bf16 tile of an output row segment is 16 KB contiguous in global memory: the epilogue writes it into a
+    // SWIZZLE_128B staging tile (16-byte chunk index ^ (row & 7): conflict-free) and ONE TMA store per tile moves it out,
+    // instead of 16 warp-level 256-bit stores that each touch 32 different 128-byte lines (ncu: l1tex 82 % busy).
     const int quarter = warp & 3;
     const int lrow = quarter * 32 + lane;
-    int buf = 0;
+    const bool issuer = threadIdx.x == 64;              // first epilogue thread (warp 2, lane 0)
+    int buf = 0, ob = 0;
     uint32_t pbuf = 0;
     for (int row = blockIdx.x; row < p.total_rows; row += gridDim.x) {
       for (int t = 0; t < p.tiles_per_row; ++t) {
-        const int64_t m = static_cast<int64_t>(row) * p.Wo + t * BM + lrow;
+        const int m0 = row * p.Wo + t * BM;
+        if (issuer) bulk_wait_group_read<1>();          // the store that last read staging tile `ob` has drained it
+        named_bar_sync(1, 128);
         mbar_wait(&tmem_full[buf], pbuf);
         tc_fence_after();
         const uint32_t t_row = tmem_base + buf * BN + (static_cast<uint32_t>(quarter * 32) << 16);
+        uint8_t* orow = smem_o + ob * OUT_TILE + lrow * 128;
 #pragma unroll
         for (int c0 = 0; c0 < BN; c0 += 16) {
           uint32_t v[16];
@@ -315,13 +328,25 @@ conv_stem_rows_kernel(const __grid_constant__ CUtensorMap tm_b, const StemRowPar
 #pragma unroll
             for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
           }
-          store_bf16x16(p.y + m * BN + c0, f);
+          const int ch = c0 >> 3;                       // 16-byte chunk index of channel c0 in the 128-byte row
+          *reinterpret_cast<uint4*>(orow + (((ch) ^ (lrow & 7)) << 4)) =
+              make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+          *reinterpret_cast<uint4*>(orow + (((ch + 1) ^ (lrow & 7)) << 4)) =
+              make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
         }
         tc_fence_before();
         mbar_arrive(&tmem_empty[buf]);
+        fence_proxy_async_smem();                       // generic-proxy writes visible to the TMA (async proxy)
+        named_bar_sync(1, 128);
+        if (issuer) {
+          tma_store_2d(&tm_y, smem_o + ob * OUT_TILE, 0, m0);
+          bulk_commit_group();
+        }
+        ob ^= 1;
         if ((buf ^= 1) == 0) pbuf ^= 1u;
       }
     }
+    if (issuer) bulk_wait_group<0>();                   // all stores complete before the CTA exits
   }
 
   tc_fence_before();
@@ -392,13 +417,23 @@ int dt_conv_stem(const dt_conv_desc* d, const void* x, const void* w, const floa
     q.row_bytes = static_cast<int>(Wp * 8);
     q.stage_bytes = (ROWS * q.row_bytes + 127) / 128 * 128;
     q.image_bytes = static_cast<int64_t>(Hp) * Wp * 8;
-    q.stages = (200 * 1024 - W_BYTES) / q.stage_bytes;
+    q.stages = (200 * 1024 - W_BYTES - 2 * OUT_TILE - 1024) / q.stage_bytes;
     if (q.stages > ROW_MAX_STAGES) q.stages = ROW_MAX_STAGES;
     if (q.stages >= 2 && (ROWS * q.row_bytes) % 16 == 0 && ROWS * q.row_bytes < (1 << 20)) {
       q.x = static_cast<const uint8_t*>(x);
       q.y = static_cast<__nv_bfloat16*>(y);
       q.scale = scale; q.shift = shift;
-      const int smem_rows = W_BYTES + q.stages * q.stage_bytes + 1024 + 256;
+      CUtensorMap tm_y;
+      {
+        const cuuint64_t ydims[2] = {BN, static_cast<cuuint64_t>(q.total_rows) * Wo};
+        const cuuint64_t ystr[1] = {BN * 2};
+        const cuuint32_t ybox[2] = {BN, BM};
+        const cuuint32_t yes[2] = {1, 1};
+        CUresult r = fn(&tm_y, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, y, ydims, ystr, ybox, yes, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        DT_REQUIRE(r == CUDA_SUCCESS, DT_ERR_CUDA, "stem output tensor map: CUresult %d", static_cast<int>(r));
+      }
+      const int smem_rows = W_BYTES + q.stages * q.stage_bytes + 1024 + 2 * OUT_TILE + 1024 + 256;
       static std::once_flag once_rows;
       static cudaError_t attr_rows = cudaSuccess;
       std::call_once(once_rows, [] {
@@ -406,7 +441,7 @@ int dt_conv_stem(const dt_conv_desc* d, const void* x, const void* w, const floa
       });
       DT_CUDA(attr_rows);
       const int grid_rows = q.total_rows < dt_num_sms() ? q.total_rows : dt_num_sms();
-      conv_stem_rows_kernel<<<grid_rows, kThreads, smem_rows, s>>>(tm_b, q);
+      conv_stem_rows_kernel<<<grid_rows, kThreads, smem_rows, s>>>(tm_b, tm_y, q);
       DT_LAUNCH_CHECK();
       return DT_OK;
     }
