@@ -67,12 +67,17 @@ __device__ __forceinline__ constexpr int tap_pixel_offset(int mt, int tap) {
   return (mt * TH + fr) * PITCH + fs;
 }
 
-template <int BN, int CW, int MT, bool PAR, int EPI>
+// FOLD (parity mode): nearest-x2 up-sampling folded into the weights.  For output parity class (a,b) the nine taps of the
+// up-sampled operand touch only 2 x 2 low-res pixels, (a-1+ey, b-1+ex); the host sums the taps that share a pixel
+// (dt_pack_conv_weight mode 5: K index = ((class * 4 + e) * C_in + ci), e = ey * 2 + ex) and the kernel issues 4 instead
+// of 9 taps per class: 16 instead of 36 tap-MMAs per super tile on a layer that is bound by the A-operand reads.
+template <int BN, int CW, int MT, bool PAR, int EPI, bool FOLD>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_res_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                 const ResParams p) {
+  static_assert(!FOLD || (PAR && MT == 4), "folded weights belong to the parity mode");
   constexpr int B_BYTES = BN * BK * 2;
-  constexpr int NCH = (9 * CW + BK - 1) / BK;               // weight chunks of 64 K elements
+  constexpr int NCH = FOLD ? (16 * CW) / BK : (9 * CW + BK - 1) / BK;   // weight chunks of 64 K elements
   constexpr int W_BYTES = NCH * B_BYTES;
   constexpr int ROW_BYTES = CW * 2;
   constexpr int TILE_ROWS = PAR ? TH : TH * MT;             // rows of the tile grid one super tile covers
@@ -138,8 +143,24 @@ conv_res_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         const uint64_t a_d = a_hi + (smem_u32(smem_a + sa * p.a_slot_bytes) >> 4);
         // k-step outer, M tile inner: consecutive MMAs go to DIFFERENT accumulators, so the tensor pipe never
         // waits on the read-modify-write latency of one accumulator (matters for the N = 16 / 32 layers)
+        if (FOLD) {
+          // effective tap outer, class inner: consecutive MMAs go to different accumulators
 #pragma unroll
-        for (int q = 0; q < NCH; ++q) {
+          for (int e = 0; e < 4; ++e) {
+#pragma unroll
+            for (int ch = 0; ch < CW; ch += 16) {
+#pragma unroll
+              for (int cls = 0; cls < 4; ++cls) {
+                const int kk = (cls * 4 + e) * CW + ch;                    // K index of the folded packing (compile time)
+                const int off = ((cls >> 1) + (e >> 1)) * PITCH + (cls & 1) + (e & 1);   // low-res pixel (a-1+ey, b-1+ex)
+                umma_bf16_ss(tmem_base + (buf * MT + cls) * BN, a_d + ((off * ROW_BYTES + ch * 2) >> 4),
+                             b_d0 + (((kk / BK) * B_BYTES + (kk % BK) * 2) >> 4), idesc, (e == 0 && ch == 0) ? 0u : 1u);
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < (FOLD ? 0 : NCH); ++q) {
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             const int kk = q * BK + k * 16;  // K index = tap * CW + channel (compile time)
@@ -262,10 +283,10 @@ conv_res_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   }
 }
 
-template <int BN, int CW, int MT, bool PAR, int EPI = 0>
+template <int BN, int CW, int MT, bool PAR, int EPI = 0, bool FOLD = false>
 int launch_res(const CUtensorMap& tm_a, const CUtensorMap& tm_b, ResParams& p, cudaStream_t s) {
   constexpr int B_BYTES = BN * BK * 2;
-  constexpr int NCH = (9 * CW + BK - 1) / BK;
+  constexpr int NCH = FOLD ? (16 * CW) / BK : (9 * CW + BK - 1) / BK;
   constexpr int W_BYTES = ((NCH * B_BYTES + 1023) / 1024) * 1024;
   constexpr int TMEM_USED = 2 * MT * BN;
   constexpr int TMEM_COLS = TMEM_USED <= 32 ? 32 : (TMEM_USED <= 64 ? 64 : (TMEM_USED <= 128 ? 128 : (TMEM_USED <= 256 ? 256 : 512)));
@@ -283,13 +304,13 @@ int launch_res(const CUtensorMap& tm_a, const CUtensorMap& tm_b, ResParams& p, c
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(conv_res_kernel<BN, CW, MT, PAR, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    attr_err = cudaFuncSetAttribute(conv_res_kernel<BN, CW, MT, PAR, EPI, FOLD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     225 * 1024);
   });
   DT_CUDA(attr_err);
   const int slots = dt_num_sms() * ctas;
   const int grid = p.total_tiles < slots ? p.total_tiles : slots;
-  conv_res_kernel<BN, CW, MT, PAR, EPI><<<grid, kThreads, smem, s>>>(tm_a, tm_b, p);
+  conv_res_kernel<BN, CW, MT, PAR, EPI, FOLD><<<grid, kThreads, smem, s>>>(tm_a, tm_b, p);
   DT_LAUNCH_CHECK();
   return DT_OK;
 }
@@ -340,6 +361,15 @@ int dt_conv_res(const dt_conv_desc* d, const void* x, const void* w, int Kpad, c
     const uint32_t box[4] = {static_cast<uint32_t>(cw), PITCH, static_cast<uint32_t>(tile_rows + 2), 1};
     int rc = dt_encode_bf16_map(&tm_a, x, 4, dims, strides, box, nullptr);
     if (rc != DT_OK) return rc;
+  }
+  if (d->flags & DT_CONV_UPS_FOLDED) {
+    // weights in the folded packing (mode 5): only the parity instances below take them
+    if (!parity || Kpad != 16 * cw) return DT_ERR_UNSUPPORTED;
+    if (bn == 16 && cw == 32) return launch_res<16, 32, 4, true, 0, true>(tm_a, tm_b, p, s);
+    if (bn == 32 && cw == 32) return launch_res<32, 32, 4, true, 0, true>(tm_a, tm_b, p, s);
+    if (bn == 16 && cw == 16) return launch_res<16, 16, 4, true, 0, true>(tm_a, tm_b, p, s);
+    if (bn == 32 && cw == 64) return launch_res<32, 64, 4, true, 0, true>(tm_a, tm_b, p, s);
+    return DT_ERR_UNSUPPORTED;
   }
 #define DT_RES(BNV, CWV, MTV, PARV) \
   if (bn == BNV && cw == CWV && mt == MTV && parity == (PARV ? 1 : 0)) \

@@ -545,6 +545,15 @@ extern "C" int dt_conv2d_fwd(const dt_conv_desc* d, const void* x, const void* s
   DT_REQUIRE(d->C_out % BN == 0 && (BN == 16 || BN == 32 || BN == 64 || BN == 128 || BN == 256), DT_ERR_BAD_SHAPE,
              "dt_conv2d_fwd: unsupported C_out %d", d->C_out);
 
+  if (d->flags & DT_CONV_UPS_FOLDED) {
+    // up-sampling folded into per-class weights (dt_pack_conv_weight mode 5): only the resident-weight parity kernel
+    DT_REQUIRE(d->upsample && d->C_x == d->C_in && !stem && !transposed, DT_ERR_BAD_SHAPE,
+               "dt_conv2d_fwd: DT_CONV_UPS_FOLDED needs an up-sampled input without a skip tensor");
+    const int rcf = dt_conv_res(d, x, w, 16 * d->C_in, scale, shift, residual, y, s);
+    DT_REQUIRE(rcf != DT_ERR_UNSUPPORTED, DT_ERR_BAD_SHAPE, "dt_conv2d_fwd: no folded kernel for %d -> %d channels at %dx%d",
+               d->C_in, d->C_out, d->H, d->W);
+    return rcf;
+  }
   if (!(d->flags & (DT_CONV_NO_HALO | DT_CONV_FORCE_GATHER)) && !stem && !transposed) {
     const int rc0 = dt_conv_res(d, x, w, Kpad, scale, shift, residual, y, s);   // weights resident in smem
     if (rc0 != DT_ERR_UNSUPPORTED) return rc0;

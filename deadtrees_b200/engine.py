@@ -13,7 +13,7 @@ from typing import Dict, List, Optional
 import torch
 
 from . import ops
-from ._lib import CONV_X_PAD3, require_device
+from ._lib import CONV_UPS_FOLDED, CONV_X_PAD3, require_device
 
 BN_EPS = 1e-5
 RESNET34_LAYERS = (3, 4, 6, 3)
@@ -38,6 +38,7 @@ class FusedConv:
     scale: torch.Tensor
     shift: torch.Tensor
     flops_per_px_out: int = field(default=0)
+    flags: int = field(default=0)          # extra DT_CONV_* flags of this layer (e.g. DT_CONV_UPS_FOLDED)
 
 
 def fold_bn(sd: Dict[str, torch.Tensor], prefix: str, C_out: int, device):
@@ -72,6 +73,35 @@ def pack_weight(w: torch.Tensor, precision: str, stem: bool, device) -> torch.Te
     return out.to(torch.bfloat16).contiguous().to(device)
 
 
+def fold_upsample_weights(w: torch.Tensor) -> torch.Tensor:
+    """(C_out, C_in, 3, 3) fp32 -> (C_out, 4 classes, 4 effective taps, C_in) fp32: nearest-x2 up-sampling folded into the
+    weights.  Output parity class (a, b) reads the 2 x 2 low-res pixels (a-1+ey, b-1+ex); the taps (fr, fs) of the 3 x 3
+    filter that land on the same low-res pixel, floor((a+fr-1)/2) = a-1+ey, are summed (in fp32, from the fp32 weights)."""
+    C_out, C_in = w.shape[:2]
+    out = w.new_zeros(C_out, 4, 4, C_in)
+    for a in range(2):
+        for b in range(2):
+            for fr in range(3):
+                ey = (a + fr - 1) // 2 - (a - 1)
+                for fs in range(3):
+                    ex = (b + fs - 1) // 2 - (b - 1)
+                    out[:, a * 2 + b, ey * 2 + ex] += w[:, :, fr, fs]
+    return out
+
+
+def pack_weight_folded(w: torch.Tensor, device) -> torch.Tensor:
+    """dt_pack_conv_weight mode 5 / DT_CONV_UPS_FOLDED: bf16 [C_out][16 * C_in], k = ((class * 4 + e) * C_in + ci)."""
+    C_out, C_in = w.shape[:2]
+    return fold_upsample_weights(w.float()).reshape(C_out, 16 * C_in).to(torch.bfloat16).contiguous().to(device)
+
+
+def folds_upsample(precision: str, C_in: int, C_x: int, C_out: int, conv_flags: int = 0) -> bool:
+    """layers whose up-sampling is folded into the weights: bf16, no skip tensor, and a shape the resident-weight parity
+    kernel has a folded instance for (in Unet-resnet34: decoder.blocks.4.conv1, 32 -> 16)."""
+    return (precision == "bf16" and not conv_flags and C_x == C_in and
+            (C_in, C_out) in ((32, 16), (32, 32), (16, 16), (64, 32)))
+
+
 class UnetEngine:
     """B200 forward pass of the reference's ``smp.Unet(resnet34, depth 5, decoder (256,128,64,32,16))``."""
 
@@ -101,7 +131,13 @@ class UnetEngine:
         scale, shift = fold_bn(sd, bn_key, C_out, self.device)
         if stem:
             C_in = 4
-        self.layers[name] = FusedConv(name, C_in, C_in if C_x is None else C_x, C_out, R, S, stride, pad, relu,
+        cx = C_in if C_x is None else C_x
+        if upsample and folds_upsample(self.precision, C_in, cx, C_out, self.conv_flags):
+            self.layers[name] = FusedConv(name, C_in, cx, C_out, R, S, stride, pad, relu, upsample,
+                                          pack_weight_folded(w, self.device), scale, shift, 2 * C_in * R * S * C_out,
+                                          flags=CONV_UPS_FOLDED)
+            return
+        self.layers[name] = FusedConv(name, C_in, cx, C_out, R, S, stride, pad, relu,
                                       upsample, pack_weight(w, self.precision, stem, self.device), scale, shift,
                                       2 * C_in * R * S * C_out)
 
@@ -146,8 +182,9 @@ class UnetEngine:
         L = self.layers[name]
         return ops.conv2d(x, L.w, L.scale, L.shift, N=N, H=H, W=W, C_in=L.C_in, C_x=L.C_x, C_out=L.C_out, R=L.R,
                           S=L.S, stride=L.stride, pad=L.pad, relu=L.relu, skip=skip, upsample=L.upsample,
-                          residual=residual, out=out, flags=self.conv_flags | flags,
-                          algo_cin=self.in_channels if name == "stem" else None, tag=name)
+                          residual=residual, out=out, flags=self.conv_flags | flags | L.flags,
+                          algo_cin=self.in_channels if name == "stem" else (L.C_in * 4.0 / 9.0 if L.flags & CONV_UPS_FOLDED
+                                                                            else None), tag=name)   # FLOPs the tensor pipe executes
 
     def _buf(self, ws, key, shape):
         t = ws.get(key)

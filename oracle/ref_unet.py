@@ -223,6 +223,40 @@ def _fused(conv: nn.Conv2d, bn: nn.BatchNorm2d, x, relu=True, residual=None):
     return _rb(F.relu(y) if relu else y)
 
 
+def fold_upsample_weights(w: torch.Tensor) -> torch.Tensor:
+    """(C_out, C_in, 3, 3) -> (C_out, C_in, 2, 2, 2, 2) [a, b, ey, ex]: the 3 x 3 taps that land on the same low-res pixel
+    of a nearest-x2 up-sampled input, summed in fp32 (output parity class (a, b) reads low-res pixels (a-1+ey, b-1+ex))."""
+    out = w.new_zeros(w.shape[0], w.shape[1], 2, 2, 2, 2)
+    for a in range(2):
+        for b in range(2):
+            for fr in range(3):
+                ey = (a + fr - 1) // 2 - (a - 1)
+                for fs in range(3):
+                    ex = (b + fs - 1) // 2 - (b - 1)
+                    out[:, :, a, b, ey, ex] += w[:, :, fr, fs]
+    return out
+
+
+def _fused_upsample_folded(conv: nn.Conv2d, bn: nn.BatchNorm2d, x_low, relu=True):
+    """conv3x3(nearest_x2(x_low)) in the engine's folded arithmetic (DT_CONV_UPS_FOLDED): per output parity class a 2 x 2
+    convolution of the LOW-RES tensor with the summed weights rounded to bf16 once (exact in real arithmetic; the
+    unfolded form rounds each of the nine weights)."""
+    scale, shift = _fold(bn)
+    wf = _rb(fold_upsample_weights(conv.weight.float()))
+    N, _, H, W = x_low.shape
+    xp = F.pad(x_low, (1, 1, 1, 1))
+    y = x_low.new_zeros(N, conv.weight.shape[0], 2 * H, 2 * W)
+    for a in range(2):
+        for b in range(2):
+            y[:, :, a::2, b::2] = F.conv2d(xp[:, :, a: a + H + 1, b: b + W + 1], wf[:, :, a, b])
+    y = y * scale[None, :, None, None] + shift[None, :, None, None]
+    return _rb(F.relu(y) if relu else y)
+
+
+# (C_in, C_out) of the up-sampled, skip-less layers the engine folds (deadtrees_b200/engine.py::folds_upsample)
+FOLDED_SHAPES = ((32, 16), (32, 32), (16, 16), (64, 32))
+
+
 def forward_bf16(model: Unet, x: torch.Tensor) -> torch.Tensor:
     """(N, C, H, W) fp32 -> fp32 logits computed with the bf16 storage points of the CUDA engine."""
     enc = model.encoder
@@ -240,10 +274,14 @@ def forward_bf16(model: Unet, x: torch.Tensor) -> torch.Tensor:
         skips = feats[::-1]
         y = skips[0]
         for i, blk in enumerate(model.decoder.blocks):
-            y = F.interpolate(y, scale_factor=2, mode="nearest")
-            if i + 1 < len(skips):
-                y = torch.cat([y, skips[i + 1]], dim=1)
-            y = _fused(blk.conv1[0], blk.conv1[1], y)
+            c1 = blk.conv1[0]
+            if i + 1 >= len(skips) and (c1.in_channels, c1.out_channels) in FOLDED_SHAPES:
+                y = _fused_upsample_folded(c1, blk.conv1[1], y)      # no skip tensor: up-sampling folded into the weights
+            else:
+                y = F.interpolate(y, scale_factor=2, mode="nearest")
+                if i + 1 < len(skips):
+                    y = torch.cat([y, skips[i + 1]], dim=1)
+                y = _fused(c1, blk.conv1[1], y)
             y = _fused(blk.conv2[0], blk.conv2[1], y)
         head = model.segmentation_head[0]   # tensor-core head: bf16 weights, fp32 accumulate, fp32 bias
         return F.conv2d(y, _rb(head.weight), head.bias, 1, 1)

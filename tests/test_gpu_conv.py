@@ -4,8 +4,9 @@ import torch
 import torch.nn.functional as F
 
 from deadtrees_b200 import ops
-from deadtrees_b200._lib import CONV_FORCE_DIRECT, CONV_FORCE_GATHER, CONV_NO_HALO, CONV_NO_QUAD, CONV_X_PAD3
-from deadtrees_b200.engine import pack_weight
+from deadtrees_b200._lib import (CONV_FORCE_DIRECT, CONV_FORCE_GATHER, CONV_NO_HALO, CONV_NO_QUAD, CONV_UPS_FOLDED,
+                                 CONV_X_PAD3)
+from deadtrees_b200.engine import fold_upsample_weights, pack_weight, pack_weight_folded
 from gpu_util import report, to_nchw
 
 pytestmark = pytest.mark.gpu
@@ -113,6 +114,37 @@ def test_conv_tcgen05(case):
         # class's K order - identical bits to the class-per-tile kernel
         got_nq = run_cuda(case, x, skip, w, scale, shift, residual, dtype=torch.bfloat16, flags=CONV_NO_QUAD)
         assert torch.equal(got, got_nq)
+
+
+@pytest.mark.parametrize("N,H,Cx,Co", [(2, 64, 32, 16), (1, 128, 32, 16), (3, 32, 32, 32), (2, 32, 16, 16), (1, 64, 64, 32)])
+def test_conv_upsample_folded(N, H, Cx, Co):
+    """DT_CONV_UPS_FOLDED: nearest-x2 up-sampling folded into per-class 2 x 2 weights (resident-weight parity kernel).
+    Against torch with the SAME folded bf16 weights (per-class convolutions of the low-res tensor), and against the
+    nine-tap kernel - the two differ only by the rounding of the summed weights."""
+    g = torch.Generator().manual_seed(N + H + Cx)
+    x = torch.randn(N, Cx, H // 2, H // 2, generator=g)
+    w = torch.randn(Co, Cx, 3, 3, generator=g) * (2.0 / (Cx * 9)) ** 0.5
+    scale, shift = 1.0 + 0.1 * torch.randn(Co, generator=g), 0.1 * torch.randn(Co, generator=g)
+    xb = x.to(torch.bfloat16).float()
+    wf = fold_upsample_weights(w).to(torch.bfloat16).float()             # (Co, class, e, Cx)
+    Hl = H // 2
+    xp = F.pad(xb, (1, 1, 1, 1))
+    ref = torch.zeros(N, Co, H, H)
+    for a in range(2):
+        for b in range(2):
+            k = wf[:, a * 2 + b].reshape(Co, 2, 2, Cx).permute(0, 3, 1, 2)
+            ref[:, :, a::2, b::2] = F.conv2d(xp[:, :, a: a + Hl + 1, b: b + Hl + 1], k)
+    ref = F.relu(ref * scale[None, :, None, None] + shift[None, :, None, None])
+    nhwc = lambda t: t.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).cuda()
+    kw = dict(N=N, H=H, W=H, C_in=Cx, C_x=Cx, C_out=Co, R=3, S=3, stride=1, pad=1, relu=True, upsample=True)
+    y_f = ops.conv2d(nhwc(x), pack_weight_folded(w, "cuda"), scale.cuda(), shift.cuda(), flags=CONV_UPS_FOLDED, **kw)
+    y_9 = ops.conv2d(nhwc(x), pack_weight(w, "bf16", False, "cuda"), scale.cuda(), shift.cuda(), **kw)
+    torch.cuda.synchronize()
+    err, rel = report(f"folded up-sample conv {Cx}->{Co} @{H}", to_nchw(y_f), ref)
+    assert rel < 1e-2
+    d = (to_nchw(y_f) - to_nchw(y_9)).abs().max().item()
+    print(f"folded vs nine-tap: max diff {d:.3e} (max |y| {ref.abs().max().item():.3e})")
+    assert d <= 2.0 ** -5 * ref.abs().max().item()
 
 
 def test_stem_tcgen05_and_fp32():
