@@ -57,6 +57,8 @@ struct HaloParams {
   const float* scale;
   const float* shift;
   PatchDesc patch[4][5];             // [class][0] = x patch, [class][1..4] = skip planes
+  int fold;                          // class-fused kernel: x operand with folded up-sampling weights (DT_CONV_UPS_FOLDED):
+  int k_skip;                        //   K index of (class c, low-res pixel e, x channel ci) = (c*4+e)*C_x + ci, skip taps from k_skip
 };
 
 struct Geo {
@@ -425,12 +427,20 @@ conv_halo_quad_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
             }
             ++q;
           };
-          if (kind == 0) {
+          if (kind == 0 && p.fold) {
+            // folded up-sampling: four effective taps per class, each class its own summed weights
+            for (int e = 0; e < 4; ++e)
+              for (int cls = 0; cls < 4; ++cls) { maybe_prefetch(); load_chunk((cls * 4 + e) * p.C_x + pi * CW); }
+          } else if (kind == 0) {
             for (int tap = 0; tap < 9; ++tap) { maybe_prefetch(); load_chunk(tap * p.C_in + choff); }
           } else {
+            const int sl = ((pi - p.n_xslab) >> 2) * BK;
             for (int cls = 0; cls < 4; ++cls) {
               const PatchDesc& pd = p.patch[cls][kind];
-              for (int j = 0; j < pd.ntaps; ++j) { maybe_prefetch(); load_chunk(pd.tap[j] * p.C_in + choff); }
+              for (int j = 0; j < pd.ntaps; ++j) {
+                maybe_prefetch();
+                load_chunk(p.fold ? p.k_skip + pd.tap[j] * (p.C_in - p.C_x) + sl : pd.tap[j] * p.C_in + choff);
+              }
             }
           }
         }
@@ -451,7 +461,26 @@ conv_halo_quad_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
           mbar_wait(&full_a[sa], pa);
           tc_fence_after();
           const uint64_t a_d = a_hi + (smem_u32(smem_a + sa * p.a_slot_bytes) >> 4);
-          if (kind == 0) {
+          if (kind == 0 && p.fold) {
+            for (int e = 0; e < 4; ++e) {
+#pragma unroll
+              for (int cls = 0; cls < 4; ++cls) {
+                mbar_wait(&full_b[sb], pb);
+                tc_fence_after();
+                const uint64_t b_d = b_hi + (smem_u32(smem_b + sb * B_BYTES) >> 4);
+                // low-res pixel (a-1+ey, b-1+ex) of class (a,b): patch offset (a+ey, b+ex)
+                const uint32_t off = static_cast<uint32_t>(((cls >> 1) + (e >> 1)) * PITCH + (cls & 1) + (e & 1));
+                const uint64_t a_t = a_d + ((off * ROW_BYTES) >> 4);
+                const uint32_t d_tmem = tmem_base + (acc * 4 + cls) * BN;
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k)
+                  umma_bf16_ss(d_tmem, a_t + 2 * k, b_d + 2 * k, idesc, (((started >> cls) & 1u) | k) != 0 ? 1u : 0u);
+                started |= 1u << cls;
+                umma_commit(&empty_b[sb]);
+                if (++sb == p.b_slots) { sb = 0; pb ^= 1u; }
+              }
+            }
+          } else if (kind == 0) {
             for (int tap = 0; tap < 9; ++tap) {
               mbar_wait(&full_b[sb], pb);
               tc_fence_after();
@@ -659,7 +688,14 @@ int dt_conv_halo(const dt_conv_desc* d, int BN, const void* x, const void* skip,
     int rc = dt_encode_bf16_map(&tm_s, skip, 4, dims, strides, box, estr);
     if (rc != DT_OK) return rc;
   }
-  if (parity && wide && !d->has_residual && d->C_out == BN && !(d->flags & DT_CONV_NO_QUAD)) {
+  if (d->flags & DT_CONV_UPS_FOLDED) {
+    // x operand with folded up-sampling weights: only the class-fused kernel knows that packing
+    if (!(parity && wide && !d->has_residual && d->C_out == BN && (BN == 32 || BN == 64)) || Kpad != 16 * d->C_x + 9 * C_s)
+      return DT_ERR_UNSUPPORTED;
+    p.fold = 1;
+    p.k_skip = 16 * d->C_x;
+  }
+  if (parity && wide && !d->has_residual && d->C_out == BN && (p.fold || !(d->flags & DT_CONV_NO_QUAD))) {
     if (BN == 32) return launch_halo_quad<32>(tm_a, tm_s, tm_b, p, s);
     if (BN == 64) return launch_halo_quad<64>(tm_a, tm_s, tm_b, p, s);
   }

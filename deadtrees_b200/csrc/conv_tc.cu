@@ -547,9 +547,10 @@ extern "C" int dt_conv2d_fwd(const dt_conv_desc* d, const void* x, const void* s
 
   if (d->flags & DT_CONV_UPS_FOLDED) {
     // up-sampling folded into per-class weights (dt_pack_conv_weight mode 5): only the resident-weight parity kernel
-    DT_REQUIRE(d->upsample && d->C_x == d->C_in && !stem && !transposed, DT_ERR_BAD_SHAPE,
-               "dt_conv2d_fwd: DT_CONV_UPS_FOLDED needs an up-sampled input without a skip tensor");
-    const int rcf = dt_conv_res(d, x, w, 16 * d->C_in, scale, shift, residual, y, s);
+    DT_REQUIRE(d->upsample && !stem && !transposed, DT_ERR_BAD_SHAPE, "dt_conv2d_fwd: DT_CONV_UPS_FOLDED needs an up-sampled input");
+    const int rcf = d->C_x == d->C_in
+                        ? dt_conv_res(d, x, w, 16 * d->C_in, scale, shift, residual, y, s)
+                        : dt_conv_halo(d, BN, x, skip, w, 16 * d->C_x + 9 * (d->C_in - d->C_x), scale, shift, residual, y, s);
     DT_REQUIRE(rcf != DT_ERR_UNSUPPORTED, DT_ERR_BAD_SHAPE, "dt_conv2d_fwd: no folded kernel for %d -> %d channels at %dx%d",
                d->C_in, d->C_out, d->H, d->W);
     return rcf;

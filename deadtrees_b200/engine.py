@@ -89,17 +89,27 @@ def fold_upsample_weights(w: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def pack_weight_folded(w: torch.Tensor, device) -> torch.Tensor:
-    """dt_pack_conv_weight mode 5 / DT_CONV_UPS_FOLDED: bf16 [C_out][16 * C_in], k = ((class * 4 + e) * C_in + ci)."""
+def pack_weight_folded(w: torch.Tensor, device, C_x: Optional[int] = None) -> torch.Tensor:
+    """DT_CONV_UPS_FOLDED packing: bf16 [C_out][16 * C_x + 9 * C_s]; the first C_x input channels are the up-sampled
+    operand, k = ((class * 4 + e) * C_x + ci), the remaining C_s the skip operand, k = 16 * C_x + tap * C_s + cs."""
     C_out, C_in = w.shape[:2]
-    return fold_upsample_weights(w.float()).reshape(C_out, 16 * C_in).to(torch.bfloat16).contiguous().to(device)
+    C_x = C_in if C_x is None else C_x
+    w = w.float()
+    parts = [fold_upsample_weights(w[:, :C_x]).reshape(C_out, 16 * C_x)]
+    if C_x < C_in:
+        parts.append(w[:, C_x:].permute(0, 2, 3, 1).reshape(C_out, 9 * (C_in - C_x)))
+    return torch.cat(parts, dim=1).to(torch.bfloat16).contiguous().to(device)
 
 
 def folds_upsample(precision: str, C_in: int, C_x: int, C_out: int, conv_flags: int = 0) -> bool:
-    """layers whose up-sampling is folded into the weights: bf16, no skip tensor, and a shape the resident-weight parity
-    kernel has a folded instance for (in Unet-resnet34: decoder.blocks.4.conv1, 32 -> 16)."""
-    return (precision == "bf16" and not conv_flags and C_x == C_in and
-            (C_in, C_out) in ((32, 16), (32, 32), (16, 16), (64, 32)))
+    """up-sample layers whose up-sampling is folded into the weights of the x operand (bf16 path): the shapes the
+    resident-weight parity kernel (no skip) or the class-fused kernel (64-channel slabs, C_out 32 / 64) have a folded
+    form for - in Unet-resnet34 decoder.blocks.2 / 3 / 4 .conv1."""
+    if precision != "bf16" or conv_flags:
+        return False
+    if C_x == C_in:
+        return (C_in, C_out) in ((32, 16), (32, 32), (16, 16), (64, 32))
+    return C_x % 64 == 0 and (C_in - C_x) % 64 == 0 and C_out in (32, 64)
 
 
 class UnetEngine:
@@ -121,6 +131,7 @@ class UnetEngine:
             raise ValueError("classes must be 1..4")
         sd = {k: v.detach() for k, v in state_dict.items()}
         self.layers: Dict[str, FusedConv] = {}
+        self.folded: Dict[str, FusedConv] = {}      # up-sample layers in the DT_CONV_UPS_FOLDED packing
         self._build(sd)
         self._ws: Dict[tuple, Dict[str, torch.Tensor]] = {}
 
@@ -133,10 +144,10 @@ class UnetEngine:
             C_in = 4
         cx = C_in if C_x is None else C_x
         if upsample and folds_upsample(self.precision, C_in, cx, C_out, self.conv_flags):
-            self.layers[name] = FusedConv(name, C_in, cx, C_out, R, S, stride, pad, relu, upsample,
-                                          pack_weight_folded(w, self.device), scale, shift, 2 * C_in * R * S * C_out,
+            # used when the low-res grid tiles into 16 x 8 regions (folded_ok); the nine-tap packing below otherwise
+            self.folded[name] = FusedConv(name, C_in, cx, C_out, R, S, stride, pad, relu, upsample,
+                                          pack_weight_folded(w, self.device, cx), scale, shift, 2 * C_in * R * S * C_out,
                                           flags=CONV_UPS_FOLDED)
-            return
         self.layers[name] = FusedConv(name, C_in, cx, C_out, R, S, stride, pad, relu,
                                       upsample, pack_weight(w, self.precision, stem, self.device), scale, shift,
                                       2 * C_in * R * S * C_out)
@@ -178,13 +189,21 @@ class UnetEngine:
             self.head_b16 = b16.to(self.device)
 
     # ------------------------------------------------------------------------------------------
+    @staticmethod
+    def folded_ok(H: int, W: int) -> bool:
+        """the folded kernels walk 16 x 8 regions of the LOW-RES grid (H, W: the layer's output size)"""
+        return (H // 2) % 16 == 0 and (W // 2) % 8 == 0
+
     def _run(self, name, x, N, H, W, skip=None, residual=None, out=None, flags=0):
         L = self.layers[name]
+        if name in self.folded and self.folded_ok(H, W):
+            L = self.folded[name]
         return ops.conv2d(x, L.w, L.scale, L.shift, N=N, H=H, W=W, C_in=L.C_in, C_x=L.C_x, C_out=L.C_out, R=L.R,
                           S=L.S, stride=L.stride, pad=L.pad, relu=L.relu, skip=skip, upsample=L.upsample,
                           residual=residual, out=out, flags=self.conv_flags | flags | L.flags,
-                          algo_cin=self.in_channels if name == "stem" else (L.C_in * 4.0 / 9.0 if L.flags & CONV_UPS_FOLDED
-                                                                            else None), tag=name)   # FLOPs the tensor pipe executes
+                          algo_cin=self.in_channels if name == "stem" else (
+                              (L.C_x * 4.0 / 9.0 + (L.C_in - L.C_x)) if L.flags & CONV_UPS_FOLDED else None),
+                          tag=name)   # folded layers: the FLOPs the tensor pipe executes
 
     def _buf(self, ws, key, shape):
         t = ws.get(key)

@@ -125,12 +125,15 @@ enum {
                                patches (conv_halo.cu, the default where the shape fits) */
   DT_CONV_NO_QUAD = 32,     /* up-sample + concat layers with C_out <= 64: one parity class per tile instead of the
                                class-fused tiles that share the five patches of a region (same results; A/B testing) */
-  DT_CONV_UPS_FOLDED = 64,  /* up-sampled input without skip tensor, C_in and C_out <= 64: the nearest-x2 up-sampling is
-                               folded into the weights - for output parity class (a,b) the nine taps touch only the 2 x 2
-                               low-res pixels (a-1+ey, b-1+ex), and w is the per-class sum of the taps sharing a pixel,
-                               bf16 [C_out][16*C_in] with k = ((a*2+b)*4 + ey*2+ex)*C_in + ci (dt_pack_conv_weight
-                               mode 5).  Exact in real arithmetic; in bf16 the summed weight is rounded once instead of
-                               each tap's weight (4 instead of 9 tap-MMAs per class) */
+  DT_CONV_UPS_FOLDED = 64,  /* up-sampled input: the nearest-x2 up-sampling is folded into the weights of the x operand -
+                               for output parity class (a,b) the nine taps touch only the 2 x 2 low-res pixels
+                               (a-1+ey, b-1+ex), and w holds the per-class sum of the taps sharing a pixel: bf16
+                               [C_out][16*C_x + 9*C_s] with k = ((a*2+b)*4 + ey*2+ex)*C_x + ci for the x operand,
+                               followed by k = 16*C_x + tap*C_s + cs for the skip operand (C_s = C_in - C_x).  Exact in
+                               real arithmetic; in bf16 the summed weight is rounded once instead of each tap's weight
+                               (4 instead of 9 tap-MMAs per class).  Shapes: no skip, C_in <= 64, C_out <= 32
+                               (resident-weight kernel); with skip, C_x and C_s multiples of 64, C_out 32 or 64
+                               (class-fused kernel) */
   DT_CONV_TRANSPOSED = 16   /* data gradient of a stride-2 conv: desc.H, W = size of the OUTPUT (the conv's input), x = gy
                                (N, Ho, Wo, C_in) at the conv's output size, out[h][w] = sum over taps with (h + pad - r)
                                even of gy[(h + pad - r) / 2][..] * w; weights in the dt_conv2d_fwd packing with

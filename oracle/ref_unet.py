@@ -237,24 +237,33 @@ def fold_upsample_weights(w: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def _fused_upsample_folded(conv: nn.Conv2d, bn: nn.BatchNorm2d, x_low, relu=True):
-    """conv3x3(nearest_x2(x_low)) in the engine's folded arithmetic (DT_CONV_UPS_FOLDED): per output parity class a 2 x 2
-    convolution of the LOW-RES tensor with the summed weights rounded to bf16 once (exact in real arithmetic; the
-    unfolded form rounds each of the nine weights)."""
+def _fused_upsample_folded(conv: nn.Conv2d, bn: nn.BatchNorm2d, x_low, skip=None, relu=True):
+    """conv3x3(cat[nearest_x2(x_low), skip]) in the engine's folded arithmetic (DT_CONV_UPS_FOLDED): for the up-sampled
+    operand, per output parity class a 2 x 2 convolution of the LOW-RES tensor with the summed weights rounded to bf16 once
+    (exact in real arithmetic; the unfolded form rounds each of the nine weights); the skip operand as usual."""
     scale, shift = _fold(bn)
-    wf = _rb(fold_upsample_weights(conv.weight.float()))
+    Cx = x_low.shape[1]
+    wf = _rb(fold_upsample_weights(conv.weight[:, :Cx].float()))
     N, _, H, W = x_low.shape
     xp = F.pad(x_low, (1, 1, 1, 1))
     y = x_low.new_zeros(N, conv.weight.shape[0], 2 * H, 2 * W)
     for a in range(2):
         for b in range(2):
             y[:, :, a::2, b::2] = F.conv2d(xp[:, :, a: a + H + 1, b: b + W + 1], wf[:, :, a, b])
+    if skip is not None:
+        y = y + F.conv2d(skip, _rb(conv.weight[:, Cx:]), None, 1, 1)
     y = y * scale[None, :, None, None] + shift[None, :, None, None]
     return _rb(F.relu(y) if relu else y)
 
 
-# (C_in, C_out) of the up-sampled, skip-less layers the engine folds (deadtrees_b200/engine.py::folds_upsample)
-FOLDED_SHAPES = ((32, 16), (32, 32), (16, 16), (64, 32))
+def folds_upsample(C_in: int, C_x: int, C_out: int, H_low: int, W_low: int) -> bool:
+    """the up-sample layers the engine folds (deadtrees_b200/engine.py::folds_upsample + folded_ok, bf16 path): shapes with
+    a folded kernel, on low-res grids that tile into 16 x 8 regions"""
+    if H_low % 16 or W_low % 8:
+        return False
+    if C_x == C_in:
+        return (C_in, C_out) in ((32, 16), (32, 32), (16, 16), (64, 32))
+    return C_x % 64 == 0 and (C_in - C_x) % 64 == 0 and C_out in (32, 64)
 
 
 def forward_bf16(model: Unet, x: torch.Tensor) -> torch.Tensor:
@@ -275,8 +284,9 @@ def forward_bf16(model: Unet, x: torch.Tensor) -> torch.Tensor:
         y = skips[0]
         for i, blk in enumerate(model.decoder.blocks):
             c1 = blk.conv1[0]
-            if i + 1 >= len(skips) and (c1.in_channels, c1.out_channels) in FOLDED_SHAPES:
-                y = _fused_upsample_folded(c1, blk.conv1[1], y)      # no skip tensor: up-sampling folded into the weights
+            skip = skips[i + 1] if i + 1 < len(skips) else None
+            if folds_upsample(c1.in_channels, y.shape[1], c1.out_channels, y.shape[2], y.shape[3]):
+                y = _fused_upsample_folded(c1, blk.conv1[1], y, skip)    # up-sampling folded into the weights
             else:
                 y = F.interpolate(y, scale_factor=2, mode="nearest")
                 if i + 1 < len(skips):

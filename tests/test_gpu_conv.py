@@ -147,6 +147,37 @@ def test_conv_upsample_folded(N, H, Cx, Co):
     assert d <= 2.0 ** -5 * ref.abs().max().item()
 
 
+@pytest.mark.parametrize("N,H,Cx,Cs,Co", [(2, 64, 128, 64, 64), (1, 128, 64, 64, 32), (3, 32, 64, 64, 32), (1, 64, 64, 128, 64)])
+def test_conv_upsample_folded_with_skip(N, H, Cx, Cs, Co):
+    """DT_CONV_UPS_FOLDED on the class-fused kernel: folded x operand + nine-tap skip operand, against torch with the same
+    bf16 weights and against the unfolded class-fused kernel."""
+    g = torch.Generator().manual_seed(N + H + Cx + Cs)
+    x = torch.randn(N, Cx, H // 2, H // 2, generator=g)
+    skip = torch.randn(N, Cs, H, H, generator=g)
+    w = torch.randn(Co, Cx + Cs, 3, 3, generator=g) * (2.0 / ((Cx + Cs) * 9)) ** 0.5
+    scale, shift = 1.0 + 0.1 * torch.randn(Co, generator=g), 0.1 * torch.randn(Co, generator=g)
+    rb = lambda t: t.to(torch.bfloat16).float()
+    wf = rb(fold_upsample_weights(w[:, :Cx]))
+    Hl = H // 2
+    xp = F.pad(rb(x), (1, 1, 1, 1))
+    ref = torch.zeros(N, Co, H, H)
+    for a in range(2):
+        for b in range(2):
+            k = wf[:, a * 2 + b].reshape(Co, 2, 2, Cx).permute(0, 3, 1, 2)
+            ref[:, :, a::2, b::2] = F.conv2d(xp[:, :, a: a + Hl + 1, b: b + Hl + 1], k)
+    ref = ref + F.conv2d(rb(skip), rb(w[:, Cx:]), None, 1, 1)
+    ref = F.relu(ref * scale[None, :, None, None] + shift[None, :, None, None])
+    nhwc = lambda t: t.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).cuda()
+    kw = dict(N=N, H=H, W=H, C_in=Cx + Cs, C_x=Cx, C_out=Co, R=3, S=3, stride=1, pad=1, relu=True, upsample=True,
+              skip=nhwc(skip))
+    y_f = ops.conv2d(nhwc(x), pack_weight_folded(w, "cuda", Cx), scale.cuda(), shift.cuda(), flags=CONV_UPS_FOLDED, **kw)
+    y_9 = ops.conv2d(nhwc(x), pack_weight(w, "bf16", False, "cuda"), scale.cuda(), shift.cuda(), **kw)
+    torch.cuda.synchronize()
+    err, rel = report(f"folded up-sample+skip conv {Cx}+{Cs}->{Co} @{H}", to_nchw(y_f), ref)
+    assert rel < 1e-2
+    assert (to_nchw(y_f) - to_nchw(y_9)).abs().max().item() <= 2.0 ** -5 * ref.abs().max().item()
+
+
 def test_stem_tcgen05_and_fp32():
     g = torch.Generator().manual_seed(3)
     N, T, C = 2, 64, 3
