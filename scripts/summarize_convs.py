@@ -15,6 +15,7 @@ for i in range(5):
 LAYERS.append("head")
 
 src, dst, title = sys.argv[1:4]
+tiles = int(sys.argv[4]) if len(sys.argv) > 4 else 135
 rows = list(csv.reader(open(src)))
 hdr = rows[0]
 col = {h: i for i, h in enumerate(hdr)}
@@ -22,7 +23,7 @@ def g(r, name, default="nan"):
     i = col.get(name)
     return r[i] if i is not None and r[i] not in ("", "n/a") else default
 out = [f"# {title}",
-       "# per launch (48 consecutive launches re-ordered to start at the stem); ncu times are cold-cache / serialised (compare",
+       "# per launch (consecutive launches of one step re-ordered to start at the stem); ncu times are cold-cache / serialised (compare",
        "# shares); traffic = dram read + write;",
        "# tensor%act = sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
        f"{'layer':22s} {'kernel':38s} {'us':>7s} {'dram_rd_MB':>10s} {'dram_wr_MB':>10s} {'dram%':>6s} {'lts%':>6s} {'l1tex%':>6s} {'tensor%act':>10s} {'regs':>5s} {'grid':>6s}"]
@@ -47,7 +48,7 @@ for name, r in zip(LAYERS, data):
                f"{float(g(r, 'l1tex__throughput.avg.pct_of_peak_sustained_elapsed')):6.1f} "
                f"{float(g(r, 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active')):10.1f} "
                f"{g(r, 'launch__registers_per_thread'):>5s} {g(r, 'launch__grid_size'):>6s}")
-out.append(f"total {tot_us:.1f} us; dram read {tot_rd / 1e3:.3f} GB + write {tot_wr / 1e3:.3f} GB = {(tot_rd + tot_wr) / 1e3:.3f} GB per 135-tile batch "
-           f"({(tot_rd + tot_wr) / 135:.1f} MB per tile)")
+out.append(f"total {tot_us:.1f} us; dram read {tot_rd / 1e3:.3f} GB + write {tot_wr / 1e3:.3f} GB = {(tot_rd + tot_wr) / 1e3:.3f} GB per {tiles}-tile batch "
+           f"({(tot_rd + tot_wr) / tiles:.1f} MB per tile)")
 open(dst, "w").write("\n".join(out) + "\n")
 print("\n".join(out))
