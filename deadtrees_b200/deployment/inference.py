@@ -182,7 +182,9 @@ class MosaicInference:
         piped_out = host_out is not None and halo_hook is None
         # single GPU: the mask is stitched band by band as soon as the tile rows of a band are done - the logits a band
         # needs were written by the last batches and are still in L2 (a batch of 135 tiles holds 53 MB of logits)
-        banded = halo_hook is None
+        # (only while a batch's logits fit in L2; with larger batches one launch over the whole shard is faster)
+        banded = halo_hook is None and (piped_out or ov == 0 or
+                                        bt * T * T * eng.classes * logits.element_size() <= (96 << 20))
         if (piped_in or host_out is not None) and layout != "hwc":
             raise ValueError("the host pipeline takes interleaved (H, W, C) mosaics")
         main = torch.cuda.current_stream()

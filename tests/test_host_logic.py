@@ -226,3 +226,28 @@ def test_gradient_bucket_allreduce_gloo(world):
     """the N>1 training path on CPU: every rank ends with the mean gradient, buckets launched as they complete."""
     port = 31500 + (os.getpid() % 2000) + world
     mp.spawn(_reducer_worker, args=(world, port), nprocs=world, join=True)
+
+
+def test_fold_upsample_weights_identity():
+    """nearest-x2 up-sampling folded into per-class 2 x 2 weights (engine.fold_upsample_weights, DT_CONV_UPS_FOLDED; restated
+    in oracle/ref_unet.py) is the same convolution: float64, borders included."""
+    import torch.nn.functional as F
+    from deadtrees_b200.engine import fold_upsample_weights, pack_weight_folded
+    from oracle import ref_unet
+    g = torch.Generator().manual_seed(0)
+    w = torch.randn(5, 7, 3, 3, generator=g, dtype=torch.float64)
+    x = torch.randn(2, 7, 6, 9, generator=g, dtype=torch.float64)
+    ref = F.conv2d(F.interpolate(x, scale_factor=2, mode="nearest"), w, None, 1, 1)
+    wf = ref_unet.fold_upsample_weights(w)                       # (C_out, C_in, a, b, ey, ex)
+    N, _, H, W = x.shape
+    xp = F.pad(x, (1, 1, 1, 1))
+    y = torch.zeros_like(ref)
+    for a in range(2):
+        for b in range(2):
+            y[:, :, a::2, b::2] = F.conv2d(xp[:, :, a: a + H + 1, b: b + W + 1], wf[:, :, a, b])
+    assert (y - ref).abs().max().item() < 1e-12
+    # the engine's packing holds the same sums: [C_out][(class * 4 + e) * C_in + ci]
+    eng = fold_upsample_weights(w.float())                       # (C_out, class, e, C_in)
+    assert torch.equal(eng, ref_unet.fold_upsample_weights(w.float()).permute(0, 2, 3, 4, 5, 1).reshape(5, 4, 4, 7))
+    packed = pack_weight_folded(torch.randn(16, 96, 3, 3, generator=g), "cpu", 64)
+    assert packed.shape == (16, 16 * 64 + 9 * 32) and packed.dtype == torch.bfloat16
