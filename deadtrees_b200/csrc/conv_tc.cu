@@ -487,6 +487,8 @@ int dt_conv_stem(const dt_conv_desc* d, const void* x, const void* w, const floa
                  cudaStream_t s);
 int dt_conv_res(const dt_conv_desc* d, const void* x, const void* w, int Kpad, const float* scale, const float* shift,
                 const void* residual, void* y, cudaStream_t s);
+int dt_conv_pair(const dt_conv_desc* d, const void* x, const void* w, int Kpad, const float* scale, const float* shift,
+                 const void* residual, void* y, cudaStream_t s);
 
 extern "C" int dt_conv2d_fwd(const dt_conv_desc* d, const void* x, const void* skip, const void* w,
                              const float* scale, const float* shift, const void* residual, void* y,
@@ -558,6 +560,10 @@ extern "C" int dt_conv2d_fwd(const dt_conv_desc* d, const void* x, const void* s
   if (!(d->flags & (DT_CONV_NO_HALO | DT_CONV_FORCE_GATHER)) && !stem && !transposed) {
     const int rc0 = dt_conv_res(d, x, w, Kpad, scale, shift, residual, y, s);   // weights resident in smem
     if (rc0 != DT_ERR_UNSUPPORTED) return rc0;
+    if (d->flags & DT_CONV_PAIR) {      // wide layers on CTA pairs (tcgen05.mma.cta_group::2)
+      const int rcp = dt_conv_pair(d, x, w, Kpad, scale, shift, residual, y, s);
+      if (rcp != DT_ERR_UNSUPPORTED) return rcp;
+    }
     const int rc = dt_conv_halo(d, BN, x, skip, w, Kpad, scale, shift, residual, y, s);
     if (rc != DT_ERR_UNSUPPORTED) return rc;   // not a 3x3/s1 layer of a fitting shape: per-tap path below
   }

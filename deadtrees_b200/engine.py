@@ -13,7 +13,7 @@ from typing import Dict, List, Optional
 import torch
 
 from . import ops
-from ._lib import CONV_UPS_FOLDED, CONV_X_PAD3, require_device
+from ._lib import CONV_PAIR, CONV_UPS_FOLDED, CONV_X_PAD3, require_device
 
 BN_EPS = 1e-5
 RESNET34_LAYERS = (3, 4, 6, 3)
@@ -130,6 +130,10 @@ class UnetEngine:
         if not 1 <= classes <= 4:
             raise ValueError("classes must be 1..4")
         sd = {k: v.detach() for k, v in state_dict.items()}
+        # wide 3x3/s1 layers on CTA pairs (tcgen05.mma.cta_group::2) where the shape allows; the library falls back itself
+        import os
+        self.pair_flag = CONV_PAIR if (precision == "bf16" and not conv_flags and
+                                       os.environ.get("DT_CONV_PAIR", "1") != "0") else 0
         self.layers: Dict[str, FusedConv] = {}
         self.folded: Dict[str, FusedConv] = {}      # up-sample layers in the DT_CONV_UPS_FOLDED packing
         self._build(sd)
@@ -200,7 +204,7 @@ class UnetEngine:
             L = self.folded[name]
         return ops.conv2d(x, L.w, L.scale, L.shift, N=N, H=H, W=W, C_in=L.C_in, C_x=L.C_x, C_out=L.C_out, R=L.R,
                           S=L.S, stride=L.stride, pad=L.pad, relu=L.relu, skip=skip, upsample=L.upsample,
-                          residual=residual, out=out, flags=self.conv_flags | flags | L.flags,
+                          residual=residual, out=out, flags=self.conv_flags | flags | L.flags | self.pair_flag,
                           algo_cin=self.in_channels if name == "stem" else (
                               (L.C_x * 4.0 / 9.0 + (L.C_in - L.C_x)) if L.flags & CONV_UPS_FOLDED else None),
                           tag=name)   # folded layers: the FLOPs the tensor pipe executes

@@ -134,6 +134,9 @@ enum {
                                (4 instead of 9 tap-MMAs per class).  Shapes: no skip, C_in <= 64, C_out <= 32
                                (resident-weight kernel); with skip, C_x and C_s multiples of 64, C_out 32 or 64
                                (class-fused kernel) */
+  DT_CONV_PAIR = 128,       /* 3x3/s1 layers with C_in % 64 == 0, C_out % 128 == 0, H % 16 == 0, W % 16 == 0: CTA pairs
+                               (tcgen05.mma.cta_group::2, M = 256; conv_pair.cu) instead of the single-CTA halo kernel;
+                               same results */
   DT_CONV_TRANSPOSED = 16   /* data gradient of a stride-2 conv: desc.H, W = size of the OUTPUT (the conv's input), x = gy
                                (N, Ho, Wo, C_in) at the conv's output size, out[h][w] = sum over taps with (h + pad - r)
                                even of gy[(h + pad - r) / 2][..] * w; weights in the dt_conv2d_fwd packing with

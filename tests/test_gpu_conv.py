@@ -4,8 +4,8 @@ import torch
 import torch.nn.functional as F
 
 from deadtrees_b200 import ops
-from deadtrees_b200._lib import (CONV_FORCE_DIRECT, CONV_FORCE_GATHER, CONV_NO_HALO, CONV_NO_QUAD, CONV_UPS_FOLDED,
-                                 CONV_X_PAD3)
+from deadtrees_b200._lib import (CONV_FORCE_DIRECT, CONV_FORCE_GATHER, CONV_NO_HALO, CONV_NO_QUAD, CONV_PAIR,
+                                 CONV_UPS_FOLDED, CONV_X_PAD3)
 from deadtrees_b200.engine import fold_upsample_weights, pack_weight, pack_weight_folded
 from gpu_util import report, to_nchw
 
@@ -176,6 +176,29 @@ def test_conv_upsample_folded_with_skip(N, H, Cx, Cs, Co):
     err, rel = report(f"folded up-sample+skip conv {Cx}+{Cs}->{Co} @{H}", to_nchw(y_f), ref)
     assert rel < 1e-2
     assert (to_nchw(y_f) - to_nchw(y_9)).abs().max().item() <= 2.0 ** -5 * ref.abs().max().item()
+
+
+PAIR_CASES = [
+    ("pair 128->128 @32", 4, 32, 128, 0, 128, 3, 1, 1, False, False, True),
+    ("pair 256->256 @16 +res", 8, 16, 256, 0, 256, 3, 1, 1, False, True, True),
+    ("pair 128->256 @32", 3, 32, 128, 0, 256, 3, 1, 1, False, False, False),
+    ("pair 256->512 @16 (two channel tiles)", 5, 16, 256, 0, 512, 3, 1, 1, False, True, True),
+    ("pair 64->128 @48x48", 2, 48, 64, 0, 128, 3, 1, 1, False, False, True),
+]
+
+
+@pytest.mark.parametrize("case", PAIR_CASES, ids=[c[0] for c in PAIR_CASES])
+def test_conv_cta_pair(case):
+    """tcgen05.mma.cta_group::2 kernel (CTA pairs, M = 256): same K order as the single-CTA halo kernel - identical bits;
+    and against torch on the bf16-rounded operands."""
+    x, skip, w, scale, shift, residual = make_case(case, seed=3)
+    xb, sb, wb, rb = bf16_round(x, skip, w, residual)
+    ref = reference(case, xb, sb, wb, scale, shift, rb)
+    got_p = run_cuda(case, x, skip, w, scale, shift, residual, dtype=torch.bfloat16, flags=CONV_PAIR)
+    got_h = run_cuda(case, x, skip, w, scale, shift, residual, dtype=torch.bfloat16)
+    err, rel = report(case[0], got_p, ref)
+    assert rel < 1e-2
+    assert torch.equal(got_p, got_h)
 
 
 def test_stem_tcgen05_and_fp32():
