@@ -15,7 +15,7 @@ from typing import Dict, List, Optional
 import torch
 
 from . import ops
-from ._lib import CONV_TRANSPOSED, CONV_X_PAD3, require_device
+from ._lib import CONV_PAIR, CONV_TRANSPOSED, CONV_X_PAD3, require_device
 from .engine import RESNET34_LAYERS, RESNET34_PLANES
 from .parallel import GradBucketReducer, backward_param_order
 
@@ -63,6 +63,8 @@ class UnetTrainEngine:
         # bound by the bytes of that one tensor), so it stays opt-in
         self.bn_mask_from_y = os.environ.get("DT_BN_MASK_FROM_Y", "0") == "1"
         self.dgrad_s2_zero_insert = os.environ.get("DT_DGRAD_S2_ZERO_INSERT", "1") != "0"
+        # wide 3x3/s1 convolutions (forward and the data gradients run as forward convs) on CTA pairs where the shape fits
+        self.pair_flag = CONV_PAIR if (precision == "bf16" and os.environ.get("DT_CONV_PAIR", "1") != "0") else 0
 
     def set_process_group(self, group, world_size: Optional[int] = None, bucket_bytes: int = 25 << 20) -> None:
         order = backward_param_order(self.param_names)
@@ -102,7 +104,7 @@ class UnetTrainEngine:
         mode = 0 if self.precision == "fp32" else (2 if stem else 1)
         wp = self.packer.get((wname, mode, None), w, mode)
         return ops.conv2d(x, wp, self._ones, self._zeros, N=N, H=H, W=W, C_in=Cx, C_x=Cx, C_out=C_out, R=R, S=S,
-                          stride=stride, pad=pad, relu=False, algo_cin=C_in, tag="train." + wname)
+                          stride=stride, pad=pad, relu=False, algo_cin=C_in, flags=self.pair_flag, tag="train." + wname)
 
     def _conv_bn(self, tape: List, x: torch.Tensor, conv: str, bn: str, stride: int, pad: int, relu: bool = True,
                  residual: Optional[torch.Tensor] = None, frame: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -182,14 +184,15 @@ class UnetTrainEngine:
             # the data gradient of a stride-1 conv is a stride-1 conv of gy with the flipped, transposed weights
             wp = self.packer.get((wname, 3, Cg), w, 3, cout_pad=Cg)
             gx = ops.conv2d(gy, wp, self._ones, self._zeros, N=N, H=H, W=W, C_in=Cg, C_x=Cg, C_out=C_in, R=3, S=3, stride=1,
-                            pad=1, relu=False, residual=addend, tag="dgrad." + wname)
+                            pad=1, relu=False, residual=addend, flags=self.pair_flag, tag="dgrad." + wname)
         elif (tc and self.dgrad_s2_zero_insert and stride == 2 and ((R == 3 and pad == 1) or (R == 1 and pad == 0))
               and Cg % 64 == 0 and H == 2 * gy.shape[1] and W == 2 * gy.shape[2]):
             # stride-2 conv: zero-insert gy to the input resolution, then the stride-1 form on the fast halo / TMA kernels
             G = ops.zero_insert2x(gy)
             wp = self.packer.get((wname, 3, Cg), w, 3, cout_pad=Cg)
             gx = ops.conv2d(G, wp, self._ones, self._zeros, N=N, H=H, W=W, C_in=Cg, C_x=Cg, C_out=C_in, R=R, S=S, stride=1,
-                            pad=pad, relu=False, residual=addend, algo_cin=Cg // 4, tag="dgrad." + wname)   # algorithmic FLOPs
+                            pad=pad, relu=False, residual=addend, algo_cin=Cg // 4, flags=self.pair_flag,
+                            tag="dgrad." + wname)   # algo_cin: the algorithmic FLOPs
         elif tc and stride == 2 and ((R == 3 and pad == 1) or (R == 1 and pad == 0)) and Cg % 64 == 0 and Cg == C_out:
             # stride-2 conv: every output pixel gathers the taps whose source coordinate is even (gather producer)
             wp = self.packer.get((wname, 4, Cg), w, 4, cout_pad=Cg)
