@@ -81,9 +81,9 @@ def synthetic_mosaic(size: int, device, seed: int = 1234) -> torch.Tensor:
 
 def ncu_conv_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum of the conv launches of one 135-tile batch, from the committed
-    `ncu --set full` capture (profiles/r01_convs_ncu_full_v5.txt, scripts/gpu_profile2.sh) - not measured in this run."""
+    `ncu --set full` capture (profiles/r01_convs_ncu_full_v6.txt, scripts/gpu_profile2.sh) - not measured in this run."""
     import re
-    f = ROOT / "profiles" / "r01_convs_ncu_full_v5.txt"
+    f = ROOT / "profiles" / "r01_convs_ncu_full_v6.txt"
     if not f.exists():
         return None
     m = re.search(r"= ([0-9.]+) GB per (\d+)-tile batch", f.read_text())
@@ -373,7 +373,7 @@ def main_b200(a):
                 out["roofline"]["traffic"] = tr[0] / tr[1] * bt / tr[2]
                 out["roofline"]["traffic_source"] = (
                     f"ncu --set full capture of the {tr[2]} conv launches of one {tr[1]}-tile batch "
-                    f"(profiles/r01_convs_ncu_full_v5.txt): {tr[0] / 1e9:.3f} GB DRAM read + write per batch = "
+                    f"(profiles/r01_convs_ncu_full_v6.txt): {tr[0] / 1e9:.3f} GB DRAM read + write per batch = "
                     f"{tr[0] / tr[1] / 1e6:.1f} MB per tile; scaled to this run's {bt}-tile batches and averaged per "
                     f"launch; bf16 activations in + out of all convs, unfused: 44.6 MB per tile")
         hb = {}
