@@ -58,6 +58,9 @@ _SIGNATURES = {
     "dt_seg_loss_partials": ([_p, _p, _i, _i, _i, _i, _p, _p, _p, _p], C.c_int),
     "dt_seg_loss_finalize": ([_p, _p, _i, _i, _i, _i, _p, _p, _p, _p], C.c_int),
     "dt_seg_loss_backward": ([_p, _p, _i, _i, _i, _i, _p, _p, _f, _p, _p], C.c_int),
+    "dt_gwdl_workspace": ([_i, _i, _i], C.c_int64),
+    "dt_gwdl_loss": ([_p, _p, _i, _i, _i, _i, C.POINTER(_f), _i, _p, C.c_int64, _p, _p, _p], C.c_int),
+    "dt_gwdl_loss_backward": ([_p, _p, _i, _i, _i, _i, C.POINTER(_f), _i, _p, _f, _p, _p], C.c_int),
     "dt_one_hot2dist_workspace": ([_i, _i, _i, _i], C.c_int64),
     "dt_one_hot2dist": ([_p, _i, _i, _i, _i, _i, _p, _p, _i64, _p], C.c_int),
     "dt_boundary_loss": ([_p, _p, _i, _i, _i, _i, C.c_uint, _p, _p, _p], C.c_int),

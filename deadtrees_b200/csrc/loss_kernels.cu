@@ -242,6 +242,163 @@ __global__ void boundary_backward_kernel(const float* __restrict__ logits, const
   }
 }
 
+// Generalized Wasserstein Dice loss (deadtrees/loss/gwdl.py:84-138, weighting "default"), on what SemSegment.calculate_loss
+// hands it: the module is called with the SOFTMAX PROBABILITIES as `input` and applies softmax again itself
+// (segmodel.py:176-178, gwdl.py:104) - q = softmax(p), p = softmax(logits), reproduced here (`twice`).
+//   W[b,s]  = sum_c M[t][c] * q_c                      (Wasserstein distance to the label's class, M normalised to max 1)
+//   u[s]    = sum_j (1 - W[j,s])                       (over the samples of the batch)
+//   tp[b]   = sum_s alpha[b,s] * u[s],  alpha = 0 for the background class 0, 1 otherwise
+//   err[b]  = sum_s W[b,s];     loss = mean_b ( 1 - (2 tp + eps) / (2 tp + err + eps) ),  eps = 2^-52
+// The sum over j in tp is what the reference computes: compute_generalized_true_positive multiplies alpha (B, 1, S) with the
+// distance map (B, S), which broadcasts to (B, B, S), and sums over dims [1, 2] (gwdl.py:187-205); for B = 1 it is the
+// per-sample sum of the paper.  Passes: W map + err partials; u[s]; tp partials; finalize (loss, coef = {dL/dtp, dL/derr} and
+// the per-pixel backward term A[s] = sum_i dL/dtp_i * alpha[i,s]); backward: dL/dW[j,s] = dL/derr_j - A[s], through both softmaxes.
+struct GwdlMatrix { float m[KMAX * KMAX]; };
+
+template <int K>
+__device__ __forceinline__ void softmax_regs(const float (&z)[K], float (&p)[K]) {
+  float mx = z[0];
+#pragma unroll
+  for (int k = 1; k < K; ++k) mx = fmaxf(mx, z[k]);
+  float sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < K; ++k) { p[k] = expf(z[k] - mx); sum += p[k]; }
+  const float inv = 1.f / sum;
+#pragma unroll
+  for (int k = 0; k < K; ++k) p[k] *= inv;
+}
+
+// block-wide fixed-order sum of one float per thread into part[slot] (double)
+__device__ __forceinline__ void gwdl_block_sum(float v, double* __restrict__ dst) {
+  __shared__ double sh[kThreads];
+  sh[threadIdx.x] = static_cast<double>(v);
+  __syncthreads();
+  for (int o = kThreads / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *dst = sh[0];
+  __syncthreads();
+}
+
+// grid (chunks, N): omw[n][s] = 1 - W[n,s];  part[(n * chunks + c) * 2 + 1] = sum of W over the chunk
+template <int K>
+__global__ void gwdl_map_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels, int64_t HW,
+                                GwdlMatrix M, int twice, float* __restrict__ omw, double* __restrict__ part) {
+  const int n = blockIdx.y;
+  const float* zl = logits + static_cast<int64_t>(n) * K * HW;
+  const int64_t* ll = labels + static_cast<int64_t>(n) * HW;
+  float* ol = omw + static_cast<int64_t>(n) * HW;
+  float err = 0.f;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < HW;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float p[K], q[K];
+    softmax_px<K>(zl + i, HW, p);
+    if (twice) softmax_regs<K>(p, q);
+    const int t = static_cast<int>(ll[i]);
+    float W = 0.f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) W += M.m[(t < 0 || t >= K ? 0 : t) * K + k] * (twice ? q[k] : p[k]);
+    err += W;
+    ol[i] = 1.f - W;
+  }
+  gwdl_block_sum(err, part + (static_cast<int64_t>(n) * gridDim.x + blockIdx.x) * 2 + 1);
+}
+
+// u[s] = sum_j omw[j][s], in sample order
+__global__ void gwdl_batch_sum_kernel(const float* __restrict__ omw, int N, int64_t HW, float* __restrict__ u) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < HW;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float acc = 0.f;
+    for (int j = 0; j < N; ++j) acc += omw[static_cast<int64_t>(j) * HW + i];
+    u[i] = acc;
+  }
+}
+
+// grid (chunks, N): part[(n * chunks + c) * 2] = sum over the chunk of alpha[n,s] * u[s]
+__global__ void gwdl_tp_kernel(const int64_t* __restrict__ labels, const float* __restrict__ u, int64_t HW,
+                               double* __restrict__ part) {
+  const int n = blockIdx.y;
+  const int64_t* ll = labels + static_cast<int64_t>(n) * HW;
+  float tp = 0.f;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < HW;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    if (ll[i] != 0) tp += u[i];
+  gwdl_block_sum(tp, part + (static_cast<int64_t>(n) * gridDim.x + blockIdx.x) * 2);
+}
+
+// one block: per image the fixed-order sum of the chunk partials, the loss, and the backward coefficients
+// coef[2b] = d loss / d tp_b, coef[2b+1] = d loss / d err_b
+__global__ void gwdl_finalize_kernel(const double* __restrict__ part, int N, int chunks, float* __restrict__ loss,
+                                     float* __restrict__ coef) {
+  __shared__ float sh[kThreads];
+  float acc = 0.f;
+  const float eps = 2.220446049250313e-16f;
+  for (int b = threadIdx.x; b < N; b += kThreads) {
+    double tp = 0.0, err = 0.0;
+    for (int c = 0; c < chunks; ++c) { tp += part[(static_cast<int64_t>(b) * chunks + c) * 2]; err += part[(static_cast<int64_t>(b) * chunks + c) * 2 + 1]; }
+    const float ftp = static_cast<float>(tp), ferr = static_cast<float>(err);
+    const float num = 2.f * ftp + eps, den = 2.f * ftp + ferr + eps;
+    acc += 1.f - num / den;
+    coef[2 * b] = -(2.f * den - 2.f * num) / (den * den) / static_cast<float>(N);
+    coef[2 * b + 1] = num / (den * den) / static_cast<float>(N);
+  }
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = kThreads / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *loss = sh[0] / static_cast<float>(N);
+}
+
+// amap[s] = sum_i coef[2i] * alpha[i,s]  (what every sample's W[.,s] contributes to through the true-positive terms)
+__global__ void gwdl_alpha_map_kernel(const int64_t* __restrict__ labels, const float* __restrict__ coef, int N, int64_t HW,
+                                      float* __restrict__ amap) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < HW;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float acc = 0.f;
+    for (int j = 0; j < N; ++j)
+      if (labels[static_cast<int64_t>(j) * HW + i] != 0) acc += coef[2 * j];
+    amap[i] = acc;
+  }
+}
+
+template <int K>
+__global__ void gwdl_backward_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels, int64_t HW,
+                                     GwdlMatrix M, int twice, const float* __restrict__ coef, const float* __restrict__ amap,
+                                     float weight, float* __restrict__ grad) {
+  const int n = blockIdx.y;
+  const float* zl = logits + static_cast<int64_t>(n) * K * HW;
+  const int64_t* ll = labels + static_cast<int64_t>(n) * HW;
+  float* gl = grad + static_cast<int64_t>(n) * K * HW;
+  const float cb = coef[2 * n + 1];
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < HW;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float p[K], q[K], g[K];
+    softmax_px<K>(zl + i, HW, p);
+    if (twice) softmax_regs<K>(p, q);
+    const int t = static_cast<int>(ll[i]);
+    const float* row = M.m + (t < 0 || t >= K ? 0 : t) * K;
+    const float gW = weight * (cb - amap[i]);                         // d loss / d W[n,s]
+    if (twice) {
+      float W = 0.f;
+#pragma unroll
+      for (int k = 0; k < K; ++k) W += row[k] * q[k];
+#pragma unroll
+      for (int k = 0; k < K; ++k) g[k] = gW * q[k] * (row[k] - W);    // d loss / d p_k through q = softmax(p)
+    } else {
+#pragma unroll
+      for (int k = 0; k < K; ++k) g[k] = gW * row[k];
+    }
+    float dot = 0.f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) dot += g[k] * p[k];
+#pragma unroll
+    for (int k = 0; k < K; ++k) gl[k * HW + i] += p[k] * (g[k] - dot);  // through p = softmax(logits)
+  }
+}
+
 // ---- probability / one-hot API (the reference's loss callables take softmax output + one-hot) ----
 
 __global__ void one_hot_kernel(const int64_t* __restrict__ labels, int K, int64_t HW, int64_t total,
@@ -493,6 +650,85 @@ int dt_boundary_loss_backward(const float* logits, const float* dist, int N, int
     case 2: boundary_backward_kernel<2><<<grid, kThreads, 0, s>>>(logits, dist, HW, idc_mask, scale, grad_logits); break;
     case 3: boundary_backward_kernel<3><<<grid, kThreads, 0, s>>>(logits, dist, HW, idc_mask, scale, grad_logits); break;
     default: boundary_backward_kernel<4><<<grid, kThreads, 0, s>>>(logits, dist, HW, idc_mask, scale, grad_logits); break;
+  }
+  DT_LAUNCH_CHECK();
+  return DT_OK;
+}
+
+static int gwdl_chunks(int64_t HW) {
+  int chunks = static_cast<int>((HW + kThreads * 4 - 1) / (kThreads * 4));
+  return chunks > 64 ? 64 : (chunks < 1 ? 1 : chunks);
+}
+
+static bool gwdl_matrix(const float* dist_matrix, int K, GwdlMatrix* M) {
+  float mx = 0.f;
+  for (int i = 0; i < K * K; ++i) mx = dist_matrix[i] > mx ? dist_matrix[i] : mx;
+  if (!(mx > 0.f)) return false;
+  for (int i = 0; i < KMAX * KMAX; ++i) M->m[i] = i < K * K ? dist_matrix[i] / mx : 0.f;     // normalised to max 1 (gwdl.py:72-77)
+  return true;
+}
+
+// workspace: [2 * 64 * N doubles: chunk partials][N * HW floats: 1 - W][HW floats: u]
+int64_t dt_gwdl_workspace(int N, int H, int W) {
+  if (N <= 0 || H <= 0 || W <= 0) return 0;
+  const int64_t HW = static_cast<int64_t>(H) * W;
+  return static_cast<int64_t>(sizeof(double)) * 2 * 64 * N + static_cast<int64_t>(sizeof(float)) * (static_cast<int64_t>(N) + 1) * HW;
+}
+
+int dt_gwdl_loss(const float* logits, const int64_t* labels, int N, int K, int H, int W, const float* dist_matrix,
+                 int softmax_twice, void* workspace, int64_t workspace_bytes, float* loss_out, float* coef,
+                 dt_stream_t stream) {
+  DT_ARCH_GUARD();
+  DT_REQUIRE(N > 0 && N <= 65535 && H > 0 && W > 0 && K >= 2 && K <= KMAX && dist_matrix != nullptr, DT_ERR_BAD_SHAPE,
+             "dt_gwdl_loss: bad shape");
+  DT_REQUIRE(workspace != nullptr && workspace_bytes >= dt_gwdl_workspace(N, H, W), DT_ERR_BAD_SHAPE,
+             "dt_gwdl_loss: workspace smaller than dt_gwdl_workspace()");
+  GwdlMatrix M;
+  DT_REQUIRE(gwdl_matrix(dist_matrix, K, &M), DT_ERR_BAD_SHAPE,
+             "dt_gwdl_loss: the class distance matrix must have a positive maximum");
+  const int64_t HW = static_cast<int64_t>(H) * W;
+  const int chunks = gwdl_chunks(HW);
+  double* part = static_cast<double*>(workspace);
+  float* omw = reinterpret_cast<float*>(part + static_cast<size_t>(2) * 64 * N);
+  float* u = omw + static_cast<size_t>(N) * HW;
+  float* amap = coef + 2 * static_cast<size_t>(N);
+  dim3 grid(chunks, N);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (K) {
+    case 2: gwdl_map_kernel<2><<<grid, kThreads, 0, s>>>(logits, labels, HW, M, softmax_twice, omw, part); break;
+    case 3: gwdl_map_kernel<3><<<grid, kThreads, 0, s>>>(logits, labels, HW, M, softmax_twice, omw, part); break;
+    default: gwdl_map_kernel<4><<<grid, kThreads, 0, s>>>(logits, labels, HW, M, softmax_twice, omw, part); break;
+  }
+  DT_LAUNCH_CHECK();
+  gwdl_batch_sum_kernel<<<grid_for(HW), kThreads, 0, s>>>(omw, N, HW, u);
+  DT_LAUNCH_CHECK();
+  gwdl_tp_kernel<<<grid, kThreads, 0, s>>>(labels, u, HW, part);
+  DT_LAUNCH_CHECK();
+  gwdl_finalize_kernel<<<1, kThreads, 0, s>>>(part, N, chunks, loss_out, coef);
+  DT_LAUNCH_CHECK();
+  gwdl_alpha_map_kernel<<<grid_for(HW), kThreads, 0, s>>>(labels, coef, N, HW, amap);
+  DT_LAUNCH_CHECK();
+  return DT_OK;
+}
+
+int dt_gwdl_loss_backward(const float* logits, const int64_t* labels, int N, int K, int H, int W, const float* dist_matrix,
+                          int softmax_twice, const float* coef, float weight, float* grad_logits, dt_stream_t stream) {
+  DT_ARCH_GUARD();
+  DT_REQUIRE(N > 0 && N <= 65535 && H > 0 && W > 0 && K >= 2 && K <= KMAX && dist_matrix != nullptr && coef != nullptr,
+             DT_ERR_BAD_SHAPE, "dt_gwdl_loss_backward: bad shape");
+  GwdlMatrix M;
+  DT_REQUIRE(gwdl_matrix(dist_matrix, K, &M), DT_ERR_BAD_SHAPE,
+             "dt_gwdl_loss_backward: the class distance matrix must have a positive maximum");
+  const int64_t HW = static_cast<int64_t>(H) * W;
+  int chunks = static_cast<int>((HW + kThreads * 4 - 1) / (kThreads * 4));
+  if (chunks < 1) chunks = 1;
+  dim3 grid(chunks, N);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const float* amap = coef + 2 * static_cast<size_t>(N);
+  switch (K) {
+    case 2: gwdl_backward_kernel<2><<<grid, kThreads, 0, s>>>(logits, labels, HW, M, softmax_twice, coef, amap, weight, grad_logits); break;
+    case 3: gwdl_backward_kernel<3><<<grid, kThreads, 0, s>>>(logits, labels, HW, M, softmax_twice, coef, amap, weight, grad_logits); break;
+    default: gwdl_backward_kernel<4><<<grid, kThreads, 0, s>>>(logits, labels, HW, M, softmax_twice, coef, amap, weight, grad_logits); break;
   }
   DT_LAUNCH_CHECK();
   return DT_OK;

@@ -47,6 +47,8 @@ class _SegLossFn(torch.autograd.Function):
         total = terms.total_loss.clone()
         if terms.boundary is not None:
             total = total + terms.boundary_weight * terms.boundary
+        if terms.gwdl is not None:
+            total = total + terms.gwdl
         return total
 
     @staticmethod
@@ -55,11 +57,13 @@ class _SegLossFn(torch.autograd.Function):
         grad = t.grad_logits(1.0)
         if t.boundary is not None:
             ops.boundary_loss_backward(t.logits, t.distmap, t.boundary_idc, t.boundary_weight, grad)
+        if t.gwdl is not None:
+            ops.gwdl_loss_backward(t.logits, t.labels, t.gwdl_matrix, t.gwdl_coef, 1.0, grad, softmax_twice=True)
         return grad.mul_(g), None
 
 
 def seg_loss(logits: torch.Tensor, labels: torch.Tensor, dice_mode: int, use_focal: bool, distmap: torch.Tensor = None,
-             boundary_idc=None, boundary_weight: float = 1.0):
+             boundary_idc=None, boundary_weight: float = 1.0, gwdl_matrix=None):
     """-> (differentiable total loss, SegLossTerms with the individual scalars and metrics).  With ``distmap`` the
     boundary loss over the classes ``boundary_idc`` is added with ``boundary_weight`` (1, or alpha when ramped)."""
     terms = SegLossTerms(logits.detach(), labels, dice_mode, use_focal)
@@ -68,4 +72,8 @@ def seg_loss(logits: torch.Tensor, labels: torch.Tensor, dice_mode: int, use_foc
         terms.distmap = distmap.float().contiguous()
         terms.boundary_idc, terms.boundary_weight = list(boundary_idc), float(boundary_weight)
         terms.boundary = ops.boundary_loss(terms.logits, terms.distmap, terms.boundary_idc)
+    terms.gwdl = None
+    if gwdl_matrix is not None:      # GWDICE replaces the Dice term (dice_mode 0): Wasserstein Dice on softmax(softmax(logits))
+        terms.gwdl_matrix = gwdl_matrix
+        terms.gwdl, terms.gwdl_coef = ops.gwdl_loss(terms.logits, terms.labels, gwdl_matrix, softmax_twice=True)
     return _SegLossFn.apply(logits, terms), terms

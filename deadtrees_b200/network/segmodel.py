@@ -22,6 +22,7 @@ from torch import Tensor
 from .. import ops
 from ..loss import fused
 from ..loss.gdl import GeneralizedDiceLoss
+from ..loss.gwdl import GeneralizedWassersteinDiceLoss
 from ..loss.losses import BoundaryLoss, DiceLoss, FocalLoss, class2one_hot
 from .unet import Unet
 
@@ -139,7 +140,11 @@ class SemSegment(_Base):  # type: ignore[misc]
             if comp == "GDICE":
                 self.dice_loss = GeneralizedDiceLoss()
             elif comp == "GWDICE":
-                raise NotImplementedError("GWDICE is a next-tier loss (SURVEY.md §8f-2), not built yet")
+                import numpy as np
+                dist_mat = np.array([[0.0, 1.0, 1.0], [1.0, 0.0, 0.5], [1.0, 0.5, 0.0]])      # segmodel.py:119
+                if n_classes == 2:      # the reference tests `self.classes_int == 2` (list vs int, never true) and then fails
+                    dist_mat = dist_mat[0:2, 0:2]      # on the 3 x 3 matrix; the 2 x 2 cut it intends is applied here
+                self.dice_loss = GeneralizedWassersteinDiceLoss(dist_matrix=dist_mat)
             elif comp == "DICE":
                 self.dice_loss = DiceLoss(idc=self.classes_int_wout_bg)
             elif comp == "FOCAL":
@@ -178,15 +183,23 @@ class SemSegment(_Base):  # type: ignore[misc]
         return self.model(x)
 
     # -- fused loss + metric ---------------------------------------------------------------------
+    def _dice_mode(self) -> int:
+        """dice term of the fused loss kernels: 1 DiceLoss, 2 GeneralizedDiceLoss, 0 none (GWDICE has its own kernels)"""
+        if isinstance(self.dice_loss, GeneralizedWassersteinDiceLoss):
+            return 0
+        return 2 if isinstance(self.dice_loss, GeneralizedDiceLoss) else 1
+
     def _fused_terms(self, logits: Tensor, mask: Tensor):
-        dice_mode = 2 if isinstance(self.dice_loss, GeneralizedDiceLoss) else 1
-        return fused.SegLossTerms(logits, mask, dice_mode=dice_mode, use_focal=self.focal_loss is not None)
+        return fused.SegLossTerms(logits, mask, dice_mode=self._dice_mode(), use_focal=self.focal_loss is not None)
 
     def calculate_loss(self, y_hat: Tensor, y: Tensor, stage: str, distmap: Optional[Tensor] = None) -> Tensor:
         """compound loss on probabilities + one-hot, as ``segmodel.py:169-200`` (API-compatible path)."""
         loss = 0
         if self.dice_loss:
-            loss_gd = self.dice_loss(y_hat, y)
+            if isinstance(self.dice_loss, GeneralizedWassersteinDiceLoss):
+                loss_gd = self.dice_loss(y_hat, torch.argmax(y, dim=1))      # "hack to make gwdice work" (segmodel.py:176-178)
+            else:
+                loss_gd = self.dice_loss(y_hat, y)
             if torch.isnan(loss_gd) or torch.isinf(loss_gd):
                 log.warning("Train dice loss is NaN! What is going on?")
             self.log(f"{stage}/dice_loss", loss_gd, on_step=False, on_epoch=True)
@@ -207,8 +220,10 @@ class SemSegment(_Base):  # type: ignore[misc]
         logits = self.model(img)
         terms = self._fused_terms(logits, mask)
         terms.check_labels()  # class2one_hot's assert (losses.py:129)
-        self.log(f"{stage}/dice_loss", terms.dice_loss)
         loss = terms.dice_loss
+        if isinstance(self.dice_loss, GeneralizedWassersteinDiceLoss):
+            loss = self.dice_loss.on_logits(logits, mask)
+        self.log(f"{stage}/dice_loss", loss)
         if self.boundary_loss and distmap is not None:
             y_hat = fused.softmax_nchw(logits)
             loss_bd = self.boundary_loss(y_hat, distmap)
@@ -227,14 +242,15 @@ class SemSegment(_Base):  # type: ignore[misc]
         differentiable: ``loss.backward()`` runs the CUDA backward pass and fills ``.grad`` of every parameter."""
         img, mask, distmap, _, stats = create_combined_batch(batch)
         logits = self.model(img)
-        dice_mode = 2 if isinstance(self.dice_loss, GeneralizedDiceLoss) else 1
         use_bd = bool(self.boundary_loss) and distmap is not None
-        loss, terms = fused.seg_loss(logits, mask, dice_mode, self.focal_loss is not None,
+        gw = isinstance(self.dice_loss, GeneralizedWassersteinDiceLoss)
+        loss, terms = fused.seg_loss(logits, mask, self._dice_mode(), self.focal_loss is not None,
                                      distmap=distmap if use_bd else None,
                                      boundary_idc=self.boundary_loss.idc if use_bd else None,
-                                     boundary_weight=self.alpha if self.boundary_loss_ramped else 1.0)
+                                     boundary_weight=self.alpha if self.boundary_loss_ramped else 1.0,
+                                     gwdl_matrix=self.dice_loss.matrix() if gw else None)
         terms.check_labels()  # class2one_hot's assert (losses.py:129); also the host sync the reference has there
-        self.log("train/dice_loss", terms.dice_loss, on_step=False, on_epoch=True)
+        self.log("train/dice_loss", terms.gwdl if gw else terms.dice_loss, on_step=False, on_epoch=True)
         if use_bd:
             self.log("train/boundary_loss", terms.boundary, on_step=False, on_epoch=True)
         if self.focal_loss:

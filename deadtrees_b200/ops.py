@@ -273,6 +273,37 @@ def _idc_mask(idc, K: int) -> int:
     return m
 
 
+def gwdl_loss(logits: torch.Tensor, labels: torch.Tensor, dist_matrix, softmax_twice: bool = True):
+    """Generalized Wasserstein Dice loss on the logits -> (loss 0-dim fp32, coef (2N + HW,) for gwdl_loss_backward)."""
+    logits, labels = _cuda(logits, "logits").contiguous(), _cuda(labels, "labels").contiguous()
+    if labels.dtype != torch.int64:
+        labels = labels.long()
+    N, K, H, W = logits.shape
+    flat = [float(v) for row in dist_matrix for v in row]
+    if len(flat) != K * K:
+        raise ValueError(f"class distance matrix must be {K} x {K}")
+    M = (C.c_float * (K * K))(*flat)
+    lib = load()
+    need = lib.dt_gwdl_workspace(N, H, W)
+    ws = torch.empty((need + 7) // 8, dtype=torch.float64, device=logits.device)
+    loss = torch.empty((), dtype=torch.float32, device=logits.device)
+    coef = torch.empty(2 * N + H * W, dtype=torch.float32, device=logits.device)
+    check(lib.dt_gwdl_loss(logits.data_ptr(), labels.data_ptr(), N, K, H, W, M, int(softmax_twice), ws.data_ptr(), need,
+                           loss.data_ptr(), coef.data_ptr(), stream_ptr()))
+    return loss, coef
+
+
+def gwdl_loss_backward(logits: torch.Tensor, labels: torch.Tensor, dist_matrix, coef: torch.Tensor, weight: float,
+                       grad_logits: torch.Tensor, softmax_twice: bool = True) -> None:
+    """grad_logits += weight * d(gwdl_loss)/d(logits)"""
+    N, K, H, W = logits.shape
+    M = (C.c_float * (K * K))(*[float(v) for row in dist_matrix for v in row])
+    if labels.dtype != torch.int64:
+        labels = labels.long()
+    check(load().dt_gwdl_loss_backward(logits.data_ptr(), labels.contiguous().data_ptr(), N, K, H, W, M, int(softmax_twice),
+                                       coef.data_ptr(), float(weight), grad_logits.data_ptr(), stream_ptr()))
+
+
 def one_hot2dist(labels: torch.Tensor, K: int, truncate: bool = True) -> torch.Tensor:
     """(N, H, W) int64 labels -> (N, K, H, W) fp32 signed distance maps of the boundary loss (the dataloader's
     one_hot2dist per sample); ``truncate``: integer truncation of the reference's int32 path."""

@@ -15,7 +15,7 @@ from typing import Dict
 import torch
 
 from .loss.fused import SegLossTerms
-from .loss.gdl import GeneralizedDiceLoss
+from . import ops
 from .optim import FusedAdam
 
 
@@ -30,7 +30,8 @@ class GraphedTrainStep:
         # data parallel: the bucketed NCCL all-reduces run on the reducer's side stream, which forks from and joins the
         # capturing stream through events, so they become nodes of the same graph (every rank captures the same sequence)
         dev = self.engine.device
-        self.dice_mode = 2 if isinstance(seg.dice_loss, GeneralizedDiceLoss) else 1
+        self.dice_mode = seg._dice_mode()
+        self.gwdl_matrix = seg.dice_loss.matrix() if self.dice_mode == 0 and seg.dice_loss is not None else None
         self.use_focal = seg.focal_loss is not None
         cin = seg.model.in_channels
         self.img = torch.zeros((batch, cin, tile, tile), dtype=torch.float32, device=dev)
@@ -70,8 +71,14 @@ class GraphedTrainStep:
         with torch.no_grad():
             logits, tape = self.engine.forward(self.img)
             self.terms = SegLossTerms(logits, self.mask, self.dice_mode, self.use_focal)
-            grads = self.engine.backward(tape, self.terms.grad_logits(1.0))
-            self.opt.step(loss=self.terms.out[2:3])         # skipped on the device when the loss is not finite
+            g_logits = self.terms.grad_logits(1.0)
+            self.total = self.terms.out[2:3]
+            if self.gwdl_matrix is not None:           # GWDICE: Wasserstein Dice term next to the focal term
+                self.gwdl, coef = ops.gwdl_loss(self.terms.logits, self.terms.labels, self.gwdl_matrix, softmax_twice=True)
+                ops.gwdl_loss_backward(self.terms.logits, self.terms.labels, self.gwdl_matrix, coef, 1.0, g_logits, softmax_twice=True)
+                self.total = self.total + self.gwdl
+            grads = self.engine.backward(tape, g_logits)
+            self.opt.step(loss=self.total)                  # skipped on the device when the loss is not finite
         for n, p in self.engine.params.items():
             p.grad = grads[n]
 
@@ -80,7 +87,7 @@ class GraphedTrainStep:
         self.img.copy_(img, non_blocking=True)
         self.mask.copy_(mask, non_blocking=True)
         self.graph.replay()
-        return self.terms.total_loss
+        return self.total[0]
 
     def prefetch(self, img: torch.Tensor, mask: torch.Tensor) -> None:
         """starts the upload of the NEXT batch (pinned host tensors) into staging buffers on a copy stream; it runs
@@ -109,12 +116,12 @@ class GraphedTrainStep:
         self._stage_free.record(main)
         self._staged = False
         self.graph.replay()
-        return self.terms.total_loss
+        return self.total[0]
 
     def check(self) -> float:
         """host-side checks of the last replayed step (one synchronisation): label range, finite loss."""
         self.terms.check_labels()
-        loss = float(self.terms.total_loss)
+        loss = float(self.total[0])
         if loss != loss or loss in (float("inf"), float("-inf")):
             import logging
             logging.getLogger(__name__).warning("Train loss is NaN! What is going on? (optimizer step skipped)")
@@ -122,5 +129,6 @@ class GraphedTrainStep:
 
     def log_terms(self) -> Dict[str, torch.Tensor]:
         t = self.terms
-        return {"train/dice_loss": t.dice_loss, "train/focal_loss": t.focal_loss, "train/total_loss": t.total_loss,
+        return {"train/dice_loss": self.gwdl if self.gwdl_matrix is not None else t.dice_loss,
+                "train/focal_loss": t.focal_loss, "train/total_loss": self.total[0],
                 "train/dice": t.fscore, "train/dice_with_bg": t.fscore_with_bg}

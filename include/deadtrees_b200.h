@@ -197,6 +197,20 @@ int dt_seg_loss_finalize(const double* sums, const int64_t* counts, int N, int K
 int dt_seg_loss_backward(const float* logits, const int64_t* labels, int N, int K, int H, int W, const float* coef,
                          const float* focal_scale, float upstream, float* grad_logits, dt_stream_t stream);
 
+/* Generalized Wasserstein Dice loss, weighting "default" (deadtrees/loss/gwdl.py:84-138; "GWDICE" in SemSegment,
+ * segmodel.py:118-124, 176-178).  logits (N, K, H, W) fp32, labels (N, H, W) int64, dist_matrix: HOST float[K*K] class
+ * distances (normalised to a maximum of 1 as the module does).  softmax_twice != 0 reproduces the reference call path, which
+ * hands the module softmax probabilities that it soft-maxes again.  As in the reference, the "generalised true positives"
+ * of a sample sum (1 - W) over ALL samples of the batch (the (B,1,S) x (B,S) broadcast of gwdl.py:187-205).
+ * loss_out: float[1]; coef: float[2*N + H*W] backward terms consumed by dt_gwdl_loss_backward, which ADDS
+ * weight * d(loss)/d(logits) to grad_logits.  workspace: dt_gwdl_workspace(N, H, W) bytes. */
+int64_t dt_gwdl_workspace(int N, int H, int W);
+int dt_gwdl_loss(const float* logits, const int64_t* labels, int N, int K, int H, int W, const float* dist_matrix,
+                 int softmax_twice, void* workspace, int64_t workspace_bytes, float* loss_out, float* coef,
+                 dt_stream_t stream);
+int dt_gwdl_loss_backward(const float* logits, const int64_t* labels, int N, int K, int H, int W, const float* dist_matrix,
+                          int softmax_twice, const float* coef, float weight, float* grad_logits, dt_stream_t stream);
+
 /* The dataloader's signed distance maps for the boundary loss (one_hot2dist, deadtrees/loss/losses.py:159-178, called at
  * deadtrees/data/deadtreedata.py:182-185): labels (N, H, W) int64 -> out (N, K, H, W) fp32 with, for every class k that has
  * a pixel in image n, edt(not k) outside the class and -(edt(k) - 1) inside it (scipy's exact Euclidean distance transform,

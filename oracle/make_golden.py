@@ -28,6 +28,7 @@ def main():
     dh = load("ref_data_handling", "deadtrees/utils/data_handling.py")
     losses = load("ref_losses_mod", "deadtrees/loss/losses.py")
     gdl = load("ref_gdl_mod", "deadtrees/loss/gdl.py")
+    gwdl = load("ref_gwdl_mod", "deadtrees/loss/gwdl.py")
 
     # ---- tiler: make/unmake blocks on seeded arrays (incl. the reference's own test vector) -------
     rng = np.random.default_rng(1234)
@@ -69,6 +70,20 @@ def main():
             z = logits.clone().requires_grad_(True)
             fn(z.softmax(dim=1)).backward()
             out[f"grad_{name}{i}"] = z.grad.numpy()
+        # Generalized Wasserstein Dice loss as SemSegment builds and calls it (segmodel.py:118-124, 176-178): on the
+        # PROBABILITIES (soft-maxed again inside) and directly on scores; gradients w.r.t. the logits through autograd
+        dist_mat = np.array([[0.0, 1.0, 1.0], [1.0, 0.0, 0.5], [1.0, 0.5, 0.0]])
+        if K == 2:
+            dist_mat = dist_mat[0:2, 0:2]
+        gw = gwdl.GeneralizedWassersteinDiceLoss(dist_matrix=dist_mat)
+        for name, pre in (("gwdl_probs", lambda z: z.softmax(dim=1)), ("gwdl_scores", lambda z: z)):
+            z = logits.clone().requires_grad_(True)
+            val = gw(pre(z), torch.argmax(onehot, dim=1))
+            val.backward()
+            out[f"{name}{i}"], out[f"grad_{name}{i}"] = val.detach().numpy(), z.grad.numpy()
+    # a 3-class matrix whose maximum is not 1 (normalised by the constructor, gwdl.py:73-78)
+    gw = gwdl.GeneralizedWassersteinDiceLoss(dist_matrix=np.array([[0.0, 2.0, 4.0], [2.0, 0.0, 1.0], [4.0, 1.0, 0.0]]))
+    out["gwdl_unnorm0"] = gw(torch.from_numpy(out["logits0"]), torch.from_numpy(out["mask0"])).numpy()
     out["ncases"] = np.int64(3)
     np.savez_compressed(OUT / "losses.npz", **out)
 

@@ -172,7 +172,8 @@ def _grad_errors(params, ref_grads):
     return out
 
 
-@pytest.mark.parametrize("cin,n,T,losses", [(4, 2, 64, ["DICE", "FOCAL"]), (3, 2, 64, ["GDICE", "FOCAL"])])
+@pytest.mark.parametrize("cin,n,T,losses", [(4, 2, 64, ["DICE", "FOCAL"]), (3, 2, 64, ["GDICE", "FOCAL"]),
+                                            (4, 2, 64, ["GWDICE", "FOCAL"])])
 def test_training_step_fp32_matches_autograd(cin, n, T, losses):
     """fp32 check mode against float64 autograd of the oracle.  Tolerance: torch's own fp32 CPU autograd differs from
     float64 by up to 1.6e-2 (max-abs / max) on these gradients - ReLU masks flip on pre-activations within rounding
@@ -187,6 +188,9 @@ def test_training_step_fp32_matches_autograd(cin, n, T, losses):
     if "GDICE" in losses:
         from deadtrees_b200.loss.gdl import GeneralizedDiceLoss
         seg.dice_loss = GeneralizedDiceLoss()
+    if "GWDICE" in losses:      # segmodel.py:118-124
+        from deadtrees_b200.loss.gwdl import GeneralizedWassersteinDiceLoss
+        seg.dice_loss = GeneralizedWassersteinDiceLoss(dist_matrix=np.array([[0.0, 1.0, 1.0], [1.0, 0.0, 0.5], [1.0, 0.5, 0.0]]))
     batch = {"main": (img.cuda(), mask.cuda(), None, torch.zeros(n), [{"file": f"t{i}"} for i in range(n)])}
     loss = seg.training_step(batch, 0)
     assert abs(float(loss.detach()) - ref["loss"]) < 1e-5 * max(1.0, abs(ref["loss"]))
@@ -522,7 +526,8 @@ def test_training_step_with_boundary_loss(losses, ramped):
     assert worst[1][0] < 2e-2 and min(v[1] for v in errs.values()) > 0.999
 
 
-def test_graphed_training_step_equals_eager():
+@pytest.mark.parametrize("loss_names", [["DICE", "FOCAL"], ["GWDICE", "FOCAL"]])
+def test_graphed_training_step_equals_eager(loss_names):
     """the whole step replayed from one CUDA graph (deadtrees_b200/train_graph.py) against the same step launched kernel
     by kernel: three steps, the graph fed once through __call__ and twice through the prefetch pipeline.  The losses
     must agree to the last bit; the parameters to 1e-6 (the head's bias gradient and the gradient norm of the clip are
@@ -536,7 +541,7 @@ def test_graphed_training_step_equals_eager():
     stats = [{"file": f"t{i}"} for i in range(n)]
     segs, losses = [], []
     for graphed in (False, True):
-        seg = SemSegment(dict(NETWORK, in_channels=cin, precision="bf16"), dict(TRAINING, gradient_clip_val=0.5))
+        seg = SemSegment(dict(NETWORK, in_channels=cin, precision="bf16", losses=loss_names), dict(TRAINING, gradient_clip_val=0.5))
         seg.model.load_state_dict(oracle.state_dict())
         seg.cuda().train()
         (opt,), _ = seg.configure_optimizers()

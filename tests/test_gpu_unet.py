@@ -163,7 +163,7 @@ def test_ensemble_inference_api(tmp_path):
 
 def test_semsegment_val_step_losses():
     model = oracle_model(3, 3)
-    for losses in (["DICE", "FOCAL"], ["GDICE", "FOCAL"]):
+    for losses in (["DICE", "FOCAL"], ["GDICE", "FOCAL"], ["GWDICE", "FOCAL"]):
         m = SemSegment(dict(NETWORK, losses=losses, precision="fp32"), TRAINING).cuda().eval()
         m.model.load_state_dict(model.state_dict())
         _, x = normalized_tiles(2, 64, 3)

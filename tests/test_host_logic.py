@@ -59,6 +59,12 @@ def test_semsegment_constructor_contract():
         SemSegment(dict(NETWORK, losses=["DICE", "BANANA"]), TRAINING)
     with pytest.raises(AssertionError):
         SemSegment(dict(NETWORK, losses=["FOCAL"]), TRAINING)  # a dice-type loss is required
+    # GWDICE: the reference's class distances (segmodel.py:118-124), cut to 2 x 2 for two classes (what its never-true
+    # `self.classes_int == 2` test intends); as in the reference the last dice-type entry of the list wins
+    gw = SemSegment(dict(NETWORK, losses=["GWDICE", "FOCAL"]), TRAINING)
+    assert gw.dice_loss.matrix() == [[0.0, 1.0, 1.0], [1.0, 0.0, 0.5], [1.0, 0.5, 0.0]] and gw._dice_mode() == 0
+    assert SemSegment(dict(NETWORK, classes=["a", "b"], losses=["GWDICE"]), TRAINING).dice_loss.matrix() == [[0.0, 1.0], [1.0, 0.0]]
+    assert SemSegment(dict(NETWORK, losses=["GWDICE", "DICE"]), TRAINING)._dice_mode() == 1
 
 
 def test_checkpoint_roundtrip(tmp_path):

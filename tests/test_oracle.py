@@ -84,6 +84,18 @@ def test_losses_against_reference_outputs(golden_dir):
         np.testing.assert_allclose(ref_losses.generalized_dice_loss(probs, onehot), g[f"gdl{i}"], rtol=1e-6, atol=1e-7)
         np.testing.assert_allclose(ref_losses.surface_loss(probs, torch.from_numpy(g[f"dist{i}"]), fg),
                                    g[f"surface{i}"], rtol=1e-5, atol=1e-7)
+        # Generalized Wasserstein Dice loss: on the probabilities (SemSegment's call) and on raw scores, value + gradient
+        D = [[0.0, 1.0, 1.0], [1.0, 0.0, 0.5], [1.0, 0.5, 0.0]]
+        D = [r[:K] for r in D[:K]]
+        for name, pre in (("gwdl_probs", lambda z: z.softmax(dim=1)), ("gwdl_scores", lambda z: z)):
+            z = logits.clone().requires_grad_(True)
+            val = ref_losses.gwdl_loss(pre(z), mask, D)
+            val.backward()
+            np.testing.assert_allclose(val.item(), g[f"{name}{i}"], rtol=1e-12)
+            np.testing.assert_allclose(z.grad.numpy(), g[f"grad_{name}{i}"], rtol=1e-5, atol=1e-9)
+        np.testing.assert_allclose(ref_losses.calculate_loss(probs, onehot, ["GWDICE"])["total_loss"].item(), g[f"gwdl_probs{i}"], rtol=1e-12)
+    np.testing.assert_allclose(ref_losses.gwdl_loss(torch.from_numpy(g["logits0"]), torch.from_numpy(g["mask0"]),
+                                                    [[0.0, 2.0, 4.0], [2.0, 0.0, 1.0], [4.0, 1.0, 0.0]]).item(), g["gwdl_unnorm0"], rtol=1e-12)
 
 
 def test_class2one_hot_rejects_out_of_range():
