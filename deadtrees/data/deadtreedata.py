@@ -1,1 +1,2 @@
-from deadtrees_b200.data.deadtreedata import DeadtreeDatasetConfig, val_transform  # noqa: F401
+from deadtrees_b200.data.deadtreedata import (DeadtreeDatasetConfig, BatchTrainTransform, train_transform, transform,  # noqa: F401
+                                               val_transform)

@@ -61,6 +61,8 @@ _SIGNATURES = {
     "dt_gwdl_workspace": ([_i, _i, _i], C.c_int64),
     "dt_gwdl_loss": ([_p, _p, _i, _i, _i, _i, C.POINTER(_f), _i, _p, C.c_int64, _p, _p, _p], C.c_int),
     "dt_gwdl_loss_backward": ([_p, _p, _i, _i, _i, _i, C.POINTER(_f), _i, _p, _f, _p, _p], C.c_int),
+    "dt_train_transform": ([_p, _p, _p, _i, _i, _i, _i, _i, _p, _p, C.POINTER(_f), C.POINTER(_f), _i, _p, _p, _p, _p, _p], C.c_int),
+    "dt_confusion_matrix": ([_p, _i, _p, _p, _i, C.c_int64, _i, _p, _p, _p], C.c_int),
     "dt_one_hot2dist_workspace": ([_i, _i, _i, _i], C.c_int64),
     "dt_one_hot2dist": ([_p, _i, _i, _i, _i, _i, _p, _p, _i64, _p], C.c_int),
     "dt_boundary_loss": ([_p, _p, _i, _i, _i, _i, C.c_uint, _p, _p, _p], C.c_int),

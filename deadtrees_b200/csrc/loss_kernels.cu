@@ -399,6 +399,39 @@ __global__ void gwdl_backward_kernel(const float* __restrict__ logits, const int
   }
 }
 
+// ---- confusion matrices of the validation / test epoch (segmodel.py:291-407) ----
+// counts[0][t][p]: every pixel; counts[1][t][p]: pixels of the forest mask (lu == 1), the reference's "masked" matrices
+// (torchmetrics confusion_matrix = bincount(target * K + pred), rows = target).  Integer histogram: per-warp private
+// counters in shared memory, one 64-bit atomic per non-zero bin and block; ACCUMULATES into counts, so the batches of an
+// epoch can be fed one by one without concatenating them.  bad: set when a label or prediction is outside [0, K).
+constexpr int KCM = 16;
+
+template <typename TP, typename TL>
+__global__ void confusion_kernel(const TP* __restrict__ pred, const int64_t* __restrict__ target, const TL* __restrict__ lu,
+                                 int64_t n, int K, unsigned long long* __restrict__ counts, int* __restrict__ bad) {
+  extern __shared__ unsigned int cm_hist[];                       // [warps][2][K*K]
+  const int KK = K * K, warps = blockDim.x >> 5;
+  for (int i = threadIdx.x; i < warps * 2 * KK; i += blockDim.x) cm_hist[i] = 0u;
+  __syncthreads();
+  unsigned int* mine = cm_hist + (threadIdx.x >> 5) * 2 * KK;
+  bool oob = false;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const long long t = target[i], p = static_cast<long long>(pred[i]);
+    if (t < 0 || t >= K || p < 0 || p >= K) { oob = true; continue; }
+    const int bin = static_cast<int>(t) * K + static_cast<int>(p);
+    atomicAdd(&mine[bin], 1u);
+    if (lu != nullptr && lu[i] == static_cast<TL>(1)) atomicAdd(&mine[KK + bin], 1u);
+  }
+  if (oob) atomicOr(bad, 1);
+  __syncthreads();
+  for (int b = threadIdx.x; b < 2 * KK; b += blockDim.x) {
+    unsigned long long sum = 0;
+    for (int w = 0; w < warps; ++w) sum += cm_hist[w * 2 * KK + b];
+    if (sum) atomicAdd(&counts[b], sum);
+  }
+}
+
 // ---- probability / one-hot API (the reference's loss callables take softmax output + one-hot) ----
 
 __global__ void one_hot_kernel(const int64_t* __restrict__ labels, int K, int64_t HW, int64_t total,
@@ -554,6 +587,22 @@ inline int grid_for(int64_t work) {
   int64_t blocks = (work + kThreads - 1) / kThreads;
   const int64_t cap = static_cast<int64_t>(dt_num_sms()) * 8;
   return static_cast<int>(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
+}
+
+template <typename TP>
+static int confusion_launch(const TP* pred, const int64_t* target, const void* lu, int lu_elem, int64_t n, int K,
+                            int64_t* counts, int32_t* bad, cudaStream_t s) {
+  // every thread's 32-bit private counter is bounded by the pixels one block sees: keep blocks under 2^31 pixels
+  int grid = grid_for(n);
+  const size_t smem = static_cast<size_t>(kThreads / 32) * 2 * K * K * sizeof(unsigned int);
+  unsigned long long* c = reinterpret_cast<unsigned long long*>(counts);
+  if (lu == nullptr || lu_elem == 1)
+    confusion_kernel<TP, uint8_t><<<grid, kThreads, smem, s>>>(pred, target, static_cast<const uint8_t*>(lu), n, K, c, bad);
+  else if (lu_elem == 4)
+    confusion_kernel<TP, int32_t><<<grid, kThreads, smem, s>>>(pred, target, static_cast<const int32_t*>(lu), n, K, c, bad);
+  else
+    confusion_kernel<TP, int64_t><<<grid, kThreads, smem, s>>>(pred, target, static_cast<const int64_t*>(lu), n, K, c, bad);
+  return 0;
 }
 
 }  // namespace
@@ -730,6 +779,22 @@ int dt_gwdl_loss_backward(const float* logits, const int64_t* labels, int N, int
     case 3: gwdl_backward_kernel<3><<<grid, kThreads, 0, s>>>(logits, labels, HW, M, softmax_twice, coef, amap, weight, grad_logits); break;
     default: gwdl_backward_kernel<4><<<grid, kThreads, 0, s>>>(logits, labels, HW, M, softmax_twice, coef, amap, weight, grad_logits); break;
   }
+  DT_LAUNCH_CHECK();
+  return DT_OK;
+}
+
+int dt_confusion_matrix(const void* pred, int pred_elem, const int64_t* target, const void* lu, int lu_elem, int64_t n,
+                        int K, int64_t* counts, int32_t* bad_label, dt_stream_t stream) {
+  DT_ARCH_GUARD();
+  DT_REQUIRE(n > 0 && K >= 2 && K <= KCM, DT_ERR_BAD_SHAPE, "dt_confusion_matrix: n=%lld K=%d (K in 2..16)",
+             static_cast<long long>(n), K);
+  DT_REQUIRE((pred_elem == 1 || pred_elem == 8) && (lu == nullptr || lu_elem == 1 || lu_elem == 4 || lu_elem == 8),
+             DT_ERR_BAD_SHAPE, "dt_confusion_matrix: pred must be uint8 or int64, lu uint8 / int32 / int64");
+  DT_REQUIRE(pred != nullptr && target != nullptr && counts != nullptr && bad_label != nullptr, DT_ERR_BAD_SHAPE,
+             "dt_confusion_matrix: null pointer");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (pred_elem == 1) confusion_launch(static_cast<const uint8_t*>(pred), target, lu, lu_elem, n, K, counts, bad_label, s);
+  else confusion_launch(static_cast<const int64_t*>(pred), target, lu, lu_elem, n, K, counts, bad_label, s);
   DT_LAUNCH_CHECK();
   return DT_OK;
 }

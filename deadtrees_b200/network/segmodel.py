@@ -15,6 +15,7 @@ from collections import Counter
 from pathlib import Path
 from typing import Any, Dict, Optional, Tuple
 
+import numpy as np
 import torch
 import torch.nn as nn
 from torch import Tensor
@@ -140,7 +141,6 @@ class SemSegment(_Base):  # type: ignore[misc]
             if comp == "GDICE":
                 self.dice_loss = GeneralizedDiceLoss()
             elif comp == "GWDICE":
-                import numpy as np
                 dist_mat = np.array([[0.0, 1.0, 1.0], [1.0, 0.0, 0.5], [1.0, 0.5, 0.0]])      # segmodel.py:119
                 if n_classes == 2:      # the reference tests `self.classes_int == 2` (list vs int, never true) and then fails
                     dist_mat = dist_mat[0:2, 0:2]      # on the 3 x 3 matrix; the 2 x 2 cut it intends is applied here
@@ -160,6 +160,7 @@ class SemSegment(_Base):  # type: ignore[misc]
         assert self.dice_loss is not None
 
         self.stats = {"train": Counter(), "val": Counter(), "test": Counter()}
+        self.confusion: Dict[str, Any] = {}
         self.logged: Dict[str, Any] = {}
         self._epoch = 0
 
@@ -275,6 +276,39 @@ class SemSegment(_Base):  # type: ignore[misc]
         logits, _, _ = self._eval_step(img, mask, "test")
         self.stats["test"].update([x["file"] for x in stats])
         return {"target": mask, "prediction": ops.argmax_nchw(logits).long(), "lu": lu}
+
+    # -- confusion matrices of an epoch (segmodel.py:291-407) --------------------------------------
+    def _epoch_confusion(self, outputs, stage: str, with_px: bool):
+        """one histogram pass per step output instead of ``torch.cat`` + four ``confusion_matrix`` calls: all pixels and the
+        forest pixels (``lu == 1``) are counted together; the normalised matrices divide each target row by its sum (rows of
+        absent classes are 0, as torchmetrics)."""
+        import pandas as pd
+        K = len(self.classes)
+        counts = None
+        for out in outputs:
+            counts = ops.confusion_matrix(out["prediction"], out["target"], K, lu=out.get("lu"), counts=counts)
+            assert int(counts.bad.item()) == 0, "prediction / target outside [0, K)"
+        cm = counts.cpu().numpy()
+        norm = cm / np.maximum(cm.sum(axis=2, keepdims=True), 1)
+        mats = {"cm_norm": norm[0], "cm_px": cm[0], "cm_norm_masked": norm[1], "cm_px_masked": cm[1]}
+        keys = ["cm_norm", "cm_px", "cm_norm_masked", "cm_px_masked"] if with_px else ["cm_norm", "cm_norm_masked"]
+        dfs = {k: pd.DataFrame(mats[k], index=self.classes, columns=self.classes) for k in keys}
+        self.confusion[stage] = dfs
+        return dfs
+
+    def validation_epoch_end(self, outputs):
+        """normalised confusion matrices, all pixels and forest only (``segmodel.py:291-332``); the chart / wandb upload of
+        the reference is UI and not part of this package - the tables are kept in ``self.confusion["val"]``."""
+        return self._epoch_confusion(outputs, "val", with_px=False)
+
+    def test_epoch_end(self, outputs):
+        """normalised and pixel-count confusion matrices, all pixels and forest only (``segmodel.py:334-407``)."""
+        dfs = self._epoch_confusion(outputs, "test", with_px=True)
+        log.info(f"CM - DEFAULT - NORMALIZED: {dfs['cm_norm'].to_string()}")
+        log.info(f"CM - FORESTONLY - NORMALIZED: {dfs['cm_norm_masked'].to_string()}")
+        log.info(f"CM - DEFAULT - PIXEL: {dfs['cm_px'].to_string()}")
+        log.info(f"CM - FORESTONLY - PIXEL: {dfs['cm_px_masked'].to_string()}")
+        return dfs
 
     def configure_optimizers(self):
         from ..optim import FusedAdam

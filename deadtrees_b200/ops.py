@@ -8,6 +8,7 @@ from __future__ import annotations
 import ctypes as C
 from typing import Optional, Sequence, Tuple
 
+import numpy as np
 import torch
 
 from . import _lib
@@ -302,6 +303,72 @@ def gwdl_loss_backward(logits: torch.Tensor, labels: torch.Tensor, dist_matrix, 
         labels = labels.long()
     check(load().dt_gwdl_loss_backward(logits.data_ptr(), labels.contiguous().data_ptr(), N, K, H, W, M, int(softmax_twice),
                                        coef.data_ptr(), float(weight), grad_logits.data_ptr(), stream_ptr()))
+
+
+def train_transform(images: torch.Tensor, masks, lus, geom, bc, offset, scale, out_channels: int, merge_classes: bool = False):
+    """``dt_train_transform``: (N, H, W, C) uint8 images (+ (N, H, W) uint8 masks / lus) and per-sample draws ``geom`` (N, 2)
+    {flip, rot}, ``bc`` (N, 2) {alpha, beta} -> (fp32 (N, out_channels, H, W), int64 masks, int64 lus)."""
+    images = _cuda(images, "images").contiguous()
+    if images.dtype != torch.uint8 or images.dim() != 4:
+        raise TypeError("train_transform expects (N, H, W, C) uint8 images")
+    N, H, W, Cc = images.shape
+    dev = images.device
+
+    def u8(t, name):
+        if t is None:
+            return None
+        t = _cuda(t, name)
+        if t.dtype != torch.uint8:
+            t = t.to(torch.uint8)
+        if tuple(t.shape) != (N, H, W):
+            raise ValueError(f"{name} must be (N, H, W) = {(N, H, W)}, got {tuple(t.shape)}")
+        return t.contiguous()
+
+    masks, lus = u8(masks, "masks"), u8(lus, "lus")
+    geom_t = torch.as_tensor(np.ascontiguousarray(geom, dtype=np.int32).reshape(N, 2)).to(dev, non_blocking=True)
+    bc_t = torch.as_tensor(np.ascontiguousarray(bc, dtype=np.float64).reshape(N, 2)).to(dev, non_blocking=True)
+    off = (C.c_float * 4)(*([float(v) for v in list(offset)[:out_channels]] + [0.0] * (4 - out_channels)))
+    sc = (C.c_float * 4)(*([float(v) for v in list(scale)[:out_channels]] + [0.0] * (4 - out_channels)))
+    sums = torch.empty((N,), dtype=torch.int64, device=dev)
+    out = torch.empty((N, out_channels, H, W), dtype=torch.float32, device=dev)
+    om = torch.empty((N, H, W), dtype=torch.int64, device=dev) if masks is not None else None
+    ol = torch.empty((N, H, W), dtype=torch.int64, device=dev) if lus is not None else None
+    check(load().dt_train_transform(images.data_ptr(), masks.data_ptr() if masks is not None else None,
+                                    lus.data_ptr() if lus is not None else None, N, H, W, Cc, out_channels,
+                                    geom_t.data_ptr(), bc_t.data_ptr(), off, sc, int(merge_classes), sums.data_ptr(),
+                                    out.data_ptr(), om.data_ptr() if om is not None else None,
+                                    ol.data_ptr() if ol is not None else None, stream_ptr()))
+    return out, om, ol
+
+
+def confusion_matrix(pred: torch.Tensor, target: torch.Tensor, K: int, lu: torch.Tensor = None,
+                     counts: torch.Tensor = None) -> torch.Tensor:
+    """adds the (target, prediction) pairs to ``counts`` int64 (2, K, K): [0] all pixels, [1] the pixels with ``lu == 1``
+    (rows = target, as torchmetrics' ``confusion_matrix``).  ``counts=None`` starts a new pair of matrices."""
+    pred, target = _cuda(pred, "pred").contiguous(), _cuda(target, "target").contiguous()
+    if pred.dtype not in (torch.uint8, torch.int64):
+        pred = pred.long()
+    if target.dtype != torch.int64:
+        target = target.long()
+    if pred.numel() != target.numel():
+        raise ValueError(f"prediction {tuple(pred.shape)} and target {tuple(target.shape)} differ in size")
+    lu_ptr, lu_elem = None, 0
+    if lu is not None:
+        lu = _cuda(lu, "lu").contiguous()
+        if lu.dtype == torch.bool:
+            lu = lu.view(torch.uint8)
+        elif lu.dtype not in (torch.uint8, torch.int32, torch.int64):
+            lu = (lu == 1).view(torch.uint8)
+        if lu.numel() != target.numel():
+            raise ValueError(f"lu {tuple(lu.shape)} and target {tuple(target.shape)} differ in size")
+        lu_ptr, lu_elem = lu.data_ptr(), lu.element_size()
+    if counts is None:
+        counts = torch.zeros((2, K, K), dtype=torch.int64, device=pred.device)
+    bad = torch.zeros((1,), dtype=torch.int32, device=pred.device)
+    check(load().dt_confusion_matrix(pred.data_ptr(), pred.element_size(), target.data_ptr(), lu_ptr, lu_elem, pred.numel(), K,
+                                     counts.data_ptr(), bad.data_ptr(), stream_ptr()))
+    counts.bad = bad
+    return counts
 
 
 def one_hot2dist(labels: torch.Tensor, K: int, truncate: bool = True) -> torch.Tensor:

@@ -211,6 +211,29 @@ int dt_gwdl_loss(const float* logits, const int64_t* labels, int N, int K, int H
 int dt_gwdl_loss_backward(const float* logits, const int64_t* labels, int N, int K, int H, int W, const float* dist_matrix,
                           int softmax_twice, const float* coef, float weight, float* grad_logits, dt_stream_t stream);
 
+/* The dataloader's train_transform for one batch (deadtrees/data/deadtreedata.py:132-146 and transform() :156-189):
+ * OneOf(HorizontalFlip, VerticalFlip) -> RandomRotate90 -> RandomBrightnessContrast(brightness_by_max=False) -> Normalize ->
+ * ToTensorV2, then image[0:out_channels], mask.long(), lu.long() and mask > 1 -> 1 when merge_classes != 0.  The random draws
+ * are the caller's: geom int32 [N][2] = {flip (0 none, 1 horizontal, 2 vertical), rot (np.rot90 quarter turns 0..3, applied
+ * after the flip)}, bc double [N][2] = {alpha, beta} of the brightness / contrast table
+ * lut[v] = uint8(clip(float32(v) * alpha + float32(beta * mean(image)), 0, 255)); {1, 0} leaves the bytes unchanged.
+ * images (N, H, W, C) uint8 with H == W, masks / lus (N, H, W) uint8 or NULL; offset / scale: HOST float[out_channels] of the
+ * normalisation (u8 - offset) * scale; sums: N uint64 of workspace; out_img (N, out_channels, H, W) fp32, out_mask / out_lu
+ * (N, H, W) int64.  All pointers except offset / scale are device memory. */
+int dt_train_transform(const uint8_t* images, const uint8_t* masks, const uint8_t* lus, int N, int H, int W, int C,
+                       int out_channels, const int32_t* geom, const double* bc, const float* offset, const float* scale,
+                       int merge_classes, uint64_t* sums, float* out_img, int64_t* out_mask, int64_t* out_lu,
+                       dt_stream_t stream);
+
+/* Confusion matrices of a validation / test epoch (SemSegment.validation_epoch_end / test_epoch_end,
+ * deadtrees/network/segmodel.py:291-407: torchmetrics confusion_matrix(prediction, target) and the same on the pixels of
+ * the forest mask, `lu == 1`).  pred: n predictions, uint8 (pred_elem 1) or int64 (8); target: n int64 labels; lu: n land-use
+ * flags (lu_elem 1, 4 or 8 bytes) or NULL.  counts: int64 [2][K][K], rows = target, columns = prediction; [0] all pixels,
+ * [1] the pixels with lu == 1 (zero when lu is NULL).  The call ADDS to counts (zero it before the first batch of an epoch);
+ * bad_label: int32 [1], set to 1 when a value lies outside [0, K) (such pixels are not counted).  K <= 16. */
+int dt_confusion_matrix(const void* pred, int pred_elem, const int64_t* target, const void* lu, int lu_elem, int64_t n,
+                        int K, int64_t* counts, int32_t* bad_label, dt_stream_t stream);
+
 /* The dataloader's signed distance maps for the boundary loss (one_hot2dist, deadtrees/loss/losses.py:159-178, called at
  * deadtrees/data/deadtreedata.py:182-185): labels (N, H, W) int64 -> out (N, K, H, W) fp32 with, for every class k that has
  * a pixel in image n, edt(not k) outside the class and -(edt(k) - 1) inside it (scipy's exact Euclidean distance transform,

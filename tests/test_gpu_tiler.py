@@ -173,3 +173,60 @@ def test_full_size_mosaic_roundtrip_property():
         cls = (tiles[..., 0].to(torch.int32) % 3).to(torch.uint8)     # identity-normalised red channel mod 3
         ops.stitch_mask(cls, gx, t0, out)
     assert torch.equal(out, (m[..., 0] % 3))
+
+
+@pytest.mark.parametrize("N,T,C,cin,classes", [(8, 64, 4, 4, 3), (5, 256, 4, 3, 2), (3, 37, 3, 3, 3), (2, 16, 1, 1, 3)])
+def test_train_transform_vs_oracle(N, T, C, cin, classes):
+    """dt_train_transform (train_transform + transform(), deadtreedata.py:132-146, 156-189) against the oracle for the
+    same draws: every flip x rotation, contrast / brightness tables that saturate at both ends, the channel slice and the
+    two-class merge.  Byte and index work: bit-exact, the normalised floats included."""
+    from oracle import ref_augment
+    from deadtrees_b200.data.deadtreedata import normalize_constants
+    rng = np.random.default_rng(N * 100 + T)
+    images = rng.integers(0, 256, (N, T, T, C), dtype=np.uint8)
+    masks = rng.integers(0, 3, (N, T, T), dtype=np.uint8)
+    lus = rng.integers(0, 4, (N, T, T), dtype=np.uint8)
+    geom = np.array([[i % 3, (i // 3 + i) % 4] for i in range(N)], dtype=np.int32)
+    bc = np.array([[1.0, 0.0] if i % 4 == 0 else [rng.uniform(0.85, 1.15), rng.uniform(-0.2, 0.2)] for i in range(N)])
+    bc[-1] = [1.15, 0.2]
+    offset, scale = normalize_constants(C)
+    img, m, l = ops.train_transform(torch.from_numpy(images), torch.from_numpy(masks), torch.from_numpy(lus), geom, bc,
+                                    offset, scale, cin, merge_classes=classes == 2)
+    assert img.shape == (N, cin, T, T) and m.dtype == torch.int64 and l.dtype == torch.int64
+    for i in range(N):
+        ri, rm, rl = ref_augment.train_transform(images[i], masks[i], lus[i], int(geom[i, 0]), int(geom[i, 1]),
+                                                 float(bc[i, 0]), float(bc[i, 1]), in_channels=cin, classes=classes)
+        np.testing.assert_array_equal(img[i].cpu().numpy(), ri, err_msg=f"sample {i} geom {geom[i]} bc {bc[i]}")
+        np.testing.assert_array_equal(m[i].cpu().numpy(), rm)
+        np.testing.assert_array_equal(l[i].cpu().numpy(), rl)
+    # image only (no mask / lu)
+    img2, m2, l2 = ops.train_transform(torch.from_numpy(images), None, None, geom, bc, offset, scale, cin)
+    assert m2 is None and l2 is None and torch.equal(img2, img)
+
+
+def test_batch_train_transform_feeds_training_step():
+    """BatchTrainTransform: uint8 tiles -> the tensors SemSegment.training_step takes, incl. the boundary-loss distance maps
+    computed from the TRANSFORMED mask (deadtreedata.py:182-185); identity draws equal val_transform."""
+    from deadtrees_b200.data.deadtreedata import BatchTrainTransform, train_transform, val_transform
+    from oracle import ref_augment, ref_dist
+    rng = np.random.default_rng(4)
+    images = rng.integers(0, 256, (4, 64, 64, 4), dtype=np.uint8)
+    masks = (rng.random((4, 64, 64)) < 0.2).astype(np.uint8) * rng.integers(1, 3, (4, 64, 64), dtype=np.uint8)
+    lus = rng.integers(0, 2, (4, 64, 64), dtype=np.uint8)
+    tf = BatchTrainTransform(in_channels=4, classes=3, distmap=True, seed=11)
+    geom = np.array([[1, 1], [2, 3], [0, 2], [0, 0]], dtype=np.int32)
+    bc = np.array([[1.1, 0.1], [0.9, -0.15], [1.0, 0.0], [1.0, 0.0]])
+    img, mask, dist, lu = tf(images, masks, lus, params=(geom, bc))
+    assert img.shape == (4, 4, 64, 64) and dist.shape == (4, 3, 64, 64) and img.is_cuda
+    for i in range(4):
+        ri, rm, rl = ref_augment.train_transform(images[i], masks[i], lus[i], *map(int, geom[i]), *map(float, bc[i]))
+        np.testing.assert_array_equal(img[i].cpu().numpy(), ri)
+        np.testing.assert_array_equal(mask[i].cpu().numpy(), rm)
+        np.testing.assert_array_equal(dist[i].cpu().numpy(), ref_dist.labels_to_dist(rm[None], 3)[0])
+    np.testing.assert_array_equal(img[3].cpu().numpy(), val_transform(image=images[3])["image"].cpu().numpy())
+    # random draws: same seed, same batch
+    a = BatchTrainTransform(seed=5)(images, masks, lus)
+    b = BatchTrainTransform(seed=5)(images, masks, lus)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and a[2] is None
+    one = train_transform(image=images[0], mask=masks[0], lu=lus[0])
+    assert one["image"].shape == (4, 64, 64) and one["mask"].shape == (64, 64) and one["lu"].dtype == torch.int64

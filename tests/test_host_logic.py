@@ -257,3 +257,20 @@ def test_fold_upsample_weights_identity():
     assert torch.equal(eng, ref_unet.fold_upsample_weights(w.float()).permute(0, 2, 3, 4, 5, 1).reshape(5, 4, 4, 7))
     packed = pack_weight_folded(torch.randn(16, 96, 3, 3, generator=g), "cpu", 64)
     assert packed.shape == (16, 16 * 64 + 9 * 32) and packed.dtype == torch.bfloat16
+
+
+def test_train_transform_draws_follow_the_reference_distributions():
+    """draw_train_params: OneOf(HFlip, VFlip, p=.5), RandomRotate90(p=.5), RandomBrightnessContrast(p=.5, 0.2 / 0.15)
+    (deadtreedata.py:132-146) - frequencies and ranges of the draws."""
+    from deadtrees_b200.data.deadtreedata import draw_train_params
+    geom, bc = draw_train_params(np.random.default_rng(1), 20000)
+    flips = np.bincount(geom[:, 0], minlength=3) / 20000
+    rots = np.bincount(geom[:, 1], minlength=4) / 20000
+    np.testing.assert_allclose(flips, [0.5, 0.25, 0.25], atol=0.015)
+    np.testing.assert_allclose(rots, [0.625, 0.125, 0.125, 0.125], atol=0.015)
+    on = bc[:, 0] != 1.0
+    assert abs(on.mean() - 0.5) < 0.015 and (bc[~on, 1] == 0).all()
+    assert bc[on, 0].min() >= 0.85 and bc[on, 0].max() <= 1.15 and np.abs(bc[on, 1]).max() <= 0.2
+    assert abs(bc[on, 0].mean() - 1.0) < 0.005 and abs(bc[on, 1].mean()) < 0.005
+    g2, b2 = draw_train_params(np.random.default_rng(1), 20000, beta_times_alpha=True)
+    np.testing.assert_allclose(b2[:, 1], bc[:, 1] * bc[:, 0]) and np.testing.assert_array_equal(g2, geom)

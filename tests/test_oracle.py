@@ -174,3 +174,50 @@ def test_distance_maps_against_reference_outputs(golden_dir):
         np.testing.assert_array_equal(ref_dist.one_hot2dist(onehot, resolution=[1, 1], dtype=np.float32), g[f"dist_f32{i}"])
         np.testing.assert_array_equal(ref_dist.labels_to_dist(lab[None], K, truncate=True)[0], g[f"dist_int{i}"].astype(np.float32))
         np.testing.assert_array_equal(ref_dist.labels_to_dist(lab[None], K, truncate=False)[0], g[f"dist_f32{i}"])
+
+
+def test_confusion_matrices_against_sklearn():
+    """oracle/ref_confusion.py (torchmetrics' published definition) against sklearn's independent implementation,
+    including an absent class (NaN row -> 0) and an empty forest mask."""
+    from sklearn.metrics import confusion_matrix as sk_cm
+    from oracle import ref_confusion
+    rng = np.random.default_rng(5)
+    for K, n, absent in ((3, 5000, None), (3, 777, 2), (2, 100, None), (4, 4096, 0)):
+        target, pred = rng.integers(0, K, n), rng.integers(0, K, n)
+        if absent is not None:
+            target[target == absent] = (absent + 1) % K
+        lu = rng.integers(0, 3, n)
+        m = ref_confusion.epoch_matrices(pred, target, lu, K)
+        np.testing.assert_array_equal(m["cm_px"], sk_cm(target, pred, labels=list(range(K))))
+        np.testing.assert_allclose(m["cm_norm"], sk_cm(target, pred, labels=list(range(K)), normalize="true"), rtol=1e-15)
+        np.testing.assert_array_equal(m["cm_px_masked"], sk_cm(target[lu == 1], pred[lu == 1], labels=list(range(K))))
+        np.testing.assert_allclose(m["cm_norm_masked"], sk_cm(target[lu == 1], pred[lu == 1], labels=list(range(K)), normalize="true"), rtol=1e-15)
+        assert m["cm_px"].sum() == n and np.isfinite(m["cm_norm"]).all()
+    empty = ref_confusion.epoch_matrices(pred, target, np.zeros(n, np.int64), K)
+    assert empty["cm_px_masked"].sum() == 0 and (empty["cm_norm_masked"] == 0).all()
+
+
+def test_train_transform_oracle_properties():
+    """oracle/ref_augment.py: identity draws reduce to val_transform, four quarter turns are the identity, a flip is an
+    involution, the table saturates, and the brightness term uses the mean over every channel of the sample."""
+    from oracle import ref_augment, ref_normalize
+    rng = np.random.default_rng(0)
+    img = rng.integers(0, 256, (32, 32, 4), dtype=np.uint8)
+    mask, lu = rng.integers(0, 3, (32, 32), dtype=np.uint8), rng.integers(0, 2, (32, 32), dtype=np.uint8)
+    out, m, l = ref_augment.train_transform(img, mask, lu, 0, 0, 1.0, 0.0)
+    np.testing.assert_array_equal(out, ref_normalize.val_transform(img))
+    np.testing.assert_array_equal(m, mask) and np.testing.assert_array_equal(l, lu)
+    a = img
+    for _ in range(4):
+        a = ref_augment.geometric(a, 0, 1)
+    np.testing.assert_array_equal(a, img)
+    for f in (1, 2):
+        np.testing.assert_array_equal(ref_augment.geometric(ref_augment.geometric(img, f, 0), f, 0), img)
+    # np.rot90 turns counter-clockwise: the top-right pixel moves to the top-left corner
+    np.testing.assert_array_equal(ref_augment.geometric(img, 0, 1)[0, 0], img[0, -1])
+    bc = ref_augment.brightness_contrast(img, 1.15, 0.2)
+    lut = np.clip(np.arange(256, dtype=np.float32) * np.float32(1.15) + np.float32(0.2 * img.mean()), 0, 255).astype(np.uint8)
+    np.testing.assert_array_equal(bc, lut[img])
+    assert bc.max() == 255 and (bc >= img).all()
+    out2, m2, _ = ref_augment.train_transform(img, mask, lu, 2, 3, 0.9, -0.1, in_channels=3, classes=2)
+    assert out2.shape == (3, 32, 32) and m2.max() == 1 and m2.dtype == np.int64
