@@ -83,7 +83,7 @@ _SIGNATURES = {
     "dt_upsample_concat": ([_p, _p, _i, _i, _i, _i, _i, _i, _p, _p], C.c_int),
     "dt_upsample_concat_bwd": ([_p, _i, _i, _i, _i, _i, _i, _p, _p, _p], C.c_int),
     "dt_nchw_to_nhwc": ([_p, _i, _i, _i, _i, _i, _i, _p, _p], C.c_int),
-    "dt_channel_sum": ([_p, _i64, _i, _i, _i, _p, _p], C.c_int),
+    "dt_channel_sum": ([_p, _i64, _i, _i, _i, _p, _p, _p], C.c_int),
     "dt_pack_conv_weight": ([_p, _i, _i, _i, _i, _i, _i, _i, _p, _p], C.c_int),
     "dt_pack_conv_weights_batched": ([_p, _i, _i64, _p], C.c_int),
     "dt_conv2d_dgrad_direct": ([_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p], C.c_int),

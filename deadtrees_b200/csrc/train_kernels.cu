@@ -650,7 +650,8 @@ __global__ void wgrad_direct_kernel(BwdGeo p, const T* __restrict__ x, const T* 
   }
 }
 
-// db[k] += sum over pixels of g[pix][k]  (bias gradient of the head; C small)
+// db[k] += sum over pixels of g[pix][k]  (bias gradient of the head; C small).  Float atomics: the sum depends on the order
+// in which the warps arrive (check-mode wgrad only; the training step uses the two-stage form below).
 template <typename T>
 __global__ void bias_grad_kernel(const T* __restrict__ g, int64_t M, int C, int K, float* __restrict__ db) {
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -662,6 +663,37 @@ __global__ void bias_grad_kernel(const T* __restrict__ g, int64_t M, int C, int 
     const float t = warp_sum(acc[k]);
     if ((threadIdx.x & 31) == 0) atomicAdd(db + k, t);
   }
+}
+
+// The same sum, bit-reproducible from run to run: stage 1 leaves one partial per (block, channel) - summed over the block in
+// a fixed order -, stage 2 adds the partials in block order.  (The atomic form made the head's bias gradient, through the
+// gradient norm of the clip, the one source of run-to-run differences of a training step.)
+template <typename T>
+__global__ void channel_sum_partials_kernel(const T* __restrict__ g, int64_t M, int C, int K, float* __restrict__ part) {
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int64_t m = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; m < M;
+       m += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    for (int k = 0; k < K; ++k) acc[k] += to_f<T>(g[m * C + k]);
+  }
+  __shared__ float sh[kThreads / 32][4];
+  for (int k = 0; k < 4; ++k) {
+    const float t = warp_sum(acc[k]);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5][k] = t;
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    float t = 0.f;
+    for (int w = 0; w < kThreads / 32; ++w) t += sh[w][threadIdx.x];
+    part[blockIdx.x * 4 + threadIdx.x] = t;
+  }
+}
+
+__global__ void channel_sum_final_kernel(const float* __restrict__ part, int blocks, int K, float* __restrict__ out) {
+  const int k = threadIdx.x;
+  if (k >= K) return;
+  double t = 0.0;
+  for (int b = 0; b < blocks; ++b) t += static_cast<double>(part[b * 4 + k]);
+  out[k] = static_cast<float>(t);
 }
 
 int reduce_blocks(int64_t M, int C, int vn) {
@@ -889,15 +921,19 @@ int dt_nchw_to_nhwc(const float* x, int N, int K, int H, int W, int Kp, int dtyp
   return DT_OK;
 }
 
-int dt_channel_sum(const void* g, int64_t M, int C, int K, int dtype, float* out, dt_stream_t stream) {
+int dt_channel_sum(const void* g, int64_t M, int C, int K, int dtype, float* workspace, float* out, dt_stream_t stream) {
   DT_ARCH_GUARD();
   DT_REQUIRE(M > 0 && C > 0 && K >= 1 && K <= 4 && K <= C && (dtype == DT_F32 || dtype == DT_BF16), DT_ERR_BAD_SHAPE,
              "dt_channel_sum: M=%lld C=%d K=%d (K <= 4)", static_cast<long long>(M), C, K);
+  DT_REQUIRE(workspace != nullptr && out != nullptr, DT_ERR_BAD_SHAPE, "dt_channel_sum: null pointer");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  DT_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * K, s));
+  int blocks = grid_for(M, 2);
+  if (blocks > 512) blocks = 512;                       // workspace: 2048 floats
   DT_DTYPE_SWITCH(dtype,
-      (bias_grad_kernel<float><<<grid_for(M, 2), kThreads, 0, s>>>(static_cast<const float*>(g), M, C, K, out)),
-      (bias_grad_kernel<__nv_bfloat16><<<grid_for(M, 2), kThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(g), M, C, K, out)));
+      (channel_sum_partials_kernel<float><<<blocks, kThreads, 0, s>>>(static_cast<const float*>(g), M, C, K, workspace)),
+      (channel_sum_partials_kernel<__nv_bfloat16><<<blocks, kThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(g), M, C, K, workspace)));
+  DT_LAUNCH_CHECK();
+  channel_sum_final_kernel<<<1, 32, 0, s>>>(workspace, blocks, K, out);
   DT_LAUNCH_CHECK();
   return DT_OK;
 }

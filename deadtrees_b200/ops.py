@@ -595,11 +595,13 @@ def nchw_to_nhwc(x: torch.Tensor, Kp: int, dtype: torch.dtype) -> torch.Tensor:
 
 
 def channel_sum(g: torch.Tensor, K: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """sum over all pixels of the first K channels of an NHWC tensor -> float (K,)."""
+    """sum over all pixels of the first K channels of an NHWC tensor -> float (K,); two fixed-order stages, so the result
+    is the same bit pattern on every run."""
     Cc = g.shape[-1]
     if out is None:
         out = torch.empty(K, dtype=torch.float32, device=g.device)
-    check(load().dt_channel_sum(g.data_ptr(), g.numel() // Cc, Cc, K, _dt(g), out.data_ptr(), stream_ptr()))
+    check(load().dt_channel_sum(g.data_ptr(), g.numel() // Cc, Cc, K, _dt(g), _reduce_ws(g.device).data_ptr(), out.data_ptr(),
+                                stream_ptr()))
     return out
 
 

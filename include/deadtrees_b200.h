@@ -317,8 +317,9 @@ int dt_upsample_concat_bwd(const void* g_cat, int N, int H, int W, int Cx, int C
                            dt_stream_t stream);
 /* (N, K, H, W) fp32 -> (N, H, W, Kp) `dtype`, channels >= K zero (gradient of the logits into the head backward) */
 int dt_nchw_to_nhwc(const float* x, int N, int K, int H, int W, int Kp, int dtype, void* out, dt_stream_t stream);
-/* out[k] = sum over the M pixels of g[pixel][k] for k < K (g: (M, C) NHWC rows) — the bias gradient of the head */
-int dt_channel_sum(const void* g, int64_t M, int C, int K, int dtype, float* out, dt_stream_t stream);
+/* out[k] = sum over the M pixels of g[pixel][k] for k < K <= 4 (g: (M, C) NHWC rows) — the bias gradient of the head.
+ * Two fixed-order stages (no atomics): the same bits on every run.  workspace: 2048 floats. */
+int dt_channel_sum(const void* g, int64_t M, int C, int K, int dtype, float* workspace, float* out, dt_stream_t stream);
 /* fp32 OIHW master weights -> kernel layouts.  mode 0: float [tap][C_in_p][C_out]; 1: bf16 [C_out][Kpad]
  * (dt_conv2d_fwd); 2: bf16 stem packing [C_out][256]; 3: bf16 [C_in][Kpad], k = (R*S-1-tap)*Cop + co — the
  * weights with which dt_conv2d_fwd computes the data gradient of a stride-1 convolution; 4: the same without the tap

@@ -190,8 +190,8 @@ def test_train_transform_vs_oracle(N, T, C, cin, classes):
     bc = np.array([[1.0, 0.0] if i % 4 == 0 else [rng.uniform(0.85, 1.15), rng.uniform(-0.2, 0.2)] for i in range(N)])
     bc[-1] = [1.15, 0.2]
     offset, scale = normalize_constants(C)
-    img, m, l = ops.train_transform(torch.from_numpy(images), torch.from_numpy(masks), torch.from_numpy(lus), geom, bc,
-                                    offset, scale, cin, merge_classes=classes == 2)
+    img, m, l = ops.train_transform(torch.from_numpy(images).cuda(), torch.from_numpy(masks).cuda(), torch.from_numpy(lus).cuda(),
+                                    geom, bc, offset, scale, cin, merge_classes=classes == 2)
     assert img.shape == (N, cin, T, T) and m.dtype == torch.int64 and l.dtype == torch.int64
     for i in range(N):
         ri, rm, rl = ref_augment.train_transform(images[i], masks[i], lus[i], int(geom[i, 0]), int(geom[i, 1]),
@@ -200,7 +200,7 @@ def test_train_transform_vs_oracle(N, T, C, cin, classes):
         np.testing.assert_array_equal(m[i].cpu().numpy(), rm)
         np.testing.assert_array_equal(l[i].cpu().numpy(), rl)
     # image only (no mask / lu)
-    img2, m2, l2 = ops.train_transform(torch.from_numpy(images), None, None, geom, bc, offset, scale, cin)
+    img2, m2, l2 = ops.train_transform(torch.from_numpy(images).cuda(), None, None, geom, bc, offset, scale, cin)
     assert m2 is None and l2 is None and torch.equal(img2, img)
 
 

@@ -530,8 +530,8 @@ def test_training_step_with_boundary_loss(losses, ramped):
 def test_graphed_training_step_equals_eager(loss_names):
     """the whole step replayed from one CUDA graph (deadtrees_b200/train_graph.py) against the same step launched kernel
     by kernel: three steps, the graph fed once through __call__ and twice through the prefetch pipeline.  The losses
-    must agree to the last bit; the parameters to 1e-6 (the head's bias gradient and the gradient norm of the clip are
-    atomic sums, so the clip factor - and with it every update - may differ in the last bit between two runs)."""
+    must agree to the last bit; the parameters to 1e-6 (the gradient norm of the clip and the loss partials are double
+    atomic sums of fixed per-block partials: the last bit of a double may differ between two runs)."""
     from deadtrees_b200.train_graph import GraphedTrainStep
     cin, n, T = 4, 2, 128
     oracle = oracle_model(cin, 3)
@@ -591,3 +591,17 @@ def test_dgrad_stride2_gather_kernel(cin, cout, k, N, H):
     assert gx.shape == (N, H, H, cin)
     err, rel = report(f"dgrad s2 k{k} {cin}<-{cout}", nchw(gx), x.grad + add)
     assert rel < 1e-2
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_channel_sum_is_reproducible(dtype):
+    """dt_channel_sum (bias gradient of the head): two fixed-order stages - the same bits on every call (its float atomics
+    were the one run-to-run difference of a training step and, through the clip's gradient norm, could tip a whole
+    trajectory) - and the float64 sum within fp32 rounding."""
+    g = torch.Generator().manual_seed(8)
+    x = (torch.randn(3 * 128 * 128, 8, generator=g) * 2.0).to(dtype).cuda()
+    ref = x.double().sum(dim=0)[:3].cpu()
+    outs = [ops.channel_sum(x, 3).cpu() for _ in range(5)]
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])
+    assert (outs[0].double() - ref).abs().max().item() < 1e-3 * max(1.0, ref.abs().max().item()) * 1e-2
