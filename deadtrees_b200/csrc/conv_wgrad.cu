@@ -200,24 +200,77 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constan
 }
 
 // dw[co][ci][tap] = sum over splits (fixed order) of partial[split][tap][co][ci]
-__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int RS, int C_out, int C_in,
+// Block (32, L): 32 float4 columns (4 consecutive ci) x L split lanes.  Lane l adds the splits l, l + L, l + 2L, ... with four
+// independent accumulators (loads in flight together), the lanes are combined through shared memory in lane order: the
+// order of every addition is a function of (splits, L) only - deterministic - while small layers with many splits (a
+// 64 x 64 layer has 147 partials of 37 k floats) get L times the loads in flight of a thread-per-element loop.
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int RS, int C_out, int C_in, int L,
                                     float* __restrict__ dw) {
+  extern __shared__ float4 wr_sh[];                      // [blockDim.y][32]
   const int64_t plane = static_cast<int64_t>(C_out) * C_in;
-  const int64_t total = plane * RS;
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int64_t cc = i % plane;      // co * C_in + ci (ci fastest: coalesced reads)
-    const int tap = static_cast<int>(i / plane);
-    // eight independent partial sums (loads in flight together), combined in a fixed order: deterministic
-    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    int s = 0;
-    for (; s + 8 <= splits; s += 8) {
+  const int64_t plane4 = plane / 4, total4 = plane4 * RS;
+  const int G = blockDim.y / L;                          // column groups of a block (L split lanes each)
+  const int lane = threadIdx.y % L, group = threadIdx.y / L, col = threadIdx.x;
+  const float4* p4 = reinterpret_cast<const float4*>(partial);
+  const int64_t per_block = static_cast<int64_t>(G) * 32;
+  for (int64_t base = blockIdx.x * per_block; base < total4; base += gridDim.x * per_block) {
+    const int64_t i = base + group * 32 + col;
+    const bool live = i < total4;
+    const int64_t c4 = live ? i % plane4 : 0;           // float4 index inside a tap plane (ci fastest: coalesced reads)
+    const int tap = live ? static_cast<int>(i / plane4) : 0;
+    float4 acc[4];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) acc[u] += partial[(static_cast<int64_t>(s + u) * RS + tap) * plane + cc];
+    for (int u = 0; u < 4; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live) {
+      int sp = lane;
+      for (; sp + 3 * L < splits; sp += 4 * L) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float4 v = p4[(static_cast<int64_t>(sp + u * L) * RS + tap) * plane4 + c4];
+          acc[u].x += v.x; acc[u].y += v.y; acc[u].z += v.z; acc[u].w += v.w;
+        }
+      }
+      for (int u = 0; sp < splits; sp += L, ++u) {
+        const float4 v = p4[(static_cast<int64_t>(sp) * RS + tap) * plane4 + c4];
+        acc[u].x += v.x; acc[u].y += v.y; acc[u].z += v.z; acc[u].w += v.w;
+      }
     }
-    for (int u = 0; s < splits; ++s, ++u) acc[u] += partial[(static_cast<int64_t>(s) * RS + tap) * plane + cc];
-    dw[cc * RS + tap] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+    float4 t;
+    t.x = (acc[0].x + acc[1].x) + (acc[2].x + acc[3].x);
+    t.y = (acc[0].y + acc[1].y) + (acc[2].y + acc[3].y);
+    t.z = (acc[0].z + acc[1].z) + (acc[2].z + acc[3].z);
+    t.w = (acc[0].w + acc[1].w) + (acc[2].w + acc[3].w);
+    if (L > 1) {
+      wr_sh[threadIdx.y * 32 + col] = t;
+      __syncthreads();
+      if (lane == 0) {
+        for (int l = 1; l < L; ++l) {
+          const float4 v = wr_sh[(threadIdx.y + l) * 32 + col];
+          t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+        }
+      }
+    }
+    if (lane == 0 && live) {
+      float* o = dw + c4 * 4 * RS + tap;
+      o[0] = t.x; o[RS] = t.y; o[2 * RS] = t.z; o[3 * RS] = t.w;
+    }
+    if (L > 1) __syncthreads();
   }
+}
+
+// launch shape of the reduction: split lanes by how many partials there are and how few columns the layer has
+static void launch_wgrad_reduce(const float* partial, int splits, int RS, int C_out, int C_in, float* dw, cudaStream_t s) {
+  const int64_t total4 = static_cast<int64_t>(C_out) * C_in / 4 * RS;
+  const int64_t cols32 = (total4 + 31) / 32;
+  int L = 1;
+  // few partials: one thread walks them all (four float4 loads in flight); many partials over few columns: up to 32 lanes
+  if (splits > 16) L = cols32 >= 2 * dt_num_sms() ? (splits <= 64 ? 4 : 8) : (cols32 >= 96 ? 16 : 32);
+  while (L > 1 && L * 4 > splits) L /= 2;                 // every lane gets at least four partials
+  const int Y = L > 8 ? L : 8, G = Y / L;
+  int64_t blocks = (cols32 + G - 1) / G;
+  const int64_t cap = static_cast<int64_t>(dt_num_sms()) * (Y >= 16 ? 2 : 8);
+  if (blocks > cap) blocks = cap;
+  wgrad_reduce_kernel<<<static_cast<int>(blocks), dim3(32, Y), sizeof(float4) * 32 * Y, s>>>(partial, splits, RS, C_out, C_in, L, dw);
 }
 
 struct WgPlan {
@@ -554,10 +607,7 @@ extern "C" int dt_conv2d_wgrad_tc(const void* x, const void* gy, int N, int Ho, 
     else if (nw.cb == 32) rc = launch_narrow<64, 32>(tm_g, tm_x, q, nw.splits, s);
     else rc = launch_narrow<64, 64>(tm_g, tm_x, q, nw.splits, s);
     if (rc != DT_OK) return rc;
-    const int64_t total = static_cast<int64_t>(C_out) * C_in * 9;
-    int64_t blocks = (total + 255) / 256;
-    if (blocks > dt_num_sms() * 8) blocks = dt_num_sms() * 8;
-    wgrad_reduce_kernel<<<static_cast<int>(blocks), 256, 0, s>>>(workspace, nw.splits, 9, C_out, C_in, dw_oihw);
+    launch_wgrad_reduce(workspace, nw.splits, 9, C_out, C_in, dw_oihw, s);
     DT_LAUNCH_CHECK();
     return DT_OK;
   }
@@ -607,10 +657,7 @@ extern "C" int dt_conv2d_wgrad_tc(const void* x, const void* gy, int N, int Ho, 
   DT_CUDA(attr_err);
   conv_wgrad_kernel<<<p.jobs * pl.splits, kThreads, SMEM, s>>>(tm_g, tm_x, p);
   DT_LAUNCH_CHECK();
-  const int64_t total = static_cast<int64_t>(C_out) * C_in * p.RS;
-  int64_t blocks = (total + 255) / 256;
-  if (blocks > dt_num_sms() * 8) blocks = dt_num_sms() * 8;
-  wgrad_reduce_kernel<<<static_cast<int>(blocks), 256, 0, s>>>(workspace, pl.splits, p.RS, C_out, C_in, dw_oihw);
+  launch_wgrad_reduce(workspace, pl.splits, p.RS, C_out, C_in, dw_oihw, s);
   DT_LAUNCH_CHECK();
   return DT_OK;
 }
