@@ -530,20 +530,85 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int C_out, int C
 }
 
 // every layout of every layer in ONE launch (the training step repacks ~93 weight tensors after each optimizer step):
-// jobs[j] covers the output elements [start_j, start_{j+1}); a thread finds its job by binary search.
+// jobs[j] covers the output elements [start_j, start_{j+1}).  Work unit = one output ROW (Kpad elements: a C_out row of the
+// forward layout, a C_in row of the dgrad layouts; 256-element chunks for the fp32 / stem layouts).  A block looks its row
+// up once (binary search over the per-job row prefix in shared memory), stages the fp32 source of the row in shared memory -
+// the forward row is ONE contiguous run of C_in * RS floats, a dgrad row is C_out runs of RS floats - and writes the row
+// with consecutive threads on consecutive elements; shared-memory reads have stride RS (odd: conflict-free).  Against the
+// thread-per-element form this removes the per-element search and 64-bit divisions and the 4-byte gathers.
+constexpr int kPackStage = 8192;                         // floats of staging per block (32 KB): rows up to C * RS = 8192
+
+__device__ __forceinline__ int pack_row_len(const dt_pack_job& jb) { return (jb.mode == 0 || jb.mode == 2) ? 256 : jb.Kpad; }
+
 __global__ void pack_weights_batched_kernel(const dt_pack_job* __restrict__ jobs, int njobs, int64_t total) {
-  extern __shared__ int64_t job_start[];          // the binary search runs on shared memory
-  for (int j = threadIdx.x; j < njobs; j += blockDim.x) job_start[j] = jobs[j].start;
+  extern __shared__ int64_t pk_sh[];                    // [njobs + 1] row prefix, then the staging floats
+  int64_t* row_start = pk_sh;
+  float* stage = reinterpret_cast<float*>(pk_sh + njobs + 1);
+  if (threadIdx.x == 0) {
+    int64_t rows = 0;
+    for (int j = 0; j < njobs; ++j) {
+      row_start[j] = rows;
+      const int64_t count = (j + 1 < njobs ? jobs[j + 1].start : total) - jobs[j].start;
+      const int len = pack_row_len(jobs[j]);
+      rows += (count + len - 1) / len;
+    }
+    row_start[njobs] = rows;
+  }
   __syncthreads();
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+  const int64_t rows = row_start[njobs];
+  for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
     int lo = 0, hi = njobs - 1;
     while (lo < hi) {
       const int mid = (lo + hi + 1) >> 1;
-      if (job_start[mid] <= i) lo = mid; else hi = mid - 1;
+      if (row_start[mid] <= row) lo = mid; else hi = mid - 1;
     }
-    const dt_pack_job& jb = jobs[lo];
-    pack_weight_element(jb.w, jb.C_out, jb.C_in, jb.R, jb.S, jb.mode, jb.C_in_p, jb.Kpad, jb.out, i - job_start[lo]);
+    const dt_pack_job jb = jobs[lo];
+    const int r = static_cast<int>(row - row_start[lo]);
+    const int RS = jb.R * jb.S;
+    if (jb.mode == 0 || jb.mode == 2) {                  // small / check-mode layouts: element form on a 256-element chunk
+      const int64_t count = (lo + 1 < njobs ? jobs[lo + 1].start : total) - jb.start;
+      const int64_t i = static_cast<int64_t>(r) * 256 + threadIdx.x;
+      if (threadIdx.x < 256 && i < count) pack_weight_element(jb.w, jb.C_out, jb.C_in, jb.R, jb.S, jb.mode, jb.C_in_p, jb.Kpad, jb.out, i);
+      continue;
+    }
+    __nv_bfloat16* out = static_cast<__nv_bfloat16*>(jb.out) + static_cast<int64_t>(r) * jb.Kpad;
+    const int X = jb.mode == 1 ? jb.C_in : jb.C_out;     // source entries of this row: X runs of RS floats
+    const bool staged = X * RS <= kPackStage;
+    if (staged) {
+      __syncthreads();                                   // the previous row's readers are done with the staging buffer
+      if (jb.mode == 1) {
+        const float* src = jb.w + static_cast<int64_t>(r) * jb.C_in * RS;          // contiguous
+        for (int e = threadIdx.x; e < X * RS; e += blockDim.x) stage[e] = src[e];
+      } else {
+        const float* src = jb.w + static_cast<int64_t>(r) * RS;                    // + co * C_in * RS + tap
+        const int64_t cstride = static_cast<int64_t>(jb.C_in) * RS;
+        for (int e = threadIdx.x; e < X * RS; e += blockDim.x) stage[e] = src[(e / RS) * cstride + e % RS];
+      }
+      __syncthreads();
+    }
+    if (jb.mode == 1) {
+      for (int k = threadIdx.x; k < jb.Kpad; k += blockDim.x) {
+        float v = 0.f;
+        if (k < RS * jb.C_in) {
+          const int tap = k / jb.C_in, ci = k - tap * jb.C_in;
+          v = staged ? stage[ci * RS + tap] : jb.w[(static_cast<int64_t>(r) * jb.C_in + ci) * RS + tap];
+        }
+        out[k] = __float2bfloat16_rn(v);
+      }
+    } else {                                             // modes 3 / 4: row = input channel r, k = tf * Cop + co
+      const int Cop = jb.C_in_p;
+      for (int k = threadIdx.x; k < jb.Kpad; k += blockDim.x) {
+        float v = 0.f;
+        if (k < RS * Cop) {
+          const int tf = k / Cop, co = k - tf * Cop;
+          if (co < jb.C_out) {
+            const int tap = jb.mode == 3 ? RS - 1 - tf : tf;
+            v = staged ? stage[co * RS + tap] : jb.w[(static_cast<int64_t>(co) * jb.C_in + r) * RS + tap];
+          }
+        }
+        out[k] = __float2bfloat16_rn(v);
+      }
+    }
   }
 }
 
@@ -966,8 +1031,14 @@ int dt_pack_conv_weights_batched(const dt_pack_job* jobs_device, int njobs, int6
   DT_ARCH_GUARD();
   DT_REQUIRE(jobs_device != nullptr && njobs > 0 && total > 0, DT_ERR_BAD_SHAPE, "dt_pack_conv_weights_batched: empty job list");
   DT_REQUIRE(njobs <= 4096, DT_ERR_BAD_SHAPE, "dt_pack_conv_weights_batched: at most 4096 jobs");
-  pack_weights_batched_kernel<<<grid_for(total, 16), kThreads, njobs * sizeof(int64_t), static_cast<cudaStream_t>(stream)>>>(
-      jobs_device, njobs, total);
+  const size_t smem = (static_cast<size_t>(njobs) + 1) * sizeof(int64_t) + kPackStage * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    DT_CUDA(cudaFuncSetAttribute(pack_weights_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>((4096 + 1) * sizeof(int64_t) + kPackStage * sizeof(float))));
+    attr_set = true;
+  }
+  pack_weights_batched_kernel<<<dt_num_sms() * 6, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(jobs_device, njobs, total);
   DT_LAUNCH_CHECK();
   return DT_OK;
 }

@@ -605,3 +605,28 @@ def test_channel_sum_is_reproducible(dtype):
     for o in outs[1:]:
         assert torch.equal(o, outs[0])
     assert (outs[0].double() - ref).abs().max().item() < 1e-3 * max(1.0, ref.abs().max().item()) * 1e-2
+
+
+def test_batched_weight_packing_equals_single_layer_packing():
+    """dt_pack_conv_weights_batched (row-staged, every layer of the step in one launch) against dt_pack_conv_weight layer by
+    layer: every layout mode, 1x1 and 3x3 and 7x7, padded gradient strides, a row too long for the staging buffer, and a
+    refresh after the master weights changed.  Pure data movement + one bf16 rounding: bit-exact."""
+    g = torch.Generator().manual_seed(17)
+    packer = ops.WeightPacker(torch.device("cuda"))
+    specs = [((64, 4, 7, 7), 2, None), ((64, 4, 7, 7), 0, None), ((64, 64, 3, 3), 1, None), ((64, 64, 3, 3), 3, None),
+             ((128, 64, 3, 3), 4, None), ((128, 64, 1, 1), 1, None), ((128, 64, 1, 1), 4, None), ((256, 768, 3, 3), 1, None),
+             ((256, 768, 3, 3), 3, None), ((16, 32, 3, 3), 3, 16), ((3, 16, 3, 3), 3, 16), ((3, 16, 3, 3), 1, None),
+             ((8, 1024, 3, 3), 1, None), ((1024, 8, 3, 3), 3, None), ((32, 96, 3, 3), 0, None)]
+    ws = [torch.randn(shape, generator=g).cuda() for shape, _, _ in specs]
+    outs = [packer.get((i, mode, pad), w, mode, cout_pad=pad) for i, (w, (_, mode, pad)) in enumerate(zip(ws, specs))]
+    for rnd in range(2):
+        with torch.no_grad():
+            for w in ws:
+                w.mul_(1.5).add_(0.01 * (rnd + 1))
+        packer.refresh()
+        torch.cuda.synchronize()
+        for w, out, (shape, mode, pad) in zip(ws, outs, specs):
+            ref = ops.pack_conv_weight(w, mode, cout_pad=pad)
+            assert out.shape == ref.shape and out.dtype == ref.dtype
+            assert torch.equal(out.view(torch.int16) if out.dtype == torch.bfloat16 else out,
+                               ref.view(torch.int16) if ref.dtype == torch.bfloat16 else ref), (shape, mode, pad)
