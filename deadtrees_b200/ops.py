@@ -658,15 +658,21 @@ class WeightPacker:
         self.entries = {}           # key -> (w, out, mode, cinp, kpad)
         self._table = None
 
-    def get(self, key, w: torch.Tensor, mode: int, cout_pad: Optional[int] = None) -> torch.Tensor:
+    def get(self, key, w: torch.Tensor, mode: int, cout_pad: Optional[int] = None, rows_pad: Optional[int] = None) -> torch.Tensor:
+        """``rows_pad`` (mode 1): the packed matrix gets this many rows, the rows past C_out stay zero (the tensor-core
+        head takes 16 rows for its K <= 4 classes)."""
         ent = self.entries.get(key)
         if ent is not None and ent[0].data_ptr() == w.data_ptr():
-            return ent[1]
-        out = pack_conv_weight(w, mode, cout_pad=cout_pad)
-        cinp, kpad, _, _ = pack_conv_weight_geometry(w.shape, mode, cout_pad)
-        self.entries[key] = (w, out, mode, cinp, kpad)
+            return ent[5]
+        cinp, kpad, shape, dtype = pack_conv_weight_geometry(w.shape, mode, cout_pad)
+        if rows_pad is not None and mode == 1 and rows_pad > shape[0]:
+            full = torch.zeros((rows_pad, shape[1]), dtype=dtype, device=w.device)
+            out = pack_conv_weight(w, mode, out=full[: shape[0]], cout_pad=cout_pad)
+        else:
+            full = out = pack_conv_weight(w, mode, cout_pad=cout_pad)
+        self.entries[key] = (w, out, mode, cinp, kpad, full)
         self._table = None
-        return out
+        return full
 
     def refresh(self) -> None:
         if not self.entries:
@@ -674,7 +680,7 @@ class WeightPacker:
         if self._table is None:
             jobs = (_lib.PackJob * len(self.entries))()
             start = 0
-            for j, (w, out, mode, cinp, kpad) in enumerate(self.entries.values()):
+            for j, (w, out, mode, cinp, kpad, _) in enumerate(self.entries.values()):
                 C_out, C_in, R, S = w.shape
                 jobs[j] = _lib.PackJob(w.data_ptr(), out.data_ptr(), C_out, C_in, R, S, mode, cinp, kpad, 0, start)
                 start += out.numel()

@@ -10,6 +10,7 @@ gradients are fp32.
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -57,7 +58,8 @@ class UnetTrainEngine:
         self.set_process_group(None, world_size=1)
         # kernel layouts (bf16 forward / data-gradient packings) of every conv weight: one batched repack per step
         self.packer = ops.WeightPacker(dev)
-        import os
+        self.head_tc = precision == "bf16" and os.environ.get("DT_TRAIN_HEAD_TC", "1") == "1"
+        self._head_b16 = None
         # BatchNorm backward of relu(bn(y)) layers can recompute the ReLU mask from y instead of reading the activation
         # (dt_bn_train_bwd_relu); measured on B200 it is not faster (11.67 vs 11.60 ms per step: these passes are not
         # bound by the bytes of that one tensor), so it stays opt-in
@@ -163,8 +165,16 @@ class UnetTrainEngine:
             xcur = self._conv_bn(tape, a1, p + ".conv2.0", p + ".conv2.1", 1, 1)
         hw = self.params["segmentation_head.0.weight"]
         logits = torch.empty((N, self.classes, T, T), dtype=torch.float32, device=self.device)
-        ops.head(xcur, self.packer.get(("segmentation_head.0.weight", 0, None), hw, 0),
-                 self.params["segmentation_head.0.bias"], logits_nchw=logits)
+        if self.head_tc and xcur.shape[-1] == 16 and T % 16 == 0:
+            # bf16 path: the head on the tensor cores like every other layer (weights rounded to bf16, 16 padded rows)
+            if self._head_b16 is None:
+                self._head_b16 = torch.zeros(16, dtype=torch.float32, device=self.device)
+            self._head_b16[: self.classes].copy_(self.params["segmentation_head.0.bias"].detach())
+            ops.head_tc(xcur, self.packer.get(("segmentation_head.0.weight", 1, 16), hw, 1, rows_pad=16), self._head_b16,
+                        self.classes, logits_nchw=logits)
+        else:
+            ops.head(xcur, self.packer.get(("segmentation_head.0.weight", 0, None), hw, 0),
+                     self.params["segmentation_head.0.bias"], logits_nchw=logits)
         self._rec("head_fwd", "segmentation_head.0", x=xcur, y=logits)
         tape.append(("head", xcur))
         if self._nbt:

@@ -4,5 +4,5 @@ set -u
 mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
 timeout 400 python -m pytest tests/test_gpu_train.py -x -q -m gpu > gpurun_out/train_tests.log 2>&1; echo "tests exit=$?"; tail -n 2 gpurun_out/train_tests.log | cut -c1-200
-timeout 300 python bench.py --workload train --no-cpu-baseline --layer-table gpurun_out/train_layers.txt > gpurun_out/bench_train.log 2>&1; echo "bench train exit=$?"; head -c 330 gpurun_out/bench_train.log; echo
-grep "^wgrad" gpurun_out/train_layers.txt | awk '{s+=$3} END {print "sum of wgrad avg_us:", s}'
+echo skip-bench
+

@@ -454,7 +454,11 @@ def test_training_step_layerwise_teacher_forced(precision, n, T):
             if t["g_skip"] is not None:
                 assert torch.equal(cpu(t["g_skip"]), gc[:, cx:])
         elif kind == "head_fwd":
-            ref = F.conv2d(cpu(t["x"]), params["segmentation_head.0.weight"], params["segmentation_head.0.bias"], 1, 1)
+            # bf16 path: the head runs on the tensor cores like every other layer - bf16 weight operands, fp32 accumulation
+            hw = params["segmentation_head.0.weight"]
+            if precision == "bf16":
+                hw = hw.to(torch.bfloat16).float()
+            ref = F.conv2d(cpu(t["x"]), hw, params["segmentation_head.0.bias"], 1, 1)
             note("head", _rel(t["y"].cpu(), ref)); assert worst["head"] < acc_tol
     assert kinds == {"conv_bn_fwd", "bn_bwd", "wgrad", "dgrad", "maxpool_fwd", "maxpool_bwd", "upcat_fwd", "upcat_bwd", "head_fwd"}
     assert sum(1 for k, _, _ in trace if k == "wgrad") == 47 and sum(1 for k, _, _ in trace if k == "dgrad") == 46
