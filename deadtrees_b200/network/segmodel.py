@@ -284,10 +284,10 @@ class SemSegment(_Base):  # type: ignore[misc]
         absent classes are 0, as torchmetrics)."""
         import pandas as pd
         K = len(self.classes)
-        counts = None
+        counts = bad = None
         for out in outputs:
-            counts = ops.confusion_matrix(out["prediction"], out["target"], K, lu=out.get("lu"), counts=counts)
-            assert int(counts.bad.item()) == 0, "prediction / target outside [0, K)"
+            counts, bad = ops.confusion_matrix(out["prediction"], out["target"], K, lu=out.get("lu"), counts=counts, bad=bad)
+        assert int(bad.item()) == 0, "prediction / target outside [0, K)"      # one synchronisation per epoch
         cm = counts.cpu().numpy()
         norm = cm / np.maximum(cm.sum(axis=2, keepdims=True), 1)
         mats = {"cm_norm": norm[0], "cm_px": cm[0], "cm_norm_masked": norm[1], "cm_px_masked": cm[1]}

@@ -342,9 +342,10 @@ def train_transform(images: torch.Tensor, masks, lus, geom, bc, offset, scale, o
 
 
 def confusion_matrix(pred: torch.Tensor, target: torch.Tensor, K: int, lu: torch.Tensor = None,
-                     counts: torch.Tensor = None) -> torch.Tensor:
+                     counts: torch.Tensor = None, bad: torch.Tensor = None):
     """adds the (target, prediction) pairs to ``counts`` int64 (2, K, K): [0] all pixels, [1] the pixels with ``lu == 1``
-    (rows = target, as torchmetrics' ``confusion_matrix``).  ``counts=None`` starts a new pair of matrices."""
+    (rows = target, as torchmetrics' ``confusion_matrix``) -> ``(counts, bad)``; ``bad`` int32 (1,) becomes 1 when a value lies
+    outside [0, K).  ``counts=None`` / ``bad=None`` start new accumulators; pass the returned ones back to go on."""
     pred, target = _cuda(pred, "pred").contiguous(), _cuda(target, "target").contiguous()
     if pred.dtype not in (torch.uint8, torch.int64):
         pred = pred.long()
@@ -364,11 +365,11 @@ def confusion_matrix(pred: torch.Tensor, target: torch.Tensor, K: int, lu: torch
         lu_ptr, lu_elem = lu.data_ptr(), lu.element_size()
     if counts is None:
         counts = torch.zeros((2, K, K), dtype=torch.int64, device=pred.device)
-    bad = torch.zeros((1,), dtype=torch.int32, device=pred.device)
+    if bad is None:
+        bad = torch.zeros((1,), dtype=torch.int32, device=pred.device)
     check(load().dt_confusion_matrix(pred.data_ptr(), pred.element_size(), target.data_ptr(), lu_ptr, lu_elem, pred.numel(), K,
                                      counts.data_ptr(), bad.data_ptr(), stream_ptr()))
-    counts.bad = bad
-    return counts
+    return counts, bad
 
 
 def one_hot2dist(labels: torch.Tensor, K: int, truncate: bool = True) -> torch.Tensor:

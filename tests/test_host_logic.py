@@ -274,3 +274,29 @@ def test_train_transform_draws_follow_the_reference_distributions():
     assert abs(bc[on, 0].mean() - 1.0) < 0.005 and abs(bc[on, 1].mean()) < 0.005
     g2, b2 = draw_train_params(np.random.default_rng(1), 20000, beta_times_alpha=True)
     np.testing.assert_allclose(b2[:, 1], bc[:, 1] * bc[:, 0]) and np.testing.assert_array_equal(g2, geom)
+
+
+def test_gwdl_constructor_contract(capsys):
+    """GeneralizedWassersteinDiceLoss(dist_matrix, weighting_mode, reduction) as deadtrees/loss/gwdl.py:44-82: the matrix is
+    normalised to a maximum of 1 (with the reference's message), unknown weighting modes are rejected by the same assert."""
+    from deadtrees.loss.gwdl import GeneralizedWassersteinDiceLoss as ShimGW
+    from deadtrees_b200.loss.gwdl import GeneralizedWassersteinDiceLoss
+    assert ShimGW is GeneralizedWassersteinDiceLoss
+    gw = GeneralizedWassersteinDiceLoss(dist_matrix=np.array([[0.0, 2.0], [2.0, 0.0]]))
+    assert "Normalize the maximum of the distance matrix" in capsys.readouterr().out
+    assert gw.matrix() == [[0.0, 1.0], [1.0, 0.0]] and gw.num_classes == 2
+    gw = GeneralizedWassersteinDiceLoss(dist_matrix=torch.tensor([[0.0, 1.0], [0.5, 0.0]]))
+    assert capsys.readouterr().out == "" and gw.matrix() == [[0.0, 1.0], [0.5, 0.0]]
+    with pytest.raises(AssertionError):
+        GeneralizedWassersteinDiceLoss(dist_matrix=np.eye(2), weighting_mode="banana")
+    with pytest.raises(NotImplementedError):
+        GeneralizedWassersteinDiceLoss(dist_matrix=1 - np.eye(2), weighting_mode="GDL")
+
+
+def test_data_shim_exports():
+    import deadtrees.data.deadtreedata as d
+    for name in ("DeadtreeDatasetConfig", "val_transform", "train_transform", "transform", "BatchTrainTransform"):
+        assert hasattr(d, name), name
+    import deadtrees.loss.losses as l
+    for name in ("DiceLoss", "FocalLoss", "BoundaryLoss", "class2one_hot", "one_hot2dist"):
+        assert hasattr(l, name), name
