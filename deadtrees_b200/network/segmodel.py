@@ -286,7 +286,10 @@ class SemSegment(_Base):  # type: ignore[misc]
         K = len(self.classes)
         counts = bad = None
         for out in outputs:
-            counts, bad = ops.confusion_matrix(out["prediction"], out["target"], K, lu=out.get("lu"), counts=counts, bad=bad)
+            pred, lu = out["prediction"], out.get("lu")
+            if lu is not None and lu.device != pred.device:      # a land-use mask the trainer left on the host
+                lu = lu.to(pred.device)
+            counts, bad = ops.confusion_matrix(pred, out["target"].to(pred.device), K, lu=lu, counts=counts, bad=bad)
         assert int(bad.item()) == 0, "prediction / target outside [0, K)"      # one synchronisation per epoch
         cm = counts.cpu().numpy()
         norm = cm / np.maximum(cm.sum(axis=2, keepdims=True), 1)
