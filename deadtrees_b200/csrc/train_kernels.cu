@@ -57,7 +57,24 @@ inline int grid_for(int64_t work, int per_sm = 8) {
 // MODE 1: (sum gz, sum gz * yhat), gz = g * [a > 0], yhat = (y - mean) * invstd  -> BatchNorm backward
 // Thread = one 16-byte vector of channels, walking pixels; block partials are written to part[2][gridDim.x][C]
 // and summed in a fixed order by the finalize kernels (deterministic, no atomics).
-template <typename T, int MODE>
+// raw 16-byte vector of channels (8 bf16 or 4 floats): kept packed while several loads are in flight
+template <typename T> __device__ __forceinline__ uint4 load_raw(const T* p) { return *reinterpret_cast<const uint4*>(p); }
+template <typename T> __device__ __forceinline__ void unpack_raw(const uint4& v, float* f);
+template <> __device__ __forceinline__ void unpack_raw<float>(const uint4& v, float* f) {
+  f[0] = __uint_as_float(v.x); f[1] = __uint_as_float(v.y); f[2] = __uint_as_float(v.z); f[3] = __uint_as_float(v.w);
+}
+template <> __device__ __forceinline__ void unpack_raw<__nv_bfloat16>(const uint4& v, float* f) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 t = unpack_bf16x2(w[j]);
+    f[2 * j] = t.x; f[2 * j + 1] = t.y;
+  }
+}
+
+// U pixels per loop trip: their loads are issued together (packed registers) and accumulated in pixel order, so the sums are
+// the same bits for every U.  With one pixel per trip the statistics pass had 16 KB of loads in flight per SM (2.6 TB/s).
+template <typename T, int MODE, int U>
 __global__ void channel_reduce_kernel(const T* __restrict__ y, const T* __restrict__ g, const T* __restrict__ a,
                                       const float* __restrict__ mean, const float* __restrict__ invstd,
                                       const float* __restrict__ fscale, const float* __restrict__ fshift, int64_t M, int C,
@@ -80,16 +97,16 @@ __global__ void channel_reduce_kernel(const T* __restrict__ y, const T* __restri
       for (int j = 0; j < VN; ++j) { fsc[j] = fscale[v * VN + j]; fsh[j] = fshift[v * VN + j]; }
     }
   }
-  for (int64_t p = static_cast<int64_t>(blockIdx.x) * lanes + lane; p < M; p += static_cast<int64_t>(gridDim.x) * lanes) {
+  auto accumulate = [&](const uint4& ry, const uint4& rg, const uint4& ra) {
     float fy[VN];
-    load_vec<T>(y + p * C + v * VN, fy);
+    unpack_raw<T>(ry, fy);
     if (MODE == 0) {
 #pragma unroll
       for (int j = 0; j < VN; ++j) { s[j] += fy[j]; q[j] = fmaf(fy[j], fy[j], q[j]); }
     } else {
       float fg[VN], fa[VN];
-      load_vec<T>(g + p * C + v * VN, fg);
-      if (a) load_vec<T>(a + p * C + v * VN, fa);
+      unpack_raw<T>(rg, fg);
+      if (a) unpack_raw<T>(ra, fa);
 #pragma unroll
       for (int j = 0; j < VN; ++j) {
         const bool on = mask_y ? fmaf(fy[j], fsc[j], fsh[j]) > 0.f : (a == nullptr || fa[j] > 0.f);
@@ -98,6 +115,31 @@ __global__ void channel_reduce_kernel(const T* __restrict__ y, const T* __restri
         q[j] = fmaf(gz, (fy[j] - mu[j]) * is[j], q[j]);
       }
     }
+  };
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * lanes;
+  int64_t p = static_cast<int64_t>(blockIdx.x) * lanes + lane;
+  for (; p + (U - 1) * stride < M; p += U * stride) {
+    uint4 ry[U], rg[U], ra[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t off = (p + u * stride) * C + v * VN;
+      ry[u] = load_raw<T>(y + off);
+      if (MODE == 1) {
+        rg[u] = load_raw<T>(g + off);
+        if (a) ra[u] = load_raw<T>(a + off);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) accumulate(ry[u], rg[u], ra[u]);
+  }
+  for (; p < M; p += stride) {
+    const int64_t off = p * C + v * VN;
+    uint4 ry = load_raw<T>(y + off), rg = make_uint4(0u, 0u, 0u, 0u), ra = rg;
+    if (MODE == 1) {
+      rg = load_raw<T>(g + off);
+      if (a) ra = load_raw<T>(a + off);
+    }
+    accumulate(ry, rg, ra);
   }
   __shared__ float sh[2][kThreads][VN + 1];
 #pragma unroll
@@ -112,6 +154,12 @@ __global__ void channel_reduce_kernel(const T* __restrict__ y, const T* __restri
       part[(static_cast<int64_t>(gridDim.x) + blockIdx.x) * C + v * VN + j] = tq;
     }
   }
+}
+
+// DT_BN_REDUCE_UNROLL=0 selects one pixel per loop trip (A/B testing; the results are bit-identical)
+static bool reduce_unrolled() {
+  static const bool on = [] { const char* e = getenv("DT_BN_REDUCE_UNROLL"); return !(e && e[0] == '0'); }();
+  return on;
 }
 
 // sum of the block partials of channel c by one 128-thread block (fixed thread -> partial assignment and a fixed-order
@@ -761,6 +809,16 @@ __global__ void channel_sum_final_kernel(const float* __restrict__ part, int blo
   out[k] = static_cast<float>(t);
 }
 
+template <typename T, int MODE>
+void launch_channel_reduce(int nb, cudaStream_t s, const T* y, const T* g, const T* a, const float* mean, const float* invstd,
+                           const float* fscale, const float* fshift, int64_t M, int C, float* part) {
+  constexpr int U = MODE == 0 ? 4 : 2;
+  if (reduce_unrolled())
+    channel_reduce_kernel<T, MODE, U><<<nb, kThreads, 0, s>>>(y, g, a, mean, invstd, fscale, fshift, M, C, part);
+  else
+    channel_reduce_kernel<T, MODE, 1><<<nb, kThreads, 0, s>>>(y, g, a, mean, invstd, fscale, fshift, M, C, part);
+}
+
 int reduce_blocks(int64_t M, int C, int vn) {
   const int lanes = kThreads / (C / vn);
   int64_t b = (M + lanes * 16 - 1) / (static_cast<int64_t>(lanes) * 16);
@@ -796,8 +854,8 @@ int dt_bn_train_stats(const void* y, int64_t M, int C, int dtype, const float* g
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int nb = reduce_blocks(M, C, dtype == DT_BF16 ? 8 : 4);
   DT_DTYPE_SWITCH(dtype,
-      (channel_reduce_kernel<float, 0><<<nb, kThreads, 0, s>>>(static_cast<const float*>(y), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, M, C, workspace)),
-      (channel_reduce_kernel<__nv_bfloat16, 0><<<nb, kThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(y), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, M, C, workspace)));
+      (launch_channel_reduce<float, 0>(nb, s, static_cast<const float*>(y), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, M, C, workspace)),
+      (launch_channel_reduce<__nv_bfloat16, 0>(nb, s, static_cast<const __nv_bfloat16*>(y), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, M, C, workspace)));
   DT_LAUNCH_CHECK();
   bn_finalize_kernel<<<C, kFinThreads, 0, s>>>(workspace, nb, C, static_cast<double>(M), gamma, beta, eps, momentum,
                                                      running_mean, running_var, scale, shift, mean, invstd);
@@ -832,8 +890,8 @@ static int bn_train_bwd_impl(const void* g, const void* a, const void* y, int64_
   float* c2 = c1 + C;
   const int64_t nvec = M * C / vn;
   DT_DTYPE_SWITCH(dtype,
-      (channel_reduce_kernel<float, 1><<<nb, kThreads, 0, s>>>(static_cast<const float*>(y), static_cast<const float*>(g), static_cast<const float*>(a), mean, invstd, scale, fshift, M, C, workspace)),
-      (channel_reduce_kernel<__nv_bfloat16, 1><<<nb, kThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(y), static_cast<const __nv_bfloat16*>(g), static_cast<const __nv_bfloat16*>(a), mean, invstd, scale, fshift, M, C, workspace)));
+      (launch_channel_reduce<float, 1>(nb, s, static_cast<const float*>(y), static_cast<const float*>(g), static_cast<const float*>(a), mean, invstd, scale, fshift, M, C, workspace)),
+      (launch_channel_reduce<__nv_bfloat16, 1>(nb, s, static_cast<const __nv_bfloat16*>(y), static_cast<const __nv_bfloat16*>(g), static_cast<const __nv_bfloat16*>(a), mean, invstd, scale, fshift, M, C, workspace)));
   DT_LAUNCH_CHECK();
   bn_bwd_finalize_kernel<<<C, kFinThreads, 0, s>>>(workspace, nb, C, static_cast<double>(M), dgamma, dbeta, c1, c2);
   DT_LAUNCH_CHECK();
