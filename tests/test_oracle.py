@@ -221,3 +221,25 @@ def test_train_transform_oracle_properties():
     assert bc.max() == 255 and (bc >= img).all()
     out2, m2, _ = ref_augment.train_transform(img, mask, lu, 2, 3, 0.9, -0.1, in_channels=3, classes=2)
     assert out2.shape == (3, 32, 32) and m2.max() == 1 and m2.dtype == np.int64
+
+
+def test_gwdl_oracle_properties():
+    """oracle Wasserstein Dice: one sample = the paper's per-sample formula; a confident correct prediction -> ~0; a target
+    without foreground -> true positives 0 and a loss of ~1; samples of a batch are coupled only through the true-positive
+    term (the reference's broadcast), so a batch of identical samples equals B times the per-sample true positives."""
+    g = torch.Generator().manual_seed(3)
+    D = [[0.0, 1.0, 1.0], [1.0, 0.0, 0.5], [1.0, 0.5, 0.0]]
+    M = torch.tensor(D, dtype=torch.float64)
+    z = torch.randn(1, 3, 12, 10, generator=g)
+    t = torch.randint(0, 3, (1, 12, 10), generator=g)
+    q = z.reshape(1, 3, -1).softmax(1).double()
+    w = (M[t.reshape(1, -1)].permute(0, 2, 1) * q).sum(1)
+    tp = ((t.reshape(1, -1) != 0) * (1 - w)).sum()
+    expect = 1 - (2 * tp + 2.0 ** -52) / (2 * tp + w.sum() + 2.0 ** -52)
+    np.testing.assert_allclose(ref_losses.gwdl_loss(z, t, D).item(), expect.item(), rtol=1e-12)
+    sure = torch.nn.functional.one_hot(t, 3).permute(0, 3, 1, 2).float() * 60.0
+    assert ref_losses.gwdl_loss(sure, t, D).item() < 1e-6
+    assert ref_losses.gwdl_loss(z, torch.zeros_like(t), D).item() > 1 - 1e-9
+    zb, tb = z.repeat(3, 1, 1, 1), t.repeat(3, 1, 1)
+    batch = 1 - (2 * 3 * tp + 2.0 ** -52) / (2 * 3 * tp + w.sum() + 2.0 ** -52)
+    np.testing.assert_allclose(ref_losses.gwdl_loss(zb, tb, D).item(), batch.item(), rtol=1e-7)
