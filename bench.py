@@ -524,7 +524,7 @@ def main_train(a):
 
     def step_device():
         if use_graph:                        # inputs already in the graph's static buffers
-            gstep.graph.replay()
+            gstep.replay()
             return gstep.terms.total_loss
         return eager_step()
 

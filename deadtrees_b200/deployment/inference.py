@@ -151,7 +151,7 @@ class MosaicInference:
 
     def run(self, mosaic: torch.Tensor, layout: str = "hwc", tile_rows: Optional[Tuple[int, int]] = None,
             out: Optional[torch.Tensor] = None, halo_hook=None, host_src: Optional[torch.Tensor] = None,
-            host_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+            host_out: Optional[torch.Tensor] = None, banded: Optional[bool] = None) -> torch.Tensor:
         """mosaic: CUDA uint8 (H, W, C) ["hwc"] or (C, H, W) ["chw"] -> uint8 class ids (H, W).
 
         ``tile_rows=(r0, r1)`` restricts the work to that range of tile rows (multi-GPU sharding); the
@@ -160,7 +160,11 @@ class MosaicInference:
         Host pipeline ("hwc" only): with ``host_src`` (pinned uint8 (H, W, C)) the rows a batch of tiles needs are copied
         into ``mosaic`` on a copy stream while the previous batches compute; with ``host_out`` (pinned uint8 (H, W)) and
         no ``halo_hook`` the mask is stitched in bands as soon as their tile rows are done and each band goes back to the
-        host behind the compute.  Only the first band's upload and the last band's download are exposed."""
+        host behind the compute.  Only the first band's upload and the last band's download are exposed.
+
+        ``banded``: stitch the blended mask band by band behind the batches (True) or in one launch over the shard
+        (False); default: bands while a batch's logits fit in L2.  A shard that starts below the first tile row blends
+        its first ``overlap`` rows with the previous shard's logits, which only ``halo_hook`` can provide."""
         H, W = (mosaic.shape[0], mosaic.shape[1]) if layout == "hwc" else (mosaic.shape[1], mosaic.shape[2])
         T, ov, eng = self.tile, self.overlap, self.engine
         gy, gx = overlap_grid(H, W, T, ov)
@@ -183,8 +187,12 @@ class MosaicInference:
         # single GPU: the mask is stitched band by band as soon as the tile rows of a band are done - the logits a band
         # needs were written by the last batches and are still in L2 (a batch of 135 tiles holds 53 MB of logits)
         # (only while a batch's logits fit in L2; with larger batches one launch over the whole shard is faster)
-        banded = halo_hook is None and (piped_out or ov == 0 or
-                                        bt * T * T * eng.classes * logits.element_size() <= (96 << 20))
+        if ov > 0 and halo and halo_hook is None:
+            raise ValueError("a shard with tile_rows[0] > 0 and overlap > 0 needs the previous shard's boundary logits: "
+                             "pass halo_hook (deadtrees_b200.sharding.make_halo_hook)")
+        if banded is None or halo_hook is not None or piped_out or ov == 0:
+            banded = halo_hook is None and (piped_out or ov == 0 or
+                                            bt * T * T * eng.classes * logits.element_size() <= (96 << 20))
         if (piped_in or host_out is not None) and layout != "hwc":
             raise ValueError("the host pipeline takes interleaved (H, W, C) mosaics")
         main = torch.cuda.current_stream()

@@ -87,7 +87,9 @@ class Unet(nn.Module):
         return tuple(p._version for p in self.parameters()) + tuple(b._version for b in self.buffers())
 
     def engine(self) -> UnetEngine:
-        key = (self._param_version(), self.precision, next(self.parameters()).device)
+        # ops.STATE_GENERATION: the optimizer / train-mode BatchNorm kernels and CUDA-graph replays write parameters and
+        # running statistics through raw pointers, which never bump `_version`
+        key = (self._param_version(), ops.STATE_GENERATION, self.precision, next(self.parameters()).device)
         if self._engine is None or key != self._engine_key:
             if self.training:
                 raise NotImplementedError(
@@ -97,8 +99,9 @@ class Unet(nn.Module):
         return self._engine
 
     def set_precision(self, precision: str) -> "Unet":
-        self.precision = precision
-        self._train_engine = None
+        if precision != self.precision:
+            self.precision = precision
+            self._train_engine = None     # an optimizer attached to the old engine refuses to step (FusedAdam.step)
         return self
 
     def train_engine(self):

@@ -21,6 +21,15 @@ LAUNCHES = 0
 # bench instrumentation: when PROFILE is a dict, conv / gather / stitch launches are bracketed by CUDA
 # events on the launching stream and appended as (kind, start, end, algorithmic_work) tuples
 PROFILE = None
+# bumped whenever a raw-pointer kernel (or a CUDA-graph replay of one) changes parameters or BatchNorm running statistics:
+# those writes do not touch torch's per-tensor version counters, so caches of folded / repacked weights
+# (``Unet.engine()``) carry this counter in their key
+STATE_GENERATION = 0
+
+
+def bump_state_generation() -> None:
+    global STATE_GENERATION
+    STATE_GENERATION += 1
 
 
 class _Timed:
@@ -454,6 +463,7 @@ def adam_step_dev(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Te
                   beta2: float, eps: float, sumsq_acc: Optional[torch.Tensor], max_norm: float,
                   loss: Optional[torch.Tensor], scratch: torch.Tensor) -> None:
     """graph-capturable Adam: state = float (2,) {step, lr} on the device; skipped when `loss` is not finite."""
+    bump_state_generation()
     check(load().dt_adam_step_dev(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), state.data_ptr(),
                                   beta1, beta2, eps, ptr(sumsq_acc), max_norm, ptr(loss), scratch.data_ptr(), stream_ptr()))
 
@@ -464,6 +474,7 @@ def sumsq(g: torch.Tensor, acc: torch.Tensor) -> None:
 
 def adam_step(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor, *, lr: float, beta1: float,
               beta2: float, eps: float, step: int, sumsq_acc: Optional[torch.Tensor], max_norm: float) -> None:
+    bump_state_generation()
     check(load().dt_adam_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, beta1, beta2,
                               eps, step, ptr(sumsq_acc), max_norm, stream_ptr()))
 
@@ -487,6 +498,8 @@ def bn_train_stats(y: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, run
     Cc = y.shape[-1]
     M = y.numel() // Cc
     scale, shift, mean, invstd = (torch.empty(Cc, dtype=torch.float32, device=y.device) for _ in range(4))
+    if running_mean is not None or running_var is not None:
+        bump_state_generation()
     check(load().dt_bn_train_stats(y.data_ptr(), M, Cc, _dt(y), gamma.data_ptr(), beta.data_ptr(), eps, momentum,
                                    ptr(running_mean), ptr(running_var), scale.data_ptr(), shift.data_ptr(),
                                    mean.data_ptr(), invstd.data_ptr(), _reduce_ws(y.device).data_ptr(), stream_ptr()))
@@ -663,7 +676,7 @@ class WeightPacker:
         """``rows_pad`` (mode 1): the packed matrix gets this many rows, the rows past C_out stay zero (the tensor-core
         head takes 16 rows for its K <= 4 classes)."""
         ent = self.entries.get(key)
-        if ent is not None and ent[0].data_ptr() == w.data_ptr():
+        if ent is not None and ent[6] == w.data_ptr():          # the address registered in the job table, not `ent[0]` (== w)
             return ent[5]
         cinp, kpad, shape, dtype = pack_conv_weight_geometry(w.shape, mode, cout_pad)
         if rows_pad is not None and mode == 1 and rows_pad > shape[0]:
@@ -671,9 +684,14 @@ class WeightPacker:
             out = pack_conv_weight(w, mode, out=full[: shape[0]], cout_pad=cout_pad)
         else:
             full = out = pack_conv_weight(w, mode, cout_pad=cout_pad)
-        self.entries[key] = (w, out, mode, cinp, kpad, full)
+        self.entries[key] = (w, out, mode, cinp, kpad, full, w.data_ptr())
         self._table = None
         return full
+
+    def clear(self) -> None:
+        """forget every registered layout (the master weights moved, e.g. ``UnetTrainEngine.flatten_parameters``)."""
+        self.entries.clear()
+        self._table = None
 
     def refresh(self) -> None:
         if not self.entries:
@@ -681,7 +699,10 @@ class WeightPacker:
         if self._table is None:
             jobs = (_lib.PackJob * len(self.entries))()
             start = 0
-            for j, (w, out, mode, cinp, kpad, _) in enumerate(self.entries.values()):
+            for j, (w, out, mode, cinp, kpad, _, wptr) in enumerate(self.entries.values()):
+                if w.data_ptr() != wptr:
+                    raise _lib.DeadtreesB200Error("a master weight moved after its kernel layout was registered; call "
+                                                  "WeightPacker.clear() (flatten_parameters does) before the next forward")
                 C_out, C_in, R, S = w.shape
                 jobs[j] = _lib.PackJob(w.data_ptr(), out.data_ptr(), C_out, C_in, R, S, mode, cinp, kpad, 0, start)
                 start += out.numel()

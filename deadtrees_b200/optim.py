@@ -24,11 +24,24 @@ class FusedAdam(torch.optim.Optimizer):
             raise ValueError("attach_engine needs one param group holding every parameter of the engine")
         fp = engine.flatten_parameters()
         dev = fp.device
+        self._engine = engine
         self._flat = dict(p=fp, g=engine.reducer.flat, m=torch.zeros_like(fp), v=torch.zeros_like(fp),
                           state=torch.tensor([0.0, self.param_groups[0]["lr"]], dtype=torch.float32, device=dev),
                           scratch=torch.zeros(4, dtype=torch.float32, device=dev),
                           acc=torch.zeros(1, dtype=torch.float64, device=dev), lr=self.param_groups[0]["lr"])
         return self
+
+    @torch.no_grad()
+    def push_lr(self) -> None:
+        """flat path: copies a learning rate changed by a scheduler (``CosineAnnealingLR`` of ``configure_optimizers``,
+        segmodel.py:420-429) into the device-side step state.  ``GraphedTrainStep`` calls this before every replay - the
+        captured graph reads the rate from the device, so the copy stays outside the graph."""
+        if self._flat is None:
+            return
+        f, lr = self._flat, self.param_groups[0]["lr"]
+        if lr != f["lr"]:
+            f["lr"] = lr
+            f["state"][1:2].fill_(lr)
 
     @torch.no_grad()
     def step(self, closure=None, loss: torch.Tensor = None):
@@ -37,9 +50,18 @@ class FusedAdam(torch.optim.Optimizer):
             # every piece of step state lives on the device (step count, lr, clip factor): the launches below can be
             # captured in a CUDA graph and replayed; a changed learning rate is pushed with one tiny copy
             f, group = self._flat, self.param_groups[0]
-            if group["lr"] != f["lr"]:
-                f["lr"] = group["lr"]
-                f["state"][1:2].fill_(group["lr"])
+            eng = self._engine
+            if (eng.reducer.flat.data_ptr() != f["g"].data_ptr() or eng.flat_params is None
+                    or eng.flat_params.data_ptr() != f["p"].data_ptr() or getattr(eng.model, "_train_engine", eng) is not eng):
+                raise RuntimeError("the train engine this optimizer was attached to has been rebuilt (set_precision / device "
+                                   "change) or its buffers replaced: call configure_optimizers() / attach_engine() again")
+            self.push_lr()
+            if loss is not None and group["max_grad_norm"] <= 0 and eng.reducer.world > 1:
+                # data parallel without clipping: the non-finite-loss skip must be the same decision on every rank (with
+                # clipping the all-reduced gradient norm already carries a NaN / Inf to all of them)
+                import torch.distributed as dist
+                loss = loss.detach().clone().reshape(1)
+                dist.all_reduce(loss, group=eng.reducer.group)
             acc = None
             if group["max_grad_norm"] > 0:
                 acc = f["acc"]

@@ -19,8 +19,12 @@ import torch.distributed as dist
 
 class GradBucketReducer:
     def __init__(self, named_shapes: Sequence[Tuple[str, torch.Size]], device, bucket_bytes: int = 25 << 20,
-                 group=None, world_size: Optional[int] = None):
-        """``named_shapes``: (name, shape) of every parameter in the order the backward pass produces the gradients."""
+                 group=None, world_size: Optional[int] = None, flat: Optional[torch.Tensor] = None):
+        """``named_shapes``: (name, shape) of every parameter in the order the backward pass produces the gradients.
+        ``flat``: an existing flat buffer of the same layout to re-bucket (offsets do not depend on ``bucket_bytes``).
+
+        BatchNorm running statistics are per-rank, exactly as under plain ``DistributedDataParallel`` without SyncBN
+        (every rank normalises with its own batch): they are NOT averaged here; rank 0's are the ones a checkpoint keeps."""
         self.group = group
         self.world = world_size if world_size is not None else (dist.get_world_size(group) if dist.is_initialized() else 1)
         self.device = torch.device(device)
@@ -39,7 +43,9 @@ class GradBucketReducer:
         sizes.append(off)
         # ONE flat fp32 buffer holds every gradient in backward order; a bucket is a contiguous slice of it, so the
         # optimizer can run a single fused clip + Adam launch over `flat`
-        self.flat = torch.zeros(sum(sizes), dtype=torch.float32, device=self.device)
+        if flat is not None and (flat.numel() != sum(sizes) or flat.device != self.device or flat.dtype != torch.float32):
+            raise ValueError("flat gradient buffer does not match the parameter layout")
+        self.flat = flat if flat is not None else torch.zeros(sum(sizes), dtype=torch.float32, device=self.device)
         self.bucket_offsets = [sum(sizes[:i]) for i in range(len(sizes))]
         self.buckets = [self.flat[o: o + n] for o, n in zip(self.bucket_offsets, sizes)]
         self.expect = [0] * len(sizes)

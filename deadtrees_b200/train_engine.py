@@ -58,6 +58,7 @@ class UnetTrainEngine:
         self.set_process_group(None, world_size=1)
         # kernel layouts (bf16 forward / data-gradient packings) of every conv weight: one batched repack per step
         self.packer = ops.WeightPacker(dev)
+        self.flat_params = None
         self.head_tc = precision == "bf16" and os.environ.get("DT_TRAIN_HEAD_TC", "1") == "1"
         self._head_b16 = None
         # BatchNorm backward of relu(bn(y)) layers can recompute the ReLU mask from y instead of reading the activation
@@ -69,9 +70,12 @@ class UnetTrainEngine:
         self.pair_flag = CONV_PAIR if (precision == "bf16" and os.environ.get("DT_CONV_PAIR", "1") != "0") else 0
 
     def set_process_group(self, group, world_size: Optional[int] = None, bucket_bytes: int = 25 << 20) -> None:
+        """(re)buckets the flat gradient buffer for ``group``.  The buffer itself is kept: the position of a gradient does
+        not depend on the bucket size, so an optimizer that already holds ``reducer.flat`` keeps stepping on live data."""
         order = backward_param_order(self.param_names)
+        old = self.reducer.flat if self.reducer is not None else None
         self.reducer = GradBucketReducer([(n, self.params[n].shape) for n in order], self.device, bucket_bytes=bucket_bytes,
-                                         group=group, world_size=world_size)
+                                         group=group, world_size=world_size, flat=old)
 
     def _rec(self, kind: str, name: str, **tensors) -> None:
         if self.trace is not None:
@@ -80,7 +84,7 @@ class UnetTrainEngine:
     def flatten_parameters(self) -> torch.Tensor:
         """re-points every parameter into ONE flat fp32 buffer with the layout of the flat gradient buffer, so the
         optimizer is a single fused clip + Adam launch (``FusedAdam.attach_engine``).  Idempotent."""
-        if getattr(self, "flat_params", None) is None or self.flat_params.numel() != self.reducer.flat.numel():
+        if self.flat_params is None or self.flat_params.numel() != self.reducer.flat.numel():
             flat = torch.zeros_like(self.reducer.flat)
             with torch.no_grad():
                 for n, p in self.params.items():
@@ -89,6 +93,7 @@ class UnetTrainEngine:
                     v.copy_(p.data)
                     p.data = v
             self.flat_params = flat
+            self.packer.clear()           # the job table of the batched repack holds the OLD addresses of the weights
         return self.flat_params
 
     # ---- forward pieces --------------------------------------------------------------------------------

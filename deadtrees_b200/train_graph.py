@@ -82,11 +82,19 @@ class GraphedTrainStep:
         for n, p in self.engine.params.items():
             p.grad = grads[n]
 
+    def replay(self) -> None:
+        """one step on whatever the static buffers hold: pushes a learning rate changed by a scheduler to the device
+        (outside the graph, same stream), replays, and invalidates the caches of folded weights (``Unet.engine()``) -
+        a replay changes parameters and running statistics without touching any tensor version counter."""
+        self.opt.push_lr()
+        self.graph.replay()
+        ops.bump_state_generation()
+
     def __call__(self, img: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
         """copies the batch into the static buffers, replays the step, returns the (device) total loss."""
         self.img.copy_(img, non_blocking=True)
         self.mask.copy_(mask, non_blocking=True)
-        self.graph.replay()
+        self.replay()
         return self.total[0]
 
     def prefetch(self, img: torch.Tensor, mask: torch.Tensor) -> None:
@@ -115,7 +123,7 @@ class GraphedTrainStep:
         self.mask.copy_(self._stage[1], non_blocking=True)
         self._stage_free.record(main)
         self._staged = False
-        self.graph.replay()
+        self.replay()
         return self.total[0]
 
     def check(self) -> float:

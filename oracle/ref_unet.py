@@ -186,6 +186,84 @@ def build_reference_unet(in_channels: int = 3, classes: int = 3, seed: int = 0,
     return model.eval()
 
 
+PATTERN_WAVES = ((97.0, 131.0, 80.0), (61.0, 173.0, 70.0), (149.0, 83.0, 90.0), (113.0, 71.0, 75.0))
+NORM_MEAN = (0.3661029729, 0.3875165941, 0.3501133538, 0.5797285859)     # deadtreedata.py:31-32
+NORM_STD = (0.2388708549, 0.2103625723, 0.2050272174, 0.2025812523)
+
+
+def synthetic_pattern(oy: int, ox: int, H: int, W: int, channels: int, rng, noise_sd: float = 20.0):
+    """the synthetic orthophoto of the tests and of bench.py (low-frequency pattern + noise) at mosaic
+    offset (oy, ox): -> (uint8 (H, W, channels), labels int64 (H, W) = the channel whose noise-free pattern is largest,
+    among the first three)."""
+    import numpy as np
+    yy, xx = np.mgrid[oy:oy + H, ox:ox + W]
+    base = np.stack([127.0 + amp * np.sin(yy / fy) * np.cos(xx / fx) for fy, fx, amp in PATTERN_WAVES[:channels]], -1)
+    img = np.clip(base + rng.normal(0.0, noise_sd, size=base.shape), 0, 255).astype(np.uint8)
+    return img, base[..., :3].argmax(-1).astype(np.int64)
+
+
+def normalize_u8(u8_nhwc) -> torch.Tensor:
+    """``val_transform`` arithmetic (deadtreedata.py:148-154) on a uint8 (N, H, W, C) array -> fp32 (N, C, H, W)."""
+    c = u8_nhwc.shape[-1]
+    x = torch.from_numpy(u8_nhwc).float()
+    x = (x - 255.0 * torch.tensor(NORM_MEAN[:c])) * (1.0 / (255.0 * torch.tensor(NORM_STD[:c])))
+    return x.permute(0, 3, 1, 2).contiguous()
+
+
+def build_trained_unet(in_channels: int = 3, classes: int = 3, seed: int = 0, steps: int = 100, tile: int = 64,
+                       batch: int = 8, lr: float = 1e-3, cache_dir=None) -> Unet:
+    """The oracle network after ``steps`` steps of the reference's own training recipe on the CPU (train-mode forward,
+    ``["DICE", "FOCAL"]`` loss terms of ``oracle/ref_losses.py`` - pinned to ``deadtrees/loss/losses.py`` -, clip 0.5, Adam;
+    ``segmodel.py:210-229,420-429``) on the synthetic pattern task above (label = strongest channel of the noise-free
+    pattern, ``classes`` <= 3).  Returned in eval mode.
+
+    Why: a freshly initialised BatchNorm network is chaotic - measured here, the relative difference between a bf16
+    and an fp32 forward grows 1.2x per conv layer (the mean-field gradient-explosion factor of BN at init) to 17 % rms at
+    the logits, whose argmax margins are dense around zero - so the north star's "2e-2 / 99.9 % of pixels" cannot hold
+    for ANY bf16 arithmetic on such weights (the bf16 restatement below is itself 0.8 abs / 6 % of pixels away from its
+    own fp32 forward).  After 100 training steps the same architecture is the well-conditioned function a checkpoint
+    of the reference is: bf16-vs-fp32 logit error 5e-3 rms, masks 99.98 % equal.  ~25 s on 8 host threads; the
+    state-dict is cached under ``cache_dir`` (default ``tests/golden/_cache``, git-ignored) keyed by the arguments."""
+    import numpy as np
+    from pathlib import Path
+    from . import ref_train
+    if classes > 3:
+        raise ValueError("the synthetic task has at most 3 classes")
+    cache_dir = Path(cache_dir) if cache_dir is not None else Path(__file__).resolve().parent.parent / "tests" / "golden" / "_cache"
+    f = cache_dir / f"trained_unet_v1_c{in_channels}_k{classes}_s{seed}_n{steps}_t{tile}_b{batch}_lr{lr:g}.pt"
+    model = build_reference_unet(in_channels, classes, seed=seed, randomize_bn=False)
+    if f.exists():
+        try:
+            model.load_state_dict(torch.load(f, map_location="cpu"))
+            return model.eval()
+        except Exception:
+            pass
+    rng = np.random.default_rng(seed + 4000)
+    state = torch.random.get_rng_state()
+    opt = torch.optim.Adam(model.parameters(), lr=lr)
+    try:
+        for _ in range(steps):
+            imgs, masks = [], []
+            for _b in range(batch):
+                oy, ox = rng.integers(0, 5000, 2)
+                u8, lab = synthetic_pattern(int(oy), int(ox), tile, tile, in_channels, rng)
+                imgs.append(u8)
+                masks.append(np.minimum(lab, classes - 1))
+            ref_train.train_step(model, normalize_u8(np.stack(imgs)), torch.from_numpy(np.stack(masks)),
+                                 lr=lr, clip=0.5, optimizer=opt)
+    finally:
+        torch.random.set_rng_state(state)
+    model.eval()
+    try:
+        cache_dir.mkdir(parents=True, exist_ok=True)
+        tmp = f.with_suffix(f".tmp{__import__('os').getpid()}")
+        torch.save(model.state_dict(), tmp)
+        tmp.replace(f)
+    except OSError:
+        pass
+    return model
+
+
 def run_inference(model: nn.Module, x: torch.Tensor, channels: int) -> torch.Tensor:
     """``PyTorchInference.run`` semantics (``deployment/inference.py:47-62``) on CPU."""
     if x.dim() == 3:

@@ -634,3 +634,117 @@ def test_batched_weight_packing_equals_single_layer_packing():
             assert out.shape == ref.shape and out.dtype == ref.dtype
             assert torch.equal(out.view(torch.int16) if out.dtype == torch.bfloat16 else out,
                                ref.view(torch.int16) if ref.dtype == torch.bfloat16 else ref), (shape, mode, pad)
+
+
+# ---- state that raw-pointer kernels / graph replays change behind torch's back ---------------------------
+def _small_seg(cin=4, precision="bf16", clip=0.5):
+    oracle = oracle_model(cin, 3)
+    seg = SemSegment(dict(NETWORK, in_channels=cin, precision=precision), dict(TRAINING, gradient_clip_val=clip))
+    seg.model.load_state_dict(oracle.state_dict())
+    return seg.cuda()
+
+
+def test_eval_engine_follows_graph_replays():
+    """eval -> graph replays -> eval: the replays move weights and running statistics through raw pointers (no tensor
+    version changes), the cached inference engine must still be rebuilt from the NEW state."""
+    from deadtrees_b200.engine import UnetEngine
+    from deadtrees_b200.train_graph import GraphedTrainStep
+    cin, n, T = 4, 2, 64
+    seg = _small_seg(cin)
+    img, mask = _batch(n, cin, T, 3)
+    seg.eval()
+    with torch.no_grad():
+        before = seg.model(img.cuda()).clone()
+    seg.train()
+    (opt,), _ = seg.configure_optimizers()
+    gs = GraphedTrainStep(seg, opt, n, T)
+    seg.eval()
+    with torch.no_grad():
+        restored = seg.model(img.cuda()).clone()
+    assert torch.equal(restored, before)          # capture + warm-up restore every piece of state
+    seg.train()
+    for _ in range(3):
+        gs(img.pin_memory(), mask.pin_memory())
+    seg.eval()
+    with torch.no_grad():
+        after = seg.model(img.cuda()).clone()
+    fresh = UnetEngine(seg.model.state_dict(), cin, 3, precision="bf16")
+    want = fresh.forward(ops.pack_input_nchw(img.cuda(), cin, torch.bfloat16), want_logits_nchw=True)["logits_nchw"]
+    torch.cuda.synchronize()
+    assert not torch.equal(after, before), "eval after training still used the engine folded from the old weights"
+    assert torch.equal(after, want)
+
+
+def test_graphed_step_follows_lr_changes():
+    """a scheduler changes param_groups[0]['lr'] between steps (CosineAnnealingLR, segmodel.py:420-429): the replayed
+    graph must use the new rate exactly like the eager step."""
+    from deadtrees_b200.train_graph import GraphedTrainStep
+    cin, n, T = 4, 2, 64
+    img, mask = _batch(n, cin, T, 3)
+    stats = [{"file": f"t{i}"} for i in range(n)]
+    lrs = [3e-4, 1e-3, 5e-5]
+    segs = []
+    for graphed in (False, True):
+        seg = _small_seg(cin).train()
+        (opt,), (sch,) = seg.configure_optimizers()
+        gs = GraphedTrainStep(seg, opt, n, T) if graphed else None
+        for lr in lrs:
+            opt.param_groups[0]["lr"] = lr
+            if graphed:
+                gs(img.pin_memory(), mask.pin_memory())
+            else:
+                seg.training_step({"main": (img.cuda(), mask.cuda(), None, torch.zeros(n), stats)}, 0).backward()
+                opt.step()
+        torch.cuda.synchronize()
+        segs.append(seg)
+    moved = 0.0
+    ref = dict(oracle_model(cin, 3).named_parameters())
+    for (name, p), (_, q) in zip(segs[0].model.named_parameters(), segs[1].model.named_parameters()):
+        assert (p.detach() - q.detach()).abs().max().item() < 1e-6, name
+        moved = max(moved, (p.detach().cpu() - ref[name].detach()).abs().max().item())
+    assert moved > 1e-3          # the 1e-3 step is visible: a rate frozen at 3e-4 would move every weight less than 1e-3
+
+
+def test_weight_packer_follows_flattened_parameters():
+    """a train-mode forward BEFORE the optimizer is attached registers kernel layouts at the parameters' old addresses;
+    attach_engine() moves the parameters into the flat buffer - the repack must read the new storage."""
+    cin, n, T = 4, 2, 64
+    img, mask = _batch(n, cin, T, 3)
+    stats = [{"file": f"t{i}"} for i in range(n)]
+    batch = {"main": (img.cuda(), mask.cuda(), None, torch.zeros(n), stats)}
+    segs = []
+    for early_forward in (False, True):
+        seg = _small_seg(cin).train()
+        if early_forward:
+            snap = {k: v.clone() for k, v in seg.model.state_dict().items()}
+            seg.training_step(batch, 0)                   # registers the layouts; restore the BN statistics it moved
+            seg.model.load_state_dict(snap)
+        (opt,), _ = seg.configure_optimizers()
+        for _ in range(3):
+            seg.training_step(batch, 0).backward()
+            opt.step()
+        torch.cuda.synchronize()
+        segs.append(seg)
+    for (name, p), (_, q) in zip(segs[0].model.named_parameters(), segs[1].model.named_parameters()):
+        assert (p.detach() - q.detach()).abs().max().item() < 1e-6, name
+
+
+def test_optimizer_survives_rebucketing_and_refuses_a_rebuilt_engine():
+    cin, n, T = 4, 2, 64
+    img, mask = _batch(n, cin, T, 3)
+    batch = {"main": (img.cuda(), mask.cuda(), None, torch.zeros(n), [{"file": "a"}, {"file": "b"}])}
+    seg = _small_seg(cin).train()
+    (opt,), _ = seg.configure_optimizers()
+    eng = seg.model.train_engine()
+    flat = eng.reducer.flat
+    eng.set_process_group(None, world_size=1, bucket_bytes=1 << 20)      # after configure_optimizers
+    assert eng.reducer.flat.data_ptr() == flat.data_ptr() and len(eng.reducer.buckets) > 4
+    before = seg.model.encoder.conv1.weight.detach().clone()
+    seg.training_step(batch, 0).backward()
+    opt.step()
+    torch.cuda.synchronize()
+    assert (seg.model.encoder.conv1.weight.detach() - before).abs().max().item() > 0      # stepped on live gradients
+    seg.model.set_precision("fp32")                                       # rebuilds the train engine
+    seg.training_step(batch, 0).backward()
+    with pytest.raises(RuntimeError, match="rebuilt"):
+        opt.step()

@@ -233,3 +233,6 @@ def test_mosaic_pipeline_vs_oracle(precision, H, W, T, ov, bt):
                     lg[:gx_, T - ov:] = saved["send"]
             part = mi.run(torch.from_numpy(mosaic).cuda(), "hwc", tile_rows=(r0, r1), out=out, halo_hook=hook if ov else None)
         assert torch.equal(out, full)
+        if ov:   # a lower shard without the neighbour's boundary logits would blend uninitialised memory: refused
+            with pytest.raises(ValueError, match="boundary logits"):
+                mi.run(torch.from_numpy(mosaic).cuda(), "hwc", tile_rows=(gy // 2, gy), out=out)

@@ -300,3 +300,27 @@ def test_data_shim_exports():
     import deadtrees.loss.losses as l
     for name in ("DiceLoss", "FocalLoss", "BoundaryLoss", "class2one_hot", "one_hot2dist"):
         assert hasattr(l, name), name
+
+
+def test_rebucketing_keeps_the_flat_gradient_buffer():
+    """set_process_group() after configure_optimizers() must not leave the optimizer on a stale buffer - the
+    reducer re-buckets the SAME flat buffer (a gradient's offset does not depend on the bucket size)."""
+    from deadtrees_b200.parallel import GradBucketReducer, backward_param_order
+    shapes = _param_shapes()
+    order = backward_param_order([n for n, _ in shapes])
+    named = [(n, dict(shapes)[n]) for n in order]
+    a = GradBucketReducer(named, "cpu", bucket_bytes=25 << 20, world_size=1)
+    b = GradBucketReducer(named, "cpu", bucket_bytes=1 << 20, world_size=1, flat=a.flat)
+    assert b.flat.data_ptr() == a.flat.data_ptr() and len(b.buckets) > len(a.buckets)
+    for n, _ in named:
+        assert a.flat_offset(n) == b.flat_offset(n)
+        assert a.view(n).data_ptr() == b.view(n).data_ptr()
+    with pytest.raises(ValueError):
+        GradBucketReducer(named[:-1], "cpu", world_size=1, flat=a.flat)
+
+
+def test_state_generation_counter():
+    from deadtrees_b200 import ops
+    g = ops.STATE_GENERATION
+    ops.bump_state_generation()
+    assert ops.STATE_GENERATION == g + 1
