@@ -55,6 +55,10 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--layer-table", default=None, help="write per-layer conv timings (CUDA events) to this file")
     ap.add_argument("--no-profile", action="store_true", help="skip the per-kernel CUDA-event instrumentation")
+    ap.add_argument("--no-extra", action="store_true",
+                    help="infer workload: skip the cfg5 (1024x1024 tiles, batch 32 per GPU) and cfg4 (training step) "
+                         "measurements that the default run appends to the JSON line as `cfg5` / `cfg4`")
+    ap.add_argument("--extra-steps", type=int, default=20, help="timed steps of the appended cfg4 / cfg5 measurements")
     return ap.parse_args()
 
 
@@ -63,7 +67,8 @@ def workload_config(a, n_tiles):
                         f"mosaic, tile {a.tile}, overlap {a.overlap} ({n_tiles} tiles), blended stitch",
             "mosaic": [a.size, a.size, 3], "tile": a.tile, "overlap": a.overlap, "tiles": n_tiles,
             "batch_tiles": a.batch_tiles, "classes": 3, "in_channels": 3,
-            "l2_policy": "inputs larger than L2 (300 MB mosaic, >1 GB of activations per step); no explicit flush"}
+            "l2_policy": "inputs larger than L2 (300 MB mosaic, >1 GB of activations per step); no explicit flush",
+            "parallelism": f"tile-range shards x{a.gpus}"}
 
 
 def synthetic_mosaic(size: int, device, seed: int = 1234) -> torch.Tensor:
@@ -83,12 +88,13 @@ def ncu_conv_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum of the conv launches of one 135-tile batch, from the committed
     `ncu --set full` capture (profiles/r01_convs_ncu_full_v6.txt, scripts/gpu_profile2.sh) - not measured in this run."""
     import re
-    f = ROOT / "profiles" / "r01_convs_ncu_full_v6.txt"
-    if not f.exists():
-        return None
-    m = re.search(r"= ([0-9.]+) GB per (\d+)-tile batch", f.read_text())
-    n = sum(1 for l in f.read_text().splitlines() if "_kernel" in l)
-    return (float(m.group(1)) * 1e9, int(m.group(2)), n) if m and n else None
+    cands = sorted((ROOT / "profiles").glob("r0*_convs_ncu_full*.txt"))
+    for f in reversed(cands):
+        m = re.search(r"= ([0-9.]+) GB per (\d+)-tile batch", f.read_text())
+        n = sum(1 for l in f.read_text().splitlines() if "_kernel" in l)
+        if m and n:
+            return float(m.group(1)) * 1e9, int(m.group(2)), n, f.name
+    return None
 
 
 def peaks():
@@ -224,20 +230,12 @@ def main_reference(a):
 def main_b200(a):
     import torch.distributed as dist
     from deadtrees_b200 import ops
-    from deadtrees_b200._lib import require_device
     from deadtrees_b200.deployment.inference import MosaicInference, overlap_grid
     from deadtrees_b200.engine import UnetEngine, conv_flops_per_tile
     from deadtrees_b200.sharding import make_halo_hook, split_tile_rows
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    require_device()
-    dev = torch.device("cuda", local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+    ctx = dist_context()
+    rank, world, local, dev = ctx
 
     # random-init weights of the reference architecture (seeded; the oracle is only the INITIALISER here,
     # so that bench, tests and the CPU baseline share one state-dict) -- built on CPU, then handed over
@@ -346,7 +344,7 @@ def main_b200(a):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": a.precision if a.precision == "bf16" else "f32", "data": "synthetic",
-        "config": dict(workload_config(a, n_tiles), parallelism=f"tile-row shards x{world}"),
+        "config": workload_config(a, n_tiles),
         "mpixel_per_s": value * T * T / 1e6, "mosaic_mpixel_per_s": H * W / 1e6 / (ms_step / 1e3),
         "e2e": {"value": n_tiles / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e},
@@ -363,7 +361,9 @@ def main_b200(a):
         ts, ws, ns = agg("stitch")
         if tc > 0:
             ach = wc / tc / 1e12
-            out["roofline"] = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit GEMM, all conv layers)",
+            out["roofline"] = {"bound": "tensor",
+                               "kernel": "all conv launches of the Unet (tcgen05 implicit GEMM: conv_stem_rows, conv_res, "
+                                         "conv_halo, conv_halo_quad, conv_pair, conv_tc, tail_fused kernels)",
                                "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"],
                                "traffic": None, "launches": nc, "share_of_step": tc * 1e3 / ms_prof_total,
                                "flops_per_tile": conv_flops_per_tile(T, 3, 3), "peak_source": pk["source"]}
@@ -372,8 +372,8 @@ def main_b200(a):
                 bt = min(a.batch_tiles, max((r1 - r0) * gx, 1))
                 out["roofline"]["traffic"] = tr[0] / tr[1] * bt / tr[2]
                 out["roofline"]["traffic_source"] = (
-                    f"ncu --set full capture of the {tr[2]} conv launches of one {tr[1]}-tile batch "
-                    f"(profiles/r01_convs_ncu_full_v6.txt): {tr[0] / 1e9:.3f} GB DRAM read + write per batch = "
+                    f"NOT measured in this run: committed ncu --set full capture of the {tr[2]} conv launches of one "
+                    f"{tr[1]}-tile batch (profiles/{tr[3]}): {tr[0] / 1e9:.3f} GB DRAM read + write per batch = "
                     f"{tr[0] / tr[1] / 1e6:.1f} MB per tile; scaled to this run's {bt}-tile batches and averaged per "
                     f"launch; bf16 activations in + out of all convs, unfused: 44.6 MB per tile")
         hb = {}
@@ -420,10 +420,17 @@ def main_b200(a):
                                "sample": f"one block of {n_s} tiles of {T}x{T} through the reference flow (make_blocks -> "
                                          f"normalise -> Unet fp32 -> argmax -> unmake_blocks; Unet = oracle port, tiler = "
                                          f"{'reference code (baseline/_ref)' if used_ref else 'oracle port'}), best of 3"}
+    gstep = None
+    if not a.no_extra and a.precision == "bf16":
+        # BASELINE configs[4] and configs[3] behind the same default invocation, at every N: extra keys of the one line
+        del mi, mosaic, mask, host_mosaic, host_mask
+        engine._ws.clear()
+        torch.cuda.empty_cache()
+        out["cfg5"] = cfg5_measure(a, ctx, engine, a.extra_steps, 3)
+        out["cfg4"], gstep = train_measure(a, ctx, a.extra_steps, 3, with_profile=True, with_cpu=not a.no_cpu_baseline)
     if rank == 0:
-        print(json.dumps(out))
-    if world > 1:
-        dist.destroy_process_group()
+        print(json.dumps(out), flush=True)
+    finish(world, gstep)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -474,22 +481,30 @@ def main_train_reference(a):
         "e2e": {"value": tps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
 
 
-def main_train(a):
+def dist_context():
+    """(rank, world, local, device); initialises NCCL under torchrun."""
     import torch.distributed as dist
-    from deadtrees_b200 import ops
     from deadtrees_b200._lib import require_device
-    from deadtrees_b200.network.segmodel import SemSegment
-
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     require_device()
     dev = torch.device("cuda", local)
-    if world > 1:
+    if world > 1 and not dist.is_initialized():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-    B, T, cin, K = a.train_batch, a.tile, 4, 3
+    return rank, world, local, dev
+
+
+def train_measure(a, ctx, steps: int, warmup: int, with_profile: bool, with_cpu: bool):
+    """cfg4: one data-parallel training step per timed step -> (JSON dict, GraphedTrainStep or None)."""
+    import torch.distributed as dist
+    from deadtrees_b200 import ops
+    from deadtrees_b200.network.segmodel import SemSegment
+
+    rank, world, local, dev = ctx
+    B, T, cin, K = a.train_batch, 256, 4, 3
     net = dict(architecture="unet", encoder_name="resnet34", encoder_depth=5, encoder_weights=None,
                decoder_channels=[256, 128, 64, 32, 16], losses=["DICE", "FOCAL"], classes=["bg", "a", "b"],
                in_channels=cin, precision=a.precision)
@@ -566,30 +581,32 @@ def main_train(a):
             ms = float(t.item())
         return ms, ops.LAUNCHES - l0, prof
 
-    for _ in range(max(a.warmup, 3)):
+    for _ in range(max(warmup, 3)):
         step_device()
     sampler = ClockSampler(local)
     sampler.start()
-    ms_total, launches, _ = timed(step_device, a.steps)
+    ms_total, launches, _ = timed(step_device, steps)
     clocks = sampler.stop()
     if use_graph:
-        launches = launches_per_replay * a.steps          # kernels replayed by the graph (no per-kernel Python call)
-    ms_step = ms_total / a.steps
-    # per-kernel CUDA events need individually launched kernels: a separate, eager, instrumented pass
+        launches = launches_per_replay * steps          # kernels replayed by the graph (no per-kernel Python call)
+    ms_step = ms_total / steps
+    # per-kernel CUDA events need individually launched kernels: a separate, eager, instrumented pass (single GPU: the
+    # eager step would re-bucket nothing, but its per-kernel NCCL launches are not what the graph replays)
     prof = None
-    if not a.no_profile:
+    psteps = min(steps, 5)
+    if with_profile and world == 1:
         eager_step()
-        _, _, prof = timed(eager_step, a.steps, profile=True)
+        _, _, prof = timed(eager_step, psteps, profile=True)
     for _ in range(2):
         step_e2e()
-    ms_e2e_total, _, _ = timed(step_e2e, a.steps)
-    ms_e2e = ms_e2e_total / a.steps
+    ms_e2e_total, _, _ = timed(step_e2e, steps)
+    ms_e2e = ms_e2e_total / steps
     last_loss = step_e2e()
     pk = peaks()
     fl = train_flops_per_tile(T, cin, K)
     out = {
         "metric": "unet_train_tiles_per_s", "value": world * B / (ms_step / 1e3), "unit": UNIT, "n_gpus": world,
-        "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "steps": steps, "warmup": max(warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": a.precision if a.precision == "bf16" else "f32", "data": "synthetic",
         "config": {"workload": f"cfg4: Unet-resnet34 training step (train-mode BN fwd + Dice/Focal + bwd + clip 0.5 + Adam), "
                                f"{B} RGB+NIR {T}x{T} tiles per GPU, data parallel x{world}",
@@ -615,11 +632,11 @@ def main_train(a):
             ach = w_all / t_all / 1e12
             out["roofline"] = {"bound": "tensor", "kernel": "tcgen05 conv forward + dgrad (forward kernels on transposed weights) + MN-major wgrad",
                                "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"],
-                               "traffic": None, "launches": nf + nd + nw, "share_of_step": (t_all * 1e3 / a.steps) / ms_step,
+                               "traffic": None, "launches": nf + nd + nw, "share_of_step": (t_all * 1e3 / psteps) / ms_step,
                                "peak_source": pk["source"],
-                               "breakdown": {"forward": {"ms_per_step": 1e3 * tf / a.steps, "tflops": wf / max(tf, 1e-12) / 1e12, "launches": nf},
-                                             "dgrad_tc": {"ms_per_step": 1e3 * td / a.steps, "tflops": wd / max(td, 1e-12) / 1e12, "launches": nd},
-                                             "wgrad_tc": {"ms_per_step": 1e3 * tw / a.steps, "tflops": ww / max(tw, 1e-12) / 1e12, "launches": nw}}}
+                               "breakdown": {"forward": {"ms_per_step": 1e3 * tf / psteps, "tflops": wf / max(tf, 1e-12) / 1e12, "launches": nf},
+                                             "dgrad_tc": {"ms_per_step": 1e3 * td / psteps, "tflops": wd / max(td, 1e-12) / 1e12, "launches": nd},
+                                             "wgrad_tc": {"ms_per_step": 1e3 * tw / psteps, "tflops": ww / max(tw, 1e-12) / 1e12, "launches": nw}}}
         if a.layer_table and rank == 0:
             per = {}
             for e0, e1, wk, tag in conv + prof.get("wgrad", []):
@@ -628,9 +645,9 @@ def main_train(a):
             with open(a.layer_table, "w") as fh:
                 fh.write(f"{'op.layer':58s} {'launches':>8s} {'avg_us':>9s} {'TFLOP/s':>9s} {'share%':>7s}\n")
                 for tag, (ms, wk, n) in per.items():
-                    fh.write(f"{tag:58s} {n:8d} {1e3 * ms / n:9.1f} {wk / (ms / 1e3) / 1e12:9.1f} {100 * (ms / a.steps) / ms_step:7.2f}\n")
-                fh.write(f"tensor-core kernels {1e3 * t_all / a.steps:.2f} ms of {ms_step:.2f} ms per step\n")
-    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+                    fh.write(f"{tag:58s} {n:8d} {1e3 * ms / n:9.1f} {wk / (ms / 1e3) / 1e12:9.1f} {100 * (ms / psteps) / ms_step:7.2f}\n")
+                fh.write(f"tensor-core kernels {1e3 * t_all / psteps:.2f} ms of {ms_step:.2f} ms per step\n")
+    if rank == 0 and world == 1 and with_cpu:
         from oracle import ref_train, ref_unet
         torch.set_num_threads(os.cpu_count() or 1)
         model = ref_unet.build_reference_unet(cin, K, seed=0)
@@ -644,21 +661,111 @@ def main_train(a):
         out["cpu_baseline"] = {"value": 8 / min(ts[1:]), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                                "sample": f"one oracle training step on 8 RGB+NIR tiles of {T}x{T} (torch CPU autograd fp32 + reference "
                                          f"loss terms + clip + Adam), best of 2 after 1 warm-up"}
-    if rank == 0:
-        print(json.dumps(out), flush=True)
-    if world > 1:
-        # a CUDA graph that holds NCCL nodes must be gone before the communicator is torn down (destroy_process_group
-        # waited forever with the graph alive); leave the process without the teardown once every rank is done
+    return out, (gstep if use_graph else None)
+
+
+def finish(world: int, gstep) -> None:
+    """process teardown.  A CUDA graph that holds NCCL nodes must be gone before the communicator is torn down
+    (destroy_process_group waited forever with the graph alive): leave the process without the teardown once every rank
+    is done."""
+    import torch.distributed as dist
+    if world <= 1:
+        return
+    torch.cuda.synchronize()
+    dist.barrier()
+    if gstep is not None:
+        gstep.graph.reset()
+        del gstep
         torch.cuda.synchronize()
-        dist.barrier()
-        if use_graph:
-            gstep.graph.reset()
-            del gstep
-            torch.cuda.synchronize()
-            sys.stdout.flush()
-            sys.stderr.flush()
-            os._exit(0)
-        dist.destroy_process_group()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
+    dist.destroy_process_group()
+
+
+def main_train(a):
+    ctx = dist_context()
+    out, gstep = train_measure(a, ctx, a.steps, a.warmup, not a.no_profile, not a.no_cpu_baseline)
+    if ctx[0] == 0:
+        print(json.dumps(out), flush=True)
+    finish(ctx[1], gstep)
+
+
+def cfg5_measure(a, ctx, engine, steps: int, warmup: int):
+    """cfg5: large-tile inference, 32 RGB tiles of 1024 x 1024 per GPU (a 4096 x 8192 uint8 block, overlap 0) through the
+    same pipeline (gather+normalise -> Unet -> head+argmax -> mask stitch); every GPU of the box runs its own block
+    (weak scaling): whole-box tiles/s and Mpixel/s, convs against the tensor roofline."""
+    import torch.distributed as dist
+    from deadtrees_b200 import ops
+    from deadtrees_b200.deployment.inference import MosaicInference
+    from deadtrees_b200.engine import conv_flops_per_tile
+    rank, world, local, dev = ctx
+    T, gy, gx = 1024, 4, 8
+    n = gy * gx
+    mi = MosaicInference(engine, tile=T, overlap=0, batch_tiles=16)
+    g = torch.Generator(device=dev).manual_seed(77 + rank)
+    block = torch.randint(0, 256, (gy * T, gx * T, 3), dtype=torch.uint8, device=dev, generator=g)
+    host_block = torch.empty(block.shape, dtype=torch.uint8, pin_memory=True)
+    host_block.copy_(block)
+    host_mask = torch.empty((gy * T, gx * T), dtype=torch.uint8, pin_memory=True)
+    mask = torch.zeros((gy * T, gx * T), dtype=torch.uint8, device=dev)
+
+    def timed(fn, k, profile=False):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ops.PROFILE = {} if profile else None
+        l0 = ops.LAUNCHES
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = e0.elapsed_time(e1)
+        prof, ops.PROFILE = ops.PROFILE, None
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, ops.LAUNCHES - l0, prof
+
+    dev_step = lambda: mi.run(block, "hwc", out=mask)
+    e2e_step = lambda: mi.run(block, "hwc", out=mask, host_src=host_block, host_out=host_mask)
+    for _ in range(max(warmup, 3)):
+        dev_step()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms_total, launches, _ = timed(dev_step, steps)
+    clocks = sampler.stop()
+    ms = ms_total / steps
+    ms_prof, _, prof = timed(dev_step, min(steps, 5), profile=True)
+    for _ in range(2):
+        e2e_step()
+    ms_e2e = timed(e2e_step, steps)[0] / steps
+    pk = peaks()
+    evs = prof.get("conv", [])
+    tc = sum(ev[0].elapsed_time(ev[1]) for ev in evs) / 1e3
+    wc = sum(ev[2] for ev in evs)
+    out = {"metric": "unet_large_tile_inference_tiles_per_s", "value": world * n / (ms / 1e3), "unit": "tiles/s",
+           "mpixel_per_s": world * n * T * T / 1e6 / (ms / 1e3), "n_gpus": world, "steps": steps, "warmup": max(warmup, 3),
+           "ms_per_step": ms, "scaling": "weak", "dtype": "bf16", "gpu_launches": int(launches), "clocks": clocks,
+           "config": {"workload": "cfg5: Unet-resnet34 inference on 32 RGB uint8 tiles of 1024x1024 per GPU (4096x8192 block, "
+                                  "overlap 0), batches of 16 tiles", "tile": T, "tiles_per_gpu": n, "batch_tiles": 16,
+                      "l2_policy": "100 MB block and > 8 GB of activations per step; no explicit flush"},
+           "e2e": {"value": world * n / (ms_e2e / 1e3), "unit": "tiles/s", "ms_per_step": ms_e2e,
+                   "h2d_bytes_per_step": int(block.numel()), "d2h_bytes_per_step": int(mask.numel())}}
+    if tc > 0:
+        out["roofline"] = {"bound": "tensor", "kernel": "all conv launches (tcgen05 implicit GEMM)", "achieved": wc / tc / 1e12,
+                           "peak": pk["tflops"], "unit": "TFLOP/s", "frac": wc / tc / 1e12 / pk["tflops"], "traffic": None,
+                           "launches": len(evs), "share_of_step": tc * 1e3 / ms_prof, "flops_per_tile": conv_flops_per_tile(T, 3, 3),
+                           "peak_source": pk["source"]}
+    del mi, block, mask
+    engine._ws.clear()
+    torch.cuda.empty_cache()
+    return out
 
 
 if __name__ == "__main__":

@@ -1,7 +1,7 @@
 """GPU parity at the north star's tolerance: the bf16 tensor-core path against the **fp32** oracle.
 
 BASELINE.json: "logits must match within 2e-2 abs in bf16 (1e-4 in an fp32 check mode), and argmax masks must agree on
-at least 99.9% of pixels".  The weights are the oracle network after 100 steps of the reference's own training recipe
+at least 99.9% of pixels".  The weights are the oracle network after 200 steps of the reference's own training recipe
 (``oracle/ref_unet.build_trained_unet``): a freshly initialised BatchNorm network amplifies ANY rounding by 1.2x per
 layer (DESIGN.md "bf16 parity"; those weights stay in ``test_gpu_unet.py`` as stress tests), a trained one does not.
 
