@@ -17,6 +17,7 @@ LIB_PATH = _PKG / "libdeadtrees_b200.so"
 DT_BF16, DT_F32 = 0, 1
 CONV_FORCE_GATHER, CONV_FORCE_DIRECT, CONV_NO_HALO, CONV_X_PAD3, CONV_TRANSPOSED, CONV_NO_QUAD, CONV_UPS_FOLDED = 1, 2, 4, 8, 16, 32, 64
 CONV_PAIR = 128
+CONV_NO_ROW = 256
 
 
 class DeadtreesB200Error(RuntimeError):

@@ -39,6 +39,14 @@ int dt_check_device();  // DT_OK iff the current device is compute capability 10
     if (rc__ != DT_OK) return rc__;       \
   } while (0)
 
+// A/B switch of the row-streaming kernels (conv_row.cu): DT_CONV_ROW=0 in the environment sends every layer to the
+// tile kernels (conv_res / conv_halo); read on every call so a test can flip it
+#include <stdlib.h>
+static inline bool dt_row_kernels_enabled() {
+  const char* e = getenv("DT_CONV_ROW");
+  return !(e && e[0] == '0');
+}
+
 static inline int dt_num_sms() {
   static thread_local int cached = 0;
   if (!cached) {
@@ -171,6 +179,18 @@ __device__ __forceinline__ void tc_fence_after() {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
 
+// one lane of a converged warp (PTX elect.sync): the form ptxas recognises as "exactly one thread", so a region guarded by
+// it keeps warp-uniform operands (UMMA descriptors, TMEM addresses) in uniform registers
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- TMA ---------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" :: "l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
@@ -226,6 +246,17 @@ __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t (&v)[16]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// writes zeros to 16 consecutive columns of this warp's 32 TMEM lanes (row-streaming kernels clear an accumulator after
+// they have read it, so that every MMA can run with accumulate = 1)
+__device__ __forceinline__ void tmem_st_zero_x16(uint32_t taddr) {
+  const uint32_t z = 0u;
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};"
+      :: "r"(taddr), "r"(z) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() {
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
 // K-major, 128-byte-swizzled shared-memory matrix descriptor (rows of 64 bf16 = 128 B, 8-row groups

@@ -318,6 +318,8 @@ int dt_conv2d_direct(const dt_conv_desc* d, int Ho, int Wo, int Kpad, int stem, 
   return DT_OK;
 }
 
+int dt_head_row(const void* x, int N, int H, int W, int K, const void* w_packed, const float* bias16, float* logits_nchw,
+                void* logits_nhwc, uint8_t* mask, cudaStream_t s);
 int dt_head_res(const void* x, int N, int H, int W, int K, const void* w_packed, const float* bias16,
                 float* logits_nchw, void* logits_nhwc, uint8_t* mask, cudaStream_t s);
 
@@ -383,6 +385,10 @@ int dt_head_fwd_tc(const void* x, int N, int H, int W, int K, const void* w_pack
   DT_REQUIRE(N > 0 && H > 0 && W > 0 && K >= 1 && K <= 4, DT_ERR_BAD_SHAPE, "dt_head_fwd_tc: bad shape");
   DT_REQUIRE(reinterpret_cast<uintptr_t>(x) % 16 == 0 && reinterpret_cast<uintptr_t>(w_packed) % 16 == 0,
              DT_ERR_BAD_ALIGN, "dt_head_fwd_tc: tensors must be 16-byte aligned");
+  if (dt_row_kernels_enabled()) {   // row-streaming kernel (vertical taps in N) where the width allows; same results
+    const int rr = dt_head_row(x, N, H, W, K, w_packed, bias16, logits_nchw, logits_nhwc, mask, static_cast<cudaStream_t>(stream));
+    if (rr != DT_ERR_UNSUPPORTED) return rr;
+  }
   const int rc = dt_head_res(x, N, H, W, K, w_packed, bias16, logits_nchw, logits_nhwc, mask,
                              static_cast<cudaStream_t>(stream));
   DT_REQUIRE(rc != DT_ERR_UNSUPPORTED, DT_ERR_BAD_SHAPE, "dt_head_fwd_tc: needs H %% 16 == 0 and W %% 8 == 0 (got %dx%d)", H, W);

@@ -119,7 +119,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // warp-uniform for the compiler (uniform registers)
   const int patches_per_tile = p.n_xslab + 4 * p.n_sslab;   // patch instance pi: x slabs first, then skip planes
 
   if (warp == 0) {
@@ -169,9 +169,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // This thread's instruction stream paces the tensor core: descriptor high words are loop invariants and the
-      // k-step offsets are immediates; per weight chunk only the tap's window offset is looked up.
+    {
+      // The whole warp runs the warp-uniform bookkeeping (barrier waits, descriptor arithmetic: uniform registers); one
+      // elected lane issues the MMAs and commits.  Inside an `if (lane == 0)` region every operand took an R2UR / ELECT
+      // round trip - ~100 clk of pure issue per MMA, more than the tensor pipe needs for N <= 64.
       const uint64_t a_hi = umma_desc(0u, PITCH * ROW_BYTES, CW == 64 ? 2u : (CW == 32 ? 4u : 6u));
       const uint64_t b_hi = umma_desc(0u, 1024u, 2u);
       int sa = 0, sb = 0, acc = 0;
@@ -194,31 +195,37 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             const uint64_t b_d = b_hi + (smem_u32(smem_b + sb * B_BYTES) >> 4);
             if (CW == BK) {
               const uint64_t a_t = a_d + ((static_cast<uint32_t>(pd.off[q]) * ROW_BYTES) >> 4);
+              if (elect_one()) {
 #pragma unroll
-              for (int k = 0; k < BK / 16; ++k) {
-                umma_bf16_ss(d_tmem, a_t + 2 * k, b_d + 2 * k, idesc, accum);
-                accum = 1;
+                for (int k = 0; k < BK / 16; ++k) umma_bf16_ss(d_tmem, a_t + 2 * k, b_d + 2 * k, idesc, (accum | k) ? 1u : 0u);
+                umma_commit(&empty_b[sb]);
               }
+              accum = 1;
             } else {
               // narrow layer: chunk q holds K elements [64q, 64q+64) = taps (64q+16k)/CW in natural order
               const int ksteps = min(BK / 16, (9 * CW - q * BK) / 16);
+              if (elect_one()) {
 #pragma unroll
-              for (int k = 0; k < BK / 16; ++k) {
-                if (k < ksteps) {
-                  const int kk = q * BK + k * 16;
-                  const uint32_t off = static_cast<uint32_t>(pd.off_by_tap[kk / CW]) * ROW_BYTES + (kk % CW) * 2;
-                  umma_bf16_ss(d_tmem, a_d + (off >> 4), b_d + 2 * k, idesc, accum);
-                  accum = 1;
+                for (int k = 0; k < BK / 16; ++k) {
+                  if (k < ksteps) {
+                    const int kk = q * BK + k * 16;
+                    const uint32_t off = static_cast<uint32_t>(pd.off_by_tap[kk / CW]) * ROW_BYTES + (kk % CW) * 2;
+                    umma_bf16_ss(d_tmem, a_d + (off >> 4), b_d + 2 * k, idesc, (accum | k) ? 1u : 0u);
+                  }
                 }
+                umma_commit(&empty_b[sb]);
               }
+              accum = 1;
             }
-            umma_commit(&empty_b[sb]);
+            __syncwarp();
             if (++sb == p.b_slots) { sb = 0; pb ^= 1u; }
           }
-          umma_commit(&empty_a[sa]);
+          if (elect_one()) umma_commit(&empty_a[sa]);
+          __syncwarp();
           if (++sa == A_SLOTS) { sa = 0; pa ^= 1u; }
         }
-        umma_commit(&tmem_full[acc]);
+        if (elect_one()) umma_commit(&tmem_full[acc]);
+        __syncwarp();
         if ((acc ^= 1) == 0) pacc ^= 1u;
       }
     }
@@ -377,7 +384,7 @@ conv_halo_quad_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // warp-uniform for the compiler (uniform registers)
   const int patches_per_tile = p.n_xslab + 4 * p.n_sslab;
   // region geometry: total_tiles = tiles_w * tiles_h * N (C_out == BN: one channel tile)
   auto region = [&](int tile, int& n, int& h0, int& w0) {
@@ -447,7 +454,7 @@ conv_halo_quad_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {   // whole warp: uniform bookkeeping; an elected lane issues (see conv_halo_kernel)
       const uint64_t a_hi = umma_desc(0u, PITCH * ROW_BYTES, 2u);
       const uint64_t b_hi = umma_desc(0u, 1024u, 2u);
       int sa = 0, sb = 0, acc = 0;
@@ -472,11 +479,14 @@ conv_halo_quad_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
                 const uint32_t off = static_cast<uint32_t>(((cls >> 1) + (e >> 1)) * PITCH + (cls & 1) + (e & 1));
                 const uint64_t a_t = a_d + ((off * ROW_BYTES) >> 4);
                 const uint32_t d_tmem = tmem_base + (acc * 4 + cls) * BN;
+                if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < BK / 16; ++k)
-                  umma_bf16_ss(d_tmem, a_t + 2 * k, b_d + 2 * k, idesc, (((started >> cls) & 1u) | k) != 0 ? 1u : 0u);
+                  for (int k = 0; k < BK / 16; ++k)
+                    umma_bf16_ss(d_tmem, a_t + 2 * k, b_d + 2 * k, idesc, (((started >> cls) & 1u) | k) != 0 ? 1u : 0u);
+                  umma_commit(&empty_b[sb]);
+                }
+                __syncwarp();
                 started |= 1u << cls;
-                umma_commit(&empty_b[sb]);
                 if (++sb == p.b_slots) { sb = 0; pb ^= 1u; }
               }
             }
@@ -485,16 +495,19 @@ conv_halo_quad_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
               mbar_wait(&full_b[sb], pb);
               tc_fence_after();
               const uint64_t b_d = b_hi + (smem_u32(smem_b + sb * B_BYTES) >> 4);
+              if (elect_one()) {
 #pragma unroll
-              for (int cls = 0; cls < 4; ++cls) {
-                const uint64_t a_t = a_d + ((static_cast<uint32_t>(p.patch[cls][0].off_by_tap[tap]) * ROW_BYTES) >> 4);
-                const uint32_t d_tmem = tmem_base + (acc * 4 + cls) * BN;
+                for (int cls = 0; cls < 4; ++cls) {
+                  const uint64_t a_t = a_d + ((static_cast<uint32_t>(p.patch[cls][0].off_by_tap[tap]) * ROW_BYTES) >> 4);
+                  const uint32_t d_tmem = tmem_base + (acc * 4 + cls) * BN;
 #pragma unroll
-                for (int k = 0; k < BK / 16; ++k)
-                  umma_bf16_ss(d_tmem, a_t + 2 * k, b_d + 2 * k, idesc, (((started >> cls) & 1u) | k) != 0 ? 1u : 0u);
+                  for (int k = 0; k < BK / 16; ++k)
+                    umma_bf16_ss(d_tmem, a_t + 2 * k, b_d + 2 * k, idesc, (((started >> cls) & 1u) | k) != 0 ? 1u : 0u);
+                }
+                umma_commit(&empty_b[sb]);
               }
+              __syncwarp();
               started = 0xFu;
-              umma_commit(&empty_b[sb]);
               if (++sb == p.b_slots) { sb = 0; pb ^= 1u; }
             }
           } else {
@@ -506,19 +519,24 @@ conv_halo_quad_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
                 tc_fence_after();
                 const uint64_t b_d = b_hi + (smem_u32(smem_b + sb * B_BYTES) >> 4);
                 const uint64_t a_t = a_d + ((static_cast<uint32_t>(pd.off[j]) * ROW_BYTES) >> 4);
+                if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < BK / 16; ++k)
-                  umma_bf16_ss(d_tmem, a_t + 2 * k, b_d + 2 * k, idesc, (((started >> cls) & 1u) | k) != 0 ? 1u : 0u);
+                  for (int k = 0; k < BK / 16; ++k)
+                    umma_bf16_ss(d_tmem, a_t + 2 * k, b_d + 2 * k, idesc, (((started >> cls) & 1u) | k) != 0 ? 1u : 0u);
+                  umma_commit(&empty_b[sb]);
+                }
+                __syncwarp();
                 started |= 1u << cls;
-                umma_commit(&empty_b[sb]);
                 if (++sb == p.b_slots) { sb = 0; pb ^= 1u; }
               }
             }
           }
-          umma_commit(&empty_a[sa]);
+          if (elect_one()) umma_commit(&empty_a[sa]);
+          __syncwarp();
           if (++sa == A_SLOTS) { sa = 0; pa ^= 1u; }
         }
-        umma_commit(&tmem_full[acc]);
+        if (elect_one()) umma_commit(&tmem_full[acc]);
+        __syncwarp();
         if (NBUF == 2) { if ((acc ^= 1) == 0) pacc ^= 1u; } else { pacc ^= 1u; }
       }
     }

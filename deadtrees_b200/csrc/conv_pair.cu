@@ -141,7 +141,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   __syncthreads();
   cluster_sync_all();            // both CTAs' barriers are initialised before any remote arrive / TMA signal
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // warp-uniform for the compiler (uniform registers)
 
   if (warp == 0) {
     if (lane == 0) {
@@ -175,7 +175,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && leader) {
+    if (leader) {   // whole warp of the leader CTA: uniform bookkeeping; an elected lane issues (see conv_halo.cu)
       const uint64_t a_hi = umma_desc(0u, PITCH * BK * 2, 2u);
       const uint64_t b_hi = umma_desc(0u, 1024u, 2u);
       int sa = 0, sb = 0, acc = 0;
@@ -194,18 +194,21 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             tc_fence_after();
             const uint64_t b_d = b_hi + (smem_u32(smem_b + sb * B_HALF) >> 4);
             const uint64_t a_t = a_d + ((static_cast<uint32_t>((tap / 3) * PITCH + tap % 3) * (BK * 2)) >> 4);
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k) {
-              umma_bf16_ss_2sm(d_tmem, a_t + 2 * k, b_d + 2 * k, idesc, accum);
-              accum = 1;
+              for (int k = 0; k < BK / 16; ++k) umma_bf16_ss_2sm(d_tmem, a_t + 2 * k, b_d + 2 * k, idesc, (accum | k) ? 1u : 0u);
+              umma_commit_pair(&empty_b[sb]);
+              if (tap == 8) {
+                umma_commit_pair(&empty_a[sa]);
+                if (slab + 1 == p.n_slabs) umma_commit_pair(&tmem_full[acc]);
+              }
             }
-            umma_commit_pair(&empty_b[sb]);
+            __syncwarp();
+            accum = 1;
             if (++sb == p.b_slots) { sb = 0; pb ^= 1u; }
           }
-          umma_commit_pair(&empty_a[sa]);
           if (++sa == A_SLOTS) { sa = 0; pa ^= 1u; }
         }
-        umma_commit_pair(&tmem_full[acc]);
         if ((acc ^= 1) == 0) pacc ^= 1u;
       }
     }

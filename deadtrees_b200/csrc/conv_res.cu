@@ -113,7 +113,7 @@ conv_res_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // warp-uniform for the compiler (uniform registers)
 
   if (warp == 0) {
     if (lane == 0) {
@@ -130,7 +130,7 @@ conv_res_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {   // whole warp: warp-uniform bookkeeping in uniform registers; an elected lane issues (see conv_halo.cu)
       const uint64_t a_hi = umma_desc(0u, PITCH * ROW_BYTES, CW == 64 ? 2u : (CW == 32 ? 4u : 6u));
       const uint64_t b_d0 = umma_desc(smem_u32(smem_w), 1024u, 2u);
       mbar_wait(w_full, 0);
@@ -143,6 +143,7 @@ conv_res_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         const uint64_t a_d = a_hi + (smem_u32(smem_a + sa * p.a_slot_bytes) >> 4);
         // k-step outer, M tile inner: consecutive MMAs go to DIFFERENT accumulators, so the tensor pipe never
         // waits on the read-modify-write latency of one accumulator (matters for the N = 16 / 32 layers)
+        if (elect_one()) {
         if (FOLD) {
           // effective tap outer, class inner: consecutive MMAs go to different accumulators
 #pragma unroll
@@ -177,6 +178,8 @@ conv_res_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         }
         umma_commit(&empty_a[sa]);
         umma_commit(&tmem_full[buf]);
+        }
+        __syncwarp();
         if (++sa == p.a_slots) { sa = 0; pa ^= 1u; }
         if ((buf ^= 1) == 0) pbuf ^= 1u;
       }

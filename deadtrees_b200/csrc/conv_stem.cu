@@ -75,7 +75,7 @@ conv_stem_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // warp-uniform for the compiler (uniform registers)
 
   if (warp == 0) {
     if (lane == 0) {
@@ -94,7 +94,7 @@ conv_stem_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {   // whole warp: uniform bookkeeping; an elected lane issues (see conv_halo.cu)
       const uint64_t a_hi = umma_desc(0u, 512u, 4u);   // 64 B rows, SWIZZLE_64B
       const uint64_t b_d0 = umma_desc(smem_u32(smem_w), 512u, 4u);
       mbar_wait(w_full, 0);
@@ -106,15 +106,18 @@ conv_stem_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         tc_fence_after();
         const uint64_t a_d = a_hi + (smem_u32(smem_a + st * A_STAGE) >> 4);
         const uint32_t d_tmem = tmem_base + buf * BN;
+        if (elect_one()) {
 #pragma unroll
-        for (int r = 0; r < ROWS; ++r) {
+          for (int r = 0; r < ROWS; ++r) {
 #pragma unroll
-          for (int k = 0; k < 2; ++k)
-            umma_bf16_ss(d_tmem, a_d + ((r * A_SUB + k * 32) >> 4), b_d0 + ((r * W_SUB + k * 32) >> 4), idesc,
-                         (r | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < 2; ++k)
+              umma_bf16_ss(d_tmem, a_d + ((r * A_SUB + k * 32) >> 4), b_d0 + ((r * W_SUB + k * 32) >> 4), idesc,
+                           (r | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty[st]);
+          umma_commit(&tmem_full[buf]);
         }
-        umma_commit(&empty[st]);
-        umma_commit(&tmem_full[buf]);
+        __syncwarp();
         if (++st == STAGES) { st = 0; ph ^= 1u; }
         if ((buf ^= 1) == 0) pbuf ^= 1u;
       }
@@ -243,7 +246,7 @@ conv_stem_rows_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_con
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // warp-uniform for the compiler (uniform registers)
 
   if (warp == 0) {
     if (lane == 0) {
@@ -262,7 +265,7 @@ conv_stem_rows_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_con
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {   // whole warp: uniform bookkeeping; an elected lane issues (see conv_halo.cu)
       const uint64_t a_hi = umma_desc(0u, 128u, 0u);   // no swizzle: rows 16 B apart, 8-row groups 128 B, K chunks 16 B
       const uint64_t b_d0 = umma_desc(smem_u32(smem_w), 512u, 4u);
       mbar_wait(w_full, 0);
@@ -277,17 +280,20 @@ conv_stem_rows_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_con
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + buf * BN;
           const uint32_t a_tile = a_stage + t * (BM * 16);
+          if (elect_one()) {
 #pragma unroll
-          for (int r = 0; r < ROWS; ++r) {
+            for (int r = 0; r < ROWS; ++r) {
 #pragma unroll
-            for (int k = 0; k < 2; ++k)
-              umma_bf16_ss(d_tmem, a_hi + (((a_tile + r * p.row_bytes + k * 32) & 0x3FFFFu) >> 4),
-                           b_d0 + ((r * W_SUB + k * 32) >> 4), idesc, (r | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < 2; ++k)
+                umma_bf16_ss(d_tmem, a_hi + (((a_tile + r * p.row_bytes + k * 32) & 0x3FFFFu) >> 4),
+                             b_d0 + ((r * W_SUB + k * 32) >> 4), idesc, (r | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(&tmem_full[buf]);
+            if (t + 1 == p.tiles_per_row) umma_commit(&empty[st]);
           }
-          umma_commit(&tmem_full[buf]);
+          __syncwarp();
           if ((buf ^= 1) == 0) pbuf ^= 1u;
         }
-        umma_commit(&empty[st]);
         if (++st == p.stages) { st = 0; ph ^= 1u; }
       }
     }
@@ -529,7 +535,7 @@ conv_stem_wgrad_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_co
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // warp-uniform for the compiler (uniform registers)
 
   if (warp == 0) {
     if (lane == 0) {

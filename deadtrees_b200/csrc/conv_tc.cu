@@ -139,7 +139,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // warp-uniform for the compiler (uniform registers)
 
   if (warp == 0) {
     // ===================== TMA producer (one lane) =====================
@@ -199,8 +199,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one lane) =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (whole warp keeps the uniform state, an elected lane issues) =====================
+    {
       constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
       // A operand layout: 128 B rows (swizzle 128), or 64 B / 32 B rows with one sub-tile per tap.
       // This thread's instruction stream paces the tensor core, so everything that does not change per
@@ -230,14 +230,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           const uint64_t b_d = b_hi + (smem_u32(smem_b + stage * Cfg::B_STAGE_BYTES) >> 4);
           // gather mode zero-fills the padded tail of K; TMA mode simply skips it
           const int ksteps = kc + 1 < p.num_k_chunks ? BK / 16 : tail_steps;
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            if (k < ksteps) umma_bf16_ss(d_tmem, a_d + a_off[k], b_d + 2 * k, idesc, (kc | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) {
+              if (k < ksteps) umma_bf16_ss(d_tmem, a_d + a_off[k], b_d + 2 * k, idesc, (kc | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs above have read it
+            if (kc + 1 == p.num_k_chunks) umma_commit(&tmem_full_bar[acc]);  // accumulator complete
           }
-          umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs above have read it
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(&tmem_full_bar[acc]);  // accumulator complete
         if ((acc ^= 1) == 0) acc_phase ^= 1u;
       }
     }
@@ -489,6 +492,8 @@ int dt_conv_res(const dt_conv_desc* d, const void* x, const void* w, int Kpad, c
                 const void* residual, void* y, cudaStream_t s);
 int dt_conv_pair(const dt_conv_desc* d, const void* x, const void* w, int Kpad, const float* scale, const float* shift,
                  const void* residual, void* y, cudaStream_t s);
+int dt_conv_row(const dt_conv_desc* d, const void* x, const void* w, int Kpad, const float* scale, const float* shift,
+                const void* residual, void* y, cudaStream_t s);
 
 extern "C" int dt_conv2d_fwd(const dt_conv_desc* d, const void* x, const void* skip, const void* w,
                              const float* scale, const float* shift, const void* residual, void* y,
@@ -558,6 +563,10 @@ extern "C" int dt_conv2d_fwd(const dt_conv_desc* d, const void* x, const void* s
     return rcf;
   }
   if (!(d->flags & (DT_CONV_NO_HALO | DT_CONV_FORCE_GATHER)) && !stem && !transposed) {
+    if (!(d->flags & DT_CONV_NO_ROW) && dt_row_kernels_enabled()) {   // narrow layers: row streaming, vertical taps in N
+      const int rcr = dt_conv_row(d, x, w, Kpad, scale, shift, residual, y, s);
+      if (rcr != DT_ERR_UNSUPPORTED) return rcr;
+    }
     const int rc0 = dt_conv_res(d, x, w, Kpad, scale, shift, residual, y, s);   // weights resident in smem
     if (rc0 != DT_ERR_UNSUPPORTED) return rc0;
     if (d->flags & DT_CONV_PAIR) {      // wide layers on CTA pairs (tcgen05.mma.cta_group::2)

@@ -137,6 +137,9 @@ enum {
   DT_CONV_PAIR = 128,       /* 3x3/s1 layers with C_in % 64 == 0, C_out % 128 == 0, H % 16 == 0, W % 16 == 0: CTA pairs
                                (tcgen05.mma.cta_group::2, M = 256; conv_pair.cu) instead of the single-CTA halo kernel;
                                same results */
+  DT_CONV_NO_ROW = 256,     /* 3x3/s1 layers with C_in, C_out <= 64: the 8 x 16 tile kernels (conv_res.cu) instead of the
+                               row-streaming kernel whose vertical taps ride in the MMA's N dimension (conv_row.cu, the
+                               default where the width is 64 or a multiple of 128); same results */
   DT_CONV_TRANSPOSED = 16   /* data gradient of a stride-2 conv: desc.H, W = size of the OUTPUT (the conv's input), x = gy
                                (N, Ho, Wo, C_in) at the conv's output size, out[h][w] = sum over taps with (h + pad - r)
                                even of gy[(h + pad - r) / 2][..] * w; weights in the dt_conv2d_fwd packing with

@@ -37,7 +37,7 @@ _TRAINED = {}
 
 
 def trained_model(cin=3, k=3, seed=0):
-    """the oracle network after 200 steps of the reference's training recipe on the CPU (a well-conditioned function,
+    """the oracle network after 100 steps of the reference's training recipe on the CPU (a well-conditioned function,
     like a checkpoint of the reference; ``ref_unet.build_trained_unet``) - one per session, cached on disk."""
     key = (cin, k, seed)
     if key not in _TRAINED:

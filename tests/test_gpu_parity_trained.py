@@ -1,7 +1,7 @@
 """GPU parity at the north star's tolerance: the bf16 tensor-core path against the **fp32** oracle.
 
 BASELINE.json: "logits must match within 2e-2 abs in bf16 (1e-4 in an fp32 check mode), and argmax masks must agree on
-at least 99.9% of pixels".  The weights are the oracle network after 200 steps of the reference's own training recipe
+at least 99.9% of pixels".  The weights are the oracle network after 100 steps of the reference's own training recipe
 (``oracle/ref_unet.build_trained_unet``): a freshly initialised BatchNorm network amplifies ANY rounding by 1.2x per
 layer (DESIGN.md "bf16 parity"; those weights stay in ``test_gpu_unet.py`` as stress tests), a trained one does not.
 
@@ -9,7 +9,7 @@ What is asserted, always against the fp32 CPU oracle (``deployment/inference.py:
   * argmax masks agree on >= 99.9 % of the pixels (literal);
   * the rms logit error is below 2e-2 (absolute, literal);
   * every logit is within 2e-2 in units of the logit scale, ``2e-2 * max(1, max|ref|)`` - the same form as the fp32
-    check mode's ``1e-4 * max(1, max|ref|)`` (trained logits reach +-25, where ONE bf16 rounding is already 6e-2);
+    check mode's ``1e-4 * max(1, max|ref|)`` (trained logits reach +-8, where ONE bf16 rounding is already 1.6e-2);
   * >= 99.9 % of the logits are within ``2e-2 * max(1, |ref|)`` of their own reference value.
 Configurations: BASELINE cfg1 (16 x 256 x 256 RGB), RGB+NIR, a cfg2 crop (T = 256, overlap 32, several batches, banded
 and whole-shard stitch, host pipeline), cfg5 (1024 x 1024 tiles), and the drop-in ``PyTorchInference`` in its default
