@@ -554,7 +554,7 @@ conv_stem_wgrad_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_co
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {   // whole warp: warp-uniform bookkeeping (uniform registers); an elected lane issues (see conv_halo.cu)
       // bf16, A and B MN-major, M = 128 (rows 64..127 read whatever follows the gy tile and are discarded), N = 32
       constexpr uint32_t idesc_w = umma_idesc_bf16(128, 32) | (1u << 15) | (1u << 16);
       const uint64_t a_hi = umma_desc_mn_sw(WG_A, 1024u, 2u);      // 128 B rows, 8-row K groups 1024 B apart
@@ -566,18 +566,22 @@ conv_stem_wgrad_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_co
         tc_fence_after();
         const uint32_t a_addr = smem_u32(smem + st * WG_STAGE);
         const uint32_t b_addr = a_addr + WG_A;
+        if (elect_one()) {
 #pragma unroll 1
-        for (int r = 0; r < ROWS; ++r) {
+          for (int r = 0; r < ROWS; ++r) {
 #pragma unroll
-          for (int k8 = 0; k8 < 8; ++k8)
-            umma_bf16_ss(tmem_base + r * 32, a_hi + ((a_addr + k8 * 2048) >> 4),
-                         b_hi + ((b_addr + r * WG_BSUB + k8 * 1024) >> 4), idesc_w, (accum | k8) != 0 ? 1u : 0u);
+            for (int k8 = 0; k8 < 8; ++k8)
+              umma_bf16_ss(tmem_base + r * 32, a_hi + ((a_addr + k8 * 2048) >> 4),
+                           b_hi + ((b_addr + r * WG_BSUB + k8 * 1024) >> 4), idesc_w, (accum | k8) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty[st]);
+          if (tile + 1 == tile_end) umma_commit(done);
         }
+        __syncwarp();
         accum = 1;
-        umma_commit(&empty[st]);
         if (++st == WG_STAGES) { st = 0; ph ^= 1u; }
       }
-      umma_commit(done);
+      if (tile_begin >= tile_end && elect_one()) umma_commit(done);
     }
   } else {
     const int quarter = warp & 3;

@@ -110,7 +110,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constan
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // warp-uniform for the compiler (uniform registers)
 
   if (warp == 0) {
     if (lane == 0) {
@@ -132,7 +132,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {   // whole warp: warp-uniform bookkeeping (uniform registers); an elected lane issues (see conv_halo.cu)
       // bf16 x bf16 -> fp32, A and B MN-major (bits 15 / 16), M = 128, N = 64
       constexpr uint32_t idesc = umma_idesc_bf16(128, NCOL) | (1u << 15) | (1u << 16);
       const uint64_t a_hi = umma_desc_mn(0u, A_SLAB, 1024u);
@@ -151,21 +151,25 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constan
         tc_fence_after();
         const uint64_t a_d = a_hi + (smem_u32(smem_a + st * A_STAGE) >> 4);
         const uint32_t b_addr = smem_u32(smem_b + st * B_STAGE);
+        if (elect_one()) {
 #pragma unroll 1
-        for (int t = 0; t < ntaps; ++t) {
-          const uint32_t toff = static_cast<uint32_t>(grp.off[t]);
-          const uint32_t d_tmem = tmem_base + t * NCOL;
+          for (int t = 0; t < ntaps; ++t) {
+            const uint32_t toff = static_cast<uint32_t>(grp.off[t]);
+            const uint32_t d_tmem = tmem_base + t * NCOL;
 #pragma unroll
-          for (int k8 = 0; k8 < 8; ++k8) {
-            const uint64_t b_d = b_hi + ((b_addr + (krow[k8] + toff) * 128u) >> 4);
-            umma_bf16_ss(d_tmem, a_d + ((k8 * 2048) >> 4), b_d, idesc, (accum | k8) != 0 ? 1u : 0u);
+            for (int k8 = 0; k8 < 8; ++k8) {
+              const uint64_t b_d = b_hi + ((b_addr + (krow[k8] + toff) * 128u) >> 4);
+              umma_bf16_ss(d_tmem, a_d + ((k8 * 2048) >> 4), b_d, idesc, (accum | k8) != 0 ? 1u : 0u);
+            }
           }
+          umma_commit(&empty[st]);
+          if (tile + 1 == tile_end) umma_commit(done);
         }
+        __syncwarp();
         accum = 1;
-        umma_commit(&empty[st]);
         if (++st == STAGES) { st = 0; ph ^= 1u; }
       }
-      umma_commit(done);
+      if (tile_begin >= tile_end && elect_one()) umma_commit(done);
     }
   } else {
     const int quarter = warp & 3;
@@ -425,7 +429,7 @@ conv_wgrad_narrow_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // warp-uniform for the compiler (uniform registers)
 
   if (warp == 0) {
     if (lane == 0) {
@@ -445,7 +449,7 @@ conv_wgrad_narrow_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {   // whole warp: warp-uniform bookkeeping (uniform registers); an elected lane issues (see conv_halo.cu)
       constexpr uint32_t idesc = umma_idesc_bf16(128, Cfg::NCOLS) | (1u << 15) | (1u << 16);
       // A: MN blocks one image row (8 px) apart = the K groups' own stride; B: MN blocks one pixel apart
       const uint64_t a_hi = umma_desc_mn_any(TW * Cfg::RA, TW * Cfg::RA, Cfg::LAYOUT_A);
@@ -457,20 +461,24 @@ conv_wgrad_narrow_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_
         tc_fence_after();
         const uint32_t a_addr = smem_u32(smem + st * Cfg::STAGE);
         const uint32_t b_addr = a_addr + Cfg::A_REGION;
+        if (elect_one()) {
 #pragma unroll
-        for (int k8 = 0; k8 < 8; ++k8) {      // 16 pixels = tile rows 2*k8, 2*k8 + 1
-          const uint64_t a_d = a_hi + (((a_addr + 2 * k8 * TW * Cfg::RA) & 0x3FFFFu) >> 4);
-          const uint64_t b_d = b_hi + (((b_addr + (2 * k8 + 1) * PITCH * Cfg::RB) & 0x3FFFFu) >> 4);
+          for (int k8 = 0; k8 < 8; ++k8) {      // 16 pixels = tile rows 2*k8, 2*k8 + 1
+            const uint64_t a_d = a_hi + (((a_addr + 2 * k8 * TW * Cfg::RA) & 0x3FFFFu) >> 4);
+            const uint64_t b_d = b_hi + (((b_addr + (2 * k8 + 1) * PITCH * Cfg::RB) & 0x3FFFFu) >> 4);
 #pragma unroll
-          for (int a = 0; a < Cfg::NM; ++a)   // second MMA: blocks BLK.. (image rows BLK further)
-            umma_bf16_ss(tmem_base + a * Cfg::NCOLS, a_d + ((a * Cfg::BLK * TW * Cfg::RA) >> 4), b_d, idesc,
-                         (accum | k8) != 0 ? 1u : 0u);
+            for (int a = 0; a < Cfg::NM; ++a)   // second MMA: blocks BLK.. (image rows BLK further)
+              umma_bf16_ss(tmem_base + a * Cfg::NCOLS, a_d + ((a * Cfg::BLK * TW * Cfg::RA) >> 4), b_d, idesc,
+                           (accum | k8) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty[st]);
+          if (tile + 1 == tile_end) umma_commit(done);
         }
+        __syncwarp();
         accum = 1;
-        umma_commit(&empty[st]);
         if (++st == NW_STAGES) { st = 0; ph ^= 1u; }
       }
-      umma_commit(done);
+      if (tile_begin >= tile_end && elect_one()) umma_commit(done);
     }
   } else {
     const int quarter = warp & 3;
