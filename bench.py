@@ -68,7 +68,7 @@ def workload_config(a, n_tiles):
             "mosaic": [a.size, a.size, 3], "tile": a.tile, "overlap": a.overlap, "tiles": n_tiles,
             "batch_tiles": a.batch_tiles, "classes": 3, "in_channels": 3,
             "l2_policy": "inputs larger than L2 (300 MB mosaic, >1 GB of activations per step); no explicit flush",
-            "parallelism": f"tile-range shards x{a.gpus}"}
+            "parallelism": f"tile-range shards x{a.gpus} (row-aligned stitch, neighbour exchange, mask rows on rank 0)"}
 
 
 def synthetic_mosaic(size: int, device, seed: int = 1234) -> torch.Tensor:
@@ -232,7 +232,7 @@ def main_b200(a):
     from deadtrees_b200 import ops
     from deadtrees_b200.deployment.inference import MosaicInference, overlap_grid
     from deadtrees_b200.engine import UnetEngine, conv_flops_per_tile
-    from deadtrees_b200.sharding import make_halo_hook, split_tile_rows
+    from deadtrees_b200.sharding import ShardPlan, exchange_logits, gather_mask_rows
 
     ctx = dist_context()
     rank, world, local, dev = ctx
@@ -257,42 +257,39 @@ def main_b200(a):
     T, ov = a.tile, a.overlap
     gy, gx = overlap_grid(H, W, T, ov)
     n_tiles = gy * gx
-    parts = split_tile_rows(gy, world)
-    r0, r1 = parts[rank]
+    # N > 1: contiguous tile-index ranges (253 / 254 tiles per rank at N = 8), row-aligned stitching, one grouped
+    # neighbour exchange of head tiles / boundary strips, mask rows gathered on rank 0 (deadtrees_b200/sharding.py)
+    plans = [ShardPlan(gy, gx, world, r, ov) for r in range(world)]
+    plan = plans[rank]
+    r0, r1 = plan.R0, plan.R1
+    my_tiles = plan.t1 - plan.t0
     mi = MosaicInference(engine, tile=T, overlap=ov, batch_tiles=a.batch_tiles)
-    hook = make_halo_hook(T, ov, rank, world, has_rows=[b > c for c, b in parts]) if world > 1 else None
+    # end to end the mosaic rows of a batch are uploaded behind the previous batch: keep at least three batches per shard
+    bt_e2e = min(a.batch_tiles, max(gx, -(-my_tiles // 3)))
     mosaic = synthetic_mosaic(a.size, dev)
     host_mosaic = torch.empty(mosaic.shape, dtype=torch.uint8, pin_memory=True)
     host_mosaic.copy_(mosaic)
     host_mask = torch.empty((H, W), dtype=torch.uint8, pin_memory=True)
     mask = torch.zeros((H, W), dtype=torch.uint8, device=dev)
-    y0, y1 = mi.owned_rows(H, T, ov, gy, r0, r1)
-    rows = [mi.owned_rows(H, T, ov, gy, c, b) for c, b in parts]
-
-    def gather_masks():
-        if world == 1:
-            return
-        if rank == 0:
-            reqs = [dist.irecv(mask[rows[k][0]: rows[k][1]], src=k) for k in range(1, world) if rows[k][1] > rows[k][0]]
-            for r in reqs:
-                r.wait()
-        elif y1 > y0:
-            dist.isend(mask[y0:y1], dst=0).wait()
+    y0, y1 = plan.mask_rows(H, T)
+    exchange = (lambda lg: exchange_logits(plan, lg, T)) if world > 1 else None
 
     def step_device():
-        if r1 > r0:
-            mi.run(mosaic, "hwc", tile_rows=(r0, r1) if world > 1 else None, out=mask, halo_hook=hook)
-        gather_masks()
+        if world == 1:
+            mi.run(mosaic, "hwc", out=mask)
+        else:
+            mi.run_shard(mosaic, plan, mask, exchange=exchange)
+            gather_mask_rows(plans, rank, mask, H, T)
 
     def step_e2e():
-        # host buffers in and out: H2D of the uint8 mosaic rows this shard needs, D2H of its mask rows
-        s = T - ov
-        ya, yb = (0, H) if world == 1 else (min(H, r0 * s), min(H, (r1 - 1) * s + T))
-        if r1 > r0:
+        # host buffers in and out: H2D of the uint8 mosaic rows this shard's tiles read, D2H of its mask rows
+        if world == 1:
             # MosaicInference's host pipeline: row bands go up on a copy stream while earlier batches compute, finished
-            # mask bands come back behind the compute (single GPU; with shards the mask rows follow the halo exchange)
-            mi.run(mosaic, "hwc", tile_rows=(r0, r1) if world > 1 else None, out=mask, halo_hook=hook,
-                   host_src=host_mosaic, host_out=host_mask)
+            # mask bands come back behind the compute
+            mi.run(mosaic, "hwc", out=mask, host_src=host_mosaic, host_out=host_mask)
+            return H * W * 3, H * W
+        mi.run_shard(mosaic, plan, mask, exchange=exchange, host_src=host_mosaic, host_out=host_mask, batch_tiles=bt_e2e)
+        ya, yb = plan.input_rows(H, T)
         return (yb - ya) * W * 3, (y1 - y0) * W
 
     def timed(fn, steps, profile=False):
@@ -369,7 +366,7 @@ def main_b200(a):
                                "flops_per_tile": conv_flops_per_tile(T, 3, 3), "peak_source": pk["source"]}
             tr = ncu_conv_traffic()
             if tr is not None and T == 256:
-                bt = min(a.batch_tiles, max((r1 - r0) * gx, 1))
+                bt = min(a.batch_tiles, max(my_tiles, 1))
                 out["roofline"]["traffic"] = tr[0] / tr[1] * bt / tr[2]
                 out["roofline"]["traffic_source"] = (
                     f"NOT measured in this run: committed ncu --set full capture of the {tr[2]} conv launches of one "

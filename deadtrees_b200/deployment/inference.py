@@ -246,6 +246,61 @@ class MosaicInference:
             main.wait_stream(cs_out)
         return mask
 
+    def run_shard(self, mosaic: torch.Tensor, plan, out: torch.Tensor, exchange=None, host_src: Optional[torch.Tensor] = None,
+                  host_out: Optional[torch.Tensor] = None, batch_tiles: Optional[int] = None) -> torch.Tensor:
+        """one rank of a multi-GPU run over tile-RANGE shards (``deadtrees_b200.sharding.ShardPlan``): the tiles
+        ``[plan.t0, plan.t1)`` go through the network in batches, ``exchange(logits)`` swaps the few boundary tiles /
+        strips with the two neighbours (``sharding.exchange_logits``), and the mask rows ``plan.mask_rows(H, T)`` are
+        stitched into ``out``.  "hwc" mosaics; ``host_src`` / ``host_out`` as in :meth:`run` (row bands of the mosaic are
+        uploaded behind the batches; the shard's mask rows go back after the stitch)."""
+        H, W = mosaic.shape[0], mosaic.shape[1]
+        T, ov, eng = self.tile, self.overlap, self.engine
+        gy, gx = overlap_grid(H, W, T, ov)
+        if (gy, gx, ov) != (plan.gy, plan.gx, plan.overlap):
+            raise ValueError("shard plan does not belong to this mosaic / tiling")
+        step = T - ov
+        bt = min(batch_tiles or self.batch_tiles, max(plan.t1 - plan.t0, 1))
+        pad = 3 if eng.stem_padded(T) else 0
+        x = self._bufs.get(("x", bt, T))
+        if x is None:
+            x = self._bufs[("x", bt, T)] = eng.alloc_input(bt, T)
+        y0, y1 = plan.mask_rows(H, T)
+        main = torch.cuda.current_stream()
+        if host_src is not None:
+            if getattr(self, "_copy_streams", None) is None:
+                self._copy_streams = (torch.cuda.Stream(device=eng.device), torch.cuda.Stream(device=eng.device))
+            cs_in = self._copy_streams[0]
+            cs_in.wait_stream(main)
+        if ov == 0:
+            tmask = self._buf("tmask", (bt, T, T), torch.uint8)
+        else:
+            logits = self._buf("logits", (plan.B1 - plan.B0, T, T, eng.classes), eng.act_dtype)
+        copied = plan.input_rows(H, T)[0]
+        for t0 in range(plan.t0, plan.t1, bt):
+            n = min(bt, plan.t1 - t0)
+            if host_src is not None:
+                need = min(H, ((t0 + n - 1) // gx) * step + T)
+                if need > copied:
+                    with torch.cuda.stream(cs_in):
+                        mosaic[copied:need].copy_(host_src[copied:need], non_blocking=True)
+                    copied = need
+                    main.wait_stream(cs_in)
+            ops.tile_gather_normalize(mosaic, "hwc", eng.in_channels, T, ov, (gy, gx), t0, n, self.offset, self.scale,
+                                      out=x[:n], pad=pad)
+            if ov == 0:
+                eng.forward(x[:n], mask_out=tmask[:n])
+                ops.stitch_mask(tmask[:n], gx, t0, out)       # overlap 0: a tile's pixels belong to whoever computed it
+            else:
+                eng.forward(x[:n], logits_nhwc_out=logits[t0 - plan.B0: t0 - plan.B0 + n])
+        if ov > 0:
+            if exchange is not None:
+                exchange(logits)
+            if y1 > y0:
+                ops.stitch_blend_argmax(logits, ov, (gy, gx), self.win, out, row0=y0, nrows=y1 - y0, ty_base=plan.ty_base)
+        if host_out is not None and y1 > y0:
+            host_out[y0:y1].copy_(out[y0:y1], non_blocking=True)
+        return out
+
     @staticmethod
     def owned_rows(H: int, T: int, overlap: int, gy: int, r0: int, r1: int) -> Tuple[int, int]:
         """mosaic rows whose output a shard with tile rows [r0, r1) writes."""

@@ -138,3 +138,52 @@ def test_pytorch_inference_api_bf16(tmp_path):
     assert agree >= 0.999
     one = inf.run(x[0].clone(), device="cuda")
     assert one.shape == (256, 256) and torch.equal(one, out[0])
+
+
+@pytest.mark.parametrize("world,ov", [(2, 32), (3, 32), (2, 0)])
+def test_tile_range_shards_equal_the_unsharded_mask(world, ov):
+    """BASELINE cfg3 logic on one GPU: the ranks of a tile-RANGE sharded run (``ShardPlan``: balanced tile ranges, row-aligned
+    stitching, head tiles / boundary strips exchanged between neighbours) executed one after the other with the exchange
+    done by hand give, bit for bit, the mask of the unsharded run."""
+    from deadtrees_b200.sharding import ShardPlan
+    H, W, T = 1100, 700, 256
+    model = trained_model(3, 3)
+    mosaic = torch.from_numpy(pattern_mosaic(H, W, 3, seed=7)).cuda()
+    eng = UnetEngine(model.state_dict(), 3, 3, precision="bf16")
+    mi = MosaicInference(eng, tile=T, overlap=ov, batch_tiles=5)
+    full = mi.run(mosaic, "hwc").clone()
+    gy, gx = overlap_grid(H, W, T, ov)
+    plans = [ShardPlan(gy, gx, world, r, ov) for r in range(world)]
+    assert any(p.send_head for p in plans) or ov == 0              # the split really cuts through a tile row
+    out = torch.zeros((H, W), dtype=torch.uint8, device="cuda")
+    # pass 1: every rank computes its tiles (no exchange yet); keep the buffers
+    bufs = []
+    for p in plans:
+        shard = MosaicInference(eng, tile=T, overlap=ov, batch_tiles=5)
+        part = torch.zeros((H, W), dtype=torch.uint8, device="cuda")
+        grabbed = {}
+        shard.run_shard(mosaic, p, part, exchange=(lambda lg, g=grabbed: g.setdefault("lg", lg.clone())) if ov else None)
+        bufs.append((shard, part, grabbed.get("lg")))
+    if ov == 0:
+        for p, (_, part, _) in zip(plans, bufs):
+            y0, y1 = p.mask_rows(H, T)
+            out[y0:y1] = part[y0:y1]
+        assert torch.equal(out, full)
+        return
+    # pass 2: the exchange by hand, then each rank's stitch
+    for k, p in enumerate(plans):
+        lg = bufs[k][2]
+        if p.recv_tail:
+            a, b = p.recv_tail
+            q = plans[k + 1]
+            lg[a - p.B0: b - p.B0] = bufs[k + 1][2][a - q.B0: b - q.B0]
+        if p.recv_halo:
+            a, b = p.recv_halo
+            q = plans[k - 1]
+            lg[a - p.B0: b - p.B0, T - ov:] = bufs[k - 1][2][a - q.B0: b - q.B0, T - ov:]
+    from deadtrees_b200 import ops
+    for k, p in enumerate(plans):
+        y0, y1 = p.mask_rows(H, T)
+        ops.stitch_blend_argmax(bufs[k][2], ov, (gy, gx), mi.win, out, row0=y0, nrows=y1 - y0, ty_base=p.ty_base)
+    torch.cuda.synchronize()
+    assert torch.equal(out, full)

@@ -324,3 +324,68 @@ def test_state_generation_counter():
     g = ops.STATE_GENERATION
     ops.bump_state_generation()
     assert ops.STATE_GENERATION == g + 1
+
+
+# ---- tile-range shards (deadtrees_b200/sharding.py::ShardPlan) ------------------------------------------------------------
+@pytest.mark.parametrize("gy,gx,world,ov", [(45, 45, 8, 32), (45, 45, 4, 32), (45, 45, 2, 32), (7, 5, 3, 8), (9, 4, 2, 16), (40, 40, 8, 0)])
+def test_shard_plan_partition(gy, gx, world, ov):
+    from deadtrees_b200.sharding import ShardPlan
+    ps = [ShardPlan(gy, gx, world, r, ov) for r in range(world)]
+    assert ps[0].t0 == 0 and ps[-1].t1 == gy * gx and ps[0].R0 == 0 and ps[-1].R1 == gy
+    sizes = [p.t1 - p.t0 for p in ps]
+    if ov > 0:
+        assert max(sizes) - min(sizes) <= 1                       # balanced to one tile (8 GPUs, cfg2: 253 / 254 tiles)
+    for a, b in zip(ps, ps[1:]):
+        assert a.t1 == b.t0 and a.R1 == b.R0
+        assert a.recv_tail == b.send_head and a.send_halo == b.recv_halo
+    rows = [p.mask_rows(10 ** 9, 256) for p in ps]                # mask rows: a partition of the mosaic rows
+    assert rows[0][0] == 0 and all(a[1] == b[0] for a, b in zip(rows, rows[1:]))
+    for p in ps:       # everything the stitch of rows [R0, R1) reads is computed locally or received
+        have = set(range(p.t0, p.t1))
+        if p.recv_tail:
+            have |= set(range(*p.recv_tail))
+        assert set(range(p.R0 * gx, p.R1 * gx)) <= have
+        if p.R0 > 0 and ov > 0:
+            halo = set(range(*p.recv_halo)) if p.recv_halo else set()
+            assert set(range((p.R0 - 1) * gx, p.R0 * gx)) <= (halo | set(range(p.t0, p.t1)))
+        assert p.B0 <= min(p.t0, p.ty_base * gx) and p.B1 >= max(p.t1, p.R1 * gx) and p.B0 % gx == 0
+
+
+def _shard_exchange_worker(rank, world, port):
+    from deadtrees_b200.sharding import ShardPlan, exchange_logits, gather_mask_rows
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    gy, gx, T, ov, K = 7, 5, 16, 4, 3
+    H = (gy - 1) * (T - ov) + T
+    g = torch.Generator().manual_seed(5)
+    full = torch.randn(gy * gx, T, T, K, generator=g)             # what a single GPU would hold
+    plans = [ShardPlan(gy, gx, world, r, ov) for r in range(world)]
+    p = plans[rank]
+    local = torch.full((p.B1 - p.B0, T, T, K), float("nan"))
+    local[p.t0 - p.B0: p.t1 - p.B0] = full[p.t0: p.t1]            # "computed" tiles
+    exchange_logits(p, local, T)
+    # after the exchange: every tile of the stitched rows is complete, the halo row has its bottom strips
+    assert torch.equal(local[p.R0 * gx - p.B0: p.R1 * gx - p.B0], full[p.R0 * gx: p.R1 * gx]), rank
+    if p.R0 > 0:
+        a = (p.R0 - 1) * gx
+        assert torch.equal(local[a - p.B0: a - p.B0 + gx, T - ov:], full[a: a + gx, T - ov:]), rank
+    # mask rows -> rank 0
+    mask = torch.zeros((H, 9), dtype=torch.uint8)
+    y0, y1 = p.mask_rows(H, T)
+    mask[y0:y1] = rank + 1
+    gather_mask_rows(plans, rank, mask, H, T)
+    if rank == 0:
+        for k, q in enumerate(plans):
+            a, b = q.mask_rows(H, T)
+            assert bool((mask[a:b] == k + 1).all()), k
+        assert int((mask == 0).sum()) == 0
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_shard_exchange_gloo(world):
+    """the N > 1 inference path on the CPU: head tiles go to the previous rank, boundary strips to the next one, mask rows
+    to rank 0 (gloo; NCCL over NVLink on the GPUs)."""
+    port = 31500 + (os.getpid() % 2000) + world
+    mp.spawn(_shard_exchange_worker, args=(world, port), nprocs=world, join=True)
