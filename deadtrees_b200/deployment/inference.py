@@ -276,6 +276,19 @@ class MosaicInference:
         else:
             logits = self._buf("logits", (plan.B1 - plan.B0, T, T, eng.classes), eng.act_dtype)
         copied = plan.input_rows(H, T)[0]
+        # with a host mask the interior rows are stitched and sent back as soon as their tile rows are complete; the first
+        # stitched tile row waits for the previous rank's boundary strips, the last one for the next rank's head tiles
+        early = host_out is not None and ov > 0
+        if early:
+            cs_out = self._copy_streams[1] if host_src is not None else None
+            if cs_out is None:
+                if getattr(self, "_copy_streams", None) is None:
+                    self._copy_streams = (torch.cuda.Stream(device=eng.device), torch.cuda.Stream(device=eng.device))
+                cs_out = self._copy_streams[1]
+            cs_out.wait_stream(main)
+        first_end = min(y1, (plan.R0 + 1) * step) if plan.ty_base < plan.R0 else y0       # rows that need the halo strips
+        stitched = first_end
+        last_row = plan.R1 - 1 if plan.recv_tail is not None else plan.R1                 # tile rows complete without the tail
         for t0 in range(plan.t0, plan.t1, bt):
             n = min(bt, plan.t1 - t0)
             if host_src is not None:
@@ -292,12 +305,29 @@ class MosaicInference:
                 ops.stitch_mask(tmask[:n], gx, t0, out)       # overlap 0: a tile's pixels belong to whoever computed it
             else:
                 eng.forward(x[:n], logits_nhwc_out=logits[t0 - plan.B0: t0 - plan.B0 + n])
+            if early:
+                rows_done = min((t0 + n) // gx, last_row)     # mask rows below rows_done * step are final
+                y_end = min(y1, rows_done * step)
+                if y_end > stitched:
+                    ops.stitch_blend_argmax(logits, ov, (gy, gx), self.win, out, row0=stitched, nrows=y_end - stitched,
+                                            ty_base=plan.ty_base)
+                    cs_out.wait_stream(main)
+                    with torch.cuda.stream(cs_out):
+                        host_out[stitched:y_end].copy_(out[stitched:y_end], non_blocking=True)
+                    stitched = y_end
         if ov > 0:
             if exchange is not None:
                 exchange(logits)
-            if y1 > y0:
-                ops.stitch_blend_argmax(logits, ov, (gy, gx), self.win, out, row0=y0, nrows=y1 - y0, ty_base=plan.ty_base)
-        if host_out is not None and y1 > y0:
+            if not early:
+                if y1 > y0:
+                    ops.stitch_blend_argmax(logits, ov, (gy, gx), self.win, out, row0=y0, nrows=y1 - y0, ty_base=plan.ty_base)
+            else:
+                for a, b in ((y0, first_end), (stitched, y1)):
+                    if b > a:
+                        ops.stitch_blend_argmax(logits, ov, (gy, gx), self.win, out, row0=a, nrows=b - a, ty_base=plan.ty_base)
+                        host_out[a:b].copy_(out[a:b], non_blocking=True)
+                main.wait_stream(cs_out)
+        if host_out is not None and y1 > y0 and not early:
             host_out[y0:y1].copy_(out[y0:y1], non_blocking=True)
         return out
 

@@ -187,3 +187,23 @@ def test_tile_range_shards_equal_the_unsharded_mask(world, ov):
         ops.stitch_blend_argmax(bufs[k][2], ov, (gy, gx), mi.win, out, row0=y0, nrows=y1 - y0, ty_base=p.ty_base)
     torch.cuda.synchronize()
     assert torch.equal(out, full)
+    # host pipeline of a shard (row bands up behind the batches, interior mask bands down as soon as they are final): with
+    # the neighbours' data already in place (an exchange that fills it in) the rank's mask rows come back identical
+    host_src = torch.from_numpy(pattern_mosaic(H, W, 3, seed=7)).pin_memory()
+    for k, p in enumerate(plans):
+        done = bufs[k][2]
+        host_mask = torch.zeros((H, W), dtype=torch.uint8).pin_memory()
+        dev_mosaic = torch.zeros_like(mosaic)
+        part = torch.zeros((H, W), dtype=torch.uint8, device="cuda")
+
+        def fill(lg, p=p, done=done):            # "exchange": copy what the neighbours would have sent
+            for rng_ in (p.recv_tail,):
+                if rng_:
+                    lg[rng_[0] - p.B0: rng_[1] - p.B0] = done[rng_[0] - p.B0: rng_[1] - p.B0]
+            if p.recv_halo:
+                a, b = p.recv_halo
+                lg[a - p.B0: b - p.B0, T - ov:] = done[a - p.B0: b - p.B0, T - ov:]
+        bufs[k][0].run_shard(dev_mosaic, p, part, exchange=fill, host_src=host_src, host_out=host_mask, batch_tiles=2)
+        torch.cuda.synchronize()
+        y0, y1 = p.mask_rows(H, T)
+        assert torch.equal(host_mask[y0:y1], full[y0:y1].cpu()), k
