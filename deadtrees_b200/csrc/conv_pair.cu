@@ -26,7 +26,11 @@ constexpr int TW = 8, TH = 16, PITCH = TW + 2, PATCH_PIX = (TH + 2) * PITCH;
 constexpr int kThreads = 192;
 constexpr int A_SLOTS = 3;
 constexpr int PATCH_BYTES = PATCH_PIX * BK * 2;                         // 23040
-constexpr int A_SLOT_BYTES = (PATCH_BYTES + 1023) / 1024 * 1024;        // 23552
+// 8 x 8 images (resnet layer4 at 256 x 256 tiles): an M tile is TWO whole images, stored row-interleaved with zero halos,
+// [10 rows][2 images][10 pixels] - the 16 groups of 8 pixels (row y of image i = group 2y + i) keep the uniform 10-pixel
+// stride the UMMA descriptor needs, a vertical tap moves 2 * PITCH pixels.  One TMA box over the map (C, x, n, y).
+constexpr int PATCH8_BYTES = 10 * 2 * PITCH * BK * 2;                   // 25600
+constexpr int A_SLOT_BYTES = (PATCH8_BYTES + 1023) / 1024 * 1024;       // 25600
 constexpr int MAX_B = 8;
 constexpr uint32_t kPeerMask = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address: the even CTA's copy
 
@@ -34,6 +38,7 @@ struct PairParams {
   int N, H, W, C_in, C_out;
   int relu, has_residual;
   int pairs_w, tiles_h, n_tiles, total_tiles, n_slabs, b_slots;
+  int img8;          // 1: 8 x 8 images, two per CTA tile (four per pair)
   const __nv_bfloat16* residual;
   __nv_bfloat16* y;
   const float* scale;
@@ -95,6 +100,10 @@ __device__ __forceinline__ PGeo pgeo(const PairParams& p, int tile, int rank) {
   PGeo g;
   g.n_tile = tile % p.n_tiles;
   int m = tile / p.n_tiles;
+  if (p.img8) {      // m = group of four images; this CTA takes two of them
+    g.w0 = 0; g.h0 = 0; g.n = m * 4 + rank * 2;
+    return g;
+  }
   g.w0 = (m % p.pairs_w) * (2 * TW) + rank * TW; m /= p.pairs_w;
   g.h0 = (m % p.tiles_h) * TH;
   g.n = m / p.tiles_h;
@@ -150,8 +159,9 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       auto load_patch = [&](int tile, int slab) {
         const PGeo g = pgeo(p, tile, rank);
         mbar_wait(&empty_a[sa], pa ^ 1u);
-        if (leader) mbar_arrive_expect_tx(&full_a[sa], 2 * PATCH_BYTES);
-        tma_load_4d_2sm(smem_a + sa * A_SLOT_BYTES, &tm_a, &full_a[sa], slab * BK, g.w0 - 1, g.h0 - 1, g.n);
+        if (leader) mbar_arrive_expect_tx(&full_a[sa], 2 * (p.img8 ? PATCH8_BYTES : PATCH_BYTES));
+        if (p.img8) tma_load_4d_2sm(smem_a + sa * A_SLOT_BYTES, &tm_a, &full_a[sa], slab * BK, -1, g.n, -1);   // (c, x, n, y)
+        else tma_load_4d_2sm(smem_a + sa * A_SLOT_BYTES, &tm_a, &full_a[sa], slab * BK, g.w0 - 1, g.h0 - 1, g.n);
         if (++sa == A_SLOTS) { sa = 0; pa ^= 1u; }
       };
       bool primed = false;
@@ -180,6 +190,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       const uint64_t b_hi = umma_desc(0u, 1024u, 2u);
       int sa = 0, sb = 0, acc = 0;
       uint32_t pa = 0, pb = 0, pacc = 0;
+      const int rowp = p.img8 ? 2 * PITCH : PITCH;      // pixels between vertically adjacent rows of the patch
       for (int tile = cluster_id; tile < p.total_tiles; tile += n_clusters) {
         mbar_wait(&tmem_empty[acc], pacc ^ 1u);
         tc_fence_after();
@@ -193,7 +204,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             mbar_wait(&full_b[sb], pb);
             tc_fence_after();
             const uint64_t b_d = b_hi + (smem_u32(smem_b + sb * B_HALF) >> 4);
-            const uint64_t a_t = a_d + ((static_cast<uint32_t>((tap / 3) * PITCH + tap % 3) * (BK * 2)) >> 4);
+            const uint64_t a_t = a_d + ((static_cast<uint32_t>((tap / 3) * rowp + tap % 3) * (BK * 2)) >> 4);
             if (elect_one()) {
 #pragma unroll
               for (int k = 0; k < BK / 16; ++k) umma_bf16_ss_2sm(d_tmem, a_t + 2 * k, b_d + 2 * k, idesc, (accum | k) ? 1u : 0u);
@@ -220,8 +231,11 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     uint32_t pacc = 0;
     for (int tile = cluster_id; tile < p.total_tiles; tile += n_clusters) {
       const PGeo g = pgeo(p, tile, rank);
-      const int oy = g.h0 + (row >> 3), ox = g.w0 + (row & 7);
-      const int64_t out_off = ((static_cast<int64_t>(g.n) * p.H + oy) * p.W + ox) * p.C_out + g.n_tile * BN;
+      // 8 x 8 images: group (row >> 3) = 2 * y + image
+      const int n_img = p.img8 ? g.n + ((row >> 3) & 1) : g.n;
+      const bool live = n_img < p.N;                      // a last group of fewer than four images
+      const int oy = p.img8 ? (row >> 4) : g.h0 + (row >> 3), ox = g.w0 + (row & 7);
+      const int64_t out_off = ((static_cast<int64_t>(live ? n_img : 0) * p.H + oy) * p.W + ox) * p.C_out + g.n_tile * BN;
       uint4 res[SC / 8];
       if (p.has_residual) {
 #pragma unroll
@@ -268,7 +282,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 #pragma unroll
             for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
           }
-          store_bf16x16(p.y + out_off + s0 + c0, f);
+          if (live) store_bf16x16(p.y + out_off + s0 + c0, f);
         }
         if (more) {
 #pragma unroll
@@ -322,8 +336,9 @@ int dt_encode_bf16_map(CUtensorMap* tm, const void* base, int rank, const uint64
 // Returns DT_ERR_UNSUPPORTED when the layer does not fit the pair scheme (caller falls back to conv_halo.cu).
 int dt_conv_pair(const dt_conv_desc* d, const void* x, const void* w, int Kpad, const float* scale, const float* shift,
                  const void* residual, void* y, cudaStream_t s) {
+  const bool img8 = d->H == 8 && d->W == 8;
   if (d->R != 3 || d->S != 3 || d->stride != 1 || d->pad != 1 || d->upsample || d->C_x != d->C_in || d->C_in % BK != 0 ||
-      d->C_out % 128 != 0 || d->H % TH != 0 || d->W % (2 * TW) != 0 || Kpad != 9 * d->C_in)
+      d->C_out % 128 != 0 || (!img8 && (d->H % TH != 0 || d->W % (2 * TW) != 0)) || Kpad != 9 * d->C_in)
     return DT_ERR_UNSUPPORTED;
   const int BN = d->C_out % 256 == 0 ? 256 : 128;
   PairParams p;
@@ -332,6 +347,8 @@ int dt_conv_pair(const dt_conv_desc* d, const void* x, const void* w, int Kpad, 
   p.relu = d->relu; p.has_residual = d->has_residual;
   p.pairs_w = d->W / (2 * TW); p.tiles_h = d->H / TH; p.n_tiles = d->C_out / BN;
   p.total_tiles = p.pairs_w * p.tiles_h * d->N * p.n_tiles;
+  p.img8 = img8 ? 1 : 0;
+  if (img8) p.total_tiles = ((d->N + 3) / 4) * p.n_tiles;
   p.n_slabs = d->C_in / BK;
   p.residual = static_cast<const __nv_bfloat16*>(residual);
   p.y = static_cast<__nv_bfloat16*>(y);
@@ -350,7 +367,15 @@ int dt_conv_pair(const dt_conv_desc* d, const void* x, const void* w, int Kpad, 
     const uint64_t strides[3] = {static_cast<uint64_t>(d->C_in) * 2, static_cast<uint64_t>(d->W) * d->C_in * 2,
                                  static_cast<uint64_t>(d->H) * d->W * d->C_in * 2};
     const uint32_t box[4] = {BK, PITCH, TH + 2, 1};
-    int rc = dt_encode_bf16_map(&tm_a, x, 4, dims, strides, box, nullptr);
+    int rc;
+    if (img8) {      // dimension order (c, x, n, y): one box = rows -1..8 of two images, row-interleaved in shared memory
+      const uint64_t dims8[4] = {dims[0], dims[1], dims[3], dims[2]};
+      const uint64_t strides8[3] = {strides[0], strides[2], strides[1]};
+      const uint32_t box8[4] = {BK, PITCH, 2, 10};
+      rc = dt_encode_bf16_map(&tm_a, x, 4, dims8, strides8, box8, nullptr);
+    } else {
+      rc = dt_encode_bf16_map(&tm_a, x, 4, dims, strides, box, nullptr);
+    }
     if (rc != DT_OK) return rc;
   }
   return BN == 256 ? launch_pair<256>(tm_a, tm_b, p, s) : launch_pair<128>(tm_a, tm_b, p, s);

@@ -184,6 +184,11 @@ PAIR_CASES = [
     ("pair 128->256 @32", 3, 32, 128, 0, 256, 3, 1, 1, False, False, False),
     ("pair 256->512 @16 (two channel tiles)", 5, 16, 256, 0, 512, 3, 1, 1, False, True, True),
     ("pair 64->128 @48x48", 2, 48, 64, 0, 128, 3, 1, 1, False, False, True),
+    # 8 x 8 images (resnet layer4 of 256 x 256 tiles): two whole images per CTA tile, row-interleaved patch
+    ("pair 512->512 @8 x8 images +res", 8, 8, 512, 0, 512, 3, 1, 1, False, True, True),
+    ("pair 512->512 @8 x6 images (half-empty last pair)", 6, 8, 512, 0, 512, 3, 1, 1, False, True, True),
+    ("pair 256->128 @8 x5 images", 5, 8, 256, 0, 128, 3, 1, 1, False, False, False),
+    ("pair 64->256 @8 x1 image", 1, 8, 64, 0, 256, 3, 1, 1, False, False, True),
 ]
 
 
@@ -198,7 +203,12 @@ def test_conv_cta_pair(case):
     got_h = run_cuda(case, x, skip, w, scale, shift, residual, dtype=torch.bfloat16)
     err, rel = report(case[0], got_p, ref)
     assert rel < 1e-2
-    assert torch.equal(got_p, got_h)
+    if case[2] == 8:
+        # 8 x 8 images: without the flag the layer runs on the per-tap kernel (conv_tc.cu), which sums K tap-major instead
+        # of slab-major - equal up to the fp32 summation order
+        assert (got_p == got_h).float().mean().item() > 0.995 and (got_p - got_h).abs().max() <= 2.0 ** -7 * ref.abs().max()
+    else:
+        assert torch.equal(got_p, got_h)
 
 
 def test_stem_tcgen05_and_fp32():
