@@ -1,17 +1,22 @@
 #!/bin/bash
-# One gpurun call: bf16 parity re-check, per-layer table, ncu launch list, ncu full capture of conv kernels.
+# ncu evidence of one round (one gpurun call, one GPU): every command runs plainly first and only then under ncu.
+#   launch list of one cfg2 batch (361 tiles = the 4096^2 mosaic), --set full of its conv launches, launch list of one
+#   cfg4 training step.  Summaries: scripts/summarize_ncu.py, scripts/summarize_convs.py, scripts/summarize_train_step.py
 set -u
 mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
-run() { name=$1; shift; echo "=== $name"; timeout "${TMO:-900}" "$@" > gpurun_out/$name.log 2>&1; echo "exit=$? ($name)"; tail -n "${TAIL:-6}" gpurun_out/$name.log; }
-TAIL=30 run unet_bf16 python -m pytest tests/test_gpu_unet.py -q -m gpu --tb=short -p no:cacheprovider -s -k "not fp32"
-TAIL=5 run smoke python -c "import __graft_entry__ as g; g.smoke()"
-TAIL=3 run bench python bench.py --steps 3 --warmup 3 --layer-table gpurun_out/layers.txt
-cat gpurun_out/layers.txt
-SMALL="python bench.py --size 4096 --steps 1 --warmup 3 --no-cpu-baseline --no-profile"
-TAIL=2 run small_plain $SMALL
-if [ "$(tail -n1 gpurun_out/small_plain.log | head -c1)" = "{" ]; then
-  TAIL=3 run ncu_list ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/launches.csv $SMALL
-  TAIL=3 run ncu_full ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -s 230 -c 6 -o gpurun_out/prof_conv -f $SMALL
-fi
-ls -la gpurun_out
+SMALL="python bench.py --size 4096 --steps 1 --warmup 3 --no-cpu-baseline --no-profile --no-extra"
+timeout 300 $SMALL > gpurun_out/prof_small_plain.log 2>&1 && {
+  # launches per step: gather + stem + maxpool + 45 convs + head + 3 stitch passes = 52; skip the 3 warm-up steps
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"conv_|gather_normalize|maxpool|stitch_" -s 156 -c 52 --csv --log-file gpurun_out/prof_launches.csv $SMALL > gpurun_out/prof_ncu_list.log 2>&1
+  echo "launch list exit=$?"
+  timeout 900 ncu --set full --clock-control none -k regex:conv_ -s 141 -c 47 -o /tmp/prof_convs -f $SMALL > gpurun_out/prof_ncu_full.log 2>&1
+  echo "full capture exit=$?"
+  ncu -i /tmp/prof_convs.ncu-rep --page raw --csv > gpurun_out/prof_convs_raw.csv 2> gpurun_out/prof_export.log
+}
+TRAIN="python bench.py --workload train --steps 2 --warmup 3 --no-cpu-baseline --no-profile --no-graph"
+timeout 300 $TRAIN > gpurun_out/prof_train_plain.log 2>&1 && {
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 1200 -c 1400 --csv --log-file gpurun_out/prof_train_launches.csv $TRAIN > gpurun_out/prof_train_ncu.log 2>&1
+  echo "train launch list exit=$?"
+}
+ls -la gpurun_out | grep prof_
