@@ -45,8 +45,13 @@ def inspect_tile(infile, tile_shape=(8192, 8192), subtile_shape=(512, 512)) -> T
         return inspect_array(infile.shape[-2:], tile_shape, subtile_shape)
     if hasattr(infile, "shape") and not isinstance(infile, (str, Path)):
         return inspect_array(tuple(infile.shape)[-2:], tile_shape, subtile_shape)
-    import rioxarray  # optional dependency
-
+    try:
+        import rioxarray  # optional dependency
+    except ImportError:
+        from PIL import Image
+        Image.MAX_IMAGE_PIXELS = None
+        with Image.open(infile) as im:           # header only: (width, height)
+            return inspect_array((im.size[1], im.size[0]), tile_shape, subtile_shape)
     with rioxarray.open_rasterio(infile).sel(band=1, drop=True) as da:
         return inspect_array(tuple(da.shape), tile_shape, subtile_shape)
 
@@ -92,15 +97,28 @@ class Tiler:
         self._subtiles_to_use = mask.ravel()
 
     def load_file(self, infile, tile_shape=None, subtile_shape=None) -> None:
-        import rioxarray  # optional dependency (absent in the build image)
-
+        """``tiler.py:82-132``.  With rioxarray installed this is the reference's call sequence; without it (this image) the
+        raster values and the geo-referencing tags come from ``deployment.geotiff.read_geotiff`` (Pillow)."""
         self._infile = infile
+        try:
+            import rioxarray  # optional dependency (absent in the build image)
+        except ImportError:
+            from .geotiff import read_geotiff
+            values, self._geo_tags = read_geotiff(infile)
+            self._source = None
+            self.load_array(values, tile_shape, subtile_shape)
+            self._target = "geotiff"          # marks: there is a geo-referenced target to write
+            return
         self._source = rioxarray.open_rasterio(self._infile, chunks={"band": 4, "x": 256, "y": 256})
         self.load_array(self._source.values, tile_shape, subtile_shape)
         self._target = self._source.sel(band=1, drop=True).astype("uint8").copy(deep=True)
 
     def write_file(self, outfile) -> None:
-        if self._target is not None:
+        """LZW-compressed single-band mask, geo-referenced like the input (``tiler.py:134-140``)"""
+        if isinstance(self._target, str):
+            from .geotiff import write_geotiff
+            write_geotiff(outfile, self.result, getattr(self, "_geo_tags", None))
+        elif self._target is not None:
             self._target[:] = self.result
             self._target.rio.to_raster(outfile, compress="LZW", tiled=True)
 
@@ -116,7 +134,7 @@ class Tiler:
         expanded = np.zeros((self._subtiles_to_use.size, d, d), dtype=np.uint8)
         expanded[self._subtiles_to_use] = batches.astype(np.uint8)  # uint8 on assignment (tiler.py:168)
         self._outdata = unmake_blocks_vectorized(expanded, d, self._tile_shape[0], self._tile_shape[1])
-        if self._target is not None:
+        if self._target is not None and not isinstance(self._target, str):
             self._target = self._target.load()
             self._target.loc[:] = self.result
 

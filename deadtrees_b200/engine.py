@@ -157,6 +157,11 @@ class UnetEngine:
                                       2 * C_in * R * S * C_out)
 
     def _build(self, sd):
+        self._build_encoder(sd)
+        self._build_decoder(sd)
+        self._build_head(sd)
+
+    def _build_encoder(self, sd):
         self._conv(sd, "stem", "encoder.conv1", "encoder.bn1", 2, 3, True, stem=True)
         for li, nblk in enumerate(RESNET34_LAYERS, start=1):
             for b in range(nblk):
@@ -166,6 +171,8 @@ class UnetEngine:
                 self._conv(sd, p + ".conv2", p + ".conv2", p + ".bn2", 1, 1, True)  # ReLU after the residual add
                 if p + ".downsample.0.weight" in sd:
                     self._conv(sd, p + ".downsample", p + ".downsample.0", p + ".downsample.1", stride, 0, False)
+
+    def _build_decoder(self, sd):
         self.decoder_blocks = 0
         while f"decoder.blocks.{self.decoder_blocks}.conv1.0.weight" in sd:
             self.decoder_blocks += 1
@@ -177,6 +184,8 @@ class UnetEngine:
             self._conv(sd, p + ".conv1", p + ".conv1.0", p + ".conv1.1", 1, 1, True, C_x=x_ch, upsample=True)
             self._conv(sd, p + ".conv2", p + ".conv2.0", p + ".conv2.1", 1, 1, True)
             x_ch = self.layers[p + ".conv1"].C_out
+
+    def _build_head(self, sd):
         hw = sd["segmentation_head.0.weight"].float()
         if hw.shape[0] != self.classes:
             raise ValueError("segmentation head does not match `classes`")
@@ -258,6 +267,10 @@ class UnetEngine:
             f[li + 1] = cur
         if keep is not None:
             keep.update({f"f{i}": f[i] for i in f})
+        return self._decode(f, N, T, buf, keep)
+
+    def _decode(self, f, N, T, buf, keep):
+        """decoder of ``smp.Unet``: five blocks, each nearest x2 + concat(skip) -> conv -> conv (never materialised)"""
         xcur, H = f[5], T // 32
         skips = [f[4], f[3], f[2], f[1], None]
         for i in range(5):
@@ -292,6 +305,68 @@ class UnetEngine:
                      logits_nhwc=out.get("logits_nhwc"), mask=out.get("mask"))
         return out
 
+
+
+class UnetPlusPlusEngine(UnetEngine):
+    """B200 forward pass of ``smp.UnetPlusPlus(resnet34)`` (``deadtrees/network/segmodel.py:63-64``): the
+    resnet34 encoder and the head of :class:`UnetEngine`, and the nested decoder whose topology the reference vendors in
+    ``deadtrees/network/extra/efficientunetplusplus/decoder.py:116-185`` - blocks ``x_{depth}_{layer}``, each
+    nearest x2(x) ++ [denser maps ..., encoder feature] -> conv3x3+BN+ReLU -> conv3x3+BN+ReLU.
+
+    Every block runs on the same fused kernels as the Unet decoder: the up-sampled operand is read at low resolution
+    (never materialised), the concatenated skip maps are one NHWC tensor (``torch.cat`` of the block's dense inputs -
+    a copy of plumbing size; a multi-operand loader is not built)."""
+
+    def _build_decoder(self, sd):
+        self.decoder_blocks = 0
+        self.pp_blocks = []
+        enc = [512, 256, 128, 64, 64]
+        dec = []
+        li = 0
+        while f"decoder.blocks.x_0_{li}.conv1.0.weight" in sd:
+            dec.append(sd[f"decoder.blocks.x_0_{li}.conv1.0.weight"].shape[0])
+            li += 1
+        if len(dec) != 5:
+            raise NotImplementedError("only encoder_depth=5 / five decoder levels are supported")
+        in_ch = [enc[0]] + dec[:-1]
+        skip_ch = enc[1:] + [0]
+        for layer_idx in range(4):
+            for depth_idx in range(layer_idx + 1):
+                cx = in_ch[layer_idx] if depth_idx == 0 else skip_ch[layer_idx - 1]
+                self._pp_block(sd, f"x_{depth_idx}_{layer_idx}", cx)
+        self._pp_block(sd, "x_0_4", in_ch[-1])
+
+    def _pp_block(self, sd, name, cx):
+        p = f"decoder.blocks.{name}"
+        self._conv(sd, p + ".conv1", p + ".conv1.0", p + ".conv1.1", 1, 1, True, C_x=cx, upsample=True)
+        self._conv(sd, p + ".conv2", p + ".conv2.0", p + ".conv2.1", 1, 1, True)
+        self.pp_blocks.append(name)
+
+    def _decode(self, f, N, T, buf, keep):
+        feats = [f[5], f[4], f[3], f[2], f[1]]             # head of the encoder first (decoder.py:158-159)
+        dense = {}
+
+        def block(name, x_low, skip):
+            p = f"decoder.blocks.{name}"
+            H = x_low.shape[1] * 2
+            c_out = self.layers[p + ".conv1"].C_out
+            t = self._run(p + ".conv1", x_low, N, H, H, skip=skip, out=buf("t_" + name, H, c_out))
+            return self._run(p + ".conv2", t, N, H, H, out=buf("o_" + name, H, c_out))
+
+        depth = 4
+        for layer_idx in range(4):
+            for depth_idx in range(depth - layer_idx):
+                if layer_idx == 0:
+                    dense[f"x_{depth_idx}_{depth_idx}"] = block(f"x_{depth_idx}_{depth_idx}", feats[depth_idx], feats[depth_idx + 1])
+                else:
+                    li = depth_idx + layer_idx
+                    cat = [dense[f"x_{idx}_{li}"] for idx in range(depth_idx + 1, li + 1)] + [feats[li + 1]]
+                    skip = torch.cat(cat, dim=-1)          # NHWC: channel concat in decoder.py:171-176's order
+                    dense[f"x_{depth_idx}_{li}"] = block(f"x_{depth_idx}_{li}", dense[f"x_{depth_idx}_{li - 1}"], skip)
+        out = block("x_0_4", dense["x_0_3"], None)
+        if keep is not None:
+            keep.update(dense)
+        return out
 
 
 def conv_flops_per_tile(T: int, in_channels: int = 3, classes: int = 3) -> float:

@@ -25,7 +25,7 @@ from ..loss import fused
 from ..loss.gdl import GeneralizedDiceLoss
 from ..loss.gwdl import GeneralizedWassersteinDiceLoss
 from ..loss.losses import BoundaryLoss, DiceLoss, FocalLoss, class2one_hot
-from .unet import Unet
+from .unet import Unet, UnetPlusPlus
 
 log = logging.getLogger(__name__)
 
@@ -98,8 +98,9 @@ class SemSegment(_Base):  # type: ignore[misc]
         architecture = str(network.architecture).lower().strip()
         if architecture == "unet":
             Model = Unet
-        elif architecture in ["unetplusplus", "unet++", "resunet", "resunetplusplus", "resunet++",
-                              "efficientunetplusplus", "efficientunet++"]:
+        elif architecture in ["unetplusplus", "unet++"]:
+            Model = UnetPlusPlus       # nested decoder on the same fused kernels (inference)
+        elif architecture in ["resunet", "resunetplusplus", "resunet++", "efficientunetplusplus", "efficientunet++"]:
             raise NotImplementedError(
                 f"architecture <{architecture}> is outside the B200 hot path (SURVEY.md D1); only Unet is built")
         else:

@@ -14,7 +14,7 @@ from typing import Optional, Sequence
 import torch
 import torch.nn as nn
 
-from ..engine import RESNET34_LAYERS, RESNET34_PLANES, UnetEngine
+from ..engine import RESNET34_LAYERS, RESNET34_PLANES, UnetEngine, UnetPlusPlusEngine
 from .. import ops
 
 
@@ -64,7 +64,31 @@ class _Decoder(nn.Module):
         self.blocks = nn.ModuleList(_DecoderBlock(i, s, o) for i, s, o in zip(cins, skips, decoder_channels))
 
 
+class _DecoderPlusPlus(nn.Module):
+    """parameters of smp's ``UnetPlusPlusDecoder`` in its registration order (topology:
+    ``deadtrees/network/extra/efficientunetplusplus/decoder.py:116-153``)"""
+
+    def __init__(self, decoder_channels: Sequence[int]):
+        super().__init__()
+        enc = [512, 256, 128, 64, 64]
+        in_ch = [enc[0]] + list(decoder_channels[:-1])
+        skip_ch = enc[1:] + [0]
+        out_ch = list(decoder_channels)
+        blocks = {}
+        for layer_idx in range(len(in_ch) - 1):
+            for depth_idx in range(layer_idx + 1):
+                if depth_idx == 0:
+                    i, s, o = in_ch[layer_idx], skip_ch[layer_idx] * (layer_idx + 1), out_ch[layer_idx]
+                else:
+                    o, s, i = skip_ch[layer_idx], skip_ch[layer_idx] * (layer_idx + 1 - depth_idx), skip_ch[layer_idx - 1]
+                blocks[f"x_{depth_idx}_{layer_idx}"] = _DecoderBlock(i, s, o)
+        blocks[f"x_0_{len(in_ch) - 1}"] = _DecoderBlock(in_ch[-1], 0, out_ch[-1])
+        self.blocks = nn.ModuleDict(blocks)
+
+
 class Unet(nn.Module):
+    ENGINE = UnetEngine
+
     def __init__(self, encoder_name: str = "resnet34", encoder_depth: int = 5, encoder_weights: Optional[str] = None,
                  decoder_channels: Sequence[int] = (256, 128, 64, 32, 16), in_channels: int = 3, classes: int = 1,
                  precision: str = "bf16", **unused):
@@ -75,12 +99,15 @@ class Unet(nn.Module):
             raise NotImplementedError("the B200 build implements encoder_depth=5, decoder_channels=[256,128,64,32,16]")
         self.in_channels, self.classes, self.precision = int(in_channels), int(classes), precision
         self.encoder = _Encoder(self.in_channels)
-        self.decoder = _Decoder(list(decoder_channels))
+        self.decoder = self._make_decoder(list(decoder_channels))
         self.segmentation_head = nn.Sequential(nn.Conv2d(decoder_channels[-1], self.classes, 3, padding=1),
                                                nn.Identity(), nn.Identity())
         self._engine: Optional[UnetEngine] = None
         self._engine_key = None
         self._train_engine = None
+
+    def _make_decoder(self, decoder_channels):
+        return _Decoder(decoder_channels)
 
     # -- engine management -------------------------------------------------------------------
     def _param_version(self):
@@ -94,7 +121,7 @@ class Unet(nn.Module):
             if self.training:
                 raise NotImplementedError(
                     "train-mode (batch-statistics BatchNorm) forward is not implemented in this round; call .eval()")
-            self._engine = UnetEngine(self.state_dict(), self.in_channels, self.classes, precision=self.precision)
+            self._engine = self.ENGINE(self.state_dict(), self.in_channels, self.classes, precision=self.precision)
             self._engine_key = key
         return self._engine
 
@@ -125,3 +152,20 @@ class Unet(nn.Module):
         eng = self.engine()
         xin = ops.pack_input_nchw(x, self.in_channels, eng.act_dtype)
         return eng.forward(xin, want_logits_nchw=True)["logits_nchw"]
+
+
+class UnetPlusPlus(Unet):
+    """drop-in for ``smp.UnetPlusPlus(encoder_name="resnet34")`` (``segmodel.py:63-64``): inference on the B200 kernels
+    (:class:`deadtrees_b200.engine.UnetPlusPlusEngine`); the training step is built for the Unet path only."""
+    ENGINE = UnetPlusPlusEngine
+
+    def _make_decoder(self, decoder_channels):
+        return _DecoderPlusPlus(decoder_channels)
+
+    def train_engine(self):
+        raise NotImplementedError("the B200 training step implements architecture 'unet'; Unet++ runs inference (eval) only")
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if self.training:
+            raise NotImplementedError("the B200 training step implements architecture 'unet'; call .eval() for Unet++")
+        return super().forward(x)

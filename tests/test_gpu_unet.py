@@ -236,3 +236,46 @@ def test_mosaic_pipeline_vs_oracle(precision, H, W, T, ov, bt):
         if ov:   # a lower shard without the neighbour's boundary logits would blend uninitialised memory: refused
             with pytest.raises(ValueError, match="boundary logits"):
                 mi.run(torch.from_numpy(mosaic).cuda(), "hwc", tile_rows=(gy // 2, gy), out=out)
+
+
+# ---- Unet++ (smp.UnetPlusPlus, segmodel.py:63-64) ---------------------------------------------------------
+@pytest.mark.parametrize("precision,T,n", [("fp32", 64, 1), ("bf16", 256, 2)])
+def test_unetplusplus_vs_oracle(precision, T, n):
+    """nested decoder on the same fused kernels: fp32 check mode within 1e-4 of the oracle restatement; the bf16 tensor-core
+    path within the random-init yardstick of test_unet_bf16_tensor_core (relative rms, mask agreement)."""
+    from deadtrees_b200.engine import UnetPlusPlusEngine
+    from oracle import ref_unetpp
+    model = ref_unetpp.build_reference_unetpp(3, 3)
+    _, x = normalized_tiles(n, T, 3)
+    with torch.no_grad():
+        ref = model(x)
+    eng = UnetPlusPlusEngine(model.state_dict(), 3, 3, precision=precision)
+    dt = torch.float32 if precision == "fp32" else torch.bfloat16
+    out = eng.forward(nhwc4(x, dt).cuda(), want_logits_nchw=True, want_mask=True)
+    torch.cuda.synchronize()
+    got = out["logits_nchw"].cpu()
+    err, rel = report(f"unet++ {precision} T={T}", got, ref)
+    agree = agreement(out["mask"], ref.argmax(1))
+    print(f"unet++ {precision}: mask agreement {agree:.5f}")
+    if precision == "fp32":
+        assert err < 1e-4 * max(1.0, ref.abs().max().item()) and agree >= 0.999
+    else:
+        rel_rms = ((got - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item()
+        assert rel_rms < 3e-2 and agree >= 0.97
+
+
+def test_unetplusplus_semsegment_api(tmp_path):
+    """architecture "unet++" through SemSegment / checkpoint / PyTorchInference; training is the Unet path only"""
+    from oracle import ref_unetpp
+    model = ref_unetpp.build_reference_unetpp(3, 3)
+    m = SemSegment(dict(NETWORK, architecture="unet++", precision="fp32"), TRAINING)
+    m.model.load_state_dict(model.state_dict())
+    ckpt = tmp_path / "pp.ckpt"
+    m.save_checkpoint(ckpt)
+    inf = PyTorchInference(ckpt)
+    _, x = normalized_tiles(2, 64, 3)
+    out = inf.run(x.cuda(), device="cuda")
+    assert agreement(out, ref_unet.run_inference(model, x, 3)) >= 0.999
+    m.cuda().train()
+    with pytest.raises(NotImplementedError):
+        m.model(x.cuda())

@@ -53,6 +53,13 @@ def test_semsegment_constructor_contract():
     assert m.classes_int_wout_bg == [1, 2] and m.hparams.training.learning_rate == 3e-4
     with pytest.raises(NotImplementedError):
         SemSegment(dict(NETWORK, architecture="fancynet"), TRAINING)
+    with pytest.raises(NotImplementedError):
+        SemSegment(dict(NETWORK, architecture="resunet++"), TRAINING)     # depthwise / scSE forks: outside the hot path
+    # Unet++ (segmodel.py:63-64): smp.UnetPlusPlus's parameter set, key for key
+    from oracle import ref_unetpp
+    pp = SemSegment(dict(NETWORK, architecture="UnetPlusPlus"), TRAINING)
+    assert list(pp.state_dict()) == ["model." + k for k in ref_unetpp.UnetPlusPlus(3, 3).state_dict()]
+    assert sum(p.numel() for p in pp.parameters()) == 26078899
     with pytest.raises(AssertionError):
         SemSegment(dict(NETWORK, losses=["GDICE", "DICE"]), TRAINING)
     with pytest.raises(NotImplementedError):
