@@ -359,8 +359,8 @@ def main_b200(a):
         if tc > 0:
             ach = wc / tc / 1e12
             out["roofline"] = {"bound": "tensor",
-                               "kernel": "all conv launches of the Unet (tcgen05 implicit GEMM: conv_stem_rows, conv_res, "
-                                         "conv_halo, conv_halo_quad, conv_pair, conv_tc, tail_fused kernels)",
+                               "kernel": "all conv launches of the Unet (tcgen05 implicit GEMM: conv_stem_rows, conv_row, "
+                                         "conv_res, conv_halo, conv_halo_quad, conv_pair, conv_tc kernels)",
                                "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"],
                                "traffic": None, "launches": nc, "share_of_step": tc * 1e3 / ms_prof_total,
                                "flops_per_tile": conv_flops_per_tile(T, 3, 3), "peak_source": pk["source"]}
