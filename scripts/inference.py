@@ -2,8 +2,10 @@
 
 Per input raster: load -> zero-pad to the tile shape -> sub-tiles -> normalise -> Unet -> argmax -> stitch ->
 crop -> write, as ``scripts/inference.py:80-111`` of the reference; the per-batch Python loop there
-(:93-105) is one device pipeline here (``MosaicInference``).  GeoTIFF I/O needs rioxarray (optional);
-``.npy`` rasters of shape (bands, H, W) uint8 are read and written without it.
+(:93-105) is one device pipeline here (``MosaicInference``).  GeoTIFF I/O: rioxarray when installed, else the GDAL-free
+reader / writer of ``deadtrees_b200.deployment.geotiff``; with ``--overlap N --pipeline`` a directory of GeoTIFF tiles runs
+through ``geotiff.segment_files`` (whole rasters on the device, the next file decoded and the previous mask encoded behind the
+GPU).  ``.npy`` rasters of shape (bands, H, W) uint8 are read and written as they are.
 """
 import argparse
 import sys
@@ -31,6 +33,8 @@ def main():
     parser.add_argument("--all", action="store_true", dest="all", default=False, help="process complete directory")
     parser.add_argument("--nopreview", action="store_false", dest="preview", default=True, help="produce preview images")
     parser.add_argument("--overlap", type=int, default=0, help="extension: overlapping sub-tiles with blended stitching")
+    parser.add_argument("--pipeline", action="store_true", default=False,
+                        help="extension: GeoTIFF inputs through the double-buffered file pipeline (no padding to the tile shape)")
     args = parser.parse_args()
 
     if len(args.model) == 0:
@@ -46,6 +50,13 @@ def main():
         infiles = sorted(args.infile.glob("ortho*.tif")) + sorted(args.infile.glob("ortho*.npy"))
     else:
         infiles = [args.infile]
+
+    if args.pipeline and isinstance(inference, PyTorchInference) and all(f.suffix != ".npy" for f in infiles):
+        from deadtrees_b200.deployment import geotiff
+        pipe = MosaicInference(inference._model.cuda(), tile=256, overlap=args.overlap, batch_tiles=64)
+        written = geotiff.segment_files(pipe, infiles, args.outpath, is_valid=is_valid_tile)
+        print(f"{len(written)} of {len(infiles)} tiles segmented -> {args.outpath}")
+        return
 
     pipe = None
     for infile in infiles:
