@@ -52,8 +52,10 @@ _SIGNATURES = {
     "dt_stitch_blend_argmax": ([_p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _i, _i, _i, _i, _p], C.c_int),
     "dt_conv2d_fwd": ([C.POINTER(ConvDesc), _p, _p, _p, _p, _p, _p, _p, _p], C.c_int),
     "dt_maxpool3x3s2": ([_p, _i, _i, _i, _i, _i, _p, _p], C.c_int),
+    "dt_stem_pool_fwd": ([_p, _p, _p, _p, _p, _p, _p, _p], C.c_int),
     "dt_head_fwd": ([_p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p], C.c_int),
     "dt_head_fwd_tc": ([_p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p], C.c_int),
+    "dt_tail_fused": ([_p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p], C.c_int),
     "dt_argmax_nchw": ([_p, _i, _i, _i, _i, _p, _p], C.c_int),
     "dt_mode_vote": ([_p, _i, _i64, _i, _p, _p], C.c_int),
     "dt_seg_loss_partials": ([_p, _p, _i, _i, _i, _i, _p, _p, _p, _p], C.c_int),

@@ -14,6 +14,8 @@
 #include <cstring>
 #include <mutex>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace {
@@ -194,6 +196,8 @@ namespace {
 
 struct StemRowParams {
   int Ho, Wo, total_rows, tiles_per_row, relu, stages;
+  int R, chunks, total_items;            // work items = R consecutive output rows of one image (R = 1: single rows)
+  __nv_bfloat16* pool;                   // POOL: (N, Ho/2, Wo/2, 64) max-pooled output
   int row_bytes, stage_bytes;            // one input row of the frame, 7 rows rounded up to 128 B
   int64_t image_bytes;                   // one frame image
   const uint8_t* x;
@@ -210,9 +214,14 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t b
 constexpr int ROW_MAX_STAGES = 8;
 constexpr int OUT_TILE = BM * BN * 2;        // 16 KB staging tile of the TMA output store
 
-__global__ void __launch_bounds__(kThreads, 1)
+// POOL: the 3x3 / stride-2 / pad-1 max pooling that follows the stem (resnet.maxpool) is computed from the staged output
+// rows: a CTA walks R consecutive output rows of one image (plus the row above them, recomputed and not stored), keeps the
+// last three staged rows in a ring and emits pooled row y after output row 2y + 1.  Requires Wo == 128 (one tile per row).
+template <bool POOL>
+__global__ void __launch_bounds__(kThreads, 2)
 conv_stem_rows_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ CUtensorMap tm_y,
                       const StemRowParams p) {
+  constexpr int OUT_TILES = POOL ? 3 : 2;
   constexpr int TMEM_COLS = 2 * BN;
   constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
   extern __shared__ uint8_t smem_raw[];
@@ -222,7 +231,7 @@ conv_stem_rows_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_con
   // two 16 KB staging tiles for the TMA output store (1024-byte aligned: SWIZZLE_128B), then the barriers
   uint8_t* smem_o = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_a + static_cast<size_t>(p.stages) * p.stage_bytes) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_o + 2 * OUT_TILE);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_o + OUT_TILES * OUT_TILE);
   uint64_t* w_full = bars;
   uint64_t* full = w_full + 1;                   // [ROW_MAX_STAGES]
   uint64_t* empty = full + ROW_MAX_STAGES;       // [ROW_MAX_STAGES]
@@ -255,13 +264,15 @@ conv_stem_rows_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_con
       int st = 0;
       uint32_t ph = 0;
       const uint32_t bytes = static_cast<uint32_t>(ROWS * p.row_bytes);
-      for (int row = blockIdx.x; row < p.total_rows; row += gridDim.x) {
-        const int n = row / p.Ho, ho = row - n * p.Ho;
-        mbar_wait(&empty[st], ph ^ 1u);
-        mbar_arrive_expect_tx(&full[st], bytes);
-        bulk_load(smem_a + static_cast<size_t>(st) * p.stage_bytes,
-                  p.x + n * p.image_bytes + static_cast<int64_t>(2 * ho) * p.row_bytes, bytes, &full[st]);
-        if (++st == p.stages) { st = 0; ph ^= 1u; }
+      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+        const int n = item / p.chunks, r0 = (item - n * p.chunks) * p.R;
+        for (int ho = (POOL && r0 > 0) ? r0 - 1 : r0; ho < r0 + p.R; ++ho) {
+          mbar_wait(&empty[st], ph ^ 1u);
+          mbar_arrive_expect_tx(&full[st], bytes);
+          bulk_load(smem_a + static_cast<size_t>(st) * p.stage_bytes,
+                    p.x + n * p.image_bytes + static_cast<int64_t>(2 * ho) * p.row_bytes, bytes, &full[st]);
+          if (++st == p.stages) { st = 0; ph ^= 1u; }
+        }
       }
     }
   } else if (warp == 1) {
@@ -271,7 +282,9 @@ conv_stem_rows_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_con
       mbar_wait(w_full, 0);
       int st = 0, buf = 0;
       uint32_t ph = 0, pbuf = 0;
-      for (int row = blockIdx.x; row < p.total_rows; row += gridDim.x) {
+      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+        const int r0 = (item % p.chunks) * p.R;
+        for (int ho = (POOL && r0 > 0) ? r0 - 1 : r0; ho < r0 + p.R; ++ho) {
         mbar_wait(&full[st], ph);
         tc_fence_after();
         const uint32_t a_stage = smem_u32(smem_a + static_cast<size_t>(st) * p.stage_bytes);
@@ -295,6 +308,7 @@ conv_stem_rows_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_con
           if ((buf ^= 1) == 0) pbuf ^= 1u;
         }
         if (++st == p.stages) { st = 0; ph ^= 1u; }
+        }
       }
     }
   } else {
@@ -306,10 +320,13 @@ conv_stem_rows_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_con
     const bool issuer = threadIdx.x == 64;              // first epilogue thread (warp 2, lane 0)
     int buf = 0, ob = 0;
     uint32_t pbuf = 0;
-    for (int row = blockIdx.x; row < p.total_rows; row += gridDim.x) {
+    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+      const int n_img = item / p.chunks, r0 = (item - n_img * p.chunks) * p.R;
+      for (int ho = (POOL && r0 > 0) ? r0 - 1 : r0; ho < r0 + p.R; ++ho) {
+      const int row = n_img * p.Ho + ho;
       for (int t = 0; t < p.tiles_per_row; ++t) {
         const int m0 = row * p.Wo + t * BM;
-        if (issuer) bulk_wait_group_read<1>();          // the store that last read staging tile `ob` has drained it
+        if (issuer) bulk_wait_group_read<OUT_TILES - 1>();   // the store that last read staging tile `ob` has drained it
         named_bar_sync(1, 128);
         mbar_wait(&tmem_full[buf], pbuf);
         tc_fence_after();
@@ -345,11 +362,46 @@ conv_stem_rows_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_con
         fence_proxy_async_smem();                       // generic-proxy writes visible to the TMA (async proxy)
         named_bar_sync(1, 128);
         if (issuer) {
-          tma_store_2d(&tm_y, smem_o + ob * OUT_TILE, 0, m0);
-          bulk_commit_group();
+          if (!POOL || ho >= r0) tma_store_2d(&tm_y, smem_o + ob * OUT_TILE, 0, m0);   // the recomputed row is not stored
+          bulk_commit_group();                          // (an empty group keeps the ring's group count uniform)
         }
-        ob ^= 1;
+        if (POOL && (ho & 1) && ho > r0) {
+          // pooled row y = max over output rows 2y-1 .. 2y+1 (ring tiles ob+1, ob+2, ob) and columns 2x-1 .. 2x+1.
+          // thread = one 16-byte channel chunk of four consecutive pooled pixels: the eight lanes of a quarter warp read the
+          // eight chunks of one staged pixel (conflict-free under the 128-byte swizzle) and write 128 contiguous bytes;
+          // same __hmax2 as dt_maxpool3x3s2, max is exact in any order
+          const int ch = lrow & 7, px0 = (lrow >> 3) * 4;
+          const __nv_bfloat162 ninf = __float2bfloat162_rn(-INFINITY);
+          __nv_bfloat162 col[9][4];                     // column maxima of staged columns 2*px0 - 1 .. 2*px0 + 7
+#pragma unroll
+          for (int cx = 0; cx < 9; ++cx) {
+            const int sx = 2 * px0 - 1 + cx;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) col[cx][u] = ninf;
+            if (sx < 0) continue;
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy) {
+              if (dy == 0 && ho < 2) continue;          // row -1 of the image
+              const uint4 v = *reinterpret_cast<const uint4*>(smem_o + ((ob + 1 + dy) % 3) * OUT_TILE + sx * 128 +
+                                                              ((ch ^ (sx & 7)) << 4));
+              const __nv_bfloat162* pv = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+              for (int u = 0; u < 4; ++u) col[cx][u] = __hmax2(col[cx][u], pv[u]);
+            }
+          }
+          uint8_t* dst = reinterpret_cast<uint8_t*>(p.pool) +
+                         (((static_cast<int64_t>(n_img) * (p.Ho >> 1) + (ho >> 1)) * (p.Wo >> 1) + px0) * BN) * 2 + ch * 16;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            __nv_bfloat162 m[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) m[u] = __hmax2(__hmax2(col[2 * i][u], col[2 * i + 1][u]), col[2 * i + 2][u]);
+            *reinterpret_cast<uint4*>(dst + i * BN * 2) = *reinterpret_cast<const uint4*>(m);
+          }
+        }
+        if (++ob == OUT_TILES) ob = 0;
         if ((buf ^= 1) == 0) pbuf ^= 1u;
+      }
       }
     }
     if (issuer) bulk_wait_group<0>();                   // all stores complete before the CTA exits
@@ -367,8 +419,9 @@ conv_stem_rows_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_con
 
 // x: zero-bordered (N, H+6, W+8, 4) bf16; w: bf16 [64][256] with k = r*32 + s*4 + c; y: (N, H/2, W/2, 64) bf16.
 // Returns DT_ERR_UNSUPPORTED when the output grid cannot be tiled into 128-pixel boxes.
+// pooled != nullptr: also write the 3x3 / s2 / pad-1 max pooling of y, (N, H/4, W/4, 64) (DT_ERR_UNSUPPORTED unless W/2 == 128).
 int dt_conv_stem(const dt_conv_desc* d, const void* x, const void* w, const float* scale, const float* shift, void* y,
-                 cudaStream_t s) {
+                 void* pooled, cudaStream_t s) {
   if (d->C_out != BN || d->H % 2 || d->W % 2) return DT_ERR_UNSUPPORTED;
   const int Ho = d->H / 2, Wo = d->W / 2;
   int bw, bh, bn;
@@ -416,6 +469,8 @@ int dt_conv_stem(const dt_conv_desc* d, const void* x, const void* w, const floa
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     DT_REQUIRE(r == CUDA_SUCCESS, DT_ERR_CUDA, "stem weight tensor map: CUresult %d", static_cast<int>(r));
   }
+  const bool want_pool = pooled != nullptr;
+  if (want_pool && !(Wo == BM && Ho % 8 == 0 && !(d->flags & DT_CONV_NO_HALO))) return DT_ERR_UNSUPPORTED;
   if (Wo % BM == 0 && !(d->flags & DT_CONV_NO_HALO)) {
     // row form: the im2col operand is read in place from the raw input rows (no-swizzle descriptors)
     StemRowParams q;
@@ -423,12 +478,35 @@ int dt_conv_stem(const dt_conv_desc* d, const void* x, const void* w, const floa
     q.row_bytes = static_cast<int>(Wp * 8);
     q.stage_bytes = (ROWS * q.row_bytes + 127) / 128 * 128;
     q.image_bytes = static_cast<int64_t>(Hp) * Wp * 8;
-    q.stages = (200 * 1024 - W_BYTES - 2 * OUT_TILE - 1024) / q.stage_bytes;
+    q.pool = static_cast<__nv_bfloat16*>(pooled);
+    const int out_tiles = want_pool ? 3 : 2;
+    // Two CTAs per SM when the stages fit in half the shared memory (T <= 256): the 14 MMAs of a row chain into one
+    // accumulator (138 clk each, profiles/r02_mma_rate.txt), a second CTA's chain and epilogue overlap it.
+    int ctas = 2;
+    q.stages = (111 * 1024 - W_BYTES - out_tiles * OUT_TILE - 2048 - 256) / q.stage_bytes;
+    if (q.stages < (want_pool ? 2 : 3) || getenv("DT_STEM_ONE_CTA")) {
+      ctas = 1;
+      q.stages = (200 * 1024 - W_BYTES - out_tiles * OUT_TILE - 1024) / q.stage_bytes;
+    }
     if (q.stages > ROW_MAX_STAGES) q.stages = ROW_MAX_STAGES;
+    if (ctas == 2 && q.stages > 4) q.stages = 4;
     if (q.stages >= 2 && (ROWS * q.row_bytes) % 16 == 0 && ROWS * q.row_bytes < (1 << 20)) {
       q.x = static_cast<const uint8_t*>(x);
       q.y = static_cast<__nv_bfloat16*>(y);
       q.scale = scale; q.shift = shift;
+      const int slots = ctas * dt_num_sms();
+      q.R = 1;
+      if (want_pool) {   // rows per item: (items per CTA) x (R + 1 rows, one recomputed) is the cost of the slowest CTA
+        long best = -1;
+        for (int R = 32; R >= 8; R >>= 1) {
+          if (Ho % R) continue;
+          const long items = static_cast<long>(d->N) * (Ho / R);
+          const long cost = ((items + slots - 1) / slots) * (R + 1);
+          if (best < 0 || cost < best) { best = cost; q.R = R; }
+        }
+      }
+      q.chunks = Ho / q.R;
+      q.total_items = d->N * q.chunks;
       CUtensorMap tm_y;
       {
         const cuuint64_t ydims[2] = {BN, static_cast<cuuint64_t>(q.total_rows) * Wo};
@@ -439,19 +517,23 @@ int dt_conv_stem(const dt_conv_desc* d, const void* x, const void* w, const floa
                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         DT_REQUIRE(r == CUDA_SUCCESS, DT_ERR_CUDA, "stem output tensor map: CUresult %d", static_cast<int>(r));
       }
-      const int smem_rows = W_BYTES + q.stages * q.stage_bytes + 1024 + 2 * OUT_TILE + 1024 + 256;
+      const int smem_rows = W_BYTES + q.stages * q.stage_bytes + 1024 + out_tiles * OUT_TILE + 1024 + 256;
       static std::once_flag once_rows;
       static cudaError_t attr_rows = cudaSuccess;
       std::call_once(once_rows, [] {
-        attr_rows = cudaFuncSetAttribute(conv_stem_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+        attr_rows = cudaFuncSetAttribute(conv_stem_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+        if (attr_rows == cudaSuccess)
+          attr_rows = cudaFuncSetAttribute(conv_stem_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
       });
       DT_CUDA(attr_rows);
-      const int grid_rows = q.total_rows < dt_num_sms() ? q.total_rows : dt_num_sms();
-      conv_stem_rows_kernel<<<grid_rows, kThreads, smem_rows, s>>>(tm_b, tm_y, q);
+      const int grid_rows = q.total_items < slots ? q.total_items : slots;
+      if (want_pool) conv_stem_rows_kernel<true><<<grid_rows, kThreads, smem_rows, s>>>(tm_b, tm_y, q);
+      else conv_stem_rows_kernel<false><<<grid_rows, kThreads, smem_rows, s>>>(tm_b, tm_y, q);
       DT_LAUNCH_CHECK();
       return DT_OK;
     }
   }
+  if (want_pool) return DT_ERR_UNSUPPORTED;
   StemParams p;
   p.Ho = Ho; p.Wo = Wo;
   p.M_total = d->N * Ho * Wo;

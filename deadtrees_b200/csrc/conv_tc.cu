@@ -487,7 +487,7 @@ int dt_conv_halo(const dt_conv_desc* d, int BN, const void* x, const void* skip,
                  const float* scale, const float* shift, const void* residual, void* y, cudaStream_t s);
 
 int dt_conv_stem(const dt_conv_desc* d, const void* x, const void* w, const float* scale, const float* shift, void* y,
-                 cudaStream_t s);
+                 void* pooled, cudaStream_t s);
 int dt_conv_res(const dt_conv_desc* d, const void* x, const void* w, int Kpad, const float* scale, const float* shift,
                 const void* residual, void* y, cudaStream_t s);
 int dt_conv_pair(const dt_conv_desc* d, const void* x, const void* w, int Kpad, const float* scale, const float* shift,
@@ -527,7 +527,7 @@ extern "C" int dt_conv2d_fwd(const dt_conv_desc* d, const void* x, const void* s
                "dt_conv2d_fwd: DT_CONV_X_PAD3 is the bf16 7x7/s2 stem layout");
     DT_REQUIRE(reinterpret_cast<uintptr_t>(y) % 32 == 0, DT_ERR_BAD_ALIGN,
                "dt_conv2d_fwd: the bf16 output must be 32-byte aligned (256-bit epilogue stores)");
-    const int rc = dt_conv_stem(d, x, w, scale, shift, y, s);
+    const int rc = dt_conv_stem(d, x, w, scale, shift, y, nullptr, s);
     DT_REQUIRE(rc != DT_ERR_UNSUPPORTED, DT_ERR_BAD_SHAPE, "dt_conv2d_fwd: stem output %dx%d cannot be tiled", Ho, Wo);
     return rc;
   }
@@ -658,4 +658,18 @@ extern "C" int dt_conv2d_fwd(const dt_conv_desc* d, const void* x, const void* s
   }
 #undef DT_TC
   return DT_ERR_UNSUPPORTED;
+}
+
+// Stem + resnet.maxpool in one launch (conv_stem.cu, POOL variant): y as dt_conv2d_fwd with DT_CONV_X_PAD3, pooled =
+// maxpool3x3/s2/pad1(y).  DT_ERR_UNSUPPORTED when the fused form does not apply (caller: dt_conv2d_fwd + dt_maxpool3x3s2).
+extern "C" int dt_stem_pool_fwd(const dt_conv_desc* d, const void* x, const void* w, const float* scale, const float* shift,
+                                void* y, void* pooled, dt_stream_t stream) {
+  DT_ARCH_GUARD();
+  DT_REQUIRE(d && x && w && scale && shift && y && pooled, DT_ERR_BAD_SHAPE, "dt_stem_pool_fwd: null argument");
+  DT_REQUIRE(d->C_in == 4 && d->R == 7 && d->S == 7 && d->stride == 2 && d->pad == 3 && d->dtype == DT_BF16 &&
+                 (d->flags & DT_CONV_X_PAD3) && !d->has_residual && !d->upsample,
+             DT_ERR_BAD_SHAPE, "dt_stem_pool_fwd: not the bf16 7x7/s2 stem on the zero-bordered frame");
+  DT_REQUIRE(reinterpret_cast<uintptr_t>(y) % 32 == 0 && reinterpret_cast<uintptr_t>(pooled) % 16 == 0, DT_ERR_BAD_ALIGN,
+             "dt_stem_pool_fwd: outputs must be 32- / 16-byte aligned");
+  return dt_conv_stem(d, x, w, scale, shift, y, pooled, static_cast<cudaStream_t>(stream));
 }

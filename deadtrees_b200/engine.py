@@ -7,6 +7,7 @@ SURVEY.md Appendix A); state-dict key layout = smp's.
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional
 
@@ -237,9 +238,11 @@ class UnetEngine:
             return torch.zeros((N, T + 6, T + 8, 4), dtype=self.act_dtype, device=self.device)
         return torch.empty((N, T, T, 4), dtype=self.act_dtype, device=self.device)
 
-    def forward_features(self, x: torch.Tensor, keep: Optional[Dict[str, torch.Tensor]] = None) -> torch.Tensor:
+    def forward_features(self, x: torch.Tensor, keep: Optional[Dict[str, torch.Tensor]] = None,
+                         stop_before_tail: bool = False) -> torch.Tensor:
         """x: (N, T, T, 4) NHWC in the engine's activation dtype, or the padded frame (N, T+6, T+8, 4) from
-        `alloc_input` -> decoder output (N, T, T, 16)."""
+        `alloc_input` -> decoder output (N, T, T, 16); with `stop_before_tail` the output of the last block's conv1
+        (the input of :func:`ops.tail_fused`)."""
         N, H_in, W_in, C4 = x.shape
         padded = W_in == H_in + 2
         T = H_in - 6 if padded else H_in
@@ -248,8 +251,13 @@ class UnetEngine:
         ws = self._ws.setdefault((N, T), {})
         buf = lambda key, h, c: self._buf(ws, key, (N, h, h, c))
         f = {}
-        f[1] = self._run("stem", x, N, T, T, out=buf("f1", T // 2, 64), flags=CONV_X_PAD3 if padded else 0)
-        cur = ops.maxpool3x3s2(f[1], out=buf("pool", T // 4, 64))
+        if padded and T == 256 and self.layers["stem"].relu and os.environ.get("DT_STEM_POOL_FUSED", "1") != "0":
+            L = self.layers["stem"]                 # stem + maxpool in one launch: the pooling reads the rows from smem
+            f[1], cur = buf("f1", T // 2, 64), buf("pool", T // 4, 64)
+            ops.stem_pool(x, L.w, L.scale, L.shift, N=N, H=T, W=T, out=f[1], pooled=cur, algo_cin=self.in_channels)
+        else:
+            f[1] = self._run("stem", x, N, T, T, out=buf("f1", T // 2, 64), flags=CONV_X_PAD3 if padded else 0)
+            cur = ops.maxpool3x3s2(f[1], out=buf("pool", T // 4, 64))
         H = T // 4
         for li, (planes, nblk) in enumerate(zip(RESNET34_PLANES, RESNET34_LAYERS), start=1):
             for b in range(nblk):
@@ -267,9 +275,18 @@ class UnetEngine:
             f[li + 1] = cur
         if keep is not None:
             keep.update({f"f{i}": f[i] for i in f})
-        return self._decode(f, N, T, buf, keep)
+        return self._decode(f, N, T, buf, keep, stop_before_tail)
 
-    def _decode(self, f, N, T, buf, keep):
+    TAIL_LAYER = "decoder.blocks.4.conv2"
+
+    def tail_fusable(self, T: int) -> bool:
+        """True when decoder.blocks.4.conv2 and the head run as one launch (conv_tail.cu): bf16 path, 16 channels into
+        the head, full rows of 128 or 256 pixels.  ``DT_TAIL_FUSED=0`` keeps the two launches."""
+        L = self.layers.get(self.TAIL_LAYER)
+        return (self.head_w_tc is not None and L is not None and L.C_in == 16 and L.C_out == 16 and not self.conv_flags
+                and T in (128, 256) and os.environ.get("DT_TAIL_FUSED", "1") != "0")
+
+    def _decode(self, f, N, T, buf, keep, stop_before_tail=False):
         """decoder of ``smp.Unet``: five blocks, each nearest x2 + concat(skip) -> conv -> conv (never materialised)"""
         xcur, H = f[5], T // 32
         skips = [f[4], f[3], f[2], f[1], None]
@@ -278,6 +295,8 @@ class UnetEngine:
             H *= 2
             c_out = self.layers[p + ".conv1"].C_out
             t = self._run(p + ".conv1", xcur, N, H, H, skip=skips[i], out=buf(f"dt{i}", H, c_out))
+            if i == 4 and stop_before_tail:
+                return t
             xcur = self._run(p + ".conv2", t, N, H, H, out=buf(f"d{i}", H, c_out))
             if keep is not None:
                 keep[f"d{i}"] = xcur
@@ -286,7 +305,9 @@ class UnetEngine:
     def forward(self, x: torch.Tensor, *, want_logits_nchw: bool = False, want_logits_nhwc: bool = False,
                 want_mask: bool = False, mask_out: Optional[torch.Tensor] = None,
                 logits_nhwc_out: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
-        d = self.forward_features(x)
+        fused = type(self)._decode is UnetEngine._decode and self.tail_fusable(x.shape[1] - 6 if x.shape[2] == x.shape[1] + 2
+                                                                                   else x.shape[1])
+        d = self.forward_features(x, stop_before_tail=fused)
         N, T = d.shape[0], d.shape[1]
         out: Dict[str, torch.Tensor] = {}
         if want_logits_nchw:
@@ -297,7 +318,12 @@ class UnetEngine:
         if want_mask or mask_out is not None:
             out["mask"] = mask_out if mask_out is not None else torch.empty((N, T, T), dtype=torch.uint8,
                                                                             device=self.device)
-        if self.head_w_tc is not None:
+        if fused:
+            L = self.layers[self.TAIL_LAYER]
+            ops.tail_fused(d, L.w, L.scale, L.shift, self.head_w_tc, self.head_b16, self.classes,
+                           logits_nchw=out.get("logits_nchw"), logits_nhwc=out.get("logits_nhwc"), mask=out.get("mask"),
+                           tag="tail(dec4.conv2+head)")
+        elif self.head_w_tc is not None:
             ops.head_tc(d, self.head_w_tc, self.head_b16, self.classes, logits_nchw=out.get("logits_nchw"),
                         logits_nhwc=out.get("logits_nhwc"), mask=out.get("mask"))
         else:
@@ -342,7 +368,7 @@ class UnetPlusPlusEngine(UnetEngine):
         self._conv(sd, p + ".conv2", p + ".conv2.0", p + ".conv2.1", 1, 1, True)
         self.pp_blocks.append(name)
 
-    def _decode(self, f, N, T, buf, keep):
+    def _decode(self, f, N, T, buf, keep, stop_before_tail=False):
         feats = [f[5], f[4], f[3], f[2], f[1]]             # head of the encoder first (decoder.py:158-159)
         dense = {}
 

@@ -195,6 +195,16 @@ def conv2d(x: torch.Tensor, w: torch.Tensor, scale: torch.Tensor, shift: torch.T
     return out
 
 
+def stem_pool(x: torch.Tensor, w: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, *, N: int, H: int, W: int,
+              out: torch.Tensor, pooled: torch.Tensor, algo_cin: int = 4, tag: str = "stem+pool") -> None:
+    """7x7/s2 stem (BN + ReLU) and the 3x3/s2 max pooling behind it in one launch (conv_stem.cu, POOL variant); x is the
+    zero-bordered bf16 frame (N, H+6, W+8, 4), W / 2 must be 128.  Bit-identical to ``conv2d`` + :func:`maxpool3x3s2`."""
+    d = ConvDesc(N, H, W, 4, 4, 0, 64, 7, 7, 2, 3, 1, 0, _dt(x), _lib.CONV_X_PAD3)
+    with _Timed("conv", 2.0 * N * (H // 2) * (W // 2) * 64 * algo_cin * 49, tag):
+        check(load().dt_stem_pool_fwd(C.byref(d), x.data_ptr(), w.data_ptr(), scale.data_ptr(), shift.data_ptr(),
+                                      out.data_ptr(), pooled.data_ptr(), stream_ptr()))
+
+
 def maxpool3x3s2(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     N, H, W, Cc = x.shape
     if out is None:
@@ -218,6 +228,21 @@ def head_tc(x: torch.Tensor, w_packed: torch.Tensor, bias16: torch.Tensor, K: in
     N, H, W, Cc = x.shape
     check(load().dt_head_fwd_tc(x.data_ptr(), N, H, W, K, w_packed.data_ptr(), bias16.data_ptr(), ptr(logits_nchw),
                                 ptr(logits_nhwc), ptr(mask), stream_ptr()))
+
+
+def tail_fused(x: torch.Tensor, w2_packed: torch.Tensor, scale2: torch.Tensor, shift2: torch.Tensor, wh_packed: torch.Tensor,
+               bias16: torch.Tensor, K: int, *, logits_nchw: Optional[torch.Tensor] = None,
+               logits_nhwc: Optional[torch.Tensor] = None, mask: Optional[torch.Tensor] = None,
+               tag: str = "tail") -> None:
+    """decoder.blocks.4.conv2 (16 -> 16, BN + ReLU) + segmentation head in one launch (conv_tail.cu); x = the output of
+    decoder.blocks.4.conv1, bf16 NHWC, width 128 or 256.  Bit-identical to ``conv2d`` followed by :func:`head_tc`."""
+    N, H, W, Cc = x.shape
+    if Cc != 16 or x.dtype != torch.bfloat16:
+        raise ValueError("tail_fused: x must be bf16 NHWC with 16 channels")
+    with _Timed("conv", 2.0 * N * H * W * 16 * 9 * (16 + K), tag):
+        check(load().dt_tail_fused(x.data_ptr(), N, H, W, K, w2_packed.data_ptr(), scale2.data_ptr(), shift2.data_ptr(),
+                                   wh_packed.data_ptr(), bias16.data_ptr(), ptr(logits_nchw), ptr(logits_nhwc), ptr(mask),
+                                   stream_ptr()))
 
 
 def argmax_nchw(logits: torch.Tensor) -> torch.Tensor:

@@ -152,6 +152,14 @@ int dt_conv2d_fwd(const dt_conv_desc* desc, const void* x, const void* skip, con
 /* K3: maxpool 3x3 stride 2 pad 1 (torchvision resnet `maxpool`), NHWC, dtype as above. */
 int dt_maxpool3x3s2(const void* x, int N, int H, int W, int C, int dtype, void* y, dt_stream_t stream);
 
+/* Stem + maxpool in one launch (bf16 path, zero-bordered input frame, DT_CONV_X_PAD3): y = ReLU(BN(conv7x7/s2(x))) =
+ * `encoder.conv1/bn1/relu` and pooled = `encoder.maxpool(y)` of smp's ResNetEncoder.forward (the first two stages of
+ * segmodel.py:214 `self.model(x)`); the pooling reads the stem rows from shared memory instead of HBM.  d as for
+ * dt_conv2d_fwd.  Returns DT_ERR_UNSUPPORTED unless W/2 == 128 and H/2 % 8 == 0: call dt_conv2d_fwd + dt_maxpool3x3s2 then.
+ * Both outputs are bit-identical to those two calls. */
+int dt_stem_pool_fwd(const dt_conv_desc* d, const void* x, const void* w, const float* scale, const float* shift, void* y,
+                     void* pooled, dt_stream_t stream);
+
 /* ---- K9-K11: segmentation head -------------------------------------------------------------------
  * smp SegmentationHead conv 3x3 (C -> K, bias) fused with the consumers of the logits:
  *   logits_nchw (N, K, H, W) fp32   — what `self.model(img)` returns (segmodel.py:214)
@@ -165,6 +173,16 @@ int dt_head_fwd(const void* x, int x_dtype, int N, int H, int W, int C, int K, c
  * row k < K = class k in the dt_conv2d_fwd packing (k = tap*16 + c), rows >= K zero; bias16 = float[16]. */
 int dt_head_fwd_tc(const void* x, int N, int H, int W, int K, const void* w_packed, const float* bias16,
                    float* logits_nchw, void* logits_nhwc, uint8_t* mask, dt_stream_t stream);
+
+/* Decoder tail in one launch (bf16 path): decoder.blocks.4.conv2 (3x3, 16 -> 16, folded BatchNorm + ReLU; smp
+ * DecoderBlock.conv2, the last Conv2dReLU before `segmentation_head`, segmodel.py:214 via smp.Unet.forward) followed by the
+ * head above; the 16-channel intermediate stays in shared memory.  x: bf16 NHWC (N, H, W, 16) = the output of
+ * decoder.blocks.4.conv1; w2_packed / wh_packed: bf16 [16][192] in the dt_conv2d_fwd packing; scale2 / shift2: float[16].
+ * W must be 128 or 256 (DT_ERR_UNSUPPORTED otherwise: call dt_conv2d_fwd + dt_head_fwd_tc).  Outputs as dt_head_fwd, bit-
+ * identical to the two-launch path. */
+int dt_tail_fused(const void* x, int N, int H, int W, int K, const void* w2_packed, const float* scale2, const float* shift2,
+                  const void* wh_packed, const float* bias16, float* logits_nchw, void* logits_nhwc, uint8_t* mask,
+                  dt_stream_t stream);
 
 /* argmax over the class dim of NCHW fp32 logits -> uint8 (first max wins) */
 int dt_argmax_nchw(const float* logits, int N, int K, int H, int W, uint8_t* mask, dt_stream_t stream);

@@ -255,6 +255,44 @@ def test_stem_tma_im2col_padded_input(N, T):
     assert torch.equal(y_t, y_m)
 
 
+@pytest.mark.parametrize("N", [1, 3, 40])
+def test_stem_pool_fused_equals_stem_then_maxpool(N):
+    """conv_stem.cu POOL variant: the max pooling is taken from the staged stem rows in shared memory; both outputs must be
+    bit-identical to dt_conv2d_fwd + dt_maxpool3x3s2 (N = 40: several items per CTA, ring reuse across items)."""
+    T = 256
+    g = torch.Generator().manual_seed(60 + N)
+    xpad = torch.zeros(N, T + 6, T + 8, 4)
+    xpad[:, 3:3 + T, 3:3 + T, :3] = torch.randn(N, T, T, 3, generator=g)
+    w = torch.randn(64, 3, 7, 7, generator=g) * (2.0 / 147) ** 0.5
+    scale, shift = (1.0 + 0.1 * torch.randn(64, generator=g)).cuda(), (0.1 * torch.randn(64, generator=g) - 0.05).cuda()
+    wp = pack_weight(w, "bf16", True, "cuda")
+    xd = xpad.to(torch.bfloat16).cuda()
+    y_ref = ops.conv2d(xd, wp, scale, shift, N=N, H=T, W=T, C_in=4, C_x=4, C_out=64, R=7, S=7, stride=2, pad=3, relu=True,
+                       flags=CONV_X_PAD3)
+    p_ref = ops.maxpool3x3s2(y_ref)
+    y = torch.full_like(y_ref, float("nan"))
+    pooled = torch.full_like(p_ref, float("nan"))
+    ops.stem_pool(xd, wp, scale, shift, N=N, H=T, W=T, out=y, pooled=pooled)
+    torch.cuda.synchronize()
+    assert torch.equal(y.view(torch.int16), y_ref.view(torch.int16))
+    bad = (pooled.view(torch.int16) != p_ref.view(torch.int16))
+    if bad.any():
+        idx = bad.nonzero()[0].tolist()
+        print(f"pooled differs at {int(bad.sum())} of {bad.numel()} elements, first {idx}")
+    assert not bad.any()
+    ref = F.max_pool2d(y_ref.float().permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1)
+    assert torch.equal(pooled.float(), ref)
+
+
+def test_stem_pool_fused_rejects_other_widths():
+    xd = torch.zeros(1, 128 + 6, 128 + 8, 4, dtype=torch.bfloat16, device="cuda")
+    wp = pack_weight(torch.zeros(64, 3, 7, 7), "bf16", True, "cuda")
+    z = torch.zeros(64, device="cuda")
+    with pytest.raises(RuntimeError):
+        ops.stem_pool(xd, wp, z, z, N=1, H=128, W=128, out=torch.empty(1, 64, 64, 64, dtype=torch.bfloat16, device="cuda"),
+                      pooled=torch.empty(1, 32, 32, 64, dtype=torch.bfloat16, device="cuda"))
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_maxpool(dtype):
     g = torch.Generator().manual_seed(4)

@@ -100,3 +100,57 @@ def test_head_row_equals_head_tile_kernel(N, H, W, K):
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][2], outs[1][2])
     assert torch.equal(outs[0][1].view(torch.int16), outs[1][1].view(torch.int16))
     assert torch.equal(outs[0][2].cpu().long(), outs[0][0].argmax(1).cpu())
+
+
+@pytest.mark.parametrize("N,H,W,K", [(2, 256, 256, 3), (1, 256, 256, 2), (3, 128, 128, 4), (1, 40, 128, 1), (11, 256, 256, 3),
+                                     (1, 8, 256, 3), (2, 33, 128, 3)])
+def test_fused_tail_equals_conv2_then_head(N, H, W, K):
+    """conv_tail.cu (decoder.blocks.4.conv2 + head in one launch, intermediate rows in shared memory) must be bit-identical
+    to the two launches it replaces: same bf16 rounding of the intermediate, same accumulation order."""
+    g = torch.Generator().manual_seed(7 * N + H + K)
+    x = torch.randn(N, H, W, 16, generator=g).to(torch.bfloat16).cuda()
+    w2 = torch.randn(16, 16, 3, 3, generator=g) * (2.0 / 144) ** 0.5
+    scale = (1.0 + 0.1 * torch.randn(16, generator=g)).cuda()
+    shift = (0.1 * torch.randn(16, generator=g)).cuda()
+    hw = torch.zeros(16, 16, 3, 3)
+    hw[:K] = torch.randn(K, 16, 3, 3, generator=g) * 0.1
+    w2p, whp = pack_weight(w2, "bf16", False, "cuda"), pack_weight(hw, "bf16", False, "cuda")
+    b16 = torch.zeros(16)
+    b16[:K] = torch.randn(K, generator=g)
+    b16 = b16.cuda()
+
+    def outputs():
+        return (torch.full((N, K, H, W), float("nan"), dtype=torch.float32, device="cuda"),
+                torch.zeros(N, H, W, K, dtype=torch.bfloat16, device="cuda"),
+                torch.full((N, H, W), 255, dtype=torch.uint8, device="cuda"))
+
+    mid = run(x, w2, scale, shift, None, True, 0)
+    a = outputs()
+    ops.head_tc(mid, whp, b16, K, logits_nchw=a[0], logits_nhwc=a[1], mask=a[2])
+    b = outputs()
+    ops.tail_fused(x, w2p, scale, shift, whp, b16, K, logits_nchw=b[0], logits_nhwc=b[1], mask=b[2])
+    torch.cuda.synchronize()
+    d = (a[0] - b[0]).abs()
+    if not torch.equal(a[0], b[0]):
+        print(f"fused tail differs: max {d.max().item():.4e}, {int((d > 0).sum() + torch.isnan(d).sum())} of {d.numel()}")
+    assert torch.equal(a[0], b[0])
+    assert torch.equal(a[1].view(torch.int16), b[1].view(torch.int16))
+    assert torch.equal(a[2], b[2])
+    # only some outputs requested
+    c = outputs()
+    ops.tail_fused(x, w2p, scale, shift, whp, b16, K, mask=c[2])
+    torch.cuda.synchronize()
+    assert torch.equal(a[2], c[2])
+    ref_mid = torch.relu(F.conv2d(x.float().permute(0, 3, 1, 2).cpu(), w2.to(torch.bfloat16).float(), None, 1, 1)
+                         * scale.cpu().view(1, -1, 1, 1) + shift.cpu().view(1, -1, 1, 1)).to(torch.bfloat16).float()
+    ref = F.conv2d(ref_mid, hw[:K].to(torch.bfloat16).float(), b16[:K].cpu(), 1, 1)
+    err, rel = report(f"fused tail N={N} {H}x{W} K={K}", b[0].cpu(), ref)
+    assert rel < 2e-2
+
+
+def test_fused_tail_rejects_other_widths():
+    x = torch.zeros(1, 64, 64, 16, dtype=torch.bfloat16, device="cuda")
+    w = pack_weight(torch.zeros(16, 16, 3, 3), "bf16", False, "cuda")
+    z = torch.zeros(16, device="cuda")
+    with pytest.raises(RuntimeError):
+        ops.tail_fused(x, w, z, z, w, z, 3, mask=torch.zeros(1, 64, 64, dtype=torch.uint8, device="cuda"))
