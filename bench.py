@@ -59,6 +59,10 @@ def parse():
                     help="infer workload: skip the cfg5 (1024x1024 tiles, batch 32 per GPU) and cfg4 (training step) "
                          "measurements that the default run appends to the JSON line as `cfg5` / `cfg4`")
     ap.add_argument("--extra-steps", type=int, default=20, help="timed steps of the appended cfg4 / cfg5 measurements")
+    ap.add_argument("--e2e-batches", default=None,
+                    help="N > 1: batch sizes of the end-to-end shard pipeline, comma separated (the last one repeats)")
+    ap.add_argument("--e2e-sweep", default=None,
+                    help="N > 1 experiment: ';'-separated batch plans, each timed end to end and reported on stderr")
     return ap.parse_args()
 
 
@@ -264,8 +268,13 @@ def main_b200(a):
     r0, r1 = plan.R0, plan.R1
     my_tiles = plan.t1 - plan.t0
     mi = MosaicInference(engine, tile=T, overlap=ov, batch_tiles=a.batch_tiles)
-    # end to end the mosaic rows of a batch are uploaded behind the previous batch: keep at least three batches per shard
-    bt_e2e = min(a.batch_tiles, max(gx, -(-my_tiles // 3)))
+    # end to end the mosaic rows of a batch are uploaded behind the previous batch.  The first upload cannot be hidden, so
+    # the pipeline (deployment/inference.py batch_plan) starts with ONE tile row and sends the rest in equal batches of
+    # at most batch_tiles, which keeps the deep layers' grids full (measured at N = 8, ms per step: [45, 209] 6.30,
+    # one batch 6.38, three equal batches 7.41)
+    bt_e2e = None
+    if a.e2e_batches:
+        bt_e2e = [int(v) for v in a.e2e_batches.split(",")]
     mosaic = synthetic_mosaic(a.size, dev)
     host_mosaic = torch.empty(mosaic.shape, dtype=torch.uint8, pin_memory=True)
     host_mosaic.copy_(mosaic)
@@ -335,6 +344,16 @@ def main_b200(a):
     h2d, d2h = step_e2e()
     torch.cuda.synchronize()
     ms_e2e = ms_e2e_total / a.steps
+    if a.e2e_sweep and world > 1:
+        keep = bt_e2e
+        for spec in a.e2e_sweep.split(";"):
+            bt_e2e = [int(v) for v in spec.split(",")]
+            for _ in range(2):
+                step_e2e()
+            ms_sw, _, _ = timed(step_e2e, a.steps)
+            if rank == 0:
+                print(f"[e2e sweep] batches {spec}: {ms_sw / a.steps:.3f} ms/step", file=sys.stderr, flush=True)
+        bt_e2e = keep
 
     pk = peaks()
     out = {

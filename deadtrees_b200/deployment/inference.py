@@ -121,6 +121,33 @@ def blend_window(T: int, overlap: int, device) -> torch.Tensor:
     return torch.from_numpy(w.astype(np.float32)).to(device)
 
 
+def batch_plan(first_tile: int, n_tiles: int, batch_tiles, lead: int = 0):
+    """[(t0, n), ...] covering ``n_tiles`` tiles from ``first_tile``.  ``batch_tiles``: an upper bound (the batches are then
+    EQUAL - a short last batch leaves the deep layers' grids mostly empty) or an explicit sequence of sizes (the last one
+    repeats).  ``lead`` > 0 puts a short batch of that many tiles first: with host buffers its upload is the only one
+    nothing hides."""
+    if isinstance(batch_tiles, (list, tuple)):
+        sizes = [int(v) for v in batch_tiles]
+        if not sizes or min(sizes) < 1:
+            raise ValueError("batch sizes must be positive")
+    else:
+        if int(batch_tiles) < 1:
+            raise ValueError("batch_tiles must be positive")
+        sizes = []
+        rest = n_tiles
+        if 0 < lead < n_tiles:
+            sizes.append(lead)
+            rest -= lead
+        nb = max(1, -(-rest // int(batch_tiles)))
+        sizes.append(max(1, -(-rest // nb)))
+    plan, t, end = [], first_tile, first_tile + n_tiles
+    while t < end:
+        n = min(sizes[min(len(plan), len(sizes) - 1)], end - t)
+        plan.append((t, n))
+        t += n
+    return plan
+
+
 class MosaicInference:
     """Sliding-window segmentation of a whole uint8 mosaic on one GPU (or one tile-row shard of it)."""
 
@@ -171,7 +198,9 @@ class MosaicInference:
         r0, r1 = (0, gy) if tile_rows is None else tile_rows
         mask = out if out is not None else self._buf("mask", (H, W), torch.uint8)
         ntiles = (r1 - r0) * gx
-        bt = min(self.batch_tiles, max(ntiles, 1))
+        # equal batches; with a host source a first batch of one tile row (the only upload nothing hides)
+        batches = batch_plan(r0 * gx, ntiles, self.batch_tiles, lead=gx if host_src is not None else 0)
+        bt = max([n for _, n in batches] + [1])
         pad = 3 if eng.stem_padded(T) else 0
         x = self._bufs.get(("x", bt, T))
         if x is None:
@@ -205,8 +234,7 @@ class MosaicInference:
         y_own0, y_own1 = self.owned_rows(H, T, ov, gy, r0, r1)
         copied = min(H, r0 * step)                # mosaic rows [r0 * step, copied) are on the device
         stitched = y_own0                         # mask rows [y_own0, stitched) are final
-        for t0 in range(r0 * gx, r1 * gx, bt):
-            n = min(bt, r1 * gx - t0)
+        for t0, n in batches:
             xb = x[:n]
             if piped_in:
                 need = min(H, ((t0 + n - 1) // gx) * step + T)
@@ -247,19 +275,23 @@ class MosaicInference:
         return mask
 
     def run_shard(self, mosaic: torch.Tensor, plan, out: torch.Tensor, exchange=None, host_src: Optional[torch.Tensor] = None,
-                  host_out: Optional[torch.Tensor] = None, batch_tiles: Optional[int] = None) -> torch.Tensor:
+                  host_out: Optional[torch.Tensor] = None, batch_tiles=None) -> torch.Tensor:
         """one rank of a multi-GPU run over tile-RANGE shards (``deadtrees_b200.sharding.ShardPlan``): the tiles
         ``[plan.t0, plan.t1)`` go through the network in batches, ``exchange(logits)`` swaps the few boundary tiles /
         strips with the two neighbours (``sharding.exchange_logits``), and the mask rows ``plan.mask_rows(H, T)`` are
         stitched into ``out``.  "hwc" mosaics; ``host_src`` / ``host_out`` as in :meth:`run` (row bands of the mosaic are
-        uploaded behind the batches; the shard's mask rows go back after the stitch)."""
+        uploaded behind the batches; the shard's mask rows go back after the stitch).  ``batch_tiles``: one size, or a
+        sequence of batch sizes (the last one repeats) - with host buffers a short first batch shortens the upload nothing
+        can hide, and large later batches keep the deep layers' grids full."""
         H, W = mosaic.shape[0], mosaic.shape[1]
         T, ov, eng = self.tile, self.overlap, self.engine
         gy, gx = overlap_grid(H, W, T, ov)
         if (gy, gx, ov) != (plan.gy, plan.gx, plan.overlap):
             raise ValueError("shard plan does not belong to this mosaic / tiling")
         step = T - ov
-        bt = min(batch_tiles or self.batch_tiles, max(plan.t1 - plan.t0, 1))
+        starts = batch_plan(plan.t0, plan.t1 - plan.t0, batch_tiles or self.batch_tiles,
+                            lead=gx if host_src is not None and not isinstance(batch_tiles, (list, tuple)) else 0)
+        bt = max([n for _, n in starts] + [1])
         pad = 3 if eng.stem_padded(T) else 0
         x = self._bufs.get(("x", bt, T))
         if x is None:
@@ -289,8 +321,7 @@ class MosaicInference:
         first_end = min(y1, (plan.R0 + 1) * step) if plan.ty_base < plan.R0 else y0       # rows that need the halo strips
         stitched = first_end
         last_row = plan.R1 - 1 if plan.recv_tail is not None else plan.R1                 # tile rows complete without the tail
-        for t0 in range(plan.t0, plan.t1, bt):
-            n = min(bt, plan.t1 - t0)
+        for t0, n in starts:
             if host_src is not None:
                 need = min(H, ((t0 + n - 1) // gx) * step + T)
                 if need > copied:

@@ -396,3 +396,26 @@ def test_shard_exchange_gloo(world):
     to rank 0 (gloo; NCCL over NVLink on the GPUs)."""
     port = 31500 + (os.getpid() % 2000) + world
     mp.spawn(_shard_exchange_worker, args=(world, port), nprocs=world, join=True)
+
+
+def test_batch_plan_equal_batches_and_lead():
+    """deployment/inference.py batch_plan: equal batches under the bound, optional short first batch, explicit sizes"""
+    from deadtrees_b200.deployment.inference import batch_plan
+    assert batch_plan(0, 2025, 405) == [(i * 405, 405) for i in range(5)]
+    p = batch_plan(10, 506, 405)                         # 506 tiles: two batches of 253, not 405 + 101
+    assert p == [(10, 253), (263, 253)]
+    p = batch_plan(0, 254, 405, lead=45)
+    assert p == [(0, 45), (45, 209)]
+    p = batch_plan(0, 1012, 405, lead=45)                # 967 left: three batches of 323 / 323 / 321
+    assert [n for _, n in p] == [45, 323, 323, 321] and p[-1][0] + p[-1][1] == 1012
+    assert batch_plan(0, 30, 405, lead=45) == [(0, 30)]  # shard smaller than the lead batch
+    assert batch_plan(5, 100, [10, 40]) == [(5, 10), (15, 40), (55, 40), (95, 10)]
+    assert batch_plan(0, 0, 8) == []
+    for bad in (0, [], [4, 0]):
+        with pytest.raises(ValueError):
+            batch_plan(0, 10, bad)
+    for total in (1, 44, 45, 46, 253, 2025, 7777):
+        for lead in (0, 45):
+            p = batch_plan(3, total, 405, lead=lead)
+            assert p[0][0] == 3 and sum(n for _, n in p) == total
+            assert all(a[0] + a[1] == b[0] for a, b in zip(p, p[1:])) and max(n for _, n in p) <= 405
