@@ -59,6 +59,8 @@ def parse():
                     help="infer workload: skip the cfg5 (1024x1024 tiles, batch 32 per GPU) and cfg4 (training step) "
                          "measurements that the default run appends to the JSON line as `cfg5` / `cfg4`")
     ap.add_argument("--extra-steps", type=int, default=20, help="timed steps of the appended cfg4 / cfg5 measurements")
+    ap.add_argument("--e2e-no-overlap", action="store_true",
+                    help="end to end: every mosaic is a closed job (no overlap of successive mosaics' copies with compute)")
     ap.add_argument("--e2e-batches", default=None,
                     help="N > 1: batch sizes of the end-to-end shard pipeline, comma separated (the last one repeats)")
     ap.add_argument("--e2e-sweep", default=None,
@@ -295,13 +297,19 @@ def main_b200(a):
         if world == 1:
             # MosaicInference's host pipeline: row bands go up on a copy stream while earlier batches compute, finished
             # mask bands come back behind the compute
-            mi.run(mosaic, "hwc", out=mask, host_src=host_mosaic, host_out=host_mask)
+            mi.run(mosaic, "hwc", out=mask, host_src=host_mosaic, host_out=host_mask, pipelined=pipelined)
             return H * W * 3, H * W
-        mi.run_shard(mosaic, plan, mask, exchange=exchange, host_src=host_mosaic, host_out=host_mask, batch_tiles=bt_e2e)
+        mi.run_shard(mosaic, plan, mask, exchange=exchange, host_src=host_mosaic, host_out=host_mask, batch_tiles=bt_e2e,
+                     pipelined=pipelined)
         ya, yb = plan.input_rows(H, T)
         return (yb - ya) * W * 3, (y1 - y0) * W
 
-    def timed(fn, steps, profile=False):
+    # back-to-back mosaics overlap like a production loop over files (scripts/inference.py --pipeline): the next mosaic's rows go
+    # up as soon as the current one's last gather has read the staging buffer, the last mask band comes back behind the next
+    # mosaic's first batch; mi.finish() joins the copy streams INSIDE the timed region
+    pipelined = not a.e2e_no_overlap
+
+    def timed(fn, steps, profile=False, after=None):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -311,6 +319,8 @@ def main_b200(a):
         e0.record()
         for _ in range(steps):
             fn()
+        if after is not None:
+            after()
         e1.record()
         torch.cuda.synchronize()
         if world > 1:
@@ -338,10 +348,19 @@ def main_b200(a):
         ms_prof_total, _, prof = timed(step_device, a.steps, profile=True)
 
     # end-to-end through the public pipeline with host buffers (pinned), same number of steps
+    ms_closed = None
+    if pipelined:            # the same pipeline with every mosaic a closed job (nothing of step k+1 starts before step k's mask is back)
+        pipelined = False
+        for _ in range(2):
+            step_e2e()
+        ms_closed = timed(step_e2e, a.steps)[0] / a.steps
+        pipelined = True
     for _ in range(2):
         step_e2e()
-    ms_e2e_total, _, _ = timed(step_e2e, a.steps)
+    mi.finish()
+    ms_e2e_total, _, _ = timed(step_e2e, a.steps, after=mi.finish)
     h2d, d2h = step_e2e()
+    mi.finish()
     torch.cuda.synchronize()
     ms_e2e = ms_e2e_total / a.steps
     if a.e2e_sweep and world > 1:
@@ -350,7 +369,8 @@ def main_b200(a):
             bt_e2e = [int(v) for v in spec.split(",")]
             for _ in range(2):
                 step_e2e()
-            ms_sw, _, _ = timed(step_e2e, a.steps)
+            mi.finish()
+            ms_sw, _, _ = timed(step_e2e, a.steps, after=mi.finish)
             if rank == 0:
                 print(f"[e2e sweep] batches {spec}: {ms_sw / a.steps:.3f} ms/step", file=sys.stderr, flush=True)
         bt_e2e = keep
@@ -363,7 +383,12 @@ def main_b200(a):
         "config": workload_config(a, n_tiles),
         "mpixel_per_s": value * T * T / 1e6, "mosaic_mpixel_per_s": H * W / 1e6 / (ms_step / 1e3),
         "e2e": {"value": n_tiles / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-                "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e},
+                "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e,
+                "pipeline": ("successive mosaics overlap (next upload behind the current mosaic's last batch, last mask band "
+                             "behind the next mosaic's first batch); all copies and MosaicInference.finish() inside the timed "
+                             "region" if pipelined else "every mosaic a closed job"),
+                "closed_job": (None if ms_closed is None else
+                               {"value": n_tiles / (ms_closed / 1e3), "unit": UNIT, "ms_per_step": ms_closed})},
         "gpu_launches": int(launches), "clocks": clocks,
     }
     if prof:
@@ -575,7 +600,12 @@ def train_measure(a, ctx, steps: int, warmup: int, with_profile: bool, with_cpu:
         torch.cuda.current_stream().synchronize()
         return float(loss_h)
 
-    def timed(fn, steps, profile=False):
+    # back-to-back mosaics overlap like a production loop over files (scripts/inference.py --pipeline): the next mosaic's rows go
+    # up as soon as the current one's last gather has read the staging buffer, the last mask band comes back behind the next
+    # mosaic's first batch; mi.finish() joins the copy streams INSIDE the timed region
+    pipelined = not a.e2e_no_overlap
+
+    def timed(fn, steps, profile=False, after=None):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -585,6 +615,8 @@ def train_measure(a, ctx, steps: int, warmup: int, with_profile: bool, with_cpu:
         e0.record()
         for _ in range(steps):
             fn()
+        if after is not None:
+            after()
         e1.record()
         torch.cuda.synchronize()
         if world > 1:
@@ -658,7 +690,9 @@ def train_measure(a, ctx, steps: int, warmup: int, with_profile: bool, with_cpu:
             for e0, e1, wk, tag in conv + prof.get("wgrad", []):
                 d = per.setdefault(tag, [0.0, 0.0, 0])
                 d[0] += e0.elapsed_time(e1); d[1] += wk; d[2] += 1
-            with open(a.layer_table, "w") as fh:
+            # appended to the default invocation (cfg4 behind cfg2) the training table gets its own file
+            path = a.layer_table if a.workload == "train" else a.layer_table + ".train"
+            with open(path, "w") as fh:
                 fh.write(f"{'op.layer':58s} {'launches':>8s} {'avg_us':>9s} {'TFLOP/s':>9s} {'share%':>7s}\n")
                 for tag, (ms, wk, n) in per.items():
                     fh.write(f"{tag:58s} {n:8d} {1e3 * ms / n:9.1f} {wk / (ms / 1e3) / 1e12:9.1f} {100 * (ms / psteps) / ms_step:7.2f}\n")

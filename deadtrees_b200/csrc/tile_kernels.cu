@@ -483,43 +483,67 @@ __device__ __forceinline__ void store_mask8(uint8_t* __restrict__ mask, int y, i
   }
 }
 
-// Thread blocks are (256 / cb) rows x cb column groups, cb a power of two chosen by the host to fit the row length.
-template <int K>
-__global__ void __launch_bounds__(256)
-stitch_single_kernel(const __nv_bfloat16* __restrict__ logits, int T, int step, FastDiv fd, int gy, int gx, int ty_base,
-                     uint8_t* __restrict__ mask, int W, int row0, int nrows, int cb_shift) {
-  const int r = blockIdx.y * (256 >> cb_shift) + (threadIdx.x >> cb_shift);
-  if (r >= nrows) return;
-  const int y = row0 + r;
-  const int ty0 = (y - T + 1 <= 0) ? 0 : fd.div(y - T + step);
-  const int ty1 = min(gy - 1, fd.div(y));
-  if (ty0 != ty1) return;                                  // a row of a horizontal overlap strip: pass 2
-  const int x0 = ((blockIdx.x << cb_shift) + (threadIdx.x & ((1 << cb_shift) - 1))) << 3;
-  if (x0 >= W) return;
-  const int tx0 = (x0 - T + 1 <= 0) ? 0 : fd.div(x0 - T + step);
-  const int tx1 = min(gx - 1, fd.div(x0));
-  if (tx0 != tx1) return;                                  // a column group of a vertical overlap strip: pass 2
-  const int ly = y - ty0 * step, lx = x0 - tx0 * step;
-  float z[8][K];
-  unpack_group<K>(reinterpret_cast<const uint4*>(
-      logits + ((static_cast<int64_t>(ty0 - ty_base) * gx + tx0) * T * T + static_cast<int64_t>(ly) * T + lx) * K), z);
-  uint32_t best[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    uint32_t b = 0;
-    float bv = z[j][0];
-#pragma unroll
-    for (int k = 1; k < K; ++k)
-      if (z[j][k] > bv) { bv = z[j][k]; b = k; }
-    best[j] = b;
-  }
-  store_mask8(mask, y, x0, W, best);
-}
-
 template <int K>
 __device__ __forceinline__ void load_raw(const __nv_bfloat16* __restrict__ p, uint4 (&raw)[K]) {
 #pragma unroll
   for (int q = 0; q < K; ++q) raw[q] = __ldg(reinterpret_cast<const uint4*>(p) + q);
+}
+
+// Thread blocks are (256 / cb) rows x cb column groups, cb a power of two chosen by the host to fit the row length.
+// Pass 1: a thread owns one 8-pixel column group in RS rows (rows_pb apart); the loads of all its rows are issued before
+// the first compare (RS x K x 16 bytes in flight per thread).
+template <int K, int RS>
+__device__ __forceinline__ void stitch_single_body(const __nv_bfloat16* __restrict__ logits, int T, int step, FastDiv fd,
+                                                   int gy, int gx, int ty_base, uint8_t* __restrict__ mask, int W, int row0,
+                                                   int nrows, int cb_shift, int bx, int by) {
+  const int rows_pb = 256 >> cb_shift;
+  const int x0 = ((bx << cb_shift) + (threadIdx.x & ((1 << cb_shift) - 1))) << 3;
+  if (x0 >= W) return;
+  const int tx0 = (x0 - T + 1 <= 0) ? 0 : fd.div(x0 - T + step);
+  const int tx1 = min(gx - 1, fd.div(x0));
+  if (tx0 != tx1) return;                                  // a column group of a vertical overlap strip: pass 2
+  const int lx = x0 - tx0 * step;
+  const int rbase = by * rows_pb * RS + (threadIdx.x >> cb_shift);
+  uint4 raw[RS][K];
+  bool ok[RS];
+#pragma unroll
+  for (int i = 0; i < RS; ++i) {
+    const int r = rbase + i * rows_pb;
+    const int y = row0 + r;
+    const int ty0 = (y - T + 1 <= 0) ? 0 : fd.div(y - T + step);
+    const int ty1 = min(gy - 1, fd.div(y));
+    ok[i] = r < nrows && ty0 == ty1;                       // else: a row of a horizontal overlap strip (pass 2)
+    if (ok[i]) {
+      const int ly = y - ty0 * step;
+      load_raw<K>(logits + ((static_cast<int64_t>(ty0 - ty_base) * gx + tx0) * T * T + static_cast<int64_t>(ly) * T + lx) * K,
+                  raw[i]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < RS; ++i) {
+    if (!ok[i]) continue;
+    uint32_t words[4 * K];
+#pragma unroll
+    for (int q = 0; q < K; ++q) {
+      words[4 * q] = raw[i][q].x; words[4 * q + 1] = raw[i][q].y; words[4 * q + 2] = raw[i][q].z; words[4 * q + 3] = raw[i][q].w;
+    }
+    uint32_t best[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      uint32_t bi = 0;
+      float bv = 0.f;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const int e = j * K + k;
+        const uint32_t word = words[e >> 1];
+        const float z = (e & 1) ? __uint_as_float(word & 0xffff0000u) : __uint_as_float(word << 16);
+        if (k == 0) bv = z;
+        else if (z > bv) { bv = z; bi = k; }
+      }
+      best[j] = bi;
+    }
+    store_mask8(mask, row0 + rbase + i * rows_pb, x0, W, best);
+  }
 }
 
 template <int K>
@@ -548,16 +572,28 @@ __device__ __forceinline__ void blend_accumulate(const uint4 (&raw)[K], float wy
 // part 0: rows = the rows of the horizontal strips (strip-major), columns = all column groups of the row;
 // part 1: rows = mosaic rows (rows of horizontal strips return), columns = the column groups of the vertical strips.
 // The covering tiles are visited in (ty, tx) order two at a time, both tiles' loads in flight together.
-template <int K>
+// One launch for both strip parts (round 2: two launches of ~18 us each, 44 % idle lanes in part 1 and 16 warps per SM left
+// the strips at 1.8 TB/s while pass 1 ran at 5.9): blocks [0, n0) are part 0 (2-D block grid, bx0 blocks per block row),
+// the rest part 1 with a LINEAR index over (row, column group) - no idle lanes -; three blocks per SM.  (Pass 1 as a
+// third role of the same launch was slower: it inherits the strips' 80 registers and loses its occupancy.)
+template <int K, int RS>
 __global__ void __launch_bounds__(256)
+stitch_single_kernel(const __nv_bfloat16* __restrict__ logits, int T, int step, FastDiv fd, int gy, int gx, int ty_base,
+                     uint8_t* __restrict__ mask, int W, int row0, int nrows, int cb_shift) {
+  stitch_single_body<K, RS>(logits, T, step, fd, gy, gx, ty_base, mask, W, row0, nrows, cb_shift, blockIdx.x, blockIdx.y);
+}
+
+template <int K>
+__global__ void __launch_bounds__(256, 3)
 stitch_strips_kernel(const __nv_bfloat16* __restrict__ logits, int T, int step, FastDiv fd, int gy, int gx, int ty_base,
                      const float* __restrict__ win, uint8_t* __restrict__ mask, int H, int W, int row0, int nrows,
-                     int part, int first_strip, int nstrip_rows, int cb_shift) {
+                     int n0, int bx0, int first_strip, int nstrip_rows, int cb_shift, int groups, FastDiv gd) {
   const int ov = T - step;
-  const int r = blockIdx.y * (256 >> cb_shift) + (threadIdx.x >> cb_shift);
-  const int c = (blockIdx.x << cb_shift) + (threadIdx.x & ((1 << cb_shift) - 1));
   int y, x0;
-  if (part == 0) {
+  if (static_cast<int>(blockIdx.x) < n0) {
+    const int by = blockIdx.x / bx0, bx = blockIdx.x - by * bx0;
+    const int r = by * (256 >> cb_shift) + (threadIdx.x >> cb_shift);
+    const int c = (bx << cb_shift) + (threadIdx.x & ((1 << cb_shift) - 1));
     if (r >= nstrip_rows) return;
     const int sq = r / ov;
     y = (first_strip + sq) * step + (r - sq * ov);          // tile row first_strip+sq overlaps the previous one here
@@ -565,12 +601,14 @@ stitch_strips_kernel(const __nv_bfloat16* __restrict__ logits, int T, int step, 
     x0 = c << 3;
     if (x0 >= W) return;
   } else {
+    const int idx = (blockIdx.x - n0) * 256 + threadIdx.x;
+    const int r = gd.div(idx);
+    const int c = idx - r * groups;
     if (r >= nrows) return;
     y = row0 + r;
     const int ty0r = (y - T + 1 <= 0) ? 0 : fd.div(y - T + step);
     if (ty0r != min(gy - 1, fd.div(y))) return;             // done by part 0
     const int ov8 = ov >> 3;
-    if (c >= (gx - 1) * ov8) return;
     const int strip = c / ov8;
     x0 = (strip + 1) * step + ((c - strip * ov8) << 3);
     if (x0 >= W) return;
@@ -643,25 +681,29 @@ void launch_stitch_two_pass(const __nv_bfloat16* lg, int T, int step, int gy, in
   fd.magic = static_cast<uint32_t>(((1ull << 32) + step - 1) / step);
   const int W8 = (W + 7) / 8, ov = T - step;
   const int sh = pick_cb_shift(W8), rows_pb = 256 >> sh;
-  stitch_single_kernel<K><<<dim3((W8 + (1 << sh) - 1) >> sh, (nrows + rows_pb - 1) / rows_pb), 256, 0, s>>>(
-      lg, T, step, fd, gy, gx, ty_base, mask, W, row0, nrows, sh);
+  const int bx0 = (W8 + (1 << sh) - 1) >> sh;
+  // pass 1 is DRAM-bound with one row per thread (5.9 TB/s; two or four rows per thread measured the same)
+  stitch_single_kernel<K, 1><<<dim3(bx0, (nrows + rows_pb - 1) / rows_pb), 256, 0, s>>>(lg, T, step, fd, gy, gx, ty_base, mask,
+                                                                                      W, row0, nrows, sh);
   if (ov == 0) return;
   // horizontal strips that intersect [row0, row0 + nrows): tile rows `first`..`last` (>= 1)
   int first = (row0 - ov + 1 <= 0) ? 1 : (row0 - ov + step) / step;          // smallest ty with ty*step + ov > row0
   if (first < 1) first = 1;
   int last = (row0 + nrows - 1) / step;
   if (last > gy - 1) last = gy - 1;
+  int n0 = 0, srows = 0;
   if (last >= first) {
-    const int srows = (last - first + 1) * ov;
-    stitch_strips_kernel<K><<<dim3((W8 + (1 << sh) - 1) >> sh, (srows + rows_pb - 1) / rows_pb), 256, 0, s>>>(
-        lg, T, step, fd, gy, gx, ty_base, win, mask, H, W, row0, nrows, 0, first, srows, sh);
+    srows = (last - first + 1) * ov;
+    n0 = bx0 * ((srows + rows_pb - 1) / rows_pb);
   }
-  if (gx > 1) {
-    const int groups = (gx - 1) * (ov / 8);
-    const int sh1 = pick_cb_shift(groups), rows1 = 256 >> sh1;
-    stitch_strips_kernel<K><<<dim3((groups + (1 << sh1) - 1) >> sh1, (nrows + rows1 - 1) / rows1), 256, 0, s>>>(
-        lg, T, step, fd, gy, gx, ty_base, win, mask, H, W, row0, nrows, 1, 0, 0, sh1);
-  }
+  const int groups = gx > 1 ? (gx - 1) * (ov / 8) : 0;
+  const int n1 = static_cast<int>((static_cast<int64_t>(nrows) * groups + 255) / 256);   // items < 2^32 / groups
+  if (n0 + n1 == 0) return;
+  FastDiv gd;
+  gd.d = groups > 0 ? groups : 1;
+  gd.magic = static_cast<uint32_t>(((1ull << 32) + gd.d - 1) / gd.d);
+  stitch_strips_kernel<K><<<n0 + n1, 256, 0, s>>>(lg, T, step, fd, gy, gx, ty_base, win, mask, H, W, row0, nrows, n0, bx0,
+                                                  first, srows, sh, gd.d, gd);
 }
 
 // (N, C_src, H, W) fp32 planes -> (N, H, W, 4) NHWC, first C channels kept (RGB slice), rest zero.

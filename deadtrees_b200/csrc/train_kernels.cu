@@ -223,54 +223,88 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ part, int nbloc
 }
 
 // a = [relu]( y * scale + shift (+ residual) )
+// The block size and the grid stride are multiples of V = C / VN, so a thread keeps ONE channel group: its coefficients
+// live in registers (round 1 re-read them through __ldg for every vector - 16 / 48 extra load instructions per 16 bytes of
+// output, which left both apply passes LSU-bound at half of the copy bandwidth) and two vectors per trip are in flight.
 template <typename T>
-__global__ void bn_apply_kernel(const T* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
-                                const T* __restrict__ residual, int relu, int64_t nvec, int C, T* __restrict__ out) {
+__global__ void __launch_bounds__(kThreads)
+bn_apply_kernel(const T* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
+                const T* __restrict__ residual, int relu, int64_t nvec, int C, T* __restrict__ out) {
   constexpr int VN = VecOf<T>::N;
   const int V = C / VN;
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < nvec;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int c0 = static_cast<int>(i % V) * VN;
-    float f[VN], r[VN];
-    load_vec<T>(y + i * VN, f);
-    if (residual) load_vec<T>(residual + i * VN, r);
+  const int c0 = (threadIdx.x % V) * VN;
+  float sc[VN], sh[VN];
+#pragma unroll
+  for (int j = 0; j < VN; ++j) { sc[j] = __ldg(scale + c0 + j); sh[j] = __ldg(shift + c0 + j); }
+  auto apply = [&](float* f, const float* r) {
 #pragma unroll
     for (int j = 0; j < VN; ++j) {
-      float t = fmaf(f[j], __ldg(scale + c0 + j), __ldg(shift + c0 + j));
+      float t = fmaf(f[j], sc[j], sh[j]);
       if (residual) t += r[j];
       f[j] = relu ? fmaxf(t, 0.f) : t;
     }
-    store_vec<T>(out + i * VN, f);
+  };
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  for (; i + stride < nvec; i += 2 * stride) {
+    float f0[VN], f1[VN], r0[VN], r1[VN];
+    load_vec<T>(y + i * VN, f0);
+    load_vec<T>(y + (i + stride) * VN, f1);
+    if (residual) { load_vec<T>(residual + i * VN, r0); load_vec<T>(residual + (i + stride) * VN, r1); }
+    apply(f0, r0);
+    apply(f1, r1);
+    store_vec<T>(out + i * VN, f0);
+    store_vec<T>(out + (i + stride) * VN, f1);
+  }
+  if (i < nvec) {
+    float f0[VN], r0[VN];
+    load_vec<T>(y + i * VN, f0);
+    if (residual) load_vec<T>(residual + i * VN, r0);
+    apply(f0, r0);
+    store_vec<T>(out + i * VN, f0);
   }
 }
 
 // gz = g * [a > 0];  gy = scale * (gz - c1 - yhat * c2);  optional second output gz (identity branch of a block)
+// (coefficients in registers - see bn_apply_kernel)
 template <typename T>
-__global__ void bn_bwd_apply_kernel(const T* __restrict__ g, const T* __restrict__ a, const T* __restrict__ y,
-                                    const float* __restrict__ mean, const float* __restrict__ invstd,
-                                    const float* __restrict__ scale, const float* __restrict__ c1,
-                                    const float* __restrict__ c2, const float* __restrict__ fshift, int64_t nvec, int C,
-                                    T* __restrict__ gy, T* __restrict__ gz_out) {
+__global__ void __launch_bounds__(kThreads, 3)
+bn_bwd_apply_kernel(const T* __restrict__ g, const T* __restrict__ a, const T* __restrict__ y,
+                    const float* __restrict__ mean, const float* __restrict__ invstd,
+                    const float* __restrict__ scale, const float* __restrict__ c1,
+                    const float* __restrict__ c2, const float* __restrict__ fshift, int64_t nvec, int C,
+                    T* __restrict__ gy, T* __restrict__ gz_out) {
   constexpr int VN = VecOf<T>::N;
   const int V = C / VN;
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < nvec;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int c0 = static_cast<int>(i % V) * VN;
-    float fg[VN], fa[VN], fy[VN], o[VN];
-    load_vec<T>(g + i * VN, fg);
-    if (a) load_vec<T>(a + i * VN, fa);
-    load_vec<T>(y + i * VN, fy);
+  const int c0 = (threadIdx.x % V) * VN;
+  const bool mask_y = a == nullptr && fshift != nullptr;
+  float sc[VN], mu[VN], is[VN], k1[VN], k2[VN], fsh[VN];
+#pragma unroll
+  for (int j = 0; j < VN; ++j) {
+    sc[j] = __ldg(scale + c0 + j); mu[j] = __ldg(mean + c0 + j); is[j] = __ldg(invstd + c0 + j);
+    k1[j] = __ldg(c1 + c0 + j); k2[j] = __ldg(c2 + c0 + j);
+    fsh[j] = mask_y ? __ldg(fshift + c0 + j) : 0.f;
+  }
+  auto apply = [&](float* fg, const float* fa, const float* fy, float* o) {
 #pragma unroll
     for (int j = 0; j < VN; ++j) {
-      const bool on = (a == nullptr && fshift != nullptr) ? fmaf(fy[j], __ldg(scale + c0 + j), __ldg(fshift + c0 + j)) > 0.f
-                                                           : (a == nullptr || fa[j] > 0.f);
+      const bool on = mask_y ? fmaf(fy[j], sc[j], fsh[j]) > 0.f : (a == nullptr || fa[j] > 0.f);
       const float gz = on ? fg[j] : 0.f;
       fg[j] = gz;
-      const float yhat = (fy[j] - __ldg(mean + c0 + j)) * __ldg(invstd + c0 + j);
-      o[j] = __ldg(scale + c0 + j) * (gz - __ldg(c1 + c0 + j) - yhat * __ldg(c2 + c0 + j));
+      const float yhat = (fy[j] - mu[j]) * is[j];
+      o[j] = sc[j] * (gz - k1[j] - yhat * k2[j]);
     }
-    store_vec<T>(gy + i * VN, o);
-    if (gz_out) store_vec<T>(gz_out + i * VN, fg);
+  };
+  // one vector per trip: with two in flight the 48 coefficient registers push the kernel past 96 registers (two blocks per SM)
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < nvec; i += stride) {
+    float g0[VN], a0[VN], y0[VN], o0[VN];
+    load_vec<T>(g + i * VN, g0);
+    if (a) load_vec<T>(a + i * VN, a0);
+    load_vec<T>(y + i * VN, y0);
+    apply(g0, a0, y0, o0);
+    store_vec<T>(gy + i * VN, o0);
+    if (gz_out) store_vec<T>(gz_out + i * VN, g0);
   }
 }
 

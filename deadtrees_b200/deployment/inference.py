@@ -178,7 +178,8 @@ class MosaicInference:
 
     def run(self, mosaic: torch.Tensor, layout: str = "hwc", tile_rows: Optional[Tuple[int, int]] = None,
             out: Optional[torch.Tensor] = None, halo_hook=None, host_src: Optional[torch.Tensor] = None,
-            host_out: Optional[torch.Tensor] = None, banded: Optional[bool] = None) -> torch.Tensor:
+            host_out: Optional[torch.Tensor] = None, banded: Optional[bool] = None,
+            pipelined: bool = False) -> torch.Tensor:
         """mosaic: CUDA uint8 (H, W, C) ["hwc"] or (C, H, W) ["chw"] -> uint8 class ids (H, W).
 
         ``tile_rows=(r0, r1)`` restricts the work to that range of tile rows (multi-GPU sharding); the
@@ -188,6 +189,11 @@ class MosaicInference:
         into ``mosaic`` on a copy stream while the previous batches compute; with ``host_out`` (pinned uint8 (H, W)) and
         no ``halo_hook`` the mask is stitched in bands as soon as their tile rows are done and each band goes back to the
         host behind the compute.  Only the first band's upload and the last band's download are exposed.
+
+        ``pipelined`` (host pipeline only): successive calls overlap like a loop over many mosaics does - ``mosaic`` and
+        ``out`` are then staging buffers that only this object touches; the next call's upload starts as soon as this call's
+        last gather has read ``mosaic``, and this call's last mask band goes to the host while the next call computes.
+        ``host_out`` is complete after :meth:`finish` (or the next ``finish``), not after this call.
 
         ``banded``: stitch the blended mask band by band behind the batches (True) or in one launch over the shard
         (False); default: bands while a batch's logits fit in L2.  A shard that starts below the first tile row blends
@@ -199,7 +205,9 @@ class MosaicInference:
         mask = out if out is not None else self._buf("mask", (H, W), torch.uint8)
         ntiles = (r1 - r0) * gx
         # equal batches; with a host source a first batch of one tile row (the only upload nothing hides)
-        batches = batch_plan(r0 * gx, ntiles, self.batch_tiles, lead=gx if host_src is not None else 0)
+        # (a pipelined call whose predecessor left its events behind has its first rows uploaded behind that call)
+        prefetched = pipelined and host_src is not None and getattr(self, "_gather_done", None) is not None
+        batches = batch_plan(r0 * gx, ntiles, self.batch_tiles, lead=gx if host_src is not None and not prefetched else 0)
         bt = max([n for _, n in batches] + [1])
         pad = 3 if eng.stem_padded(T) else 0
         x = self._bufs.get(("x", bt, T))
@@ -229,8 +237,12 @@ class MosaicInference:
             if getattr(self, "_copy_streams", None) is None:
                 self._copy_streams = (torch.cuda.Stream(device=eng.device), torch.cuda.Stream(device=eng.device))
             cs_in, cs_out = self._copy_streams    # uploads never queue behind a download that waits for compute
-            cs_in.wait_stream(main)               # earlier work on `mosaic` / `mask` is done before they are overwritten
+            if prefetched:
+                cs_in.wait_event(self._gather_done)   # the previous call's gathers have read `mosaic`
+            else:
+                cs_in.wait_stream(main)           # earlier work on `mosaic` / `mask` is done before they are overwritten
             cs_out.wait_stream(main)
+        out_done = getattr(self, "_out_done", None) if pipelined else None   # previous call's downloads still read `mask`
         y_own0, y_own1 = self.owned_rows(H, T, ov, gy, r0, r1)
         copied = min(H, r0 * step)                # mosaic rows [r0 * step, copied) are on the device
         stitched = y_own0                         # mask rows [y_own0, stitched) are final
@@ -245,8 +257,14 @@ class MosaicInference:
                     main.wait_stream(cs_in)
             ops.tile_gather_normalize(mosaic, layout, eng.in_channels, T, ov, (gy, gx), t0, n, self.offset,
                                       self.scale, out=xb, pad=pad)
+            if pipelined and piped_in and t0 + n >= r1 * gx:
+                self._gather_done = torch.cuda.Event()
+                self._gather_done.record(main)
             if ov == 0:
                 eng.forward(xb, mask_out=tmask[:n])
+                if out_done is not None:
+                    main.wait_event(out_done)
+                    out_done = None
                 ops.stitch_mask(tmask[:n], gx, t0, mask)
             else:
                 lo = t0 - (r0 - halo) * gx
@@ -256,6 +274,9 @@ class MosaicInference:
                 y_end = y_own1 if t0 + n >= r1 * gx else min(y_own1, rows_done * step)
                 if y_end > stitched:
                     if ov > 0:
+                        if out_done is not None:
+                            main.wait_event(out_done)
+                            out_done = None
                         ops.stitch_blend_argmax(logits, ov, (gy, gx), self.win, mask, row0=stitched, nrows=y_end - stitched,
                                                 ty_base=r0 - halo)
                     if piped_out:
@@ -266,31 +287,50 @@ class MosaicInference:
         if ov > 0 and not banded:
             if halo_hook is not None:
                 halo_hook(logits, gx, halo)  # multi-GPU: exchange boundary logits rows with the neighbours
+            if out_done is not None:
+                main.wait_event(out_done)
             ops.stitch_blend_argmax(logits, ov, (gy, gx), self.win, mask, row0=y_own0, nrows=y_own1 - y_own0, ty_base=r0 - halo)
         if host_out is not None and not piped_out:
             host_out[y_own0:y_own1].copy_(mask[y_own0:y_own1], non_blocking=True)
         if piped_in or piped_out:
-            main.wait_stream(cs_in)               # callers synchronise the current stream only
-            main.wait_stream(cs_out)
+            main.wait_stream(cs_in)               # (every upload was already waited for by its gather)
+            if pipelined and piped_out:
+                self._out_done = torch.cuda.Event()
+                self._out_done.record(cs_out)     # the next call's first stitch waits for this; finish() joins the stream
+            else:
+                main.wait_stream(cs_out)          # callers synchronise the current stream only
         return mask
 
+    def finish(self) -> None:
+        """join the copy streams of ``pipelined`` calls into the current stream: after this (and a synchronise of the current
+        stream) every ``host_out`` handed to an earlier call is complete, and ``mosaic`` / ``out`` may be touched again."""
+        streams = getattr(self, "_copy_streams", None)
+        if streams is not None:
+            main = torch.cuda.current_stream()
+            main.wait_stream(streams[0])
+            main.wait_stream(streams[1])
+        self._gather_done = None
+        self._out_done = None
+
     def run_shard(self, mosaic: torch.Tensor, plan, out: torch.Tensor, exchange=None, host_src: Optional[torch.Tensor] = None,
-                  host_out: Optional[torch.Tensor] = None, batch_tiles=None) -> torch.Tensor:
+                  host_out: Optional[torch.Tensor] = None, batch_tiles=None, pipelined: bool = False) -> torch.Tensor:
         """one rank of a multi-GPU run over tile-RANGE shards (``deadtrees_b200.sharding.ShardPlan``): the tiles
         ``[plan.t0, plan.t1)`` go through the network in batches, ``exchange(logits)`` swaps the few boundary tiles /
         strips with the two neighbours (``sharding.exchange_logits``), and the mask rows ``plan.mask_rows(H, T)`` are
         stitched into ``out``.  "hwc" mosaics; ``host_src`` / ``host_out`` as in :meth:`run` (row bands of the mosaic are
         uploaded behind the batches; the shard's mask rows go back after the stitch).  ``batch_tiles``: one size, or a
         sequence of batch sizes (the last one repeats) - with host buffers a short first batch shortens the upload nothing
-        can hide, and large later batches keep the deep layers' grids full."""
+        can hide, and large later batches keep the deep layers' grids full.  ``pipelined`` (with ``host_src``): as in
+        :meth:`run`, the next call's upload starts once this call's last gather has read ``mosaic`` (a staging buffer then)."""
         H, W = mosaic.shape[0], mosaic.shape[1]
         T, ov, eng = self.tile, self.overlap, self.engine
         gy, gx = overlap_grid(H, W, T, ov)
         if (gy, gx, ov) != (plan.gy, plan.gx, plan.overlap):
             raise ValueError("shard plan does not belong to this mosaic / tiling")
         step = T - ov
+        prefetched = pipelined and host_src is not None and getattr(self, "_gather_done", None) is not None
         starts = batch_plan(plan.t0, plan.t1 - plan.t0, batch_tiles or self.batch_tiles,
-                            lead=gx if host_src is not None and not isinstance(batch_tiles, (list, tuple)) else 0)
+                            lead=gx if host_src is not None and not prefetched and not isinstance(batch_tiles, (list, tuple)) else 0)
         bt = max([n for _, n in starts] + [1])
         pad = 3 if eng.stem_padded(T) else 0
         x = self._bufs.get(("x", bt, T))
@@ -302,7 +342,10 @@ class MosaicInference:
             if getattr(self, "_copy_streams", None) is None:
                 self._copy_streams = (torch.cuda.Stream(device=eng.device), torch.cuda.Stream(device=eng.device))
             cs_in = self._copy_streams[0]
-            cs_in.wait_stream(main)
+            if prefetched:
+                cs_in.wait_event(self._gather_done)
+            else:
+                cs_in.wait_stream(main)
         if ov == 0:
             tmask = self._buf("tmask", (bt, T, T), torch.uint8)
         else:
@@ -331,6 +374,9 @@ class MosaicInference:
                     main.wait_stream(cs_in)
             ops.tile_gather_normalize(mosaic, "hwc", eng.in_channels, T, ov, (gy, gx), t0, n, self.offset, self.scale,
                                       out=x[:n], pad=pad)
+            if pipelined and host_src is not None and t0 + n >= plan.t1:
+                self._gather_done = torch.cuda.Event()
+                self._gather_done.record(main)
             if ov == 0:
                 eng.forward(x[:n], mask_out=tmask[:n])
                 ops.stitch_mask(tmask[:n], gx, t0, out)       # overlap 0: a tile's pixels belong to whoever computed it

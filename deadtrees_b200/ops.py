@@ -165,9 +165,15 @@ def stitch_blend_argmax(logits: torch.Tensor, overlap: int, grid: Tuple[int, int
     _, T, _, K = logits.shape
     H, W = mosaic_mask.shape
     nrows = H - row0 if nrows is None else nrows
-    # algorithmic bytes of THIS call (the mask may be stitched band by band): K logits in + 1 B out per mosaic pixel of the
-    # rows written - a lower bound of SURVEY.md §8d's "every logit once" (pixels under an overlap read 2 or 4 tiles)
-    with _Timed("stitch", float(nrows) * W * (K * logits.element_size() + 1)):
+    # algorithmic bytes of THIS call (the mask may be stitched band by band), SURVEY.md §8d: every logit that covers a
+    # written mosaic row once (gather form: a row under a horizontal overlap reads two tile rows, each gx * T pixels wide)
+    # + 1 B of mask per pixel; summed over the bands of a mosaic this is N_tiles * T^2 * K * elem + H * W
+    step = T - overlap
+    covered = 0
+    if PROFILE is not None:
+        for ty in range(grid[0]):
+            covered += max(0, min(row0 + nrows, ty * step + T) - max(row0, ty * step))
+    with _Timed("stitch", float(covered) * grid[1] * T * K * logits.element_size() + float(nrows) * W):
         check(load().dt_stitch_blend_argmax(logits.data_ptr(), _dt(logits), K, T, overlap, grid[0], grid[1],
                                             ty_base, win.data_ptr(), mosaic_mask.data_ptr(), ptr(blended), H, W,
                                             row0, nrows, stream_ptr()))

@@ -119,6 +119,33 @@ def test_cfg2_crop_mosaic_vs_fp32_oracle(banded):
     assert torch.equal(xg[..., :3].permute(0, 3, 1, 2).cpu(), x)
 
 
+@pytest.mark.parametrize("ov", [32, 0])
+def test_pipelined_mosaics_equal_closed_jobs(ov):
+    """``MosaicInference.run(..., pipelined=True)``: successive mosaics through ONE pair of staging buffers (the next upload
+    starts behind the current mosaic's last gather, the last mask band is downloaded behind the next mosaic's first
+    batch) must give, bit for bit, the masks of the same mosaics run as closed jobs - three different mosaics, so a copy
+    that overtakes a gather or a stitch that overtakes a download shows up as a wrong band."""
+    H, W, T = 700, 930, 256
+    model = trained_model(3, 3)
+    eng = UnetEngine(model.state_dict(), 3, 3, precision="bf16")
+    mi = MosaicInference(eng, tile=T, overlap=ov, batch_tiles=4)
+    mosaics = [pattern_mosaic(H, W, 3, seed=s, oy=1000 * s, ox=777 * s) for s in (3, 4, 5)]
+    want = [mi.run(torch.from_numpy(m).cuda(), "hwc").cpu().numpy().copy() for m in mosaics]
+    assert not np.array_equal(want[0], want[1])
+    dev = torch.empty((H, W, 3), dtype=torch.uint8, device="cuda")
+    dev_mask = torch.empty((H, W), dtype=torch.uint8, device="cuda")
+    srcs = [torch.from_numpy(m).pin_memory() for m in mosaics]
+    outs = [torch.zeros((H, W), dtype=torch.uint8).pin_memory() for _ in mosaics]
+    for rep in range(2):                      # the second round starts with the events of the first one in place
+        for src, out in zip(srcs, outs):
+            mi.run(dev, "hwc", out=dev_mask, host_src=src, host_out=out, pipelined=True)
+        mi.finish()
+        torch.cuda.current_stream().synchronize()
+        for k, out in enumerate(outs):
+            assert np.array_equal(out.numpy(), want[k]), f"round {rep}, mosaic {k}"
+            out.zero_()
+
+
 def test_pytorch_inference_api_bf16(tmp_path):
     """the drop-in ``PyTorchInference`` in its DEFAULT precision (bf16 tensor-core path), rgbn data into an rgb model."""
     model = trained_model(3, 3)
