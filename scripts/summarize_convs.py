@@ -1,18 +1,18 @@
-"""per-layer table of a `ncu --set full` capture of the 46 conv launches + head of one batch
-(gpurun_out/prof_convs_raw.csv from scripts/gpu_profile2.sh) -> profiles/*.txt"""
+"""per-layer table of a `ncu --set full` capture of the 46 conv launches of one batch (stem + maxpool and the decoder tail are
+fused launches; gpurun_out/prof_convs_raw.csv from scripts/gpu_profile.sh) -> profiles/*.txt"""
 import csv
 import sys
 
-LAYERS = ["stem"]
+LAYERS = ["stem+pool"]
 for li, n in ((1, 3), (2, 4), (3, 6), (4, 3)):
     for b in range(n):
         if b == 0 and li > 1:
             LAYERS += [f"layer{li}.0.downsample", f"layer{li}.0.conv1", f"layer{li}.0.conv2"]
         else:
             LAYERS += [f"layer{li}.{b}.conv1", f"layer{li}.{b}.conv2"]
-for i in range(5):
+for i in range(4):
     LAYERS += [f"dec{i}.conv1", f"dec{i}.conv2"]
-LAYERS.append("head")
+LAYERS += ["dec4.conv1", "tail(dec4.conv2+head)"]      # 46 launches: stem + maxpool and the decoder tail are fused launches
 
 src, dst, title = sys.argv[1:4]
 tiles = int(sys.argv[4]) if len(sys.argv) > 4 else 135
