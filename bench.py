@@ -419,9 +419,14 @@ def main_b200(a):
                     f"launch; bf16 activations in + out of all convs, unfused: 44.6 MB per tile")
         hb = {}
         if tg > 0:
+            # algorithmic bytes: T^2 * C * (1 B in + 2 B out) per tile; the bytes the kernel really moves are
+            # T^2 * (3 B in + 8 B out): the stem's TMA im2col map needs 4-channel (8-byte) pixels
+            moved = wg * (3 + 8) / 9.0
             hb["gather_normalize"] = {"achieved": wg / tg / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                                      "frac": wg / tg / 1e9 / pk["hbm_gbs"], "launches": ng}
+                                      "frac": wg / tg / 1e9 / pk["hbm_gbs"], "launches": ng,
+                                      "moved_gbs": moved / tg / 1e9, "frac_moved": moved / tg / 1e9 / pk["hbm_gbs"]}
         if ts > 0:
+            # algorithmic bytes: every covering logit once + 1 B of mask per pixel (ops.stitch_blend_argmax)
             hb["stitch"] = {"achieved": ws / ts / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
                             "frac": ws / ts / 1e9 / pk["hbm_gbs"], "launches": ns}
         if world == 1 and n_tiles * (T + 6) * (T + 8) * 8 < (8 << 30):
@@ -442,7 +447,8 @@ def main_b200(a):
             gb = n_tiles * T * T * 3 * (1 + 2) / 1e9
             hb["gather_normalize_whole_mosaic"] = {"achieved": gb / (best / 1e3), "peak": pk["hbm_gbs"], "unit": "GB/s",
                                                    "frac": gb / (best / 1e3) / pk["hbm_gbs"], "launches": 1,
-                                                   "us": 1e3 * best, "bytes": gb * 1e9}
+                                                   "us": 1e3 * best, "bytes": gb * 1e9,
+                                                   "frac_moved": gb * 11.0 / 9.0 / (best / 1e3) / pk["hbm_gbs"]}
             del frame
         out["roofline_hbm"] = hb
         if a.layer_table and rank == 0:
