@@ -455,7 +455,7 @@ def main_b200(a):
             per = {}
             for e0, e1, wk, tag in prof.get("conv", []):
                 d = per.setdefault(tag, [0.0, 0.0, 0])
-                d[0] += e0.elapsed_time(e1); d[1] += wk; d[2] += 1
+                d[0] += e0.elapsed_time(e1); d[1] += wk; d[2] += 1 if wk > 0 else 0   # (helper launches of a layer carry no work)
             with open(a.layer_table, "w") as fh:
                 fh.write(f"{'layer':34s} {'launches':>8s} {'avg_us':>9s} {'TFLOP/s':>9s} {'share%':>7s}\n")
                 for tag, (ms, wk, n) in per.items():

@@ -277,6 +277,15 @@ class UnetEngine:
             keep.update({f"f{i}": f[i] for i in f})
         return self._decode(f, N, T, buf, keep, stop_before_tail)
 
+    def materialize_concat(self, name: str, H: int) -> bool:
+        """True when an up-sample + concat layer runs faster on a materialised input: bf16 tensor-core path, 16 x 16 output
+        (the halo kernels need whole 8 x 16 tiles of the LOW-RES grid), channel counts the CTA-pair kernel takes.
+        ``DT_MATERIALIZE_CONCAT=0`` keeps the virtual form."""
+        L = self.layers[name]
+        return (self.precision == "bf16" and not self.conv_flags and bool(self.pair_flag) and L.upsample and H == 16
+                and name not in self.folded and L.C_in % 64 == 0 and L.C_out % 128 == 0 and L.C_in > L.C_x
+                and os.environ.get("DT_MATERIALIZE_CONCAT", "1") != "0")
+
     TAIL_LAYER = "decoder.blocks.4.conv2"
 
     def tail_fusable(self, T: int) -> bool:
@@ -294,6 +303,22 @@ class UnetEngine:
             p = f"decoder.blocks.{i}"
             H *= 2
             c_out = self.layers[p + ".conv1"].C_out
+            if self.materialize_concat(p + ".conv1", H):
+                # 8 x 8 low-res images (256^2 tiles, first decoder block): no 8 x 16 halo tile fits, the virtual up-sample +
+                # concat would run on the per-tap gather kernel (1.0 PFLOP/s).  The concatenated tensor is small here
+                # (0.4 MB per tile): write it once and run the CTA-pair kernel on it as a plain 3 x 3 conv (1.4 PFLOP/s)
+                L = self.layers[p + ".conv1"]
+                with ops._Timed("conv", 0.0, p + ".conv1"):      # its time belongs to the layer (no FLOPs of its own)
+                    cat = ops.upsample_concat(xcur, skips[i], out=buf(f"cat{i}", H, L.C_in))
+                t = ops.conv2d(cat, L.w, L.scale, L.shift, N=N, H=H, W=H, C_in=L.C_in, C_x=L.C_in, C_out=L.C_out, R=L.R, S=L.S,
+                               stride=1, pad=L.pad, relu=L.relu, out=buf(f"dt{i}", H, c_out), flags=self.pair_flag,
+                               tag=p + ".conv1")
+                if i == 4 and stop_before_tail:
+                    return t
+                xcur = self._run(p + ".conv2", t, N, H, H, out=buf(f"d{i}", H, c_out))
+                if keep is not None:
+                    keep[f"d{i}"] = xcur
+                continue
             t = self._run(p + ".conv1", xcur, N, H, H, skip=skips[i], out=buf(f"dt{i}", H, c_out))
             if i == 4 and stop_before_tail:
                 return t

@@ -613,10 +613,11 @@ def zero_insert2x(gy: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def upsample_concat(x_low: torch.Tensor, skip: Optional[torch.Tensor]) -> torch.Tensor:
+def upsample_concat(x_low: torch.Tensor, skip: Optional[torch.Tensor], out: Optional[torch.Tensor] = None) -> torch.Tensor:
     N, Hl, Wl, Cx = x_low.shape
     Cs = 0 if skip is None else skip.shape[-1]
-    out = torch.empty((N, 2 * Hl, 2 * Wl, Cx + Cs), dtype=x_low.dtype, device=x_low.device)
+    if out is None:
+        out = torch.empty((N, 2 * Hl, 2 * Wl, Cx + Cs), dtype=x_low.dtype, device=x_low.device)
     check(load().dt_upsample_concat(x_low.data_ptr(), ptr(skip), N, 2 * Hl, 2 * Wl, Cx, Cs, _dt(x_low), out.data_ptr(),
                                     stream_ptr()))
     return out
