@@ -341,20 +341,10 @@ def main_b200(a):
     clocks = sampler.stop()
     ms_step = ms_total / a.steps
     value = n_tiles / (ms_step / 1e3)
-    # per-launch CUDA events (the roofline numbers) are taken in a separate pass so that the ~1500 event records of a
-    # step do not sit inside the headline's timed region
-    prof, ms_prof_total = None, ms_total
-    if not a.no_profile:
-        ms_prof_total, _, prof = timed(step_device, a.steps, profile=True)
-
-    # end-to-end through the public pipeline with host buffers (pinned), same number of steps
-    ms_closed = None
-    if pipelined:            # the same pipeline with every mosaic a closed job (nothing of step k+1 starts before step k's mask is back)
-        pipelined = False
-        for _ in range(2):
-            step_e2e()
-        ms_closed = timed(step_e2e, a.steps)[0] / a.steps
-        pipelined = True
+    # end-to-end through the public pipeline with host buffers (pinned), same number of steps - timed right after the
+    # device-resident steps: under the power cap the SM clock keeps sinking for seconds (scripts/exp/e2e_split.py: the same
+    # device step 34.3 ms at the start of a script and 35.0 ms three seconds later), so measurements that are compared
+    # should be neighbours in time
     for _ in range(2):
         step_e2e()
     mi.finish()
@@ -363,6 +353,18 @@ def main_b200(a):
     mi.finish()
     torch.cuda.synchronize()
     ms_e2e = ms_e2e_total / a.steps
+    ms_closed = None
+    if pipelined:            # the same pipeline with every mosaic a closed job (nothing of step k+1 starts before step k's mask is back)
+        pipelined = False
+        for _ in range(2):
+            step_e2e()
+        ms_closed = timed(step_e2e, a.steps)[0] / a.steps
+        pipelined = True
+    # per-launch CUDA events (the roofline numbers) are taken in a separate pass so that the ~1500 event records of a
+    # step do not sit inside the headline's timed region
+    prof, ms_prof_total = None, ms_total
+    if not a.no_profile:
+        ms_prof_total, _, prof = timed(step_device, a.steps, profile=True)
     if a.e2e_sweep and world > 1:
         keep = bt_e2e
         for spec in a.e2e_sweep.split(";"):
@@ -766,7 +768,7 @@ def cfg5_measure(a, ctx, engine, steps: int, warmup: int):
     host_mask = torch.empty((gy * T, gx * T), dtype=torch.uint8, pin_memory=True)
     mask = torch.zeros((gy * T, gx * T), dtype=torch.uint8, device=dev)
 
-    def timed(fn, k, profile=False):
+    def timed(fn, k, profile=False, after=None):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -776,6 +778,8 @@ def cfg5_measure(a, ctx, engine, steps: int, warmup: int):
         e0.record()
         for _ in range(k):
             fn()
+        if after is not None:
+            after()
         e1.record()
         torch.cuda.synchronize()
         if world > 1:
@@ -789,7 +793,8 @@ def cfg5_measure(a, ctx, engine, steps: int, warmup: int):
         return ms, ops.LAUNCHES - l0, prof
 
     dev_step = lambda: mi.run(block, "hwc", out=mask)
-    e2e_step = lambda: mi.run(block, "hwc", out=mask, host_src=host_block, host_out=host_mask)
+    pipelined = not a.e2e_no_overlap       # successive blocks overlap their copies with the neighbours' compute (as in cfg2)
+    e2e_step = lambda: mi.run(block, "hwc", out=mask, host_src=host_block, host_out=host_mask, pipelined=pipelined)
     for _ in range(max(warmup, 3)):
         dev_step()
     sampler = ClockSampler(local)
@@ -800,7 +805,8 @@ def cfg5_measure(a, ctx, engine, steps: int, warmup: int):
     ms_prof, _, prof = timed(dev_step, min(steps, 5), profile=True)
     for _ in range(2):
         e2e_step()
-    ms_e2e = timed(e2e_step, steps)[0] / steps
+    mi.finish()
+    ms_e2e = timed(e2e_step, steps, after=mi.finish)[0] / steps
     pk = peaks()
     evs = prof.get("conv", [])
     tc = sum(ev[0].elapsed_time(ev[1]) for ev in evs) / 1e3
@@ -812,7 +818,8 @@ def cfg5_measure(a, ctx, engine, steps: int, warmup: int):
                                   "overlap 0), batches of 16 tiles", "tile": T, "tiles_per_gpu": n, "batch_tiles": 16,
                       "l2_policy": "100 MB block and > 8 GB of activations per step; no explicit flush"},
            "e2e": {"value": world * n / (ms_e2e / 1e3), "unit": "tiles/s", "ms_per_step": ms_e2e,
-                   "h2d_bytes_per_step": int(block.numel()), "d2h_bytes_per_step": int(mask.numel())}}
+                   "h2d_bytes_per_step": int(block.numel()), "d2h_bytes_per_step": int(mask.numel()),
+                   "pipeline": "successive blocks overlap; finish() inside the timed region" if pipelined else "closed jobs"}}
     if tc > 0:
         out["roofline"] = {"bound": "tensor", "kernel": "all conv launches (tcgen05 implicit GEMM)", "achieved": wc / tc / 1e12,
                            "peak": pk["tflops"], "unit": "TFLOP/s", "frac": wc / tc / 1e12 / pk["tflops"], "traffic": None,

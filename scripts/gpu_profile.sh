@@ -14,6 +14,7 @@ timeout 300 $SMALL > gpurun_out/prof_small_plain.log 2>&1 && {
   echo "full capture exit=$?"
   ncu -i /tmp/prof_convs.ncu-rep --page raw --csv > gpurun_out/prof_convs_raw.csv 2> gpurun_out/prof_export.log
 }
+[ "${PROFILE_TRAIN:-1}" = "0" ] && { ls -la gpurun_out | grep prof_; exit 0; }
 TRAIN="python bench.py --workload train --steps 2 --warmup 3 --no-cpu-baseline --no-profile --no-graph"
 timeout 300 $TRAIN > gpurun_out/prof_train_plain.log 2>&1 && {
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 1200 -c 1400 --csv --log-file gpurun_out/prof_train_launches.csv $TRAIN > gpurun_out/prof_train_ncu.log 2>&1
