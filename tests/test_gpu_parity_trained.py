@@ -234,3 +234,14 @@ def test_tile_range_shards_equal_the_unsharded_mask(world, ov):
         torch.cuda.synchronize()
         y0, y1 = p.mask_rows(H, T)
         assert torch.equal(host_mask[y0:y1], full[y0:y1].cpu()), k
+        # pipelined calls (the next upload waits for the last gather only): a second call in flight behind the first one,
+        # through the same staging buffers, returns the same rows
+        for rep in range(2):
+            host_mask.zero_()
+            bufs[k][0].run_shard(dev_mosaic, p, part, exchange=fill, host_src=host_src, host_out=host_mask, batch_tiles=2,
+                                 pipelined=True)
+            bufs[k][0].run_shard(dev_mosaic, p, part, exchange=fill, host_src=host_src, host_out=host_mask, batch_tiles=2,
+                                 pipelined=True)
+            bufs[k][0].finish()
+            torch.cuda.synchronize()
+            assert torch.equal(host_mask[y0:y1], full[y0:y1].cpu()), (k, rep)
