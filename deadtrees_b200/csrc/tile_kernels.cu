@@ -569,6 +569,35 @@ __device__ __forceinline__ void blend_accumulate(const uint4 (&raw)[K], float wy
   }
 }
 
+// first maximum of the blended logits of 8 pixels from the un-normalised sums (see stitch_blend_v8_kernel) -> mask
+template <int K>
+__device__ __forceinline__ void blend_argmax_store(const float (&acc)[8][K], const float (&wsum)[8], uint8_t* __restrict__ mask,
+                                                   int y, int x0, int W) {
+  uint32_t best[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    int b = 0;
+    float bv = acc[j][0];
+#pragma unroll
+    for (int k = 1; k < K; ++k)
+      if (acc[j][k] > bv) { bv = acc[j][k]; b = k; }
+    bool near = false;
+#pragma unroll
+    for (int k = 0; k < K - 1; ++k)
+      near = near || (k < b && bv - acc[j][k] <= 4.76837158e-7f * fmaxf(fabsf(bv), fabsf(acc[j][k])));
+    if (near) {        // an earlier class can tie with the maximum after the division: first maximum wins
+      const float qb = __fdiv_rn(bv, wsum[j]);
+      int nb = b;
+#pragma unroll
+      for (int k = K - 2; k >= 0; --k)       // static indices: acc stays in registers
+        if (k < b && __fdiv_rn(acc[j][k], wsum[j]) == qb) nb = k;
+      b = nb;
+    }
+    best[j] = static_cast<uint32_t>(b);
+  }
+  store_mask8(mask, y, x0, W, best);
+}
+
 // part 0: rows = the rows of the horizontal strips (strip-major), columns = all column groups of the row;
 // part 1: rows = mosaic rows (rows of horizontal strips return), columns = the column groups of the vertical strips.
 // The covering tiles are visited in (ty, tx) order two at a time, both tiles' loads in flight together.
@@ -638,29 +667,88 @@ stitch_strips_kernel(const __nv_bfloat16* __restrict__ logits, int T, int step, 
     blend_accumulate<K>(raw0, __ldg(win + ly0), win + lx0, acc, wsum);
     if (two) blend_accumulate<K>(raw1, __ldg(win + ly1), win + lx1, acc, wsum);
   }
-  uint32_t best[8];
+  blend_argmax_store<K>(acc, wsum, mask, y, x0, W);
+}
+
+// Strips with at most TWO covering tiles per axis (overlap < step), three warp-uniform roles in one launch (round 2, later):
+// in the kernel above a warp of the horizontal strips spans a whole tile width, so every warp contains a corner group and ran
+// the four-tile loop for all its lanes (ncu: 820 instructions per warp, issue slots 59 % busy, 2.5 TB/s).  Here
+//   blocks [0, nH)        horizontal strips outside the vertical ones: tiles (ty, tx), (ty + 1, tx)        - 2-D block grid
+//   blocks [nH, nH + nV)  vertical strips outside the horizontal ones: tiles (ty, tx), (ty, tx + 1)       - linear index
+//   the rest              corners: four tiles in (ty, tx) order, two at a time                             - linear index
+// Same tile order and arithmetic as the general kernel: identical bits.
+template <int K>
+__global__ void __launch_bounds__(256, 3)
+stitch_strips3_kernel(const __nv_bfloat16* __restrict__ logits, int T, int step, FastDiv fd, int gy, int gx, int ty_base,
+                      const float* __restrict__ win, uint8_t* __restrict__ mask, int H, int W, int row0, int nrows,
+                      int nH, int nV, int bx0, int first_strip, int nstrip_rows, int cb_shift, int groups, FastDiv gd) {
+  const int ov = T - step, ov8 = ov >> 3;
+  int y, x0, ty0, tx0, role;
+  if (static_cast<int>(blockIdx.x) < nH) {
+    role = 0;
+    const int by = blockIdx.x / bx0, bx = blockIdx.x - by * bx0;
+    const int r = by * (256 >> cb_shift) + (threadIdx.x >> cb_shift);
+    const int c = (bx << cb_shift) + (threadIdx.x & ((1 << cb_shift) - 1));
+    if (r >= nstrip_rows) return;
+    const int sq = r / ov;
+    ty0 = first_strip + sq - 1;
+    y = (ty0 + 1) * step + (r - sq * ov);                   // tile row ty0 + 1 overlaps tile row ty0 here
+    if (y < row0 || y >= row0 + nrows) return;
+    x0 = c << 3;
+    if (x0 >= W) return;
+    tx0 = (x0 - T + 1 <= 0) ? 0 : fd.div(x0 - T + step);
+    if (tx0 != min(gx - 1, fd.div(x0))) return;             // a corner: third role
+  } else {
+    role = static_cast<int>(blockIdx.x) < nH + nV ? 1 : 2;
+    const int idx = (blockIdx.x - (role == 1 ? nH : nH + nV)) * 256 + threadIdx.x;
+    const int r = gd.div(idx);
+    const int c = idx - r * groups;
+    const int strip = c / ov8;
+    x0 = (strip + 1) * step + ((c - strip * ov8) << 3);
+    tx0 = strip;
+    if (x0 >= W) return;
+    if (role == 1) {
+      if (r >= nrows) return;
+      y = row0 + r;
+      ty0 = (y - T + 1 <= 0) ? 0 : fd.div(y - T + step);
+      if (ty0 != min(gy - 1, fd.div(y))) return;            // a row of a horizontal strip: roles 0 / 2
+    } else {
+      if (r >= nstrip_rows) return;
+      const int sq = r / ov;
+      ty0 = first_strip + sq - 1;
+      y = (ty0 + 1) * step + (r - sq * ov);
+      if (y < row0 || y >= row0 + nrows) return;
+    }
+  }
+  float acc[8][K], wsum[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    int b = 0;
-    float bv = acc[j][0];
+    wsum[j] = 0.f;
 #pragma unroll
-    for (int k = 1; k < K; ++k)
-      if (acc[j][k] > bv) { bv = acc[j][k]; b = k; }
-    bool near = false;
-#pragma unroll
-    for (int k = 0; k < K - 1; ++k)
-      near = near || (k < b && bv - acc[j][k] <= 4.76837158e-7f * fmaxf(fabsf(bv), fabsf(acc[j][k])));
-    if (near) {        // an earlier class can tie with the maximum after the division: first maximum wins
-      const float qb = __fdiv_rn(bv, wsum[j]);
-      int nb = b;
-#pragma unroll
-      for (int k = K - 2; k >= 0; --k)       // static indices: acc stays in registers
-        if (k < b && __fdiv_rn(acc[j][k], wsum[j]) == qb) nb = k;
-      b = nb;
-    }
-    best[j] = static_cast<uint32_t>(b);
+    for (int k = 0; k < K; ++k) acc[j][k] = 0.f;
   }
-  store_mask8(mask, y, x0, W, best);
+  auto tile_ptr = [&](int ty, int tx) {
+    return logits + ((static_cast<int64_t>(ty - ty_base) * gx + tx) * T * T + static_cast<int64_t>(y - ty * step) * T +
+                     (x0 - tx * step)) * K;
+  };
+  // second tile of the first pair: the lower tile (role 0) or the right-hand tile (roles 1, 2)
+  const int ty_b = role == 0 ? ty0 + 1 : ty0, tx_b = role == 0 ? tx0 : tx0 + 1;
+  {
+    uint4 raw0[K], raw1[K];
+    load_raw<K>(tile_ptr(ty0, tx0), raw0);
+    load_raw<K>(tile_ptr(ty_b, tx_b), raw1);
+    blend_accumulate<K>(raw0, __ldg(win + y - ty0 * step), win + x0 - tx0 * step, acc, wsum);
+    blend_accumulate<K>(raw1, __ldg(win + y - ty_b * step), win + x0 - tx_b * step, acc, wsum);
+  }
+  if (role == 2) {
+    uint4 raw0[K], raw1[K];
+    load_raw<K>(tile_ptr(ty0 + 1, tx0), raw0);
+    load_raw<K>(tile_ptr(ty0 + 1, tx0 + 1), raw1);
+    const float wy = __ldg(win + y - (ty0 + 1) * step);
+    blend_accumulate<K>(raw0, wy, win + x0 - tx0 * step, acc, wsum);
+    blend_accumulate<K>(raw1, wy, win + x0 - (tx0 + 1) * step, acc, wsum);
+  }
+  blend_argmax_store<K>(acc, wsum, mask, y, x0, W);
 }
 
 // smallest waste of ceil(n / cb) * cb over cb in {32, 64, 128, 256}; ties go to the wider block row
@@ -702,6 +790,13 @@ void launch_stitch_two_pass(const __nv_bfloat16* lg, int T, int step, int gy, in
   FastDiv gd;
   gd.d = groups > 0 ? groups : 1;
   gd.magic = static_cast<uint32_t>(((1ull << 32) + gd.d - 1) / gd.d);
+  static const bool general = [] { const char* e = std::getenv("DT_STITCH_GENERAL"); return e && e[0] == '1'; }();
+  if (ov < step && !general) {          // at most two covering tiles per axis: the three-role kernel
+    const int n2 = static_cast<int>((static_cast<int64_t>(srows) * groups + 255) / 256);   // corners
+    stitch_strips3_kernel<K><<<n0 + n1 + n2, 256, 0, s>>>(lg, T, step, fd, gy, gx, ty_base, win, mask, H, W, row0, nrows, n0,
+                                                          n1, bx0, first, srows, sh, gd.d, gd);
+    return;
+  }
   stitch_strips_kernel<K><<<n0 + n1, 256, 0, s>>>(lg, T, step, fd, gy, gx, ty_base, win, mask, H, W, row0, nrows, n0, bx0,
                                                   first, srows, sh, gd.d, gd);
 }
