@@ -32,6 +32,13 @@ def test_header_and_binding_agree(lib):
         assert hasattr(lib, s), f"{s} declared in include/deadtrees_b200.h but not exported"
 
 
+def test_integration_doc_names_every_entry_point():
+    """INTEGRATION.md says, for every exported entry point, which reference code it replaces."""
+    doc = (ROOT / "INTEGRATION.md").read_text()
+    missing = [s for s in declared_symbols() if s not in doc]
+    assert not missing, f"entry points without a row in INTEGRATION.md: {missing}"
+
+
 def test_version(lib):
     assert lib.dt_version() == 100
 
