@@ -46,10 +46,12 @@ def parse():
     ap.add_argument("--size", type=int, default=10000, help="mosaic side in pixels")
     ap.add_argument("--tile", type=int, default=256)
     ap.add_argument("--overlap", type=int, default=32)
-    ap.add_argument("--batch-tiles", type=int, default=405,
-                    help="tiles per Unet launch sequence: 405 = 9 tile rows of the cfg2 grid (5 equal batches); measured on "
-                         "B200: 135 -> 44.4 ms, 270 -> 42.9, 405 -> 41.0, 675 -> 41.3, 2025 -> 41.1 ms per mosaic, end to "
-                         "end best at 405 (enough batches left to hide the host copies)")
+    ap.add_argument("--batch-tiles", type=int, default=1013,
+                    help="upper bound of the tiles per Unet launch sequence (the batches of a mosaic are equal): 1013 = two "
+                         "batches of the cfg2 grid.  Measured on B200 with the final round-2 kernels, ms per mosaic device-"
+                         "resident / end to end pipelined / end to end as closed jobs: 338 -> 34.0 / 34.4 / -, 405 -> 33.0-33.3 / "
+                         "33.3-33.8 / 35.9, 675 -> 32.7-33.2 / 33.2-33.8 / 35.5, 1013 -> 31.7-32.6 / 32.2-32.9 / 35.5-36.1, 2025 -> "
+                         "32.1-32.5 / 32.9-33.2 / 37.7-38.4 (boxes differ by their power cap; round 1 kernels: 405 was best)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-sample-tiles", type=int, default=36)
     ap.add_argument("--no-cpu-baseline", action="store_true")
