@@ -762,7 +762,8 @@ def cfg5_measure(a, ctx, engine, steps: int, warmup: int):
     rank, world, local, dev = ctx
     T, gy, gx = 1024, 4, 8
     n = gy * gx
-    mi = MosaicInference(engine, tile=T, overlap=0, batch_tiles=16)
+    bt5 = int(os.environ.get("DT_CFG5_BATCH", "32"))      # one batch per block (16: 8.6-8.7 ms, 32: 8.3-8.4 ms per 32 tiles)
+    mi = MosaicInference(engine, tile=T, overlap=0, batch_tiles=bt5)
     g = torch.Generator(device=dev).manual_seed(77 + rank)
     block = torch.randint(0, 256, (gy * T, gx * T, 3), dtype=torch.uint8, device=dev, generator=g)
     host_block = torch.empty(block.shape, dtype=torch.uint8, pin_memory=True)
@@ -817,7 +818,7 @@ def cfg5_measure(a, ctx, engine, steps: int, warmup: int):
            "mpixel_per_s": world * n * T * T / 1e6 / (ms / 1e3), "n_gpus": world, "steps": steps, "warmup": max(warmup, 3),
            "ms_per_step": ms, "scaling": "weak", "dtype": "bf16", "gpu_launches": int(launches), "clocks": clocks,
            "config": {"workload": "cfg5: Unet-resnet34 inference on 32 RGB uint8 tiles of 1024x1024 per GPU (4096x8192 block, "
-                                  "overlap 0), batches of 16 tiles", "tile": T, "tiles_per_gpu": n, "batch_tiles": 16,
+                                  f"overlap 0), batches of {bt5} tiles", "tile": T, "tiles_per_gpu": n, "batch_tiles": bt5,
                       "l2_policy": "100 MB block and > 8 GB of activations per step; no explicit flush"},
            "e2e": {"value": world * n / (ms_e2e / 1e3), "unit": "tiles/s", "ms_per_step": ms_e2e,
                    "h2d_bytes_per_step": int(block.numel()), "d2h_bytes_per_step": int(mask.numel()),
