@@ -233,6 +233,10 @@ class MosaicInference:
         if (piped_in or host_out is not None) and layout != "hwc":
             raise ValueError("the host pipeline takes interleaved (H, W, C) mosaics")
         main = torch.cuda.current_stream()
+        if not pipelined and getattr(self, "_out_done", None) is not None:
+            # a closed job after pipelined ones without finish(): their last downloads still read `mask`
+            main.wait_event(self._out_done)
+            self._out_done = self._gather_done = None
         if piped_in or piped_out:
             if getattr(self, "_copy_streams", None) is None:
                 self._copy_streams = (torch.cuda.Stream(device=eng.device), torch.cuda.Stream(device=eng.device))

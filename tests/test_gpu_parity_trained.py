@@ -144,6 +144,11 @@ def test_pipelined_mosaics_equal_closed_jobs(ov):
         for k, out in enumerate(outs):
             assert np.array_equal(out.numpy(), want[k]), f"round {rep}, mosaic {k}"
             out.zero_()
+    # a closed job right behind a pipelined one, without finish(): it waits for the pipelined call's downloads itself
+    mi.run(dev, "hwc", out=dev_mask, host_src=srcs[0], host_out=outs[0], pipelined=True)
+    mi.run(dev, "hwc", out=dev_mask, host_src=srcs[1], host_out=outs[1])
+    torch.cuda.current_stream().synchronize()
+    assert np.array_equal(outs[0].numpy(), want[0]) and np.array_equal(outs[1].numpy(), want[1])
 
 
 def test_pytorch_inference_api_bf16(tmp_path):
